@@ -1,0 +1,174 @@
+/*
+ * lutgen_cuda.h -- C ABI of the B200 (sm_100a) implementation of lutgen's
+ * Hald-CLUT generation / application hot path.
+ *
+ * This is the drop-in boundary: exactly the entry points a Rust `lutgen` crate
+ * (crates/lib of ozwaldorf/lutgen-rs 0.15.0) would bind over FFI to move its hot
+ * path to the GPU while keeping its public API. Each export cites the reference
+ * interface it replaces (paths relative to the reference root). INTEGRATION.md
+ * shows the Rust-side binding; include/lutgen.hpp is the C++ host mirror of the
+ * crate API built on these symbols; lutgen_rs_b200/ is the Python (ctypes) one.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only. Pointers are HOST memory unless the
+ *    function name ends in `_dev` (then: device memory of the current device).
+ *  - Images are tightly packed, row-major, x fastest: RGB8 = 3 B/px (Hald CLUTs,
+ *    `image::RgbImage`), RGBA8 = 4 B/px (`image::RgbaImage`). A level-L CLUT is
+ *    L^3 x L^3 pixels = 3*L^6 bytes.
+ *  - Return value: LUTGEN_OK (0), LUTGEN_ABORTED (1, the caller's abort flag was
+ *    seen set -- the reference returns `None`), or a negative LUTGEN_ERR_*. The
+ *    library never aborts the process where the reference panics; the message
+ *    is available from lutgen_cuda_last_error() (thread local).
+ *  - One process drives one GPU (select it with lutgen_cuda_init). Multi-GPU
+ *    jobs run one process per GPU and shard rows / frames through the `_dev`
+ *    entry points; the collective (NCCL all-gather) lives in the host layer.
+ *  - There is no CPU fallback: without a usable sm_100 device every compute
+ *    entry point returns LUTGEN_ERR_NO_DEVICE / LUTGEN_ERR_CUDA.
+ *  - `stream` arguments are `cudaStream_t` passed as void* (NULL = the
+ *    library's own stream; `_dev` calls with a caller stream do not synchronise).
+ */
+#ifndef LUTGEN_CUDA_H
+#define LUTGEN_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define LUTGEN_API
+#else
+#define LUTGEN_API __attribute__((visibility("default")))
+#endif
+
+/* ---- status codes ------------------------------------------------------- */
+#define LUTGEN_OK 0
+#define LUTGEN_ABORTED 1
+#define LUTGEN_ERR_INVALID (-1)   /* bad argument (where the reference panics) */
+#define LUTGEN_ERR_CUDA (-2)      /* CUDA runtime failure */
+#define LUTGEN_ERR_NO_DEVICE (-3) /* no sm_100 device / library not initialised */
+#define LUTGEN_ERR_UNSUPPORTED (-4)
+
+/* ---- remapper kinds (crates/lib/src/interpolation/mod.rs:6-13) ----------- */
+#define LUTGEN_GAUSSIAN 0 /* GaussianRemapper   rbf.rs:171-180  w = exp(-shape*d)      */
+#define LUTGEN_SHEPARD 1  /* ShepardRemapper    rbf.rs:161-169  w = 1/sqrt(d)^power    */
+#define LUTGEN_LINEAR 2   /* LinearRemapper     rbf.rs:153-159  w = d                  */
+#define LUTGEN_NEAREST 3  /* NearestNeighborRemapper  nearest_neighbor.rs:11-61        */
+#define LUTGEN_SAMPLING 4 /* GaussianSamplingRemapper gaussian_sample.rs:18-76         */
+
+/* Constructor arguments of every remapper, flattened.
+ *   Gaussian/Shepard/Linear::new(palette, [shape|power], nearest, lum_factor, preserve_lum)  rbf.rs:126-140
+ *   NearestNeighborRemapper::new(palette, lum_factor, preserve)                              nearest_neighbor.rs:19
+ *   GaussianSamplingRemapper::new(palette, mean, std_dev, iterations, lum_factor, seed, preserve)  gaussian_sample.rs:27-35
+ * Unused fields are ignored. The palette is copied (callers may free it). */
+typedef struct lutgen_remapper_desc {
+    int32_t kind;           /* LUTGEN_GAUSSIAN .. LUTGEN_SAMPLING */
+    int32_t preserve;       /* preserve_lum / preserve (bool) */
+    const uint8_t* palette; /* palette_len x [u8; 3] sRGB */
+    uint64_t palette_len;
+    double param;           /* Gaussian shape / Shepard power */
+    uint64_t nearest;       /* 0 or >= palette_len: use every colour (rbf.rs:38) */
+    double lum_factor;
+    double mean, std_dev;   /* sampling */
+    uint64_t iterations;    /* sampling */
+    uint64_t seed;          /* sampling */
+} lutgen_remapper_desc;
+
+typedef struct lutgen_remapper lutgen_remapper; /* opaque; owns device copies */
+
+/* ---- library ------------------------------------------------------------ */
+
+/* Bind this process to CUDA device `device` (-1: $LUTGEN_CUDA_DEVICE, else
+ * $LOCAL_RANK, else 0), create the stream, upload the constant tables.
+ * Idempotent for the same device. Fails with LUTGEN_ERR_NO_DEVICE when there is
+ * no device of compute capability 10.x. */
+LUTGEN_API int lutgen_cuda_init(int device);
+LUTGEN_API int lutgen_cuda_shutdown(void);
+LUTGEN_API int lutgen_cuda_device_count(int* count);
+LUTGEN_API const char* lutgen_cuda_last_error(void);
+LUTGEN_API const char* lutgen_cuda_version(void);
+/* Number of kernels this library has launched so far in this process. */
+LUTGEN_API uint64_t lutgen_cuda_launch_count(void);
+
+/* Pinned host buffers: host pointers handed to the non-_dev entry points are
+ * copied by DMA directly when they come from here (or are otherwise
+ * page-locked); pageable memory is staged through an internal pinned ring. */
+LUTGEN_API int lutgen_cuda_host_alloc(size_t bytes, void** out);
+LUTGEN_API int lutgen_cuda_host_free(void* p);
+
+/* ---- identity.rs ---------------------------------------------------------- */
+
+/* identity::generate(level) -> RgbImage            crates/lib/src/identity.rs:7-34
+ * level in 2..=16 (the reference divides by zero below 2). out: 3*level^6 B. */
+LUTGEN_API int lutgen_cuda_identity(uint8_t level, uint8_t* out_rgb);
+LUTGEN_API int lutgen_cuda_identity_dev(uint8_t level, uint8_t* out_rgb_dev, void* stream);
+
+/* identity::detect_level(&RgbImage) -> u8           identity.rs:85-99
+ * LUTGEN_ERR_INVALID where the reference's assert_eq! panics. */
+LUTGEN_API int lutgen_cuda_detect_level(uint32_t width, uint32_t height, uint8_t* level);
+
+/* identity::correct_image_with_level(&mut RgbaImage, &RgbImage, level)   identity.rs:71-78
+ * (= correct_pixel, identity.rs:40-52, per pixel). In place, alpha untouched,
+ * no interpolation. npix may be 0. */
+LUTGEN_API int lutgen_cuda_apply_hald(uint8_t* rgba, size_t npix, const uint8_t* lut_rgb, uint8_t level);
+LUTGEN_API int lutgen_cuda_apply_hald_dev(uint8_t* rgba_dev, size_t npix, const uint8_t* lut_rgb_dev, uint8_t level,
+                                          void* stream);
+/* The CLI's frame loops (crates/cli/src/main.rs:852-886): one LUT, many images.
+ * frames[i] has npix[i] RGBA8 pixels; uploads, kernels and downloads of
+ * successive frames overlap on the copy engines. */
+LUTGEN_API int lutgen_cuda_apply_hald_batch(uint8_t* const* frames, const size_t* npix, size_t nframes,
+                                            const uint8_t* lut_rgb, uint8_t level);
+
+/* identity::correct_pixel for n independent colours (identity.rs:40-52; the CLI's
+ * `patch` calls it per colour, crates/cli/src/main.rs:1028-1042). in/out: n x [u8;3]. */
+LUTGEN_API int lutgen_cuda_correct_pixels(const uint8_t* in_rgb, size_t n, const uint8_t* lut_rgb, uint8_t level,
+                                          uint8_t* out_rgb);
+
+/* ---- remappers ------------------------------------------------------------ */
+
+LUTGEN_API int lutgen_cuda_remapper_create(const lutgen_remapper_desc* desc, lutgen_remapper** out);
+LUTGEN_API int lutgen_cuda_remapper_destroy(lutgen_remapper* r);
+
+/* GenerateLut::{generate_lut, par_generate_lut, *_with_interrupt}   crates/lib/src/lib.rs:113-171
+ * identity -> Rgb->Rgba -> remap_image -> Rgba->Rgb fused into one pass; no
+ * intermediate images. abort_flag may be NULL; when it reads non-zero before,
+ * between or after the launches the call returns LUTGEN_ABORTED and out_rgb is
+ * unspecified (the reference returns None, lib.rs:149-170). */
+LUTGEN_API int lutgen_cuda_generate_lut(const lutgen_remapper* r, uint8_t level, uint8_t* out_rgb,
+                                        const volatile uint8_t* abort_flag);
+/* Row shard of the same: rows [row_begin, row_end) of the level^3 x level^3 CLUT
+ * are written at their place inside the full-size device image lut_rgb_dev
+ * (3*level^6 B). This is the unit the multi-GPU path all-gathers. */
+LUTGEN_API int lutgen_cuda_generate_lut_rows_dev(const lutgen_remapper* r, uint8_t level, uint8_t* lut_rgb_dev,
+                                                 uint32_t row_begin, uint32_t row_end, void* stream);
+
+/* InterpolatedRemapper::{remap_image, par_remap_image, *_with_interrupt}
+ * crates/lib/src/interpolation/mod.rs:23-61. RGBA8 in place, alpha untouched.
+ * npix == 1 is InterpolatedRemapper::remap_pixel (mod.rs:25). */
+LUTGEN_API int lutgen_cuda_remap_image(const lutgen_remapper* r, uint8_t* rgba, size_t npix,
+                                       const volatile uint8_t* abort_flag);
+LUTGEN_API int lutgen_cuda_remap_image_dev(const lutgen_remapper* r, uint8_t* rgba_dev, size_t npix, void* stream);
+
+/* GaussianSamplingRemapper noise table: iterations x 4 f64 normals (r, g, b,
+ * alpha order, gaussian_sample.rs:55-58), shared by every pixel because the
+ * reference re-seeds its RNG per pixel (gaussian_sample.rs:52). `get` returns
+ * the table the library drew with its own counter-based generator
+ * (Philox4x32-10 + Box-Muller; the stream differs from rand's ChaCha12 +
+ * ziggurat by design); `set` replaces it (test hook: lets a CPU oracle consume
+ * the identical normals so results compare byte for byte). */
+LUTGEN_API int lutgen_cuda_sampling_get_noise(const lutgen_remapper* r, double* noise_out);
+LUTGEN_API int lutgen_cuda_sampling_set_noise(lutgen_remapper* r, const double* noise);
+
+/* ---- oklab (third-party arithmetic on the path; oklab 1.1.2) --------------- */
+
+/* oklab::srgb_to_oklab for n colours: in n x [u8;3], out n x [f32;3] (l, a, b). */
+LUTGEN_API int lutgen_cuda_srgb_to_oklab(const uint8_t* rgb, size_t n, float* out_lab);
+/* oklab::oklab_to_srgb for n colours: in n x [f32;3], out n x [u8;3]. */
+LUTGEN_API int lutgen_cuda_oklab_to_srgb(const float* lab, size_t n, uint8_t* out_rgb);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUTGEN_CUDA_H */

@@ -1,0 +1,778 @@
+// api.cu -- the extern "C" boundary declared in include/lutgen_cuda.h.
+//
+// Host-side plumbing only: argument validation (returning status codes where
+// the reference panics), device buffers, streams, host<->device copies and
+// kernel dispatch. All arithmetic lives in the kernels_*.cuh headers.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/lutgen_cuda.h"
+#include "kernels_apply.cuh"
+#include "kernels_exact.cuh"
+
+using namespace lutgen;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                       \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess)                                                                             \
+            return fail(LUTGEN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                                     \
+    do {                                                                                                   \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                                \
+        cudaError_t _e = cudaGetLastError();                                                               \
+        if (_e != cudaSuccess)                                                                             \
+            return fail(LUTGEN_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// Grow-only device buffer.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+constexpr int kBatchStreams = 3;
+
+struct Ctx {
+    std::mutex mu;
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t batch_streams[kBatchStreams] = {nullptr, nullptr, nullptr};
+    ColorTables* tables = nullptr;  // device
+    DevBuf lut_rgb;                 // RGB8 CLUT (host-API scratch)
+    DevBuf lut_rgbx;                // expanded CLUT for apply
+    DevBuf frame;                   // RGBA8 image scratch
+    DevBuf batch_frames[kBatchStreams];
+    DevBuf misc;
+} g;
+
+int ensure_ready() {
+    if (!g.ready) return fail(LUTGEN_ERR_NO_DEVICE, "lutgen_cuda_init has not succeeded in this process (no CPU fallback exists)");
+    cudaError_t e = cudaSetDevice(g.device);
+    if (e != cudaSuccess) return fail(LUTGEN_ERR_CUDA, "cudaSetDevice(%d): %s", g.device, cudaGetErrorString(e));
+    return LUTGEN_OK;
+}
+
+inline bool level_ok(uint8_t level) { return level >= 2 && level <= 33; }
+inline size_t lut_entries(uint8_t level) {
+    size_t l = level;
+    return l * l * l * l * l * l;
+}
+inline unsigned blocks_for(unsigned long long n, unsigned per_block) { return (unsigned)((n + per_block - 1) / per_block); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// remapper object
+// ---------------------------------------------------------------------------
+struct lutgen_remapper {
+    lutgen_remapper_desc d;
+    uint32_t n = 0;
+    uint32_t k_eff = 0;              // 0: every colour
+    std::vector<uint8_t> pal_host;   // n x 3
+    uint8_t* pal_rgb4 = nullptr;     // device n x 4
+    double* pal_lab = nullptr;       // device n x 3
+    float* pal_ab = nullptr;         // device n x 2
+    float4* pal_lab32 = nullptr;     // device n x float4 (l*lum, a, b, 0)
+    // sampling
+    std::vector<double> noise;       // iterations x 4 (host)
+    short4* offsets = nullptr;       // device, iteration order
+    mutable uint32_t* nn_table = nullptr;  // device 2^24 x u32, built lazily
+    mutable bool nn_table_ready = false;
+    mutable std::mutex mu;
+    // fast-path work list (flagged entries), device
+    mutable uint32_t* flag_list = nullptr;
+    mutable uint32_t* flag_count = nullptr;
+    mutable size_t flag_cap = 0;
+    bool fast_ok = false;
+};
+
+namespace {
+
+RemapParams params_of(const lutgen_remapper* r) {
+    RemapParams P;
+    P.pal_lab = r->pal_lab;
+    P.pal_ab = r->pal_ab;
+    P.pal_rgb = r->pal_rgb4;
+    P.n = r->n;
+    P.nearest = r->k_eff;
+    P.preserve = r->d.preserve;
+    P.lum = r->d.lum_factor;
+    P.param = r->d.param;
+    return P;
+}
+
+inline uint8_t f64_as_u8(double v) {  // Rust `as u8`: saturating, NaN -> 0
+    if (!(v > 0.0)) return 0;
+    if (v >= 255.0) return 255;
+    return (uint8_t)v;
+}
+
+// Noise table -> integer channel offsets such that, for every c in 0..=255,
+// sat_u8(round(c + noise)) == clamp(c + o, 0, 255)   (gaussian_sample.rs:57).
+int derive_offsets(const lutgen_remapper* r, std::vector<short>& out) {
+    size_t K = (size_t)r->d.iterations;
+    out.assign(4 * K, 0);
+    for (size_t k = 0; k < K; ++k) {
+        for (int ch = 0; ch < 3; ++ch) {
+            double nz = r->noise[4 * k + ch];
+            int cand;
+            if (nz != nz) cand = -256;
+            else {
+                double t = std::floor(nz + 0.5);
+                cand = t > 256.0 ? 256 : (t < -256.0 ? -256 : (int)t);
+            }
+            int found = 1000;
+            for (int delta : {0, -1, 1}) {
+                int o = cand + delta;
+                bool ok = true;
+                for (int c = 0; c < 256 && ok; ++c) {
+                    int want = f64_as_u8(std::round((double)c + nz));
+                    int got = c + o;
+                    got = got < 0 ? 0 : (got > 255 ? 255 : got);
+                    ok = (want == got);
+                }
+                if (ok) { found = o; break; }
+            }
+            if (found == 1000)
+                return fail(LUTGEN_ERR_UNSUPPORTED, "noise value %.17g (iteration %zu) is not representable as an integer channel offset", nz, k);
+            out[4 * k + ch] = (short)found;
+        }
+    }
+    return LUTGEN_OK;
+}
+
+int upload_offsets(lutgen_remapper* r) {
+    std::vector<short> off;
+    int rc = derive_offsets(r, off);
+    if (rc != LUTGEN_OK) return rc;
+    size_t K = (size_t)r->d.iterations;
+    if (K == 0) return LUTGEN_OK;
+    CU_TRY(cudaMemcpyAsync(r->offsets, off.data(), sizeof(short) * 4 * K, cudaMemcpyHostToDevice, g.stream));
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    return LUTGEN_OK;
+}
+
+template <int MODE>
+int launch_nn_mode(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
+    if (f.count == 0) return LUTGEN_OK;
+    RemapParams P = params_of(r);
+    k_nn_exact<MODE><<<blocks_for(f.count, 256), 256, 0, s>>>(f, P, g.tables);
+    LAUNCH_CHECK();
+    return LUTGEN_OK;
+}
+
+int launch_nn(const Front& f, const lutgen_remapper* r, int mode, cudaStream_t s) {
+    switch (mode) {
+        case FRONT_LUT: return launch_nn_mode<FRONT_LUT>(f, r, s);
+        case FRONT_IMAGE: return launch_nn_mode<FRONT_IMAGE>(f, r, s);
+        default: return launch_nn_mode<FRONT_TABLE>(f, r, s);
+    }
+}
+
+// NN over the whole sRGB cube, once per sampling remapper (see kernels_apply.cuh).
+int ensure_nn_table(const lutgen_remapper* r, cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(r->mu);
+    if (r->nn_table_ready) return LUTGEN_OK;
+    if (!r->nn_table) CU_TRY(cudaMalloc((void**)&r->nn_table, sizeof(uint32_t) << 24));
+    Front f{};
+    f.out = reinterpret_cast<uint8_t*>(r->nn_table);
+    f.begin = 0;
+    f.count = 1ull << 24;
+    int rc = launch_nn(f, r, FRONT_TABLE, s);
+    if (rc != LUTGEN_OK) return rc;
+    r->nn_table_ready = true;
+    return LUTGEN_OK;
+}
+
+template <int KIND, int MODE>
+int launch_rbf_exact_km(const Front& f, const lutgen_remapper* r, cudaStream_t s, unsigned long long nthreads) {
+    if (nthreads == 0) return LUTGEN_OK;
+    RemapParams P = params_of(r);
+    k_rbf_exact<KIND, MODE><<<blocks_for(nthreads, 256), 256, 0, s>>>(f, P, g.tables);
+    LAUNCH_CHECK();
+    return LUTGEN_OK;
+}
+
+template <int MODE>
+int launch_rbf_exact(const Front& f, const lutgen_remapper* r, cudaStream_t s, unsigned long long nthreads) {
+    switch (r->d.kind) {
+        case LUTGEN_GAUSSIAN: return launch_rbf_exact_km<0, MODE>(f, r, s, nthreads);
+        case LUTGEN_SHEPARD: return launch_rbf_exact_km<1, MODE>(f, r, s, nthreads);
+        default: return launch_rbf_exact_km<2, MODE>(f, r, s, nthreads);
+    }
+}
+
+template <int MODE>
+int launch_sampling(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
+    int rc = ensure_nn_table(r, s);
+    if (rc != LUTGEN_OK) return rc;
+    if (f.count == 0) return LUTGEN_OK;
+    uint64_t K = r->d.iterations;
+    bool pow2 = K != 0 && (K & (K - 1)) == 0 && K <= (1ull << 24);
+    uint32_t log2k = 0;
+    while (pow2 && (1ull << log2k) < K) ++log2k;
+    if (pow2)
+        k_sampling<MODE, false><<<blocks_for(f.count, 256), 256, 0, s>>>(f, r->nn_table, r->offsets, (uint32_t)K, log2k);
+    else
+        k_sampling<MODE, true><<<blocks_for(f.count, 256), 256, 0, s>>>(f, r->nn_table, r->offsets, (uint32_t)K, 0);
+    LAUNCH_CHECK();
+    return LUTGEN_OK;
+}
+
+// Remap `f.count` colours with remapper r on stream s (no synchronisation).
+template <int MODE>
+int launch_remap(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
+    switch (r->d.kind) {
+        case LUTGEN_NEAREST: return launch_nn(f, r, MODE, s);
+        case LUTGEN_SAMPLING: return launch_sampling<MODE>(f, r, s);
+        default: {
+            return launch_rbf_exact<MODE>(f, r, s, f.count);
+        }
+    }
+}
+
+int expand_lut(const uint8_t* lut_rgb_dev, uint8_t level, cudaStream_t s) {
+    size_t E = lut_entries(level);
+    CU_TRY(g.lut_rgbx.reserve(E * 4));
+    k_expand_lut<<<blocks_for(E, 256), 256, 0, s>>>(lut_rgb_dev, E, (uint32_t*)g.lut_rgbx.p);
+    LAUNCH_CHECK();
+    return LUTGEN_OK;
+}
+
+int launch_apply(uint8_t* rgba_dev, size_t npix, const uint32_t* lut_rgbx, uint8_t level, cudaStream_t s) {
+    if (npix == 0) return LUTGEN_OK;
+    if (reinterpret_cast<uintptr_t>(rgba_dev) & 3u) return fail(LUTGEN_ERR_INVALID, "rgba_dev must be 4-byte aligned");
+    uint32_t cs = (uint32_t)level * level;
+    size_t head = ((16 - (reinterpret_cast<uintptr_t>(rgba_dev) & 15u)) & 15u) / 4;
+    if (head > npix) head = npix;
+    size_t nvec = (npix - head) / 4;
+    size_t want = (nvec + 255) / 256;
+    if (want == 0) want = 1;
+    // enough resident work to cover the gather latency, capped so the grid-stride loop amortises launch
+    size_t cap = (size_t)g.sm_count * 64;
+    unsigned grid = (unsigned)(want < cap ? want : cap);
+    k_apply<<<grid, 256, 0, s>>>((uint32_t*)rgba_dev, npix, head, nvec, lut_rgbx, cs, cs - 1);
+    LAUNCH_CHECK();
+    return LUTGEN_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// library
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char* lutgen_cuda_last_error(void) { return g_err.c_str(); }
+const char* lutgen_cuda_version(void) { return "lutgen-b200 0.1.0 (sm_100a)"; }
+uint64_t lutgen_cuda_launch_count(void) { return g_launches.load(); }
+
+int lutgen_cuda_device_count(int* count) {
+    if (!count) return fail(LUTGEN_ERR_INVALID, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(LUTGEN_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_init(int device) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (device < 0) {
+        const char* e = getenv("LUTGEN_CUDA_DEVICE");
+        if (!e) e = getenv("LOCAL_RANK");
+        device = e ? atoi(e) : 0;
+    }
+    if (g.ready) {
+        if (g.device == device) return LUTGEN_OK;
+        return fail(LUTGEN_ERR_INVALID, "already initialised on device %d (one process drives one GPU)", g.device);
+    }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(LUTGEN_ERR_NO_DEVICE, "no CUDA device: %s", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device >= n) return fail(LUTGEN_ERR_NO_DEVICE, "device %d requested but only %d visible", device, n);
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(LUTGEN_ERR_NO_DEVICE, "device %d (%s) is sm_%d%d; this library carries sm_100a code only", device, prop.name, prop.major,
+                    prop.minor);
+    CU_TRY(cudaSetDevice(device));
+    g.device = device;
+    g.sm_count = prop.multiProcessorCount;
+    CU_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < kBatchStreams; ++i) CU_TRY(cudaStreamCreateWithFlags(&g.batch_streams[i], cudaStreamNonBlocking));
+    ColorTables host;
+    for (int i = 0; i < 256; ++i) memcpy(&host.decode[i], &k_srgb_decode_bits[i], 4);
+    for (int i = 0; i < 104; ++i) host.encode[i] = k_srgb_encode_table[i];
+    CU_TRY(cudaMalloc((void**)&g.tables, sizeof(ColorTables)));
+    CU_TRY(cudaMemcpy(g.tables, &host, sizeof host, cudaMemcpyHostToDevice));
+    g.ready = true;
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!g.ready) return LUTGEN_OK;
+    cudaSetDevice(g.device);
+    cudaDeviceSynchronize();
+    g.lut_rgb.release();
+    g.lut_rgbx.release();
+    g.frame.release();
+    g.misc.release();
+    for (int i = 0; i < kBatchStreams; ++i) {
+        g.batch_frames[i].release();
+        if (g.batch_streams[i]) cudaStreamDestroy(g.batch_streams[i]);
+        g.batch_streams[i] = nullptr;
+    }
+    if (g.tables) cudaFree(g.tables);
+    g.tables = nullptr;
+    if (g.stream) cudaStreamDestroy(g.stream);
+    g.stream = nullptr;
+    g.ready = false;
+    g.device = -1;
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(LUTGEN_ERR_INVALID, "out is NULL");
+    int rc = ensure_ready();
+    if (rc) return rc;
+    CU_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return LUTGEN_OK;
+}
+int lutgen_cuda_host_free(void* p) {
+    if (!p) return LUTGEN_OK;
+    int rc = ensure_ready();
+    if (rc) return rc;
+    CU_TRY(cudaFreeHost(p));
+    return LUTGEN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// identity.rs
+// ---------------------------------------------------------------------------
+int lutgen_cuda_detect_level(uint32_t width, uint32_t height, uint8_t* level) {
+    if (!level) return fail(LUTGEN_ERR_INVALID, "level is NULL");
+    uint64_t l = 2;
+    while (l * l * l < width) ++l;
+    if (width != l * l * l) return fail(LUTGEN_ERR_INVALID, "hald clut width %u is not a cube (assert_eq!(width, level^3), identity.rs:95)", width);
+    if (width != height) return fail(LUTGEN_ERR_INVALID, "hald clut is not square: %u x %u (identity.rs:96)", width, height);
+    *level = (uint8_t)l;
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_identity_dev(uint8_t level, uint8_t* out_rgb_dev, void* stream) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33 (the reference divides by zero / overflows)", level);
+    if (!out_rgb_dev) return fail(LUTGEN_ERR_INVALID, "out_rgb_dev is NULL");
+    cudaStream_t s = stream ? (cudaStream_t)stream : g.stream;
+    size_t E = lut_entries(level);
+    uint32_t cs = (uint32_t)level * level;
+    k_identity<<<blocks_for((E + 3) / 4, 256), 256, 0, s>>>(out_rgb_dev, 0, E, cs, cs - 1);
+    LAUNCH_CHECK();
+    if (!stream) CU_TRY(cudaStreamSynchronize(s));
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_identity(uint8_t level, uint8_t* out_rgb) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33 (the reference divides by zero / overflows)", level);
+    if (!out_rgb) return fail(LUTGEN_ERR_INVALID, "out_rgb is NULL");
+    std::lock_guard<std::mutex> lk(g.mu);
+    size_t bytes = 3 * lut_entries(level);
+    CU_TRY(g.lut_rgb.reserve(bytes));
+    rc = lutgen_cuda_identity_dev(level, (uint8_t*)g.lut_rgb.p, g.stream);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(out_rgb, g.lut_rgb.p, bytes, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_apply_hald_dev(uint8_t* rgba_dev, size_t npix, const uint8_t* lut_rgb_dev, uint8_t level, void* stream) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33", level);
+    if (!lut_rgb_dev || (!rgba_dev && npix)) return fail(LUTGEN_ERR_INVALID, "NULL buffer");
+    cudaStream_t s = stream ? (cudaStream_t)stream : g.stream;
+    if (npix) {
+        rc = expand_lut(lut_rgb_dev, level, s);
+        if (rc) return rc;
+        rc = launch_apply(rgba_dev, npix, (const uint32_t*)g.lut_rgbx.p, level, s);
+        if (rc) return rc;
+    }
+    if (!stream) CU_TRY(cudaStreamSynchronize(s));
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_apply_hald(uint8_t* rgba, size_t npix, const uint8_t* lut_rgb, uint8_t level) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33", level);
+    if (!lut_rgb || (!rgba && npix)) return fail(LUTGEN_ERR_INVALID, "NULL buffer");
+    if (npix == 0) return LUTGEN_OK;
+    std::lock_guard<std::mutex> lk(g.mu);
+    size_t lut_bytes = 3 * lut_entries(level);
+    CU_TRY(g.lut_rgb.reserve(lut_bytes));
+    CU_TRY(g.frame.reserve(npix * 4));
+    CU_TRY(cudaMemcpyAsync(g.lut_rgb.p, lut_rgb, lut_bytes, cudaMemcpyHostToDevice, g.stream));
+    CU_TRY(cudaMemcpyAsync(g.frame.p, rgba, npix * 4, cudaMemcpyHostToDevice, g.stream));
+    rc = lutgen_cuda_apply_hald_dev((uint8_t*)g.frame.p, npix, (const uint8_t*)g.lut_rgb.p, level, g.stream);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(rgba, g.frame.p, npix * 4, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_apply_hald_batch(uint8_t* const* frames, const size_t* npix, size_t nframes, const uint8_t* lut_rgb, uint8_t level) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33", level);
+    if (!lut_rgb || (nframes && (!frames || !npix))) return fail(LUTGEN_ERR_INVALID, "NULL buffer");
+    if (nframes == 0) return LUTGEN_OK;
+    std::lock_guard<std::mutex> lk(g.mu);
+    size_t lut_bytes = 3 * lut_entries(level), max_px = 0;
+    for (size_t i = 0; i < nframes; ++i) {
+        if (npix[i] && !frames[i]) return fail(LUTGEN_ERR_INVALID, "frame %zu is NULL", i);
+        if (npix[i] > max_px) max_px = npix[i];
+    }
+    if (max_px == 0) return LUTGEN_OK;
+    CU_TRY(g.lut_rgb.reserve(lut_bytes));
+    CU_TRY(cudaMemcpyAsync(g.lut_rgb.p, lut_rgb, lut_bytes, cudaMemcpyHostToDevice, g.stream));
+    rc = expand_lut((const uint8_t*)g.lut_rgb.p, level, g.stream);
+    if (rc) return rc;
+    cudaEvent_t lut_ready;
+    CU_TRY(cudaEventCreateWithFlags(&lut_ready, cudaEventDisableTiming));
+    CU_TRY(cudaEventRecord(lut_ready, g.stream));
+    for (int i = 0; i < kBatchStreams; ++i) {
+        CU_TRY(g.batch_frames[i].reserve(max_px * 4));
+        CU_TRY(cudaStreamWaitEvent(g.batch_streams[i], lut_ready, 0));
+    }
+    // Frame i rides stream i % 3: its upload overlaps frame i-1's kernel and
+    // frame i-2's download (separate copy engines per direction).
+    for (size_t i = 0; i < nframes; ++i) {
+        if (!npix[i]) continue;
+        int b = (int)(i % kBatchStreams);
+        cudaStream_t s = g.batch_streams[b];
+        uint8_t* dev = (uint8_t*)g.batch_frames[b].p;
+        CU_TRY(cudaMemcpyAsync(dev, frames[i], npix[i] * 4, cudaMemcpyHostToDevice, s));
+        rc = launch_apply(dev, npix[i], (const uint32_t*)g.lut_rgbx.p, level, s);
+        if (rc) return rc;
+        CU_TRY(cudaMemcpyAsync(frames[i], dev, npix[i] * 4, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < kBatchStreams; ++i) CU_TRY(cudaStreamSynchronize(g.batch_streams[i]));
+    cudaEventDestroy(lut_ready);
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_correct_pixels(const uint8_t* in_rgb, size_t n, const uint8_t* lut_rgb, uint8_t level, uint8_t* out_rgb) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33", level);
+    if (!lut_rgb || (n && (!in_rgb || !out_rgb))) return fail(LUTGEN_ERR_INVALID, "NULL buffer");
+    if (n == 0) return LUTGEN_OK;
+    std::lock_guard<std::mutex> lk(g.mu);
+    size_t lut_bytes = 3 * lut_entries(level);
+    uint32_t cs = (uint32_t)level * level;
+    CU_TRY(g.lut_rgb.reserve(lut_bytes));
+    CU_TRY(g.misc.reserve(6 * n));
+    uint8_t* din = (uint8_t*)g.misc.p;
+    uint8_t* dout = din + 3 * n;
+    CU_TRY(cudaMemcpyAsync(g.lut_rgb.p, lut_rgb, lut_bytes, cudaMemcpyHostToDevice, g.stream));
+    CU_TRY(cudaMemcpyAsync(din, in_rgb, 3 * n, cudaMemcpyHostToDevice, g.stream));
+    rc = expand_lut((const uint8_t*)g.lut_rgb.p, level, g.stream);
+    if (rc) return rc;
+    k_correct_pixels<<<blocks_for(n, 256), 256, 0, g.stream>>>(din, n, (const uint32_t*)g.lut_rgbx.p, cs, cs - 1, dout);
+    LAUNCH_CHECK();
+    CU_TRY(cudaMemcpyAsync(out_rgb, dout, 3 * n, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    return LUTGEN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// remappers
+// ---------------------------------------------------------------------------
+int lutgen_cuda_remapper_destroy(lutgen_remapper* r) {
+    if (!r) return LUTGEN_OK;
+    if (g.ready) {
+        cudaSetDevice(g.device);
+        cudaDeviceSynchronize();
+        cudaFree(r->pal_rgb4);
+        cudaFree(r->pal_lab);
+        cudaFree(r->pal_ab);
+        cudaFree(r->pal_lab32);
+        cudaFree(r->offsets);
+        cudaFree(r->nn_table);
+        cudaFree(r->flag_list);
+        cudaFree(r->flag_count);
+    }
+    delete r;
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_remapper_create(const lutgen_remapper_desc* desc, lutgen_remapper** out) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!desc || !out) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (desc->kind < LUTGEN_GAUSSIAN || desc->kind > LUTGEN_SAMPLING) return fail(LUTGEN_ERR_INVALID, "unknown remapper kind %d", desc->kind);
+    if (desc->palette_len && !desc->palette) return fail(LUTGEN_ERR_INVALID, "palette is NULL");
+    if (desc->palette_len > (1u << 20)) return fail(LUTGEN_ERR_UNSUPPORTED, "palette of %llu colours (limit 2^20)", (unsigned long long)desc->palette_len);
+    if (desc->kind == LUTGEN_SAMPLING) {
+        // rand_distr::Normal::new(mean, std_dev).unwrap() (gaussian_sample.rs:36) rejects a non-finite std_dev
+        if (!std::isfinite(desc->std_dev)) return fail(LUTGEN_ERR_INVALID, "std_dev must be finite (Normal::new(..).unwrap() panics)");
+        if (desc->iterations > (1ull << 31)) return fail(LUTGEN_ERR_UNSUPPORTED, "iterations > 2^31");
+    }
+    if ((desc->kind == LUTGEN_NEAREST || desc->kind == LUTGEN_SAMPLING) && desc->palette_len == 0)
+        return fail(LUTGEN_ERR_INVALID, "empty palette (kiddo nearest_one on an empty tree panics)");
+    std::lock_guard<std::mutex> lk(g.mu);
+    lutgen_remapper* r = new lutgen_remapper();
+    r->d = *desc;
+    r->n = (uint32_t)desc->palette_len;
+    r->pal_host.assign(desc->palette, desc->palette + 3 * (size_t)r->n);
+    r->d.palette = r->pal_host.data();
+    r->k_eff = (desc->nearest != 0 && desc->nearest < desc->palette_len) ? (uint32_t)desc->nearest : 0u;  // rbf.rs:38
+    auto bail = [&](int code) {
+        lutgen_cuda_remapper_destroy(r);
+        return code;
+    };
+#define CU_TRY_R(expr)                                                                                         \
+    do {                                                                                                       \
+        cudaError_t _e = (expr);                                                                               \
+        if (_e != cudaSuccess) return bail(fail(LUTGEN_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e))); \
+    } while (0)
+    size_t n = r->n, na = n ? n : 1;
+    std::vector<uint8_t> rgb4(4 * na, 0);
+    for (size_t i = 0; i < n; ++i) {
+        rgb4[4 * i] = r->pal_host[3 * i];
+        rgb4[4 * i + 1] = r->pal_host[3 * i + 1];
+        rgb4[4 * i + 2] = r->pal_host[3 * i + 2];
+    }
+    CU_TRY_R(cudaMalloc((void**)&r->pal_rgb4, 4 * na));
+    CU_TRY_R(cudaMalloc((void**)&r->pal_lab, sizeof(double) * 3 * na));
+    CU_TRY_R(cudaMalloc((void**)&r->pal_ab, sizeof(float) * 2 * na));
+    CU_TRY_R(cudaMalloc((void**)&r->pal_lab32, sizeof(float4) * na));
+    CU_TRY_R(cudaMemcpyAsync(r->pal_rgb4, rgb4.data(), 4 * na, cudaMemcpyHostToDevice, g.stream));
+    if (n) {
+        k_palette_setup<<<blocks_for(n, 128), 128, 0, g.stream>>>(r->pal_rgb4, r->n, desc->lum_factor, g.tables->decode, r->pal_lab, r->pal_ab,
+                                                                  r->pal_lab32);
+        g_launches.fetch_add(1);
+        CU_TRY_R(cudaGetLastError());
+    }
+    if (desc->kind == LUTGEN_SAMPLING) {
+        size_t K = (size_t)desc->iterations, Ka = K ? K : 1;
+        r->noise.assign(4 * K, 0.0);
+        CU_TRY_R(cudaMalloc((void**)&r->offsets, sizeof(short4) * Ka));
+        if (K) {
+            CU_TRY_R(g.misc.reserve(sizeof(double) * 4 * K));
+            k_philox_normals<<<blocks_for(2 * K, 128), 128, 0, g.stream>>>((double*)g.misc.p, K, desc->mean, desc->std_dev, desc->seed);
+            g_launches.fetch_add(1);
+            CU_TRY_R(cudaGetLastError());
+            CU_TRY_R(cudaMemcpyAsync(r->noise.data(), g.misc.p, sizeof(double) * 4 * K, cudaMemcpyDeviceToHost, g.stream));
+            CU_TRY_R(cudaStreamSynchronize(g.stream));
+            int rc2 = upload_offsets(r);
+            if (rc2) return bail(rc2);
+        }
+    }
+    CU_TRY_R(cudaStreamSynchronize(g.stream));
+    r->fast_ok = false;
+#undef CU_TRY_R
+    *out = r;
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_sampling_get_noise(const lutgen_remapper* r, double* noise_out) {
+    if (!r || !noise_out) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    if (r->d.kind != LUTGEN_SAMPLING) return fail(LUTGEN_ERR_INVALID, "not a sampling remapper");
+    memcpy(noise_out, r->noise.data(), sizeof(double) * r->noise.size());
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_sampling_set_noise(lutgen_remapper* r, const double* noise) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!r || !noise) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    if (r->d.kind != LUTGEN_SAMPLING) return fail(LUTGEN_ERR_INVALID, "not a sampling remapper");
+    std::lock_guard<std::mutex> lk(g.mu);
+    std::vector<double> old = r->noise;
+    r->noise.assign(noise, noise + r->noise.size());
+    rc = upload_offsets(r);
+    if (rc) {
+        r->noise = old;
+        upload_offsets(r);
+    }
+    return rc;
+}
+
+int lutgen_cuda_generate_lut_rows_dev(const lutgen_remapper* r, uint8_t level, uint8_t* lut_rgb_dev, uint32_t row_begin, uint32_t row_end,
+                                      void* stream) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!r || !lut_rgb_dev) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33", level);
+    uint32_t side = (uint32_t)level * level * level;
+    if (row_begin > row_end || row_end > side) return fail(LUTGEN_ERR_INVALID, "rows [%u, %u) outside 0..%u", row_begin, row_end, side);
+    cudaStream_t s = stream ? (cudaStream_t)stream : g.stream;
+    Front f{};
+    f.out = lut_rgb_dev;
+    f.begin = (unsigned long long)row_begin * side;
+    f.count = (unsigned long long)(row_end - row_begin) * side;
+    f.cs = (uint32_t)level * level;
+    f.csm1 = f.cs - 1;
+    rc = launch_remap<FRONT_LUT>(f, r, s);
+    if (rc) return rc;
+    if (!stream) CU_TRY(cudaStreamSynchronize(s));
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_generate_lut(const lutgen_remapper* r, uint8_t level, uint8_t* out_rgb, const volatile uint8_t* abort_flag) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!r || !out_rgb) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33", level);
+    if (abort_flag && *abort_flag) return LUTGEN_ABORTED;
+    std::lock_guard<std::mutex> lk(g.mu);
+    size_t bytes = 3 * lut_entries(level);
+    uint32_t side = (uint32_t)level * level * level;
+    CU_TRY(g.lut_rgb.reserve(bytes));
+    // Row chunks so a set abort flag is honoured between launches (lib.rs:149-170).
+    uint32_t chunks = abort_flag ? 8u : 1u;
+    if (chunks > side) chunks = side;
+    for (uint32_t c = 0; c < chunks; ++c) {
+        uint32_t r0 = (uint32_t)((uint64_t)side * c / chunks), r1 = (uint32_t)((uint64_t)side * (c + 1) / chunks);
+        rc = lutgen_cuda_generate_lut_rows_dev(r, level, (uint8_t*)g.lut_rgb.p, r0, r1, g.stream);
+        if (rc) return rc;
+        if (abort_flag) {
+            CU_TRY(cudaStreamSynchronize(g.stream));
+            if (*abort_flag) return LUTGEN_ABORTED;
+        }
+    }
+    CU_TRY(cudaMemcpyAsync(out_rgb, g.lut_rgb.p, bytes, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    if (abort_flag && *abort_flag) return LUTGEN_ABORTED;
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_remap_image_dev(const lutgen_remapper* r, uint8_t* rgba_dev, size_t npix, void* stream) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!r || (!rgba_dev && npix)) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    if (reinterpret_cast<uintptr_t>(rgba_dev) & 3u) return fail(LUTGEN_ERR_INVALID, "rgba_dev must be 4-byte aligned");
+    if (npix >= (1ull << 32)) return fail(LUTGEN_ERR_UNSUPPORTED, "more than 2^32 pixels in one call");
+    cudaStream_t s = stream ? (cudaStream_t)stream : g.stream;
+    Front f{};
+    f.out = rgba_dev;
+    f.begin = 0;
+    f.count = npix;
+    rc = launch_remap<FRONT_IMAGE>(f, r, s);
+    if (rc) return rc;
+    if (!stream) CU_TRY(cudaStreamSynchronize(s));
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_remap_image(const lutgen_remapper* r, uint8_t* rgba, size_t npix, const volatile uint8_t* abort_flag) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!r || (!rgba && npix)) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    if (abort_flag && *abort_flag) return LUTGEN_ABORTED;
+    if (npix == 0) return LUTGEN_OK;
+    std::lock_guard<std::mutex> lk(g.mu);
+    CU_TRY(g.frame.reserve(npix * 4));
+    CU_TRY(cudaMemcpyAsync(g.frame.p, rgba, npix * 4, cudaMemcpyHostToDevice, g.stream));
+    rc = lutgen_cuda_remap_image_dev(r, (uint8_t*)g.frame.p, npix, g.stream);
+    if (rc) return rc;
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    // The reference skips pixels once the flag is set and the caller discards the
+    // image (mod.rs:36-42, lib.rs:152-157): report it and leave `rgba` untouched.
+    if (abort_flag && *abort_flag) return LUTGEN_ABORTED;
+    CU_TRY(cudaMemcpyAsync(rgba, g.frame.p, npix * 4, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    return LUTGEN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// oklab
+// ---------------------------------------------------------------------------
+int lutgen_cuda_srgb_to_oklab(const uint8_t* rgb, size_t n, float* out_lab) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (n && (!rgb || !out_lab)) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    if (n == 0) return LUTGEN_OK;
+    std::lock_guard<std::mutex> lk(g.mu);
+    CU_TRY(g.misc.reserve(16 * n));
+    float* dout = (float*)g.misc.p;
+    uint8_t* din = (uint8_t*)g.misc.p + 12 * n;
+    CU_TRY(cudaMemcpyAsync(din, rgb, 3 * n, cudaMemcpyHostToDevice, g.stream));
+    k_srgb_to_oklab<<<blocks_for(n, 256), 256, 0, g.stream>>>(din, n, dout, g.tables);
+    LAUNCH_CHECK();
+    CU_TRY(cudaMemcpyAsync(out_lab, dout, 12 * n, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_oklab_to_srgb(const float* lab, size_t n, uint8_t* out_rgb) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (n && (!lab || !out_rgb)) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    if (n == 0) return LUTGEN_OK;
+    std::lock_guard<std::mutex> lk(g.mu);
+    CU_TRY(g.misc.reserve(16 * n));
+    float* din = (float*)g.misc.p;
+    uint8_t* dout = (uint8_t*)g.misc.p + 12 * n;
+    CU_TRY(cudaMemcpyAsync(din, lab, 12 * n, cudaMemcpyHostToDevice, g.stream));
+    k_oklab_to_srgb<<<blocks_for(n, 256), 256, 0, g.stream>>>(din, n, dout, g.tables);
+    LAUNCH_CHECK();
+    CU_TRY(cudaMemcpyAsync(out_rgb, dout, 3 * n, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    return LUTGEN_OK;
+}
+
+}  // extern "C"
