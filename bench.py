@@ -1,0 +1,442 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the Hald-CLUT hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload generate|apply]
+
+One JSON line on stdout (rank 0). BASELINE.json's metric has two parts and both are
+measured in every run:
+
+  * top level  : "LUT entries/s (level-16 Gaussian RBF)". One step = one complete level-16
+                 CLUT (16,777,216 entries) of GaussianRemapper(catppuccin-mocha, shape 128,
+                 nearest 16, lum 1.0, preserve off) -- BASELINE config 1's remapper at the level
+                 the metric names. With N > 1 the rows are sharded across ranks and one in-place
+                 NCCL all-gather assembles the CLUT on every rank (strong scaling: the work is one
+                 CLUT however many GPUs share it).
+  * "apply"    : "LUT apply Gpix/s". One step = the level-8 CLUT applied in place to a batch of
+                 synthetic 3840x2160 RGBA8 frames resident in HBM (BASELINE configs 2/5; frames are
+                 sharded across ranks, no collective, weak scaling).
+
+`--workload apply` swaps the two (apply on top, generation under "generate").
+
+`value` is device-resident throughput (CUDA events on the launching stream, L2 flushed
+between generation steps; the apply batch is larger than L2). `e2e` is the same metric through
+the public host API with page-locked HOST buffers, copies inside the timed region.
+`cpu_baseline` / `--impl reference`: the reference is pure Rust and no Rust toolchain exists in
+this environment, so its CPU path is timed as the C restatement in oracle/ ("port"), on the
+box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+LEVEL_GEN = 16
+LEVEL_APPLY = 8
+FRAME_W, FRAME_H = 3840, 2160
+FRAME_PIX = FRAME_W * FRAME_H
+GEN_PARAMS = dict(shape=128.0, nearest=16, lum=1.0, preserve=False)
+# flops per entry = 8N + 9k + 77 (N palette colours, k neighbours), FMA = 2
+GEN_N, GEN_K = 26, 16
+GEN_FLOPS_PER_ENTRY = 8 * GEN_N + 9 * GEN_K + 77
+APPLY_BYTES_PER_PIXEL = 8  # 4 read + 4 written, in place; CLUT traffic is cache resident
+
+
+def load_palette():
+    with open(os.path.join(ROOT, "tests", "golden", "palettes.json")) as f:
+        return np.array(json.load(f)["catppuccin_mocha"], np.uint8)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- reference arm / CPU baseline
+def cpu_generate(steps, warmup, threads):
+    """Oracle port of par_generate_lut on a bounded sample: 8 bands of 64 rows spread over the
+    level-16 CLUT (1/8 of its 4096 rows = 2,097,152 entries per step)."""
+    import oracle_lib as O
+    pal = load_palette()
+    r = O.Remapper(O.GAUSSIAN, pal, param=GEN_PARAMS["shape"], nearest=GEN_PARAMS["nearest"], lum_factor=GEN_PARAMS["lum"],
+                   preserve=GEN_PARAMS["preserve"])
+    side = LEVEL_GEN ** 3
+    out = np.zeros((side, side, 3), np.uint8)
+    bands = [(i * 512, i * 512 + 64) for i in range(8)]
+    entries = sum(b - a for a, b in bands) * side
+
+    def step():
+        for a, b in bands:
+            O.lib().lutgen_oracle_generate_lut_rows(r._h, LEVEL_GEN, out.ctypes.data, a, b, threads)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return entries / dt, dt, "8 bands x 64 rows of the level-16 CLUT (2,097,152 of 16,777,216 entries) per step"
+
+
+def cpu_apply(steps, warmup, threads):
+    """Oracle port of correct_image on one 4K frame; threads=1 is what the reference does
+    (identity.rs:71-78 is a serial loop)."""
+    import oracle_lib as O
+    from conftest import random_rgba
+    pal = load_palette()
+    lut = O.Remapper(O.GAUSSIAN, pal, param=128.0, nearest=16).generate_lut(LEVEL_APPLY)
+    img = random_rgba(FRAME_PIX, 42080085)
+
+    def step():
+        buf = img.copy()
+        t = time.perf_counter()
+        O.lib().lutgen_oracle_correct_image(buf.ctypes.data, FRAME_PIX, lut.ctypes.data, LEVEL_APPLY, threads)
+        return time.perf_counter() - t
+
+    for _ in range(warmup):
+        step()
+    dt = float(np.mean([step() for _ in range(steps)]))
+    return FRAME_PIX / dt / 1e9, dt, "one 3840x2160 RGBA8 frame per step"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_lib as O
+    cores = O.max_threads()
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    gen_v, gen_dt, gen_sample = cpu_generate(min(steps, 5), min(warmup, 1), cores)
+    app_v, app_dt, app_sample = cpu_apply(min(steps, 10), min(warmup, 2), 1)
+    gen = {"metric": "LUT entries/s (level-16 Gaussian RBF)", "value": gen_v, "unit": "entries/s", "ms_per_step": gen_dt * 1e3,
+           "cpu_baseline": {"value": gen_v, "unit": "entries/s", "cores": cores, "kind": "port", "sample": gen_sample},
+           "e2e": {"value": gen_v, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "config": {"workload": "generate level-16 Gaussian RBF CLUT, catppuccin-mocha (26 colours), shape 128, nearest 16, lum 1.0"}}
+    app = {"metric": "LUT apply Gpix/s", "value": app_v, "unit": "Gpix/s", "ms_per_step": app_dt * 1e3,
+           "cpu_baseline": {"value": app_v, "unit": "Gpix/s", "cores": 1, "kind": "port", "sample": app_sample},
+           "e2e": {"value": app_v, "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "config": {"workload": "apply level-8 CLUT to 3840x2160 RGBA8 (uniform random pixels)"}}
+    top, other, other_key = (gen, app, "apply") if args.workload == "generate" else (app, gen, "generate")
+    line = dict(top)
+    line.update({"impl": "reference", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "higher_is_better": True,
+                 "scaling": "strong" if args.workload == "generate" else "weak", "vs_baseline": None,
+                 "dtype": "f32/f64" if args.workload == "generate" else "u8", "data": "synthetic",
+                 "note": "CPU restatement of the reference algorithm (oracle/), not the Rust binary: no Rust toolchain here",
+                 other_key: other})
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from lutgen_rs_b200 import _native, device, identity, interpolation
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    device.init(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    peaks, peak_kind = measured_peaks()
+    L = _native.lib()
+    pal = load_palette()
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+    def flush_l2():
+        flush_buf.fill_(1)
+
+    def timed(fn, n, flush, prepare=None):
+        """n timed calls of fn, each bracketed by CUDA events on the launching stream.
+        `prepare` (untimed) restores the inputs an in-place step consumed."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for a, b in evs:
+            if prepare is not None:
+                prepare()
+            if flush:
+                flush_l2()
+            a.record(stream)
+            fn()
+            b.record(stream)
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) * 1e-3 for a, b in evs]
+
+    # ---------------- generation ----------------
+    remapper = interpolation.GaussianRemapper(pal, GEN_PARAMS["shape"], GEN_PARAMS["nearest"], GEN_PARAMS["lum"], GEN_PARAMS["preserve"])
+    side = LEVEL_GEN ** 3
+    entries = side * side
+    r0, r1, per = device.shard_rows(side, world, rank)
+    lut16 = torch.empty(per * world * side * 3, dtype=torch.uint8, device="cuda")
+
+    def gen_step():
+        device.generate_lut(remapper, LEVEL_GEN, out=lut16)
+
+    def gen_kernel_only():
+        device.generate_lut_rows_(remapper, LEVEL_GEN, lut16, r0, r1)
+
+    # ---------------- apply ----------------
+    lut8_host = interpolation.GaussianRemapper(pal, 128.0, 16, 1.0, False).generate_lut(LEVEL_APPLY)
+    lut8 = torch.from_numpy(lut8_host).cuda().reshape(-1)
+    frames_per_gpu = args.frames
+    g = torch.Generator(device="cuda")
+    g.manual_seed(42080085 + rank)
+    shape = (frames_per_gpu, FRAME_H, FRAME_W, 4)
+    # (a) uniform random RGBA: the worst case for the CLUT gather (no two neighbours share a cell)
+    pristine_random = torch.randint(0, 256, shape, dtype=torch.uint8, device="cuda", generator=g)
+    # (b) photo-like: smooth gradients + a few LSB of noise per channel, opaque alpha
+    xs = torch.arange(FRAME_W, device="cuda", dtype=torch.float32).view(1, 1, FRAME_W)
+    ys = torch.arange(FRAME_H, device="cuda", dtype=torch.float32).view(1, FRAME_H, 1)
+    ph = torch.arange(frames_per_gpu, device="cuda", dtype=torch.float32).view(-1, 1, 1) * 7.0
+    chans = [(xs * (255.0 / FRAME_W) + ph) % 256.0 + 0 * ys, (ys * (255.0 / FRAME_H) + 2 * ph) % 256.0 + 0 * xs,
+             ((xs + ys) * (255.0 / (FRAME_W + FRAME_H)) + 3 * ph) % 256.0]
+    noise = torch.randint(-4, 4, (frames_per_gpu, FRAME_H, FRAME_W, 3), device="cuda", generator=g, dtype=torch.int16)
+    pristine_photo = torch.empty(shape, dtype=torch.uint8, device="cuda")
+    for c in range(3):
+        pristine_photo[..., c] = (chans[c].to(torch.int16) + noise[..., c]).clamp_(0, 255).to(torch.uint8)
+    pristine_photo[..., 3] = 255
+    del noise, chans
+    frames = torch.empty(shape, dtype=torch.uint8, device="cuda")
+    apply_pix = frames_per_gpu * FRAME_PIX
+
+    def apply_step():
+        device.apply_hald_(frames, lut8, LEVEL_APPLY)
+
+    # e2e buffers (page-locked host memory)
+    lut16_host = torch.empty((side, side, 3), dtype=torch.uint8).pin_memory()
+    e2e_frames = 4
+    host_frames = [torch.randint(0, 256, (FRAME_H, FRAME_W, 4), dtype=torch.uint8).pin_memory() for _ in range(e2e_frames)]
+    host_frames_np = [t.numpy() for t in host_frames]
+
+    def gen_e2e():
+        if world == 1:
+            remapper.generate_lut(LEVEL_GEN, out=lut16_host.numpy())
+        else:
+            full = device.generate_lut(remapper, LEVEL_GEN, out=lut16)
+            if rank == 0:
+                lut16_host.copy_(full, non_blocking=True)
+            torch.cuda.synchronize()
+
+    def apply_e2e():
+        identity.correct_images(host_frames_np, lut8_host, LEVEL_APPLY)
+
+    # warm-up
+    for _ in range(warmup):
+        gen_step()
+        apply_step()
+    gen_e2e()
+    apply_e2e()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _native.launch_count()
+
+    # generation, device resident (whole step incl. all-gather), max over ranks
+    barrier()
+    gen_times = timed(gen_step, steps, flush=True)
+    barrier()
+    gen_launches = _native.launch_count() - launches0
+    gen_t = max_over_ranks(float(np.mean(gen_times)))
+    gen_kernel_times = timed(gen_kernel_only, steps, flush=True)
+    gen_kernel_t = float(np.mean(gen_kernel_times))
+    # apply, device resident
+    launches1 = _native.launch_count()
+    barrier()
+    apply_times = timed(apply_step, steps, flush=False, prepare=lambda: frames.copy_(pristine_random))
+    barrier()
+    apply_launches = _native.launch_count() - launches1
+    apply_t = max_over_ranks(float(np.mean(apply_times)))
+    photo_times = timed(apply_step, steps, flush=False, prepare=lambda: frames.copy_(pristine_photo))
+    barrier()
+    photo_t = max_over_ranks(float(np.mean(photo_times)))
+    # end to end through the host API
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        gen_e2e()
+    barrier()
+    gen_e2e_t = max_over_ranks((time.perf_counter() - t0) / steps)
+    host_pristine = [t.clone() for t in host_frames]
+    acc = 0.0
+    for _ in range(steps):
+        for t, p in zip(host_frames, host_pristine):
+            t.copy_(p)
+        barrier()
+        t0 = time.perf_counter()
+        apply_e2e()
+        acc += time.perf_counter() - t0
+    barrier()
+    apply_e2e_t = max_over_ranks(acc / steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # roofline denominators
+    fp32 = C_double()
+    mufu = C_double()
+    _native.check(L.lutgen_cuda_measure_peaks(fp32.ref, mufu.ref))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    shard_entries = (r1 - r0) * side
+    gen_achieved = shard_entries * GEN_FLOPS_PER_ENTRY / gen_kernel_t / 1e12
+    gen_line = {
+        "metric": "LUT entries/s (level-16 Gaussian RBF)", "value": entries / gen_t, "unit": "entries/s",
+        "ms_per_step": gen_t * 1e3, "scaling": "strong", "dtype": "f32 (f64 on flagged near-ties)",
+        "gpu_launches": int(gen_launches),
+        "e2e": {"value": entries / gen_e2e_t, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 3 * entries,
+                "ms_per_step": gen_e2e_t * 1e3},
+        "roofline": {"bound": "fp32", "achieved": gen_achieved, "peak": fp32.value, "unit": "TFLOP/s",
+                     "frac": gen_achieved / fp32.value if fp32.value else None, "traffic": None,
+                     "peak_source": "on-box FFMA micro-benchmark (lutgen_cuda_measure_peaks), this run",
+                     "mufu_peak_tops": mufu.value, "kernel_ms": gen_kernel_t * 1e3,
+                     "algorithmic_flops_per_entry": GEN_FLOPS_PER_ENTRY},
+        "config": {"workload": "generate level-16 Gaussian RBF CLUT (16,777,216 entries), catppuccin-mocha 26 colours, "
+                               "shape 128, nearest 16, lum 1.0, preserve off; rows sharded over ranks + in-place NCCL all-gather",
+                   "level": LEVEL_GEN, "l2": "flushed between timed iterations (512 MiB fill)"},
+    }
+    total_pix = apply_pix * world
+    apply_bw = apply_pix * APPLY_BYTES_PER_PIXEL / apply_t / 1e9
+    apply_line = {
+        "metric": "LUT apply Gpix/s", "value": total_pix / apply_t / 1e9, "unit": "Gpix/s", "ms_per_step": apply_t * 1e3,
+        "scaling": "weak", "dtype": "u8", "gpu_launches": int(apply_launches),
+        "e2e": {"value": e2e_frames * FRAME_PIX * world / apply_e2e_t / 1e9, "unit": "Gpix/s",
+                "h2d_bytes_per_step": e2e_frames * FRAME_PIX * 4 + lut8_host.size, "d2h_bytes_per_step": e2e_frames * FRAME_PIX * 4,
+                "ms_per_step": apply_e2e_t * 1e3},
+        "roofline": {"bound": "hbm", "achieved": apply_bw, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": apply_bw / peaks["hbm_gbs"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})"},
+        "config": {"workload": f"apply level-8 CLUT in place to {frames_per_gpu} x 3840x2160 RGBA8 frames per GPU, uniform random pixels "
+                               "(worst case: every gather is its own 32 B L2 sector)",
+                   "level": LEVEL_APPLY, "frames_per_gpu": frames_per_gpu,
+                   "l2": f"batch is {apply_pix * 4 >> 20} MiB per GPU, larger than the 126 MB L2; frames restored (untimed) before every step"},
+    }
+    photo_bw = apply_pix * APPLY_BYTES_PER_PIXEL / photo_t / 1e9
+    apply_line["photo_like"] = {
+        "value": total_pix / photo_t / 1e9, "unit": "Gpix/s", "ms_per_step": photo_t * 1e3,
+        "roofline": {"bound": "hbm", "achieved": photo_bw, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": photo_bw / peaks["hbm_gbs"]},
+        "config": {"workload": "same batch shape, photo-like pixels: per-frame colour gradients + 3 bits of noise per channel, alpha 255"},
+    }
+    # CPU baseline (rank 0, N = 1 only): oracle port on the host cores, bounded sample
+    if world == 1 and not args.no_cpu:
+        import oracle_lib as O
+        cores = O.max_threads()
+        v, _, sample = cpu_generate(2, 1, cores)
+        gen_line["cpu_baseline"] = {"value": v, "unit": "entries/s", "cores": cores, "kind": "port", "sample": sample}
+        v, _, sample = cpu_apply(5, 1, 1)
+        apply_line["cpu_baseline"] = {"value": v, "unit": "Gpix/s", "cores": 1, "kind": "port",
+                                      "sample": sample + " (single thread, as identity.rs:71-78)"}
+        v, _, _ = cpu_apply(5, 1, cores)
+        apply_line["cpu_baseline"]["all_cores_value"] = v
+        apply_line["cpu_baseline"]["all_cores"] = cores
+
+    top, other, other_key = (gen_line, apply_line, "apply") if args.workload == "generate" else (apply_line, gen_line, "generate")
+    line = dict(top)
+    line.update({"n_gpus": world, "steps": steps, "warmup": warmup, "higher_is_better": True, "vs_baseline": None,
+                 "data": "synthetic", "clocks": clocks, other_key: other})
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+class C_double:
+    def __init__(self):
+        import ctypes
+        self._v = ctypes.c_double(0.0)
+        self.ref = ctypes.byref(self._v)
+
+    @property
+    def value(self):
+        return float(self._v.value)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="generate", choices=["generate", "apply"])
+    ap.add_argument("--frames", type=int, default=32, help="4K frames per GPU in the device-resident apply batch")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

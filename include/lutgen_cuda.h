@@ -168,6 +168,21 @@ LUTGEN_API int lutgen_cuda_srgb_to_oklab(const uint8_t* rgb, size_t n, float* ou
 /* oklab::oklab_to_srgb for n colours: in n x [f32;3], out n x [u8;3]. */
 LUTGEN_API int lutgen_cuda_oklab_to_srgb(const float* lab, size_t n, uint8_t* out_rgb);
 
+/* ---- diagnostics ---------------------------------------------------------- */
+
+/* Measured FP32 FMA throughput (TFLOP/s, FMA = 2) and MUFU throughput (T op/s)
+ * of this GPU at the clocks it sustains: the roofline denominators for the
+ * generation kernels (no counterpart in the reference). */
+LUTGEN_API int lutgen_cuda_measure_peaks(double* fp32_tflops, double* mufu_tops);
+
+/* The few-ulp f32 Oklab conversion the throughput kernels use for their tile bounds
+ * (tests bound its distance to the exact lutgen_cuda_srgb_to_oklab). */
+LUTGEN_API int lutgen_cuda_srgb_to_oklab_fast(const uint8_t* rgb, size_t n, float* out_lab);
+
+/* With LUTGEN_CUDA_STATS=1 in the environment at init: per-tile histograms of the throughput
+ * kernel's classification, out128[0..64) = number of UNCERTAIN colours, [64..128) = IN colours. */
+LUTGEN_API int lutgen_cuda_debug_stats(uint32_t* out128, int reset);
+
 #ifdef __cplusplus
 }
 #endif

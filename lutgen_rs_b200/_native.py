@@ -23,7 +23,8 @@ EXPORTS = [
     "lutgen_cuda_correct_pixels", "lutgen_cuda_remapper_create", "lutgen_cuda_remapper_destroy",
     "lutgen_cuda_generate_lut", "lutgen_cuda_generate_lut_rows_dev", "lutgen_cuda_remap_image",
     "lutgen_cuda_remap_image_dev", "lutgen_cuda_sampling_get_noise", "lutgen_cuda_sampling_set_noise",
-    "lutgen_cuda_srgb_to_oklab", "lutgen_cuda_oklab_to_srgb",
+    "lutgen_cuda_srgb_to_oklab", "lutgen_cuda_oklab_to_srgb", "lutgen_cuda_measure_peaks",
+    "lutgen_cuda_srgb_to_oklab_fast", "lutgen_cuda_debug_stats",
 ]
 
 
@@ -99,6 +100,9 @@ def load():
             "lutgen_cuda_sampling_set_noise": ([vp, vp], i32),
             "lutgen_cuda_srgb_to_oklab": ([vp, sz, vp], i32),
             "lutgen_cuda_oklab_to_srgb": ([vp, sz, vp], i32),
+            "lutgen_cuda_srgb_to_oklab_fast": ([vp, sz, vp], i32),
+            "lutgen_cuda_debug_stats": ([vp, i32], i32),
+            "lutgen_cuda_measure_peaks": ([C.POINTER(C.c_double), C.POINTER(C.c_double)], i32),
         }
         for name, (args, res) in sig.items():
             fn = getattr(L, name)

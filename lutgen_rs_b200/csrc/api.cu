@@ -18,6 +18,7 @@
 #include "../../include/lutgen_cuda.h"
 #include "kernels_apply.cuh"
 #include "kernels_exact.cuh"
+#include "kernels_fast.cuh"
 
 using namespace lutgen;
 
@@ -86,6 +87,7 @@ struct Ctx {
     DevBuf frame;                   // RGBA8 image scratch
     DevBuf batch_frames[kBatchStreams];
     DevBuf misc;
+    uint32_t* stats = nullptr;      // device [128], only with LUTGEN_CUDA_STATS set
 } g;
 
 int ensure_ready() {
@@ -122,11 +124,25 @@ struct lutgen_remapper {
     mutable uint32_t* nn_table = nullptr;  // device 2^24 x u32, built lazily
     mutable bool nn_table_ready = false;
     mutable std::mutex mu;
+    mutable cudaEvent_t nn_table_ev = nullptr;
+    // whole-cube table of the remapper itself (r | g<<8 | b<<16 per sRGB colour): large images
+    // are remapped as "build the level-16 CLUT once, then gather" (remap_pixel is a pure function
+    // of the colour; alpha is untouched)
+    mutable uint32_t* full_table = nullptr;
+    mutable bool full_table_ready = false;
+    mutable cudaEvent_t full_table_ev = nullptr;
     // fast-path work list (flagged entries), device
     mutable uint32_t* flag_list = nullptr;
     mutable uint32_t* flag_count = nullptr;
     mutable size_t flag_cap = 0;
     bool fast_ok = false;
+    // NearestNeighbor fast path: palette with repeated colours dropped (first occurrence wins,
+    // exactly what a strict `<` argmin returns), so duplicates never look like ties
+    uint32_t un = 0;
+    uint8_t* upal_rgb4 = nullptr;
+    float* upal_ab = nullptr;
+    float4* upal_lab32 = nullptr;
+    double* upal_lab = nullptr;
 };
 
 namespace {
@@ -195,54 +211,164 @@ int upload_offsets(lutgen_remapper* r) {
     return LUTGEN_OK;
 }
 
+int launch_apply(uint8_t* rgba_dev, size_t npix, const uint32_t* lut_rgbx, uint8_t level, cudaStream_t s);
+
+// ---- exact kernels ------------------------------------------------------------------------
 template <int MODE>
-int launch_nn_mode(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
-    if (f.count == 0) return LUTGEN_OK;
+int launch_nn_exact(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
+    if (MODE != FRONT_LIST && f.count == 0) return LUTGEN_OK;
     RemapParams P = params_of(r);
-    k_nn_exact<MODE><<<blocks_for(f.count, 256), 256, 0, s>>>(f, P, g.tables);
+    unsigned grid = MODE == FRONT_LIST ? (unsigned)g.sm_count * 4u : blocks_for(f.count, 256);
+    k_nn_exact<MODE><<<grid, 256, 0, s>>>(f, P, g.tables);
     LAUNCH_CHECK();
     return LUTGEN_OK;
 }
 
-int launch_nn(const Front& f, const lutgen_remapper* r, int mode, cudaStream_t s) {
-    switch (mode) {
-        case FRONT_LUT: return launch_nn_mode<FRONT_LUT>(f, r, s);
-        case FRONT_IMAGE: return launch_nn_mode<FRONT_IMAGE>(f, r, s);
-        default: return launch_nn_mode<FRONT_TABLE>(f, r, s);
+template <int KIND, int MODE>
+int launch_rbf_exact_km(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
+    if (MODE != FRONT_LIST && f.count == 0) return LUTGEN_OK;
+    RemapParams P = params_of(r);
+    unsigned grid = MODE == FRONT_LIST ? (unsigned)g.sm_count * 4u : blocks_for(f.count, 256);
+    k_rbf_exact<KIND, MODE><<<grid, 256, 0, s>>>(f, P, g.tables);
+    LAUNCH_CHECK();
+    return LUTGEN_OK;
+}
+
+template <int MODE>
+int launch_rbf_exact(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
+    switch (r->d.kind) {
+        case LUTGEN_GAUSSIAN: return launch_rbf_exact_km<0, MODE>(f, r, s);
+        case LUTGEN_SHEPARD: return launch_rbf_exact_km<1, MODE>(f, r, s);
+        default: return launch_rbf_exact_km<2, MODE>(f, r, s);
+    }
+}
+
+// ---- fast (tile-bounded) kernel + exact pass over what it flagged ---------------------------
+bool fast_path_supported(const lutgen_remapper* r) {
+    if (getenv("LUTGEN_CUDA_EXACT_ONLY")) return false;
+    double lum = r->d.lum_factor;
+    if (!(lum > 0.0) || !std::isnormal(lum) || !std::isnormal((float)lum) || !std::isnormal((float)(1.0 / lum))) return false;
+    bool nn = r->d.kind == LUTGEN_NEAREST || r->d.kind == LUTGEN_SAMPLING;
+    uint32_t n = nn ? r->un : r->n;
+    if (n == 0 || n > 2048) return false;
+    if (!nn && r->d.param != r->d.param) return false;
+    return true;
+}
+
+template <int KIND, int MODE>
+int launch_fast(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
+    if (f.count == 0) return LUTGEN_OK;
+    {
+        std::lock_guard<std::mutex> lk(r->mu);
+        if (!r->flag_count) CU_TRY(cudaMalloc((void**)&r->flag_count, 64));
+        if (r->flag_cap < f.count) {
+            if (r->flag_list) CU_TRY(cudaFree(r->flag_list));
+            r->flag_list = nullptr;
+            r->flag_cap = 0;
+            size_t cap = ((size_t)f.count + 1023) & ~(size_t)1023;
+            CU_TRY(cudaMalloc((void**)&r->flag_list, cap * sizeof(uint32_t)));
+            r->flag_cap = cap;
+        }
+    }
+    const bool nn = KIND == KIND_NN;
+    FastArgs a{};
+    a.f = f;
+    a.pal = nn ? r->upal_lab32 : r->pal_lab32;
+    a.pal_rgb = reinterpret_cast<const uint32_t*>(nn ? r->upal_rgb4 : r->pal_rgb4);
+    a.pal_ab = nn ? r->upal_ab : r->pal_ab;
+    a.n = nn ? r->un : r->n;
+    a.k = nn ? 1u : r->k_eff;
+    a.preserve = r->d.preserve;
+    a.lum = (float)r->d.lum_factor;
+    a.inv_lum = (float)(1.0 / r->d.lum_factor);
+    a.stats = g.stats;
+    a.c1 = KIND == 0 ? (float)(-r->d.param * 1.4426950408889634) : (KIND == 1 ? (float)(-0.5 * r->d.param) : 0.0f);
+    a.flag_list = r->flag_list;
+    a.flag_count = r->flag_count;
+    a.tables = g.tables;
+    unsigned grid;
+    if (MODE == FRONT_IMAGE) {
+        a.tr = a.tg = a.tb = 1;
+        a.sh_r = a.sh_g = 0;
+        a.tiles_r = a.tiles_g = 1;
+        a.ept = FAST_MAX_EPT;
+        grid = blocks_for(f.count, FAST_TILE_MAX);
+    } else {
+        uint32_t cs = f.cs;
+        // brick sides: powers of two, at most 8 x 8 x 16 (1024 colours, 4 per thread)
+        a.sh_r = 0;
+        while (a.sh_r < 3 && (2u << a.sh_r) <= cs) ++a.sh_r;
+        a.sh_g = a.sh_r;
+        uint32_t sh_b = 0;
+        while (sh_b < 4 && (2u << sh_b) <= cs) ++sh_b;
+        a.tr = 1u << a.sh_r;
+        a.tg = 1u << a.sh_g;
+        a.tb = 1u << sh_b;
+        a.ept = (a.tr * a.tg * a.tb + FAST_THREADS - 1) / FAST_THREADS;
+        a.tiles_r = (cs + a.tr - 1) / a.tr;
+        a.tiles_g = (cs + a.tg - 1) / a.tg;
+        unsigned long long plane = (unsigned long long)cs * cs;
+        // tile origins are multiples of the brick in every axis whatever the shard, so a colour
+        // always meets the same tile (and the same classification): results are shard-independent
+        uint32_t b_lo = (uint32_t)(f.begin / plane) / a.tb * a.tb, b_hi = (uint32_t)((f.begin + f.count - 1) / plane);
+        a.b_lo = b_lo;
+        uint32_t tiles_b = (b_hi - b_lo) / a.tb + 1;
+        grid = a.tiles_r * a.tiles_g * tiles_b;
+    }
+    size_t smem = fast_smem_bytes(a.n, a.ept * FAST_THREADS);
+    static bool attr_done = false;  // one flag per <KIND, MODE> instantiation
+    if (!attr_done) {
+        CU_TRY(cudaFuncSetAttribute(k_remap_fast<KIND, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_done = true;
+    }
+    CU_TRY(cudaMemsetAsync(r->flag_count, 0, sizeof(uint32_t), s));
+    k_remap_fast<KIND, MODE><<<grid, FAST_THREADS, smem, s>>>(a);
+    LAUNCH_CHECK();
+    Front fl = f;
+    fl.list = r->flag_list;
+    fl.list_count = r->flag_count;
+    fl.list_mode = MODE;
+    if (nn) return launch_nn_exact<FRONT_LIST>(fl, r, s);
+    return launch_rbf_exact_km<KIND < 3 ? KIND : 0, FRONT_LIST>(fl, r, s);
+}
+
+template <int MODE>
+int launch_nn(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
+    if (r->fast_ok) return launch_fast<KIND_NN, MODE>(f, r, s);
+    return launch_nn_exact<MODE>(f, r, s);
+}
+
+template <int MODE>
+int launch_rbf(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
+    if (!r->fast_ok) return launch_rbf_exact<MODE>(f, r, s);
+    switch (r->d.kind) {
+        case LUTGEN_GAUSSIAN: return launch_fast<0, MODE>(f, r, s);
+        case LUTGEN_SHEPARD: return launch_fast<1, MODE>(f, r, s);
+        default: return launch_fast<2, MODE>(f, r, s);
     }
 }
 
 // NN over the whole sRGB cube, once per sampling remapper (see kernels_apply.cuh).
 int ensure_nn_table(const lutgen_remapper* r, cudaStream_t s) {
-    std::lock_guard<std::mutex> lk(r->mu);
-    if (r->nn_table_ready) return LUTGEN_OK;
-    if (!r->nn_table) CU_TRY(cudaMalloc((void**)&r->nn_table, sizeof(uint32_t) << 24));
-    Front f{};
-    f.out = reinterpret_cast<uint8_t*>(r->nn_table);
-    f.begin = 0;
-    f.count = 1ull << 24;
-    int rc = launch_nn(f, r, FRONT_TABLE, s);
-    if (rc != LUTGEN_OK) return rc;
-    r->nn_table_ready = true;
-    return LUTGEN_OK;
-}
-
-template <int KIND, int MODE>
-int launch_rbf_exact_km(const Front& f, const lutgen_remapper* r, cudaStream_t s, unsigned long long nthreads) {
-    if (nthreads == 0) return LUTGEN_OK;
-    RemapParams P = params_of(r);
-    k_rbf_exact<KIND, MODE><<<blocks_for(nthreads, 256), 256, 0, s>>>(f, P, g.tables);
-    LAUNCH_CHECK();
-    return LUTGEN_OK;
-}
-
-template <int MODE>
-int launch_rbf_exact(const Front& f, const lutgen_remapper* r, cudaStream_t s, unsigned long long nthreads) {
-    switch (r->d.kind) {
-        case LUTGEN_GAUSSIAN: return launch_rbf_exact_km<0, MODE>(f, r, s, nthreads);
-        case LUTGEN_SHEPARD: return launch_rbf_exact_km<1, MODE>(f, r, s, nthreads);
-        default: return launch_rbf_exact_km<2, MODE>(f, r, s, nthreads);
+    std::unique_lock<std::mutex> lk(r->mu);
+    if (!r->nn_table_ready) {
+        if (!r->nn_table) CU_TRY(cudaMalloc((void**)&r->nn_table, sizeof(uint32_t) << 24));
+        if (!r->nn_table_ev) CU_TRY(cudaEventCreateWithFlags(&r->nn_table_ev, cudaEventDisableTiming));
+        Front f{};
+        f.out = reinterpret_cast<uint8_t*>(r->nn_table);
+        f.begin = 0;
+        f.count = 1ull << 24;
+        f.cs = 256;
+        f.csm1 = 255;
+        lk.unlock();
+        int rc = launch_nn<FRONT_TABLE>(f, r, s);
+        if (rc != LUTGEN_OK) return rc;
+        lk.lock();
+        CU_TRY(cudaEventRecord(r->nn_table_ev, s));
+        r->nn_table_ready = true;
     }
+    CU_TRY(cudaStreamWaitEvent(s, r->nn_table_ev, 0));
+    return LUTGEN_OK;
 }
 
 template <int MODE>
@@ -262,15 +388,48 @@ int launch_sampling(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
     return LUTGEN_OK;
 }
 
+template <int MODE>
+int launch_remap(const Front& f, const lutgen_remapper* r, cudaStream_t s);
+
+// The remapper tabulated over all 2^24 colours (= its level-16 CLUT in packed form).
+int ensure_full_table(const lutgen_remapper* r, cudaStream_t s) {
+    std::unique_lock<std::mutex> lk(r->mu);
+    if (!r->full_table_ready) {
+        if (!r->full_table) CU_TRY(cudaMalloc((void**)&r->full_table, sizeof(uint32_t) << 24));
+        if (!r->full_table_ev) CU_TRY(cudaEventCreateWithFlags(&r->full_table_ev, cudaEventDisableTiming));
+        Front f{};
+        f.out = reinterpret_cast<uint8_t*>(r->full_table);
+        f.begin = 0;
+        f.count = 1ull << 24;
+        f.cs = 256;
+        f.csm1 = 255;
+        lk.unlock();
+        int rc = launch_remap<FRONT_TABLE>(f, r, s);
+        if (rc != LUTGEN_OK) return rc;
+        lk.lock();
+        CU_TRY(cudaEventRecord(r->full_table_ev, s));
+        r->full_table_ready = true;
+    }
+    CU_TRY(cudaStreamWaitEvent(s, r->full_table_ev, 0));
+    return LUTGEN_OK;
+}
+
 // Remap `f.count` colours with remapper r on stream s (no synchronisation).
 template <int MODE>
 int launch_remap(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
-    switch (r->d.kind) {
-        case LUTGEN_NEAREST: return launch_nn(f, r, MODE, s);
-        case LUTGEN_SAMPLING: return launch_sampling<MODE>(f, r, s);
-        default: {
-            return launch_rbf_exact<MODE>(f, r, s, f.count);
+    if (MODE == FRONT_IMAGE) {
+        // Big images: one pass over the colour cube costs less than one pass over the pixels.
+        unsigned long long threshold = r->d.kind == LUTGEN_SAMPLING ? (1ull << 24) : (1ull << 20);
+        if (f.count >= threshold && !getenv("LUTGEN_CUDA_NO_TABLE")) {
+            int rc = ensure_full_table(r, s);
+            if (rc != LUTGEN_OK) return rc;
+            return launch_apply(f.out, (size_t)f.count, r->full_table, 16, s);
         }
+    }
+    switch (r->d.kind) {
+        case LUTGEN_NEAREST: return launch_nn<MODE>(f, r, s);
+        case LUTGEN_SAMPLING: return launch_sampling<MODE>(f, r, s);
+        default: return launch_rbf<MODE>(f, r, s);
     }
 }
 
@@ -353,6 +512,10 @@ int lutgen_cuda_init(int device) {
     for (int i = 0; i < 104; ++i) host.encode[i] = k_srgb_encode_table[i];
     CU_TRY(cudaMalloc((void**)&g.tables, sizeof(ColorTables)));
     CU_TRY(cudaMemcpy(g.tables, &host, sizeof host, cudaMemcpyHostToDevice));
+    if (getenv("LUTGEN_CUDA_STATS")) {
+        CU_TRY(cudaMalloc((void**)&g.stats, 128 * sizeof(uint32_t)));
+        CU_TRY(cudaMemset(g.stats, 0, 128 * sizeof(uint32_t)));
+    }
     g.ready = true;
     return LUTGEN_OK;
 }
@@ -553,6 +716,13 @@ int lutgen_cuda_remapper_destroy(lutgen_remapper* r) {
         cudaFree(r->nn_table);
         cudaFree(r->flag_list);
         cudaFree(r->flag_count);
+        cudaFree(r->full_table);
+        cudaFree(r->upal_rgb4);
+        cudaFree(r->upal_ab);
+        cudaFree(r->upal_lab32);
+        cudaFree(r->upal_lab);
+        if (r->nn_table_ev) cudaEventDestroy(r->nn_table_ev);
+        if (r->full_table_ev) cudaEventDestroy(r->full_table_ev);
     }
     delete r;
     return LUTGEN_OK;
@@ -622,8 +792,34 @@ int lutgen_cuda_remapper_create(const lutgen_remapper_desc* desc, lutgen_remappe
             if (rc2) return bail(rc2);
         }
     }
+    if (desc->kind == LUTGEN_NEAREST || desc->kind == LUTGEN_SAMPLING) {
+        // unique colours, first occurrence kept (see lutgen_remapper::un)
+        std::vector<uint8_t> u4;
+        std::vector<uint32_t> seen;
+        for (size_t i = 0; i < n; ++i) {
+            uint32_t key = rgb4[4 * i] | (rgb4[4 * i + 1] << 8) | (rgb4[4 * i + 2] << 16);
+            bool dup = false;
+            for (uint32_t s2 : seen) dup |= (s2 == key);
+            if (dup) continue;
+            seen.push_back(key);
+            u4.insert(u4.end(), {rgb4[4 * i], rgb4[4 * i + 1], rgb4[4 * i + 2], 0});
+        }
+        r->un = (uint32_t)seen.size();
+        size_t ua = r->un ? r->un : 1;
+        CU_TRY_R(cudaMalloc((void**)&r->upal_rgb4, 4 * ua));
+        CU_TRY_R(cudaMalloc((void**)&r->upal_lab, sizeof(double) * 3 * ua));
+        CU_TRY_R(cudaMalloc((void**)&r->upal_ab, sizeof(float) * 2 * ua));
+        CU_TRY_R(cudaMalloc((void**)&r->upal_lab32, sizeof(float4) * ua));
+        if (r->un) {
+            CU_TRY_R(cudaMemcpyAsync(r->upal_rgb4, u4.data(), 4 * (size_t)r->un, cudaMemcpyHostToDevice, g.stream));
+            k_palette_setup<<<blocks_for(r->un, 128), 128, 0, g.stream>>>(r->upal_rgb4, r->un, desc->lum_factor, g.tables->decode, r->upal_lab,
+                                                                          r->upal_ab, r->upal_lab32);
+            g_launches.fetch_add(1);
+            CU_TRY_R(cudaGetLastError());
+        }
+    }
     CU_TRY_R(cudaStreamSynchronize(g.stream));
-    r->fast_ok = false;
+    r->fast_ok = fast_path_supported(r);
 #undef CU_TRY_R
     *out = r;
     return LUTGEN_OK;
@@ -644,6 +840,11 @@ int lutgen_cuda_sampling_set_noise(lutgen_remapper* r, const double* noise) {
     std::lock_guard<std::mutex> lk(g.mu);
     std::vector<double> old = r->noise;
     r->noise.assign(noise, noise + r->noise.size());
+    {
+        std::lock_guard<std::mutex> lk2(r->mu);
+        r->full_table_ready = false;  // the tabulated remapper depends on the noise
+    }
+    CU_TRY(cudaDeviceSynchronize());
     rc = upload_offsets(r);
     if (rc) {
         r->noise = old;
@@ -739,6 +940,46 @@ int lutgen_cuda_remap_image(const lutgen_remapper* r, uint8_t* rgba, size_t npix
 }
 
 // ---------------------------------------------------------------------------
+// diagnostics
+// ---------------------------------------------------------------------------
+int lutgen_cuda_measure_peaks(double* fp32_tflops, double* mufu_tops) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!fp32_tflops || !mufu_tops) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(g.mu);
+    CU_TRY(g.misc.reserve(256));
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0));
+    CU_TRY(cudaEventCreate(&e1));
+    const int blocks = g.sm_count * 8, iters = 4096;
+    float ms = 0.f;
+    double best_fma = 0.0, best_mufu = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU_TRY(cudaEventRecord(e0, g.stream));
+        k_peak_fma<<<blocks, 256, 0, g.stream>>>((float*)g.misc.p, iters, 0.999f, 0.001f);
+        LAUNCH_CHECK();
+        CU_TRY(cudaEventRecord(e1, g.stream));
+        CU_TRY(cudaEventSynchronize(e1));
+        CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        double tf = (double)blocks * 256 * iters * 64 * 2 / (ms * 1e-3) / 1e12;
+        if (rep && tf > best_fma) best_fma = tf;
+        CU_TRY(cudaEventRecord(e0, g.stream));
+        k_peak_mufu<<<blocks, 256, 0, g.stream>>>((float*)g.misc.p, iters / 4);
+        LAUNCH_CHECK();
+        CU_TRY(cudaEventRecord(e1, g.stream));
+        CU_TRY(cudaEventSynchronize(e1));
+        CU_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        double tm = (double)blocks * 256 * (iters / 4) * 64 / (ms * 1e-3) / 1e12;
+        if (rep && tm > best_mufu) best_mufu = tm;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *fp32_tflops = best_fma;
+    *mufu_tops = best_mufu;
+    return LUTGEN_OK;
+}
+
+// ---------------------------------------------------------------------------
 // oklab
 // ---------------------------------------------------------------------------
 int lutgen_cuda_srgb_to_oklab(const uint8_t* rgb, size_t n, float* out_lab) {
@@ -752,6 +993,34 @@ int lutgen_cuda_srgb_to_oklab(const uint8_t* rgb, size_t n, float* out_lab) {
     uint8_t* din = (uint8_t*)g.misc.p + 12 * n;
     CU_TRY(cudaMemcpyAsync(din, rgb, 3 * n, cudaMemcpyHostToDevice, g.stream));
     k_srgb_to_oklab<<<blocks_for(n, 256), 256, 0, g.stream>>>(din, n, dout, g.tables);
+    LAUNCH_CHECK();
+    CU_TRY(cudaMemcpyAsync(out_lab, dout, 12 * n, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_debug_stats(uint32_t* out128, int reset) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!out128) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    if (!g.stats) return fail(LUTGEN_ERR_UNSUPPORTED, "set LUTGEN_CUDA_STATS=1 before lutgen_cuda_init");
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(out128, g.stats, 128 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (reset) CU_TRY(cudaMemset(g.stats, 0, 128 * sizeof(uint32_t)));
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_srgb_to_oklab_fast(const uint8_t* rgb, size_t n, float* out_lab) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (n && (!rgb || !out_lab)) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    if (n == 0) return LUTGEN_OK;
+    std::lock_guard<std::mutex> lk(g.mu);
+    CU_TRY(g.misc.reserve(16 * n));
+    float* dout = (float*)g.misc.p;
+    uint8_t* din = (uint8_t*)g.misc.p + 12 * n;
+    CU_TRY(cudaMemcpyAsync(din, rgb, 3 * n, cudaMemcpyHostToDevice, g.stream));
+    k_srgb_to_oklab_fast<<<blocks_for(n, 256), 256, 0, g.stream>>>(din, n, dout, g.tables);
     LAUNCH_CHECK();
     CU_TRY(cudaMemcpyAsync(out_lab, dout, 12 * n, cudaMemcpyDeviceToHost, g.stream));
     CU_TRY(cudaStreamSynchronize(g.stream));

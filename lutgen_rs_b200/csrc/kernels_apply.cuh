@@ -165,4 +165,35 @@ __global__ void __launch_bounds__(256) k_sampling(Front f, const uint32_t* __res
     front_store<MODE>(f, px, r, g, b);
 }
 
+// ---------------------------------------------------------------------------
+// Diagnostics: on-box FP32 FMA and MUFU peak (the generation kernels' roofline
+// denominators must be MEASURED at the clocks this GPU sustains, SURVEY.md
+// hard part 10). 8 independent dependency chains per thread.
+__global__ void __launch_bounds__(256) k_peak_fma(float* __restrict__ sink, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456f) sink[0] = s;
+}
+__global__ void __launch_bounds__(256) k_peak_mufu(float* __restrict__ sink, int iters) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + .1f, x2 = x0 + .2f, x3 = x0 + .3f;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = ex2_approx(x0); x1 = ex2_approx(x1); x2 = ex2_approx(x2); x3 = ex2_approx(x3);
+            x0 = lg2_approx(x0); x1 = lg2_approx(x1); x2 = lg2_approx(x2); x3 = lg2_approx(x3);
+        }
+    }
+    float s = (x0 + x1) + (x2 + x3);
+    if (s == 123.456f) sink[0] = s;
+}
+
 }  // namespace lutgen

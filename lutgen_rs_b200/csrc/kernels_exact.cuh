@@ -19,8 +19,9 @@ enum FrontMode { FRONT_LUT = 0, FRONT_IMAGE = 1, FRONT_TABLE = 2, FRONT_LIST = 3
 //  FRONT_IMAGE : pixel i of an RGBA8 buffer, in place, alpha kept (mod.rs:30-50)
 //  FRONT_TABLE : colour i of the full 2^24 sRGB cube (r = i & 255, g, b);
 //                result -> ((uint32_t*)out)[i] = r | g<<8 | b<<16
-//  FRONT_LIST  : like FRONT_LUT/IMAGE, but i indexes `list` (entry / pixel ids
-//                flagged by the fast kernel); list_is_image selects the layout.
+//  FRONT_LIST  : the colours are the entry / pixel / table ids in `list` (flagged by the
+//                fast kernel); list_mode (FRONT_LUT / FRONT_IMAGE / FRONT_TABLE) selects
+//                how an id maps to a colour and where the result is stored.
 struct Front {
     uint8_t* out;
     unsigned long long begin;
@@ -29,7 +30,7 @@ struct Front {
     uint32_t csm1;   // level^2 - 1
     const uint32_t* list;
     const uint32_t* list_count;
-    int list_is_image;
+    int list_mode;
 };
 
 struct RemapParams {
@@ -45,50 +46,41 @@ struct RemapParams {
 
 struct PixelIO {
     uint32_t r, g, b;
-    unsigned long long slot;  // entry index (LUT) or pixel index (IMAGE/TABLE)
-    bool image;
+    unsigned long long slot;  // entry index (LUT), pixel index (IMAGE) or colour (TABLE)
+    int mode;                 // FRONT_LUT / FRONT_IMAGE / FRONT_TABLE
 };
 
+__device__ __forceinline__ void front_decode(const Front& f, int mode, unsigned long long id, PixelIO& p) {
+    p.slot = id;
+    p.mode = mode;
+    if (mode == FRONT_IMAGE) {
+        uchar4 v = reinterpret_cast<const uchar4*>(f.out)[id];
+        p.r = v.x; p.g = v.y; p.b = v.z;
+    } else if (mode == FRONT_TABLE) {
+        p.r = (uint32_t)(id & 255u); p.g = (uint32_t)((id >> 8) & 255u); p.b = (uint32_t)((id >> 16) & 255u);
+    } else {
+        uint32_t red = (uint32_t)(id % f.cs), green = (uint32_t)((id / f.cs) % f.cs), blue = (uint32_t)(id / ((unsigned long long)f.cs * f.cs));
+        p.r = hald_channel(red, f.csm1); p.g = hald_channel(green, f.csm1); p.b = hald_channel(blue, f.csm1);
+    }
+}
+
+// Colour number i of this launch (false: past the end).
 template <int MODE>
 __device__ __forceinline__ bool front_load(const Front& f, unsigned long long i, PixelIO& p) {
     if (MODE == FRONT_LIST) {
         if (i >= (unsigned long long)*f.list_count) return false;
-        unsigned long long id = f.list[i];
-        p.slot = id;
-        p.image = f.list_is_image != 0;
-        if (p.image) {
-            uchar4 v = reinterpret_cast<const uchar4*>(f.out)[id];
-            p.r = v.x; p.g = v.y; p.b = v.z;
-        } else {
-            uint32_t red = (uint32_t)(id % f.cs), green = (uint32_t)((id / f.cs) % f.cs), blue = (uint32_t)(id / ((unsigned long long)f.cs * f.cs));
-            p.r = hald_channel(red, f.csm1); p.g = hald_channel(green, f.csm1); p.b = hald_channel(blue, f.csm1);
-        }
+        front_decode(f, f.list_mode, f.list[i], p);
         return true;
     }
     if (i >= f.count) return false;
-    if (MODE == FRONT_LUT) {
-        unsigned long long e = f.begin + i;
-        uint32_t red = (uint32_t)(e % f.cs), green = (uint32_t)((e / f.cs) % f.cs), blue = (uint32_t)(e / ((unsigned long long)f.cs * f.cs));
-        p.r = hald_channel(red, f.csm1); p.g = hald_channel(green, f.csm1); p.b = hald_channel(blue, f.csm1);
-        p.slot = e; p.image = false;
-    } else if (MODE == FRONT_IMAGE) {
-        unsigned long long e = f.begin + i;
-        uchar4 v = reinterpret_cast<const uchar4*>(f.out)[e];
-        p.r = v.x; p.g = v.y; p.b = v.z;
-        p.slot = e; p.image = true;
-    } else {
-        unsigned long long e = f.begin + i;
-        p.r = (uint32_t)(e & 255u); p.g = (uint32_t)((e >> 8) & 255u); p.b = (uint32_t)((e >> 16) & 255u);
-        p.slot = e; p.image = false;
-    }
+    front_decode(f, MODE, f.begin + i, p);
     return true;
 }
 
-template <int MODE>
-__device__ __forceinline__ void front_store(const Front& f, const PixelIO& p, uint32_t r, uint32_t g, uint32_t b) {
-    if (MODE == FRONT_TABLE) {
+__device__ __forceinline__ void front_store_mode(const Front& f, int mode, const PixelIO& p, uint32_t r, uint32_t g, uint32_t b) {
+    if (mode == FRONT_TABLE) {
         reinterpret_cast<uint32_t*>(f.out)[p.slot] = r | (g << 8) | (b << 16);
-    } else if (MODE == FRONT_IMAGE || (MODE == FRONT_LIST && p.image)) {
+    } else if (mode == FRONT_IMAGE) {
         uchar4* q = reinterpret_cast<uchar4*>(f.out) + p.slot;
         uchar4 v = *q;
         v.x = (unsigned char)r; v.y = (unsigned char)g; v.z = (unsigned char)b;
@@ -97,6 +89,18 @@ __device__ __forceinline__ void front_store(const Front& f, const PixelIO& p, ui
         uint8_t* q = f.out + 3ull * p.slot;
         q[0] = (uint8_t)r; q[1] = (uint8_t)g; q[2] = (uint8_t)b;
     }
+}
+
+template <int MODE>
+__device__ __forceinline__ void front_store(const Front& f, const PixelIO& p, uint32_t r, uint32_t g, uint32_t b) {
+    front_store_mode(f, MODE == FRONT_LIST ? p.mode : MODE, p, r, g, b);
+}
+
+// Threads of a launch walk colours i, i + stride, ...: one colour each for the direct front-ends
+// (the grid covers the range), a grid-stride loop for FRONT_LIST (its length lives on the device).
+template <int MODE>
+__device__ __forceinline__ unsigned long long front_stride() {
+    return MODE == FRONT_LIST ? (unsigned long long)gridDim.x * blockDim.x : ~0ull >> 1;
 }
 
 // ---------------------------------------------------------------------------
@@ -172,25 +176,25 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_nn_exact(Front f, RemapParams P, const ColorTables* __restrict__ tables) {
     __shared__ SmemTables st;
     stage_tables(st, tables);
-    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     PixelIO px;
-    if (!front_load<MODE>(f, i, px)) return;
-    Lab c = linear_to_oklab_exact(st.decode[px.r], st.decode[px.g], st.decode[px.b]);
-    double c0 = __dmul_rn((double)c.l, P.lum), c1 = (double)c.a, c2 = (double)c.b;
-    uint32_t best = 0;
-    double bd = INFINITY;
-    for (uint32_t j = 0; j < P.n; ++j) {
-        double d = sq_dist_exact(c0, c1, c2, P.pal_lab + 3 * j);
-        if (d < bd) { bd = d; best = j; }
-    }
-    if (!P.preserve) {
-        const uint8_t* q = P.pal_rgb + 4 * best;
-        front_store<MODE>(f, px, q[0], q[1], q[2]);
-    } else {
-        Lab o = {c.l, P.pal_ab[2 * best], P.pal_ab[2 * best + 1]};
-        float r, g, b;
-        oklab_to_linear_exact(o, r, g, b);
-        front_store<MODE>(f, px, f32_to_srgb8(r, st.encode), f32_to_srgb8(g, st.encode), f32_to_srgb8(b, st.encode));
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; front_load<MODE>(f, i, px); i += front_stride<MODE>()) {
+        Lab c = linear_to_oklab_exact(st.decode[px.r], st.decode[px.g], st.decode[px.b]);
+        double c0 = __dmul_rn((double)c.l, P.lum), c1 = (double)c.a, c2 = (double)c.b;
+        uint32_t best = 0;
+        double bd = INFINITY;
+        for (uint32_t j = 0; j < P.n; ++j) {
+            double d = sq_dist_exact(c0, c1, c2, P.pal_lab + 3 * j);
+            if (d < bd) { bd = d; best = j; }
+        }
+        if (!P.preserve) {
+            const uint8_t* q = P.pal_rgb + 4 * best;
+            front_store<MODE>(f, px, q[0], q[1], q[2]);
+        } else {
+            Lab o = {c.l, P.pal_ab[2 * best], P.pal_ab[2 * best + 1]};
+            float r, g, b;
+            oklab_to_linear_exact(o, r, g, b);
+            front_store<MODE>(f, px, f32_to_srgb8(r, st.encode), f32_to_srgb8(g, st.encode), f32_to_srgb8(b, st.encode));
+        }
     }
 }
 
@@ -207,12 +211,7 @@ __device__ __forceinline__ double radial_basis_exact(double d, double param) {
 // in ascending lexicographic order, so the f64 accumulation order equals the
 // oracle's (kiddo returns neighbours by ascending distance).
 template <int KIND, int MODE>
-__global__ void __launch_bounds__(256) k_rbf_exact(Front f, RemapParams P, const ColorTables* __restrict__ tables) {
-    __shared__ SmemTables st;
-    stage_tables(st, tables);
-    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    PixelIO px;
-    if (!front_load<MODE>(f, i, px)) return;
+__device__ __forceinline__ void rbf_exact_one(const Front& f, const RemapParams& P, const SmemTables& st, const PixelIO& px) {
     Lab c = linear_to_oklab_exact(st.decode[px.r], st.decode[px.g], st.decode[px.b]);
     double c0 = __dmul_rn((double)c.l, P.lum), c1 = (double)c.a, c2 = (double)c.b;
     const uint32_t n = P.n;
@@ -223,7 +222,7 @@ __global__ void __launch_bounds__(256) k_rbf_exact(Front f, RemapParams P, const
         hit |= (p[0] == c0 && p[1] == c1 && p[2] == c2);
     }
     if (hit) {
-        if (MODE == FRONT_LUT || MODE == FRONT_TABLE || (MODE == FRONT_LIST && !px.image)) front_store<MODE>(f, px, px.r, px.g, px.b);
+        if ((MODE == FRONT_LIST ? px.mode : MODE) != FRONT_IMAGE) front_store<MODE>(f, px, px.r, px.g, px.b);
         return;
     }
     double n0 = 0.0, n1 = 0.0, n2 = 0.0, den = 0.0;
@@ -265,6 +264,15 @@ __global__ void __launch_bounds__(256) k_rbf_exact(Front f, RemapParams P, const
     float r, g, b;
     oklab_to_linear_exact(o, r, g, b);
     front_store<MODE>(f, px, f32_to_srgb8(r, st.encode), f32_to_srgb8(g, st.encode), f32_to_srgb8(b, st.encode));
+}
+
+template <int KIND, int MODE>
+__global__ void __launch_bounds__(256) k_rbf_exact(Front f, RemapParams P, const ColorTables* __restrict__ tables) {
+    __shared__ SmemTables st;
+    stage_tables(st, tables);
+    PixelIO px;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; front_load<MODE>(f, i, px); i += front_stride<MODE>())
+        rbf_exact_one<KIND, MODE>(f, P, st, px);
 }
 
 // oklab::srgb_to_oklab / oklab_to_srgb for arrays (C ABI utility + parity tests).

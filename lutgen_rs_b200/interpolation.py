@@ -92,15 +92,20 @@ class InterpolatedRemapper:
     par_remap_image_with_interrupt = remap_image_with_interrupt
 
     # -- GenerateLut ---------------------------------------------------------
-    def generate_lut(self, level):
-        return self.generate_lut_with_interrupt(level, None)
+    def generate_lut(self, level, out=None):
+        return self.generate_lut_with_interrupt(level, None, out=out)
 
-    def generate_lut_with_interrupt(self, level, abort):
+    def generate_lut_with_interrupt(self, level, abort, out=None):
+        """`out` (optional, not in the reference): a preallocated (n, n, 3) uint8 array to fill,
+        e.g. page-locked memory so the device-to-host copy is a single DMA."""
         level = int(level)
         if not 0 <= level <= 255:
             raise OverflowError("level is a u8")
         n = level ** 3 if 2 <= level <= 33 else 1
-        out = np.empty((n, n, 3), np.uint8)
+        if out is None:
+            out = np.empty((n, n, 3), np.uint8)
+        elif out.dtype != np.uint8 or out.size != 3 * n * n or not out.flags.c_contiguous:
+            raise TypeError("out must be a contiguous uint8 array of 3*level^6 bytes")
         aborted = _native.check(_native.lib().lutgen_cuda_generate_lut(self._h, level, _ptr(out), _abort_ptr(abort)))
         return None if aborted else out
 

@@ -307,3 +307,117 @@ def test_interrupt_semantics(palettes):
     before = img.copy()
     r.par_remap_image_with_interrupt(img, flag)  # flag set: every pixel skipped (mod.rs:54-60)
     assert (img == before).all()
+
+
+# ------------------------------------------------------------ fast path vs exact path
+def _exact_only(monkeypatch, on):
+    if on:
+        monkeypatch.setenv("LUTGEN_CUDA_EXACT_ONLY", "1")
+    else:
+        monkeypatch.delenv("LUTGEN_CUDA_EXACT_ONLY", raising=False)
+
+
+def test_fast_oklab_within_tile_padding():
+    """The tile bounds are padded by 2e-5; the fast f32 conversion must stay well inside that."""
+    import ctypes as C
+    from lutgen_rs_b200 import _native
+    L = _native.lib()
+    worst = 0.0
+    step = 1 << 22
+    for start in range(0, 1 << 24, step):
+        i = np.arange(start, start + step, dtype=np.uint32)
+        rgb = np.stack([i & 255, (i >> 8) & 255, i >> 16], 1).astype(np.uint8)
+        fast = np.empty((step, 3), np.float32)
+        exact = np.empty((step, 3), np.float32)
+        _native.check(L.lutgen_cuda_srgb_to_oklab_fast(C.c_void_p(rgb.ctypes.data), step, C.c_void_p(fast.ctypes.data)))
+        _native.check(L.lutgen_cuda_srgb_to_oklab(C.c_void_p(rgb.ctypes.data), step, C.c_void_p(exact.ctypes.data)))
+        worst = max(worst, float(np.abs(fast.astype(np.float64) - exact.astype(np.float64)).max()))
+    assert worst < 3e-6, worst
+
+
+@pytest.mark.parametrize("lum,preserve", [(1.0, False), (0.7, True)])
+def test_level16_nearest_neighbor_fast_equals_exact(palettes, monkeypatch, lum, preserve):
+    """Full-size CLUT (16.7M entries): the tile-bounded kernel and the f64 brute-force kernel
+    must agree on every byte (NearestNeighbor is the bit-exact row)."""
+    pal = palettes["catppuccin_mocha"]
+    _exact_only(monkeypatch, True)
+    exact = interpolation.NearestNeighborRemapper(pal, lum, preserve).generate_lut(16)
+    _exact_only(monkeypatch, False)
+    fast = interpolation.NearestNeighborRemapper(pal, lum, preserve).generate_lut(16)
+    assert (fast == exact).all()
+    # idempotence at full size: every CLUT colour is a palette colour (preserve off)
+    if not preserve:
+        cols = np.unique(fast.reshape(-1, 3), axis=0)
+        assert set(map(tuple, cols.tolist())) <= set(map(tuple, pal.tolist()))
+
+
+@pytest.mark.parametrize("cls,param,nearest,pal_kind", [
+    (interpolation.GaussianRemapper, 128.0, 16, "builtin"),
+    (interpolation.ShepardRemapper, 4.0, 16, "synthetic256"),
+    (interpolation.GaussianRemapper, 96.0, 0, "builtin"),
+])
+def test_level16_rbf_fast_vs_exact_within_1lsb(palettes, monkeypatch, cls, param, nearest, pal_kind):
+    """BASELINE configs 1/3 at the full 4096x4096: fast f32 kernel vs the f64 kernel, +-1 LSB."""
+    pal = palettes["catppuccin_mocha"] if pal_kind == "builtin" else synthetic_palette(256, seed=1)
+    _exact_only(monkeypatch, True)
+    exact = cls(pal, param, nearest, 1.0, False).generate_lut(16)
+    _exact_only(monkeypatch, False)
+    fast = cls(pal, param, nearest, 1.0, False).generate_lut(16)
+    d = _diff(fast, exact)
+    assert d.max() <= 1, (int(d.max()), int((d > 1).sum()))
+    assert (d > 0).mean() < 2e-3, float((d > 0).mean())
+    # and a strided 1/64 sample against the CPU oracle itself
+    okind = O.GAUSSIAN if cls is interpolation.GaussianRemapper else O.SHEPARD
+    orc = O.Remapper(okind, pal, param=param, nearest=nearest, lum_factor=1.0, preserve=False)
+    rows = list(range(0, 4096, 64))
+    for r0 in rows[::8]:
+        want = orc.generate_lut(16, rows=(r0, r0 + 1))[r0]
+        assert _diff(fast[r0], want).max() <= 1
+
+
+def test_row_shards_tile_the_whole_lut(palettes):
+    """Multi-GPU unit: any split of the rows reproduces the single-launch CLUT byte for byte."""
+    import torch
+    from lutgen_rs_b200 import device
+    device.init(0)
+    pal = palettes["nord"]
+    for level, cuts in ((8, [0, 1, 100, 101, 300, 512]), (5, [0, 7, 64, 125]), (16, [0, 512, 1000, 4096])):
+        r = interpolation.GaussianRemapper(pal, 128.0, 16, 1.0, False)
+        whole = torch.from_numpy(r.generate_lut(level)).reshape(-1)
+        lut = torch.zeros(3 * level ** 6, dtype=torch.uint8, device="cuda")
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            device.generate_lut_rows_(r, level, lut, a, b)
+        torch.cuda.synchronize()
+        assert torch.equal(lut.cpu(), whole)
+
+
+def test_large_image_goes_through_the_colour_cube(palettes, monkeypatch):
+    """remap_image on >= 2^20 pixels tabulates the remapper over the sRGB cube and gathers; the
+    result must equal the per-pixel kernels' (same bytes for NN, +-1 LSB for RBF)."""
+    pal = palettes["catppuccin_mocha"]
+    img = random_rgba((1 << 20) + 12345, seed=77).reshape(1, -1, 4)
+    for make, exact_bytes in ((lambda: interpolation.NearestNeighborRemapper(pal, 1.0, False), True),
+                              (lambda: interpolation.GaussianRemapper(pal, 128.0, 16, 1.0, False), False)):
+        monkeypatch.setenv("LUTGEN_CUDA_NO_TABLE", "1")
+        direct = img.copy()
+        make().remap_image(direct)
+        monkeypatch.delenv("LUTGEN_CUDA_NO_TABLE")
+        via = img.copy()
+        make().remap_image(via)
+        d = _diff(via, direct)
+        assert d.max() <= (0 if exact_bytes else 1)
+        assert (via[..., 3] == img[..., 3]).all()
+    sample = img[:, :20000]
+    want = O.Remapper(O.NEAREST, pal, lum_factor=1.0).remap_image(sample)
+    got = img.copy()
+    interpolation.NearestNeighborRemapper(pal, 1.0, False).remap_image(got)
+    assert (got[:, :20000] == want).all()
+
+
+def test_duplicate_palette_colours(palettes):
+    """A palette with repeated colours (4 built-ins have them): NN stays bit exact, RBF +-1 LSB."""
+    pal = np.concatenate([palettes["nord"], palettes["nord"][:5], palettes["nord"][3:4]])
+    want = O.Remapper(O.NEAREST, pal, lum_factor=1.0).generate_lut(8)
+    assert (interpolation.NearestNeighborRemapper(pal, 1.0, False).generate_lut(8) == want).all()
+    d = _rbf_case(interpolation.GaussianRemapper, O.GAUSSIAN, pal, 8, 128.0, 16, 1.0, False)
+    assert d.max() <= 1
