@@ -285,6 +285,7 @@ int launch_fast(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
     a.c1 = KIND == 0 ? (float)(-r->d.param * 1.4426950408889634) : (KIND == 1 ? (float)(-0.5 * r->d.param) : 0.0f);
     a.flag_list = r->flag_list;
     a.flag_count = r->flag_count;
+    a.tile_counter = r->flag_count + 1;
     a.tables = g.tables;
     unsigned grid;
     if (MODE == FRONT_IMAGE) {
@@ -321,7 +322,14 @@ int launch_fast(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
         CU_TRY(cudaFuncSetAttribute(k_remap_fast<KIND, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         attr_done = true;
     }
-    CU_TRY(cudaMemsetAsync(r->flag_count, 0, sizeof(uint32_t), s));
+    // persistent CTAs: as many as fit on the device at once, striding over the tiles
+    a.ntiles = grid;
+    int per_sm = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_remap_fast<KIND, MODE>, FAST_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    unsigned resident = (unsigned)per_sm * (unsigned)g.sm_count;
+    if (grid > resident) grid = resident;
+    CU_TRY(cudaMemsetAsync(r->flag_count, 0, 2 * sizeof(uint32_t), s));
     k_remap_fast<KIND, MODE><<<grid, FAST_THREADS, smem, s>>>(a);
     LAUNCH_CHECK();
     Front fl = f;

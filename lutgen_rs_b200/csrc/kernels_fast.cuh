@@ -54,8 +54,10 @@ struct FastArgs {
     uint32_t tiles_r, tiles_g;
     uint32_t b_lo;            // first blue plane covered by the grid (multiple of tb)
     uint32_t ept;             // entries per thread
+    uint32_t ntiles;          // tiles in this launch (CTAs stride over them)
     uint32_t* flag_list;
     uint32_t* flag_count;
+    uint32_t* tile_counter;   // zeroed before the launch
     uint32_t* stats;          // optional [128]: histogram of |UNCERTAIN| and |IN| per tile
     const ColorTables* tables;
 };
@@ -186,14 +188,25 @@ __host__ __device__ inline size_t fast_smem_bytes(uint32_t n, uint32_t tile) {
     return (size_t)n * (16 + 16 + 4 + 4 + 4) + (size_t)tile * 16 + 64;
 }
 
+// Negligibility test of step 4 for a colour whose distance is at least `lb`, against the tile's
+// guaranteed-nearest distance `ubmin` (log2 of it in lg_ubmin for Shepard).
+template <int KIND>
+__device__ __forceinline__ bool negligible_at(float lb, float ubmin, float lg_ubmin, float c1) {
+    if (KIND == 0) return c1 < 0.f && c1 * (lb - ubmin) < FAST_NEGLIGIBLE_LOG2;
+    if (KIND == 1) return c1 < 0.f && lb > 0.f && ubmin > 0.f && c1 * (lg2_approx(lb) - lg_ubmin) < FAST_NEGLIGIBLE_LOG2 - 1e-3f;
+    return false;
+}
+
+// Persistent CTAs: the grid is a few CTAs per SM; each stages the colour tables and the palette
+// once and then walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
 template <int KIND, int MODE>
-__global__ void __launch_bounds__(FAST_THREADS) k_remap_fast(const FastArgs a) {
+__global__ void __launch_bounds__(FAST_THREADS, 4) k_remap_fast(const FastArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ SmemTables st;
     __shared__ uint32_t s_box[12];        // Oklab min keys [0..3), max keys [3..6), sRGB min [6..9), max [9..12)
-    __shared__ uint32_t s_lbmin, s_ubmin, s_uk;
+    __shared__ uint32_t s_lbmin, s_ubmin, s_uk, s_lk;
     __shared__ uint32_t s_wcnt[2][FAST_THREADS / 32];
-    __shared__ uint32_t s_nhit;
+    __shared__ uint32_t s_nhit, s_next;
     __shared__ uint32_t s_hit[FAST_MAX_HITS];
     __shared__ uint32_t s_chan[3][16];    // identity channel value of each brick coordinate
 
@@ -207,285 +220,299 @@ __global__ void __launch_bounds__(FAST_THREADS) k_remap_fast(const FastArgs a) {
     float* s_lab = reinterpret_cast<float*>(s_cidx + n);
     uint32_t* s_rgb = reinterpret_cast<uint32_t*>(s_lab + 3 * tile);
 
-    // ---- tile geometry ------------------------------------------------------------------
-    uint32_t r0 = 0, g0 = 0, b0 = 0;
     const uint32_t cs = a.f.cs, csm1 = a.f.csm1;
-    unsigned long long img_base = 0;
-    if (MODE == FRONT_IMAGE) {
-        img_base = (unsigned long long)blockIdx.x * tile;
-    } else {
-        uint32_t bid = blockIdx.x;
-        uint32_t ir = bid % a.tiles_r, ig = (bid / a.tiles_r) % a.tiles_g, ib = bid / (a.tiles_r * a.tiles_g);
-        r0 = ir << a.sh_r; g0 = ig << a.sh_g; b0 = a.b_lo + ib * a.tb;
-        // whole tile outside the requested entry range: nothing to do
-        unsigned long long first = ((unsigned long long)b0 * cs + g0) * cs + r0;
-        unsigned long long last = ((unsigned long long)min(b0 + a.tb - 1, csm1) * cs + min(g0 + a.tg - 1, csm1)) * cs + min(r0 + a.tr - 1, csm1);
-        if (last < a.f.begin || first >= a.f.begin + a.f.count) return;
-        if (tid < 48) {
+    const uint32_t begin = (uint32_t)a.f.begin, end = (uint32_t)(a.f.begin + a.f.count);  // < 2^32 by construction
+    const uint32_t lr = tid & (a.tr - 1), lg = (tid >> a.sh_r) & (a.tg - 1);
+    const uint32_t lb_step = FAST_THREADS >> (a.sh_r + a.sh_g), lb0 = tid >> (a.sh_r + a.sh_g);
+    const uint32_t k = a.k;
+    const float c1 = a.c1;
+
+    for (uint32_t i = tid; i < n; i += FAST_THREADS) s_pal[i] = a.pal[i];
+    stage_tables(st, a.tables);  // ends with __syncthreads()
+
+    // Tiles differ a lot in cost (0 to 30 uncertain colours), so they are handed out dynamically:
+    // the first wave is blockIdx.x, later ones come from a device-wide counter.
+    for (uint32_t bid = blockIdx.x; bid < a.ntiles;) {
+        __syncthreads();  // previous tile's shared state (and s_next) is no longer read
+        if (tid == 0) s_next = gridDim.x + atomicAdd(a.tile_counter, 1u);
+        // ---- tile geometry --------------------------------------------------------------
+        uint32_t r0 = 0, g0 = 0, b0 = 0, img_base = 0;
+        if (MODE == FRONT_IMAGE) {
+            img_base = bid * tile;
+        } else {
+            uint32_t ir = bid % a.tiles_r, ig = (bid / a.tiles_r) % a.tiles_g, ib = bid / (a.tiles_r * a.tiles_g);
+            r0 = ir << a.sh_r; g0 = ig << a.sh_g; b0 = a.b_lo + ib * a.tb;
+            // whole tile outside the requested entry range: nothing to do
+            uint32_t first = (b0 * cs + g0) * cs + r0;
+            uint32_t last = (min(b0 + a.tb - 1, csm1) * cs + min(g0 + a.tg - 1, csm1)) * cs + min(r0 + a.tr - 1, csm1);
+            if (b0 > csm1 || last < begin || first >= end) { __syncthreads(); bid = s_next; continue; }
+        }
+        if (MODE != FRONT_IMAGE && tid < 48) {
             uint32_t c = tid >> 4, i = tid & 15;
             uint32_t v = min((c == 0 ? r0 : c == 1 ? g0 : b0) + i, csm1);
             s_chan[c][i] = MODE == FRONT_TABLE ? v : hald_channel(v, csm1);
         }
-    }
+        if (tid >= 64 && tid < 67) { s_box[tid - 64] = 0xffffffffu; s_box[6 + tid - 64] = 0xffffffffu; }
+        else if (tid >= 67 && tid < 70) { s_box[tid - 64] = 0u; s_box[6 + tid - 64] = 0u; }
+        if (tid == 96) { s_lbmin = 0x7f800000u; s_ubmin = 0x7f800000u; s_uk = 0x7f800000u; s_lk = 0x7f800000u; s_nhit = 0; }
+        __syncthreads();
 
-    for (uint32_t i = tid; i < n; i += FAST_THREADS) s_pal[i] = a.pal[i];
-    if (tid < 3) { s_box[tid] = 0xffffffffu; s_box[6 + tid] = 0xffffffffu; }
-    else if (tid < 6) { s_box[tid] = 0u; s_box[6 + tid] = 0u; }
-    if (tid == 0) { s_lbmin = 0x7f800000u; s_ubmin = 0x7f800000u; s_uk = 0x7f800000u; s_nhit = 0; }
-    stage_tables(st, a.tables);  // ends with __syncthreads()
-
-    // ---- 1. colours of this tile -> Oklab, bounding box --------------------------------
-    uint32_t kmin[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, kmax[3] = {0u, 0u, 0u};
-    uint32_t cmin[3] = {255u, 255u, 255u}, cmax[3] = {0u, 0u, 0u};
-    uint32_t valid_mask = 0;
-    const uint32_t lr = tid & (a.tr - 1), lg = (tid >> a.sh_r) & (a.tg - 1);
-    const uint32_t lb_step = FAST_THREADS >> (a.sh_r + a.sh_g), lb0 = tid >> (a.sh_r + a.sh_g);
-    for (uint32_t e = 0; e < a.ept; ++e) {
-        uint32_t li = e * FAST_THREADS + tid;
-        uint32_t R, G, B;
-        // `valid`: this thread must produce the colour; `in_tile`: the colour belongs to the tile's
-        // geometry. The bounding box is taken over in_tile so that the classification -- hence
-        // every byte of the result -- does not depend on how the rows were sharded.
-        bool valid, in_tile;
-        if (MODE == FRONT_IMAGE) {
-            unsigned long long pix = img_base + li;
-            valid = in_tile = pix < a.f.count;
-            uchar4 v = valid ? reinterpret_cast<const uchar4*>(a.f.out)[pix] : make_uchar4(0, 0, 0, 0);
-            R = v.x; G = v.y; B = v.z;
-        } else {
-            uint32_t lb = lb0 + e * lb_step;
-            uint32_t r = r0 + lr, g = g0 + lg, b = b0 + lb;
-            unsigned long long flat = ((unsigned long long)b * cs + g) * cs + r;
-            in_tile = r < cs && g < cs && b < cs && lb < a.tb;
-            valid = in_tile && flat >= a.f.begin && flat < a.f.begin + a.f.count;
-            R = s_chan[0][lr]; G = s_chan[1][lg]; B = s_chan[2][lb & 15];
+        // ---- 1. colours of this tile -> Oklab, bounding box ----------------------------
+        uint32_t kmin[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, kmax[3] = {0u, 0u, 0u};
+        uint32_t cmin[3] = {255u, 255u, 255u}, cmax[3] = {0u, 0u, 0u};
+        uint32_t valid_mask = 0;
+        for (uint32_t e = 0; e < a.ept; ++e) {
+            uint32_t li = e * FAST_THREADS + tid;
+            uint32_t R, G, B;
+            // `valid`: this thread must produce the colour; `in_tile`: the colour belongs to the
+            // tile's geometry. The bounding box is taken over in_tile so that the classification --
+            // hence every byte of the result -- does not depend on how the rows were sharded.
+            bool valid, in_tile;
+            if (MODE == FRONT_IMAGE) {
+                uint32_t pix = img_base + li;
+                valid = in_tile = pix < end;
+                uchar4 v = valid ? reinterpret_cast<const uchar4*>(a.f.out)[pix] : make_uchar4(0, 0, 0, 0);
+                R = v.x; G = v.y; B = v.z;
+            } else {
+                uint32_t lb = lb0 + e * lb_step;
+                uint32_t r = r0 + lr, g = g0 + lg, b = b0 + lb;
+                uint32_t flat = (b * cs + g) * cs + r;
+                in_tile = r < cs && g < cs && b < cs && lb < a.tb;
+                valid = in_tile && flat >= begin && flat < end;
+                R = s_chan[0][lr]; G = s_chan[1][lg]; B = s_chan[2][lb & 15];
+            }
+            Lab c = linear_to_oklab_fast(st.decode[R], st.decode[G], st.decode[B]);
+            float Lp = c.l * a.lum;
+            s_lab[li] = Lp;
+            s_lab[tile + li] = c.a;
+            s_lab[2 * tile + li] = c.b;
+            s_rgb[li] = R | (G << 8) | (B << 16);
+            if (valid) valid_mask |= 1u << e;
+            if (in_tile) {
+                uint32_t k0 = f2key(Lp), k1 = f2key(c.a), k2 = f2key(c.b);
+                kmin[0] = min(kmin[0], k0); kmax[0] = max(kmax[0], k0);
+                kmin[1] = min(kmin[1], k1); kmax[1] = max(kmax[1], k1);
+                kmin[2] = min(kmin[2], k2); kmax[2] = max(kmax[2], k2);
+                cmin[0] = min(cmin[0], R); cmax[0] = max(cmax[0], R);
+                cmin[1] = min(cmin[1], G); cmax[1] = max(cmax[1], G);
+                cmin[2] = min(cmin[2], B); cmax[2] = max(cmax[2], B);
+            }
         }
-        Lab c = linear_to_oklab_fast(st.decode[R], st.decode[G], st.decode[B]);
-        float Lp = c.l * a.lum;
-        s_lab[li] = Lp;
-        s_lab[tile + li] = c.a;
-        s_lab[2 * tile + li] = c.b;
-        s_rgb[li] = R | (G << 8) | (B << 16);
-        if (valid) valid_mask |= 1u << e;
-        if (in_tile) {
-            uint32_t k0 = f2key(Lp), k1 = f2key(c.a), k2 = f2key(c.b);
-            kmin[0] = min(kmin[0], k0); kmax[0] = max(kmax[0], k0);
-            kmin[1] = min(kmin[1], k1); kmax[1] = max(kmax[1], k1);
-            kmin[2] = min(kmin[2], k2); kmax[2] = max(kmax[2], k2);
-            cmin[0] = min(cmin[0], R); cmax[0] = max(cmax[0], R);
-            cmin[1] = min(cmin[1], G); cmax[1] = max(cmax[1], G);
-            cmin[2] = min(cmin[2], B); cmax[2] = max(cmax[2], B);
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        uint32_t lo = __reduce_min_sync(0xffffffffu, kmin[c]), hi = __reduce_max_sync(0xffffffffu, kmax[c]);
-        uint32_t clo = __reduce_min_sync(0xffffffffu, cmin[c]), chi = __reduce_max_sync(0xffffffffu, cmax[c]);
-        if (lane == 0) {
-            atomicMin(&s_box[c], lo); atomicMax(&s_box[3 + c], hi);
-            atomicMin(&s_box[6 + c], clo); atomicMax(&s_box[9 + c], chi);
-        }
-    }
-    __syncthreads();
-    if (s_box[0] == 0xffffffffu) return;  // no colour in this tile (uniform)
-
-    // ---- 2. LB / UB of every palette colour against the inflated box --------------------
-    const float PAD = 2e-5f;
-    float lo[3], hi[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { lo[c] = key2f(s_box[c]) - PAD; hi[c] = key2f(s_box[3 + c]) + PAD; }
-    for (uint32_t t = tid; t < n; t += FAST_THREADS) {
-        float4 p = s_pal[t];
-        float pv[3] = {p.x, p.y, p.z};
-        float lbv = 0.f, ubv = 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            float below = lo[c] - pv[c], above = pv[c] - hi[c];
-            float ex = fmaxf(0.f, fmaxf(below, above));
-            float fx = fmaxf(fabsf(pv[c] - lo[c]), fabsf(pv[c] - hi[c]));
-            lbv = fmaf(ex, ex, lbv);
-            ubv = fmaf(fx, fx, ubv);
-        }
-        lbv *= (1.0f - 2e-6f);
-        ubv *= (1.0f + 2e-6f);
-        s_lb[t] = lbv;
-        s_ub[t] = ubv;
-        atomicMin(&s_lbmin, __float_as_uint(lbv));
-        atomicMin(&s_ubmin, __float_as_uint(ubv));
-        // palette colours whose sRGB lies inside the tile's sRGB box can be hit exactly (rbf.rs:66)
-        if (KIND != KIND_NN) {
-            uint32_t q = a.pal_rgb[t], qr = q & 255u, qg = (q >> 8) & 255u, qb = (q >> 16) & 255u;
-            if (qr >= s_box[6] && qr <= s_box[9] && qg >= s_box[7] && qg <= s_box[10] && qb >= s_box[8] && qb <= s_box[11]) {
-                uint32_t h = atomicAdd(&s_nhit, 1u);
-                if (h < FAST_MAX_HITS) s_hit[h] = q;
+            uint32_t lo = __reduce_min_sync(0xffffffffu, kmin[c]), hi = __reduce_max_sync(0xffffffffu, kmax[c]);
+            uint32_t clo = __reduce_min_sync(0xffffffffu, cmin[c]), chi = __reduce_max_sync(0xffffffffu, cmax[c]);
+            if (lane == 0) {
+                atomicMin(&s_box[c], lo); atomicMax(&s_box[3 + c], hi);
+                atomicMin(&s_box[6 + c], clo); atomicMax(&s_box[9 + c], chi);
             }
         }
-    }
-    __syncthreads();
+        __syncthreads();
+        const uint32_t next_bid = s_next;
+        if (s_box[0] == 0xffffffffu) { bid = next_bid; continue; }  // no colour in this tile (uniform)
 
-    // ---- 3./4. classification ------------------------------------------------------------
-    const uint32_t k = a.k;
-    const float c1 = a.c1;
-    const float ubmin = __uint_as_float(s_ubmin), lbmin = __uint_as_float(s_lbmin);
-    if (k != 0) {
-        for (uint32_t t = tid; t < n; t += FAST_THREADS) {
-            float u = s_ub[t];
-            uint32_t rank = 0;
-            for (uint32_t q = 0; q < n; ++q) {
-                float uq = s_ub[q];
-                rank += (uq < u || (uq == u && q < t)) ? 1u : 0u;
-            }
-            if (rank == k - 1) s_uk = __float_as_uint(u);
-        }
-        __syncthreads();
-    }
-    const float uk = __uint_as_float(s_uk);
-    const float lg_ubmin = KIND == 1 ? lg2_approx(ubmin) : 0.f;
-    uint32_t nin = 0, nunc = 0;          // list lengths (negligible colours dropped)
-    uint32_t nin_all = 0, nunc_all = 0;  // class sizes
-    for (uint32_t t0 = 0; t0 < n; t0 += FAST_THREADS) {
-        uint32_t t = t0 + tid;
-        bool is_in = false, is_unc = false, negl = false;
-        if (t < n) {
-            float l = s_lb[t], u = s_ub[t];
-            if (k == 0) {
-                is_in = true;
-            } else if (l <= uk) {
-                uint32_t rivals = 0;
-                for (uint32_t q = 0; q < n; ++q) rivals += (q != t && s_lb[q] <= u) ? 1u : 0u;
-                is_in = rivals <= k - 1;
-                is_unc = !is_in;
-            }
-            // step 4: weight at most 2^-24 of the nearest colour's anywhere in the tile
-            if (KIND == 0) negl = c1 < 0.f && c1 * (l - ubmin) < FAST_NEGLIGIBLE_LOG2;
-            if (KIND == 1) negl = c1 < 0.f && l > 0.f && ubmin > 0.f && c1 * (lg2_approx(l) - lg_ubmin) < FAST_NEGLIGIBLE_LOG2 - 1e-3f;
-        }
-        nin_all += __syncthreads_count(is_in);
-        nunc_all += __syncthreads_count(is_unc);
-        bool list_in = is_in && !negl, list_unc = is_unc && !negl;
-        uint32_t bin = __ballot_sync(0xffffffffu, list_in), bun = __ballot_sync(0xffffffffu, list_unc);
-        if (lane == 0) { s_wcnt[0][warp] = __popc(bin); s_wcnt[1][warp] = __popc(bun); }
-        __syncthreads();
-        uint32_t pre_in = nin, pre_unc = nunc, tot_in = 0, tot_unc = 0;
+        // ---- 2. LB / UB of every palette colour against the inflated box ----------------
+        const float PAD = 2e-5f;
+        float lo[3], hi[3];
 #pragma unroll
-        for (int w = 0; w < FAST_THREADS / 32; ++w) {
-            uint32_t ci = s_wcnt[0][w], cu = s_wcnt[1][w];
-            if ((uint32_t)w < warp) { pre_in += ci; pre_unc += cu; }
-            tot_in += ci; tot_unc += cu;
-        }
-        uint32_t lt = (1u << lane) - 1u;
-        // IN colours fill s_cidx from the front, UNCERTAIN ones from the back (palette order both)
-        if (list_in) s_cidx[pre_in + __popc(bin & lt)] = t;
-        if (list_unc) s_cidx[n - 1 - (pre_unc + __popc(bun & lt))] = t;
-        nin += tot_in; nunc += tot_unc;
-        __syncthreads();
-    }
-    for (uint32_t j = tid; j < nin; j += FAST_THREADS) s_cand[j] = s_pal[s_cidx[j]];
-    for (uint32_t j = tid; j < nunc; j += FAST_THREADS) s_cand[nin + j] = s_pal[s_cidx[n - 1 - j]];
-    __syncthreads();
-    if (a.stats && tid == 0) {
-        atomicAdd(&a.stats[min(nunc, 63u)], 1u);
-        atomicAdd(&a.stats[64 + min(nin, 63u)], 1u);
-    }
-    // neighbours still to choose per pixel among the uncertain colours
-    const int kp_all = (int)k - (int)nin_all;
-    const bool choose = (k != 0) && kp_all > 0 && (int)nunc_all > kp_all && (int)nunc > kp_all;
-    const uint32_t direct = (k == 0 || kp_all <= 0 || choose) ? nin : nin + nunc;  // listed colours taken unconditionally
-    const int kp = kp_all;
-    const uint32_t nhit = min(s_nhit, (uint32_t)FAST_MAX_HITS);
-    const bool hits_overflow = s_nhit > FAST_MAX_HITS;
-
-    // weight shift
-    float c0 = 0.f;
-    if (KIND == 0) c0 = -c1 * lbmin;
-    if (KIND == 1) c0 = -c1 * lg2_approx(lbmin > 0.f ? lbmin : ubmin);
-
-    // ---- 5. per colour --------------------------------------------------------------------
-    for (uint32_t e = 0; e < a.ept; ++e) {
-        if (!((valid_mask >> e) & 1u)) continue;
-        uint32_t li = e * FAST_THREADS + tid;
-        float L = s_lab[li], A = s_lab[tile + li], B = s_lab[2 * tile + li];
-        uint32_t packed = s_rgb[li];
-        PixelIO px;
-        px.r = packed & 255u; px.g = (packed >> 8) & 255u; px.b = packed >> 16;
-        if (MODE == FRONT_IMAGE) {
-            px.slot = img_base + li; px.mode = FRONT_IMAGE;
-        } else {
-            uint32_t lb = lb0 + e * lb_step;
-            px.slot = ((unsigned long long)(b0 + lb) * cs + (g0 + lg)) * cs + (r0 + lr); px.mode = MODE;
-        }
-        if (hits_overflow) { flag_entry(a, px.slot); continue; }
-
-        if (KIND == KIND_NN) {
-            // nearest_one: IN holds at most one colour; otherwise argmin over the uncertain ones
-            uint32_t best_j = 0;
-            bool risky = false;
-            if (nin == 0) {
-                float best = INFINITY, second = INFINITY;
-                for (uint32_t j = 0; j < nunc; ++j) {
-                    float d = dist3(L, A, B, s_cand[j]);
-                    bool better = d < best;
-                    second = better ? best : fminf(second, d);
-                    best_j = better ? j : best_j;
-                    best = better ? d : best;
+        for (int c = 0; c < 3; ++c) { lo[c] = key2f(s_box[c]) - PAD; hi[c] = key2f(s_box[3 + c]) + PAD; }
+        for (uint32_t t = tid; t < n; t += FAST_THREADS) {
+            float4 p = s_pal[t];
+            float pv[3] = {p.x, p.y, p.z};
+            float lbv = 0.f, ubv = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float below = lo[c] - pv[c], above = pv[c] - hi[c];
+                float ex = fmaxf(0.f, fmaxf(below, above));
+                float fx = fmaxf(fabsf(pv[c] - lo[c]), fabsf(pv[c] - hi[c]));
+                lbv = fmaf(ex, ex, lbv);
+                ubv = fmaf(fx, fx, ubv);
+            }
+            lbv *= (1.0f - 2e-6f);
+            ubv *= (1.0f + 2e-6f);
+            s_lb[t] = lbv;
+            s_ub[t] = ubv;
+            atomicMin(&s_lbmin, __float_as_uint(lbv));
+            atomicMin(&s_ubmin, __float_as_uint(ubv));
+            // palette colours whose sRGB lies inside the tile's sRGB box can be hit exactly (rbf.rs:66)
+            if (KIND != KIND_NN) {
+                uint32_t q = a.pal_rgb[t], qr = q & 255u, qg = (q >> 8) & 255u, qb = (q >> 16) & 255u;
+                if (qr >= s_box[6] && qr <= s_box[9] && qg >= s_box[7] && qg <= s_box[10] && qb >= s_box[8] && qb <= s_box[11]) {
+                    uint32_t h = atomicAdd(&s_nhit, 1u);
+                    if (h < FAST_MAX_HITS) s_hit[h] = q;
                 }
-                float gap = second - best;
-                risky = (gap * gap <= FAST_TIE_TOL * second) && (second < INFINITY);
             }
-            if (risky) { flag_entry(a, px.slot); continue; }
-            uint32_t idx = (nin != 0) ? s_cidx[0] : s_cidx[n - 1 - best_j];
-            if (!a.preserve) {
-                uint32_t q = a.pal_rgb[idx];
-                front_store<MODE>(a.f, px, q & 255u, (q >> 8) & 255u, (q >> 16) & 255u);
-            } else {
-                // nearest_neighbor.rs:57-59: pixel's own (unscaled, exact) l with the colour's a, b
-                Lab ex = linear_to_oklab_exact(st.decode[px.r], st.decode[px.g], st.decode[px.b]);
-                Lab o = {ex.l, a.pal_ab[2 * idx], a.pal_ab[2 * idx + 1]};
-                float r, g, b;
-                oklab_to_linear_exact(o, r, g, b);
-                front_store<MODE>(a.f, px, f32_to_srgb8(r, st.encode), f32_to_srgb8(g, st.encode), f32_to_srgb8(b, st.encode));
-            }
-            continue;
         }
+        __syncthreads();
 
-        // rbf.rs:66-68 palette.contains(&color): identical sRGB <=> identical Oklab triple
-        bool hit = false;
-        for (uint32_t h = 0; h < nhit; ++h) hit |= (s_hit[h] == packed);
-        if (hit) {
-            if (MODE != FRONT_IMAGE) front_store<MODE>(a.f, px, px.r, px.g, px.b);
-            continue;
-        }
-        float n0 = 0.f, n1 = 0.f, n2 = 0.f, den = 0.f;
-#pragma unroll 4
-        for (uint32_t j = 0; j < direct; ++j) {
-            float4 p = s_cand[j];
-            float w = fast_weight<KIND>(dist3(L, A, B, p), c1, c0);
-            n0 = fmaf(p.x, w, n0);
-            n1 = fmaf(p.y, w, n1);
-            n2 = fmaf(p.z, w, n2);
-            den += w;
-        }
-        bool risky = false;
-        if (choose) {
-            const float4* unc = s_cand + nin;
-            if (nunc <= 4) risky = select_accumulate<4, KIND>(unc, (int)nunc, kp, L, A, B, c1, c0, n0, n1, n2, den);
-            else if (nunc <= 8) risky = select_accumulate<8, KIND>(unc, (int)nunc, kp, L, A, B, c1, c0, n0, n1, n2, den);
-            else if (nunc <= 16) risky = select_accumulate<16, KIND>(unc, (int)nunc, kp, L, A, B, c1, c0, n0, n1, n2, den);
-            else {
-                LoopAcc la = select_accumulate_loop<KIND>(unc, (int)nunc, kp, L, A, B, c1, c0);
-                n0 += la.n0; n1 += la.n1; n2 += la.n2; den += la.den;
-                risky = la.risky != 0;
+        // ---- 3./4. classification --------------------------------------------------------
+        const float ubmin = __uint_as_float(s_ubmin), lbmin = __uint_as_float(s_lbmin);
+        const float lg_ubmin = KIND == 1 ? lg2_approx(ubmin) : 0.f;
+        if (k != 0) {
+            // U_k: k-th smallest UB (every pixel's k-th neighbour is at most this far);
+            // L_k: k-th smallest LB (... and at least this far)
+            for (uint32_t t = tid; t < n; t += FAST_THREADS) {
+                float u = s_ub[t], l = s_lb[t];
+                uint32_t rank_u = 0, rank_l = 0;
+                for (uint32_t q = 0; q < n; ++q) {
+                    float uq = s_ub[q], lq = s_lb[q];
+                    rank_u += (uq < u || (uq == u && q < t)) ? 1u : 0u;
+                    rank_l += (lq < l || (lq == l && q < t)) ? 1u : 0u;
+                }
+                if (rank_u == k - 1) s_uk = __float_as_uint(u);
+                if (rank_l == k - 1) s_lk = __float_as_uint(l);
             }
+            __syncthreads();
         }
-        if (risky || !(den > 1e-30f) || !(den < 1e30f)) { flag_entry(a, px.slot); continue; }
-        float inv = __frcp_rn(den);
-        Lab o;
-        o.l = a.preserve ? L * a.inv_lum : n0 * inv * a.inv_lum;
-        o.a = n1 * inv;
-        o.b = n2 * inv;
-        float r, g, b;
-        oklab_to_linear_fast(o, r, g, b);
-        front_store<MODE>(a.f, px, f32_to_srgb8(r, st.encode), f32_to_srgb8(g, st.encode), f32_to_srgb8(b, st.encode));
+        const float uk = __uint_as_float(s_uk);
+        // If even the k-th neighbour's weight is negligible everywhere in the tile, "nearest k" no
+        // longer constrains anything: every colour that can matter is taken, nothing is chosen.
+        const bool moot = (k != 0) && (KIND != KIND_NN) && negligible_at<KIND>(__uint_as_float(s_lk), ubmin, lg_ubmin, c1);
+        const bool take_all = (k == 0) || moot;
+        uint32_t nin = 0, nunc = 0;          // list lengths (negligible colours dropped)
+        uint32_t nin_all = 0, nunc_all = 0;  // class sizes
+        for (uint32_t t0 = 0; t0 < n; t0 += FAST_THREADS) {
+            uint32_t t = t0 + tid;
+            bool is_in = false, is_unc = false, negl = false;
+            if (t < n) {
+                float l = s_lb[t], u = s_ub[t];
+                if (take_all) {
+                    is_in = true;
+                } else if (l <= uk) {
+                    uint32_t rivals = 0;
+                    for (uint32_t q = 0; q < n; ++q) rivals += (q != t && s_lb[q] <= u) ? 1u : 0u;
+                    is_in = rivals <= k - 1;
+                    is_unc = !is_in;
+                }
+                if (KIND != KIND_NN) negl = negligible_at<KIND>(l, ubmin, lg_ubmin, c1);
+            }
+            nin_all += __syncthreads_count(is_in);
+            nunc_all += __syncthreads_count(is_unc);
+            bool list_in = is_in && !negl, list_unc = is_unc && !negl;
+            uint32_t bin = __ballot_sync(0xffffffffu, list_in), bun = __ballot_sync(0xffffffffu, list_unc);
+            if (lane == 0) { s_wcnt[0][warp] = __popc(bin); s_wcnt[1][warp] = __popc(bun); }
+            __syncthreads();
+            uint32_t pre_in = nin, pre_unc = nunc, tot_in = 0, tot_unc = 0;
+#pragma unroll
+            for (int w = 0; w < FAST_THREADS / 32; ++w) {
+                uint32_t ci = s_wcnt[0][w], cu = s_wcnt[1][w];
+                if ((uint32_t)w < warp) { pre_in += ci; pre_unc += cu; }
+                tot_in += ci; tot_unc += cu;
+            }
+            uint32_t lt = (1u << lane) - 1u;
+            // IN colours fill s_cidx from the front, UNCERTAIN ones from the back (palette order both)
+            if (list_in) s_cidx[pre_in + __popc(bin & lt)] = t;
+            if (list_unc) s_cidx[n - 1 - (pre_unc + __popc(bun & lt))] = t;
+            nin += tot_in; nunc += tot_unc;
+            __syncthreads();
+        }
+        for (uint32_t j = tid; j < nin; j += FAST_THREADS) s_cand[j] = s_pal[s_cidx[j]];
+        for (uint32_t j = tid; j < nunc; j += FAST_THREADS) s_cand[nin + j] = s_pal[s_cidx[n - 1 - j]];
+        __syncthreads();
+        if (a.stats && tid == 0) {
+            atomicAdd(&a.stats[min(nunc, 63u)], 1u);
+            atomicAdd(&a.stats[64 + min(nin, 63u)], 1u);
+        }
+        // neighbours still to choose per pixel among the uncertain colours
+        const int kp = (int)k - (int)nin_all;
+        const bool choose = !take_all && kp > 0 && (int)nunc_all > kp && (int)nunc > kp;
+        const uint32_t direct = (take_all || kp <= 0 || choose) ? nin : nin + nunc;  // listed colours taken unconditionally
+        const uint32_t nhit = min(s_nhit, (uint32_t)FAST_MAX_HITS);
+        const bool hits_overflow = s_nhit > FAST_MAX_HITS;
+
+        // weight shift
+        float c0 = 0.f;
+        if (KIND == 0) c0 = -c1 * lbmin;
+        if (KIND == 1) c0 = -c1 * lg2_approx(lbmin > 0.f ? lbmin : ubmin);
+
+        // ---- 5. per colour ----------------------------------------------------------------
+        for (uint32_t e = 0; e < a.ept; ++e) {
+            if (!((valid_mask >> e) & 1u)) continue;
+            uint32_t li = e * FAST_THREADS + tid;
+            float L = s_lab[li], A = s_lab[tile + li], B = s_lab[2 * tile + li];
+            uint32_t packed = s_rgb[li];
+            PixelIO px;
+            px.r = packed & 255u; px.g = (packed >> 8) & 255u; px.b = packed >> 16;
+            if (MODE == FRONT_IMAGE) {
+                px.slot = img_base + li; px.mode = FRONT_IMAGE;
+            } else {
+                uint32_t lb = lb0 + e * lb_step;
+                px.slot = ((b0 + lb) * cs + (g0 + lg)) * cs + (r0 + lr); px.mode = MODE;
+            }
+            if (hits_overflow) { flag_entry(a, px.slot); continue; }
+
+            if (KIND == KIND_NN) {
+                // nearest_one: IN holds at most one colour; otherwise argmin over the uncertain ones
+                uint32_t best_j = 0;
+                bool risky = false;
+                if (nin == 0) {
+                    float best = INFINITY, second = INFINITY;
+                    for (uint32_t j = 0; j < nunc; ++j) {
+                        float d = dist3(L, A, B, s_cand[j]);
+                        bool better = d < best;
+                        second = better ? best : fminf(second, d);
+                        best_j = better ? j : best_j;
+                        best = better ? d : best;
+                    }
+                    float gap = second - best;
+                    risky = (gap * gap <= FAST_TIE_TOL * second) && (second < INFINITY);
+                }
+                if (risky) { flag_entry(a, px.slot); continue; }
+                uint32_t idx = (nin != 0) ? s_cidx[0] : s_cidx[n - 1 - best_j];
+                if (!a.preserve) {
+                    uint32_t q = a.pal_rgb[idx];
+                    front_store<MODE>(a.f, px, q & 255u, (q >> 8) & 255u, (q >> 16) & 255u);
+                } else {
+                    // nearest_neighbor.rs:57-59: pixel's own (unscaled, exact) l with the colour's a, b
+                    Lab ex = linear_to_oklab_exact(st.decode[px.r], st.decode[px.g], st.decode[px.b]);
+                    Lab o = {ex.l, a.pal_ab[2 * idx], a.pal_ab[2 * idx + 1]};
+                    float r, g, b;
+                    oklab_to_linear_exact(o, r, g, b);
+                    front_store<MODE>(a.f, px, f32_to_srgb8(r, st.encode), f32_to_srgb8(g, st.encode), f32_to_srgb8(b, st.encode));
+                }
+                continue;
+            }
+
+            // rbf.rs:66-68 palette.contains(&color): identical sRGB <=> identical Oklab triple
+            bool hit = false;
+            for (uint32_t h = 0; h < nhit; ++h) hit |= (s_hit[h] == packed);
+            if (hit) {
+                if (MODE != FRONT_IMAGE) front_store<MODE>(a.f, px, px.r, px.g, px.b);
+                continue;
+            }
+            float n0 = 0.f, n1 = 0.f, n2 = 0.f, den = 0.f;
+#pragma unroll 4
+            for (uint32_t j = 0; j < direct; ++j) {
+                float4 p = s_cand[j];
+                float w = fast_weight<KIND>(dist3(L, A, B, p), c1, c0);
+                n0 = fmaf(p.x, w, n0);
+                n1 = fmaf(p.y, w, n1);
+                n2 = fmaf(p.z, w, n2);
+                den += w;
+            }
+            bool risky = false;
+            if (choose) {
+                const float4* unc = s_cand + nin;
+                if (nunc <= 4) risky = select_accumulate<4, KIND>(unc, (int)nunc, kp, L, A, B, c1, c0, n0, n1, n2, den);
+                else if (nunc <= 8) risky = select_accumulate<8, KIND>(unc, (int)nunc, kp, L, A, B, c1, c0, n0, n1, n2, den);
+                else if (nunc <= 16) risky = select_accumulate<16, KIND>(unc, (int)nunc, kp, L, A, B, c1, c0, n0, n1, n2, den);
+                else {
+                    LoopAcc la = select_accumulate_loop<KIND>(unc, (int)nunc, kp, L, A, B, c1, c0);
+                    n0 += la.n0; n1 += la.n1; n2 += la.n2; den += la.den;
+                    risky = la.risky != 0;
+                }
+            }
+            if (risky || !(den > 1e-30f) || !(den < 1e30f)) { flag_entry(a, px.slot); continue; }
+            float inv = __frcp_rn(den);
+            Lab o;
+            o.l = a.preserve ? L * a.inv_lum : n0 * inv * a.inv_lum;
+            o.a = n1 * inv;
+            o.b = n2 * inv;
+            float r, g, b;
+            oklab_to_linear_fast(o, r, g, b);
+            front_store<MODE>(a.f, px, f32_to_srgb8(r, st.encode), f32_to_srgb8(g, st.encode), f32_to_srgb8(b, st.encode));
+        }
+        bid = next_bid;
     }
 }
 
