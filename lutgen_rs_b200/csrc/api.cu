@@ -892,20 +892,39 @@ int lutgen_cuda_generate_lut(const lutgen_remapper* r, uint8_t level, uint8_t* o
     size_t bytes = 3 * lut_entries(level);
     uint32_t side = (uint32_t)level * level * level;
     CU_TRY(g.lut_rgb.reserve(bytes));
-    // Row chunks so a set abort flag is honoured between launches (lib.rs:149-170).
-    uint32_t chunks = abort_flag ? 8u : 1u;
-    if (chunks > side) chunks = side;
-    for (uint32_t c = 0; c < chunks; ++c) {
-        uint32_t r0 = (uint32_t)((uint64_t)side * c / chunks), r1 = (uint32_t)((uint64_t)side * (c + 1) / chunks);
+    // Row chunks: (1) a set abort flag is honoured between launches (lib.rs:149-170); (2) the
+    // download of chunk i rides a second stream while chunk i+1 is being computed, so a large
+    // CLUT costs about max(kernel, PCIe copy) instead of their sum. Chunk edges sit on multiples
+    // of 16 blue planes (16*level rows), the kernels' brick depth, so no brick is visited twice.
+    const uint32_t group = 16u * level;
+    uint32_t ngroups = (side + group - 1) / group;
+    uint32_t chunks = (bytes >= (8u << 20)) ? 4u : 1u;
+    if (abort_flag && chunks < 8u) chunks = 8u;
+    if (chunks > ngroups) chunks = ngroups;
+    cudaStream_t copy_stream = g.batch_streams[0];
+    cudaEvent_t done[8];
+    for (uint32_t c = 0; c < chunks; ++c) CU_TRY(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
+    int result = LUTGEN_OK;
+    for (uint32_t c = 0; c < chunks && result == LUTGEN_OK; ++c) {
+        uint32_t r0 = (uint32_t)((uint64_t)ngroups * c / chunks) * group, r1 = (uint32_t)((uint64_t)ngroups * (c + 1) / chunks) * group;
+        if (r1 > side) r1 = side;
         rc = lutgen_cuda_generate_lut_rows_dev(r, level, (uint8_t*)g.lut_rgb.p, r0, r1, g.stream);
-        if (rc) return rc;
+        if (rc) { result = rc; break; }
+        cudaError_t e = cudaEventRecord(done[c], g.stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(copy_stream, done[c], 0);
+        size_t off = (size_t)r0 * side * 3, len = (size_t)(r1 - r0) * side * 3;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_rgb + off, (uint8_t*)g.lut_rgb.p + off, len, cudaMemcpyDeviceToHost, copy_stream);
+        if (e != cudaSuccess) { result = fail(LUTGEN_ERR_CUDA, "chunk %u: %s", c, cudaGetErrorString(e)); break; }
         if (abort_flag) {
-            CU_TRY(cudaStreamSynchronize(g.stream));
-            if (*abort_flag) return LUTGEN_ABORTED;
+            cudaStreamSynchronize(g.stream);
+            if (*abort_flag) result = LUTGEN_ABORTED;
         }
     }
-    CU_TRY(cudaMemcpyAsync(out_rgb, g.lut_rgb.p, bytes, cudaMemcpyDeviceToHost, g.stream));
-    CU_TRY(cudaStreamSynchronize(g.stream));
+    cudaError_t e1 = cudaStreamSynchronize(g.stream), e2 = cudaStreamSynchronize(copy_stream);
+    for (uint32_t c = 0; c < chunks; ++c) cudaEventDestroy(done[c]);
+    if (result != LUTGEN_OK) return result;
+    if (e1 != cudaSuccess || e2 != cudaSuccess)
+        return fail(LUTGEN_ERR_CUDA, "generate_lut: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     if (abort_flag && *abort_flag) return LUTGEN_ABORTED;
     return LUTGEN_OK;
 }

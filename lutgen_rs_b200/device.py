@@ -59,29 +59,48 @@ def shard_rows(side, world, rank):
     return min(rank * per, side), min((rank + 1) * per, side), per
 
 
+def sharded_rows_all_gather(side, compute_rows, out=None, group=None, device="cuda"):
+    """Row-sharded generation + in-place all-gather, independent of what fills the rows.
+
+    `compute_rows(flat, r0, r1)` writes rows [r0, r1) of the side x side RGB8 image at their place in
+    `flat` (a uint8 tensor of padded_rows * side * 3 bytes). Every rank owns ceil(side/world) rows (the
+    last ranks may own fewer or none; the buffer is padded so all shards have equal size) and one
+    all_gather_into_tensor, whose output IS that buffer, leaves the whole image on every rank.
+    Returns the (side, side, 3) view. The GPU path passes the CUDA kernel launch as `compute_rows`;
+    the CPU (gloo) tests pass the oracle, so the sharding arithmetic is tested without a GPU.
+    """
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    r0, r1, per = shard_rows(side, world, rank)
+    nbytes = per * world * side * 3
+    if out is None:
+        out = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    if not (out.dtype == torch.uint8 and out.is_contiguous() and out.numel() >= nbytes):
+        raise TypeError(f"out must be a contiguous uint8 tensor of at least {nbytes} bytes")
+    flat = out.view(-1)[:nbytes]
+    compute_rows(flat, r0, r1)
+    if world > 1:
+        mine = flat[rank * per * side * 3:(rank + 1) * per * side * 3]
+        dist.all_gather_into_tensor(flat, mine, group=group)
+    return flat[: side * side * 3].view(side, side, 3)
+
+
 def generate_lut(remapper, level, group=None, stream=None, out=None):
     """GenerateLut::par_generate_lut on the device(s): returns a (side, side, 3) uint8 CUDA tensor.
 
     With a process group of G ranks each rank computes side/G rows and an in-place
     all-gather (NCCL, NVLink) leaves the complete CLUT on every rank.
     """
-    import torch.distributed as dist
     level = int(level)
     side = level ** 3
-    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
-    rank = dist.get_rank(group) if world > 1 else 0
-    r0, r1, per = shard_rows(side, world, rank)
-    padded_rows = per * world
-    if out is None:
-        out = torch.empty(padded_rows * side * 3, dtype=torch.uint8, device="cuda")
-    _check_u8(out, "out")
-    assert out.numel() >= padded_rows * side * 3
-    generate_lut_rows_(remapper, level, out, r0, r1, stream)
-    if world > 1:
-        flat = out[: padded_rows * side * 3]
-        mine = flat[rank * per * side * 3:(rank + 1) * per * side * 3]
-        dist.all_gather_into_tensor(flat, mine, group=group)
-    return out[: side * side * 3].view(side, side, 3)
+    if out is not None:
+        _check_u8(out, "out")
+
+    def compute_rows(flat, r0, r1):
+        generate_lut_rows_(remapper, level, flat, r0, r1, stream)
+
+    return sharded_rows_all_gather(side, compute_rows, out=out, group=group, device="cuda")
 
 
 def apply_hald_(rgba, lut, level, stream=None):
