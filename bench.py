@@ -39,6 +39,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
+# stdout carries exactly one JSON line: keep NCCL's version banner off it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 LEVEL_GEN = 16
 LEVEL_APPLY = 8
 FRAME_W, FRAME_H = 3840, 2160
@@ -363,7 +367,9 @@ def run_b200(args):
                      "frac": gen_achieved / fp32.value if fp32.value else None, "traffic": None,
                      "peak_source": "on-box FFMA micro-benchmark (lutgen_cuda_measure_peaks), this run",
                      "mufu_peak_tops": mufu.value, "kernel_ms": gen_kernel_t * 1e3,
-                     "algorithmic_flops_per_entry": GEN_FLOPS_PER_ENTRY},
+                     "algorithmic_flops_per_entry": GEN_FLOPS_PER_ENTRY,
+                     "step_ms_each": [round(t * 1e3, 4) for t in gen_times],
+                     "kernel_ms_each": [round(t * 1e3, 4) for t in gen_kernel_times]},
         "config": {"workload": "generate level-16 Gaussian RBF CLUT (16,777,216 entries), catppuccin-mocha 26 colours, "
                                "shape 128, nearest 16, lum 1.0, preserve off; rows sharded over ranks + in-place NCCL all-gather",
                    "level": LEVEL_GEN, "l2": "flushed between timed iterations (512 MiB fill)"},

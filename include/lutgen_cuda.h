@@ -24,8 +24,11 @@
  *    entry points; the collective (NCCL all-gather) lives in the host layer.
  *  - There is no CPU fallback: without a usable sm_100 device every compute
  *    entry point returns LUTGEN_ERR_NO_DEVICE / LUTGEN_ERR_CUDA.
- *  - `stream` arguments are `cudaStream_t` passed as void* (NULL = the
- *    library's own stream; `_dev` calls with a caller stream do not synchronise).
+ *  - `stream` arguments are `cudaStream_t` passed as void*; 0 / NULL is CUDA's
+ *    default stream, as in every CUDA API. `_dev` calls only enqueue work: they
+ *    never synchronise, and results are ordered with the caller's other work on
+ *    that stream. A remapper handle, and the apply entry points (which share
+ *    one expanded-CLUT scratch buffer), must be driven from one stream at a time.
  */
 #ifndef LUTGEN_CUDA_H
 #define LUTGEN_CUDA_H

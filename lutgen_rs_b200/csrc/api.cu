@@ -584,12 +584,11 @@ int lutgen_cuda_identity_dev(uint8_t level, uint8_t* out_rgb_dev, void* stream) 
     if (rc) return rc;
     if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33 (the reference divides by zero / overflows)", level);
     if (!out_rgb_dev) return fail(LUTGEN_ERR_INVALID, "out_rgb_dev is NULL");
-    cudaStream_t s = stream ? (cudaStream_t)stream : g.stream;
+    cudaStream_t s = (cudaStream_t)stream;  // 0 is CUDA's default stream, as everywhere in CUDA
     size_t E = lut_entries(level);
     uint32_t cs = (uint32_t)level * level;
     k_identity<<<blocks_for((E + 3) / 4, 256), 256, 0, s>>>(out_rgb_dev, 0, E, cs, cs - 1);
     LAUNCH_CHECK();
-    if (!stream) CU_TRY(cudaStreamSynchronize(s));
     return LUTGEN_OK;
 }
 
@@ -613,14 +612,13 @@ int lutgen_cuda_apply_hald_dev(uint8_t* rgba_dev, size_t npix, const uint8_t* lu
     if (rc) return rc;
     if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33", level);
     if (!lut_rgb_dev || (!rgba_dev && npix)) return fail(LUTGEN_ERR_INVALID, "NULL buffer");
-    cudaStream_t s = stream ? (cudaStream_t)stream : g.stream;
+    cudaStream_t s = (cudaStream_t)stream;  // 0 is CUDA's default stream, as everywhere in CUDA
     if (npix) {
         rc = expand_lut(lut_rgb_dev, level, s);
         if (rc) return rc;
         rc = launch_apply(rgba_dev, npix, (const uint32_t*)g.lut_rgbx.p, level, s);
         if (rc) return rc;
     }
-    if (!stream) CU_TRY(cudaStreamSynchronize(s));
     return LUTGEN_OK;
 }
 
@@ -869,7 +867,7 @@ int lutgen_cuda_generate_lut_rows_dev(const lutgen_remapper* r, uint8_t level, u
     if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33", level);
     uint32_t side = (uint32_t)level * level * level;
     if (row_begin > row_end || row_end > side) return fail(LUTGEN_ERR_INVALID, "rows [%u, %u) outside 0..%u", row_begin, row_end, side);
-    cudaStream_t s = stream ? (cudaStream_t)stream : g.stream;
+    cudaStream_t s = (cudaStream_t)stream;  // 0 is CUDA's default stream, as everywhere in CUDA
     Front f{};
     f.out = lut_rgb_dev;
     f.begin = (unsigned long long)row_begin * side;
@@ -878,7 +876,6 @@ int lutgen_cuda_generate_lut_rows_dev(const lutgen_remapper* r, uint8_t level, u
     f.csm1 = f.cs - 1;
     rc = launch_remap<FRONT_LUT>(f, r, s);
     if (rc) return rc;
-    if (!stream) CU_TRY(cudaStreamSynchronize(s));
     return LUTGEN_OK;
 }
 
@@ -935,14 +932,13 @@ int lutgen_cuda_remap_image_dev(const lutgen_remapper* r, uint8_t* rgba_dev, siz
     if (!r || (!rgba_dev && npix)) return fail(LUTGEN_ERR_INVALID, "NULL argument");
     if (reinterpret_cast<uintptr_t>(rgba_dev) & 3u) return fail(LUTGEN_ERR_INVALID, "rgba_dev must be 4-byte aligned");
     if (npix >= (1ull << 32)) return fail(LUTGEN_ERR_UNSUPPORTED, "more than 2^32 pixels in one call");
-    cudaStream_t s = stream ? (cudaStream_t)stream : g.stream;
+    cudaStream_t s = (cudaStream_t)stream;  // 0 is CUDA's default stream, as everywhere in CUDA
     Front f{};
     f.out = rgba_dev;
     f.begin = 0;
     f.count = npix;
     rc = launch_remap<FRONT_IMAGE>(f, r, s);
     if (rc) return rc;
-    if (!stream) CU_TRY(cudaStreamSynchronize(s));
     return LUTGEN_OK;
 }
 
