@@ -197,7 +197,20 @@ def run_b200(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     device.init(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on stdout when the communicator comes up; stdout must
+        # carry exactly one JSON line, so it is pointed at stderr until the first collective is done
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            t = torch.zeros(1, device="cuda")
+            dist.all_reduce(t)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     steps, warmup = max(1, args.steps), max(3, args.warmup)
     peaks, peak_kind = measured_peaks()
     L = _native.lib()

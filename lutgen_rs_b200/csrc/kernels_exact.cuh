@@ -235,7 +235,38 @@ __device__ __forceinline__ void rbf_exact_one(const Front& f, const RemapParams&
             n2 = __dadd_rn(n2, __dmul_rn(p[2], w));
             den = __dadd_rn(den, w);
         }
+    } else if (P.nearest <= 64) {
+        // One pass over the palette keeping the k best (distance, index) pairs sorted ascending in
+        // a per-thread array: a later colour at an equal distance sorts after an earlier one, so
+        // the array ends as kiddo's nearest_n order and the f64 sums run in the oracle's order.
+        double td[64];
+        uint32_t tj[64];
+        const uint32_t k = P.nearest;
+        uint32_t cnt = 0;
+        for (uint32_t j = 0; j < n; ++j) {
+            double d = sq_dist_exact(c0, c1, c2, P.pal_lab + 3 * j);
+            if (cnt < k || d < td[cnt - 1]) {
+                uint32_t i = cnt < k ? cnt : k - 1;
+                while (i > 0 && td[i - 1] > d) {
+                    td[i] = td[i - 1];
+                    tj[i] = tj[i - 1];
+                    --i;
+                }
+                td[i] = d;
+                tj[i] = j;
+                if (cnt < k) ++cnt;
+            }
+        }
+        for (uint32_t a = 0; a < cnt; ++a) {
+            const double* p = P.pal_lab + 3 * tj[a];
+            double w = radial_basis_exact<KIND>(td[a], P.param);
+            n0 = __dadd_rn(n0, __dmul_rn(p[0], w));
+            n1 = __dadd_rn(n1, __dmul_rn(p[1], w));
+            n2 = __dadd_rn(n2, __dmul_rn(p[2], w));
+            den = __dadd_rn(den, w);
+        }
     } else {
+        // k > 64: k passes, each extracting the next (distance, index) in ascending order
         double last_d = -1.0;
         uint32_t last_j = 0;
         bool first = true;

@@ -85,6 +85,7 @@ __device__ __forceinline__ float dist3(float L, float A, float B, float4 p) {
 __device__ __forceinline__ void flag_entry(const FastArgs& a, unsigned long long slot) {
     uint32_t pos = atomicAdd(a.flag_count, 1u);
     a.flag_list[pos] = (uint32_t)slot;
+    if (a.stats) atomicAdd(&a.stats[127], 1u);
 }
 
 // Ascending bitonic network over M registers (all indices compile-time after unrolling).
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_remap_fast(const FastArgs a
     __shared__ uint32_t s_box[12];        // Oklab min keys [0..3), max keys [3..6), sRGB min [6..9), max [9..12)
     __shared__ uint32_t s_lbmin, s_ubmin, s_uk, s_lk;
     __shared__ uint32_t s_wcnt[2][FAST_THREADS / 32];
-    __shared__ uint32_t s_nhit, s_next;
+    __shared__ uint32_t s_nhit, s_next, s_geo[3];
     __shared__ uint32_t s_hit[FAST_MAX_HITS];
     __shared__ uint32_t s_chan[3][16];    // identity channel value of each brick coordinate
 
@@ -235,27 +236,31 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_remap_fast(const FastArgs a
     for (uint32_t bid = blockIdx.x; bid < a.ntiles;) {
         __syncthreads();  // previous tile's shared state (and s_next) is no longer read
         if (tid == 0) s_next = gridDim.x + atomicAdd(a.tile_counter, 1u);
-        // ---- tile geometry --------------------------------------------------------------
+        // ---- tile geometry (the divisions run in the first two warps only) -----------------
         uint32_t r0 = 0, g0 = 0, b0 = 0, img_base = 0;
         if (MODE == FRONT_IMAGE) {
             img_base = bid * tile;
-        } else {
+        } else if (tid < 64) {
             uint32_t ir = bid % a.tiles_r, ig = (bid / a.tiles_r) % a.tiles_g, ib = bid / (a.tiles_r * a.tiles_g);
             r0 = ir << a.sh_r; g0 = ig << a.sh_g; b0 = a.b_lo + ib * a.tb;
-            // whole tile outside the requested entry range: nothing to do
-            uint32_t first = (b0 * cs + g0) * cs + r0;
-            uint32_t last = (min(b0 + a.tb - 1, csm1) * cs + min(g0 + a.tg - 1, csm1)) * cs + min(r0 + a.tr - 1, csm1);
-            if (b0 > csm1 || last < begin || first >= end) { __syncthreads(); bid = s_next; continue; }
-        }
-        if (MODE != FRONT_IMAGE && tid < 48) {
-            uint32_t c = tid >> 4, i = tid & 15;
-            uint32_t v = min((c == 0 ? r0 : c == 1 ? g0 : b0) + i, csm1);
-            s_chan[c][i] = MODE == FRONT_TABLE ? v : hald_channel(v, csm1);
+            if (tid == 0) { s_geo[0] = r0; s_geo[1] = g0; s_geo[2] = b0; }
+            if (tid < 48) {
+                uint32_t c = tid >> 4, i = tid & 15;
+                uint32_t v = min((c == 0 ? r0 : c == 1 ? g0 : b0) + i, csm1);
+                s_chan[c][i] = MODE == FRONT_TABLE ? v : hald_channel(v, csm1);
+            }
         }
         if (tid >= 64 && tid < 67) { s_box[tid - 64] = 0xffffffffu; s_box[6 + tid - 64] = 0xffffffffu; }
         else if (tid >= 67 && tid < 70) { s_box[tid - 64] = 0u; s_box[6 + tid - 64] = 0u; }
         if (tid == 96) { s_lbmin = 0x7f800000u; s_ubmin = 0x7f800000u; s_uk = 0x7f800000u; s_lk = 0x7f800000u; s_nhit = 0; }
         __syncthreads();
+        if (MODE != FRONT_IMAGE) {
+            r0 = s_geo[0]; g0 = s_geo[1]; b0 = s_geo[2];
+            // whole tile outside the requested entry range: nothing to do (uniform)
+            uint32_t first = (b0 * cs + g0) * cs + r0;
+            uint32_t last = (min(b0 + a.tb - 1, csm1) * cs + min(g0 + a.tg - 1, csm1)) * cs + min(r0 + a.tr - 1, csm1);
+            if (b0 > csm1 || last < begin || first >= end) { bid = s_next; continue; }
+        }
 
         // ---- 1. colours of this tile -> Oklab, bounding box ----------------------------
         uint32_t kmin[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, kmax[3] = {0u, 0u, 0u};

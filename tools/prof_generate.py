@@ -66,7 +66,8 @@ def main():
         tiles = max(1, int(st[:64].sum()))
         print("tiles", tiles, "(all reps)")
         print("  |UNCERTAIN| histogram:", {i: int(v) for i, v in enumerate(st[:64]) if v})
-        print("  |IN| histogram:", {i: int(v) for i, v in enumerate(st[64:]) if v})
+        print("  |IN| histogram:", {i: int(v) for i, v in enumerate(st[64:127]) if v})
+        print("  colours sent to the exact kernel:", int(st[127]))
 
 
 if __name__ == "__main__":
