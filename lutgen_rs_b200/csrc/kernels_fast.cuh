@@ -507,6 +507,10 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_remap_fast(const FastArgs a
                     risky = la.risky != 0;
                 }
             }
+            // The reference's f64 sums have their own failure modes (every exp() underflowing ->
+            // 0/0 -> black; 1/sqrt(d)^p overflowing -> inf/inf -> black). log2 of the true denominator
+            // is lg2(den) - c0; near either end of the f64 range the exact kernel reproduces them.
+            if (KIND != 2 && fabsf(lg2_approx(den) - c0) > 1000.0f) risky = true;
             if (risky || !(den > 1e-30f) || !(den < 1e30f)) { flag_entry(a, px.slot); continue; }
             float inv = __frcp_rn(den);
             Lab o;
