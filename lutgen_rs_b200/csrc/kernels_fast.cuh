@@ -113,26 +113,38 @@ __device__ __forceinline__ void bitonic_sort(float (&v)[M]) {
 // the choice is within the f32 error bound of flipping (the entry must be recomputed exactly).
 // The sorted copy lives in registers; distances are recomputed for the accumulation pass (6 cheap
 // instructions each) rather than kept in a second register array.
+// kp is uniform across the CTA: a chain of uniform branches reads s[kp-1], s[kp] from registers
+// without turning the array into local memory.
+template <int M, int I = 1>
+__device__ __forceinline__ void pick_threshold(const float (&s)[M], int kp, float& tau, float& nxt) {
+    if (kp == I) {
+        tau = s[I - 1];
+        nxt = s[I];
+    } else if constexpr (I + 1 < M) {
+        pick_threshold<M, I + 1>(s, kp, tau, nxt);
+    }
+}
+
 template <int M, int KIND>
 __device__ __forceinline__ bool select_accumulate(const float4* __restrict__ unc, int mU, int kp, float L, float A, float B, float c1,
                                                   float c0, float& n0, float& n1, float& n2, float& den) {
-    float s[M];
-#pragma unroll
-    for (int i = 0; i < M; ++i) s[i] = i < mU ? dist3(L, A, B, unc[i]) : INFINITY;
-    bitonic_sort<M>(s);
-    float tau = s[0], nxt = s[M - 1];
+    constexpr bool KEEP = M <= 8;  // small sets keep their distances; M = 16 recomputes them (registers)
+    float s[M], du[KEEP ? M : 1];
 #pragma unroll
     for (int i = 0; i < M; ++i) {
-        tau = (i == kp - 1) ? s[i] : tau;
-        nxt = (i == kp) ? s[i] : nxt;
+        s[i] = i < mU ? dist3(L, A, B, unc[i]) : INFINITY;
+        if (KEEP) du[i] = s[i];
     }
+    bitonic_sort<M>(s);
+    float tau = s[0], nxt = s[M - 1];
+    pick_threshold<M>(s, kp, tau, nxt);
     float gap = nxt - tau;
     bool risky = (gap * gap <= FAST_TIE_TOL * nxt) && (nxt < INFINITY);
 #pragma unroll
     for (int i = 0; i < M; ++i) {
         if (i < mU) {
             float4 p = unc[i];
-            float d = dist3(L, A, B, p);
+            float d = KEEP ? du[KEEP ? i : 0] : dist3(L, A, B, p);
             float w = fast_weight<KIND>(d, c1, c0);
             w = d <= tau ? w : 0.0f;
             n0 = fmaf(p.x, w, n0);
@@ -198,6 +210,92 @@ __device__ __forceinline__ bool negligible_at(float lb, float ubmin, float lg_ub
     return false;
 }
 
+// Outcome of steps 2-4 for one tile, published through shared memory.
+struct TileClass {
+    uint32_t nin, nunc;          // list lengths (negligible colours dropped)
+    uint32_t nin_all, nunc_all;  // class sizes
+    uint32_t nhit, take_all;
+    float lbmin, ubmin;
+};
+
+__device__ __forceinline__ void bounds_of(float4 p, const float (&lo)[3], const float (&hi)[3], float& lbv, float& ubv) {
+    float pv[3] = {p.x, p.y, p.z};
+    lbv = 0.f;
+    ubv = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float below = lo[c] - pv[c], above = pv[c] - hi[c];
+        float ex = fmaxf(0.f, fmaxf(below, above));
+        float fx = fmaxf(fabsf(pv[c] - lo[c]), fabsf(pv[c] - hi[c]));
+        lbv = fmaf(ex, ex, lbv);
+        ubv = fmaf(fx, fx, ubv);
+    }
+    lbv *= (1.0f - 2e-6f);
+    ubv *= (1.0f + 2e-6f);
+}
+
+// Steps 2-4 for palettes of at most 32 colours (the common case: the built-in palettes average 22):
+// one warp, one colour per lane, ranks by shuffles, lists by ballots -- no shared-memory atomics
+// and a single CTA barrier afterwards, while the other seven warps wait.
+template <int KIND>
+__device__ __forceinline__ void classify_one_warp(uint32_t lane, uint32_t n, uint32_t k, float c1, const float (&lo)[3], const float (&hi)[3],
+                                                  const uint32_t* s_box, const float4* s_pal, const uint32_t* pal_rgb, float4* s_cand,
+                                                  uint32_t* s_cidx, uint32_t* s_hit, TileClass* out) {
+    const uint32_t FULL = 0xffffffffu;
+    const bool active = lane < n;
+    float4 p = active ? s_pal[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float lbv, ubv;
+    bounds_of(p, lo, hi, lbv, ubv);
+    if (!active) { lbv = INFINITY; ubv = INFINITY; }
+    const float lbmin = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(lbv)));
+    const float ubmin = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(ubv)));
+    uint32_t nhit = 0;
+    if (KIND != KIND_NN) {
+        uint32_t q = active ? pal_rgb[lane] : 0u, qr = q & 255u, qg = (q >> 8) & 255u, qb = (q >> 16) & 255u;
+        bool inside = active && qr >= s_box[6] && qr <= s_box[9] && qg >= s_box[7] && qg <= s_box[10] && qb >= s_box[8] && qb <= s_box[11];
+        uint32_t bh = __ballot_sync(FULL, inside);
+        nhit = __popc(bh);
+        uint32_t pos = __popc(bh & ((1u << lane) - 1u));
+        if (inside && pos < FAST_MAX_HITS) s_hit[pos] = q;
+    }
+    uint32_t rank_u = 0, rank_l = 0, rivals = 0;
+    if (k != 0) {
+        for (uint32_t q = 0; q < n; ++q) {
+            float uq = __shfl_sync(FULL, ubv, q), lq = __shfl_sync(FULL, lbv, q);
+            rank_u += (uq < ubv || (uq == ubv && q < lane)) ? 1u : 0u;
+            rank_l += (lq < lbv || (lq == lbv && q < lane)) ? 1u : 0u;
+            rivals += (q != lane && lq <= ubv) ? 1u : 0u;
+        }
+    }
+    float uk = INFINITY, lk = INFINITY;
+    if (k != 0) {
+        uint32_t bu = __ballot_sync(FULL, active && rank_u == k - 1), bl = __ballot_sync(FULL, active && rank_l == k - 1);
+        if (bu) uk = __shfl_sync(FULL, ubv, __ffs(bu) - 1);
+        if (bl) lk = __shfl_sync(FULL, lbv, __ffs(bl) - 1);
+    }
+    const float lg_ubmin = KIND == 1 ? lg2_approx(ubmin) : 0.f;
+    const bool moot = (k != 0) && (KIND != KIND_NN) && negligible_at<KIND>(lk, ubmin, lg_ubmin, c1);
+    const bool take_all = (k == 0) || moot;
+    bool is_in = false, is_unc = false, negl = false;
+    if (active) {
+        if (take_all) is_in = true;
+        else if (lbv <= uk) { is_in = rivals <= k - 1; is_unc = !is_in; }
+        if (KIND != KIND_NN) negl = negligible_at<KIND>(lbv, ubmin, lg_ubmin, c1);
+    }
+    const uint32_t nin_all = __popc(__ballot_sync(FULL, is_in)), nunc_all = __popc(__ballot_sync(FULL, is_unc));
+    const bool list_in = is_in && !negl, list_unc = is_unc && !negl;
+    const uint32_t bin = __ballot_sync(FULL, list_in), bun = __ballot_sync(FULL, list_unc);
+    const uint32_t nin = __popc(bin), nunc = __popc(bun), lt = (1u << lane) - 1u;
+    // IN colours first, UNCERTAIN ones after them, palette order in both; s_cidx mirrors the kernel's
+    // general layout (IN from the front, UNCERTAIN from the back)
+    if (list_in) { uint32_t pos = __popc(bin & lt); s_cand[pos] = p; s_cidx[pos] = lane; }
+    if (list_unc) { uint32_t pos = __popc(bun & lt); s_cand[nin + pos] = p; s_cidx[n - 1 - pos] = lane; }
+    if (lane == 0) {
+        out->nin = nin; out->nunc = nunc; out->nin_all = nin_all; out->nunc_all = nunc_all;
+        out->nhit = nhit; out->take_all = take_all ? 1u : 0u; out->lbmin = lbmin; out->ubmin = ubmin;
+    }
+}
+
 // Persistent CTAs: the grid is a few CTAs per SM; each stages the colour tables and the palette
 // once and then walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
 template <int KIND, int MODE>
@@ -208,6 +306,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_remap_fast(const FastArgs a
     __shared__ uint32_t s_lbmin, s_ubmin, s_uk, s_lk;
     __shared__ uint32_t s_wcnt[2][FAST_THREADS / 32];
     __shared__ uint32_t s_nhit, s_next, s_geo[3];
+    __shared__ TileClass s_cls;
     __shared__ uint32_t s_hit[FAST_MAX_HITS];
     __shared__ uint32_t s_chan[3][16];    // identity channel value of each brick coordinate
 
@@ -321,20 +420,20 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_remap_fast(const FastArgs a
         float lo[3], hi[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) { lo[c] = key2f(s_box[c]) - PAD; hi[c] = key2f(s_box[3 + c]) + PAD; }
+        uint32_t nin = 0, nunc = 0;          // list lengths (negligible colours dropped)
+        uint32_t nin_all = 0, nunc_all = 0;  // class sizes
+        uint32_t nhit_raw = 0;
+        bool take_all = false;
+        float lbmin = 0.f, ubmin = 0.f;
+        if (n <= 32) {
+            if (warp == 0) classify_one_warp<KIND>(lane, n, k, c1, lo, hi, s_box, s_pal, a.pal_rgb, s_cand, s_cidx, s_hit, &s_cls);
+            __syncthreads();
+            nin = s_cls.nin; nunc = s_cls.nunc; nin_all = s_cls.nin_all; nunc_all = s_cls.nunc_all;
+            nhit_raw = s_cls.nhit; take_all = s_cls.take_all != 0; lbmin = s_cls.lbmin; ubmin = s_cls.ubmin;
+        } else {
         for (uint32_t t = tid; t < n; t += FAST_THREADS) {
-            float4 p = s_pal[t];
-            float pv[3] = {p.x, p.y, p.z};
-            float lbv = 0.f, ubv = 0.f;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float below = lo[c] - pv[c], above = pv[c] - hi[c];
-                float ex = fmaxf(0.f, fmaxf(below, above));
-                float fx = fmaxf(fabsf(pv[c] - lo[c]), fabsf(pv[c] - hi[c]));
-                lbv = fmaf(ex, ex, lbv);
-                ubv = fmaf(fx, fx, ubv);
-            }
-            lbv *= (1.0f - 2e-6f);
-            ubv *= (1.0f + 2e-6f);
+            float lbv, ubv;
+            bounds_of(s_pal[t], lo, hi, lbv, ubv);
             s_lb[t] = lbv;
             s_ub[t] = ubv;
             atomicMin(&s_lbmin, __float_as_uint(lbv));
@@ -351,7 +450,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_remap_fast(const FastArgs a
         __syncthreads();
 
         // ---- 3./4. classification --------------------------------------------------------
-        const float ubmin = __uint_as_float(s_ubmin), lbmin = __uint_as_float(s_lbmin);
+        ubmin = __uint_as_float(s_ubmin);
+        lbmin = __uint_as_float(s_lbmin);
         const float lg_ubmin = KIND == 1 ? lg2_approx(ubmin) : 0.f;
         if (k != 0) {
             // U_k: k-th smallest UB (every pixel's k-th neighbour is at most this far);
@@ -373,9 +473,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_remap_fast(const FastArgs a
         // If even the k-th neighbour's weight is negligible everywhere in the tile, "nearest k" no
         // longer constrains anything: every colour that can matter is taken, nothing is chosen.
         const bool moot = (k != 0) && (KIND != KIND_NN) && negligible_at<KIND>(__uint_as_float(s_lk), ubmin, lg_ubmin, c1);
-        const bool take_all = (k == 0) || moot;
-        uint32_t nin = 0, nunc = 0;          // list lengths (negligible colours dropped)
-        uint32_t nin_all = 0, nunc_all = 0;  // class sizes
+        take_all = (k == 0) || moot;
         for (uint32_t t0 = 0; t0 < n; t0 += FAST_THREADS) {
             uint32_t t = t0 + tid;
             bool is_in = false, is_unc = false, negl = false;
@@ -414,6 +512,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_remap_fast(const FastArgs a
         for (uint32_t j = tid; j < nin; j += FAST_THREADS) s_cand[j] = s_pal[s_cidx[j]];
         for (uint32_t j = tid; j < nunc; j += FAST_THREADS) s_cand[nin + j] = s_pal[s_cidx[n - 1 - j]];
         __syncthreads();
+        nhit_raw = s_nhit;
+        }  // general (n > 32) classification
         if (a.stats && tid == 0) {
             atomicAdd(&a.stats[min(nunc, 63u)], 1u);
             atomicAdd(&a.stats[64 + min(nin, 63u)], 1u);
@@ -422,8 +522,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_remap_fast(const FastArgs a
         const int kp = (int)k - (int)nin_all;
         const bool choose = !take_all && kp > 0 && (int)nunc_all > kp && (int)nunc > kp;
         const uint32_t direct = (take_all || kp <= 0 || choose) ? nin : nin + nunc;  // listed colours taken unconditionally
-        const uint32_t nhit = min(s_nhit, (uint32_t)FAST_MAX_HITS);
-        const bool hits_overflow = s_nhit > FAST_MAX_HITS;
+        const uint32_t nhit = min(nhit_raw, (uint32_t)FAST_MAX_HITS);
+        const bool hits_overflow = nhit_raw > FAST_MAX_HITS;
 
         // weight shift
         float c0 = 0.f;
