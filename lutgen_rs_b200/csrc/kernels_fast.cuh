@@ -195,6 +195,45 @@ __device__ __noinline__ LoopAcc select_accumulate_loop(const float4* __restrict_
     return LoopAcc{n0, n1, n2, den, 0};
 }
 
+// Many uncertain colours, moderate kp (<= 32): one pass keeping the kp + 1 best (distance, index)
+// pairs sorted in a small per-thread array (local memory, L1 resident); about 10 instructions per
+// colour plus the occasional insertion, instead of kp + 1 full passes.
+template <int KIND>
+__device__ __noinline__ LoopAcc select_accumulate_insert(const float4* __restrict__ unc, int mU, int kp, float L, float A, float B, float c1,
+                                                         float c0) {
+    constexpr int CAP = 33;
+    float td[CAP];
+    unsigned short tj[CAP];
+    const int keep = kp + 1;  // the extra one decides whether the k-boundary is a near-tie
+    int cnt = 0;
+    for (int j = 0; j < mU; ++j) {
+        float d = dist3(L, A, B, unc[j]);
+        if (cnt < keep || d < td[cnt - 1]) {
+            int i = cnt < keep ? cnt : keep - 1;
+            while (i > 0 && td[i - 1] > d) {
+                td[i] = td[i - 1];
+                tj[i] = tj[i - 1];
+                --i;
+            }
+            td[i] = d;
+            tj[i] = (unsigned short)j;
+            if (cnt < keep) ++cnt;
+        }
+    }
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f, den = 0.f;
+    if (cnt < keep) return LoopAcc{n0, n1, n2, den, 1};  // NaNs swallowed candidates: exact kernel decides
+    for (int i = 0; i < kp; ++i) {
+        float4 p = unc[tj[i]];
+        float w = fast_weight<KIND>(td[i], c1, c0);
+        n0 = fmaf(p.x, w, n0);
+        n1 = fmaf(p.y, w, n1);
+        n2 = fmaf(p.z, w, n2);
+        den += w;
+    }
+    float gap = td[kp] - td[kp - 1];
+    return LoopAcc{n0, n1, n2, den, gap * gap <= FAST_TIE_TOL * td[kp] ? 1 : 0};
+}
+
 // Dynamic shared memory (bytes): pal[n] float4 | cand[n] float4 | lb[n] f32 | ub[n] f32 |
 // cand_idx[n] u32 | lab[3][tile] f32 | rgb[tile] u32
 __host__ __device__ inline size_t fast_smem_bytes(uint32_t n, uint32_t tile) {
@@ -319,6 +358,12 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_remap_fast(const FastArgs a
     uint32_t* s_cidx = reinterpret_cast<uint32_t*>(s_ub + n);
     float* s_lab = reinterpret_cast<float*>(s_cidx + n);
     uint32_t* s_rgb = reinterpret_cast<uint32_t*>(s_lab + 3 * tile);
+    // scratch for the sorted bound arrays of the general classification: the candidate buffer,
+    // which is only filled afterwards (2 * n_pad floats <= n float4 because n_pad < 2n)
+    uint32_t n_pad = 1;
+    while (n_pad < n) n_pad <<= 1;
+    float* srt_u = reinterpret_cast<float*>(s_cand);
+    float* srt_l = srt_u + n_pad;
 
     const uint32_t cs = a.f.cs, csm1 = a.f.csm1;
     const uint32_t begin = (uint32_t)a.f.begin, end = (uint32_t)(a.f.begin + a.f.count);  // < 2^32 by construction
@@ -456,17 +501,27 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_remap_fast(const FastArgs a
         if (k != 0) {
             // U_k: k-th smallest UB (every pixel's k-th neighbour is at most this far);
             // L_k: k-th smallest LB (... and at least this far)
-            for (uint32_t t = tid; t < n; t += FAST_THREADS) {
-                float u = s_ub[t], l = s_lb[t];
-                uint32_t rank_u = 0, rank_l = 0;
-                for (uint32_t q = 0; q < n; ++q) {
-                    float uq = s_ub[q], lq = s_lb[q];
-                    rank_u += (uq < u || (uq == u && q < t)) ? 1u : 0u;
-                    rank_l += (lq < l || (lq == l && q < t)) ? 1u : 0u;
-                }
-                if (rank_u == k - 1) s_uk = __float_as_uint(u);
-                if (rank_l == k - 1) s_lk = __float_as_uint(l);
+            // Sorted copies of both bound arrays (CTA-wide bitonic network in the not-yet-used
+            // candidate buffer): O(n log^2 n / 256) per thread instead of O(n) rank loops.
+            for (uint32_t i = tid; i < n_pad; i += FAST_THREADS) {
+                srt_u[i] = i < n ? s_ub[i] : INFINITY;
+                srt_l[i] = i < n ? s_lb[i] : INFINITY;
             }
+            __syncthreads();
+            for (uint32_t size = 2; size <= n_pad; size <<= 1) {
+                for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (uint32_t i = tid; i < (n_pad >> 1); i += FAST_THREADS) {
+                        uint32_t lo_i = ((i & ~(stride - 1)) << 1) | (i & (stride - 1)), hi_i = lo_i + stride;
+                        bool up = (lo_i & size) == 0;
+                        float a0 = srt_u[lo_i], a1 = srt_u[hi_i], b0v = srt_l[lo_i], b1v = srt_l[hi_i];
+                        float amin = fminf(a0, a1), amax = fmaxf(a0, a1), bmin = fminf(b0v, b1v), bmax = fmaxf(b0v, b1v);
+                        srt_u[lo_i] = up ? amin : amax; srt_u[hi_i] = up ? amax : amin;
+                        srt_l[lo_i] = up ? bmin : bmax; srt_l[hi_i] = up ? bmax : bmin;
+                    }
+                    __syncthreads();
+                }
+            }
+            if (tid == 0) { s_uk = __float_as_uint(srt_u[k - 1]); s_lk = __float_as_uint(srt_l[k - 1]); }
             __syncthreads();
         }
         const float uk = __uint_as_float(s_uk);
@@ -482,8 +537,13 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_remap_fast(const FastArgs a
                 if (take_all) {
                     is_in = true;
                 } else if (l <= uk) {
-                    uint32_t rivals = 0;
-                    for (uint32_t q = 0; q < n; ++q) rivals += (q != t && s_lb[q] <= u) ? 1u : 0u;
+                    // rivals = #{q != t : LB(q) <= UB(t)} = upper_bound(sorted LB, UB(t)) - 1 (t counts itself)
+                    uint32_t lo_b = 0, hi_b = n;
+                    while (lo_b < hi_b) {
+                        uint32_t mid = (lo_b + hi_b) >> 1;
+                        if (srt_l[mid] <= u) lo_b = mid + 1; else hi_b = mid;
+                    }
+                    uint32_t rivals = lo_b - 1;
                     is_in = rivals <= k - 1;
                     is_unc = !is_in;
                 }
@@ -602,7 +662,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_remap_fast(const FastArgs a
                 else if (nunc <= 8) risky = select_accumulate<8, KIND>(unc, (int)nunc, kp, L, A, B, c1, c0, n0, n1, n2, den);
                 else if (nunc <= 16) risky = select_accumulate<16, KIND>(unc, (int)nunc, kp, L, A, B, c1, c0, n0, n1, n2, den);
                 else {
-                    LoopAcc la = select_accumulate_loop<KIND>(unc, (int)nunc, kp, L, A, B, c1, c0);
+                    LoopAcc la = kp <= 32 ? select_accumulate_insert<KIND>(unc, (int)nunc, kp, L, A, B, c1, c0)
+                                          : select_accumulate_loop<KIND>(unc, (int)nunc, kp, L, A, B, c1, c0);
                     n0 += la.n0; n1 += la.n1; n2 += la.n2; den += la.den;
                     risky = la.risky != 0;
                 }
