@@ -207,7 +207,10 @@ __device__ __noinline__ LoopAcc select_accumulate_insert(const float4* __restric
     const int keep = kp + 1;  // the extra one decides whether the k-boundary is a near-tie
     int cnt = 0;
     for (int j = 0; j < mU; ++j) {
-        float d = dist3(L, A, B, unc[j]);
+        float4 pj = unc[j];
+        // the list is sorted by LB (in .w): nothing from here on can beat the current (kp+1)-th best
+        if (cnt == keep && pj.w >= td[keep - 1]) break;
+        float d = dist3(L, A, B, pj);
         if (cnt < keep || d < td[cnt - 1]) {
             int i = cnt < keep ? cnt : keep - 1;
             while (i > 0 && td[i - 1] > d) {
@@ -328,7 +331,21 @@ __device__ __forceinline__ void classify_one_warp(uint32_t lane, uint32_t n, uin
     // IN colours first, UNCERTAIN ones after them, palette order in both; s_cidx mirrors the kernel's
     // general layout (IN from the front, UNCERTAIN from the back)
     if (list_in) { uint32_t pos = __popc(bin & lt); s_cand[pos] = p; s_cidx[pos] = lane; }
-    if (list_unc) { uint32_t pos = __popc(bun & lt); s_cand[nin + pos] = p; s_cidx[n - 1 - pos] = lane; }
+    if (KIND != KIND_NN && nunc > 16) {
+        // large uncertain sets are listed by ascending LB (kept in .w) so the insertion selection can
+        // stop at the first colour whose LB already exceeds the thread's current k-th distance
+        uint32_t rank = 0;
+        for (uint32_t q = 0; q < 32; ++q) {
+            float lq = __shfl_sync(FULL, lbv, q);
+            rank += (((bun >> q) & 1u) && (lq < lbv || (lq == lbv && q < lane))) ? 1u : 0u;
+        }
+        if (list_unc) { p.w = lbv; s_cand[nin + rank] = p; s_cidx[n - 1 - rank] = lane; }
+    } else if (list_unc) {
+        uint32_t pos = __popc(bun & lt);
+        p.w = lbv;
+        s_cand[nin + pos] = p;
+        s_cidx[n - 1 - pos] = lane;
+    }
     if (lane == 0) {
         out->nin = nin; out->nunc = nunc; out->nin_all = nin_all; out->nunc_all = nunc_all;
         out->nhit = nhit; out->take_all = take_all ? 1u : 0u; out->lbmin = lbmin; out->ubmin = ubmin;
@@ -570,7 +587,20 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_remap_fast(const FastArgs a
             __syncthreads();
         }
         for (uint32_t j = tid; j < nin; j += FAST_THREADS) s_cand[j] = s_pal[s_cidx[j]];
-        for (uint32_t j = tid; j < nunc; j += FAST_THREADS) s_cand[nin + j] = s_pal[s_cidx[n - 1 - j]];
+        for (uint32_t j = tid; j < nunc; j += FAST_THREADS) {
+            uint32_t t = s_cidx[n - 1 - j];
+            float4 p = s_pal[t];
+            p.w = s_lb[t];
+            uint32_t pos = j;
+            if (KIND != KIND_NN && nunc > 16) {  // ascending LB, see classify_one_warp
+                pos = 0;
+                for (uint32_t i = 0; i < nunc; ++i) {
+                    float li = s_lb[s_cidx[n - 1 - i]];
+                    pos += (li < p.w || (li == p.w && i < j)) ? 1u : 0u;
+                }
+            }
+            s_cand[nin + pos] = p;
+        }
         __syncthreads();
         nhit_raw = s_nhit;
         }  // general (n > 32) classification
