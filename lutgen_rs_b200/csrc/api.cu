@@ -3,6 +3,7 @@
 // Host-side plumbing only: argument validation (returning status codes where
 // the reference panics), device buffers, streams, host<->device copies and
 // kernel dispatch. All arithmetic lives in the kernels_*.cuh headers.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -206,7 +207,19 @@ int upload_offsets(lutgen_remapper* r) {
     if (rc != LUTGEN_OK) return rc;
     size_t K = (size_t)r->d.iterations;
     if (K == 0) return LUTGEN_OK;
-    CU_TRY(cudaMemcpyAsync(r->offsets, off.data(), sizeof(short) * 4 * K, cudaMemcpyHostToDevice, g.stream));
+    // second copy ordered by (blue, green, red): consecutive gathers of the order-independent
+    // integer-sum mode then walk the NN table almost linearly (L1 hits)
+    std::vector<size_t> order(K);
+    for (size_t k = 0; k < K; ++k) order[k] = k;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+        if (off[4 * a + 2] != off[4 * b + 2]) return off[4 * a + 2] < off[4 * b + 2];
+        if (off[4 * a + 1] != off[4 * b + 1]) return off[4 * a + 1] < off[4 * b + 1];
+        return off[4 * a] < off[4 * b];
+    });
+    off.resize(8 * K);
+    for (size_t k = 0; k < K; ++k)
+        for (int c = 0; c < 4; ++c) off[4 * (K + k) + c] = off[4 * order[k] + c];
+    CU_TRY(cudaMemcpyAsync(r->offsets, off.data(), sizeof(short) * 8 * K, cudaMemcpyHostToDevice, g.stream));
     CU_TRY(cudaStreamSynchronize(g.stream));
     return LUTGEN_OK;
 }
@@ -390,7 +403,7 @@ int launch_sampling(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
     uint32_t log2k = 0;
     while (pow2 && (1ull << log2k) < K) ++log2k;
     if (pow2)
-        k_sampling<MODE, false><<<blocks_for(f.count, 256), 256, 0, s>>>(f, r->nn_table, r->offsets, (uint32_t)K, log2k);
+        k_sampling<MODE, false><<<blocks_for(f.count, 256), 256, 0, s>>>(f, r->nn_table, r->offsets + K, (uint32_t)K, log2k);
     else
         k_sampling<MODE, true><<<blocks_for(f.count, 256), 256, 0, s>>>(f, r->nn_table, r->offsets, (uint32_t)K, 0);
     LAUNCH_CHECK();
@@ -787,7 +800,7 @@ int lutgen_cuda_remapper_create(const lutgen_remapper_desc* desc, lutgen_remappe
     if (desc->kind == LUTGEN_SAMPLING) {
         size_t K = (size_t)desc->iterations, Ka = K ? K : 1;
         r->noise.assign(4 * K, 0.0);
-        CU_TRY_R(cudaMalloc((void**)&r->offsets, sizeof(short4) * Ka));
+        CU_TRY_R(cudaMalloc((void**)&r->offsets, sizeof(short4) * Ka * 2));  // iteration order + sorted copy
         if (K) {
             CU_TRY_R(g.misc.reserve(sizeof(double) * 4 * K));
             k_philox_normals<<<blocks_for(2 * K, 128), 128, 0, g.stream>>>((double*)g.misc.p, K, desc->mean, desc->std_dev, desc->seed);

@@ -36,6 +36,7 @@ constexpr int FAST_THREADS = 256;
 constexpr int FAST_MAX_EPT = 4;                    // entries per thread
 constexpr int FAST_TILE_MAX = FAST_THREADS * FAST_MAX_EPT;
 constexpr int FAST_MAX_HITS = 16;
+constexpr uint32_t FAST_BUCKET_MAX = 16;           // uncertain sets up to this size use the register buckets (measured: 16 beats 8)
 constexpr int KIND_NN = 3;
 constexpr float FAST_NEGLIGIBLE_LOG2 = -24.0f;     // step 4 threshold
 constexpr float FAST_TIE_TOL = 5e-10f;             // (gap)^2 <= TOL * d  ->  recompute exactly
@@ -331,7 +332,7 @@ __device__ __forceinline__ void classify_one_warp(uint32_t lane, uint32_t n, uin
     // IN colours first, UNCERTAIN ones after them, palette order in both; s_cidx mirrors the kernel's
     // general layout (IN from the front, UNCERTAIN from the back)
     if (list_in) { uint32_t pos = __popc(bin & lt); s_cand[pos] = p; s_cidx[pos] = lane; }
-    if (KIND != KIND_NN && nunc > 16) {
+    if (KIND != KIND_NN && nunc > FAST_BUCKET_MAX) {
         // large uncertain sets are listed by ascending LB (kept in .w) so the insertion selection can
         // stop at the first colour whose LB already exceeds the thread's current k-th distance
         uint32_t rank = 0;
@@ -592,7 +593,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_remap_fast(const FastArgs a
             float4 p = s_pal[t];
             p.w = s_lb[t];
             uint32_t pos = j;
-            if (KIND != KIND_NN && nunc > 16) {  // ascending LB, see classify_one_warp
+            if (KIND != KIND_NN && nunc > FAST_BUCKET_MAX) {  // ascending LB, see classify_one_warp
                 pos = 0;
                 for (uint32_t i = 0; i < nunc; ++i) {
                     float li = s_lb[s_cidx[n - 1 - i]];
@@ -690,7 +691,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_remap_fast(const FastArgs a
                 const float4* unc = s_cand + nin;
                 if (nunc <= 4) risky = select_accumulate<4, KIND>(unc, (int)nunc, kp, L, A, B, c1, c0, n0, n1, n2, den);
                 else if (nunc <= 8) risky = select_accumulate<8, KIND>(unc, (int)nunc, kp, L, A, B, c1, c0, n0, n1, n2, den);
-                else if (nunc <= 16) risky = select_accumulate<16, KIND>(unc, (int)nunc, kp, L, A, B, c1, c0, n0, n1, n2, den);
+                else if (FAST_BUCKET_MAX >= 16 && nunc <= 16) risky = select_accumulate<16, KIND>(unc, (int)nunc, kp, L, A, B, c1, c0, n0, n1, n2, den);
                 else {
                     LoopAcc la = kp <= 32 ? select_accumulate_insert<KIND>(unc, (int)nunc, kp, L, A, B, c1, c0)
                                           : select_accumulate_loop<KIND>(unc, (int)nunc, kp, L, A, B, c1, c0);
