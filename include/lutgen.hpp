@@ -233,5 +233,21 @@ public:
     }
 };
 
+// GaussianBlurRemapper::new(palette, radius, lum_factor, preserve)                gaussian_blur.rs:34-53
+// The CLI's and Studio's default. Like the reference type it implements GenerateLut only
+// (gaussian_blur.rs:512-541): the remap_* members are not exposed.
+class GaussianBlurRemapper : private InterpolatedRemapper {
+public:
+    GaussianBlurRemapper(const Palette& palette, double radius, double lum_factor, bool preserve) {
+        auto d = desc(LUTGEN_BLUR, palette);
+        d.param = radius; d.lum_factor = lum_factor; d.preserve = preserve;
+        create(d);
+    }
+    using InterpolatedRemapper::generate_lut;
+    using InterpolatedRemapper::par_generate_lut;
+    using InterpolatedRemapper::generate_lut_with_interrupt;
+    using InterpolatedRemapper::par_generate_lut_with_interrupt;
+};
+
 }  // namespace interpolation
 }  // namespace lutgen

@@ -60,6 +60,8 @@ extern "C" {
 #define LUTGEN_LINEAR 2   /* LinearRemapper     rbf.rs:153-159  w = d                  */
 #define LUTGEN_NEAREST 3  /* NearestNeighborRemapper  nearest_neighbor.rs:11-61        */
 #define LUTGEN_SAMPLING 4 /* GaussianSamplingRemapper gaussian_sample.rs:18-76         */
+#define LUTGEN_BLUR 5     /* GaussianBlurRemapper     gaussian_blur.rs:26-542 (GenerateLut only;
+                             param = radius; the CLI's and Studio's default algorithm)  */
 
 /* Constructor arguments of every remapper, flattened.
  *   Gaussian/Shepard/Linear::new(palette, [shape|power], nearest, lum_factor, preserve_lum)  rbf.rs:126-140

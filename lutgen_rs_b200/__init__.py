@@ -13,11 +13,11 @@ entry points (torch tensors, torch.distributed over NCCL).
 """
 from . import _native, identity, interpolation
 from ._native import LutgenError, LutgenPanic
-from .interpolation import (AbortFlag, GaussianRemapper, GaussianSamplingRemapper, InterpolatedRemapper,
+from .interpolation import (AbortFlag, GaussianBlurRemapper, GaussianRemapper, GaussianSamplingRemapper, InterpolatedRemapper,
                             LinearRemapper, NearestNeighborRemapper, ShepardRemapper)
 
 __all__ = [
     "identity", "interpolation", "LutgenError", "LutgenPanic", "AbortFlag", "InterpolatedRemapper",
-    "GaussianRemapper", "ShepardRemapper", "LinearRemapper", "NearestNeighborRemapper",
+    "GaussianRemapper", "GaussianBlurRemapper", "ShepardRemapper", "LinearRemapper", "NearestNeighborRemapper",
     "GaussianSamplingRemapper",
 ]

@@ -12,7 +12,7 @@ SO_PATH = os.path.join(HERE, "liblutgen_cuda.so")
 
 OK, ABORTED = 0, 1
 ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED = -1, -2, -3, -4
-GAUSSIAN, SHEPARD, LINEAR, NEAREST, SAMPLING = range(5)
+GAUSSIAN, SHEPARD, LINEAR, NEAREST, SAMPLING, BLUR = range(6)
 
 # Every symbol include/lutgen_cuda.h declares (tests check the .so exports them all).
 EXPORTS = [

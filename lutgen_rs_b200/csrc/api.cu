@@ -18,6 +18,7 @@
 
 #include "../../include/lutgen_cuda.h"
 #include "kernels_apply.cuh"
+#include "kernels_blur.cuh"
 #include "kernels_exact.cuh"
 #include "kernels_fast.cuh"
 
@@ -144,6 +145,18 @@ struct lutgen_remapper {
     float* upal_ab = nullptr;
     float4* upal_lab32 = nullptr;
     double* upal_lab = nullptr;
+    // GaussianBlurRemapper: f32 palette ([l*lum, a, b] and what a cell stores), tap weights, and the
+    // blurred volume of the last level asked for (row shards of one CLUT reuse it)
+    float* blur_pal3 = nullptr;
+    float* blur_out3 = nullptr;
+    float* blur_kernel = nullptr;
+    int blur_klen = 0;
+    mutable float* blur_vol[2] = {nullptr, nullptr};
+    mutable size_t blur_vol_cap = 0;
+    mutable uint8_t* blur_chan = nullptr;
+    mutable int blur_level = 0;       // level whose blurred volume sits in blur_vol[blur_result]
+    mutable int blur_result = 0;
+    mutable cudaEvent_t blur_ev = nullptr;
 };
 
 namespace {
@@ -410,6 +423,93 @@ int launch_sampling(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
     return LUTGEN_OK;
 }
 
+// ---- GaussianBlurRemapper -----------------------------------------------------------------
+// generate_lut_inner / par_generate_lut_inner, gaussian_blur.rs:197-431 (par semantics: the NN
+// hint restarts per (r, g) row, which is what the CLI and Studio call).
+int ensure_blur_volume(const lutgen_remapper* r, uint32_t level, cudaStream_t s) {
+    std::unique_lock<std::mutex> lk(r->mu);
+    if (!r->blur_ev) CU_TRY(cudaEventCreateWithFlags(&r->blur_ev, cudaEventDisableTiming));
+    if (r->blur_level != (int)level) {
+        const uint32_t size = level * level, ch = r->d.preserve ? 2u : 3u;
+        const size_t cells = (size_t)size * size * size, bytes = cells * ch * sizeof(float);
+        if (r->blur_vol_cap < bytes) {
+            for (int i = 0; i < 2; ++i) {
+                if (r->blur_vol[i]) CU_TRY(cudaFree(r->blur_vol[i]));
+                r->blur_vol[i] = nullptr;
+            }
+            r->blur_vol_cap = 0;
+            CU_TRY(cudaMalloc((void**)&r->blur_vol[0], bytes));
+            CU_TRY(cudaMalloc((void**)&r->blur_vol[1], bytes));
+            r->blur_vol_cap = bytes;
+        }
+        if (!r->blur_chan) CU_TRY(cudaMalloc((void**)&r->blur_chan, 2048));
+        // (i as f32 * scale).round() as u8, scale = 255.0 / (size - 1) as f32   (gaussian_blur.rs:200, 206-210)
+        std::vector<uint8_t> chan(size);
+        const float scale = 255.0f / (float)(size - 1);
+        for (uint32_t i = 0; i < size; ++i) {
+            float v = roundf((float)i * scale);
+            chan[i] = !(v > 0.0f) ? 0 : (v >= 255.0f ? 255 : (uint8_t)v);
+        }
+        CU_TRY(cudaMemcpyAsync(r->blur_chan, chan.data(), size, cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaStreamSynchronize(s));  // `chan` is a stack-lifetime pageable buffer
+        const float lum = (float)r->d.lum_factor;
+        const float step = 1.0f / (float)size, threshold_sq = step * step * 0.5f;
+        float* a = r->blur_vol[0];
+        float* b = r->blur_vol[1];
+        unsigned rows = size * size;
+        unsigned grid_nn = blocks_for(rows, BLUR_ROW_WARPS);
+        if (grid_nn > (unsigned)g.sm_count * 8u) grid_nn = (unsigned)g.sm_count * 8u;
+        k_blur_nn_volume<<<grid_nn, BLUR_ROW_WARPS * 32, 0, s>>>(a, size, ch, r->blur_chan, r->blur_pal3, r->blur_out3, r->n, lum, threshold_sq, g.tables);
+        LAUNCH_CHECK();
+        static bool attr_done = false;
+        if (!attr_done) {
+            CU_TRY(cudaFuncSetAttribute(k_blur_inner, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            CU_TRY(cudaFuncSetAttribute(k_blur_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            attr_done = true;
+        }
+        const int klen = r->blur_klen;
+        // pass 1: B axis (innermost)
+        const uint32_t row_len = size * ch;
+        uint32_t lines = 12288u / row_len;
+        if (lines < 1) lines = 1;
+        size_t smem1 = ((size_t)klen + (size_t)lines * row_len) * sizeof(float);
+        k_blur_inner<<<blocks_for(rows, lines), 256, smem1, s>>>(a, b, size, ch, lines, r->blur_kernel, klen);
+        LAUNCH_CHECK();
+        // pass 2: R axis (stride size^2 cells); pass 3: G axis (stride size cells)
+        uint32_t cols = 12288u / size;
+        if (cols > 32) cols = 32;
+        if (cols < 1) cols = 1;
+        size_t smem2 = ((size_t)klen + (size_t)size * cols) * sizeof(float);
+        {
+            uint32_t inner = size * size * ch, groups = (inner + cols - 1) / cols;
+            k_blur_strided<<<groups, 256, smem2, s>>>(b, a, size, inner, groups, 0u, inner, cols, r->blur_kernel, klen);
+            LAUNCH_CHECK();
+        }
+        {
+            uint32_t inner = size * ch, groups = (inner + cols - 1) / cols;
+            k_blur_strided<<<groups * size, 256, smem2, s>>>(a, b, size, inner, groups, size * size * ch, inner, cols, r->blur_kernel, klen);
+            LAUNCH_CHECK();
+        }
+        r->blur_result = 1;
+        r->blur_level = (int)level;
+        CU_TRY(cudaEventRecord(r->blur_ev, s));
+    }
+    CU_TRY(cudaStreamWaitEvent(s, r->blur_ev, 0));
+    return LUTGEN_OK;
+}
+
+int launch_blur_lut(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
+    uint32_t level = 2;
+    while (level * level < f.cs) ++level;
+    int rc = ensure_blur_volume(r, level, s);
+    if (rc != LUTGEN_OK) return rc;
+    if (f.count == 0) return LUTGEN_OK;
+    const uint32_t ch = r->d.preserve ? 2u : 3u;
+    k_blur_to_lut<<<blocks_for(f.count, 256), 256, 0, s>>>(r->blur_vol[r->blur_result], f.cs, ch, r->blur_chan, f.out, f.begin, f.count, g.tables);
+    LAUNCH_CHECK();
+    return LUTGEN_OK;
+}
+
 template <int MODE>
 int launch_remap(const Front& f, const lutgen_remapper* r, cudaStream_t s);
 
@@ -451,6 +551,9 @@ int launch_remap(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
     switch (r->d.kind) {
         case LUTGEN_NEAREST: return launch_nn<MODE>(f, r, s);
         case LUTGEN_SAMPLING: return launch_sampling<MODE>(f, r, s);
+        case LUTGEN_BLUR:
+            if (MODE == FRONT_LUT) return launch_blur_lut(f, r, s);
+            return fail(LUTGEN_ERR_INVALID, "GaussianBlurRemapper implements GenerateLut only (gaussian_blur.rs:512-541), not remap_image");
         default: return launch_rbf<MODE>(f, r, s);
     }
 }
@@ -743,6 +846,13 @@ int lutgen_cuda_remapper_destroy(lutgen_remapper* r) {
         cudaFree(r->upal_lab);
         if (r->nn_table_ev) cudaEventDestroy(r->nn_table_ev);
         if (r->full_table_ev) cudaEventDestroy(r->full_table_ev);
+        cudaFree(r->blur_pal3);
+        cudaFree(r->blur_out3);
+        cudaFree(r->blur_kernel);
+        cudaFree(r->blur_vol[0]);
+        cudaFree(r->blur_vol[1]);
+        cudaFree(r->blur_chan);
+        if (r->blur_ev) cudaEventDestroy(r->blur_ev);
     }
     delete r;
     return LUTGEN_OK;
@@ -753,7 +863,12 @@ int lutgen_cuda_remapper_create(const lutgen_remapper_desc* desc, lutgen_remappe
     if (rc) return rc;
     if (!desc || !out) return fail(LUTGEN_ERR_INVALID, "NULL argument");
     *out = nullptr;
-    if (desc->kind < LUTGEN_GAUSSIAN || desc->kind > LUTGEN_SAMPLING) return fail(LUTGEN_ERR_INVALID, "unknown remapper kind %d", desc->kind);
+    if (desc->kind < LUTGEN_GAUSSIAN || desc->kind > LUTGEN_BLUR) return fail(LUTGEN_ERR_INVALID, "unknown remapper kind %d", desc->kind);
+    if (desc->kind == LUTGEN_BLUR) {
+        if (desc->palette_len == 0) return fail(LUTGEN_ERR_INVALID, "empty palette (palette_oklab[hint] is out of bounds, gaussian_blur.rs:58)");
+        float r3 = ceilf((float)desc->param * 3.0f);
+        if (r3 > 4096.0f) return fail(LUTGEN_ERR_UNSUPPORTED, "blur radius %g needs more than 8193 taps", desc->param);
+    }
     if (desc->palette_len && !desc->palette) return fail(LUTGEN_ERR_INVALID, "palette is NULL");
     if (desc->palette_len > (1u << 20)) return fail(LUTGEN_ERR_UNSUPPORTED, "palette of %llu colours (limit 2^20)", (unsigned long long)desc->palette_len);
     if (desc->kind == LUTGEN_SAMPLING) {
@@ -811,6 +926,28 @@ int lutgen_cuda_remapper_create(const lutgen_remapper_desc* desc, lutgen_remappe
             int rc2 = upload_offsets(r);
             if (rc2) return bail(rc2);
         }
+    }
+    if (desc->kind == LUTGEN_BLUR) {
+        // GaussianBlurRemapper::new + build_kernel (gaussian_blur.rs:34-53, 87-96), all f32. expf is
+        // the host libm's, the same one a CPU build of the reference would call.
+        const float lum = (float)desc->lum_factor, radius = (float)desc->param;
+        CU_TRY_R(cudaMalloc((void**)&r->blur_pal3, sizeof(float) * 3 * na));
+        CU_TRY_R(cudaMalloc((void**)&r->blur_out3, sizeof(float) * 3 * na));
+        k_blur_palette<<<blocks_for(n, 128), 128, 0, g.stream>>>(r->pal_rgb4, r->n, lum, g.tables->decode, r->blur_pal3, r->blur_out3);
+        g_launches.fetch_add(1);
+        CU_TRY_R(cudaGetLastError());
+        float h3 = ceilf(radius * 3.0f);
+        int half = (h3 != h3) ? 0 : (h3 < -1e6f ? -1000000 : (int)h3);  // `as i32`: NaN -> 0
+        const float two_sigma_sq = 2.0f * radius * radius;
+        std::vector<float> kw;
+        for (int i = -half; i <= half; ++i) kw.push_back(expf((float)(-(i * i)) / two_sigma_sq));
+        float sum = 0.0f;
+        for (float w : kw) sum += w;
+        for (float& w : kw) w /= sum;
+        r->blur_klen = (int)kw.size();
+        CU_TRY_R(cudaMalloc((void**)&r->blur_kernel, sizeof(float) * (kw.size() + 1)));
+        if (!kw.empty()) CU_TRY_R(cudaMemcpyAsync(r->blur_kernel, kw.data(), sizeof(float) * kw.size(), cudaMemcpyHostToDevice, g.stream));
+        CU_TRY_R(cudaStreamSynchronize(g.stream));
     }
     if (desc->kind == LUTGEN_NEAREST || desc->kind == LUTGEN_SAMPLING) {
         // unique colours, first occurrence kept (see lutgen_remapper::un)

@@ -164,3 +164,23 @@ class GaussianSamplingRemapper(InterpolatedRemapper):
         """Test hook: replace the noise table (lets the CPU oracle share it)."""
         nz = np.ascontiguousarray(noise, np.float64).reshape(self.iterations, 4)
         _native.check(_native.lib().lutgen_cuda_sampling_set_noise(self._h, _ptr(nz)))
+
+
+class GaussianBlurRemapper(InterpolatedRemapper):
+    """GaussianBlurRemapper::new(palette, radius, lum_factor, preserve)  (gaussian_blur.rs:34-53).
+
+    The CLI's and Studio's default algorithm. Like the reference type it implements `GenerateLut`
+    only (gaussian_blur.rs:512-541): the `remap_*` methods of `InterpolatedRemapper` do not exist on
+    it. All four generate spellings follow `par_generate_lut_inner` (the nearest-neighbour hint
+    restarts per (r, g) row), which is what the reference's callers use.
+    """
+    _kind = _native.BLUR
+
+    def __init__(self, palette, radius, lum_factor, preserve):
+        self._create(palette, param=radius, lum_factor=lum_factor, preserve=preserve)
+
+    def _no_remap(self, *a, **k):
+        raise AttributeError("GaussianBlurRemapper implements GenerateLut only, as in the reference")
+
+    remap_pixel = remap_image = remap_image_with_interrupt = _no_remap
+    par_remap_image = par_remap_image_with_interrupt = _no_remap

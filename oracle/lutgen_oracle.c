@@ -49,6 +49,8 @@
 
 #define ORACLE_API __attribute__((visibility("default")))
 
+ORACLE_API int lutgen_oracle_max_threads(void);
+
 /* ------------------------------------------------------------------------- */
 /* fast-srgb8 (third party, un-vendored): decode table + table encoder        */
 /* ------------------------------------------------------------------------- */
@@ -276,7 +278,7 @@ ORACLE_API int lutgen_oracle_detect_level(uint32_t width, uint32_t height) {
 /* remappers                                                                  */
 /* ------------------------------------------------------------------------- */
 
-enum { K_GAUSSIAN = 0, K_SHEPARD = 1, K_LINEAR = 2, K_NEAREST = 3, K_SAMPLING = 4 };
+enum { K_GAUSSIAN = 0, K_SHEPARD = 1, K_LINEAR = 2, K_NEAREST = 3, K_SAMPLING = 4, K_BLUR = 5 };
 
 typedef struct {
     int32_t kind;
@@ -326,7 +328,7 @@ static void fill_normals(double* out, size_t n, double mean, double std_dev, uin
  * (nearest_neighbor.rs:19-37), GaussianSamplingRemapper::new (gaussian_sample.rs:27-46). */
 ORACLE_API void* lutgen_oracle_remapper_create(const lutgen_oracle_desc* desc) {
     init_tables();
-    if (!desc || desc->kind < 0 || desc->kind > K_SAMPLING) return NULL;
+    if (!desc || desc->kind < 0 || desc->kind > K_BLUR) return NULL;
     if (desc->kind == K_SAMPLING && !isfinite(desc->std_dev)) return NULL; /* Normal::new(..).unwrap() */
     oracle_remapper* r = (oracle_remapper*)calloc(1, sizeof *r);
     r->d = *desc;
@@ -556,6 +558,164 @@ ORACLE_API void lutgen_oracle_generate_lut_rows(const void* h, uint8_t level8, u
 ORACLE_API void lutgen_oracle_generate_lut(const void* h, uint8_t level, uint8_t* out_rgb, int threads) {
     uint32_t side = (uint32_t)level * level * level;
     lutgen_oracle_generate_lut_rows(h, level, out_rgb, 0, side, threads);
+}
+
+/* ------------------------------------------------------------------------- */
+/* GaussianBlurRemapper, crates/lib/src/interpolation/gaussian_blur.rs        */
+/* (the remapper the CLI and Studio use by default)        */
+/* ------------------------------------------------------------------------- */
+
+/* sq_dist, gaussian_blur.rs:504-510: f32, left to right, no FMA. */
+static inline float sq_dist_f32(const float a[3], const float b[3]) {
+    float dl = a[0] - b[0], da = a[1] - b[1], db = a[2] - b[2];
+    return dl * dl + da * da + db * db;
+}
+
+/* find_nearest_with_hint, gaussian_blur.rs:57-80. */
+static size_t blur_find_nearest(const float* pal, size_t n, const float color[3], size_t hint, float threshold_sq) {
+    float hint_dist = sq_dist_f32(color, pal + 3 * hint);
+    if (hint_dist < threshold_sq) return hint;
+    size_t best = hint;
+    float best_dist = hint_dist;
+    for (size_t i = 0; i < n; ++i) {
+        if (i == hint) continue;
+        float d = sq_dist_f32(color, pal + 3 * i);
+        if (d < best_dist) {
+            best_dist = d;
+            best = i;
+        }
+    }
+    return best;
+}
+
+/* Rust `f32 as u8`: saturating, NaN -> 0. */
+static inline uint8_t f32_as_u8(float v) {
+    if (!(v > 0.0f)) return 0;
+    if (v >= 255.0f) return 255;
+    return (uint8_t)v;
+}
+
+/* blur_inner / par_blur_inner (gaussian_blur.rs:100-162) along an arbitrary axis of the
+ * [r][g][b][ch] volume. The reference rotates the volume between passes so the blurred axis is
+ * always innermost; the arithmetic per output (taps in order, sum += kw * src, clamped edge) does
+ * not depend on the memory layout, so the rotations are not restated. */
+static void blur_axis(const float* src, float* dst, size_t size, size_t ch, size_t axis_stride, const float* kernel, int klen, int threads) {
+    int half = klen / 2, max = (int)size - 1;
+    size_t cells = size * size * size;
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (long long cell = 0; cell < (long long)cells; ++cell) {
+        size_t pos = ((size_t)cell / axis_stride) % size; /* coordinate along the blurred axis */
+        for (size_t c = 0; c < ch; ++c) {
+            float sum = 0.0f;
+            for (int ki = 0; ki < klen; ++ki) {
+                int p = (int)pos + ki - half;
+                p = p < 0 ? 0 : (p > max ? max : p);
+                size_t src_cell = (size_t)cell + ((size_t)p - pos) * axis_stride; /* size_t wraparound is fine */
+                sum += kernel[ki] * src[src_cell * ch + c];
+            }
+            dst[(size_t)cell * ch + c] = sum;
+        }
+    }
+}
+
+/* GaussianBlurRemapper::{new, par_generate_lut_inner / generate_lut_inner, colors_to_lut}
+ * (gaussian_blur.rs:34-53, 197-431, 433-500). sequential_hints = 0 follows par_generate_lut_inner
+ * (what the CLI and Studio call: the NN hint restarts at 0 for every (r, g) row, l.339);
+ * sequential_hints = 1 follows generate_lut_inner (the hint carries across rows, l.213). */
+ORACLE_API int lutgen_oracle_blur_generate(const void* h, uint8_t level8, uint8_t* out_rgb, int sequential_hints, int threads) {
+    const oracle_remapper* r = (const oracle_remapper*)h;
+    if (!r || r->d.kind != K_BLUR || r->d.palette_len == 0) return -1;
+    if (threads < 1) threads = 1;
+    size_t n = r->d.palette_len;
+    float lum = (float)r->d.lum_factor, radius = (float)r->d.param;
+    int preserve = r->d.preserve;
+    float* pal = (float*)malloc(sizeof(float) * 3 * n);
+    for (size_t i = 0; i < n; ++i) { /* new(): [l * lum_factor, a, b] in f32 */
+        oklab_t o = srgb_to_oklab(r->pal_rgb[3 * i], r->pal_rgb[3 * i + 1], r->pal_rgb[3 * i + 2]);
+        pal[3 * i] = o.l * lum;
+        pal[3 * i + 1] = o.a;
+        pal[3 * i + 2] = o.b;
+    }
+    size_t level = level8, size = level * level, cells = size * size * size;
+    float scale = 255.0f / (float)(size - 1);
+    size_t ch = preserve ? 2 : 3;
+    float step = 1.0f / (float)size, threshold_sq = step * step * 0.5f;
+    float* colors = (float*)malloc(sizeof(float) * cells * ch);
+    float* next = (float*)malloc(sizeof(float) * cells * ch);
+    uint8_t* chan = (uint8_t*)malloc(size);
+    for (size_t i = 0; i < size; ++i) chan[i] = f32_as_u8(roundf((float)i * scale));
+
+    /* NN volume in [r][g][b] order */
+    if (sequential_hints) threads = 1;
+    size_t carried = 0;
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 16) if (!sequential_hints)
+    for (long long row = 0; row < (long long)(size * size); ++row) {
+        size_t rr = (size_t)row / size, gg = (size_t)row % size;
+        size_t hint = sequential_hints ? carried : 0;
+        for (size_t b = 0; b < size; ++b) {
+            oklab_t o = srgb_to_oklab(chan[rr], chan[gg], chan[b]);
+            float color[3] = {o.l * lum, o.a, o.b};
+            size_t nearest = blur_find_nearest(pal, n, color, hint, threshold_sq);
+            hint = nearest;
+            const float* t = pal + 3 * nearest;
+            float* dst = colors + ((size_t)row * size + b) * ch;
+            if (preserve) {
+                dst[0] = t[1];
+                dst[1] = t[2];
+            } else {
+                dst[0] = t[0] / lum;
+                dst[1] = t[1];
+                dst[2] = t[2];
+            }
+        }
+        if (sequential_hints) carried = hint;
+    }
+
+    /* build_kernel, gaussian_blur.rs:87-96 */
+    /* `(radius * 3.0).ceil() as i32`: NaN -> 0, saturating; a negative half makes `-half..=half`
+     * empty, i.e. a kernel with no taps (every blurred value becomes 0.0) */
+    float h3 = ceilf(radius * 3.0f);
+    int half = (h3 != h3) ? 0 : (h3 > 1e6f ? 1000000 : (h3 < -1e6f ? -1000000 : (int)h3));
+    float two_sigma_sq = 2.0f * radius * radius;
+    int klen = half < 0 ? 0 : 2 * half + 1;
+    float* kernel = (float*)malloc(sizeof(float) * (size_t)(klen + 1));
+    float ksum = 0.0f;
+    for (int i = -half; i <= half && klen; ++i) {
+        kernel[i + half] = expf((float)(-(i * i)) / two_sigma_sq);
+        ksum += kernel[i + half];
+    }
+    for (int i = 0; i < klen; ++i) kernel[i] /= ksum;
+
+    int bt = r->d.kind == K_BLUR ? lutgen_oracle_max_threads() : 1;
+    if (sequential_hints) bt = 1;
+    blur_axis(colors, next, size, ch, 1, kernel, klen, bt);           /* pass 1: B axis */
+    blur_axis(next, colors, size, ch, size * size, kernel, klen, bt); /* pass 2: R axis */
+    blur_axis(colors, next, size, ch, size, kernel, klen, bt);        /* pass 3: G axis */
+
+    /* colors_to_lut: Hald order (b outer, g, r inner) */
+#pragma omp parallel for num_threads(bt) schedule(static)
+    for (long long px = 0; px < (long long)cells; ++px) {
+        size_t ri = (size_t)px % size, gi = ((size_t)px / size) % size, bi = (size_t)px / (size * size);
+        const float* c = next + ((ri * size + gi) * size + bi) * ch;
+        oklab_t o;
+        if (preserve) {
+            oklab_t own = srgb_to_oklab(chan[ri], chan[gi], chan[bi]);
+            o.l = own.l;
+            o.a = c[0];
+            o.b = c[1];
+        } else {
+            o.l = c[0];
+            o.a = c[1];
+            o.b = c[2];
+        }
+        oklab_to_srgb(o, out_rgb + 3 * px);
+    }
+    free(pal);
+    free(colors);
+    free(next);
+    free(chan);
+    free(kernel);
+    return 0;
 }
 
 ORACLE_API int lutgen_oracle_max_threads(void) {

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "_build", "liblutgen_oracle.so")
 
-GAUSSIAN, SHEPARD, LINEAR, NEAREST, SAMPLING = range(5)
+GAUSSIAN, SHEPARD, LINEAR, NEAREST, SAMPLING, BLUR = range(6)
 
 
 class Desc(C.Structure):
@@ -69,6 +69,8 @@ def lib():
         L.lutgen_oracle_generate_lut_rows.argtypes = [vp, u8, vp, u32, u32, i32]
         L.lutgen_oracle_generate_lut.argtypes = [vp, u8, vp, i32]
         L.lutgen_oracle_max_threads.restype = i32
+        L.lutgen_oracle_blur_generate.argtypes = [vp, u8, vp, i32, i32]
+        L.lutgen_oracle_blur_generate.restype = i32
         _lib = L
     return _lib
 
@@ -161,9 +163,14 @@ class Remapper:
         lib().lutgen_oracle_remap_image(self._h, _ptr(out), out.size // 4, threads or max_threads())
         return out
 
-    def generate_lut(self, level, threads=None, rows=None):
+    def generate_lut(self, level, threads=None, rows=None, sequential_hints=False):
         n = level ** 3
         out = np.zeros((n, n, 3), np.uint8)
+        if self.kind == BLUR:
+            rc = lib().lutgen_oracle_blur_generate(self._h, level, _ptr(out), int(bool(sequential_hints)), threads or max_threads())
+            if rc != 0:
+                raise ValueError("oracle: GaussianBlurRemapper with an empty palette panics")
+            return out
         r0, r1 = rows if rows is not None else (0, n)
         lib().lutgen_oracle_generate_lut_rows(self._h, level, _ptr(out), r0, r1, threads or max_threads())
         return out

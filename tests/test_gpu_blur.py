@@ -1,0 +1,98 @@
+"""GaussianBlurRemapper (crates/lib/src/interpolation/gaussian_blur.rs; SURVEY 8(f) row 1, the CLI's
+and Studio's default algorithm): the CUDA path must be BIT EXACT with the CPU restatement -- every
+step is f32 arithmetic evaluated in the reference's order. Nothing in the reference pins this
+remapper's output (no golden image, no test): parity is against the oracle's restatement only."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from conftest import synthetic_palette
+
+pytestmark = pytest.mark.gpu
+
+lg = pytest.importorskip("lutgen_rs_b200")
+from lutgen_rs_b200 import identity, interpolation  # noqa: E402
+
+
+def _case(pal, level, radius, lum=1.0, preserve=False):
+    got = interpolation.GaussianBlurRemapper(pal, radius, lum, preserve).par_generate_lut(level)
+    want = O.Remapper(O.BLUR, pal, param=radius, lum_factor=lum, preserve=preserve).generate_lut(level)
+    return got, want
+
+
+@pytest.mark.parametrize("pal_name,level,radius,lum,preserve", [
+    ("catppuccin_mocha", 10, 8.0, 1.0, False),   # CLI defaults (crates/cli/src/main.rs:70, 139)
+    ("carburetor", 8, 8.0, 1.0, False),          # reference bench parameters (benches/main.rs:136-138)
+    ("nord", 8, 8.0, 0.7, True),                 # Studio defaults: lum 0.7, preserve (state.rs:277-288)
+    ("gruvbox_dark", 12, 3.5, 1.0, False),       # Studio's native default level
+    ("catppuccin_mocha", 6, 0.4, 1.3, True),     # 5 taps
+    ("nord", 5, 20.0, 1.0, False),               # kernel wider than the cube
+    ("nord", 2, 1.0, 1.0, False),                # smallest level
+    ("carburetor", 7, 2.0, 1.0, True),           # odd level, cube side 49
+])
+def test_blur_lut_bit_exact(palettes, pal_name, level, radius, lum, preserve):
+    got, want = _case(palettes[pal_name], level, radius, lum, preserve)
+    assert got.shape == want.shape
+    assert (got == want).all(), int((got != want).sum())
+
+
+def test_blur_level16_bit_exact(palettes):
+    got, want = _case(palettes["catppuccin_mocha"], 16, 8.0)
+    assert (got == want).all(), int((got != want).sum())
+
+
+def test_blur_256_colour_palette(palettes):
+    got, want = _case(synthetic_palette(256, seed=1), 8, 4.0)
+    assert (got == want).all()
+
+
+@pytest.mark.parametrize("radius", [0.0, -1.0, float("nan"), 1e-3])
+def test_blur_degenerate_radii(palettes, radius):
+    """radius 0 -> one NaN tap -> black; negative -> no taps -> zeros; tiny -> identity kernel."""
+    got, want = _case(palettes["nord"], 4, radius)
+    assert (got == want).all()
+    got, want = _case(palettes["nord"], 4, radius, preserve=True)
+    assert (got == want).all()
+
+
+def test_blur_sequential_hint_variant_agrees_here(palettes):
+    """generate_lut_inner carries the NN hint across rows, par_generate_lut_inner restarts it; the two
+    can only differ where a stale hint is within the early-exit threshold. Record that they agree on
+    the CLI default configuration (the GPU follows the par variant, which the callers use)."""
+    pal = palettes["catppuccin_mocha"]
+    orc = O.Remapper(O.BLUR, pal, param=8.0, lum_factor=1.0, preserve=False)
+    assert (orc.generate_lut(8) == orc.generate_lut(8, sequential_hints=True)).all()
+
+
+def test_blur_generate_variants_and_interrupt(palettes):
+    r = interpolation.GaussianBlurRemapper(palettes["nord"], 8.0, 1.0, False)
+    a = r.generate_lut(6)
+    assert (r.par_generate_lut(6) == a).all()
+    flag = lg.AbortFlag()
+    assert (r.par_generate_lut_with_interrupt(6, flag) == a).all()
+    flag.set()
+    assert r.generate_lut_with_interrupt(6, flag) is None
+    with pytest.raises(AttributeError):
+        r.remap_image(np.zeros((2, 2, 4), np.uint8))
+    with pytest.raises(lg.LutgenPanic):
+        interpolation.GaussianBlurRemapper(np.zeros((0, 3), np.uint8), 8.0, 1.0, False)
+
+
+def test_blur_rows_and_apply(palettes):
+    """Row shards of a blur CLUT tile the whole CLUT; the CLUT then drives correct_image."""
+    import torch
+    from lutgen_rs_b200 import device
+    device.init(0)
+    pal = palettes["catppuccin_mocha"]
+    r = interpolation.GaussianBlurRemapper(pal, 8.0, 1.0, False)
+    whole = r.generate_lut(8)
+    lut = torch.zeros(3 * 8 ** 6, dtype=torch.uint8, device="cuda")
+    for a, b in ((0, 100), (100, 101), (101, 512)):
+        device.generate_lut_rows_(r, 8, lut, a, b)
+    torch.cuda.synchronize()
+    assert (lut.cpu().numpy().reshape(512, 512, 3) == whole).all()
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (100, 200, 4), dtype=np.uint8)
+    got = img.copy()
+    identity.correct_image(got, whole)
+    assert (got == O.correct_image(img, whole, 8)).all()

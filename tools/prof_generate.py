@@ -43,6 +43,8 @@ def main():
             r = interpolation.ShepardRemapper(synthetic_palette(256, 1), 4.0, 16, 1.0, False)
         elif what == "nn":
             r = interpolation.NearestNeighborRemapper(pal, 1.0, False)
+        elif what == "blur":
+            r = None  # a fresh remapper per repetition: the blurred volume is cached per handle
         elif what == "sampling":
             from conftest import synthetic_palette
             r = interpolation.GaussianSamplingRemapper(synthetic_palette(256, 1), 0.0, 20.0, 512, 1.0, 42080085, False)
@@ -52,6 +54,8 @@ def main():
         side = level ** 3
         lut = torch.empty(3 * side * side, dtype=torch.uint8, device="cuda")
         for _ in range(reps):
+            if what == "blur":
+                r = interpolation.GaussianBlurRemapper(pal, 8.0, 1.0, False)
             ev0.record()
             device.generate_lut_rows_(r, level, lut, 0, side)
             ev1.record()
