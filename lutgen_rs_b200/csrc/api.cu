@@ -21,6 +21,7 @@
 #include "kernels_blur.cuh"
 #include "kernels_exact.cuh"
 #include "kernels_fast.cuh"
+#include "kernels_warp.cuh"
 
 using namespace lutgen;
 
@@ -282,6 +283,58 @@ bool fast_path_supported(const lutgen_remapper* r) {
     return true;
 }
 
+// Warp-tile kernel (kernels_warp.cuh): palettes of at most 32 colours and ordinary parameters.
+template <int KIND>
+bool warp_path_supported(const lutgen_remapper* r, uint32_t n) {
+    static const bool off = getenv("LUTGEN_CUDA_NO_WARP") != nullptr;
+    if (off || n > (uint32_t)WT_MAX_N) return false;
+    if (KIND == 0) {
+        // the expanded distance is scaled by C = shape*log2(e): keep it where f32 has room
+        double C = r->d.param * 1.4426950408889634;
+        if (!(C >= 1e-3 && C <= 2000.0)) return false;
+    }
+    return true;
+}
+
+template <int KIND, int MODE, int EPT>
+int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const FastArgs& fa) {
+    WarpArgs a{};
+    a.f = f;
+    a.pal = fa.pal; a.pal_rgb = fa.pal_rgb; a.pal_ab = fa.pal_ab;
+    a.n = fa.n; a.k = fa.k; a.preserve = fa.preserve; a.lum = fa.lum; a.inv_lum = fa.inv_lum; a.c1 = fa.c1;
+    a.flag_list = fa.flag_list; a.flag_count = fa.flag_count; a.tile_counter = fa.tile_counter;
+    a.stats = fa.stats; a.tables = fa.tables;
+    if (MODE == FRONT_IMAGE) {
+        a.tiles_r = a.tiles_g = 1;
+        a.inv_tiles_r = a.inv_tiles_g = 1.0f;
+        a.ntiles = blocks_for(f.count, 32u * EPT);
+    } else {
+        uint32_t cs = f.cs;
+        a.tiles_r = (cs + 7) / 8;
+        a.tiles_g = (cs + 3) / 4;
+        a.inv_tiles_r = 1.0f / (float)a.tiles_r;
+        a.inv_tiles_g = 1.0f / (float)a.tiles_g;
+        unsigned long long plane = (unsigned long long)cs * cs;
+        // tile origins are multiples of the tile in every axis whatever the shard (see launch_fast)
+        uint32_t b_lo = (uint32_t)(f.begin / plane) / EPT * EPT, b_hi = (uint32_t)((f.begin + f.count - 1) / plane);
+        a.b_lo = b_lo;
+        a.ntiles = a.tiles_r * a.tiles_g * ((b_hi - b_lo) / EPT + 1);
+    }
+    static int per_sm = 0;  // one per <KIND, MODE, EPT> instantiation
+    if (per_sm == 0) {
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_remap_warp<KIND, MODE, EPT>, WT_THREADS, 0));
+        if (per_sm < 1) per_sm = 1;
+    }
+    unsigned grid = (unsigned)per_sm * (unsigned)g.sm_count;
+    unsigned need = blocks_for(a.ntiles, WT_WARPS * WT_BATCH);
+    (void)need;
+    if (grid > need) grid = need;
+    CU_TRY(cudaMemsetAsync(r->flag_count, 0, 2 * sizeof(uint32_t), s));
+    k_remap_warp<KIND, MODE, EPT><<<grid, WT_THREADS, 0, s>>>(a);
+    LAUNCH_CHECK();
+    return LUTGEN_OK;
+}
+
 template <int KIND, int MODE>
 int launch_fast(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
     if (f.count == 0) return LUTGEN_OK;
@@ -314,6 +367,16 @@ int launch_fast(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
     a.flag_count = r->flag_count;
     a.tile_counter = r->flag_count + 1;
     a.tables = g.tables;
+    Front fl = f;
+    fl.list = r->flag_list;
+    fl.list_count = r->flag_count;
+    fl.list_mode = MODE;
+    if (warp_path_supported<KIND>(r, a.n)) {
+        int rc = launch_warp<KIND, MODE, 4>(f, r, s, a);
+        if (rc != LUTGEN_OK) return rc;
+        if (nn) return launch_nn_exact<FRONT_LIST>(fl, r, s);
+        return launch_rbf_exact_km<KIND < 3 ? KIND : 0, FRONT_LIST>(fl, r, s);
+    }
     unsigned grid;
     if (MODE == FRONT_IMAGE) {
         a.tr = a.tg = a.tb = 1;
@@ -359,10 +422,6 @@ int launch_fast(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
     CU_TRY(cudaMemsetAsync(r->flag_count, 0, 2 * sizeof(uint32_t), s));
     k_remap_fast<KIND, MODE><<<grid, FAST_THREADS, smem, s>>>(a);
     LAUNCH_CHECK();
-    Front fl = f;
-    fl.list = r->flag_list;
-    fl.list_count = r->flag_count;
-    fl.list_mode = MODE;
     if (nn) return launch_nn_exact<FRONT_LIST>(fl, r, s);
     return launch_rbf_exact_km<KIND < 3 ? KIND : 0, FRONT_LIST>(fl, r, s);
 }

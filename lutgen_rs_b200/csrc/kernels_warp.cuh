@@ -1,0 +1,642 @@
+// kernels_warp.cuh -- the throughput remap kernel for palettes of at most 32 colours (the
+// built-in palettes average 22): the tile-bounded nearest-k of kernels_fast.cuh with one WARP per
+// tile instead of one CTA, and the arithmetic in packed f32x2 (FFMA2 / FMUL2 / FADD2, sm_100a).
+//
+// Why a warp per tile: the smaller the tile, the tighter its Oklab bounding box and the fewer
+// palette colours are left UNCERTAIN at the k-boundary (tools/sim_tiles.py: 6.9 per 8x8x16 CTA tile,
+// 2.7 per 8x4x4 warp tile for the headline configuration); per-entry selection among the uncertain
+// colours was the most expensive part of the CTA kernel. A warp classifies a 26-colour palette in
+// ~200 instructions (one colour per lane, ranks from one broadcast loop), needs no CTA barrier,
+// keeps its entries' Oklab values in registers, and takes tiles from a device-wide counter.
+//
+// Why f32x2: the kernel is bound by instruction ISSUE, not by the FMA pipe. A lane owns EPT entries
+// of its tile; two of them share every instruction as a float2 (the palette colour is the scalar
+// broadcast operand FFMA2 accepts), which halves the issue slots of all the per-entry arithmetic.
+//
+//   tile        : 8 (r) x 4 (g) x EPT (b) Hald-identity entries (LUT / TABLE front-ends; lane =
+//                 (r, g), entry e = b plane) or 32*EPT consecutive pixels (IMAGE).
+//   classify    : as kernels_fast.cuh steps 2-4 (LB/UB against the inflated box, U_k, IN / OUT /
+//                 UNCERTAIN, negligible colours dropped, "moot" tiles take every colour).
+//   accumulate  : the candidate list is walked once for the lane's EPT entries together (one
+//                 broadcast LDS.128 serves all of them).
+//   Gaussian    : the list holds q = (-2C p, C(|p|^2 - lbmin)), C = shape*log2(e), so that
+//                 s = C(d - lbmin) = q.xyz . c + q.w + C|c|^2 costs 3 FFMA2 + 1 FADD2 per pair,
+//                 w = ex2(-s), and the sums run over q.xyz (-2C is divided out once per entry).
+//   NN          : the same expansion ranks by d - |c|^2.
+//   near-ties   : as in kernels_fast.cuh every decision closer than the f32 error bound (here a
+//                 per-tile constant) sends the entry to the exact f64 kernel's work list.
+//
+// Code size matters: warps run free of each other, so the SM's instruction cache sees the whole
+// kernel body at once. Everything rare or repeated per entry (selection networks, flagging) is out
+// of line, and loops that would unroll into kilobytes are kept rolled.
+#pragma once
+#include "kernels_fast.cuh"
+
+namespace lutgen {
+
+constexpr int WT_THREADS = 256;
+constexpr int WT_WARPS = WT_THREADS / 32;
+constexpr int WT_BATCH = 4;          // warp tiles per hand-out
+constexpr int WT_MAX_N = 32;         // one palette colour per lane
+constexpr int WT_MAX_CS = 1089;      // level 33
+constexpr float WT_TIE_SLOPE = 2.24e-5f;   // sqrt(FAST_TIE_TOL): conversion error, scales with sqrt(d)
+constexpr float WT_TIE_CONST = 1.5e-6f;    // rounding of the expanded distance (|p|^2 - 2 p.c + |c|^2)
+
+struct WarpArgs {
+    Front f;
+    const float4* pal;        // n x (l*lum, a, b, 0)
+    const uint32_t* pal_rgb;  // n x packed r | g<<8 | b<<16
+    const float* pal_ab;      // n x 2 (NearestNeighbor preserve)
+    uint32_t n, k;            // k = 0: every colour
+    int preserve;
+    float lum, inv_lum;
+    float c1;                 // weight slope (kernels_fast.cuh header)
+    uint32_t tiles_r, tiles_g;
+    float inv_tiles_r, inv_tiles_g;
+    uint32_t b_lo;            // first blue plane covered (multiple of EPT)
+    uint32_t ntiles;
+    uint32_t* flag_list;
+    uint32_t* flag_count;
+    uint32_t* tile_counter;   // zeroed before the launch
+    uint32_t* stats;
+    const ColorTables* tables;
+};
+
+typedef float2 f2;
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 splat(float x) { return make_float2(x, x); }
+
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// x^(1/3) for two LMS values >= 0: MUFU seed for x^(-1/3) + one Newton step, as cbrtf_fast, with the
+// zero guard folded into a clamp (cbrt(1e-30) = 1e-10 is zero at Oklab's resolution).
+__device__ __forceinline__ f2 cbrt2(f2 x) {
+    x.x = fmaxf(x.x, 1e-30f);
+    x.y = fmaxf(x.y, 1e-30f);
+    f2 lg = make_float2(lg2_approx(x.x), lg2_approx(x.y));
+    lg = mul2(lg, splat(-0.33333334f));
+    f2 t = make_float2(ex2_approx(lg.x), ex2_approx(lg.y));
+    f2 v = mul2(mul2(x, t), mul2(t, t));           // x t^3
+    f2 r = fma2(v, splat(-1.0f), splat(1.0f));      // 1 - x t^3
+    t = fma2(mul2(t, splat(0.33333334f)), r, t);
+    return mul2(mul2(x, t), t);
+}
+
+// Two entries' Oklab from their LMS values.
+__device__ __forceinline__ void lms_to_lab2(f2 l, f2 m, f2 s, float lum, f2& L, f2& A, f2& B) {
+    f2 l_ = cbrt2(l), m_ = cbrt2(m), s_ = cbrt2(s);
+    L = mul2(fma2(splat(0.2104542553f), l_, fma2(splat(0.7936177850f), m_, mul2(splat(-0.0040720468f), s_))), splat(lum));
+    A = fma2(splat(1.9779984951f), l_, fma2(splat(-2.4285922050f), m_, mul2(splat(0.4505937099f), s_)));
+    B = fma2(splat(0.0259040371f), l_, fma2(splat(0.7827717662f), m_, mul2(splat(-0.8086757660f), s_)));
+}
+
+__device__ __forceinline__ void oklab_to_linear2(f2 L, f2 A, f2 B, f2& r, f2& g, f2& b) {
+    f2 l_ = fma2(splat(0.3963377774f), A, fma2(splat(0.2158037573f), B, L));
+    f2 m_ = fma2(splat(-0.1055613458f), A, fma2(splat(-0.0638541728f), B, L));
+    f2 s_ = fma2(splat(-0.0894841775f), A, fma2(splat(-1.2914855480f), B, L));
+    f2 l = mul2(mul2(l_, l_), l_), m = mul2(mul2(m_, m_), m_), s = mul2(mul2(s_, s_), s_);
+    r = fma2(splat(4.0767416621f), l, fma2(splat(-3.3077115913f), m, mul2(splat(0.2309699292f), s)));
+    g = fma2(splat(-1.2684380046f), l, fma2(splat(2.6097574011f), m, mul2(splat(-0.3413193965f), s)));
+    b = fma2(splat(-0.0041960863f), l, fma2(splat(-0.7034186147f), m, mul2(splat(1.7076147010f), s)));
+}
+
+// Score of candidate q for two entries (smaller = nearer):
+//   Gaussian   C (d - lbmin)  = q.xyz . c + (q.w + C |c|^2)            (cc = C |c|^2)
+//   NN         d - |c|^2      = q.xyz . c + q.w
+//   Shepard / Linear  d       (differences: small distances keep their relative precision)
+template <int KIND>
+__device__ __forceinline__ f2 wt_score2(float4 q, f2 L, f2 A, f2 B, f2 cc) {
+    if (KIND == 0) return fma2(splat(q.x), L, fma2(splat(q.y), A, fma2(splat(q.z), B, add2(splat(q.w), cc))));
+    if (KIND == KIND_NN) return fma2(splat(q.x), L, fma2(splat(q.y), A, fma2(splat(q.z), B, splat(q.w))));
+    f2 dx = fma2(splat(q.x), splat(-1.0f), L), dy = fma2(splat(q.y), splat(-1.0f), A), dz = fma2(splat(q.z), splat(-1.0f), B);
+    return fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+}
+template <int KIND>
+__device__ __forceinline__ f2 wt_weight2(f2 s, float c1, float c0) {
+    if (KIND == 0) return make_float2(ex2_approx(-s.x), ex2_approx(-s.y));
+    if (KIND == 1) {
+        f2 e = fma2(splat(c1), make_float2(lg2_approx(s.x), lg2_approx(s.y)), splat(c0));
+        return make_float2(ex2_approx(e.x), ex2_approx(e.y));
+    }
+    return s;
+}
+
+// Optimal sorting networks for 4 and 8 keys (5 and 19 compare-exchanges), bitonic beyond.
+__device__ __forceinline__ void cswap(float& a, float& b) {
+    float lo = fminf(a, b), hi = fmaxf(a, b);
+    a = lo; b = hi;
+}
+template <int M>
+__device__ __forceinline__ void wt_sort(float (&v)[M]) {
+    if constexpr (M == 4) {
+        cswap(v[0], v[1]); cswap(v[2], v[3]); cswap(v[0], v[2]); cswap(v[1], v[3]); cswap(v[1], v[2]);
+    } else if constexpr (M == 8) {
+        cswap(v[0], v[1]); cswap(v[2], v[3]); cswap(v[4], v[5]); cswap(v[6], v[7]);
+        cswap(v[0], v[2]); cswap(v[1], v[3]); cswap(v[4], v[6]); cswap(v[5], v[7]);
+        cswap(v[1], v[2]); cswap(v[5], v[6]); cswap(v[0], v[4]); cswap(v[3], v[7]);
+        cswap(v[1], v[5]); cswap(v[2], v[6]);
+        cswap(v[1], v[4]); cswap(v[3], v[6]);
+        cswap(v[2], v[4]); cswap(v[3], v[5]);
+        cswap(v[3], v[4]);
+    } else {
+        bitonic_sort<M>(v);
+    }
+}
+
+struct PairAcc {
+    f2 n0, n1, n2, den;
+    uint32_t risky;  // bit 0: first entry of the pair, bit 1: second
+};
+
+// kp-th and (kp+1)-th smallest of the first mU of `sc` (component C of each pair).
+template <int M, int C>
+__device__ __forceinline__ void wt_threshold(const f2 (&sc)[M], int mU, int kp, float& tau, float& nxt) {
+    float s[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) s[i] = i < mU ? (C == 0 ? sc[i].x : sc[i].y) : INFINITY;
+    wt_sort<M>(s);
+    tau = s[0];
+    nxt = s[M - 1];
+    pick_threshold<M>(s, kp, tau, nxt);
+}
+
+// Choose the kp nearest of mU (kp < mU <= M) uncertain colours for the two entries of a pair and
+// accumulate them.
+template <int M, int KIND>
+__device__ __forceinline__ PairAcc wt_select(const float4* __restrict__ unc, int mU, int kp, f2 L, f2 A, f2 B, f2 cc, float c1, float c0, float tol) {
+    f2 sc[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) sc[i] = i < mU ? wt_score2<KIND>(unc[i], L, A, B, cc) : splat(INFINITY);
+    float tau0, nxt0, tau1, nxt1;
+    wt_threshold<M, 0>(sc, mU, kp, tau0, nxt0);
+    wt_threshold<M, 1>(sc, mU, kp, tau1, nxt1);
+    PairAcc r;
+    r.n0 = r.n1 = r.n2 = r.den = splat(0.f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        if (i < mU) {
+            float4 q = unc[i];
+            f2 w = wt_weight2<KIND>(sc[i], c1, c0);
+            w.x = sc[i].x <= tau0 ? w.x : 0.0f;
+            w.y = sc[i].y <= tau1 ? w.y : 0.0f;
+            r.n0 = fma2(splat(q.x), w, r.n0);
+            r.n1 = fma2(splat(q.y), w, r.n1);
+            r.n2 = fma2(splat(q.z), w, r.n2);
+            r.den = add2(r.den, w);
+        }
+    }
+    r.risky = (((nxt0 - tau0 <= tol) && (nxt0 < INFINITY)) ? 1u : 0u) | (((nxt1 - tau1 <= tol) && (nxt1 < INFINITY)) ? 2u : 0u);
+    return r;
+}
+
+// More than 16 uncertain colours (rare with warp tiles): per entry, one pass keeping the kp + 1
+// best scores sorted in a small local array.
+template <int KIND>
+__device__ __forceinline__ PairAcc wt_select_insert(const float4* __restrict__ unc, int mU, int kp, f2 L, f2 A, f2 B, f2 cc, float c1, float c0,
+                                                    float tol) {
+    constexpr int CAP = 33;
+    PairAcc r;
+    r.n0 = r.n1 = r.n2 = r.den = splat(0.f);
+    r.risky = 0;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        float td[CAP];
+        unsigned char tj[CAP];
+        const int keep = kp + 1;
+        int cnt = 0;
+        for (int j = 0; j < mU; ++j) {
+            f2 s2 = wt_score2<KIND>(unc[j], L, A, B, cc);
+            float d = half ? s2.y : s2.x;
+            if (cnt < keep || d < td[cnt - 1]) {
+                int i = cnt < keep ? cnt : keep - 1;
+                while (i > 0 && td[i - 1] > d) {
+                    td[i] = td[i - 1];
+                    tj[i] = tj[i - 1];
+                    --i;
+                }
+                td[i] = d;
+                tj[i] = (unsigned char)j;
+                if (cnt < keep) ++cnt;
+            }
+        }
+        if (cnt < keep) { r.risky |= 1u << half; continue; }
+        float n0 = 0.f, n1 = 0.f, n2 = 0.f, den = 0.f;
+        for (int i = 0; i < kp; ++i) {
+            float4 q = unc[tj[i]];
+            f2 w2 = wt_weight2<KIND>(splat(td[i]), c1, c0);
+            n0 = fmaf(q.x, w2.x, n0);
+            n1 = fmaf(q.y, w2.x, n1);
+            n2 = fmaf(q.z, w2.x, n2);
+            den += w2.x;
+        }
+        if (td[kp] - td[kp - 1] <= tol) r.risky |= 1u << half;
+        if (half) { r.n0.y = n0; r.n1.y = n1; r.n2.y = n2; r.den.y = den; }
+        else { r.n0.x = n0; r.n1.x = n1; r.n2.x = n2; r.den.x = den; }
+    }
+    return r;
+}
+
+// One call site per pair of entries; the bucket (4 / 8 / 16 / more) is chosen inside. Out of line:
+// a copy of every network per pair made the kernel 100 KB of SASS, and warps that run free of each
+// other then spend their time waiting for instruction fetch.
+template <int KIND>
+__device__ __noinline__ PairAcc wt_select_any(const float4* __restrict__ unc, int mU, int kp, f2 L, f2 A, f2 B, f2 cc, float c1, float c0, float tol) {
+    if (mU <= 4) return wt_select<4, KIND>(unc, mU, kp, L, A, B, cc, c1, c0, tol);
+    if (mU <= 8) return wt_select<8, KIND>(unc, mU, kp, L, A, B, cc, c1, c0, tol);
+    if (mU <= 16) return wt_select<16, KIND>(unc, mU, kp, L, A, B, cc, c1, c0, tol);
+    return wt_select_insert<KIND>(unc, mU, kp, L, A, B, cc, c1, c0, tol);
+}
+
+// Entries (bits of `mask`) this lane hands to the exact kernel. Out of line and rare.
+__device__ __noinline__ void wt_flag_mask(uint32_t* flag_count, uint32_t* flag_list, uint32_t* stats, uint32_t mask, uint32_t slot0,
+                                          uint32_t slot_step) {
+    while (mask) {
+        const uint32_t e = __ffs(mask) - 1;
+        mask &= mask - 1;
+        uint32_t pos = atomicAdd(flag_count, 1u);
+        flag_list[pos] = slot0 + e * slot_step;
+        if (stats) atomicAdd(&stats[127], 1u);
+    }
+}
+
+// n / d for n < 2^24 with inv = 1.0f / d (host): float estimate, one correction either way.
+__device__ __forceinline__ void wt_divmod(uint32_t n, uint32_t d, float inv, uint32_t& q, uint32_t& r) {
+    q = (uint32_t)(__uint2float_rz(n) * inv);
+    int rem = (int)(n - q * d);
+    if (rem < 0) { --q; rem += (int)d; }
+    if (rem >= (int)d) { ++q; rem -= (int)d; }
+    r = (uint32_t)rem;
+}
+
+template <int KIND, int MODE, int EPT>
+__global__ void __launch_bounds__(WT_THREADS, 3) k_remap_warp(const WarpArgs a) {
+    static_assert(EPT % 2 == 0, "entries are processed in pairs");
+    constexpr int NP = EPT / 2;
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr bool BRICK = MODE != FRONT_IMAGE;
+    __shared__ SmemTables st;
+    __shared__ float s_lin[BRICK ? WT_MAX_CS : 1];      // decode[channel value of grid coordinate v]
+    __shared__ uint8_t s_chv[BRICK ? WT_MAX_CS + 3 : 4];  // channel value of grid coordinate v
+    __shared__ __align__(16) float4 s_cand[WT_WARPS][WT_MAX_N];
+    __shared__ __align__(8) float2 s_bnd[WT_WARPS][WT_MAX_N];
+    __shared__ uint32_t s_hit[WT_WARPS][FAST_MAX_HITS];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n = a.n, k = a.k;
+    const uint32_t cs = a.f.cs, csm1 = a.f.csm1;
+    const uint32_t begin = (uint32_t)a.f.begin, end = (uint32_t)(a.f.begin + a.f.count);
+    const float c1 = a.c1;
+
+    if (BRICK) {
+#pragma unroll 1
+        for (uint32_t v = tid; v < cs; v += WT_THREADS) s_chv[v] = (uint8_t)(MODE == FRONT_TABLE ? v : hald_channel(v, csm1));
+    }
+    stage_tables(st, a.tables);  // ends with __syncthreads()
+    if (BRICK) {
+#pragma unroll 1
+        for (uint32_t v = tid; v < cs; v += WT_THREADS) s_lin[v] = st.decode[s_chv[v]];
+        __syncthreads();
+    }
+
+    // this lane's palette colour
+    const bool active = lane < n;
+    const float4 p = active ? a.pal[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t prgb = active ? (a.pal_rgb[lane] & 0xffffffu) : 0u;
+    const float psq = fmaf(p.x, p.x, fmaf(p.y, p.y, p.z * p.z));
+    float4* cand = s_cand[warp];
+    float2* bnd = s_bnd[warp];
+    uint32_t* hits = s_hit[warp];
+    const uint32_t lr = lane & 7u, lg = lane >> 3;
+
+    for (;;) {
+        uint32_t t0 = 0;
+        if (lane == 0) t0 = atomicAdd(a.tile_counter, (uint32_t)WT_BATCH);
+        t0 = __shfl_sync(FULL, t0, 0);
+        if (t0 >= a.ntiles) break;
+        uint32_t ir = 0, ig = 0, ib = 0;
+        if (BRICK) {
+            uint32_t rest;
+            wt_divmod(t0, a.tiles_r, a.inv_tiles_r, rest, ir);
+            wt_divmod(rest, a.tiles_g, a.inv_tiles_g, ib, ig);
+        }
+        const uint32_t t1 = min(t0 + (uint32_t)WT_BATCH, a.ntiles);
+#pragma unroll 1
+        for (uint32_t t = t0; t < t1; ++t) {
+            // ---- 1. colours of this tile -> Oklab (register pairs), bounding box ----------------
+            f2 Lp[NP], Ap[NP], Bp[NP];
+            uint32_t R = 0, G = 0, Bq[EPT];
+            uint32_t slot0 = 0, slot_step = 0;  // entry e's slot = slot0 + e * slot_step
+            uint32_t valid_mask = 0;
+            uint32_t blo[3] = {0, 0, 0}, bhi[3] = {255, 255, 255};  // sRGB box of the tile
+            float lo[3], hi[3];
+            if (BRICK) {
+                const uint32_t r0 = ir * 8u, g0 = ig * 4u, b0 = a.b_lo + ib * (uint32_t)EPT;
+                if (++ir == a.tiles_r) { ir = 0; if (++ig == a.tiles_g) { ig = 0; ++ib; } }
+                const uint32_t first = (b0 * cs + g0) * cs + r0;
+                const uint32_t last = (min(b0 + EPT - 1, csm1) * cs + min(g0 + 3u, csm1)) * cs + min(r0 + 7u, csm1);
+                if (b0 > csm1 || last < begin || first >= end) continue;  // uniform
+                const uint32_t r = r0 + lr, g = g0 + lg, rc = min(r, csm1), gc = min(g, csm1);
+                const bool rg_in = r < cs && g < cs;
+                R = s_chv[rc]; G = s_chv[gc];
+                const float linr = s_lin[rc], ling = s_lin[gc];
+                const float pl = fmaf(0.5363325363f, ling, 0.4122214708f * linr);
+                const float pm = fmaf(0.6806995451f, ling, 0.2119034982f * linr);
+                const float ps = fmaf(0.2817188376f, ling, 0.0883024619f * linr);
+                slot0 = (b0 * cs + g) * cs + r;
+                slot_step = cs * cs;
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    const uint32_t bA = b0 + 2 * i, bB = bA + 1, bcA = min(bA, csm1), bcB = min(bB, csm1);
+                    const f2 linb = make_float2(s_lin[bcA], s_lin[bcB]);
+                    Bq[2 * i] = s_chv[bcA];
+                    Bq[2 * i + 1] = s_chv[bcB];
+                    lms_to_lab2(fma2(splat(0.0514459929f), linb, splat(pl)), fma2(splat(0.1073969566f), linb, splat(pm)),
+                                fma2(splat(0.6299787005f), linb, splat(ps)), a.lum, Lp[i], Ap[i], Bp[i]);
+                    const uint32_t flatA = slot0 + (2 * i) * slot_step, flatB = flatA + slot_step;
+                    if (rg_in && bA < cs && flatA >= begin && flatA < end) valid_mask |= 1u << (2 * i);
+                    if (rg_in && bB < cs && flatB >= begin && flatB < end) valid_mask |= 2u << (2 * i);
+                }
+                blo[0] = s_chv[r0]; bhi[0] = s_chv[min(r0 + 7u, csm1)];
+                blo[1] = s_chv[g0]; bhi[1] = s_chv[min(g0 + 3u, csm1)];
+                blo[2] = s_chv[b0]; bhi[2] = s_chv[min(b0 + EPT - 1, csm1)];
+            } else {
+                slot0 = t * (32u * EPT) + lane;
+                slot_step = 32u;
+                uint32_t cmin[3] = {255u, 255u, 255u}, cmax[3] = {0u, 0u, 0u};
+                f2 lin[3][NP];
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    const uint32_t pix = slot0 + e * 32u;
+                    const bool valid = pix < end;
+                    // past the end: repeat the tile's first pixel (always valid) so the box is unaffected
+                    uchar4 v = reinterpret_cast<const uchar4*>(a.f.out)[valid ? pix : t * (32u * EPT)];
+                    Bq[e] = v.x | ((uint32_t)v.y << 8) | ((uint32_t)v.z << 16);
+                    if (e & 1) { lin[0][e / 2].y = st.decode[v.x]; lin[1][e / 2].y = st.decode[v.y]; lin[2][e / 2].y = st.decode[v.z]; }
+                    else { lin[0][e / 2].x = st.decode[v.x]; lin[1][e / 2].x = st.decode[v.y]; lin[2][e / 2].x = st.decode[v.z]; }
+                    if (valid) valid_mask |= 1u << e;
+                    cmin[0] = min(cmin[0], (uint32_t)v.x); cmax[0] = max(cmax[0], (uint32_t)v.x);
+                    cmin[1] = min(cmin[1], (uint32_t)v.y); cmax[1] = max(cmax[1], (uint32_t)v.y);
+                    cmin[2] = min(cmin[2], (uint32_t)v.z); cmax[2] = max(cmax[2], (uint32_t)v.z);
+                }
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    f2 l = fma2(splat(0.4122214708f), lin[0][i], fma2(splat(0.5363325363f), lin[1][i], mul2(splat(0.0514459929f), lin[2][i])));
+                    f2 m = fma2(splat(0.2119034982f), lin[0][i], fma2(splat(0.6806995451f), lin[1][i], mul2(splat(0.1073969566f), lin[2][i])));
+                    f2 s = fma2(splat(0.0883024619f), lin[0][i], fma2(splat(0.2817188376f), lin[1][i], mul2(splat(0.6299787005f), lin[2][i])));
+                    lms_to_lab2(l, m, s, a.lum, Lp[i], Ap[i], Bp[i]);
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    blo[c] = __reduce_min_sync(FULL, cmin[c]);
+                    bhi[c] = __reduce_max_sync(FULL, cmax[c]);
+                }
+            }
+            if (!__any_sync(FULL, valid_mask != 0)) continue;
+            {
+                float mn[3] = {fminf(Lp[0].x, Lp[0].y), fminf(Ap[0].x, Ap[0].y), fminf(Bp[0].x, Bp[0].y)};
+                float mx[3] = {fmaxf(Lp[0].x, Lp[0].y), fmaxf(Ap[0].x, Ap[0].y), fmaxf(Bp[0].x, Bp[0].y)};
+#pragma unroll
+                for (int i = 1; i < NP; ++i) {
+                    mn[0] = fminf(mn[0], fminf(Lp[i].x, Lp[i].y)); mx[0] = fmaxf(mx[0], fmaxf(Lp[i].x, Lp[i].y));
+                    mn[1] = fminf(mn[1], fminf(Ap[i].x, Ap[i].y)); mx[1] = fmaxf(mx[1], fmaxf(Ap[i].x, Ap[i].y));
+                    mn[2] = fminf(mn[2], fminf(Bp[i].x, Bp[i].y)); mx[2] = fmaxf(mx[2], fmaxf(Bp[i].x, Bp[i].y));
+                }
+                // warp reduction on integer keys: a, b + 2 are positive floats (|a|, |b| < 0.5 inside the
+                // sRGB gamut; the 1.2e-7 rounding disappears in PAD); L*lum can be large and goes through f2key
+                const float PAD = 2e-5f;
+                lo[0] = key2f(__reduce_min_sync(FULL, f2key(mn[0]))) - PAD;
+                hi[0] = key2f(__reduce_max_sync(FULL, f2key(mx[0]))) + PAD;
+#pragma unroll
+                for (int c = 1; c < 3; ++c) {
+                    lo[c] = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(mn[c] + 2.0f))) - 2.0f - PAD;
+                    hi[c] = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(mx[c] + 2.0f))) - 2.0f + PAD;
+                }
+            }
+
+            // ---- 2.-4. classification, one palette colour per lane --------------------------------
+            float lbv, ubv;
+            bounds_of(p, lo, hi, lbv, ubv);
+            if (!active) { lbv = INFINITY; ubv = INFINITY; }
+            const float lbmin = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(lbv)));
+            const float ubmin = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(ubv)));
+            uint32_t nhit = 0;
+            __syncwarp();  // the previous tile's reads of hits / cand / bnd are over
+            if (KIND != KIND_NN) {
+                const uint32_t qr = prgb & 255u, qg = (prgb >> 8) & 255u, qb = prgb >> 16;
+                const bool inside = active && qr >= blo[0] && qr <= bhi[0] && qg >= blo[1] && qg <= bhi[1] && qb >= blo[2] && qb <= bhi[2];
+                const uint32_t bh = __ballot_sync(FULL, inside);
+                nhit = __popc(bh);
+                const uint32_t pos = __popc(bh & ((1u << lane) - 1u));
+                if (inside && pos < FAST_MAX_HITS) hits[pos] = prgb;
+            }
+            const float lg_ubmin = KIND == 1 ? lg2_approx(ubmin) : 0.f;
+            bool negl = false;
+            if (KIND != KIND_NN) negl = negligible_at<KIND>(lbv, ubmin, lg_ubmin, c1);
+            bool take_all = (k == 0);
+            if (k != 0 && KIND != KIND_NN) {
+                // the k-th smallest LB is negligible <=> fewer than k colours have a non-negligible LB
+                take_all = (uint32_t)__popc(__ballot_sync(FULL, active && !negl)) < k;
+            }
+            bool is_in = active, is_unc = false;
+            if (!take_all) {
+                // U_k = k-th smallest UB. Keys made unique by the lane number in the low mantissa bits
+                // (UB rounded UP to a multiple of 32 ulps first, so the bound stays conservative).
+                const uint32_t ukey = ((__float_as_uint(ubv) + 31u) & ~31u) | lane;
+                bnd[lane] = make_float2(lbv, __uint_as_float(ukey));
+                __syncwarp();
+                uint32_t rank_u = 0, rivals = 0;
+#pragma unroll 4
+                for (uint32_t q = 0; q < n; ++q) {
+                    const float2 bq = bnd[q];
+                    rank_u += (__float_as_uint(bq.y) < ukey) ? 1u : 0u;
+                    rivals += (bq.x <= ubv) ? 1u : 0u;  // counts the lane itself once (LB <= UB)
+                }
+                const uint32_t bu = __ballot_sync(FULL, active && rank_u == k - 1);
+                const float uk = __uint_as_float(__shfl_sync(FULL, ukey, __ffs(bu) - 1) | 31u);
+                const bool near = active && lbv <= uk;
+                is_in = near && rivals <= k;  // rivals - 1 (others) <= k - 1
+                is_unc = near && !is_in;
+            }
+            const uint32_t nin_all = __popc(__ballot_sync(FULL, is_in)), nunc_all = __popc(__ballot_sync(FULL, is_unc));
+            const bool list_in = is_in && !negl, list_unc = is_unc && !negl;
+            const uint32_t bin = __ballot_sync(FULL, list_in), bun = __ballot_sync(FULL, list_unc);
+            const uint32_t nin = __popc(bin), nunc = __popc(bun), lt = (1u << lane) - 1u;
+            // largest distance an uncertain colour can have: scales the near-tie tolerance
+            const float ubmax_unc = __uint_as_float(__reduce_max_sync(FULL, list_unc ? __float_as_uint(ubv) : 0u));
+            {
+                float4 q = p;
+                if (KIND == 0) {
+                    const float C = -c1;
+                    q = make_float4(-2.f * C * p.x, -2.f * C * p.y, -2.f * C * p.z, C * (psq - lbmin));
+                } else if (KIND == KIND_NN) {
+                    q = make_float4(-2.f * p.x, -2.f * p.y, -2.f * p.z, psq);
+                }
+                __syncwarp();
+                if (list_in) cand[__popc(bin & lt)] = q;
+                if (list_unc) cand[nin + __popc(bun & lt)] = q;
+                if (KIND == KIND_NN) {
+                    // palette index of every listed colour, for the result lookup
+                    if (list_in) bnd[__popc(bin & lt)].x = __uint_as_float(lane);
+                    if (list_unc) bnd[nin + __popc(bun & lt)].x = __uint_as_float(lane);
+                }
+                __syncwarp();
+            }
+            if (a.stats && lane == 0) {
+                atomicAdd(&a.stats[min(nunc, 63u)], 1u);
+                atomicAdd(&a.stats[64 + min(nin, 63u)], 1u);
+            }
+            const int kp = (int)k - (int)nin_all;
+            const bool choose = !take_all && kp > 0 && (int)nunc_all > kp && (int)nunc > kp;
+            const uint32_t direct = (take_all || kp <= 0 || choose) ? nin : nin + nunc;
+            // per-tile conditions that send every entry to the exact kernel: more exact-hit candidates
+            // than the list holds; weights so far from 1 that the reference's f64 sums leave their range
+            float c0 = 0.f;
+            bool all_exact = nhit > (uint32_t)FAST_MAX_HITS;
+            if (KIND == 0) all_exact |= !(-c1 * lbmin < 890.0f);
+            if (KIND == 1) {
+                c0 = -c1 * lg2_approx(lbmin > 0.f ? lbmin : ubmin);
+                all_exact |= !(fabsf(c0) < 890.0f);
+            }
+            nhit = min(nhit, (uint32_t)FAST_MAX_HITS);
+            float tol = WT_TIE_SLOPE * sqrt_approx(ubmax_unc);
+            if (KIND == 0 || KIND == KIND_NN) tol += WT_TIE_CONST;
+            if (KIND == 0) tol *= -c1;
+
+            // ---- 5. per entry ------------------------------------------------------------------
+            PixelIO px;
+            px.mode = MODE;
+            if (all_exact) {
+                if (valid_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, valid_mask, slot0, slot_step);
+                continue;
+            }
+            uint32_t flag_mask = 0;
+            if (KIND == KIND_NN) {
+                uint32_t best_j[EPT];
+                uint32_t risky_mask = 0;
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) best_j[e] = 0;
+                if (nin == 0) {
+                    float best[EPT], second[EPT];
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e) { best[e] = INFINITY; second[e] = INFINITY; }
+#pragma unroll 1
+                    for (uint32_t j = 0; j < nunc; ++j) {
+                        const float4 q = cand[j];
+#pragma unroll
+                        for (int i = 0; i < NP; ++i) {
+                            f2 d2 = wt_score2<KIND_NN>(q, Lp[i], Ap[i], Bp[i], splat(0.f));
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const int e = 2 * i + h;
+                                const float d = h ? d2.y : d2.x;
+                                const bool better = d < best[e];
+                                second[e] = better ? best[e] : fminf(second[e], d);
+                                best_j[e] = better ? j : best_j[e];
+                                best[e] = better ? d : best[e];
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e)
+                        if ((second[e] - best[e] <= tol) && (second[e] < INFINITY)) risky_mask |= 1u << e;
+                }
+                flag_mask = risky_mask & valid_mask;
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    if (!(((valid_mask & ~risky_mask) >> e) & 1u)) continue;
+                    px.slot = slot0 + e * slot_step;
+                    const uint32_t idx = __float_as_uint(bnd[best_j[e]].x);
+                    px.r = BRICK ? R : (Bq[e] & 255u); px.g = BRICK ? G : ((Bq[e] >> 8) & 255u); px.b = BRICK ? Bq[e] : (Bq[e] >> 16);
+                    if (!a.preserve) {
+                        uint32_t q = a.pal_rgb[idx];
+                        front_store<MODE>(a.f, px, q & 255u, (q >> 8) & 255u, (q >> 16) & 255u);
+                    } else {
+                        Lab ex = linear_to_oklab_exact(st.decode[px.r], st.decode[px.g], st.decode[px.b]);
+                        Lab o = {ex.l, a.pal_ab[2 * idx], a.pal_ab[2 * idx + 1]};
+                        float r, g, b;
+                        oklab_to_linear_exact(o, r, g, b);
+                        front_store<MODE>(a.f, px, f32_to_srgb8(r, st.encode), f32_to_srgb8(g, st.encode), f32_to_srgb8(b, st.encode));
+                    }
+                }
+                if (flag_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, flag_mask, slot0, slot_step);
+                continue;
+            }
+
+            f2 n0[NP], n1[NP], n2[NP], den[NP], cc[NP];
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                n0[i] = n1[i] = n2[i] = den[i] = splat(0.f);
+                cc[i] = KIND == 0 ? mul2(splat(-c1), fma2(Lp[i], Lp[i], fma2(Ap[i], Ap[i], mul2(Bp[i], Bp[i])))) : splat(0.f);
+            }
+#pragma unroll 2
+            for (uint32_t j = 0; j < direct; ++j) {
+                const float4 q = cand[j];
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    f2 w = wt_weight2<KIND>(wt_score2<KIND>(q, Lp[i], Ap[i], Bp[i], cc[i]), c1, c0);
+                    n0[i] = fma2(splat(q.x), w, n0[i]);
+                    n1[i] = fma2(splat(q.y), w, n1[i]);
+                    n2[i] = fma2(splat(q.z), w, n2[i]);
+                    den[i] = add2(den[i], w);
+                }
+            }
+            uint32_t risky_mask = 0;
+            if (choose) {
+                const float4* unc = cand + nin;
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    PairAcc pa = wt_select_any<KIND>(unc, (int)nunc, kp, Lp[i], Ap[i], Bp[i], cc[i], c1, c0, tol);
+                    n0[i] = add2(n0[i], pa.n0); n1[i] = add2(n1[i], pa.n1); n2[i] = add2(n2[i], pa.n2); den[i] = add2(den[i], pa.den);
+                    risky_mask |= pa.risky << (2 * i);
+                }
+            }
+            const float fs = KIND == 0 ? 0.5f / c1 : 1.0f;  // the Gaussian sums ran over -2C p = 2 c1 p
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                const f2 d = den[i];
+                if (!(d.x > 1e-30f) || !(d.x < 1e30f)) risky_mask |= 1u << (2 * i);
+                if (!(d.y > 1e-30f) || !(d.y < 1e30f)) risky_mask |= 2u << (2 * i);
+                const f2 inv = mul2(make_float2(rcp_approx(d.x), rcp_approx(d.y)), splat(fs));
+                f2 oL = a.preserve ? Lp[i] : mul2(n0[i], inv);
+                oL = mul2(oL, splat(a.inv_lum));
+                f2 r2, g2, b2;
+                oklab_to_linear2(oL, mul2(n1[i], inv), mul2(n2[i], inv), r2, g2, b2);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int e = 2 * i + h;
+                    if (!((valid_mask >> e) & 1u)) continue;
+                    px.slot = slot0 + e * slot_step;
+                    px.r = BRICK ? R : (Bq[e] & 255u); px.g = BRICK ? G : ((Bq[e] >> 8) & 255u); px.b = BRICK ? Bq[e] : (Bq[e] >> 16);
+                    // rbf.rs:66-68 palette.contains(&color): identical sRGB <=> identical Oklab triple
+                    if (nhit) {
+                        const uint32_t packed = px.r | (px.g << 8) | (px.b << 16);
+                        bool hit = false;
+#pragma unroll 1
+                        for (uint32_t hh = 0; hh < nhit; ++hh) hit |= (hits[hh] == packed);
+                        if (hit) {
+                            if (MODE != FRONT_IMAGE) front_store<MODE>(a.f, px, px.r, px.g, px.b);
+                            continue;
+                        }
+                    }
+                    if ((risky_mask >> e) & 1u) { flag_mask |= 1u << e; continue; }
+                    front_store<MODE>(a.f, px, f32_to_srgb8(h ? r2.y : r2.x, st.encode), f32_to_srgb8(h ? g2.y : g2.x, st.encode),
+                                      f32_to_srgb8(h ? b2.y : b2.x, st.encode));
+                }
+            }
+            if (flag_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, flag_mask, slot0, slot_step);
+        }
+    }
+}
+
+}  // namespace lutgen
