@@ -34,6 +34,9 @@
 
 namespace lutgen {
 
+#ifndef WT_MINB
+#define WT_MINB 3
+#endif
 constexpr int WT_THREADS = 256;
 constexpr int WT_WARPS = WT_THREADS / 32;
 constexpr int WT_BATCH = 4;          // warp tiles per hand-out
@@ -280,7 +283,7 @@ __device__ __forceinline__ void wt_divmod(uint32_t n, uint32_t d, float inv, uin
 }
 
 template <int KIND, int MODE, int EPT>
-__global__ void __launch_bounds__(WT_THREADS, 3) k_remap_warp(const WarpArgs a) {
+__global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpArgs a) {
     static_assert(EPT % 2 == 0, "entries are processed in pairs");
     constexpr int NP = EPT / 2;
     constexpr uint32_t FULL = 0xffffffffu;

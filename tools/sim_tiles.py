@@ -23,6 +23,7 @@ def main():
     shape = float(sys.argv[3]) if len(sys.argv) > 3 else 128.0
     level = int(sys.argv[4]) if len(sys.argv) > 4 else 16
     kind = sys.argv[5] if len(sys.argv) > 5 else "gauss"
+    NEG = -float(sys.argv[6]) if len(sys.argv) > 6 else -24.0
     if name.startswith("syn"):
         pal = synthetic_palette(int(name[3:]), 1)
     else:
@@ -37,7 +38,7 @@ def main():
     rgb = np.stack([rr, gg, bb], -1).reshape(-1, 3)
     lab = O.srgb_to_oklab(rgb).reshape(cs, cs, cs, 3)  # [r][g][b]
     c1 = -shape * np.log2(np.e)
-    for (tr, tg, tb) in [(8, 8, 16), (8, 8, 4), (8, 4, 4), (4, 4, 8), (4, 8, 4), (16, 4, 2), (8, 4, 8), (4, 4, 4), (8, 8, 2), (16, 8, 1), (32, 4, 1), (8, 8, 8), (16,16,4)]:
+    for (tr, tg, tb) in [(8, 8, 16), (8, 4, 4), (8, 4, 8), (4, 4, 4)]:
         if cs % tr or cs % tg or cs % tb:
             continue
         v = lab.reshape(cs // tr, tr, cs // tg, tg, cs // tb, tb, 3)
@@ -53,17 +54,17 @@ def main():
         ubmin = UB.min(1)
         kk = k if 0 < k < n else 0
         if kind == "gauss":
-            negl = c1 * (LB - ubmin[:, None]) < -24
+            negl = c1 * (LB - ubmin[:, None]) < NEG
         else:  # shepard power = shape
             with np.errstate(divide="ignore"):
-                negl = (-shape / 2) * (np.log2(np.maximum(LB, 1e-300)) - np.log2(ubmin[:, None])) < -24
+                negl = (-shape / 2) * (np.log2(np.maximum(LB, 1e-300)) - np.log2(ubmin[:, None])) < NEG
         if kk:
             uk = np.sort(UB, 1)[:, kk - 1]
             lk = np.sort(LB, 1)[:, kk - 1]
             if kind == "gauss":
-                moot = c1 * (lk - ubmin) < -24
+                moot = c1 * (lk - ubmin) < NEG
             else:
-                moot = (-shape / 2) * (np.log2(np.maximum(lk, 1e-300)) - np.log2(ubmin)) < -24
+                moot = (-shape / 2) * (np.log2(np.maximum(lk, 1e-300)) - np.log2(ubmin)) < NEG
             cand = LB <= uk[:, None]
             # rivals(t) = #{q != t: LB_q <= UB_t}
             LBs = np.sort(LB, 1)
