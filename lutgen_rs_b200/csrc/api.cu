@@ -283,20 +283,23 @@ bool fast_path_supported(const lutgen_remapper* r) {
     return true;
 }
 
-// Warp-tile kernel (kernels_warp.cuh): palettes of at most 32 colours and ordinary parameters.
+// Warp-tile kernels (kernels_warp.cuh): 0 = not applicable, 1 = k_remap_warp (palettes of at most 32
+// colours), 2 = k_remap_warp_big (33 .. 256 colours, nearest-k with k <= 32 or NearestNeighbor).
 template <int KIND>
-bool warp_path_supported(const lutgen_remapper* r, uint32_t n) {
+int warp_path(const lutgen_remapper* r, uint32_t n, uint32_t k) {
     static const bool off = getenv("LUTGEN_CUDA_NO_WARP") != nullptr;
-    if (off || n > (uint32_t)WT_MAX_N) return false;
+    if (off) return 0;
     if (KIND == 0) {
         // the expanded distance is scaled by C = shape*log2(e): keep it where f32 has room
         double C = r->d.param * 1.4426950408889634;
-        if (!(C >= 1e-3 && C <= 2000.0)) return false;
+        if (!(C >= 1e-3 && C <= 2000.0)) return 0;
     }
-    return true;
+    if (n <= (uint32_t)WT_MAX_N) return 1;
+    if (n <= (uint32_t)WB_MAX_N && k != 0 && k <= 32) return 2;
+    return 0;
 }
 
-template <int KIND, int MODE, int EPT>
+template <int KIND, int MODE, int EPT, bool BIG>
 int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const FastArgs& fa) {
     WarpArgs a{};
     a.f = f;
@@ -304,33 +307,36 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
     a.n = fa.n; a.k = fa.k; a.preserve = fa.preserve; a.lum = fa.lum; a.inv_lum = fa.inv_lum; a.c1 = fa.c1;
     a.flag_list = fa.flag_list; a.flag_count = fa.flag_count; a.tile_counter = fa.tile_counter;
     a.stats = fa.stats; a.tables = fa.tables;
+    // BIG: the CTA's eight warp tiles form one 16 x 8 x 2 EPT CTA tile (or 256 EPT pixels)
+    const uint32_t tr = BIG ? 16 : 8, tg = BIG ? 8 : 4, tb = BIG ? 2 * EPT : EPT, tpix = (BIG ? 256u : 32u) * EPT;
     if (MODE == FRONT_IMAGE) {
         a.tiles_r = a.tiles_g = 1;
         a.inv_tiles_r = a.inv_tiles_g = 1.0f;
-        a.ntiles = blocks_for(f.count, 32u * EPT);
+        a.ntiles = blocks_for(f.count, tpix);
     } else {
         uint32_t cs = f.cs;
-        a.tiles_r = (cs + 7) / 8;
-        a.tiles_g = (cs + 3) / 4;
+        a.tiles_r = (cs + tr - 1) / tr;
+        a.tiles_g = (cs + tg - 1) / tg;
         a.inv_tiles_r = 1.0f / (float)a.tiles_r;
         a.inv_tiles_g = 1.0f / (float)a.tiles_g;
         unsigned long long plane = (unsigned long long)cs * cs;
         // tile origins are multiples of the tile in every axis whatever the shard (see launch_fast)
-        uint32_t b_lo = (uint32_t)(f.begin / plane) / EPT * EPT, b_hi = (uint32_t)((f.begin + f.count - 1) / plane);
+        uint32_t b_lo = (uint32_t)(f.begin / plane) / tb * tb, b_hi = (uint32_t)((f.begin + f.count - 1) / plane);
         a.b_lo = b_lo;
-        a.ntiles = a.tiles_r * a.tiles_g * ((b_hi - b_lo) / EPT + 1);
+        a.ntiles = a.tiles_r * a.tiles_g * ((b_hi - b_lo) / tb + 1);
     }
-    static int per_sm = 0;  // one per <KIND, MODE, EPT> instantiation
+    static int per_sm = 0;  // one per instantiation
     if (per_sm == 0) {
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_remap_warp<KIND, MODE, EPT>, WT_THREADS, 0));
+        if (BIG) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_remap_warp_big<KIND, MODE, EPT>, WT_THREADS, 0));
+        else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_remap_warp<KIND, MODE, EPT>, WT_THREADS, 0));
         if (per_sm < 1) per_sm = 1;
     }
     unsigned grid = (unsigned)per_sm * (unsigned)g.sm_count;
-    unsigned need = blocks_for(a.ntiles, WT_WARPS * WT_BATCH);
-    (void)need;
+    unsigned need = BIG ? a.ntiles : blocks_for(a.ntiles, WT_WARPS * WT_BATCH);
     if (grid > need) grid = need;
     CU_TRY(cudaMemsetAsync(r->flag_count, 0, 2 * sizeof(uint32_t), s));
-    k_remap_warp<KIND, MODE, EPT><<<grid, WT_THREADS, 0, s>>>(a);
+    if (BIG) k_remap_warp_big<KIND, MODE, EPT><<<grid, WT_THREADS, 0, s>>>(a);
+    else k_remap_warp<KIND, MODE, EPT><<<grid, WT_THREADS, 0, s>>>(a);
     LAUNCH_CHECK();
     return LUTGEN_OK;
 }
@@ -371,8 +377,8 @@ int launch_fast(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
     fl.list = r->flag_list;
     fl.list_count = r->flag_count;
     fl.list_mode = MODE;
-    if (warp_path_supported<KIND>(r, a.n)) {
-        int rc = launch_warp<KIND, MODE, 4>(f, r, s, a);
+    if (const int wp = warp_path<KIND>(r, a.n, a.k)) {
+        int rc = wp == 1 ? launch_warp<KIND, MODE, 4, false>(f, r, s, a) : launch_warp<KIND, MODE, 4, true>(f, r, s, a);
         if (rc != LUTGEN_OK) return rc;
         if (nn) return launch_nn_exact<FRONT_LIST>(fl, r, s);
         return launch_rbf_exact_km<KIND < 3 ? KIND : 0, FRONT_LIST>(fl, r, s);

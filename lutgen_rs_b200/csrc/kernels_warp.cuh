@@ -282,17 +282,312 @@ __device__ __forceinline__ void wt_divmod(uint32_t n, uint32_t d, float inv, uin
     r = (uint32_t)rem;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pieces shared by the two kernels below.
+
+// A warp tile after step 1: the lane's EPT colours as Oklab register pairs, where they are stored,
+// the tile's sRGB box and its (inflated) Oklab box.
+template <int EPT>
+struct WtTile {
+    f2 Lp[EPT / 2], Ap[EPT / 2], Bp[EPT / 2];
+    uint32_t R, G, Bq[EPT];      // BRICK: channel values (R, G per lane, B per entry); IMAGE: Bq = packed rgb
+    uint32_t slot0, slot_step;   // entry e's slot = slot0 + e * slot_step
+    uint32_t valid_mask;
+    uint32_t blo[3], bhi[3];
+    float lo[3], hi[3];
+};
+
+struct WtShared {
+    const SmemTables* st;
+    const float* lin;     // decode[channel value of grid coordinate v]   (BRICK)
+    const uint8_t* chv;   // channel value of grid coordinate v            (BRICK)
+};
+
+// Step 1 for a brick tile with origin (r0, g0, b0): lane = (r, g), entry e = b plane.
+template <int EPT>
+__device__ __forceinline__ void wt_convert_brick(const WarpArgs& a, const WtShared& sh, uint32_t lane, uint32_t r0, uint32_t g0, uint32_t b0,
+                                                 WtTile<EPT>& T) {
+    constexpr int NP = EPT / 2;
+    const uint32_t cs = a.f.cs, csm1 = a.f.csm1;
+    const uint32_t begin = (uint32_t)a.f.begin, end = (uint32_t)(a.f.begin + a.f.count);
+    const uint32_t r = r0 + (lane & 7u), g = g0 + (lane >> 3), rc = min(r, csm1), gc = min(g, csm1);
+    const bool rg_in = r < cs && g < cs;
+    T.R = sh.chv[rc]; T.G = sh.chv[gc];
+    const float linr = sh.lin[rc], ling = sh.lin[gc];
+    const float pl = fmaf(0.5363325363f, ling, 0.4122214708f * linr);
+    const float pm = fmaf(0.6806995451f, ling, 0.2119034982f * linr);
+    const float ps = fmaf(0.2817188376f, ling, 0.0883024619f * linr);
+    T.slot0 = (b0 * cs + g) * cs + r;
+    T.slot_step = cs * cs;
+    T.valid_mask = 0;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const uint32_t bA = b0 + 2 * i, bB = bA + 1, bcA = min(bA, csm1), bcB = min(bB, csm1);
+        const f2 linb = make_float2(sh.lin[bcA], sh.lin[bcB]);
+        T.Bq[2 * i] = sh.chv[bcA];
+        T.Bq[2 * i + 1] = sh.chv[bcB];
+        lms_to_lab2(fma2(splat(0.0514459929f), linb, splat(pl)), fma2(splat(0.1073969566f), linb, splat(pm)),
+                    fma2(splat(0.6299787005f), linb, splat(ps)), a.lum, T.Lp[i], T.Ap[i], T.Bp[i]);
+        const uint32_t flatA = T.slot0 + (2 * i) * T.slot_step, flatB = flatA + T.slot_step;
+        if (rg_in && bA < cs && flatA >= begin && flatA < end) T.valid_mask |= 1u << (2 * i);
+        if (rg_in && bB < cs && flatB >= begin && flatB < end) T.valid_mask |= 2u << (2 * i);
+    }
+    T.blo[0] = sh.chv[min(r0, csm1)]; T.bhi[0] = sh.chv[min(r0 + 7u, csm1)];
+    T.blo[1] = sh.chv[min(g0, csm1)]; T.bhi[1] = sh.chv[min(g0 + 3u, csm1)];
+    T.blo[2] = sh.chv[min(b0, csm1)]; T.bhi[2] = sh.chv[min(b0 + EPT - 1, csm1)];
+}
+
+// Step 1 for 32*EPT consecutive pixels starting at `base` (base < end).
+template <int EPT>
+__device__ __forceinline__ void wt_convert_image(const WarpArgs& a, const WtShared& sh, uint32_t lane, uint32_t base, WtTile<EPT>& T) {
+    constexpr int NP = EPT / 2;
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t end = (uint32_t)(a.f.begin + a.f.count);
+    T.R = T.G = 0;
+    T.slot0 = base + lane;
+    T.slot_step = 32u;
+    T.valid_mask = 0;
+    uint32_t cmin[3] = {255u, 255u, 255u}, cmax[3] = {0u, 0u, 0u};
+    f2 lin[3][NP];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        const uint32_t pix = T.slot0 + e * 32u;
+        const bool valid = pix < end;
+        // past the end: repeat the tile's first pixel (always valid) so the box is unaffected
+        uchar4 v = reinterpret_cast<const uchar4*>(a.f.out)[valid ? pix : base];
+        T.Bq[e] = v.x | ((uint32_t)v.y << 8) | ((uint32_t)v.z << 16);
+        if (e & 1) { lin[0][e / 2].y = sh.st->decode[v.x]; lin[1][e / 2].y = sh.st->decode[v.y]; lin[2][e / 2].y = sh.st->decode[v.z]; }
+        else { lin[0][e / 2].x = sh.st->decode[v.x]; lin[1][e / 2].x = sh.st->decode[v.y]; lin[2][e / 2].x = sh.st->decode[v.z]; }
+        if (valid) T.valid_mask |= 1u << e;
+        cmin[0] = min(cmin[0], (uint32_t)v.x); cmax[0] = max(cmax[0], (uint32_t)v.x);
+        cmin[1] = min(cmin[1], (uint32_t)v.y); cmax[1] = max(cmax[1], (uint32_t)v.y);
+        cmin[2] = min(cmin[2], (uint32_t)v.z); cmax[2] = max(cmax[2], (uint32_t)v.z);
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        f2 l = fma2(splat(0.4122214708f), lin[0][i], fma2(splat(0.5363325363f), lin[1][i], mul2(splat(0.0514459929f), lin[2][i])));
+        f2 m = fma2(splat(0.2119034982f), lin[0][i], fma2(splat(0.6806995451f), lin[1][i], mul2(splat(0.1073969566f), lin[2][i])));
+        f2 s = fma2(splat(0.0883024619f), lin[0][i], fma2(splat(0.2817188376f), lin[1][i], mul2(splat(0.6299787005f), lin[2][i])));
+        lms_to_lab2(l, m, s, a.lum, T.Lp[i], T.Ap[i], T.Bp[i]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        T.blo[c] = __reduce_min_sync(FULL, cmin[c]);
+        T.bhi[c] = __reduce_max_sync(FULL, cmax[c]);
+    }
+}
+
+// The tile's Oklab bounding box (warp reduction), inflated by PAD.
+template <int EPT>
+__device__ __forceinline__ void wt_box(WtTile<EPT>& T) {
+    constexpr int NP = EPT / 2;
+    constexpr uint32_t FULL = 0xffffffffu;
+    float mn[3] = {fminf(T.Lp[0].x, T.Lp[0].y), fminf(T.Ap[0].x, T.Ap[0].y), fminf(T.Bp[0].x, T.Bp[0].y)};
+    float mx[3] = {fmaxf(T.Lp[0].x, T.Lp[0].y), fmaxf(T.Ap[0].x, T.Ap[0].y), fmaxf(T.Bp[0].x, T.Bp[0].y)};
+#pragma unroll
+    for (int i = 1; i < NP; ++i) {
+        mn[0] = fminf(mn[0], fminf(T.Lp[i].x, T.Lp[i].y)); mx[0] = fmaxf(mx[0], fmaxf(T.Lp[i].x, T.Lp[i].y));
+        mn[1] = fminf(mn[1], fminf(T.Ap[i].x, T.Ap[i].y)); mx[1] = fmaxf(mx[1], fmaxf(T.Ap[i].x, T.Ap[i].y));
+        mn[2] = fminf(mn[2], fminf(T.Bp[i].x, T.Bp[i].y)); mx[2] = fmaxf(mx[2], fmaxf(T.Bp[i].x, T.Bp[i].y));
+    }
+    // warp reduction on integer keys: a, b + 2 are positive floats (|a|, |b| < 0.5 inside the sRGB
+    // gamut; the 1.2e-7 rounding disappears in PAD); L*lum can be large and goes through f2key
+    const float PAD = 2e-5f;
+    T.lo[0] = key2f(__reduce_min_sync(FULL, f2key(mn[0]))) - PAD;
+    T.hi[0] = key2f(__reduce_max_sync(FULL, f2key(mx[0]))) + PAD;
+#pragma unroll
+    for (int c = 1; c < 3; ++c) {
+        T.lo[c] = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(mn[c] + 2.0f))) - 2.0f - PAD;
+        T.hi[c] = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(mx[c] + 2.0f))) - 2.0f + PAD;
+    }
+}
+
+// What the list holds for palette colour p (header).
+template <int KIND>
+__device__ __forceinline__ float4 wt_list_entry(float4 p, float psq, float c1, float lbmin) {
+    if (KIND == 0) {
+        const float C = -c1;
+        return make_float4(-2.f * C * p.x, -2.f * C * p.y, -2.f * C * p.z, C * (psq - lbmin));
+    }
+    if (KIND == KIND_NN) return make_float4(-2.f * p.x, -2.f * p.y, -2.f * p.z, psq);
+    return p;
+}
+
+// Outcome of the classification of one tile (warp uniform).
+struct WtClass {
+    uint32_t nin, nunc;          // list lengths: cand[0 .. nin) IN, cand[nin .. nin + nunc) UNCERTAIN
+    uint32_t nin_all, nunc_all;  // class sizes (negligible colours included)
+    uint32_t nhit;               // exact-hit candidates (may exceed FAST_MAX_HITS: then every entry is flagged)
+    bool take_all;
+    bool force_exact;            // the tile cannot be handled here
+    float lbmin, ubmin, ubmax_unc;
+};
+
+// Step 5: everything per entry, given the candidate list.
+//   cand  : per-warp list (wt_list_entry of every listed colour), cidx: palette index of each
+//   hits  : packed sRGB of the palette colours that may equal a colour of the tile exactly
+template <int KIND, int MODE, int EPT>
+__device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& st, const WtTile<EPT>& T, const WtClass& cl,
+                                           const float4* __restrict__ cand, const uint32_t* __restrict__ cidx,
+                                           const uint32_t* __restrict__ hits) {
+    constexpr int NP = EPT / 2;
+    constexpr bool BRICK = MODE != FRONT_IMAGE;
+    const float c1 = a.c1;
+    const uint32_t k = a.k, nin = cl.nin, nunc = cl.nunc;
+    const int kp = (int)k - (int)cl.nin_all;
+    const bool choose = !cl.take_all && kp > 0 && (int)cl.nunc_all > kp && (int)nunc > kp;
+    const uint32_t direct = (cl.take_all || kp <= 0 || choose) ? nin : nin + nunc;
+    // per-tile conditions that send every entry to the exact kernel: more exact-hit candidates than
+    // the list holds; weights so far from 1 that the reference's f64 sums leave their range; more
+    // neighbours to choose than the selection handles
+    float c0 = 0.f;
+    bool all_exact = cl.force_exact || cl.nhit > (uint32_t)FAST_MAX_HITS || (choose && kp > 32);
+    if (KIND == 0) all_exact |= !(-c1 * cl.lbmin < 890.0f);
+    if (KIND == 1) {
+        c0 = -c1 * lg2_approx(cl.lbmin > 0.f ? cl.lbmin : cl.ubmin);
+        all_exact |= !(fabsf(c0) < 890.0f);
+    }
+    const uint32_t nhit = min(cl.nhit, (uint32_t)FAST_MAX_HITS);
+    float tol = WT_TIE_SLOPE * sqrt_approx(cl.ubmax_unc);
+    if (KIND == 0 || KIND == KIND_NN) tol += WT_TIE_CONST;
+    if (KIND == 0) tol *= -c1;
+
+    PixelIO px;
+    px.mode = MODE;
+    if (all_exact) {
+        if (T.valid_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, T.valid_mask, T.slot0, T.slot_step);
+        return;
+    }
+    uint32_t flag_mask = 0;
+    if (KIND == KIND_NN) {
+        uint32_t best_j[EPT];
+        uint32_t risky_mask = 0;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) best_j[e] = 0;
+        if (nin == 0) {
+            float best[EPT], second[EPT];
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) { best[e] = INFINITY; second[e] = INFINITY; }
+#pragma unroll 1
+            for (uint32_t j = 0; j < nunc; ++j) {
+                const float4 q = cand[j];
+#pragma unroll
+                for (int i = 0; i < NP; ++i) {
+                    f2 d2 = wt_score2<KIND_NN>(q, T.Lp[i], T.Ap[i], T.Bp[i], splat(0.f));
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int e = 2 * i + h;
+                        const float d = h ? d2.y : d2.x;
+                        const bool better = d < best[e];
+                        second[e] = better ? best[e] : fminf(second[e], d);
+                        best_j[e] = better ? j : best_j[e];
+                        best[e] = better ? d : best[e];
+                    }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < EPT; ++e)
+                if ((second[e] - best[e] <= tol) && (second[e] < INFINITY)) risky_mask |= 1u << e;
+        }
+        flag_mask = risky_mask & T.valid_mask;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            if (!(((T.valid_mask & ~risky_mask) >> e) & 1u)) continue;
+            px.slot = T.slot0 + e * T.slot_step;
+            const uint32_t idx = cidx[best_j[e]];
+            px.r = BRICK ? T.R : (T.Bq[e] & 255u); px.g = BRICK ? T.G : ((T.Bq[e] >> 8) & 255u); px.b = BRICK ? T.Bq[e] : (T.Bq[e] >> 16);
+            if (!a.preserve) {
+                uint32_t q = a.pal_rgb[idx];
+                front_store<MODE>(a.f, px, q & 255u, (q >> 8) & 255u, (q >> 16) & 255u);
+            } else {
+                Lab ex = linear_to_oklab_exact(st.decode[px.r], st.decode[px.g], st.decode[px.b]);
+                Lab o = {ex.l, a.pal_ab[2 * idx], a.pal_ab[2 * idx + 1]};
+                float r, g, b;
+                oklab_to_linear_exact(o, r, g, b);
+                front_store<MODE>(a.f, px, f32_to_srgb8(r, st.encode), f32_to_srgb8(g, st.encode), f32_to_srgb8(b, st.encode));
+            }
+        }
+        if (flag_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, flag_mask, T.slot0, T.slot_step);
+        return;
+    }
+
+    f2 n0[NP], n1[NP], n2[NP], den[NP], cc[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        n0[i] = n1[i] = n2[i] = den[i] = splat(0.f);
+        cc[i] = KIND == 0 ? mul2(splat(-c1), fma2(T.Lp[i], T.Lp[i], fma2(T.Ap[i], T.Ap[i], mul2(T.Bp[i], T.Bp[i])))) : splat(0.f);
+    }
+#pragma unroll 2
+    for (uint32_t j = 0; j < direct; ++j) {
+        const float4 q = cand[j];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            f2 w = wt_weight2<KIND>(wt_score2<KIND>(q, T.Lp[i], T.Ap[i], T.Bp[i], cc[i]), c1, c0);
+            n0[i] = fma2(splat(q.x), w, n0[i]);
+            n1[i] = fma2(splat(q.y), w, n1[i]);
+            n2[i] = fma2(splat(q.z), w, n2[i]);
+            den[i] = add2(den[i], w);
+        }
+    }
+    uint32_t risky_mask = 0;
+    if (choose) {
+        const float4* unc = cand + nin;
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            PairAcc pa = wt_select_any<KIND>(unc, (int)nunc, kp, T.Lp[i], T.Ap[i], T.Bp[i], cc[i], c1, c0, tol);
+            n0[i] = add2(n0[i], pa.n0); n1[i] = add2(n1[i], pa.n1); n2[i] = add2(n2[i], pa.n2); den[i] = add2(den[i], pa.den);
+            risky_mask |= pa.risky << (2 * i);
+        }
+    }
+    const float fs = KIND == 0 ? 0.5f / c1 : 1.0f;  // the Gaussian sums ran over -2C p = 2 c1 p
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        const f2 d = den[i];
+        if (!(d.x > 1e-30f) || !(d.x < 1e30f)) risky_mask |= 1u << (2 * i);
+        if (!(d.y > 1e-30f) || !(d.y < 1e30f)) risky_mask |= 2u << (2 * i);
+        const f2 inv = mul2(make_float2(rcp_approx(d.x), rcp_approx(d.y)), splat(fs));
+        f2 oL = a.preserve ? T.Lp[i] : mul2(n0[i], inv);
+        oL = mul2(oL, splat(a.inv_lum));
+        f2 r2, g2, b2;
+        oklab_to_linear2(oL, mul2(n1[i], inv), mul2(n2[i], inv), r2, g2, b2);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int e = 2 * i + h;
+            if (!((T.valid_mask >> e) & 1u)) continue;
+            px.slot = T.slot0 + e * T.slot_step;
+            px.r = BRICK ? T.R : (T.Bq[e] & 255u); px.g = BRICK ? T.G : ((T.Bq[e] >> 8) & 255u); px.b = BRICK ? T.Bq[e] : (T.Bq[e] >> 16);
+            // rbf.rs:66-68 palette.contains(&color): identical sRGB <=> identical Oklab triple
+            if (nhit) {
+                const uint32_t packed = px.r | (px.g << 8) | (px.b << 16);
+                bool hit = false;
+#pragma unroll 1
+                for (uint32_t hh = 0; hh < nhit; ++hh) hit |= (hits[hh] == packed);
+                if (hit) {
+                    if (MODE != FRONT_IMAGE) front_store<MODE>(a.f, px, px.r, px.g, px.b);
+                    continue;
+                }
+            }
+            if ((risky_mask >> e) & 1u) { flag_mask |= 1u << e; continue; }
+            front_store<MODE>(a.f, px, f32_to_srgb8(h ? r2.y : r2.x, st.encode), f32_to_srgb8(h ? g2.y : g2.x, st.encode),
+                              f32_to_srgb8(h ? b2.y : b2.x, st.encode));
+        }
+    }
+    if (flag_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, flag_mask, T.slot0, T.slot_step);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Palettes of at most 32 colours: every warp on its own, one palette colour per lane.
 template <int KIND, int MODE, int EPT>
 __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpArgs a) {
     static_assert(EPT % 2 == 0, "entries are processed in pairs");
-    constexpr int NP = EPT / 2;
     constexpr uint32_t FULL = 0xffffffffu;
     constexpr bool BRICK = MODE != FRONT_IMAGE;
     __shared__ SmemTables st;
-    __shared__ float s_lin[BRICK ? WT_MAX_CS : 1];      // decode[channel value of grid coordinate v]
-    __shared__ uint8_t s_chv[BRICK ? WT_MAX_CS + 3 : 4];  // channel value of grid coordinate v
+    __shared__ float s_lin[BRICK ? WT_MAX_CS : 1];
+    __shared__ uint8_t s_chv[BRICK ? WT_MAX_CS + 3 : 4];
     __shared__ __align__(16) float4 s_cand[WT_WARPS][WT_MAX_N];
     __shared__ __align__(8) float2 s_bnd[WT_WARPS][WT_MAX_N];
+    __shared__ uint32_t s_cidx[WT_WARPS][WT_MAX_N];
     __shared__ uint32_t s_hit[WT_WARPS][FAST_MAX_HITS];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -311,6 +606,8 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
         for (uint32_t v = tid; v < cs; v += WT_THREADS) s_lin[v] = st.decode[s_chv[v]];
         __syncthreads();
     }
+    WtShared sh;
+    sh.st = &st; sh.lin = s_lin; sh.chv = s_chv;
 
     // this lane's palette colour
     const bool active = lane < n;
@@ -319,8 +616,8 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
     const float psq = fmaf(p.x, p.x, fmaf(p.y, p.y, p.z * p.z));
     float4* cand = s_cand[warp];
     float2* bnd = s_bnd[warp];
+    uint32_t* cidx = s_cidx[warp];
     uint32_t* hits = s_hit[warp];
-    const uint32_t lr = lane & 7u, lg = lane >> 3;
 
     for (;;) {
         uint32_t t0 = 0;
@@ -337,122 +634,48 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
 #pragma unroll 1
         for (uint32_t t = t0; t < t1; ++t) {
             // ---- 1. colours of this tile -> Oklab (register pairs), bounding box ----------------
-            f2 Lp[NP], Ap[NP], Bp[NP];
-            uint32_t R = 0, G = 0, Bq[EPT];
-            uint32_t slot0 = 0, slot_step = 0;  // entry e's slot = slot0 + e * slot_step
-            uint32_t valid_mask = 0;
-            uint32_t blo[3] = {0, 0, 0}, bhi[3] = {255, 255, 255};  // sRGB box of the tile
-            float lo[3], hi[3];
+            WtTile<EPT> T;
             if (BRICK) {
                 const uint32_t r0 = ir * 8u, g0 = ig * 4u, b0 = a.b_lo + ib * (uint32_t)EPT;
                 if (++ir == a.tiles_r) { ir = 0; if (++ig == a.tiles_g) { ig = 0; ++ib; } }
                 const uint32_t first = (b0 * cs + g0) * cs + r0;
                 const uint32_t last = (min(b0 + EPT - 1, csm1) * cs + min(g0 + 3u, csm1)) * cs + min(r0 + 7u, csm1);
                 if (b0 > csm1 || last < begin || first >= end) continue;  // uniform
-                const uint32_t r = r0 + lr, g = g0 + lg, rc = min(r, csm1), gc = min(g, csm1);
-                const bool rg_in = r < cs && g < cs;
-                R = s_chv[rc]; G = s_chv[gc];
-                const float linr = s_lin[rc], ling = s_lin[gc];
-                const float pl = fmaf(0.5363325363f, ling, 0.4122214708f * linr);
-                const float pm = fmaf(0.6806995451f, ling, 0.2119034982f * linr);
-                const float ps = fmaf(0.2817188376f, ling, 0.0883024619f * linr);
-                slot0 = (b0 * cs + g) * cs + r;
-                slot_step = cs * cs;
-#pragma unroll
-                for (int i = 0; i < NP; ++i) {
-                    const uint32_t bA = b0 + 2 * i, bB = bA + 1, bcA = min(bA, csm1), bcB = min(bB, csm1);
-                    const f2 linb = make_float2(s_lin[bcA], s_lin[bcB]);
-                    Bq[2 * i] = s_chv[bcA];
-                    Bq[2 * i + 1] = s_chv[bcB];
-                    lms_to_lab2(fma2(splat(0.0514459929f), linb, splat(pl)), fma2(splat(0.1073969566f), linb, splat(pm)),
-                                fma2(splat(0.6299787005f), linb, splat(ps)), a.lum, Lp[i], Ap[i], Bp[i]);
-                    const uint32_t flatA = slot0 + (2 * i) * slot_step, flatB = flatA + slot_step;
-                    if (rg_in && bA < cs && flatA >= begin && flatA < end) valid_mask |= 1u << (2 * i);
-                    if (rg_in && bB < cs && flatB >= begin && flatB < end) valid_mask |= 2u << (2 * i);
-                }
-                blo[0] = s_chv[r0]; bhi[0] = s_chv[min(r0 + 7u, csm1)];
-                blo[1] = s_chv[g0]; bhi[1] = s_chv[min(g0 + 3u, csm1)];
-                blo[2] = s_chv[b0]; bhi[2] = s_chv[min(b0 + EPT - 1, csm1)];
+                wt_convert_brick<EPT>(a, sh, lane, r0, g0, b0, T);
             } else {
-                slot0 = t * (32u * EPT) + lane;
-                slot_step = 32u;
-                uint32_t cmin[3] = {255u, 255u, 255u}, cmax[3] = {0u, 0u, 0u};
-                f2 lin[3][NP];
-#pragma unroll
-                for (int e = 0; e < EPT; ++e) {
-                    const uint32_t pix = slot0 + e * 32u;
-                    const bool valid = pix < end;
-                    // past the end: repeat the tile's first pixel (always valid) so the box is unaffected
-                    uchar4 v = reinterpret_cast<const uchar4*>(a.f.out)[valid ? pix : t * (32u * EPT)];
-                    Bq[e] = v.x | ((uint32_t)v.y << 8) | ((uint32_t)v.z << 16);
-                    if (e & 1) { lin[0][e / 2].y = st.decode[v.x]; lin[1][e / 2].y = st.decode[v.y]; lin[2][e / 2].y = st.decode[v.z]; }
-                    else { lin[0][e / 2].x = st.decode[v.x]; lin[1][e / 2].x = st.decode[v.y]; lin[2][e / 2].x = st.decode[v.z]; }
-                    if (valid) valid_mask |= 1u << e;
-                    cmin[0] = min(cmin[0], (uint32_t)v.x); cmax[0] = max(cmax[0], (uint32_t)v.x);
-                    cmin[1] = min(cmin[1], (uint32_t)v.y); cmax[1] = max(cmax[1], (uint32_t)v.y);
-                    cmin[2] = min(cmin[2], (uint32_t)v.z); cmax[2] = max(cmax[2], (uint32_t)v.z);
-                }
-#pragma unroll
-                for (int i = 0; i < NP; ++i) {
-                    f2 l = fma2(splat(0.4122214708f), lin[0][i], fma2(splat(0.5363325363f), lin[1][i], mul2(splat(0.0514459929f), lin[2][i])));
-                    f2 m = fma2(splat(0.2119034982f), lin[0][i], fma2(splat(0.6806995451f), lin[1][i], mul2(splat(0.1073969566f), lin[2][i])));
-                    f2 s = fma2(splat(0.0883024619f), lin[0][i], fma2(splat(0.2817188376f), lin[1][i], mul2(splat(0.6299787005f), lin[2][i])));
-                    lms_to_lab2(l, m, s, a.lum, Lp[i], Ap[i], Bp[i]);
-                }
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    blo[c] = __reduce_min_sync(FULL, cmin[c]);
-                    bhi[c] = __reduce_max_sync(FULL, cmax[c]);
-                }
+                wt_convert_image<EPT>(a, sh, lane, t * (32u * EPT), T);
             }
-            if (!__any_sync(FULL, valid_mask != 0)) continue;
-            {
-                float mn[3] = {fminf(Lp[0].x, Lp[0].y), fminf(Ap[0].x, Ap[0].y), fminf(Bp[0].x, Bp[0].y)};
-                float mx[3] = {fmaxf(Lp[0].x, Lp[0].y), fmaxf(Ap[0].x, Ap[0].y), fmaxf(Bp[0].x, Bp[0].y)};
-#pragma unroll
-                for (int i = 1; i < NP; ++i) {
-                    mn[0] = fminf(mn[0], fminf(Lp[i].x, Lp[i].y)); mx[0] = fmaxf(mx[0], fmaxf(Lp[i].x, Lp[i].y));
-                    mn[1] = fminf(mn[1], fminf(Ap[i].x, Ap[i].y)); mx[1] = fmaxf(mx[1], fmaxf(Ap[i].x, Ap[i].y));
-                    mn[2] = fminf(mn[2], fminf(Bp[i].x, Bp[i].y)); mx[2] = fmaxf(mx[2], fmaxf(Bp[i].x, Bp[i].y));
-                }
-                // warp reduction on integer keys: a, b + 2 are positive floats (|a|, |b| < 0.5 inside the
-                // sRGB gamut; the 1.2e-7 rounding disappears in PAD); L*lum can be large and goes through f2key
-                const float PAD = 2e-5f;
-                lo[0] = key2f(__reduce_min_sync(FULL, f2key(mn[0]))) - PAD;
-                hi[0] = key2f(__reduce_max_sync(FULL, f2key(mx[0]))) + PAD;
-#pragma unroll
-                for (int c = 1; c < 3; ++c) {
-                    lo[c] = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(mn[c] + 2.0f))) - 2.0f - PAD;
-                    hi[c] = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(mx[c] + 2.0f))) - 2.0f + PAD;
-                }
-            }
+            if (!__any_sync(FULL, T.valid_mask != 0)) continue;
+            wt_box<EPT>(T);
 
             // ---- 2.-4. classification, one palette colour per lane --------------------------------
+            WtClass cl;
+            cl.force_exact = false;
             float lbv, ubv;
-            bounds_of(p, lo, hi, lbv, ubv);
+            bounds_of(p, T.lo, T.hi, lbv, ubv);
             if (!active) { lbv = INFINITY; ubv = INFINITY; }
-            const float lbmin = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(lbv)));
-            const float ubmin = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(ubv)));
-            uint32_t nhit = 0;
-            __syncwarp();  // the previous tile's reads of hits / cand / bnd are over
+            cl.lbmin = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(lbv)));
+            cl.ubmin = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(ubv)));
+            cl.nhit = 0;
+            __syncwarp();  // the previous tile's reads of hits / cand / cidx / bnd are over
             if (KIND != KIND_NN) {
                 const uint32_t qr = prgb & 255u, qg = (prgb >> 8) & 255u, qb = prgb >> 16;
-                const bool inside = active && qr >= blo[0] && qr <= bhi[0] && qg >= blo[1] && qg <= bhi[1] && qb >= blo[2] && qb <= bhi[2];
+                const bool inside = active && qr >= T.blo[0] && qr <= T.bhi[0] && qg >= T.blo[1] && qg <= T.bhi[1] && qb >= T.blo[2] && qb <= T.bhi[2];
                 const uint32_t bh = __ballot_sync(FULL, inside);
-                nhit = __popc(bh);
+                cl.nhit = __popc(bh);
                 const uint32_t pos = __popc(bh & ((1u << lane) - 1u));
                 if (inside && pos < FAST_MAX_HITS) hits[pos] = prgb;
             }
-            const float lg_ubmin = KIND == 1 ? lg2_approx(ubmin) : 0.f;
+            const float lg_ubmin = KIND == 1 ? lg2_approx(cl.ubmin) : 0.f;
             bool negl = false;
-            if (KIND != KIND_NN) negl = negligible_at<KIND>(lbv, ubmin, lg_ubmin, c1);
-            bool take_all = (k == 0);
+            if (KIND != KIND_NN) negl = negligible_at<KIND>(lbv, cl.ubmin, lg_ubmin, c1);
+            cl.take_all = (k == 0);
             if (k != 0 && KIND != KIND_NN) {
                 // the k-th smallest LB is negligible <=> fewer than k colours have a non-negligible LB
-                take_all = (uint32_t)__popc(__ballot_sync(FULL, active && !negl)) < k;
+                cl.take_all = (uint32_t)__popc(__ballot_sync(FULL, active && !negl)) < k;
             }
             bool is_in = active, is_unc = false;
-            if (!take_all) {
+            if (!cl.take_all) {
                 // U_k = k-th smallest UB. Keys made unique by the lane number in the low mantissa bits
                 // (UB rounded UP to a multiple of 32 ulps first, so the bound stays conservative).
                 const uint32_t ukey = ((__float_as_uint(ubv) + 31u) & ~31u) | lane;
@@ -471,174 +694,319 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
                 is_in = near && rivals <= k;  // rivals - 1 (others) <= k - 1
                 is_unc = near && !is_in;
             }
-            const uint32_t nin_all = __popc(__ballot_sync(FULL, is_in)), nunc_all = __popc(__ballot_sync(FULL, is_unc));
+            cl.nin_all = __popc(__ballot_sync(FULL, is_in));
+            cl.nunc_all = __popc(__ballot_sync(FULL, is_unc));
             const bool list_in = is_in && !negl, list_unc = is_unc && !negl;
-            const uint32_t bin = __ballot_sync(FULL, list_in), bun = __ballot_sync(FULL, list_unc);
-            const uint32_t nin = __popc(bin), nunc = __popc(bun), lt = (1u << lane) - 1u;
+            const uint32_t bin = __ballot_sync(FULL, list_in), bun = __ballot_sync(FULL, list_unc), lt = (1u << lane) - 1u;
+            cl.nin = __popc(bin);
+            cl.nunc = __popc(bun);
             // largest distance an uncertain colour can have: scales the near-tie tolerance
-            const float ubmax_unc = __uint_as_float(__reduce_max_sync(FULL, list_unc ? __float_as_uint(ubv) : 0u));
+            cl.ubmax_unc = __uint_as_float(__reduce_max_sync(FULL, list_unc ? __float_as_uint(ubv) : 0u));
             {
-                float4 q = p;
-                if (KIND == 0) {
-                    const float C = -c1;
-                    q = make_float4(-2.f * C * p.x, -2.f * C * p.y, -2.f * C * p.z, C * (psq - lbmin));
-                } else if (KIND == KIND_NN) {
-                    q = make_float4(-2.f * p.x, -2.f * p.y, -2.f * p.z, psq);
-                }
-                __syncwarp();
-                if (list_in) cand[__popc(bin & lt)] = q;
-                if (list_unc) cand[nin + __popc(bun & lt)] = q;
-                if (KIND == KIND_NN) {
-                    // palette index of every listed colour, for the result lookup
-                    if (list_in) bnd[__popc(bin & lt)].x = __uint_as_float(lane);
-                    if (list_unc) bnd[nin + __popc(bun & lt)].x = __uint_as_float(lane);
-                }
+                const float4 q = wt_list_entry<KIND>(p, psq, c1, cl.lbmin);
+                if (list_in) { const uint32_t pos = __popc(bin & lt); cand[pos] = q; if (KIND == KIND_NN) cidx[pos] = lane; }
+                if (list_unc) { const uint32_t pos = cl.nin + __popc(bun & lt); cand[pos] = q; if (KIND == KIND_NN) cidx[pos] = lane; }
                 __syncwarp();
             }
             if (a.stats && lane == 0) {
-                atomicAdd(&a.stats[min(nunc, 63u)], 1u);
-                atomicAdd(&a.stats[64 + min(nin, 63u)], 1u);
+                atomicAdd(&a.stats[min(cl.nunc, 63u)], 1u);
+                atomicAdd(&a.stats[64 + min(cl.nin, 63u)], 1u);
             }
-            const int kp = (int)k - (int)nin_all;
-            const bool choose = !take_all && kp > 0 && (int)nunc_all > kp && (int)nunc > kp;
-            const uint32_t direct = (take_all || kp <= 0 || choose) ? nin : nin + nunc;
-            // per-tile conditions that send every entry to the exact kernel: more exact-hit candidates
-            // than the list holds; weights so far from 1 that the reference's f64 sums leave their range
-            float c0 = 0.f;
-            bool all_exact = nhit > (uint32_t)FAST_MAX_HITS;
-            if (KIND == 0) all_exact |= !(-c1 * lbmin < 890.0f);
-            if (KIND == 1) {
-                c0 = -c1 * lg2_approx(lbmin > 0.f ? lbmin : ubmin);
-                all_exact |= !(fabsf(c0) < 890.0f);
-            }
-            nhit = min(nhit, (uint32_t)FAST_MAX_HITS);
-            float tol = WT_TIE_SLOPE * sqrt_approx(ubmax_unc);
-            if (KIND == 0 || KIND == KIND_NN) tol += WT_TIE_CONST;
-            if (KIND == 0) tol *= -c1;
-
             // ---- 5. per entry ------------------------------------------------------------------
-            PixelIO px;
-            px.mode = MODE;
-            if (all_exact) {
-                if (valid_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, valid_mask, slot0, slot_step);
-                continue;
-            }
-            uint32_t flag_mask = 0;
-            if (KIND == KIND_NN) {
-                uint32_t best_j[EPT];
-                uint32_t risky_mask = 0;
-#pragma unroll
-                for (int e = 0; e < EPT; ++e) best_j[e] = 0;
-                if (nin == 0) {
-                    float best[EPT], second[EPT];
-#pragma unroll
-                    for (int e = 0; e < EPT; ++e) { best[e] = INFINITY; second[e] = INFINITY; }
-#pragma unroll 1
-                    for (uint32_t j = 0; j < nunc; ++j) {
-                        const float4 q = cand[j];
-#pragma unroll
-                        for (int i = 0; i < NP; ++i) {
-                            f2 d2 = wt_score2<KIND_NN>(q, Lp[i], Ap[i], Bp[i], splat(0.f));
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                const int e = 2 * i + h;
-                                const float d = h ? d2.y : d2.x;
-                                const bool better = d < best[e];
-                                second[e] = better ? best[e] : fminf(second[e], d);
-                                best_j[e] = better ? j : best_j[e];
-                                best[e] = better ? d : best[e];
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int e = 0; e < EPT; ++e)
-                        if ((second[e] - best[e] <= tol) && (second[e] < INFINITY)) risky_mask |= 1u << e;
-                }
-                flag_mask = risky_mask & valid_mask;
-#pragma unroll
-                for (int e = 0; e < EPT; ++e) {
-                    if (!(((valid_mask & ~risky_mask) >> e) & 1u)) continue;
-                    px.slot = slot0 + e * slot_step;
-                    const uint32_t idx = __float_as_uint(bnd[best_j[e]].x);
-                    px.r = BRICK ? R : (Bq[e] & 255u); px.g = BRICK ? G : ((Bq[e] >> 8) & 255u); px.b = BRICK ? Bq[e] : (Bq[e] >> 16);
-                    if (!a.preserve) {
-                        uint32_t q = a.pal_rgb[idx];
-                        front_store<MODE>(a.f, px, q & 255u, (q >> 8) & 255u, (q >> 16) & 255u);
-                    } else {
-                        Lab ex = linear_to_oklab_exact(st.decode[px.r], st.decode[px.g], st.decode[px.b]);
-                        Lab o = {ex.l, a.pal_ab[2 * idx], a.pal_ab[2 * idx + 1]};
-                        float r, g, b;
-                        oklab_to_linear_exact(o, r, g, b);
-                        front_store<MODE>(a.f, px, f32_to_srgb8(r, st.encode), f32_to_srgb8(g, st.encode), f32_to_srgb8(b, st.encode));
-                    }
-                }
-                if (flag_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, flag_mask, slot0, slot_step);
-                continue;
-            }
-
-            f2 n0[NP], n1[NP], n2[NP], den[NP], cc[NP];
-#pragma unroll
-            for (int i = 0; i < NP; ++i) {
-                n0[i] = n1[i] = n2[i] = den[i] = splat(0.f);
-                cc[i] = KIND == 0 ? mul2(splat(-c1), fma2(Lp[i], Lp[i], fma2(Ap[i], Ap[i], mul2(Bp[i], Bp[i])))) : splat(0.f);
-            }
-#pragma unroll 2
-            for (uint32_t j = 0; j < direct; ++j) {
-                const float4 q = cand[j];
-#pragma unroll
-                for (int i = 0; i < NP; ++i) {
-                    f2 w = wt_weight2<KIND>(wt_score2<KIND>(q, Lp[i], Ap[i], Bp[i], cc[i]), c1, c0);
-                    n0[i] = fma2(splat(q.x), w, n0[i]);
-                    n1[i] = fma2(splat(q.y), w, n1[i]);
-                    n2[i] = fma2(splat(q.z), w, n2[i]);
-                    den[i] = add2(den[i], w);
-                }
-            }
-            uint32_t risky_mask = 0;
-            if (choose) {
-                const float4* unc = cand + nin;
-#pragma unroll
-                for (int i = 0; i < NP; ++i) {
-                    PairAcc pa = wt_select_any<KIND>(unc, (int)nunc, kp, Lp[i], Ap[i], Bp[i], cc[i], c1, c0, tol);
-                    n0[i] = add2(n0[i], pa.n0); n1[i] = add2(n1[i], pa.n1); n2[i] = add2(n2[i], pa.n2); den[i] = add2(den[i], pa.den);
-                    risky_mask |= pa.risky << (2 * i);
-                }
-            }
-            const float fs = KIND == 0 ? 0.5f / c1 : 1.0f;  // the Gaussian sums ran over -2C p = 2 c1 p
-#pragma unroll
-            for (int i = 0; i < NP; ++i) {
-                const f2 d = den[i];
-                if (!(d.x > 1e-30f) || !(d.x < 1e30f)) risky_mask |= 1u << (2 * i);
-                if (!(d.y > 1e-30f) || !(d.y < 1e30f)) risky_mask |= 2u << (2 * i);
-                const f2 inv = mul2(make_float2(rcp_approx(d.x), rcp_approx(d.y)), splat(fs));
-                f2 oL = a.preserve ? Lp[i] : mul2(n0[i], inv);
-                oL = mul2(oL, splat(a.inv_lum));
-                f2 r2, g2, b2;
-                oklab_to_linear2(oL, mul2(n1[i], inv), mul2(n2[i], inv), r2, g2, b2);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int e = 2 * i + h;
-                    if (!((valid_mask >> e) & 1u)) continue;
-                    px.slot = slot0 + e * slot_step;
-                    px.r = BRICK ? R : (Bq[e] & 255u); px.g = BRICK ? G : ((Bq[e] >> 8) & 255u); px.b = BRICK ? Bq[e] : (Bq[e] >> 16);
-                    // rbf.rs:66-68 palette.contains(&color): identical sRGB <=> identical Oklab triple
-                    if (nhit) {
-                        const uint32_t packed = px.r | (px.g << 8) | (px.b << 16);
-                        bool hit = false;
-#pragma unroll 1
-                        for (uint32_t hh = 0; hh < nhit; ++hh) hit |= (hits[hh] == packed);
-                        if (hit) {
-                            if (MODE != FRONT_IMAGE) front_store<MODE>(a.f, px, px.r, px.g, px.b);
-                            continue;
-                        }
-                    }
-                    if ((risky_mask >> e) & 1u) { flag_mask |= 1u << e; continue; }
-                    front_store<MODE>(a.f, px, f32_to_srgb8(h ? r2.y : r2.x, st.encode), f32_to_srgb8(h ? g2.y : g2.x, st.encode),
-                                      f32_to_srgb8(h ? b2.y : b2.x, st.encode));
-                }
-            }
-            if (flag_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, flag_mask, slot0, slot_step);
+            wt_entries<KIND, MODE, EPT>(a, st, T, cl, cand, cidx, hits);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Palettes of 33 .. 256 colours: two levels. The CTA's eight warp tiles form one CTA tile
+// (16 x 8 x 2 EPT entries, or 256 EPT pixels); the CTA, one palette colour per thread, bounds every
+// colour against the CTA tile's box and drops those that are OUT for the whole CTA tile
+// (LB > U, U >= the k-th smallest UB, found by bisection on block-wide counts). Each warp then
+// classifies the survivors (a few dozen) against its own, smaller box exactly as the kernel above
+// does with a whole small palette -- lanes take survivors lane, lane + 32, ...
+//
+// Dropping is safe for the warp level: an OUT colour is farther than the k-th neighbour of every
+// colour of the CTA tile, so it is neither one of the k nearest nor closer than any of them, and
+// ranks / rival counts taken over the survivors alone equal those over the whole palette. The
+// "moot" rule needs the number of colours with a non-negligible LB; OUT colours are counted with
+// their CTA-level LB (an over-estimate, so the rule only fires less often).
+constexpr int WB_MAX_N = 256;    // one palette colour per thread
+constexpr int WB_MAX_M = 128;    // survivors a warp can classify (4 per lane); beyond: exact kernel
+constexpr int WB_BISECT = 12;
+
+template <int KIND, int MODE, int EPT>
+__global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp_big(const WarpArgs a) {
+    static_assert(EPT % 2 == 0, "entries are processed in pairs");
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr bool BRICK = MODE != FRONT_IMAGE;
+    __shared__ SmemTables st;
+    __shared__ float s_lin[BRICK ? WT_MAX_CS : 1];
+    __shared__ uint8_t s_chv[BRICK ? WT_MAX_CS + 3 : 4];
+    __shared__ __align__(16) float4 s_cand[WT_WARPS][WB_MAX_M];
+    __shared__ __align__(8) float2 s_bnd[WT_WARPS][WB_MAX_M];
+    __shared__ uint32_t s_cidx[WT_WARPS][WB_MAX_M];
+    __shared__ uint32_t s_riv[WT_WARPS][WB_MAX_M];
+    __shared__ __align__(16) float4 s_surv[WB_MAX_N];   // survivors of the CTA level (palette order)
+    __shared__ uint32_t s_sidx[WB_MAX_N];               // their palette indices
+    __shared__ uint32_t s_srgb[WB_MAX_N];               // their packed sRGB
+    __shared__ uint32_t s_hit[FAST_MAX_HITS];
+    __shared__ float s_wbox[WT_WARPS][6];
+    __shared__ uint32_t s_wsrgb[WT_WARPS][6];
+    __shared__ float s_cbox[6];
+    __shared__ uint32_t s_csrgb[6];
+    __shared__ uint32_t s_red[4];      // ubmin, ubmax, lbmin (bit patterns), hit count
+    __shared__ uint32_t s_wcnt[WT_WARPS];
+    __shared__ uint32_t s_tile;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n = a.n, k = a.k;
+    const uint32_t cs = a.f.cs, csm1 = a.f.csm1;
+    const uint32_t begin = (uint32_t)a.f.begin, end = (uint32_t)(a.f.begin + a.f.count);
+    const float c1 = a.c1;
+
+    if (BRICK) {
+#pragma unroll 1
+        for (uint32_t v = tid; v < cs; v += WT_THREADS) s_chv[v] = (uint8_t)(MODE == FRONT_TABLE ? v : hald_channel(v, csm1));
+    }
+    stage_tables(st, a.tables);  // ends with __syncthreads()
+    if (BRICK) {
+#pragma unroll 1
+        for (uint32_t v = tid; v < cs; v += WT_THREADS) s_lin[v] = st.decode[s_chv[v]];
+        __syncthreads();
+    }
+    WtShared sh;
+    sh.st = &st; sh.lin = s_lin; sh.chv = s_chv;
+
+    // this thread's palette colour (CTA level)
+    const bool owner = tid < n;
+    const float4 p = owner ? a.pal[tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t prgb = owner ? (a.pal_rgb[tid] & 0xffffffu) : 0u;
+    float4* cand = s_cand[warp];
+    float2* bnd = s_bnd[warp];
+    uint32_t* cidx = s_cidx[warp];
+    uint32_t* riv = s_riv[warp];
+
+    for (;;) {
+        __syncthreads();  // the previous CTA tile's shared state is no longer read
+        if (tid == 0) s_tile = atomicAdd(a.tile_counter, 1u);
+        if (tid < 4) s_red[tid] = tid == 1 ? 0u : (tid == 3 ? 0u : 0x7f800000u);
+        __syncthreads();
+        const uint32_t ct = s_tile;
+        if (ct >= a.ntiles) break;
+
+        // ---- 1. every warp converts its tile; boxes of the eight tiles -> CTA box ------------------
+        WtTile<EPT> T;
+        if (BRICK) {
+            uint32_t ir, ig, ib, rest;
+            wt_divmod(ct, a.tiles_r, a.inv_tiles_r, rest, ir);
+            wt_divmod(rest, a.tiles_g, a.inv_tiles_g, ib, ig);
+            const uint32_t R0 = ir * 16u, G0 = ig * 8u, B0 = a.b_lo + ib * (2u * EPT);
+            const uint32_t first = (B0 * cs + G0) * cs + R0;
+            const uint32_t last = (min(B0 + 2u * EPT - 1, csm1) * cs + min(G0 + 7u, csm1)) * cs + min(R0 + 15u, csm1);
+            if (B0 > csm1 || last < begin || first >= end) continue;  // uniform over the CTA
+            wt_convert_brick<EPT>(a, sh, lane, R0 + 8u * (warp & 1u), G0 + 4u * ((warp >> 1) & 1u), B0 + (uint32_t)EPT * (warp >> 2), T);
+        } else {
+            // a warp tile past the end of the image repeats the CTA tile's first pixels
+            uint32_t base = ct * (256u * EPT) + warp * (32u * EPT);
+            if (base >= end) base = ct * (256u * EPT);
+            wt_convert_image<EPT>(a, sh, lane, base, T);
+            if (ct * (256u * EPT) + warp * (32u * EPT) >= end) T.valid_mask = 0;
+        }
+        wt_box<EPT>(T);
+        if (lane < 6) {
+            s_wbox[warp][lane] = lane < 3 ? T.lo[lane] : T.hi[lane - 3];
+            s_wsrgb[warp][lane] = lane < 3 ? T.blo[lane] : T.bhi[lane - 3];
+        }
+        const bool cta_any = __syncthreads_or(T.valid_mask != 0);
+        if (!cta_any) continue;
+        if (tid < 6) {
+            float v = s_wbox[0][tid];
+            uint32_t u = s_wsrgb[0][tid];
+#pragma unroll
+            for (int w = 1; w < WT_WARPS; ++w) {
+                v = tid < 3 ? fminf(v, s_wbox[w][tid]) : fmaxf(v, s_wbox[w][tid]);
+                u = tid < 3 ? min(u, s_wsrgb[w][tid]) : max(u, s_wsrgb[w][tid]);
+            }
+            s_cbox[tid] = v;
+            s_csrgb[tid] = u;
+        }
+        __syncthreads();
+
+        // ---- 2. CTA level: bounds of every colour against the CTA box, U, survivors ----------------
+        float clo[3] = {s_cbox[0], s_cbox[1], s_cbox[2]}, chi[3] = {s_cbox[3], s_cbox[4], s_cbox[5]};
+        float lbc, ubc;
+        bounds_of(p, clo, chi, lbc, ubc);
+        if (!owner) { lbc = INFINITY; ubc = INFINITY; }
+        {
+            const uint32_t wmin = __reduce_min_sync(FULL, __float_as_uint(ubc));
+            const uint32_t wmax = __reduce_max_sync(FULL, owner ? __float_as_uint(ubc) : 0u);
+            const uint32_t lmin = __reduce_min_sync(FULL, __float_as_uint(lbc));
+            if (lane == 0) { atomicMin(&s_red[0], wmin); atomicMax(&s_red[1], wmax); atomicMin(&s_red[2], lmin); }
+        }
+        if (KIND != KIND_NN) {
+            const uint32_t qr = prgb & 255u, qg = (prgb >> 8) & 255u, qb = prgb >> 16;
+            if (owner && qr >= s_csrgb[0] && qr <= s_csrgb[3] && qg >= s_csrgb[1] && qg <= s_csrgb[4] && qb >= s_csrgb[2] && qb <= s_csrgb[5]) {
+                const uint32_t h = atomicAdd(&s_red[3], 1u);
+                if (h < FAST_MAX_HITS) s_hit[h] = prgb;
+            }
+        }
+        __syncthreads();
+        const float ubmin_c = __uint_as_float(s_red[0]), ubmax_c = __uint_as_float(s_red[1]);
+        const uint32_t nhit_c = s_red[3];
+        float U = ubmax_c;
+        if (k != 0) {
+            // smallest of WB_BISECT probes v with #{UB <= v} >= k: an upper bound of the k-th smallest UB
+            float lo_v = ubmin_c, hi_v = ubmax_c;
+#pragma unroll 1
+            for (int it = 0; it < WB_BISECT; ++it) {
+                const float mid = 0.5f * (lo_v + hi_v);
+                const uint32_t c = (uint32_t)__syncthreads_count(owner && ubc <= mid);
+                if (c >= k) hi_v = mid; else lo_v = mid;
+            }
+            U = hi_v;
+        }
+        const bool surv = owner && lbc <= U;
+        uint32_t out_nonnegl = 0;
+        if (KIND != KIND_NN && k != 0) {
+            const float lg_c = KIND == 1 ? lg2_approx(ubmin_c) : 0.f;
+            out_nonnegl = (uint32_t)__syncthreads_count(owner && !surv && !negligible_at<KIND>(lbc, ubmin_c, lg_c, c1));
+        }
+        {
+            const uint32_t bs = __ballot_sync(FULL, surv);
+            if (lane == 0) s_wcnt[warp] = __popc(bs);
+            __syncthreads();
+            uint32_t pre = 0;
+#pragma unroll
+            for (int w = 0; w < WT_WARPS; ++w) pre += ((uint32_t)w < warp) ? s_wcnt[w] : 0u;
+            if (surv) {
+                const uint32_t pos = pre + __popc(bs & ((1u << lane) - 1u));
+                s_surv[pos] = p;
+                s_sidx[pos] = tid;
+            }
+        }
+        __syncthreads();
+        uint32_t m = 0;
+#pragma unroll
+        for (int w = 0; w < WT_WARPS; ++w) m += s_wcnt[w];
+
+        // ---- 3. warp level: classify the m survivors against the warp's own box -------------------
+        if (!__any_sync(FULL, T.valid_mask != 0)) continue;  // nothing to produce (the next barrier is at the loop top)
+        WtClass cl;
+        cl.force_exact = m > (uint32_t)WB_MAX_M;
+        cl.nhit = nhit_c;
+        cl.take_all = (k == 0);
+        cl.nin = cl.nunc = cl.nin_all = cl.nunc_all = 0;
+        cl.lbmin = cl.ubmin = INFINITY;
+        cl.ubmax_unc = 0.f;
+        if (!cl.force_exact) {
+            const uint32_t nslots = (m + 31u) >> 5;
+            // bounds against the warp box; U_k keys carry the survivor number in 7 low mantissa bits
+            float lbm = INFINITY, ubm = INFINITY;
+#pragma unroll 1
+            for (uint32_t s = 0; s < nslots; ++s) {
+                const uint32_t j = lane + 32u * s;
+                if (j < m) {
+                    float lbv, ubv;
+                    bounds_of(s_surv[j], T.lo, T.hi, lbv, ubv);
+                    const uint32_t ukey = ((__float_as_uint(ubv) + 127u) & ~127u) | j;
+                    bnd[j] = make_float2(lbv, __uint_as_float(ukey));
+                    lbm = fminf(lbm, lbv);
+                    ubm = fminf(ubm, ubv);
+                }
+            }
+            cl.lbmin = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(lbm)));
+            cl.ubmin = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(ubm)));
+            __syncwarp();
+            const float lg_ubmin = KIND == 1 ? lg2_approx(cl.ubmin) : 0.f;
+            if (k != 0 && KIND != KIND_NN) {
+                uint32_t nn_cnt = 0;
+#pragma unroll 1
+                for (uint32_t s = 0; s < nslots; ++s) {
+                    const uint32_t j = lane + 32u * s;
+                    const bool nonnegl = j < m && !negligible_at<KIND>(bnd[j].x, cl.ubmin, lg_ubmin, c1);
+                    nn_cnt += __popc(__ballot_sync(FULL, nonnegl));
+                }
+                cl.take_all = nn_cnt + out_nonnegl < k;
+            }
+            float uk = INFINITY;
+            if (!cl.take_all) {
+#pragma unroll 1
+                for (uint32_t s = 0; s < nslots; ++s) {
+                    const uint32_t j = lane + 32u * s;
+                    const float2 me = j < m ? bnd[j] : make_float2(INFINITY, INFINITY);
+                    const uint32_t ukey = __float_as_uint(me.y);
+                    const float ubr = __uint_as_float(ukey | 127u);
+                    uint32_t rank_u = 0, rivals = 0;
+#pragma unroll 4
+                    for (uint32_t q = 0; q < m; ++q) {
+                        const float2 bq = bnd[q];
+                        rank_u += (__float_as_uint(bq.y) < ukey) ? 1u : 0u;
+                        rivals += (bq.x <= ubr) ? 1u : 0u;
+                    }
+                    if (j < m) riv[j] = rivals;
+                    const uint32_t bu = __ballot_sync(FULL, j < m && rank_u == k - 1);
+                    if (bu) uk = __uint_as_float(__shfl_sync(FULL, ukey, __ffs(bu) - 1) | 127u);
+                }
+            }
+            __syncwarp();
+            uint32_t ubmax_bits = 0;
+#pragma unroll 1
+            for (uint32_t s = 0; s < nslots; ++s) {
+                const uint32_t j = lane + 32u * s;
+                bool is_in = j < m, is_unc = false, negl = false;
+                float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
+                float lbv = INFINITY, ubr = INFINITY;
+                if (j < m) {
+                    pj = s_surv[j];
+                    const float2 me = bnd[j];
+                    lbv = me.x;
+                    ubr = __uint_as_float(__float_as_uint(me.y) | 127u);
+                    if (KIND != KIND_NN) negl = negligible_at<KIND>(lbv, cl.ubmin, lg_ubmin, c1);
+                    if (!cl.take_all) {
+                        const bool near = lbv <= uk;
+                        is_in = near && riv[j] <= k;
+                        is_unc = near && !is_in;
+                    }
+                }
+                cl.nin_all += __popc(__ballot_sync(FULL, is_in));
+                cl.nunc_all += __popc(__ballot_sync(FULL, is_unc));
+                const bool list_in = is_in && !negl, list_unc = is_unc && !negl;
+                const uint32_t bin = __ballot_sync(FULL, list_in), bun = __ballot_sync(FULL, list_unc), lt = (1u << lane) - 1u;
+                // IN colours fill the list from the front, UNCERTAIN ones from the back (reversed below)
+                const float4 q = wt_list_entry<KIND>(pj, fmaf(pj.x, pj.x, fmaf(pj.y, pj.y, pj.z * pj.z)), c1, cl.lbmin);
+                if (list_in) { const uint32_t pos = cl.nin + __popc(bin & lt); cand[pos] = q; cidx[pos] = s_sidx[j]; }
+                if (list_unc) { const uint32_t pos = WB_MAX_M - 1u - (cl.nunc + __popc(bun & lt)); cand[pos] = q; cidx[pos] = s_sidx[j]; }
+                if (list_unc) ubmax_bits = max(ubmax_bits, __float_as_uint(ubr));
+                cl.nin += __popc(bin);
+                cl.nunc += __popc(bun);
+            }
+            cl.ubmax_unc = __uint_as_float(__reduce_max_sync(FULL, ubmax_bits));
+            __syncwarp();
+            // move the UNCERTAIN block right behind the IN block (nin + nunc <= m <= WB_MAX_M: the
+            // source [M - nunc, M) never lies below the destination; copy low to high in chunks)
+            {
+                const uint32_t src0 = WB_MAX_M - cl.nunc, dst0 = cl.nin;
+                if (src0 != dst0) {
+#pragma unroll 1
+                    for (uint32_t i0 = 0; i0 < cl.nunc; i0 += 32u) {
+                        const uint32_t i = i0 + lane;
+                        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                        uint32_t ci = 0;
+                        if (i < cl.nunc) { q = cand[src0 + i]; ci = cidx[src0 + i]; }
+                        __syncwarp();
+                        if (i < cl.nunc) { cand[dst0 + i] = q; cidx[dst0 + i] = ci; }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        if (a.stats && lane == 0) {
+            atomicAdd(&a.stats[min(cl.nunc, 63u)], 1u);
+            atomicAdd(&a.stats[64 + min(cl.nin, 63u)], 1u);
+        }
+        // ---- 4. per entry ----------------------------------------------------------------------
+        wt_entries<KIND, MODE, EPT>(a, st, T, cl, cand, cidx, s_hit);
     }
 }
 
