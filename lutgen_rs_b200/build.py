@@ -5,6 +5,9 @@
 The shared object lands next to this file so it travels to the GPU box with the
 repository snapshot. cudart is linked statically: the library needs nothing but
 the NVIDIA driver at run time (no torch, no toolkit).
+
+Two translation units: api.cu (everything) and blur.cu (the GaussianBlurRemapper kernels, compiled
+with --fmad=false: see csrc/blur_launch.h).
 """
 import os
 import shutil
@@ -14,15 +17,18 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "liblutgen_cuda.so")
-SOURCES = [os.path.join(CSRC, "api.cu")]
+OBJ_DIR = os.path.join(HERE, "_obj")
+# (source, extra nvcc flags)
+UNITS = [("api.cu", []), ("blur.cu", ["--fmad=false"])]
+SOURCES = [os.path.join(CSRC, u) for u, _ in UNITS]
 
-NVCC_FLAGS = [
+COMMON_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2",
-    "-cudart", "static",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2",
     "--expt-relaxed-constexpr",
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static"]
 
 
 def _deps():
@@ -47,11 +53,20 @@ def build(force=False, verbose=False, extra=()):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found; cannot build liblutgen_cuda.so")
-    cmd = [nvcc, *NVCC_FLAGS, *extra, "-ccbin", "/usr/bin/g++", "-o", OUT, *SOURCES]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), file=sys.stderr)
-    subprocess.check_call(cmd)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    procs, objs = [], []
+    for unit, flags in UNITS:
+        obj = os.path.join(OBJ_DIR, unit.replace(".cu", ".o"))
+        cmd = [nvcc, *COMMON_FLAGS, *flags, *extra, "-ccbin", "/usr/bin/g++", "-c", "-o", obj, os.path.join(CSRC, unit)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), file=sys.stderr)
+        procs.append((cmd, subprocess.Popen(cmd)))
+        objs.append(obj)
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
+    subprocess.check_call([nvcc, *LINK_FLAGS, "-ccbin", "/usr/bin/g++", "-o", OUT, *objs])
     return OUT
 
 

@@ -18,7 +18,7 @@
 
 #include "../../include/lutgen_cuda.h"
 #include "kernels_apply.cuh"
-#include "kernels_blur.cuh"
+#include "blur_launch.h"
 #include "kernels_exact.cuh"
 #include "kernels_fast.cuh"
 #include "kernels_warp.cuh"
@@ -524,36 +524,53 @@ int ensure_blur_volume(const lutgen_remapper* r, uint32_t level, cudaStream_t s)
         unsigned rows = size * size;
         unsigned grid_nn = blocks_for(rows, BLUR_ROW_WARPS);
         if (grid_nn > (unsigned)g.sm_count * 8u) grid_nn = (unsigned)g.sm_count * 8u;
-        k_blur_nn_volume<<<grid_nn, BLUR_ROW_WARPS * 32, 0, s>>>(a, size, ch, r->blur_chan, r->blur_pal3, r->blur_out3, r->n, lum, threshold_sq, g.tables);
-        LAUNCH_CHECK();
         static bool attr_done = false;
         if (!attr_done) {
-            CU_TRY(cudaFuncSetAttribute(k_blur_inner, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            CU_TRY(cudaFuncSetAttribute(k_blur_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            CU_TRY(blur_set_attributes());
             attr_done = true;
         }
-        const int klen = r->blur_klen;
-        // pass 1: B axis (innermost)
-        const uint32_t row_len = size * ch;
-        uint32_t lines = 12288u / row_len;
-        if (lines < 1) lines = 1;
-        size_t smem1 = ((size_t)klen + (size_t)lines * row_len) * sizeof(float);
-        k_blur_inner<<<blocks_for(rows, lines), 256, smem1, s>>>(a, b, size, ch, lines, r->blur_kernel, klen);
+        const int stage_pal = (size_t)r->n * 12 <= 64 * 1024;
+        const size_t smem_nn = 1024 + (stage_pal ? (size_t)r->n * 12 : 0);
+        blur_launch_nn_volume(grid_nn, smem_nn, s, a, size, ch, r->blur_chan, r->blur_pal3, r->blur_out3, r->n, lum, threshold_sq, g.tables, stage_pal);
         LAUNCH_CHECK();
-        // pass 2: R axis (stride size^2 cells); pass 3: G axis (stride size cells)
-        uint32_t cols = 12288u / size;
-        if (cols > 32) cols = 32;
-        if (cols < 1) cols = 1;
-        size_t smem2 = ((size_t)klen + (size_t)size * cols) * sizeof(float);
-        {
-            uint32_t inner = size * size * ch, groups = (inner + cols - 1) / cols;
-            k_blur_strided<<<groups, 256, smem2, s>>>(b, a, size, inner, groups, 0u, inner, cols, r->blur_kernel, klen);
+        const int klen = r->blur_klen;
+        // columns per CTA: an even number that keeps tile + taps within ~48 KB (several CTAs per SM),
+        // but never fewer than one cell's channels; the B pass takes whole rows (ch columns each)
+        auto launch_axis = [&](const float* src, float* dst, BlurAxis P, uint32_t outers) -> int {
+            P.groups = (P.total_cols + P.cols - 1) / P.cols;
+            size_t smem = ((size_t)P.size * P.pitch + (size_t)klen + 4) * sizeof(float);
+            if (smem > 200 * 1024) return fail(LUTGEN_ERR_UNSUPPORTED, "blur: %zu bytes of shared memory per tile (level %u, radius %g)", smem, level, r->d.param);
+            blur_launch_axis(P.groups * outers, smem, s, src, dst, P, r->blur_kernel, klen);
             LAUNCH_CHECK();
+            return LUTGEN_OK;
+        };
+        uint32_t want = 12288u / size;
+        if (want > 32) want = 32;
+        if (want < 2) want = 2;
+        {   // pass 1: B axis (innermost)
+            BlurAxis P{};
+            uint32_t lines = want / ch;
+            if (lines < 1) lines = 1;
+            if ((lines * ch) & 1u) ++lines;  // an even number of columns per full tile
+            P.size = size; P.pstride = ch; P.cols = lines * ch;
+            P.pitch = P.cols + ((2 * ch + 32 - (P.cols & 31u)) & 31u);  // even, = 2 ch mod 32: staging conflicts stay 2-way
+            P.cpl = ch; P.run_stride = size * ch; P.total_cols = rows * ch; P.outer_stride = 0;
+            int rc = launch_axis(a, b, P, 1);
+            if (rc) return rc;
         }
-        {
-            uint32_t inner = size * ch, groups = (inner + cols - 1) / cols;
-            k_blur_strided<<<groups * size, 256, smem2, s>>>(a, b, size, inner, groups, size * size * ch, inner, cols, r->blur_kernel, klen);
-            LAUNCH_CHECK();
+        {   // pass 2: R axis (stride size^2 cells)
+            BlurAxis P{};
+            P.size = size; P.pstride = size * size * ch; P.cols = want & ~1u; P.pitch = P.cols;
+            P.cpl = 0; P.run_stride = 0; P.total_cols = size * size * ch; P.outer_stride = 0;
+            int rc = launch_axis(b, a, P, 1);
+            if (rc) return rc;
+        }
+        {   // pass 3: G axis (stride size cells), one slab per r
+            BlurAxis P{};
+            P.size = size; P.pstride = size * ch; P.cols = want & ~1u; P.pitch = P.cols;
+            P.cpl = 0; P.run_stride = 0; P.total_cols = size * ch; P.outer_stride = size * size * ch;
+            int rc = launch_axis(a, b, P, size);
+            if (rc) return rc;
         }
         r->blur_result = 1;
         r->blur_level = (int)level;
@@ -570,7 +587,14 @@ int launch_blur_lut(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
     if (rc != LUTGEN_OK) return rc;
     if (f.count == 0) return LUTGEN_OK;
     const uint32_t ch = r->d.preserve ? 2u : 3u;
-    k_blur_to_lut<<<blocks_for(f.count, 256), 256, 0, s>>>(r->blur_vol[r->blur_result], f.cs, ch, r->blur_chan, f.out, f.begin, f.count, g.tables);
+    {
+        const uint32_t size = f.cs;
+        const unsigned long long plane = (unsigned long long)size * size;
+        const uint32_t b_first = (uint32_t)(f.begin / plane) / BLUR_TB * BLUR_TB, b_last = (uint32_t)((f.begin + f.count - 1) / plane);
+        const uint32_t tiles_r = (size + BLUR_TR - 1) / BLUR_TR, tiles_b = (b_last - b_first) / BLUR_TB + 1;
+        blur_launch_to_lut(tiles_r * size * tiles_b, s, r->blur_vol[r->blur_result], size, ch, r->blur_chan, f.out, f.begin, f.count, b_first,
+                                                                tiles_r, g.tables);
+    }
     LAUNCH_CHECK();
     return LUTGEN_OK;
 }
@@ -998,7 +1022,7 @@ int lutgen_cuda_remapper_create(const lutgen_remapper_desc* desc, lutgen_remappe
         const float lum = (float)desc->lum_factor, radius = (float)desc->param;
         CU_TRY_R(cudaMalloc((void**)&r->blur_pal3, sizeof(float) * 3 * na));
         CU_TRY_R(cudaMalloc((void**)&r->blur_out3, sizeof(float) * 3 * na));
-        k_blur_palette<<<blocks_for(n, 128), 128, 0, g.stream>>>(r->pal_rgb4, r->n, lum, g.tables->decode, r->blur_pal3, r->blur_out3);
+        blur_launch_palette(blocks_for(n, 128), g.stream, r->pal_rgb4, r->n, lum, g.tables->decode, r->blur_pal3, r->blur_out3);
         g_launches.fetch_add(1);
         CU_TRY_R(cudaGetLastError());
         float h3 = ceilf(radius * 3.0f);

@@ -1,0 +1,31 @@
+// blur.cu -- GaussianBlurRemapper kernels, compiled with --fmad=false (see blur_launch.h).
+#include "blur_launch.h"
+#include "kernels_blur.cuh"
+
+namespace lutgen {
+
+cudaError_t blur_set_attributes() {
+    cudaError_t e = cudaFuncSetAttribute(k_blur_nn_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_blur_axis, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
+void blur_launch_palette(unsigned grid, cudaStream_t s, const uint8_t* pal_rgb4, uint32_t n, float lum, const float* decode, float* pal3, float* out3) {
+    k_blur_palette<<<grid, 128, 0, s>>>(pal_rgb4, n, lum, decode, pal3, out3);
+}
+
+void blur_launch_nn_volume(unsigned grid, size_t smem, cudaStream_t s, float* colors, uint32_t size, uint32_t ch, const uint8_t* chan, const float* pal3,
+                           const float* out3, uint32_t n, float lum, float threshold_sq, const ColorTables* tables, int stage_palette) {
+    k_blur_nn_volume<<<grid, BLUR_ROW_WARPS * 32, smem, s>>>(colors, size, ch, chan, pal3, out3, n, lum, threshold_sq, tables, stage_palette, 1.0f);
+}
+
+void blur_launch_axis(unsigned grid, size_t smem, cudaStream_t s, const float* src, float* dst, const BlurAxis& P, const float* kernel, int klen) {
+    k_blur_axis<<<grid, 256, smem, s>>>(src, dst, P, kernel, klen, 1.0f);
+}
+
+void blur_launch_to_lut(unsigned grid, cudaStream_t s, const float* colors, uint32_t size, uint32_t ch, const uint8_t* chan, uint8_t* out_rgb,
+                        unsigned long long begin, unsigned long long count, uint32_t b_first, uint32_t tiles_r, const ColorTables* tables) {
+    k_blur_to_lut<<<grid, 256, 0, s>>>(colors, size, ch, chan, out_rgb, begin, count, b_first, tiles_r, tables);
+}
+
+}  // namespace lutgen

@@ -155,6 +155,17 @@ __device__ __forceinline__ uint32_t f32_to_srgb8(float f, const uint32_t* __rest
     return (bias + scale * t) >> 16;
 }
 
+// Shared staging of the colour tables for kernels whose lanes index them divergently.
+struct SmemTables {
+    float decode[256];
+    uint32_t encode[104];
+};
+__device__ __forceinline__ void stage_tables(SmemTables& s, const ColorTables* __restrict__ t) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s.decode[i] = t->decode[i];
+    for (int i = threadIdx.x; i < 104; i += blockDim.x) s.encode[i] = t->encode[i];
+    __syncthreads();
+}
+
 // identity::generate's channel value for grid coordinate v of a level-L CLUT:
 // v * 255 / (cs - 1), integer floor (crates/lib/src/identity.rs:16-20).
 __device__ __forceinline__ uint32_t hald_channel(uint32_t v, uint32_t cs_minus_1) { return v * 255u / cs_minus_1; }

@@ -8,7 +8,8 @@
 // CPU cache; the result of a pass does not depend on the layout, so here each pass reads strided
 // lines through a shared-memory tile instead and the volume never moves.
 #pragma once
-#include "kernels_exact.cuh"
+#include "blur_launch.h"
+#include "color.cuh"
 
 namespace lutgen {
 
@@ -32,94 +33,123 @@ __global__ void k_blur_palette(const uint8_t* __restrict__ pal_rgb4, uint32_t n,
 
 // Nearest-neighbour volume with the reference's hint rule (find_nearest_with_hint,
 // gaussian_blur.rs:57-80; row loop of par_generate_lut_inner, l.320-358: the hint restarts at 0 for
-// every (r, g) row and then walks b). One warp per row, 256 cells at a time:
-//   parallel part: each lane converts its cells and finds (M, I) = (smallest distance, first index
-//                  reaching it) over the whole palette;
-//   serial part  : lane 0 replays the hint chain. With hint h the reference returns h when
-//                  d(h) < threshold or d(h) == M, else I -- one distance per cell whose hint differs
-//                  from I, nothing otherwise.
+// every (r, g) row and then walks b). With hint h the reference returns
+//     h                         if d(h) < threshold            (early exit, l.61-63)
+//     argmin, h winning ties    otherwise                      (strict `<` scan from best = h)
+// Let M be the smallest distance of the cell, I the first palette index reaching it, and
+// S = {t : d(t) < threshold or d(t) == M}. Then the result is h if h is in S, else I -- and S = {I}
+// unless two colours tie at M or two colours lie within the (tiny) threshold. So the hint matters
+// only in AMBIGUOUS cells (second-smallest distance == M or < threshold); everywhere else the
+// result is I whatever came before. One warp per row, 64 cells at a time (two per lane, the palette
+// scan in packed f32x2): all cells are resolved in parallel and only ambiguous ones -- rare --
+// replay the chain.
 // `chan[i]` = (i as f32 * scale).round() as u8 (l.206-210), filled on the host.
-constexpr int BLUR_ROW_WARPS = 8;
-constexpr int BLUR_SEG = 256;
+
+__device__ __forceinline__ float2 blur_sub2(float2 a, float b) { return __ffma2_rn(make_float2(b, b), make_float2(-1.0f, -1.0f), a); }  // a - b, exact product
+// a + b with ONE rounding, as a packed instruction ptxas cannot fuse with the multiply that produced
+// b: `one` is 1.0f passed at run time (a * 1.0 is exact). ptxas contracts mul.rn.f32x2 + add.rn.f32x2
+// into FFMA2 -- even under --fmad=false, unlike the scalar .rn forms -- and the reference rounds the
+// product before it adds.
+__device__ __forceinline__ float2 blur_add2(float2 a, float2 b, float one) { return __ffma2_rn(a, make_float2(one, one), b); }
 
 __global__ void __launch_bounds__(BLUR_ROW_WARPS * 32) k_blur_nn_volume(float* __restrict__ colors, uint32_t size, uint32_t ch, const uint8_t* __restrict__ chan,
                                                                          const float* __restrict__ pal3, const float* __restrict__ out3, uint32_t n,
-                                                                         float lum, float threshold_sq, const ColorTables* __restrict__ tables) {
-    __shared__ float s_decode[256];
-    __shared__ float s_col[BLUR_ROW_WARPS][3][BLUR_SEG];
-    __shared__ float s_m[BLUR_ROW_WARPS][BLUR_SEG];
-    __shared__ uint32_t s_i[BLUR_ROW_WARPS][BLUR_SEG];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_decode[i] = tables->decode[i];
+                                                                         float lum, float threshold_sq, const ColorTables* __restrict__ tables,
+                                                                         int stage_palette, float one) {
+    extern __shared__ float s_blur_nn[];   // decode[256] | palette 3n (when it fits)
+    float* s_decode = s_blur_nn;
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_decode[i] = tables->decode[i];
+    if (stage_palette)
+        for (uint32_t i = threadIdx.x; i < 3 * n; i += blockDim.x) s_blur_nn[256 + i] = pal3[i];
+    const float* __restrict__ s_pal = stage_palette ? s_blur_nn + 256 : pal3;
     __syncthreads();
+    const uint32_t FULL = 0xffffffffu;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rows = size * size;
     for (uint32_t row = blockIdx.x * BLUR_ROW_WARPS + warp; row < rows; row += gridDim.x * BLUR_ROW_WARPS) {
         const uint32_t r = row / size, g = row % size;
         const float lr = s_decode[chan[r]], lg = s_decode[chan[g]];
-        uint32_t hint = 0;
-        for (uint32_t b0 = 0; b0 < size; b0 += BLUR_SEG) {
-            const uint32_t seg = min((uint32_t)BLUR_SEG, size - b0);
-            for (uint32_t j = lane; j < seg; j += 32) {
-                Lab o = linear_to_oklab_exact(lr, lg, s_decode[chan[b0 + j]]);
-                float c0 = __fmul_rn(o.l, lum), c1 = o.a, c2 = o.b;
-                float best = INFINITY;
-                uint32_t bi = 0;
-                for (uint32_t t = 0; t < n; ++t) {
-                    float d = blur_sq_dist(c0, c1, c2, pal3 + 3 * t);
-                    if (d < best) { best = d; bi = t; }
-                }
-                s_col[warp][0][j] = c0; s_col[warp][1][j] = c1; s_col[warp][2][j] = c2;
-                s_m[warp][j] = best; s_i[warp][j] = bi;
+        uint32_t hint = 0;  // result of the previous cell
+        for (uint32_t b0 = 0; b0 < size; b0 += 64) {
+            // cells b0 + lane (x) and b0 + 32 + lane (y); past the end they repeat the last cell
+            const uint32_t bx = min(b0 + lane, size - 1), by = min(b0 + 32 + lane, size - 1);
+            Lab ox = linear_to_oklab_exact(lr, lg, s_decode[chan[bx]]), oy = linear_to_oklab_exact(lr, lg, s_decode[chan[by]]);
+            const float2 c0 = make_float2(__fmul_rn(ox.l, lum), __fmul_rn(oy.l, lum)), c1 = make_float2(ox.a, oy.a), c2 = make_float2(ox.b, oy.b);
+            float2 best = make_float2(INFINITY, INFINITY), second = best;
+            uint32_t ix = 0, iy = 0;
+#pragma unroll 2
+            for (uint32_t t = 0; t < n; ++t) {
+                // sq_dist, gaussian_blur.rs:504-510: (dl*dl + da*da) + db*db, every operation rounded
+                const float2 dl = blur_sub2(c0, s_pal[3 * t]), da = blur_sub2(c1, s_pal[3 * t + 1]), db = blur_sub2(c2, s_pal[3 * t + 2]);
+                const float2 d = blur_add2(blur_add2(__fmul2_rn(dl, dl), __fmul2_rn(da, da), one), __fmul2_rn(db, db), one);
+                const bool bx_ = d.x < best.x, by_ = d.y < best.y;
+                second.x = bx_ ? best.x : fminf(second.x, d.x);
+                second.y = by_ ? best.y : fminf(second.y, d.y);
+                best.x = bx_ ? d.x : best.x;
+                best.y = by_ ? d.y : best.y;
+                ix = bx_ ? t : ix;
+                iy = by_ ? t : iy;
             }
-            __syncwarp();
-            if (lane == 0) {
-                for (uint32_t j = 0; j < seg; ++j) {
-                    uint32_t I = s_i[warp][j];
-                    if (hint != I) {
-                        float dh = blur_sq_dist(s_col[warp][0][j], s_col[warp][1][j], s_col[warp][2][j], pal3 + 3 * hint);
-                        if (!(dh < threshold_sq || dh == s_m[warp][j])) hint = I;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const uint32_t cell = b0 + 32u * half + lane;
+                if (b0 + 32u * half >= size) break;  // uniform
+                const float M = half ? best.y : best.x, S2 = half ? second.y : second.x;
+                const uint32_t I = half ? iy : ix;
+                const bool in_row = cell < size;
+                const bool amb = in_row && (S2 == M || S2 < threshold_sq);
+                uint32_t res = I;
+                uint32_t am = __ballot_sync(FULL, amb);
+                while (am) {
+                    const uint32_t j = __ffs(am) - 1;
+                    am &= am - 1;
+                    // the hint that reaches cell j: the previous group's last result, or cell j-1's
+                    const uint32_t prev = __shfl_sync(FULL, res, j == 0 ? 0 : j - 1);
+                    const uint32_t h = j == 0 ? hint : prev;
+                    if (lane == j && h != I) {
+                        const float cc0 = half ? c0.y : c0.x, cc1 = half ? c1.y : c1.x, cc2 = half ? c2.y : c2.x;
+                        const float dh = blur_sq_dist(cc0, cc1, cc2, s_pal + 3 * h);
+                        if (dh < threshold_sq || dh == M) res = h;
                     }
-                    s_i[warp][j] = hint;
+                }
+                const uint32_t valid = min(size - (b0 + 32u * half), 32u);
+                hint = __shfl_sync(FULL, res, valid - 1);
+                if (in_row) {
+                    const float* t = out3 + 3 * res;
+                    float* dst = colors + ((size_t)row * size + cell) * ch;
+                    if (ch == 2) { dst[0] = t[1]; dst[1] = t[2]; }
+                    else { dst[0] = t[0]; dst[1] = t[1]; dst[2] = t[2]; }
                 }
             }
-            hint = __shfl_sync(0xffffffffu, hint, 0);
-            __syncwarp();
-            for (uint32_t j = lane; j < seg; j += 32) {
-                const float* t = out3 + 3 * s_i[warp][j];
-                float* dst = colors + ((size_t)row * size + b0 + j) * ch;
-                if (ch == 2) { dst[0] = t[1]; dst[1] = t[2]; }
-                else { dst[0] = t[0]; dst[1] = t[1]; dst[2] = t[2]; }
-            }
-            __syncwarp();
         }
     }
 }
 
 // blur_inner / par_blur_inner, gaussian_blur.rs:100-162: out[p] = sum_k kw[k] * in[clamp(p+k-half)],
-// accumulated in tap order with a rounded multiply and a rounded add per tap.
+// accumulated in tap order with a rounded multiply and a rounded add per tap (no FMA: blur_add2).
 //
-// One thread produces BLUR_R consecutive outputs p0 .. p0+R-1 of a line. Output q's tap k reads
-// input position clamp(p0 + q + k - half); stepping j = q + k, every output needs the SAME input
-// in[clamp(p0 + j - half)] at step j (with its own weight kw[j - q]), and each output still meets its
-// taps in increasing k. So one shared-memory load and one clamp serve R outputs, and the sums are
-// bit-identical to the one-output-at-a-time loop.
+// One thread produces 4 consecutive positions p0 .. p0+3 of TWO neighbouring columns, as float2
+// accumulators (FMUL2 + FADD2: the two columns share the weight, which is the scalar operand).
+// Output q's tap k reads position clamp(p0 + q + k - half); stepping j = q + k, every output needs
+// the SAME input row clamp(p0 + j - half) at step j (with its own weight kw[j - q]), and each
+// output still meets its taps in increasing k. So one 8-byte shared-memory load and one clamp serve
+// 8 outputs, and the sums are bit-identical to the one-output-at-a-time loop.
 constexpr int BLUR_R = 4;
 
-__device__ __forceinline__ void blur_taps4(const float* __restrict__ line, uint32_t line_stride, int pos0, int maxpos,
-                                           const float* __restrict__ kw, int klen, int half, float (&out)[BLUR_R]) {
-    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+__device__ __forceinline__ void blur_taps4x2(const float* __restrict__ colp, uint32_t pitch, int pos0, int maxpos,
+                                             const float* __restrict__ kw, int klen, int half, float one, float2 (&out)[BLUR_R]) {
+    float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
     // weights live in four registers named by j mod 4 (ra = kw[j] for j = 0 mod 4, ...): no shifting
     float ra = 0.0f, rb = 0.0f, rc = 0.0f, rd = 0.0f;
     const int steps = klen + BLUR_R - 1;
-    // input at step j; away from the line's ends the clamp is the identity and the address is affine
+    // away from the line's ends the clamp is the identity and the address is affine
     const bool interior = pos0 - half >= 0 && pos0 + steps - 1 - half <= maxpos;
-    const float* ptr = line + (ptrdiff_t)(pos0 - half) * (ptrdiff_t)line_stride;
-#define BLUR_IN(J) (interior ? ptr[(uint32_t)(J) * line_stride] : line[(uint32_t)min(max(pos0 + (J) - half, 0), maxpos) * line_stride])
-#define BLUR_ACC(S, W, V) S = __fadd_rn(S, __fmul_rn(W, V))
-    // head: steps 0..3 (outputs join one by one), generic form
+    const float* ptr = colp + (ptrdiff_t)(pos0 - half) * (ptrdiff_t)pitch;
+#define BLUR_IN(J) (*reinterpret_cast<const float2*>(interior ? ptr + (uint32_t)(J) * pitch : colp + (uint32_t)min(max(pos0 + (J) - half, 0), maxpos) * pitch))
+#define BLUR_ACC(S, W, V) S = blur_add2(S, __fmul2_rn(make_float2(W, W), V), one)
     int j = 0;
-    for (; j < 4 && j < steps; ++j) {
-        float v = BLUR_IN(j);
+    for (; j < 4 && j < steps; ++j) {  // head: outputs join one by one
+        float2 v = BLUR_IN(j);
         float w = j < klen ? kw[j] : 0.0f;
         if (j == 0) ra = w; else if (j == 1) rb = w; else if (j == 2) rc = w; else rd = w;
         if (j < klen) BLUR_ACC(s0, w, v);
@@ -127,17 +157,15 @@ __device__ __forceinline__ void blur_taps4(const float* __restrict__ line, uint3
         if (j >= 2 && j - 2 < klen) BLUR_ACC(s2, (j == 2 ? ra : rb), v);
         if (j >= 3 && j - 3 < klen) BLUR_ACC(s3, ra, v);
     }
-    // body: four steps per iteration while every output is active (j + 3 < klen), no predicates
-    for (; j + 3 < klen; j += 4) {
-        float v0 = BLUR_IN(j), v1 = BLUR_IN(j + 1), v2 = BLUR_IN(j + 2), v3 = BLUR_IN(j + 3);
+    for (; j + 3 < klen; j += 4) {  // body: every output active, no predicates
+        float2 v0 = BLUR_IN(j), v1 = BLUR_IN(j + 1), v2 = BLUR_IN(j + 2), v3 = BLUR_IN(j + 3);
         ra = kw[j];     BLUR_ACC(s0, ra, v0); BLUR_ACC(s1, rd, v0); BLUR_ACC(s2, rc, v0); BLUR_ACC(s3, rb, v0);
         rb = kw[j + 1]; BLUR_ACC(s0, rb, v1); BLUR_ACC(s1, ra, v1); BLUR_ACC(s2, rd, v1); BLUR_ACC(s3, rc, v1);
         rc = kw[j + 2]; BLUR_ACC(s0, rc, v2); BLUR_ACC(s1, rb, v2); BLUR_ACC(s2, ra, v2); BLUR_ACC(s3, rd, v2);
         rd = kw[j + 3]; BLUR_ACC(s0, rd, v3); BLUR_ACC(s1, rc, v3); BLUR_ACC(s2, rb, v3); BLUR_ACC(s3, ra, v3);
     }
-    // tail: remaining steps (outputs leave one by one), generic form; j is a multiple of 4 here
-    for (; j < steps; ++j) {
-        float v = BLUR_IN(j);
+    for (; j < steps; ++j) {  // tail: outputs leave one by one; j is a multiple of 4 at entry
+        float2 v = BLUR_IN(j);
         const int m = j & 3;
         float w = j < klen ? kw[j] : 0.0f;
         if (m == 0) ra = w; else if (m == 1) rb = w; else if (m == 2) rc = w; else rd = w;
@@ -155,86 +183,90 @@ __device__ __forceinline__ void blur_taps4(const float* __restrict__ line, uint3
     out[0] = s0; out[1] = s1; out[2] = s2; out[3] = s3;
 }
 
-// Blur along the innermost (b) axis: a CTA stages `lines` consecutive (r, g) rows -- each a
-// contiguous run of size*ch floats -- in shared memory.
-__global__ void __launch_bounds__(256) k_blur_inner(const float* __restrict__ src, float* __restrict__ dst, uint32_t size, uint32_t ch, uint32_t lines,
-                                                     const float* __restrict__ kernel, int klen) {
-    extern __shared__ float s_blur[];
-    float* s_kw = s_blur;
-    float* s_tile = s_blur + klen;
-    const uint32_t row_len = size * ch, rows = size * size;
-    const uint32_t row0 = blockIdx.x * lines, nrows = min(lines, rows - row0);
+// One blur pass along one axis of the [r][g][b][ch] volume, whatever the axis. Position p of the
+// axis is `pstride` floats from position p-1. A CTA owns `cols` columns of one outer slab and
+// stages all `size` positions of them: tile[p][c], c fastest, `pitch` floats per row. Column c of a
+// slab lives at (c / cpl) * run_stride + (c % cpl): runs of `cpl` contiguous floats (cpl = 0: the
+// whole slab is one run).
+//   B axis: pstride ch,         columns = (row, channel): cpl ch, run_stride size*ch, one slab
+//   R axis: pstride size^2*ch,  columns = the size^2*ch floats of a (g, b, channel) plane, one slab
+//   G axis: pstride size*ch,    columns = the size*ch floats of a (b, channel) line, one slab per r
+
+__global__ void __launch_bounds__(256) k_blur_axis(const float* __restrict__ src, float* __restrict__ dst, const BlurAxis P,
+                                                    const float* __restrict__ kernel, int klen, float one) {
+    extern __shared__ __align__(16) float s_blur[];
+    float* s_tile = s_blur;                                   // size * pitch, 8-byte aligned rows
+    float* s_kw = s_blur + (size_t)P.size * P.pitch;
+    const uint32_t outer = blockIdx.x / P.groups, grp = blockIdx.x % P.groups;
+    const uint32_t col0 = grp * P.cols, ncols = min(P.cols, P.total_cols - col0);
+    const uint32_t cpl = P.cpl ? P.cpl : P.total_cols;
+    const size_t base = (size_t)outer * P.outer_stride + (size_t)(col0 / cpl) * P.run_stride + (col0 % cpl);
     for (int i = threadIdx.x; i < klen; i += blockDim.x) s_kw[i] = kernel[i];
-    const float* base = src + (size_t)row0 * row_len;
-    for (uint32_t i = threadIdx.x; i < nrows * row_len; i += blockDim.x) s_tile[i] = base[i];
+    {
+        // staging walks memory run by run (contiguous floats), whatever that means for the tile
+        const uint32_t rcols = P.cpl ? P.cpl : ncols, nruns = (ncols + rcols - 1) / rcols, per_run = P.size * rcols;
+        for (uint32_t i = threadIdx.x; i < nruns * per_run; i += blockDim.x) {
+            const uint32_t run = i / per_run, x = i % per_run, p = x / rcols, cc = x % rcols, c = run * rcols + cc;
+            if (c < ncols) s_tile[p * P.pitch + c] = src[base + (size_t)run * P.run_stride + (size_t)p * P.pstride + cc];
+        }
+    }
     __syncthreads();
-    const int half = klen / 2, maxpos = (int)size - 1;
-    const uint32_t pblocks = (size + BLUR_R - 1) / BLUR_R, per_line = pblocks * ch;
-    for (uint32_t i = threadIdx.x; i < nrows * per_line; i += blockDim.x) {
-        uint32_t line = i / per_line, within = i % per_line, pb = within / ch, c = within % ch;
-        float o[BLUR_R];
-        blur_taps4(s_tile + line * row_len + c, ch, (int)(pb * BLUR_R), maxpos, s_kw, klen, half, o);
-        float* d = dst + (size_t)(row0 + line) * row_len + c;
+    const int half = klen / 2, maxpos = (int)P.size - 1;
+    const uint32_t pblocks = (P.size + BLUR_R - 1) / BLUR_R, npairs = (ncols + 1) / 2;
+    for (uint32_t i = threadIdx.x; i < pblocks * npairs; i += blockDim.x) {
+        const uint32_t pb = i / npairs, c = 2 * (i % npairs);
+        float2 o[BLUR_R];
+        blur_taps4x2(s_tile + c, P.pitch, (int)(pb * BLUR_R), maxpos, s_kw, klen, half, one, o);
+        const uint32_t rcols = P.cpl ? P.cpl : ncols;
+        const size_t offA = base + (size_t)(c / rcols) * P.run_stride + (c % rcols);
+        const size_t offB = base + (size_t)((c + 1) / rcols) * P.run_stride + ((c + 1) % rcols);
+        const bool hasB = c + 1 < ncols;
 #pragma unroll
-        for (int q = 0; q < BLUR_R; ++q)
-            if (pb * BLUR_R + q < size) d[(pb * BLUR_R + q) * ch] = o[q];
+        for (int q = 0; q < BLUR_R; ++q) {
+            const uint32_t pq = pb * BLUR_R + q;
+            if (pq < P.size) {
+                dst[offA + (size_t)pq * P.pstride] = o[q].x;
+                if (hasB) dst[offB + (size_t)pq * P.pstride] = o[q].y;
+            }
+        }
     }
 }
 
-// Blur along a strided axis (g: stride size cells, r: stride size^2 cells). A CTA owns `cols`
-// consecutive floats of the fastest-varying remainder (a run of b cells x channels, contiguous in
-// memory) and stages all `size` positions of the axis for them: tile[pos][col].
-__global__ void __launch_bounds__(256) k_blur_strided(const float* __restrict__ src, float* __restrict__ dst, uint32_t size, uint32_t axis_stride_floats,
-                                                       uint32_t groups_per_outer, uint32_t outer_stride_floats, uint32_t inner_floats, uint32_t cols,
-                                                       const float* __restrict__ kernel, int klen) {
-    extern __shared__ float s_blur[];
-    float* s_kw = s_blur;
-    float* s_tile = s_blur + klen;
-    const uint32_t outer = blockIdx.x / groups_per_outer, grp = blockIdx.x % groups_per_outer;
-    const uint32_t col0 = grp * cols, ncols = min(cols, inner_floats - col0);
-    const size_t base = (size_t)outer * outer_stride_floats + col0;
-    for (int i = threadIdx.x; i < klen; i += blockDim.x) s_kw[i] = kernel[i];
-    for (uint32_t i = threadIdx.x; i < size * ncols; i += blockDim.x) {
-        uint32_t pos = i / ncols, col = i % ncols;
-        s_tile[pos * cols + col] = src[base + (size_t)pos * axis_stride_floats + col];
-    }
-    __syncthreads();
-    const int half = klen / 2, maxpos = (int)size - 1;
-    const uint32_t pblocks = (size + BLUR_R - 1) / BLUR_R;
-    for (uint32_t i = threadIdx.x; i < pblocks * ncols; i += blockDim.x) {
-        uint32_t pb = i / ncols, col = i % ncols;
-        float o[BLUR_R];
-        blur_taps4(s_tile + col, cols, (int)(pb * BLUR_R), maxpos, s_kw, klen, half, o);
-#pragma unroll
-        for (int q = 0; q < BLUR_R; ++q)
-            if (pb * BLUR_R + q < size) dst[base + (size_t)(pb * BLUR_R + q) * axis_stride_floats + col] = o[q];
-    }
-}
+// colors_to_lut / cell_to_rgb, gaussian_blur.rs:433-500: the [r][g][b] volume to Hald order
+// (b outer, g, r inner), entries [begin, begin + count). A CTA transposes a block of 32 r x 8 b cells
+// of one g through shared memory: reads are runs of 8*ch floats, writes runs of 96 bytes.
 
-// colors_to_lut / cell_to_rgb, gaussian_blur.rs:433-500: Hald order (b outer, g, r inner), entries
-// [begin, begin + count) only.
 __global__ void __launch_bounds__(256) k_blur_to_lut(const float* __restrict__ colors, uint32_t size, uint32_t ch, const uint8_t* __restrict__ chan,
                                                       uint8_t* __restrict__ out_rgb, unsigned long long begin, unsigned long long count,
-                                                      const ColorTables* __restrict__ tables) {
+                                                      uint32_t b_first, uint32_t tiles_r, const ColorTables* __restrict__ tables) {
     __shared__ SmemTables st;
+    __shared__ float s_c[BLUR_TR][BLUR_TB * 3 + 1];
     stage_tables(st, tables);
-    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    unsigned long long px = begin + i;
-    uint32_t ri = (uint32_t)(px % size), gi = (uint32_t)((px / size) % size), bi = (uint32_t)(px / ((unsigned long long)size * size));
-    const float* c = colors + (((size_t)ri * size + gi) * size + bi) * ch;
+    const uint32_t tr = blockIdx.x % tiles_r, g = (blockIdx.x / tiles_r) % size, tb = blockIdx.x / (tiles_r * size);
+    const uint32_t r0 = tr * BLUR_TR, b0 = b_first + tb * BLUR_TB;
+    const uint32_t nb = min((uint32_t)BLUR_TB, size - min(b0, size)), run = nb * ch;
+    for (uint32_t i = threadIdx.x; i < BLUR_TR * run; i += blockDim.x) {
+        const uint32_t rr = i / run, x = i % run;
+        if (r0 + rr < size) s_c[rr][x] = colors[(((size_t)(r0 + rr) * size + g) * size + b0) * ch + x];
+    }
+    __syncthreads();
+    const uint32_t rr = threadIdx.x % BLUR_TR, bb = threadIdx.x / BLUR_TR;  // 32 x 8
+    const uint32_t ri = r0 + rr, bi = b0 + bb;
+    if (ri >= size || bb >= nb) return;
+    const unsigned long long px = ((unsigned long long)bi * size + g) * size + ri;
+    if (px < begin || px >= begin + count) return;
     Lab o;
     if (ch == 2) {
-        Lab own = linear_to_oklab_exact(st.decode[chan[ri]], st.decode[chan[gi]], st.decode[chan[bi]]);
-        o.l = own.l; o.a = c[0]; o.b = c[1];
+        Lab own = linear_to_oklab_exact(st.decode[chan[ri]], st.decode[chan[g]], st.decode[chan[bi]]);
+        o.l = own.l; o.a = s_c[rr][bb * 2]; o.b = s_c[rr][bb * 2 + 1];
     } else {
-        o.l = c[0]; o.a = c[1]; o.b = c[2];
+        o.l = s_c[rr][bb * 3]; o.a = s_c[rr][bb * 3 + 1]; o.b = s_c[rr][bb * 3 + 2];
     }
-    float r, g, b;
-    oklab_to_linear_exact(o, r, g, b);
+    float r, gg, b;
+    oklab_to_linear_exact(o, r, gg, b);
     uint8_t* q = out_rgb + 3ull * px;
     q[0] = (uint8_t)f32_to_srgb8(r, st.encode);
-    q[1] = (uint8_t)f32_to_srgb8(g, st.encode);
+    q[1] = (uint8_t)f32_to_srgb8(gg, st.encode);
     q[2] = (uint8_t)f32_to_srgb8(b, st.encode);
 }
 

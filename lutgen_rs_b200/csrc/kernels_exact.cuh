@@ -159,17 +159,6 @@ __device__ __forceinline__ double sq_dist_exact(double c0, double c1, double c2,
     return acc;
 }
 
-// Shared staging of the colour tables for kernels whose lanes index them divergently.
-struct SmemTables {
-    float decode[256];
-    uint32_t encode[104];
-};
-__device__ __forceinline__ void stage_tables(SmemTables& s, const ColorTables* __restrict__ t) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s.decode[i] = t->decode[i];
-    for (int i = threadIdx.x; i < 104; i += blockDim.x) s.encode[i] = t->encode[i];
-    __syncthreads();
-}
-
 // NearestNeighborRemapper::remap_pixel, nearest_neighbor.rs:46-61.
 // argmin over f64 squared distances, first minimum in palette order.
 template <int MODE>
