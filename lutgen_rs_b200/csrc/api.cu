@@ -592,8 +592,10 @@ int launch_blur_lut(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
         const unsigned long long plane = (unsigned long long)size * size;
         const uint32_t b_first = (uint32_t)(f.begin / plane) / BLUR_TB * BLUR_TB, b_last = (uint32_t)((f.begin + f.count - 1) / plane);
         const uint32_t tiles_r = (size + BLUR_TR - 1) / BLUR_TR, tiles_b = (b_last - b_first) / BLUR_TB + 1;
-        blur_launch_to_lut(tiles_r * size * tiles_b, s, r->blur_vol[r->blur_result], size, ch, r->blur_chan, f.out, f.begin, f.count, b_first,
-                                                                tiles_r, g.tables);
+        const uint32_t ntiles = tiles_r * size * tiles_b;
+        unsigned grid = (unsigned)g.sm_count * 8u;
+        if (grid > ntiles) grid = ntiles;
+        blur_launch_to_lut(grid, s, r->blur_vol[r->blur_result], size, ch, r->blur_chan, f.out, f.begin, f.count, b_first, tiles_r, ntiles, g.tables);
     }
     LAUNCH_CHECK();
     return LUTGEN_OK;

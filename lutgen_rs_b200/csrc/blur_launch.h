@@ -26,6 +26,6 @@ void blur_launch_nn_volume(unsigned grid, size_t smem, cudaStream_t s, float* co
                            const float* out3, uint32_t n, float lum, float threshold_sq, const ColorTables* tables, int stage_palette);
 void blur_launch_axis(unsigned grid, size_t smem, cudaStream_t s, const float* src, float* dst, const BlurAxis& P, const float* kernel, int klen);
 void blur_launch_to_lut(unsigned grid, cudaStream_t s, const float* colors, uint32_t size, uint32_t ch, const uint8_t* chan, uint8_t* out_rgb,
-                        unsigned long long begin, unsigned long long count, uint32_t b_first, uint32_t tiles_r, const ColorTables* tables);
+                        unsigned long long begin, unsigned long long count, uint32_t b_first, uint32_t tiles_r, uint32_t ntiles, const ColorTables* tables);
 
 }  // namespace lutgen

@@ -136,16 +136,17 @@ __global__ void __launch_bounds__(BLUR_ROW_WARPS * 32) k_blur_nn_volume(float* _
 // 8 outputs, and the sums are bit-identical to the one-output-at-a-time loop.
 constexpr int BLUR_R = 4;
 
+// INTERIOR: the whole window p0 - half .. p0 + 3 + half lies inside the line, so the clamp is the
+// identity and the input address just advances by `pitch` per step.
+template <bool INTERIOR>
 __device__ __forceinline__ void blur_taps4x2(const float* __restrict__ colp, uint32_t pitch, int pos0, int maxpos,
                                              const float* __restrict__ kw, int klen, int half, float one, float2 (&out)[BLUR_R]) {
     float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
     // weights live in four registers named by j mod 4 (ra = kw[j] for j = 0 mod 4, ...): no shifting
     float ra = 0.0f, rb = 0.0f, rc = 0.0f, rd = 0.0f;
     const int steps = klen + BLUR_R - 1;
-    // away from the line's ends the clamp is the identity and the address is affine
-    const bool interior = pos0 - half >= 0 && pos0 + steps - 1 - half <= maxpos;
-    const float* ptr = colp + (ptrdiff_t)(pos0 - half) * (ptrdiff_t)pitch;
-#define BLUR_IN(J) (*reinterpret_cast<const float2*>(interior ? ptr + (uint32_t)(J) * pitch : colp + (uint32_t)min(max(pos0 + (J) - half, 0), maxpos) * pitch))
+    const float* ptr = colp + (ptrdiff_t)(pos0 - half) * (ptrdiff_t)pitch;  // INTERIOR: input of the current step
+#define BLUR_IN(J) (*reinterpret_cast<const float2*>(INTERIOR ? ptr + (uint32_t)(J) * pitch : colp + (uint32_t)min(max(pos0 + (J) - half, 0), maxpos) * pitch))
 #define BLUR_ACC(S, W, V) S = blur_add2(S, __fmul2_rn(make_float2(W, W), V), one)
     int j = 0;
     for (; j < 4 && j < steps; ++j) {  // head: outputs join one by one
@@ -157,12 +158,29 @@ __device__ __forceinline__ void blur_taps4x2(const float* __restrict__ colp, uin
         if (j >= 2 && j - 2 < klen) BLUR_ACC(s2, (j == 2 ? ra : rb), v);
         if (j >= 3 && j - 3 < klen) BLUR_ACC(s3, ra, v);
     }
-    for (; j + 3 < klen; j += 4) {  // body: every output active, no predicates
-        float2 v0 = BLUR_IN(j), v1 = BLUR_IN(j + 1), v2 = BLUR_IN(j + 2), v3 = BLUR_IN(j + 3);
-        ra = kw[j];     BLUR_ACC(s0, ra, v0); BLUR_ACC(s1, rd, v0); BLUR_ACC(s2, rc, v0); BLUR_ACC(s3, rb, v0);
-        rb = kw[j + 1]; BLUR_ACC(s0, rb, v1); BLUR_ACC(s1, ra, v1); BLUR_ACC(s2, rd, v1); BLUR_ACC(s3, rc, v1);
-        rc = kw[j + 2]; BLUR_ACC(s0, rc, v2); BLUR_ACC(s1, rb, v2); BLUR_ACC(s2, ra, v2); BLUR_ACC(s3, rd, v2);
-        rd = kw[j + 3]; BLUR_ACC(s0, rd, v3); BLUR_ACC(s1, rc, v3); BLUR_ACC(s2, rb, v3); BLUR_ACC(s3, ra, v3);
+    if (INTERIOR) {
+        // body: every output active, no predicates; `q` walks the input rows, `kq` the weights
+        const float* q = ptr + (uint32_t)j * pitch;
+        const float* kq = kw + j;
+        const uint32_t p4 = 4u * pitch;
+#pragma unroll 1
+        for (; j + 3 < klen; j += 4, q += p4, kq += 4) {
+            const float2 v0 = *reinterpret_cast<const float2*>(q), v1 = *reinterpret_cast<const float2*>(q + pitch);
+            const float2 v2 = *reinterpret_cast<const float2*>(q + 2u * pitch), v3 = *reinterpret_cast<const float2*>(q + 3u * pitch);
+            ra = kq[0]; BLUR_ACC(s0, ra, v0); BLUR_ACC(s1, rd, v0); BLUR_ACC(s2, rc, v0); BLUR_ACC(s3, rb, v0);
+            rb = kq[1]; BLUR_ACC(s0, rb, v1); BLUR_ACC(s1, ra, v1); BLUR_ACC(s2, rd, v1); BLUR_ACC(s3, rc, v1);
+            rc = kq[2]; BLUR_ACC(s0, rc, v2); BLUR_ACC(s1, rb, v2); BLUR_ACC(s2, ra, v2); BLUR_ACC(s3, rd, v2);
+            rd = kq[3]; BLUR_ACC(s0, rd, v3); BLUR_ACC(s1, rc, v3); BLUR_ACC(s2, rb, v3); BLUR_ACC(s3, ra, v3);
+        }
+    } else {
+#pragma unroll 1
+        for (; j + 3 < klen; j += 4) {
+            float2 v0 = BLUR_IN(j), v1 = BLUR_IN(j + 1), v2 = BLUR_IN(j + 2), v3 = BLUR_IN(j + 3);
+            ra = kw[j];     BLUR_ACC(s0, ra, v0); BLUR_ACC(s1, rd, v0); BLUR_ACC(s2, rc, v0); BLUR_ACC(s3, rb, v0);
+            rb = kw[j + 1]; BLUR_ACC(s0, rb, v1); BLUR_ACC(s1, ra, v1); BLUR_ACC(s2, rd, v1); BLUR_ACC(s3, rc, v1);
+            rc = kw[j + 2]; BLUR_ACC(s0, rc, v2); BLUR_ACC(s1, rb, v2); BLUR_ACC(s2, ra, v2); BLUR_ACC(s3, rd, v2);
+            rd = kw[j + 3]; BLUR_ACC(s0, rd, v3); BLUR_ACC(s1, rc, v3); BLUR_ACC(s2, rb, v3); BLUR_ACC(s3, ra, v3);
+        }
     }
     for (; j < steps; ++j) {  // tail: outputs leave one by one; j is a multiple of 4 at entry
         float2 v = BLUR_IN(j);
@@ -191,7 +209,6 @@ __device__ __forceinline__ void blur_taps4x2(const float* __restrict__ colp, uin
 //   B axis: pstride ch,         columns = (row, channel): cpl ch, run_stride size*ch, one slab
 //   R axis: pstride size^2*ch,  columns = the size^2*ch floats of a (g, b, channel) plane, one slab
 //   G axis: pstride size*ch,    columns = the size*ch floats of a (b, channel) line, one slab per r
-
 __global__ void __launch_bounds__(256) k_blur_axis(const float* __restrict__ src, float* __restrict__ dst, const BlurAxis P,
                                                     const float* __restrict__ kernel, int klen, float one) {
     extern __shared__ __align__(16) float s_blur[];
@@ -202,25 +219,42 @@ __global__ void __launch_bounds__(256) k_blur_axis(const float* __restrict__ src
     const uint32_t cpl = P.cpl ? P.cpl : P.total_cols;
     const size_t base = (size_t)outer * P.outer_stride + (size_t)(col0 / cpl) * P.run_stride + (col0 % cpl);
     for (int i = threadIdx.x; i < klen; i += blockDim.x) s_kw[i] = kernel[i];
-    {
-        // staging walks memory run by run (contiguous floats), whatever that means for the tile
-        const uint32_t rcols = P.cpl ? P.cpl : ncols, nruns = (ncols + rcols - 1) / rcols, per_run = P.size * rcols;
-        for (uint32_t i = threadIdx.x; i < nruns * per_run; i += blockDim.x) {
-            const uint32_t run = i / per_run, x = i % per_run, p = x / rcols, cc = x % rcols, c = run * rcols + cc;
-            if (c < ncols) s_tile[p * P.pitch + c] = src[base + (size_t)run * P.run_stride + (size_t)p * P.pstride + cc];
+    if (P.cpl == 0) {
+        // the columns are contiguous floats: thread = (row of the wave, column), waves of 256 / cols rows
+        const uint32_t c = threadIdx.x % P.cols, prow = threadIdx.x / P.cols, pstep = blockDim.x / P.cols;
+        if (c < ncols && prow < pstep) {
+            const float* q = src + base + c;
+            for (uint32_t p = prow; p < P.size; p += pstep) s_tile[p * P.pitch + c] = q[(size_t)p * P.pstride];
+        }
+    } else {
+        // runs of cpl (= channels: 2 or 3) columns, each run one contiguous row of size * cpl floats
+        const uint32_t rcols = P.cpl, nruns = (ncols + rcols - 1) / rcols, per_run = P.size * rcols;
+        for (uint32_t run = 0; run < nruns; ++run) {
+            const float* q = src + base + (size_t)run * P.run_stride;
+            float* t = s_tile + run * rcols;
+            for (uint32_t x = threadIdx.x; x < per_run; x += blockDim.x) {
+                const uint32_t p = rcols == 3 ? x / 3u : (rcols == 2 ? x >> 1 : x / rcols), cc = x - p * rcols;
+                if (run * rcols + cc < ncols) t[p * P.pitch + cc] = q[x];
+            }
         }
     }
     __syncthreads();
     const int half = klen / 2, maxpos = (int)P.size - 1;
     const uint32_t pblocks = (P.size + BLUR_R - 1) / BLUR_R, npairs = (ncols + 1) / 2;
-    for (uint32_t i = threadIdx.x; i < pblocks * npairs; i += blockDim.x) {
-        const uint32_t pb = i / npairs, c = 2 * (i % npairs);
+    const uint32_t pair = threadIdx.x % npairs, pb0 = threadIdx.x / npairs, pbstep = blockDim.x / npairs;
+    if (pb0 >= pbstep) return;  // blockDim.x is not a multiple of npairs: the remainder threads idle
+    const uint32_t c = 2 * pair;
+    const uint32_t rcols = P.cpl ? P.cpl : ncols;
+    const size_t offA = base + (size_t)(c / rcols) * P.run_stride + (c % rcols);
+    const size_t offB = base + (size_t)((c + 1) / rcols) * P.run_stride + ((c + 1) % rcols);
+    const bool hasB = c + 1 < ncols;
+    for (uint32_t pb = pb0; pb < pblocks; pb += pbstep) {
         float2 o[BLUR_R];
-        blur_taps4x2(s_tile + c, P.pitch, (int)(pb * BLUR_R), maxpos, s_kw, klen, half, one, o);
-        const uint32_t rcols = P.cpl ? P.cpl : ncols;
-        const size_t offA = base + (size_t)(c / rcols) * P.run_stride + (c % rcols);
-        const size_t offB = base + (size_t)((c + 1) / rcols) * P.run_stride + ((c + 1) % rcols);
-        const bool hasB = c + 1 < ncols;
+        const int pos0 = (int)(pb * BLUR_R);
+        if (pos0 - half >= 0 && pos0 + klen + BLUR_R - 2 - half <= maxpos)
+            blur_taps4x2<true>(s_tile + c, P.pitch, pos0, maxpos, s_kw, klen, half, one, o);
+        else
+            blur_taps4x2<false>(s_tile + c, P.pitch, pos0, maxpos, s_kw, klen, half, one, o);
 #pragma unroll
         for (int q = 0; q < BLUR_R; ++q) {
             const uint32_t pq = pb * BLUR_R + q;
@@ -233,41 +267,56 @@ __global__ void __launch_bounds__(256) k_blur_axis(const float* __restrict__ src
 }
 
 // colors_to_lut / cell_to_rgb, gaussian_blur.rs:433-500: the [r][g][b] volume to Hald order
-// (b outer, g, r inner), entries [begin, begin + count). A CTA transposes a block of 32 r x 8 b cells
-// of one g through shared memory: reads are runs of 8*ch floats, writes runs of 96 bytes.
-
+// (b outer, g, r inner), entries [begin, begin + count). A tile is 32 r x 8 b cells of one g,
+// transposed through shared memory (reads are runs of 8*ch floats, writes runs of 96 bytes); CTAs
+// are persistent and walk tiles blockIdx.x, blockIdx.x + gridDim.x, ...
 __global__ void __launch_bounds__(256) k_blur_to_lut(const float* __restrict__ colors, uint32_t size, uint32_t ch, const uint8_t* __restrict__ chan,
                                                       uint8_t* __restrict__ out_rgb, unsigned long long begin, unsigned long long count,
-                                                      uint32_t b_first, uint32_t tiles_r, const ColorTables* __restrict__ tables) {
+                                                      uint32_t b_first, uint32_t tiles_r, uint32_t ntiles, const ColorTables* __restrict__ tables) {
     __shared__ SmemTables st;
     __shared__ float s_c[BLUR_TR][BLUR_TB * 3 + 1];
     stage_tables(st, tables);
-    const uint32_t tr = blockIdx.x % tiles_r, g = (blockIdx.x / tiles_r) % size, tb = blockIdx.x / (tiles_r * size);
-    const uint32_t r0 = tr * BLUR_TR, b0 = b_first + tb * BLUR_TB;
-    const uint32_t nb = min((uint32_t)BLUR_TB, size - min(b0, size)), run = nb * ch;
-    for (uint32_t i = threadIdx.x; i < BLUR_TR * run; i += blockDim.x) {
-        const uint32_t rr = i / run, x = i % run;
-        if (r0 + rr < size) s_c[rr][x] = colors[(((size_t)(r0 + rr) * size + g) * size + b0) * ch + x];
+    const uint32_t lr = threadIdx.x >> 3, lb = threadIdx.x & 7u;      // loading: 8 b cells of one r are contiguous
+    const uint32_t rr = threadIdx.x & 31u, bb = threadIdx.x >> 5;      // storing: 32 r entries of one b are contiguous
+    const float inv_tr = 1.0f / (float)tiles_r, inv_size = 1.0f / (float)size;
+    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        // t = (tb * size + g) * tiles_r + tr   (float estimate + correction: t < 2^24)
+        uint32_t q1 = (uint32_t)(__uint2float_rz(t) * inv_tr);
+        int rem = (int)(t - q1 * tiles_r);
+        if (rem < 0) { --q1; rem += (int)tiles_r; }
+        if (rem >= (int)tiles_r) { ++q1; rem -= (int)tiles_r; }
+        const uint32_t tr = (uint32_t)rem;
+        uint32_t tb = (uint32_t)(__uint2float_rz(q1) * inv_size);
+        int g_ = (int)(q1 - tb * size);
+        if (g_ < 0) { --tb; g_ += (int)size; }
+        if (g_ >= (int)size) { ++tb; g_ -= (int)size; }
+        const uint32_t g = (uint32_t)g_, r0 = tr * BLUR_TR, b0 = b_first + tb * BLUR_TB;
+        __syncthreads();  // the previous tile's s_c is no longer read
+        if (r0 + lr < size && b0 + lb < size) {
+            const float* q = colors + (((size_t)(r0 + lr) * size + g) * size + b0 + lb) * ch;
+            s_c[lr][lb * ch] = q[0];
+            s_c[lr][lb * ch + 1] = q[1];
+            if (ch == 3) s_c[lr][lb * ch + 2] = q[2];
+        }
+        __syncthreads();
+        const uint32_t ri = r0 + rr, bi = b0 + bb;
+        if (ri >= size || bi >= size) continue;
+        const unsigned long long px = ((unsigned long long)bi * size + g) * size + ri;
+        if (px < begin || px >= begin + count) continue;
+        Lab o;
+        if (ch == 2) {
+            Lab own = linear_to_oklab_exact(st.decode[chan[ri]], st.decode[chan[g]], st.decode[chan[bi]]);
+            o.l = own.l; o.a = s_c[rr][bb * 2]; o.b = s_c[rr][bb * 2 + 1];
+        } else {
+            o.l = s_c[rr][bb * 3]; o.a = s_c[rr][bb * 3 + 1]; o.b = s_c[rr][bb * 3 + 2];
+        }
+        float r, gg, b;
+        oklab_to_linear_exact(o, r, gg, b);
+        uint8_t* q = out_rgb + 3ull * px;
+        q[0] = (uint8_t)f32_to_srgb8(r, st.encode);
+        q[1] = (uint8_t)f32_to_srgb8(gg, st.encode);
+        q[2] = (uint8_t)f32_to_srgb8(b, st.encode);
     }
-    __syncthreads();
-    const uint32_t rr = threadIdx.x % BLUR_TR, bb = threadIdx.x / BLUR_TR;  // 32 x 8
-    const uint32_t ri = r0 + rr, bi = b0 + bb;
-    if (ri >= size || bb >= nb) return;
-    const unsigned long long px = ((unsigned long long)bi * size + g) * size + ri;
-    if (px < begin || px >= begin + count) return;
-    Lab o;
-    if (ch == 2) {
-        Lab own = linear_to_oklab_exact(st.decode[chan[ri]], st.decode[chan[g]], st.decode[chan[bi]]);
-        o.l = own.l; o.a = s_c[rr][bb * 2]; o.b = s_c[rr][bb * 2 + 1];
-    } else {
-        o.l = s_c[rr][bb * 3]; o.a = s_c[rr][bb * 3 + 1]; o.b = s_c[rr][bb * 3 + 2];
-    }
-    float r, gg, b;
-    oklab_to_linear_exact(o, r, gg, b);
-    uint8_t* q = out_rgb + 3ull * px;
-    q[0] = (uint8_t)f32_to_srgb8(r, st.encode);
-    q[1] = (uint8_t)f32_to_srgb8(gg, st.encode);
-    q[2] = (uint8_t)f32_to_srgb8(b, st.encode);
 }
 
 }  // namespace lutgen
