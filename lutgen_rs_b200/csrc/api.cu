@@ -287,8 +287,7 @@ bool fast_path_supported(const lutgen_remapper* r) {
 // colours), 2 = k_remap_warp_big (33 .. 256 colours, nearest-k with k <= 32 or NearestNeighbor).
 template <int KIND>
 int warp_path(const lutgen_remapper* r, uint32_t n, uint32_t k) {
-    static const bool off = getenv("LUTGEN_CUDA_NO_WARP") != nullptr;
-    if (off) return 0;
+    if (getenv("LUTGEN_CUDA_NO_WARP")) return 0;  // read per call: tests compare the two families of kernels
     if (KIND == 0) {
         // the expanded distance is scaled by C = shape*log2(e): keep it where f32 has room
         double C = r->d.param * 1.4426950408889634;
