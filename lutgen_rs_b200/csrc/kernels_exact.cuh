@@ -195,6 +195,46 @@ __device__ __forceinline__ double radial_basis_exact(double d, double param) {
     return exp(__dmul_rn(-param, d));                     // GaussianFn    rbf.rs:178
 }
 
+// The k <= RK nearest colours of a flagged entry (list mode: the fast kernel only flags entries whose
+// distances are finite), kept sorted in REGISTERS: the list pass is a few thousand threads, each
+// one entry, and with the sorted array in local memory every insertion was a chain of dependent
+// loads and stores (47 % of the pass's instructions, 0.1 IPC). Same order as the array version:
+// ascending distance, a later colour at an equal distance after an earlier one, so the f64 sums
+// below run in the oracle's order. The list holds RK >= k candidates; the first k are summed.
+template <int KIND, int RK>
+__device__ __forceinline__ void rbf_exact_topk_regs(const RemapParams& P, double c0, double c1, double c2, double& n0, double& n1, double& n2,
+                                                    double& den) {
+    double td[RK];
+    uint32_t tj[RK];
+#pragma unroll
+    for (int i = 0; i < RK; ++i) { td[i] = INFINITY; tj[i] = 0; }
+    for (uint32_t j = 0; j < P.n; ++j) {
+        const double d = sq_dist_exact(c0, c1, c2, P.pal_lab + 3 * j);
+        if (d < td[RK - 1]) {
+#pragma unroll
+            for (int i = RK - 1; i >= 1; --i) {
+                const bool shift = td[i - 1] > d, place = !shift && td[i] > d;
+                td[i] = shift ? td[i - 1] : (place ? d : td[i]);
+                tj[i] = shift ? tj[i - 1] : (place ? j : tj[i]);
+            }
+            const bool place0 = td[0] > d;
+            td[0] = place0 ? d : td[0];
+            tj[0] = place0 ? j : tj[0];
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < RK; ++a) {
+        if ((uint32_t)a < P.nearest) {
+            const double* p = P.pal_lab + 3 * tj[a];
+            double w = radial_basis_exact<KIND>(td[a], P.param);
+            n0 = __dadd_rn(n0, __dmul_rn(p[0], w));
+            n1 = __dadd_rn(n1, __dmul_rn(p[1], w));
+            n2 = __dadd_rn(n2, __dmul_rn(p[2], w));
+            den = __dadd_rn(den, w);
+        }
+    }
+}
+
 // RBFRemapper::remap_pixel, rbf.rs:57-111, operation for operation in f64.
 // nearest_n is brute force: k passes, each extracting the next (distance, index)
 // in ascending lexicographic order, so the f64 accumulation order equals the
@@ -224,6 +264,8 @@ __device__ __forceinline__ void rbf_exact_one(const Front& f, const RemapParams&
             n2 = __dadd_rn(n2, __dmul_rn(p[2], w));
             den = __dadd_rn(den, w);
         }
+    } else if (MODE == FRONT_LIST && P.nearest <= 16) {
+        rbf_exact_topk_regs<KIND, 16>(P, c0, c1, c2, n0, n1, n2, den);
     } else if (P.nearest <= 64) {
         // One pass over the palette keeping the k best (distance, index) pairs sorted ascending in
         // a per-thread array: a later colour at an equal distance sorts after an earlier one, so
