@@ -256,7 +256,17 @@ def run_b200(args):
     r0, r1, per = device.shard_rows(side, world, rank)
     lut16 = torch.empty(per * world * side * 3, dtype=torch.uint8, device="cuda")
 
+    fused = world > 1 and not os.environ.get("LUTGEN_BENCH_ALLGATHER")
+
     def gen_step():
+        # N > 1: every rank computes its share of the tiles and stores it into all ranks' CLUT buffers
+        # over NVLink while it computes; a barrier through peer memory replaces the all-gather
+        if fused:
+            device.generate_lut_fused(remapper, LEVEL_GEN)
+        else:
+            device.generate_lut(remapper, LEVEL_GEN, out=lut16)
+
+    def gen_allgather_step():
         device.generate_lut(remapper, LEVEL_GEN, out=lut16)
 
     def gen_kernel_only():
@@ -299,7 +309,7 @@ def run_b200(args):
         if world == 1:
             remapper.generate_lut(LEVEL_GEN, out=lut16_host.numpy())
         else:
-            full = device.generate_lut(remapper, LEVEL_GEN, out=lut16)
+            full = device.generate_lut_fused(remapper, LEVEL_GEN) if fused else device.generate_lut(remapper, LEVEL_GEN, out=lut16)
             if rank == 0:
                 lut16_host.copy_(full, non_blocking=True)
             torch.cuda.synchronize()
@@ -328,6 +338,11 @@ def run_b200(args):
     gen_t = max_over_ranks(float(np.mean(gen_times)))
     gen_kernel_times = timed(gen_kernel_only, steps, flush=True)
     gen_kernel_t = float(np.mean(gen_kernel_times))
+    gen_ag_t = None
+    if world > 1 and fused:
+        barrier()
+        gen_ag_t = max_over_ranks(float(np.mean(timed(gen_allgather_step, steps, flush=True))))
+        barrier()
     # apply, device resident
     launches1 = _native.launch_count()
     barrier()
@@ -384,9 +399,16 @@ def run_b200(args):
                      "step_ms_each": [round(t * 1e3, 4) for t in gen_times],
                      "kernel_ms_each": [round(t * 1e3, 4) for t in gen_kernel_times]},
         "config": {"workload": "generate level-16 Gaussian RBF CLUT (16,777,216 entries), catppuccin-mocha 26 colours, "
-                               "shape 128, nearest 16, lum 1.0, preserve off; rows sharded over ranks + in-place NCCL all-gather",
+                               "shape 128, nearest 16, lum 1.0, preserve off; "
+                               + ("one GPU" if world == 1 else
+                                  ("tiles interleaved over ranks, results stored into every rank's buffer over NVLink by the kernel "
+                                   "(CUDA IPC peer memory) + peer-memory barrier" if fused else
+                                   "rows sharded over ranks + in-place NCCL all-gather")),
                    "level": LEVEL_GEN, "l2": "flushed between timed iterations (512 MiB fill)"},
     }
+    if gen_ag_t is not None:
+        gen_line["allgather_variant"] = {"ms_per_step": gen_ag_t * 1e3, "value": entries / gen_ag_t,
+                                         "what": "same CLUT as contiguous row shards + in-place NCCL all-gather (the unfused scheme)"}
     total_pix = apply_pix * world
     apply_bw = apply_pix * APPLY_BYTES_PER_PIXEL / apply_t / 1e9
     apply_line = {

@@ -149,6 +149,36 @@ LUTGEN_API int lutgen_cuda_generate_lut(const lutgen_remapper* r, uint8_t level,
 LUTGEN_API int lutgen_cuda_generate_lut_rows_dev(const lutgen_remapper* r, uint8_t level, uint8_t* lut_rgb_dev,
                                                  uint32_t row_begin, uint32_t row_end, void* stream);
 
+/* Rows [row_begin, row_end) written to SEVERAL full-size CLUT images at once: luts_rgb_dev[0] is this
+ * GPU's, the others are the same buffer of the other ranks mapped into this process (CUDA IPC below),
+ * written over NVLink while the kernel computes. This is the fused form of "row shard + all-gather"
+ * (reference loop: crates/lib/src/interpolation/mod.rs:46-50 over lib.rs:143-147): after a
+ * barrier across the ranks every buffer holds the whole CLUT. RBF and NearestNeighbor remappers;
+ * LUTGEN_ERR_UNSUPPORTED for the sampling and blur remappers (generate locally, then all-gather). */
+LUTGEN_API int lutgen_cuda_generate_lut_rows_multi_dev(const lutgen_remapper* r, uint8_t level, uint8_t* const* luts_rgb_dev, int nluts,
+                                                       uint32_t row_begin, uint32_t row_end, void* stream);
+
+/* The same with BALANCED shards: this launch is shard `shard_index` of `shard_count` of the whole CLUT and
+ * takes every shard_count-th tile hand-out of the warp-tile kernels (tiles differ a lot in cost; contiguous
+ * row shards do not balance). Remappers that run on other kernels get the shard's contiguous rows. Every
+ * destination must receive all shards (one launch per rank) before the CLUT is complete. */
+LUTGEN_API int lutgen_cuda_generate_lut_shard_multi_dev(const lutgen_remapper* r, uint8_t level, uint8_t* const* luts_rgb_dev, int nluts,
+                                                        uint32_t shard_index, uint32_t shard_count, void* stream);
+
+/* Barrier between the per-GPU processes through flags in peer memory. flags_dev_table: DEVICE array of
+ * nranks pointers, entry i = rank i's flag array (>= nranks zero-initialised u32, mapped into this process);
+ * epoch must grow by one per barrier. Orders this GPU's earlier writes to peer buffers before the peers'
+ * later reads. Replaces the collective of the row-shard + all-gather scheme. */
+LUTGEN_API int lutgen_cuda_peer_barrier_dev(unsigned* const* flags_dev_table, int nranks, int rank, unsigned epoch, void* stream);
+
+/* Device memory that can be shared between the per-GPU processes of one node, and its CUDA IPC
+ * handle (64 bytes) / mapping. Plumbing for the call above; no reference counterpart. */
+LUTGEN_API int lutgen_cuda_device_alloc(size_t bytes, void** out);
+LUTGEN_API int lutgen_cuda_device_free(void* p);
+LUTGEN_API int lutgen_cuda_ipc_export(void* dev_ptr, unsigned char handle[64]);
+LUTGEN_API int lutgen_cuda_ipc_import(const unsigned char handle[64], void** dev_ptr_out);
+LUTGEN_API int lutgen_cuda_ipc_close(void* dev_ptr);
+
 /* InterpolatedRemapper::{remap_image, par_remap_image, *_with_interrupt}
  * crates/lib/src/interpolation/mod.rs:23-61. RGBA8 in place, alpha untouched.
  * npix == 1 is InterpolatedRemapper::remap_pixel (mod.rs:25). */

@@ -283,6 +283,25 @@ bool fast_path_supported(const lutgen_remapper* r) {
     return true;
 }
 
+// A launch that is "shard i of n" of its range but runs on a kernel that does not interleave tiles:
+// the shard's contiguous rows (ceil(rows / n) each), as device.shard_rows does on the host side.
+Front rows_of_shard(const Front& f) {
+    Front o = f;
+    if (f.shard_count <= 1) return o;
+    uint32_t level = 2;
+    while (level * level < f.cs) ++level;
+    const unsigned long long row_len = (unsigned long long)level * f.cs;  // level^3 entries per row
+    const unsigned long long rows = f.count / row_len, per = (rows + f.shard_count - 1) / f.shard_count;
+    unsigned long long r0 = per * f.shard_index, r1 = r0 + per;
+    if (r0 > rows) r0 = rows;
+    if (r1 > rows) r1 = rows;
+    o.begin = f.begin + r0 * row_len;
+    o.count = (r1 - r0) * row_len;
+    o.shard_index = 0;
+    o.shard_count = 1;
+    return o;
+}
+
 // Warp-tile kernels (kernels_warp.cuh): 0 = not applicable, 1 = k_remap_warp (palettes of at most 32
 // colours), 2 = k_remap_warp_big (33 .. 256 colours, nearest-k with k <= 32 or NearestNeighbor).
 template <int KIND>
@@ -306,6 +325,12 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
     a.n = fa.n; a.k = fa.k; a.preserve = fa.preserve; a.lum = fa.lum; a.inv_lum = fa.inv_lum; a.c1 = fa.c1;
     a.flag_list = fa.flag_list; a.flag_count = fa.flag_count; a.tile_counter = fa.tile_counter;
     a.stats = fa.stats; a.tables = fa.tables;
+    a.words_ok = 0;
+    if (MODE == FRONT_LUT && (f.cs & 3u) == 0) {
+        uintptr_t bits = reinterpret_cast<uintptr_t>(f.out);
+        for (int x = 0; x < f.nextra; ++x) bits |= reinterpret_cast<uintptr_t>(f.extra[x]);
+        a.words_ok = (bits & 3u) == 0;
+    }
     // BIG: the CTA's eight warp tiles form one 16 x 8 x 2 EPT CTA tile (or 256 EPT pixels)
     const uint32_t tr = BIG ? 16 : 8, tg = BIG ? 8 : 4, tb = BIG ? 2 * EPT : EPT, tpix = (BIG ? 256u : 32u) * EPT;
     if (MODE == FRONT_IMAGE) {
@@ -324,6 +349,20 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
         a.b_lo = b_lo;
         a.ntiles = a.tiles_r * a.tiles_g * ((b_hi - b_lo) / tb + 1);
     }
+    a.ntiles_global = a.ntiles;
+    a.shard_index = 0;
+    a.shard_count = 1;
+    if (MODE == FRONT_LUT && f.shard_count > 1) {
+        // hand-outs (WT_BATCH warp tiles, or one CTA tile) index, index + count, ...
+        const uint32_t per = BIG ? 1u : (uint32_t)WT_BATCH, handouts = (a.ntiles_global + per - 1) / per;
+        a.shard_index = f.shard_index;
+        a.shard_count = f.shard_count;
+        a.ntiles = handouts > f.shard_index ? ((handouts - f.shard_index + f.shard_count - 1) / f.shard_count) * per : 0;
+        if (a.ntiles == 0) {
+            CU_TRY(cudaMemsetAsync(r->flag_count, 0, 2 * sizeof(uint32_t), s));
+            return LUTGEN_OK;
+        }
+    }
     static int per_sm = 0;  // one per instantiation
     if (per_sm == 0) {
         if (BIG) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_remap_warp_big<KIND, MODE, EPT>, WT_THREADS, 0));
@@ -341,7 +380,10 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
 }
 
 template <int KIND, int MODE>
-int launch_fast(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
+int launch_fast(const Front& f_in, const lutgen_remapper* r, cudaStream_t s) {
+    // interleaved shards exist in the warp-tile kernels only
+    const bool nn_ = KIND == KIND_NN;
+    const Front f = (f_in.shard_count > 1 && !warp_path<KIND>(r, nn_ ? r->un : r->n, nn_ ? 1u : r->k_eff)) ? rows_of_shard(f_in) : f_in;
     if (f.count == 0) return LUTGEN_OK;
     {
         std::lock_guard<std::mutex> lk(r->mu);
@@ -373,6 +415,8 @@ int launch_fast(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
     a.tile_counter = r->flag_count + 1;
     a.tables = g.tables;
     Front fl = f;
+    fl.shard_index = 0;
+    fl.shard_count = 1;
     fl.list = r->flag_list;
     fl.list_count = r->flag_count;
     fl.list_mode = MODE;
@@ -434,12 +478,12 @@ int launch_fast(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
 template <int MODE>
 int launch_nn(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
     if (r->fast_ok) return launch_fast<KIND_NN, MODE>(f, r, s);
-    return launch_nn_exact<MODE>(f, r, s);
+    return launch_nn_exact<MODE>(rows_of_shard(f), r, s);
 }
 
 template <int MODE>
 int launch_rbf(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
-    if (!r->fast_ok) return launch_rbf_exact<MODE>(f, r, s);
+    if (!r->fast_ok) return launch_rbf_exact<MODE>(rows_of_shard(f), r, s);
     switch (r->d.kind) {
         case LUTGEN_GAUSSIAN: return launch_fast<0, MODE>(f, r, s);
         case LUTGEN_SHEPARD: return launch_fast<1, MODE>(f, r, s);
@@ -1117,6 +1161,129 @@ int lutgen_cuda_generate_lut_rows_dev(const lutgen_remapper* r, uint8_t level, u
     f.csm1 = f.cs - 1;
     rc = launch_remap<FRONT_LUT>(f, r, s);
     if (rc) return rc;
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_generate_lut_rows_multi_dev(const lutgen_remapper* r, uint8_t level, uint8_t* const* luts_rgb_dev, int nluts, uint32_t row_begin,
+                                            uint32_t row_end, void* stream) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!r || !luts_rgb_dev || nluts < 1) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    if (nluts > 1 + LUTGEN_MAX_PEERS) return fail(LUTGEN_ERR_UNSUPPORTED, "%d destinations (limit %d)", nluts, 1 + LUTGEN_MAX_PEERS);
+    for (int i = 0; i < nluts; ++i)
+        if (!luts_rgb_dev[i]) return fail(LUTGEN_ERR_INVALID, "destination %d is NULL", i);
+    if (r->d.kind == LUTGEN_SAMPLING || r->d.kind == LUTGEN_BLUR)
+        return fail(LUTGEN_ERR_UNSUPPORTED, "multi-destination rows: RBF and NearestNeighbor remappers only (others: generate locally, then all-gather)");
+    if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33", level);
+    uint32_t side = (uint32_t)level * level * level;
+    if (row_begin > row_end || row_end > side) return fail(LUTGEN_ERR_INVALID, "rows [%u, %u) outside 0..%u", row_begin, row_end, side);
+    cudaStream_t s = (cudaStream_t)stream;
+    Front f{};
+    f.out = luts_rgb_dev[0];
+    f.nextra = nluts - 1;
+    for (int i = 1; i < nluts; ++i) f.extra[i - 1] = luts_rgb_dev[i];
+    f.begin = (unsigned long long)row_begin * side;
+    f.count = (unsigned long long)(row_end - row_begin) * side;
+    f.cs = (uint32_t)level * level;
+    f.csm1 = f.cs - 1;
+    return launch_remap<FRONT_LUT>(f, r, s);
+}
+
+int lutgen_cuda_generate_lut_shard_multi_dev(const lutgen_remapper* r, uint8_t level, uint8_t* const* luts_rgb_dev, int nluts, uint32_t shard_index,
+                                             uint32_t shard_count, void* stream) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!r || !luts_rgb_dev || nluts < 1) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    if (nluts > 1 + LUTGEN_MAX_PEERS) return fail(LUTGEN_ERR_UNSUPPORTED, "%d destinations (limit %d)", nluts, 1 + LUTGEN_MAX_PEERS);
+    for (int i = 0; i < nluts; ++i)
+        if (!luts_rgb_dev[i]) return fail(LUTGEN_ERR_INVALID, "destination %d is NULL", i);
+    if (shard_count == 0 || shard_index >= shard_count) return fail(LUTGEN_ERR_INVALID, "shard %u of %u", shard_index, shard_count);
+    if (r->d.kind == LUTGEN_SAMPLING || r->d.kind == LUTGEN_BLUR)
+        return fail(LUTGEN_ERR_UNSUPPORTED, "multi-destination shards: RBF and NearestNeighbor remappers only (others: generate locally, then all-gather)");
+    if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33", level);
+    uint32_t side = (uint32_t)level * level * level;
+    Front f{};
+    f.out = luts_rgb_dev[0];
+    f.nextra = nluts - 1;
+    for (int i = 1; i < nluts; ++i) f.extra[i - 1] = luts_rgb_dev[i];
+    f.begin = 0;
+    f.count = (unsigned long long)side * side;
+    f.cs = (uint32_t)level * level;
+    f.csm1 = f.cs - 1;
+    f.shard_index = shard_index;
+    f.shard_count = shard_count;
+    return launch_remap<FRONT_LUT>(f, r, (cudaStream_t)stream);
+}
+
+// Barrier between the per-GPU processes of one node through flags in peer memory: rank r writes
+// `epoch` into slot r of every rank's flag array (release, system scope: everything this GPU wrote
+// before -- its rows in the peers' CLUT buffers -- is visible to whoever sees the flag) and waits
+// until all slots of its own array have reached `epoch`. A few microseconds, where an NCCL
+// barrier is a 40 us all-reduce.
+__global__ void k_peer_barrier(unsigned* const* flags, int nranks, int rank, unsigned epoch) {
+    const int t = threadIdx.x;
+    if (t >= nranks) return;
+    __threadfence_system();
+    unsigned* remote = flags[t] + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+    const unsigned* mine = flags[rank] + t;
+    unsigned v;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    } while ((int)(v - epoch) < 0);
+}
+
+int lutgen_cuda_peer_barrier_dev(unsigned* const* flags_dev_table, int nranks, int rank, unsigned epoch, void* stream) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!flags_dev_table || nranks < 1 || nranks > 1 + LUTGEN_MAX_PEERS || rank < 0 || rank >= nranks)
+        return fail(LUTGEN_ERR_INVALID, "peer barrier: %d ranks, rank %d", nranks, rank);
+    k_peer_barrier<<<1, 32, 0, (cudaStream_t)stream>>>(flags_dev_table, nranks, rank, epoch);
+    LAUNCH_CHECK();
+    return LUTGEN_OK;
+}
+
+// CUDA IPC: one process per GPU; a rank exports its CLUT buffer and maps the other ranks'.
+int lutgen_cuda_device_alloc(size_t bytes, void** out) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!out) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    CU_TRY(cudaMalloc(out, bytes ? bytes : 1));
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_device_free(void* p) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    CU_TRY(cudaFree(p));
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_ipc_export(void* dev_ptr, unsigned char handle[64]) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!dev_ptr || !handle) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle, &h, 64);
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_ipc_import(const unsigned char handle[64], void** dev_ptr_out) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!handle || !dev_ptr_out) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU_TRY(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_ipc_close(void* dev_ptr) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    CU_TRY(cudaIpcCloseMemHandle(dev_ptr));
     return LUTGEN_OK;
 }
 

@@ -11,6 +11,8 @@
 
 namespace lutgen {
 
+constexpr int LUTGEN_MAX_PEERS = 7;
+
 enum FrontMode { FRONT_LUT = 0, FRONT_IMAGE = 1, FRONT_TABLE = 2, FRONT_LIST = 3 };
 
 // Where a thread's colour comes from and where its result goes.
@@ -31,6 +33,14 @@ struct Front {
     const uint32_t* list;
     const uint32_t* list_count;
     int list_mode;
+    // FRONT_LUT only: further copies of the CLUT that receive every stored entry -- the other ranks'
+    // buffers, mapped into this process (CUDA IPC) and written over NVLink while the kernel runs
+    uint8_t* extra[LUTGEN_MAX_PEERS];
+    int nextra;
+    // FRONT_LUT only: this launch is shard `shard_index` of `shard_count` of the range. Kernels that
+    // walk tiles take every shard_count-th hand-out (balanced whatever the colours cost); the others
+    // are given the shard's contiguous rows instead (api.cu: rows_of_shard).
+    uint32_t shard_index, shard_count;
 };
 
 struct RemapParams {
@@ -88,6 +98,10 @@ __device__ __forceinline__ void front_store_mode(const Front& f, int mode, const
     } else {
         uint8_t* q = f.out + 3ull * p.slot;
         q[0] = (uint8_t)r; q[1] = (uint8_t)g; q[2] = (uint8_t)b;
+        for (int x = 0; x < f.nextra; ++x) {
+            uint8_t* qx = f.extra[x] + 3ull * p.slot;
+            qx[0] = (uint8_t)r; qx[1] = (uint8_t)g; qx[2] = (uint8_t)b;
+        }
     }
 }
 

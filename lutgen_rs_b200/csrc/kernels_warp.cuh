@@ -57,12 +57,15 @@ struct WarpArgs {
     uint32_t tiles_r, tiles_g;
     float inv_tiles_r, inv_tiles_g;
     uint32_t b_lo;            // first blue plane covered (multiple of EPT)
-    uint32_t ntiles;
+    uint32_t ntiles;          // tiles this launch walks (local numbering)
+    uint32_t ntiles_global;   // tiles of the whole range
+    uint32_t shard_index, shard_count;  // this launch takes hand-outs index, index + count, ... (1 hand-out = WT_BATCH warp tiles / 1 CTA tile)
     uint32_t* flag_list;
     uint32_t* flag_count;
     uint32_t* tile_counter;   // zeroed before the launch
     uint32_t* stats;
     const ColorTables* tables;
+    int words_ok;             // FRONT_LUT: cs % 4 == 0 and every destination 4-byte aligned -> whole tiles go out as words
 };
 
 typedef float2 f2;
@@ -423,13 +426,63 @@ struct WtClass {
     float lbmin, ubmin, ubmax_unc;
 };
 
+// Stores the lane's EPT results (packed r | g<<8 | b<<16; bit e of `smask`: entry e has one).
+// FRONT_LUT tiles that lie wholly inside the launch go through shared memory and leave as aligned
+// 32-bit words -- each (b, g) row of the tile is 8 entries = 24 contiguous bytes = 6 words -- to the
+// CLUT and to every extra destination (peer GPUs over NVLink: 24-byte runs instead of single bytes).
+// Entries without a result (flagged for the exact kernel, which runs afterwards on the same stream
+// and writes all destinations too) are sent as zeros in that case.
+template <int MODE, int EPT>
+__device__ __forceinline__ void wt_store(const WarpArgs& a, const WtTile<EPT>& T, const uint32_t (&res)[EPT], uint32_t smask, uint32_t* stage) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr bool BRICK = MODE != FRONT_IMAGE;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (MODE == FRONT_LUT) {
+        const bool whole = a.words_ok && __all_sync(FULL, T.valid_mask == (1u << EPT) - 1u);
+        if (whole) {
+            uint8_t* sb = reinterpret_cast<uint8_t*>(stage);
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const uint32_t v = ((smask >> e) & 1u) ? res[e] : 0u;
+                uint8_t* q = sb + ((e * 4u + (lane >> 3)) * 8u + (lane & 7u)) * 3u;
+                q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16);
+            }
+            __syncwarp();
+            const uint32_t flat0 = __shfl_sync(FULL, T.slot0, 0), cs = a.f.cs;
+#pragma unroll
+            for (int i = 0; i < (EPT * 4 * 6 + 31) / 32; ++i) {
+                const uint32_t wi = lane + 32u * i;          // word of the tile: row (e, g) = wi / 6
+                if (wi < (uint32_t)EPT * 24u) {
+                    const uint32_t row = (wi * 43u) >> 8, e = row >> 2, gi = row & 3u;   // wi / 6 for wi < 256
+                    const size_t off = 3ull * (flat0 + e * T.slot_step + gi * cs) + 4u * (wi - row * 6u);
+                    const uint32_t v = stage[wi];
+                    *reinterpret_cast<uint32_t*>(a.f.out + off) = v;
+                    for (int x = 0; x < a.f.nextra; ++x) *reinterpret_cast<uint32_t*>(a.f.extra[x] + off) = v;
+                }
+            }
+            return;
+        }
+    }
+    PixelIO px;
+    px.mode = MODE;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        if (!((smask >> e) & 1u)) continue;
+        px.slot = T.slot0 + e * T.slot_step;
+        px.r = px.g = px.b = 0;
+        front_store<MODE>(a.f, px, res[e] & 255u, (res[e] >> 8) & 255u, res[e] >> 16);
+    }
+    (void)BRICK;
+}
+
 // Step 5: everything per entry, given the candidate list.
 //   cand  : per-warp list (wt_list_entry of every listed colour), cidx: palette index of each
 //   hits  : packed sRGB of the palette colours that may equal a colour of the tile exactly
 template <int KIND, int MODE, int EPT>
 __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& st, const WtTile<EPT>& T, const WtClass& cl,
                                            const float4* __restrict__ cand, const uint32_t* __restrict__ cidx,
-                                           const uint32_t* __restrict__ hits) {
+                                           const uint32_t* __restrict__ hits, uint32_t* stage) {
     constexpr int NP = EPT / 2;
     constexpr bool BRICK = MODE != FRONT_IMAGE;
     const float c1 = a.c1;
@@ -452,8 +505,6 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
     if (KIND == 0 || KIND == KIND_NN) tol += WT_TIE_CONST;
     if (KIND == 0) tol *= -c1;
 
-    PixelIO px;
-    px.mode = MODE;
     if (all_exact) {
         if (T.valid_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, T.valid_mask, T.slot0, T.slot_step);
         return;
@@ -490,23 +541,24 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
                 if ((second[e] - best[e] <= tol) && (second[e] < INFINITY)) risky_mask |= 1u << e;
         }
         flag_mask = risky_mask & T.valid_mask;
+        uint32_t res[EPT];
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
+            res[e] = 0;
             if (!(((T.valid_mask & ~risky_mask) >> e) & 1u)) continue;
-            px.slot = T.slot0 + e * T.slot_step;
             const uint32_t idx = cidx[best_j[e]];
-            px.r = BRICK ? T.R : (T.Bq[e] & 255u); px.g = BRICK ? T.G : ((T.Bq[e] >> 8) & 255u); px.b = BRICK ? T.Bq[e] : (T.Bq[e] >> 16);
             if (!a.preserve) {
-                uint32_t q = a.pal_rgb[idx];
-                front_store<MODE>(a.f, px, q & 255u, (q >> 8) & 255u, (q >> 16) & 255u);
+                res[e] = a.pal_rgb[idx] & 0xffffffu;
             } else {
-                Lab ex = linear_to_oklab_exact(st.decode[px.r], st.decode[px.g], st.decode[px.b]);
+                const uint32_t pr = BRICK ? T.R : (T.Bq[e] & 255u), pg = BRICK ? T.G : ((T.Bq[e] >> 8) & 255u), pb = BRICK ? T.Bq[e] : (T.Bq[e] >> 16);
+                Lab ex = linear_to_oklab_exact(st.decode[pr], st.decode[pg], st.decode[pb]);
                 Lab o = {ex.l, a.pal_ab[2 * idx], a.pal_ab[2 * idx + 1]};
                 float r, g, b;
                 oklab_to_linear_exact(o, r, g, b);
-                front_store<MODE>(a.f, px, f32_to_srgb8(r, st.encode), f32_to_srgb8(g, st.encode), f32_to_srgb8(b, st.encode));
+                res[e] = f32_to_srgb8(r, st.encode) | (f32_to_srgb8(g, st.encode) << 8) | (f32_to_srgb8(b, st.encode) << 16);
             }
         }
+        wt_store<MODE, EPT>(a, T, res, T.valid_mask & ~risky_mask, stage);
         if (flag_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, flag_mask, T.slot0, T.slot_step);
         return;
     }
@@ -540,6 +592,7 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
         }
     }
     const float fs = KIND == 0 ? 0.5f / c1 : 1.0f;  // the Gaussian sums ran over -2C p = 2 c1 p
+    uint32_t res[EPT], smask = 0;
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
         const f2 d = den[i];
@@ -553,25 +606,27 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int e = 2 * i + h;
+            res[e] = 0;
             if (!((T.valid_mask >> e) & 1u)) continue;
-            px.slot = T.slot0 + e * T.slot_step;
-            px.r = BRICK ? T.R : (T.Bq[e] & 255u); px.g = BRICK ? T.G : ((T.Bq[e] >> 8) & 255u); px.b = BRICK ? T.Bq[e] : (T.Bq[e] >> 16);
+            const uint32_t pr = BRICK ? T.R : (T.Bq[e] & 255u), pg = BRICK ? T.G : ((T.Bq[e] >> 8) & 255u), pb = BRICK ? T.Bq[e] : (T.Bq[e] >> 16);
             // rbf.rs:66-68 palette.contains(&color): identical sRGB <=> identical Oklab triple
             if (nhit) {
-                const uint32_t packed = px.r | (px.g << 8) | (px.b << 16);
+                const uint32_t packed = pr | (pg << 8) | (pb << 16);
                 bool hit = false;
 #pragma unroll 1
                 for (uint32_t hh = 0; hh < nhit; ++hh) hit |= (hits[hh] == packed);
                 if (hit) {
-                    if (MODE != FRONT_IMAGE) front_store<MODE>(a.f, px, px.r, px.g, px.b);
+                    if (MODE != FRONT_IMAGE) { res[e] = packed; smask |= 1u << e; }  // images: the pixel stays as it is
                     continue;
                 }
             }
             if ((risky_mask >> e) & 1u) { flag_mask |= 1u << e; continue; }
-            front_store<MODE>(a.f, px, f32_to_srgb8(h ? r2.y : r2.x, st.encode), f32_to_srgb8(h ? g2.y : g2.x, st.encode),
-                              f32_to_srgb8(h ? b2.y : b2.x, st.encode));
+            res[e] = f32_to_srgb8(h ? r2.y : r2.x, st.encode) | (f32_to_srgb8(h ? g2.y : g2.x, st.encode) << 8) |
+                     (f32_to_srgb8(h ? b2.y : b2.x, st.encode) << 16);
+            smask |= 1u << e;
         }
     }
+    wt_store<MODE, EPT>(a, T, res, smask, stage);
     if (flag_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, flag_mask, T.slot0, T.slot_step);
 }
 
@@ -589,6 +644,7 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
     __shared__ __align__(8) float2 s_bnd[WT_WARPS][WT_MAX_N];
     __shared__ uint32_t s_cidx[WT_WARPS][WT_MAX_N];
     __shared__ uint32_t s_hit[WT_WARPS][FAST_MAX_HITS];
+    __shared__ uint32_t s_stage[WT_WARPS][EPT * 24];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n = a.n, k = a.k;
@@ -624,13 +680,15 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
         if (lane == 0) t0 = atomicAdd(a.tile_counter, (uint32_t)WT_BATCH);
         t0 = __shfl_sync(FULL, t0, 0);
         if (t0 >= a.ntiles) break;
+        if (a.shard_count > 1) t0 = ((t0 / (uint32_t)WT_BATCH) * a.shard_count + a.shard_index) * (uint32_t)WT_BATCH;
+        if (t0 >= a.ntiles_global) break;
         uint32_t ir = 0, ig = 0, ib = 0;
         if (BRICK) {
             uint32_t rest;
             wt_divmod(t0, a.tiles_r, a.inv_tiles_r, rest, ir);
             wt_divmod(rest, a.tiles_g, a.inv_tiles_g, ib, ig);
         }
-        const uint32_t t1 = min(t0 + (uint32_t)WT_BATCH, a.ntiles);
+        const uint32_t t1 = min(t0 + (uint32_t)WT_BATCH, a.ntiles_global);
 #pragma unroll 1
         for (uint32_t t = t0; t < t1; ++t) {
             // ---- 1. colours of this tile -> Oklab (register pairs), bounding box ----------------
@@ -713,7 +771,7 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
                 atomicAdd(&a.stats[64 + min(cl.nin, 63u)], 1u);
             }
             // ---- 5. per entry ------------------------------------------------------------------
-            wt_entries<KIND, MODE, EPT>(a, st, T, cl, cand, cidx, hits);
+            wt_entries<KIND, MODE, EPT>(a, st, T, cl, cand, cidx, hits, s_stage[warp]);
         }
     }
 }
@@ -751,6 +809,7 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp_big(const Wa
     __shared__ uint32_t s_sidx[WB_MAX_N];               // their palette indices
     __shared__ uint32_t s_srgb[WB_MAX_N];               // their packed sRGB
     __shared__ uint32_t s_hit[FAST_MAX_HITS];
+    __shared__ uint32_t s_stage[WT_WARPS][EPT * 24];
     __shared__ float s_wbox[WT_WARPS][6];
     __shared__ uint32_t s_wsrgb[WT_WARPS][6];
     __shared__ float s_cbox[6];
@@ -792,8 +851,10 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp_big(const Wa
         if (tid == 0) s_tile = atomicAdd(a.tile_counter, 1u);
         if (tid < 4) s_red[tid] = tid == 1 ? 0u : (tid == 3 ? 0u : 0x7f800000u);
         __syncthreads();
-        const uint32_t ct = s_tile;
+        uint32_t ct = s_tile;
         if (ct >= a.ntiles) break;
+        ct = ct * a.shard_count + a.shard_index;
+        if (ct >= a.ntiles_global) break;
 
         // ---- 1. every warp converts its tile; boxes of the eight tiles -> CTA box ------------------
         WtTile<EPT> T;
@@ -1006,7 +1067,7 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp_big(const Wa
             atomicAdd(&a.stats[64 + min(cl.nin, 63u)], 1u);
         }
         // ---- 4. per entry ----------------------------------------------------------------------
-        wt_entries<KIND, MODE, EPT>(a, st, T, cl, cand, cidx, s_hit);
+        wt_entries<KIND, MODE, EPT>(a, st, T, cl, cand, cidx, s_hit, s_stage[warp]);
     }
 }
 

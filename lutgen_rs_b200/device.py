@@ -8,6 +8,9 @@ Multi-GPU model: one process per GPU.
   * LUT generation shards the level^3 x level^3 CLUT by ROWS; every rank writes
     its rows at their place in a full-size buffer and one in-place NCCL
     all-gather over NVLink assembles the CLUT on every rank.
+    `generate_lut_fused` is the fused form: every rank's kernel writes its rows straight into ALL
+    ranks' buffers (CUDA IPC mappings, stores over NVLink while it computes) and a barrier replaces
+    the collective.
   * LUT application / direct remap shard FRAMES; no collective is needed.
 """
 import os
@@ -101,6 +104,119 @@ def generate_lut(remapper, level, group=None, stream=None, out=None):
         generate_lut_rows_(remapper, level, flat, r0, r1, stream)
 
     return sharded_rows_all_gather(side, compute_rows, out=out, group=group, device="cuda")
+
+
+class _RawCuda:
+    """A raw device allocation as a zero-copy torch tensor (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerLut:
+    """One CLUT-sized buffer per rank, each mapped into every other rank's process (CUDA IPC), in two
+    copies used alternately (a rank may still be reading step i's CLUT when another rank starts
+    writing step i + 1's), plus a flag array per rank for the peer-memory barrier. Collective: every
+    rank of `group` must construct it at the same time."""
+
+    MAX_WORLD = 8  # 1 + LUTGEN_MAX_PEERS destinations per launch
+    FLAG_BYTES = 256
+
+    def __init__(self, nbytes, group=None):
+        import ctypes as C
+
+        import torch.distributed as dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > self.MAX_WORLD:
+            raise ValueError(f"at most {self.MAX_WORLD} ranks")
+        self.nbytes = int(nbytes)
+        self._lut_bytes = (self.nbytes + 255) // 256 * 256   # flags follow the CLUT, 256-byte aligned
+        L = _native.lib()
+        self._own, self._ptrs, self._imported = [], [], []
+        for _ in range(2):
+            p = C.c_void_p()
+            _native.check(L.lutgen_cuda_device_alloc(self._lut_bytes + self.FLAG_BYTES, C.byref(p)))
+            self._own.append(p.value)
+            torch.as_tensor(_RawCuda(p.value + self._lut_bytes, self.FLAG_BYTES), device="cuda").zero_()
+            handle = (C.c_uint8 * 64)()
+            _native.check(L.lutgen_cuda_ipc_export(C.c_void_p(p.value), C.cast(handle, C.c_void_p)))
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+            allh = torch.empty(self.world * 64, dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(allh, mine, group=group)
+            allh = allh.cpu().numpy().reshape(self.world, 64)
+            ptrs = []
+            for r in range(self.world):
+                if r == self.rank:
+                    ptrs.append(p.value)
+                    continue
+                h = (C.c_uint8 * 64)(*allh[r].tolist())
+                q = C.c_void_p()
+                _native.check(L.lutgen_cuda_ipc_import(C.cast(h, C.c_void_p), C.byref(q)))
+                self._imported.append(q.value)
+                ptrs.append(q.value)
+            self._ptrs.append(ptrs)
+        self.tensors = [torch.as_tensor(_RawCuda(p, self.nbytes), device="cuda") for p in self._own]
+        # the barrier uses the flag arrays of copy 0 throughout: device table of their addresses, by rank
+        self._flag_table = torch.tensor([q + self._lut_bytes for q in self._ptrs[0]], dtype=torch.int64, device="cuda")
+        self._epoch = 0
+        self._turn = 0
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+
+    def next(self):
+        """(tensor of this rank's buffer, ctypes array of all ranks' pointers, own first) for the next step."""
+        import ctypes as C
+        i = self._turn
+        self._turn ^= 1
+        ptrs = self._ptrs[i]
+        order = [ptrs[self.rank]] + [ptrs[r] for r in range(self.world) if r != self.rank]
+        return self.tensors[i], (C.c_void_p * len(order))(*order)
+
+    def barrier(self, stream=None):
+        """All ranks' earlier writes into the peer buffers are complete and visible after this."""
+        self._epoch += 1
+        _native.check(_native.lib().lutgen_cuda_peer_barrier_dev(self._flag_table.data_ptr(), self.world, self.rank,
+                                                                  self._epoch & 0xFFFFFFFF, _stream(stream)))
+
+    def close(self):
+        import ctypes as C
+        L = _native.lib()
+        self.tensors = []
+        self._flag_table = None
+        for q in self._imported:
+            L.lutgen_cuda_ipc_close(C.c_void_p(q))
+        self._imported = []
+        for p in self._own:
+            L.lutgen_cuda_device_free(C.c_void_p(p))
+        self._own = []
+
+
+_peer_luts = {}
+
+
+def generate_lut_fused(remapper, level, group=None, stream=None):
+    """Sharded generation with the exchange fused into the kernel: each rank computes its share of
+    the tiles (every world-th hand-out: balanced) and stores the results into EVERY rank's buffer over
+    NVLink while it computes (lutgen_cuda_generate_lut_shard_multi_dev); a barrier through flags in
+    peer memory then makes the whole CLUT valid on every rank. Returns a (side, side, 3) uint8 CUDA
+    tensor that stays valid until the second next call. Falls back to `generate_lut` (all-gather)
+    for remappers the fused entry point does not take, and for a single rank."""
+    import torch.distributed as dist
+    level = int(level)
+    side = level ** 3
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if world == 1 or world > PeerLut.MAX_WORLD or remapper._kind in (_native.SAMPLING, _native.BLUR):
+        return generate_lut(remapper, level, group=group, stream=stream)
+    key = (side, id(group))
+    peers = _peer_luts.get(key)
+    if peers is None:
+        peers = _peer_luts[key] = PeerLut(3 * side * side, group)
+    mine, ptrs = peers.next()
+    _native.check(_native.lib().lutgen_cuda_generate_lut_shard_multi_dev(remapper._h, level, ptrs, len(ptrs), peers.rank, world, _stream(stream)))
+    peers.barrier(stream)
+    return mine.view(side, side, 3)
 
 
 def apply_hald_(rgba, lut, level, stream=None):
