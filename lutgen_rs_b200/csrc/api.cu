@@ -330,6 +330,8 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
         uintptr_t bits = reinterpret_cast<uintptr_t>(f.out);
         for (int x = 0; x < f.nextra; ++x) bits |= reinterpret_cast<uintptr_t>(f.extra[x]);
         a.words_ok = (bits & 3u) == 0;
+        if (a.words_ok && (bits & 15u) == 0) a.words_ok = 2;   // 16-byte stores of whole hand-outs possible
+        if (const char* e = getenv("LUTGEN_CUDA_STORE")) a.words_ok = std::min(a.words_ok, atoi(e));  // 0 bytes, 1 tile words, 2 hand-out rows
     }
     // BIG: the CTA's eight warp tiles form one 16 x 8 x 2 EPT CTA tile (or 256 EPT pixels)
     const uint32_t tr = BIG ? 16 : 8, tg = BIG ? 8 : 4, tb = BIG ? 2 * EPT : EPT, tpix = (BIG ? 256u : 32u) * EPT;
@@ -363,18 +365,32 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
             return LUTGEN_OK;
         }
     }
-    static int per_sm = 0;  // one per instantiation
-    if (per_sm == 0) {
-        if (BIG) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_remap_warp_big<KIND, MODE, EPT>, WT_THREADS, 0));
-        else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_remap_warp<KIND, MODE, EPT>, WT_THREADS, 0));
-        if (per_sm < 1) per_sm = 1;
+    // MULTI: the variant that stages tiles and writes them to several destinations (multi-GPU); a single
+    // destination takes the leaner kernel (the extra code costs instruction-cache misses)
+    const bool multi = MODE == FRONT_LUT && f.nextra > 0;
+    static int per_sm[2] = {0, 0};  // per instantiation
+    if (per_sm[multi] == 0) {
+        int v = 0;
+        if (BIG) {
+            if (multi) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp_big<KIND, MODE, EPT, MODE == FRONT_LUT>, WT_THREADS, 0));
+            else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp_big<KIND, MODE, EPT, false>, WT_THREADS, 0));
+        } else {
+            if (multi) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, MODE == FRONT_LUT>, WT_THREADS, 0));
+            else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, false>, WT_THREADS, 0));
+        }
+        per_sm[multi] = v < 1 ? 1 : v;
     }
-    unsigned grid = (unsigned)per_sm * (unsigned)g.sm_count;
+    unsigned grid = (unsigned)per_sm[multi] * (unsigned)g.sm_count;
     unsigned need = BIG ? a.ntiles : blocks_for(a.ntiles, WT_WARPS * WT_BATCH);
     if (grid > need) grid = need;
     CU_TRY(cudaMemsetAsync(r->flag_count, 0, 2 * sizeof(uint32_t), s));
-    if (BIG) k_remap_warp_big<KIND, MODE, EPT><<<grid, WT_THREADS, 0, s>>>(a);
-    else k_remap_warp<KIND, MODE, EPT><<<grid, WT_THREADS, 0, s>>>(a);
+    if (BIG) {
+        if (multi) k_remap_warp_big<KIND, MODE, EPT, MODE == FRONT_LUT><<<grid, WT_THREADS, 0, s>>>(a);
+        else k_remap_warp_big<KIND, MODE, EPT, false><<<grid, WT_THREADS, 0, s>>>(a);
+    } else {
+        if (multi) k_remap_warp<KIND, MODE, EPT, MODE == FRONT_LUT><<<grid, WT_THREADS, 0, s>>>(a);
+        else k_remap_warp<KIND, MODE, EPT, false><<<grid, WT_THREADS, 0, s>>>(a);
+    }
     LAUNCH_CHECK();
     return LUTGEN_OK;
 }

@@ -98,7 +98,9 @@ __device__ __forceinline__ void front_store_mode(const Front& f, int mode, const
     } else {
         uint8_t* q = f.out + 3ull * p.slot;
         q[0] = (uint8_t)r; q[1] = (uint8_t)g; q[2] = (uint8_t)b;
-        for (int x = 0; x < f.nextra; ++x) {
+#pragma unroll
+        for (int x = 0; x < LUTGEN_MAX_PEERS; ++x) {  // static indices: a dynamic one would move the whole parameter block to local memory
+            if (x >= f.nextra) break;
             uint8_t* qx = f.extra[x] + 3ull * p.slot;
             qx[0] = (uint8_t)r; qx[1] = (uint8_t)g; qx[2] = (uint8_t)b;
         }

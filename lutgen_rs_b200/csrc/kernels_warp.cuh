@@ -65,7 +65,8 @@ struct WarpArgs {
     uint32_t* tile_counter;   // zeroed before the launch
     uint32_t* stats;
     const ColorTables* tables;
-    int words_ok;             // FRONT_LUT: cs % 4 == 0 and every destination 4-byte aligned -> whole tiles go out as words
+    int words_ok;             // FRONT_LUT, cs % 4 == 0: 1 = destinations 4-byte aligned (whole tiles leave as words),
+                              // 2 = 16-byte aligned (whole hand-outs leave as 16-byte pieces), 0 = byte stores
 };
 
 typedef float2 f2;
@@ -426,63 +427,147 @@ struct WtClass {
     float lbmin, ubmin, ubmax_unc;
 };
 
+// Where a tile's staged bytes go: a per-warp shared-memory image of `pitch` bytes per (b, g) row.
+// slot = the tile's place in a hand-out of WT_BATCH tiles that are consecutive in r (its 24 bytes of
+// every row start at byte 24 * slot); defer = the caller writes the hand-out's rows out in one go
+// (wt_flush_batch) instead of tile by tile.
+struct WtStage {
+    uint8_t* const* extras;   // shared-memory copy of Front::extra (a dynamic index into the kernel parameters would move them to local memory)
+    uint32_t* buf;
+    uint32_t pitch;   // bytes per row: 24 (one tile) or 24 * WT_BATCH
+    uint32_t slot;
+    bool defer;
+    uint32_t staged;  // out: bit `slot` set when the tile was staged and its store deferred
+};
+
+// One tile's rows (24 bytes each) from the staging image to the CLUT and every extra destination,
+// as aligned 32-bit words.
+template <int EPT>
+__device__ __noinline__ void wt_flush_tile(uint8_t* out, uint8_t* const* extras, int nextra, uint32_t cs, const uint32_t* stage, uint32_t pitch,
+                                           uint32_t slot, uint32_t flat0, uint32_t slot_step) {
+    const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int i = 0; i < (EPT * 4 * 6 + 31) / 32; ++i) {
+        const uint32_t wi = lane + 32u * i;          // word of the tile: row (e, g) = wi / 6
+        if (wi < (uint32_t)EPT * 24u) {
+            const uint32_t row = (wi * 43u) >> 8, e = row >> 2, gi = row & 3u, q = wi - row * 6u;   // wi / 6 for wi < 256
+            const size_t off = 3ull * (flat0 + e * slot_step + gi * cs) + 4u * q;
+            const uint32_t v = stage[(row * pitch + slot * 24u) / 4u + q];
+            *reinterpret_cast<uint32_t*>(out + off) = v;
+#pragma unroll 1
+            for (int x = 0; x < nextra; ++x) *reinterpret_cast<uint32_t*>(extras[x] + off) = v;
+        }
+    }
+}
+
+// A whole hand-out (WT_BATCH tiles consecutive in r, all staged): every (b, g) row is 96 contiguous
+// bytes = six 16-byte stores per destination -- the unit in which the rows travel to the peer GPUs.
+template <int EPT>
+__device__ __noinline__ void wt_flush_batch(uint8_t* out, uint8_t* const* extras, int nextra, uint32_t cs, const uint32_t* stage, uint32_t flat0,
+                                            uint32_t slot_step) {
+    const uint32_t lane = threadIdx.x & 31u;
+    constexpr uint32_t ROW16 = 24u * WT_BATCH / 16u;   // 16-byte pieces per row
+#pragma unroll
+    for (int i = 0; i < (EPT * 4 * (int)ROW16 + 31) / 32; ++i) {
+        const uint32_t wi = lane + 32u * i;
+        if (wi < (uint32_t)EPT * 4u * ROW16) {
+            const uint32_t row = wi / ROW16, e = row >> 2, gi = row & 3u, q = wi - row * ROW16;
+            const size_t off = 3ull * (flat0 + e * slot_step + gi * cs) + 16u * q;
+            const uint4 v = reinterpret_cast<const uint4*>(stage)[wi];
+            *reinterpret_cast<uint4*>(out + off) = v;
+#pragma unroll 1
+            for (int x = 0; x < nextra; ++x) *reinterpret_cast<uint4*>(extras[x] + off) = v;
+        }
+    }
+}
+
+// Entry-by-entry stores of one lane's four results (tiles cut by the launch's range or by the cube's
+// edge, images, the table front end). Out of line: with up to eight destinations the byte stores
+// are a few hundred instructions that whole tiles never execute.
+template <int MODE>
+__device__ __noinline__ void wt_store_entries(uint8_t* out, uint8_t* const* extras, int nextra, uint32_t slot0, uint32_t slot_step, uint32_t smask,
+                                              uint4 res) {
+    const uint32_t v[4] = {res.x, res.y, res.z, res.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        if (!((smask >> e) & 1u)) continue;
+        const uint32_t slot = slot0 + e * slot_step;
+        if (MODE == FRONT_TABLE) {
+            reinterpret_cast<uint32_t*>(out)[slot] = v[e];
+        } else if (MODE == FRONT_IMAGE) {
+            uchar4* q = reinterpret_cast<uchar4*>(out) + slot;   // alpha stays (mod.rs:30-50 writes bytes 0..3)
+            uchar4 px = *q;
+            px.x = (unsigned char)v[e]; px.y = (unsigned char)(v[e] >> 8); px.z = (unsigned char)(v[e] >> 16);
+            *q = px;
+        } else {
+            uint8_t* q = out + 3ull * slot;
+            q[0] = (uint8_t)v[e]; q[1] = (uint8_t)(v[e] >> 8); q[2] = (uint8_t)(v[e] >> 16);
+#pragma unroll 1
+            for (int x = 0; x < nextra; ++x) {
+                uint8_t* qx = extras[x] + 3ull * slot;
+                qx[0] = (uint8_t)v[e]; qx[1] = (uint8_t)(v[e] >> 8); qx[2] = (uint8_t)(v[e] >> 16);
+            }
+        }
+    }
+}
+
 // Stores the lane's EPT results (packed r | g<<8 | b<<16; bit e of `smask`: entry e has one).
 // FRONT_LUT tiles that lie wholly inside the launch go through shared memory and leave as aligned
-// 32-bit words -- each (b, g) row of the tile is 8 entries = 24 contiguous bytes = 6 words -- to the
-// CLUT and to every extra destination (peer GPUs over NVLink: 24-byte runs instead of single bytes).
+// words -- each (b, g) row of a tile is 8 entries = 24 contiguous bytes -- to the CLUT and to every
+// extra destination (peer GPUs over NVLink: runs of 24 or 96 bytes instead of single bytes).
 // Entries without a result (flagged for the exact kernel, which runs afterwards on the same stream
 // and writes all destinations too) are sent as zeros in that case.
-template <int MODE, int EPT>
-__device__ __forceinline__ void wt_store(const WarpArgs& a, const WtTile<EPT>& T, const uint32_t (&res)[EPT], uint32_t smask, uint32_t* stage) {
+template <int MODE, int EPT, bool MULTI>
+__device__ __forceinline__ void wt_store(const WarpArgs& a, const WtTile<EPT>& T, const uint32_t (&res)[EPT], uint32_t smask, WtStage& sg) {
     constexpr uint32_t FULL = 0xffffffffu;
-    constexpr bool BRICK = MODE != FRONT_IMAGE;
     const uint32_t lane = threadIdx.x & 31u;
+    if (!MULTI) {
+        // one destination: plain stores, entry by entry (the CLUT stays in L2, which merges the bytes)
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            if (!((smask >> e) & 1u)) continue;
+            const uint32_t slot = T.slot0 + e * T.slot_step, v = res[e];
+            if (MODE == FRONT_TABLE) {
+                reinterpret_cast<uint32_t*>(a.f.out)[slot] = v;
+            } else if (MODE == FRONT_IMAGE) {
+                uchar4* q = reinterpret_cast<uchar4*>(a.f.out) + slot;   // alpha stays (mod.rs:30-50 writes bytes 0..3)
+                uchar4 px = *q;
+                px.x = (unsigned char)v; px.y = (unsigned char)(v >> 8); px.z = (unsigned char)(v >> 16);
+                *q = px;
+            } else {
+                uint8_t* q = a.f.out + 3ull * slot;
+                q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16);
+            }
+        }
+        return;
+    }
     if (MODE == FRONT_LUT) {
         const bool whole = a.words_ok && __all_sync(FULL, T.valid_mask == (1u << EPT) - 1u);
         if (whole) {
-            uint8_t* sb = reinterpret_cast<uint8_t*>(stage);
-            __syncwarp();
+            uint8_t* sb = reinterpret_cast<uint8_t*>(sg.buf);
+            if (!sg.defer) __syncwarp();   // the previous tile's words have been read
 #pragma unroll
             for (int e = 0; e < EPT; ++e) {
                 const uint32_t v = ((smask >> e) & 1u) ? res[e] : 0u;
-                uint8_t* q = sb + ((e * 4u + (lane >> 3)) * 8u + (lane & 7u)) * 3u;
+                uint8_t* q = sb + (e * 4u + (lane >> 3)) * sg.pitch + sg.slot * 24u + (lane & 7u) * 3u;
                 q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16);
             }
+            if (sg.defer) { sg.staged |= 1u << sg.slot; return; }
             __syncwarp();
-            const uint32_t flat0 = __shfl_sync(FULL, T.slot0, 0), cs = a.f.cs;
-#pragma unroll
-            for (int i = 0; i < (EPT * 4 * 6 + 31) / 32; ++i) {
-                const uint32_t wi = lane + 32u * i;          // word of the tile: row (e, g) = wi / 6
-                if (wi < (uint32_t)EPT * 24u) {
-                    const uint32_t row = (wi * 43u) >> 8, e = row >> 2, gi = row & 3u;   // wi / 6 for wi < 256
-                    const size_t off = 3ull * (flat0 + e * T.slot_step + gi * cs) + 4u * (wi - row * 6u);
-                    const uint32_t v = stage[wi];
-                    *reinterpret_cast<uint32_t*>(a.f.out + off) = v;
-                    for (int x = 0; x < a.f.nextra; ++x) *reinterpret_cast<uint32_t*>(a.f.extra[x] + off) = v;
-                }
-            }
+            wt_flush_tile<EPT>(a.f.out, sg.extras, a.f.nextra, a.f.cs, sg.buf, sg.pitch, sg.slot, __shfl_sync(FULL, T.slot0, 0), T.slot_step);
             return;
         }
     }
-    PixelIO px;
-    px.mode = MODE;
-#pragma unroll
-    for (int e = 0; e < EPT; ++e) {
-        if (!((smask >> e) & 1u)) continue;
-        px.slot = T.slot0 + e * T.slot_step;
-        px.r = px.g = px.b = 0;
-        front_store<MODE>(a.f, px, res[e] & 255u, (res[e] >> 8) & 255u, res[e] >> 16);
-    }
-    (void)BRICK;
+    if (EPT == 4) wt_store_entries<MODE>(a.f.out, sg.extras, a.f.nextra, T.slot0, T.slot_step, smask, make_uint4(res[0], res[1], res[2], res[3]));
 }
 
 // Step 5: everything per entry, given the candidate list.
 //   cand  : per-warp list (wt_list_entry of every listed colour), cidx: palette index of each
 //   hits  : packed sRGB of the palette colours that may equal a colour of the tile exactly
-template <int KIND, int MODE, int EPT>
+template <int KIND, int MODE, int EPT, bool MULTI>
 __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& st, const WtTile<EPT>& T, const WtClass& cl,
                                            const float4* __restrict__ cand, const uint32_t* __restrict__ cidx,
-                                           const uint32_t* __restrict__ hits, uint32_t* stage) {
+                                           const uint32_t* __restrict__ hits, WtStage& stage) {
     constexpr int NP = EPT / 2;
     constexpr bool BRICK = MODE != FRONT_IMAGE;
     const float c1 = a.c1;
@@ -558,7 +643,7 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
                 res[e] = f32_to_srgb8(r, st.encode) | (f32_to_srgb8(g, st.encode) << 8) | (f32_to_srgb8(b, st.encode) << 16);
             }
         }
-        wt_store<MODE, EPT>(a, T, res, T.valid_mask & ~risky_mask, stage);
+        wt_store<MODE, EPT, MULTI>(a, T, res, T.valid_mask & ~risky_mask, stage);
         if (flag_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, flag_mask, T.slot0, T.slot_step);
         return;
     }
@@ -626,15 +711,15 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
             smask |= 1u << e;
         }
     }
-    wt_store<MODE, EPT>(a, T, res, smask, stage);
+    wt_store<MODE, EPT, MULTI>(a, T, res, smask, stage);
     if (flag_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, flag_mask, T.slot0, T.slot_step);
 }
 
 // ---------------------------------------------------------------------------------------------
 // Palettes of at most 32 colours: every warp on its own, one palette colour per lane.
-template <int KIND, int MODE, int EPT>
+template <int KIND, int MODE, int EPT, bool MULTI>
 __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpArgs a) {
-    static_assert(EPT % 2 == 0, "entries are processed in pairs");
+    static_assert(EPT == 4, "entries are processed in two pairs (wt_store_entries takes four results)");
     constexpr uint32_t FULL = 0xffffffffu;
     constexpr bool BRICK = MODE != FRONT_IMAGE;
     __shared__ SmemTables st;
@@ -644,7 +729,8 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
     __shared__ __align__(8) float2 s_bnd[WT_WARPS][WT_MAX_N];
     __shared__ uint32_t s_cidx[WT_WARPS][WT_MAX_N];
     __shared__ uint32_t s_hit[WT_WARPS][FAST_MAX_HITS];
-    __shared__ uint32_t s_stage[WT_WARPS][EPT * 24];
+    __shared__ __align__(16) uint32_t s_stage[MULTI ? WT_WARPS : 1][MULTI ? EPT * 24 * WT_BATCH : 1];
+    __shared__ uint8_t* s_extra[LUTGEN_MAX_PEERS];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n = a.n, k = a.k;
@@ -656,6 +742,10 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
 #pragma unroll 1
         for (uint32_t v = tid; v < cs; v += WT_THREADS) s_chv[v] = (uint8_t)(MODE == FRONT_TABLE ? v : hald_channel(v, csm1));
     }
+    if (tid == 0) {
+#pragma unroll
+        for (int x = 0; x < LUTGEN_MAX_PEERS; ++x) s_extra[x] = a.f.extra[x];
+    }
     stage_tables(st, a.tables);  // ends with __syncthreads()
     if (BRICK) {
 #pragma unroll 1
@@ -664,6 +754,9 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
     }
     WtShared sh;
     sh.st = &st; sh.lin = s_lin; sh.chv = s_chv;
+    // FRONT_LUT: a hand-out of WT_BATCH tiles is one run of 8 * WT_BATCH entries per (b, g) row when the
+    // tile rows hold a multiple of WT_BATCH tiles; with cs % 16 == 0 those runs are 16-byte aligned
+    const bool batch_rows = MULTI && a.words_ok == 2 && (cs & 15u) == 0 && (a.tiles_r % (uint32_t)WT_BATCH) == 0;
 
     // this lane's palette colour
     const bool active = lane < n;
@@ -689,10 +782,19 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
             wt_divmod(rest, a.tiles_g, a.inv_tiles_g, ib, ig);
         }
         const uint32_t t1 = min(t0 + (uint32_t)WT_BATCH, a.ntiles_global);
+        WtStage sg;
+        sg.extras = s_extra;
+        sg.buf = s_stage[MULTI ? warp : 0];
+        sg.defer = batch_rows && t1 - t0 == (uint32_t)WT_BATCH;
+        sg.pitch = sg.defer ? 24u * WT_BATCH : 24u;
+        sg.staged = 0;
+        uint32_t batch_flat0 = 0, batch_step = 0;
+        __syncwarp();  // the previous hand-out's staged rows have been read
 #pragma unroll 1
         for (uint32_t t = t0; t < t1; ++t) {
             // ---- 1. colours of this tile -> Oklab (register pairs), bounding box ----------------
             WtTile<EPT> T;
+            sg.slot = sg.defer ? t - t0 : 0u;
             if (BRICK) {
                 const uint32_t r0 = ir * 8u, g0 = ig * 4u, b0 = a.b_lo + ib * (uint32_t)EPT;
                 if (++ir == a.tiles_r) { ir = 0; if (++ig == a.tiles_g) { ig = 0; ++ib; } }
@@ -771,7 +873,24 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
                 atomicAdd(&a.stats[64 + min(cl.nin, 63u)], 1u);
             }
             // ---- 5. per entry ------------------------------------------------------------------
-            wt_entries<KIND, MODE, EPT>(a, st, T, cl, cand, cidx, hits, s_stage[warp]);
+            if (MULTI && t == t0) { batch_flat0 = __shfl_sync(FULL, T.slot0, 0); batch_step = T.slot_step; }
+            wt_entries<KIND, MODE, EPT, MULTI>(a, st, T, cl, cand, cidx, hits, sg);
+        }
+        if (MULTI && sg.staged) {
+            __syncwarp();
+            if (sg.staged == (1u << WT_BATCH) - 1u) {
+                wt_flush_batch<EPT>(a.f.out, sg.extras, a.f.nextra, cs, sg.buf, batch_flat0, batch_step);
+            } else {
+                // some tiles of the hand-out went out entry by entry (or were skipped): the staged ones go tile by tile.
+                // batch_flat0 is the first tile's origin only if that tile reached step 5; recompute from the tile number
+                uint32_t rest, ir0, ig0, ib0;
+                wt_divmod(t0, a.tiles_r, a.inv_tiles_r, rest, ir0);
+                wt_divmod(rest, a.tiles_g, a.inv_tiles_g, ib0, ig0);
+                const uint32_t flat_first = ((a.b_lo + ib0 * (uint32_t)EPT) * cs + ig0 * 4u) * cs + ir0 * 8u;
+#pragma unroll 1
+                for (uint32_t sl = 0; sl < (uint32_t)WT_BATCH; ++sl)
+                    if ((sg.staged >> sl) & 1u) wt_flush_tile<EPT>(a.f.out, sg.extras, a.f.nextra, cs, sg.buf, sg.pitch, sl, flat_first + 8u * sl, cs * cs);
+            }
         }
     }
 }
@@ -793,7 +912,7 @@ constexpr int WB_MAX_N = 256;    // one palette colour per thread
 constexpr int WB_MAX_M = 128;    // survivors a warp can classify (4 per lane); beyond: exact kernel
 constexpr int WB_BISECT = 12;
 
-template <int KIND, int MODE, int EPT>
+template <int KIND, int MODE, int EPT, bool MULTI>
 __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp_big(const WarpArgs a) {
     static_assert(EPT % 2 == 0, "entries are processed in pairs");
     constexpr uint32_t FULL = 0xffffffffu;
@@ -809,7 +928,8 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp_big(const Wa
     __shared__ uint32_t s_sidx[WB_MAX_N];               // their palette indices
     __shared__ uint32_t s_srgb[WB_MAX_N];               // their packed sRGB
     __shared__ uint32_t s_hit[FAST_MAX_HITS];
-    __shared__ uint32_t s_stage[WT_WARPS][EPT * 24];
+    __shared__ uint32_t s_stage[MULTI ? WT_WARPS : 1][MULTI ? EPT * 24 : 1];
+    __shared__ uint8_t* s_extra[LUTGEN_MAX_PEERS];
     __shared__ float s_wbox[WT_WARPS][6];
     __shared__ uint32_t s_wsrgb[WT_WARPS][6];
     __shared__ float s_cbox[6];
@@ -827,6 +947,10 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp_big(const Wa
     if (BRICK) {
 #pragma unroll 1
         for (uint32_t v = tid; v < cs; v += WT_THREADS) s_chv[v] = (uint8_t)(MODE == FRONT_TABLE ? v : hald_channel(v, csm1));
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int x = 0; x < LUTGEN_MAX_PEERS; ++x) s_extra[x] = a.f.extra[x];
     }
     stage_tables(st, a.tables);  // ends with __syncthreads()
     if (BRICK) {
@@ -1067,7 +1191,14 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp_big(const Wa
             atomicAdd(&a.stats[64 + min(cl.nin, 63u)], 1u);
         }
         // ---- 4. per entry ----------------------------------------------------------------------
-        wt_entries<KIND, MODE, EPT>(a, st, T, cl, cand, cidx, s_hit, s_stage[warp]);
+        WtStage sg;
+        sg.extras = s_extra;
+        sg.buf = s_stage[MULTI ? warp : 0];
+        sg.pitch = 24u;
+        sg.slot = 0;
+        sg.defer = false;
+        sg.staged = 0;
+        wt_entries<KIND, MODE, EPT, MULTI>(a, st, T, cl, cand, cidx, s_hit, sg);
     }
 }
 
