@@ -165,6 +165,14 @@ LUTGEN_API int lutgen_cuda_generate_lut_rows_multi_dev(const lutgen_remapper* r,
 LUTGEN_API int lutgen_cuda_generate_lut_shard_multi_dev(const lutgen_remapper* r, uint8_t level, uint8_t* const* luts_rgb_dev, int nluts,
                                                         uint32_t shard_index, uint32_t shard_count, void* stream);
 
+/* The same with the destinations ALSO mapped as one NVSwitch multicast address (`multicast_lut`, e.g. from
+ * torch's symmetric memory; NULL = none): whole tiles are stored once to that address and the switch
+ * replicates them to every GPU, so a rank sends its share of the CLUT once instead of once per peer. Entries
+ * that are stored byte by byte (tiles cut by the cube's edge, entries recomputed by the exact kernel) still
+ * go to each of luts_rgb_dev[]. */
+LUTGEN_API int lutgen_cuda_generate_lut_shard_mc_dev(const lutgen_remapper* r, uint8_t level, uint8_t* const* luts_rgb_dev, int nluts,
+                                                     uint8_t* multicast_lut, uint32_t shard_index, uint32_t shard_count, void* stream);
+
 /* Barrier between the per-GPU processes through flags in peer memory. flags_dev_table: DEVICE array of
  * nranks pointers, entry i = rank i's flag array (>= nranks zero-initialised u32, mapped into this process);
  * epoch must grow by one per barrier. Orders this GPU's earlier writes to peer buffers before the peers'

@@ -27,7 +27,7 @@ EXPORTS = [
     "lutgen_cuda_srgb_to_oklab_fast", "lutgen_cuda_debug_stats",
     "lutgen_cuda_generate_lut_rows_multi_dev", "lutgen_cuda_device_alloc", "lutgen_cuda_device_free",
     "lutgen_cuda_ipc_export", "lutgen_cuda_ipc_import", "lutgen_cuda_ipc_close",
-    "lutgen_cuda_generate_lut_shard_multi_dev", "lutgen_cuda_peer_barrier_dev",
+    "lutgen_cuda_generate_lut_shard_multi_dev", "lutgen_cuda_peer_barrier_dev", "lutgen_cuda_generate_lut_shard_mc_dev",
 ]
 
 
@@ -108,6 +108,7 @@ def load():
             "lutgen_cuda_measure_peaks": ([C.POINTER(C.c_double), C.POINTER(C.c_double)], i32),
             "lutgen_cuda_generate_lut_rows_multi_dev": ([vp, u8, C.POINTER(vp), i32, u32, u32, vp], i32),
             "lutgen_cuda_generate_lut_shard_multi_dev": ([vp, u8, C.POINTER(vp), i32, u32, u32, vp], i32),
+            "lutgen_cuda_generate_lut_shard_mc_dev": ([vp, u8, C.POINTER(vp), i32, vp, u32, u32, vp], i32),
             "lutgen_cuda_peer_barrier_dev": ([vp, i32, i32, u32, vp], i32),
             "lutgen_cuda_device_alloc": ([sz, C.POINTER(vp)], i32),
             "lutgen_cuda_device_free": ([vp], i32),

@@ -329,6 +329,7 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
     if (MODE == FRONT_LUT && (f.cs & 3u) == 0) {
         uintptr_t bits = reinterpret_cast<uintptr_t>(f.out);
         for (int x = 0; x < f.nextra; ++x) bits |= reinterpret_cast<uintptr_t>(f.extra[x]);
+        bits |= reinterpret_cast<uintptr_t>(f.mc);
         a.words_ok = (bits & 3u) == 0;
         if (a.words_ok && (bits & 15u) == 0) a.words_ok = 2;   // 16-byte stores of whole hand-outs possible
         if (const char* e = getenv("LUTGEN_CUDA_STORE")) a.words_ok = std::min(a.words_ok, atoi(e));  // 0 bytes, 1 tile words, 2 hand-out rows
@@ -1207,6 +1208,11 @@ int lutgen_cuda_generate_lut_rows_multi_dev(const lutgen_remapper* r, uint8_t le
 
 int lutgen_cuda_generate_lut_shard_multi_dev(const lutgen_remapper* r, uint8_t level, uint8_t* const* luts_rgb_dev, int nluts, uint32_t shard_index,
                                              uint32_t shard_count, void* stream) {
+    return lutgen_cuda_generate_lut_shard_mc_dev(r, level, luts_rgb_dev, nluts, nullptr, shard_index, shard_count, stream);
+}
+
+int lutgen_cuda_generate_lut_shard_mc_dev(const lutgen_remapper* r, uint8_t level, uint8_t* const* luts_rgb_dev, int nluts, uint8_t* multicast_lut,
+                                          uint32_t shard_index, uint32_t shard_count, void* stream) {
     int rc = ensure_ready();
     if (rc) return rc;
     if (!r || !luts_rgb_dev || nluts < 1) return fail(LUTGEN_ERR_INVALID, "NULL argument");
@@ -1228,6 +1234,7 @@ int lutgen_cuda_generate_lut_shard_multi_dev(const lutgen_remapper* r, uint8_t l
     f.csm1 = f.cs - 1;
     f.shard_index = shard_index;
     f.shard_count = shard_count;
+    f.mc = nluts > 1 ? multicast_lut : nullptr;
     return launch_remap<FRONT_LUT>(f, r, (cudaStream_t)stream);
 }
 

@@ -37,6 +37,9 @@ struct Front {
     // buffers, mapped into this process (CUDA IPC) and written over NVLink while the kernel runs
     uint8_t* extra[LUTGEN_MAX_PEERS];
     int nextra;
+    // ... and optionally the same buffers as ONE multicast address (NVSwitch replicates a store to every
+    // GPU, this one included): whole tiles are stored there once, as words, instead of to out + extra
+    uint8_t* mc;
     // FRONT_LUT only: this launch is shard `shard_index` of `shard_count` of the range. Kernels that
     // walk tiles take every shard_count-th hand-out (balanced whatever the colours cost); the others
     // are given the shard's contiguous rows instead (api.cu: rows_of_shard).

@@ -554,7 +554,8 @@ __device__ __forceinline__ void wt_store(const WarpArgs& a, const WtTile<EPT>& T
             }
             if (sg.defer) { sg.staged |= 1u << sg.slot; return; }
             __syncwarp();
-            wt_flush_tile<EPT>(a.f.out, sg.extras, a.f.nextra, a.f.cs, sg.buf, sg.pitch, sg.slot, __shfl_sync(FULL, T.slot0, 0), T.slot_step);
+            wt_flush_tile<EPT>(a.f.mc ? a.f.mc : a.f.out, sg.extras, a.f.mc ? 0 : a.f.nextra, a.f.cs, sg.buf, sg.pitch, sg.slot,
+                               __shfl_sync(FULL, T.slot0, 0), T.slot_step);
             return;
         }
     }
@@ -879,7 +880,7 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
         if (MULTI && sg.staged) {
             __syncwarp();
             if (sg.staged == (1u << WT_BATCH) - 1u) {
-                wt_flush_batch<EPT>(a.f.out, sg.extras, a.f.nextra, cs, sg.buf, batch_flat0, batch_step);
+                wt_flush_batch<EPT>(a.f.mc ? a.f.mc : a.f.out, sg.extras, a.f.mc ? 0 : a.f.nextra, cs, sg.buf, batch_flat0, batch_step);
             } else {
                 // some tiles of the hand-out went out entry by entry (or were skipped): the staged ones go tile by tile.
                 // batch_flat0 is the first tile's origin only if that tile reached step 5; recompute from the tile number
@@ -889,7 +890,8 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
                 const uint32_t flat_first = ((a.b_lo + ib0 * (uint32_t)EPT) * cs + ig0 * 4u) * cs + ir0 * 8u;
 #pragma unroll 1
                 for (uint32_t sl = 0; sl < (uint32_t)WT_BATCH; ++sl)
-                    if ((sg.staged >> sl) & 1u) wt_flush_tile<EPT>(a.f.out, sg.extras, a.f.nextra, cs, sg.buf, sg.pitch, sl, flat_first + 8u * sl, cs * cs);
+                    if ((sg.staged >> sl) & 1u)
+                        wt_flush_tile<EPT>(a.f.mc ? a.f.mc : a.f.out, sg.extras, a.f.mc ? 0 : a.f.nextra, cs, sg.buf, sg.pitch, sl, flat_first + 8u * sl, cs * cs);
             }
         }
     }

@@ -134,11 +134,37 @@ class PeerLut:
         self.nbytes = int(nbytes)
         self._lut_bytes = (self.nbytes + 255) // 256 * 256   # flags follow the CLUT, 256-byte aligned
         L = _native.lib()
-        self._own, self._ptrs, self._imported = [], [], []
+        self._own, self._ptrs, self._imported, self._mc, self._symm = [], [], [], [], []
+        total = self._lut_bytes + self.FLAG_BYTES
+        use_symm = not os.environ.get("LUTGEN_NO_SYMM_MEM")
         for _ in range(2):
+            got = None
+            if use_symm:
+                # torch symmetric memory: peer mappings AND one NVSwitch multicast address for all of them
+                try:
+                    import torch.distributed._symmetric_memory as symm_mem
+                    t = symm_mem.empty(total, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+                    hdl = symm_mem.rendezvous(t, group=group if group is not None else dist.group.WORLD)
+                    got = (t, hdl)
+                except Exception:  # not available here: CUDA IPC below
+                    got = None
+                # all ranks must take the same route
+                okt = torch.tensor([1 if got is not None else 0], device="cuda")
+                dist.all_reduce(okt, op=dist.ReduceOp.MIN, group=group)
+                if int(okt.item()) == 0:
+                    got, use_symm = None, False
+            if got is not None:
+                t, hdl = got
+                t.zero_()
+                self._symm.append(got)
+                self._own.append(t.data_ptr())
+                self._ptrs.append([int(q) for q in hdl.buffer_ptrs])
+                self._mc.append(int(hdl.multicast_ptr or 0))
+                continue
             p = C.c_void_p()
-            _native.check(L.lutgen_cuda_device_alloc(self._lut_bytes + self.FLAG_BYTES, C.byref(p)))
+            _native.check(L.lutgen_cuda_device_alloc(total, C.byref(p)))
             self._own.append(p.value)
+            self._mc.append(0)
             torch.as_tensor(_RawCuda(p.value + self._lut_bytes, self.FLAG_BYTES), device="cuda").zero_()
             handle = (C.c_uint8 * 64)()
             _native.check(L.lutgen_cuda_ipc_export(C.c_void_p(p.value), C.cast(handle, C.c_void_p)))
@@ -166,13 +192,14 @@ class PeerLut:
         dist.barrier(group=group)
 
     def next(self):
-        """(tensor of this rank's buffer, ctypes array of all ranks' pointers, own first) for the next step."""
+        """(tensor of this rank's buffer, ctypes array of all ranks' pointers -- own first --, multicast
+        address of the same buffers or 0) for the next step."""
         import ctypes as C
         i = self._turn
         self._turn ^= 1
         ptrs = self._ptrs[i]
         order = [ptrs[self.rank]] + [ptrs[r] for r in range(self.world) if r != self.rank]
-        return self.tensors[i], (C.c_void_p * len(order))(*order)
+        return self.tensors[i], (C.c_void_p * len(order))(*order), self._mc[i]
 
     def barrier(self, stream=None):
         """All ranks' earlier writes into the peer buffers are complete and visible after this."""
@@ -188,9 +215,10 @@ class PeerLut:
         for q in self._imported:
             L.lutgen_cuda_ipc_close(C.c_void_p(q))
         self._imported = []
-        for p in self._own:
-            L.lutgen_cuda_device_free(C.c_void_p(p))
-        self._own = []
+        if not self._symm:
+            for p in self._own:
+                L.lutgen_cuda_device_free(C.c_void_p(p))
+        self._own, self._symm = [], []
 
 
 _peer_luts = {}
@@ -199,8 +227,9 @@ _peer_luts = {}
 def generate_lut_fused(remapper, level, group=None, stream=None):
     """Sharded generation with the exchange fused into the kernel: each rank computes its share of
     the tiles (every world-th hand-out: balanced) and stores the results into EVERY rank's buffer over
-    NVLink while it computes (lutgen_cuda_generate_lut_shard_multi_dev); a barrier through flags in
-    peer memory then makes the whole CLUT valid on every rank. Returns a (side, side, 3) uint8 CUDA
+    NVLink while it computes -- once, to an NVSwitch multicast address, when torch's symmetric memory
+    provides one (lutgen_cuda_generate_lut_shard_mc_dev), else to each peer mapping (CUDA IPC); a
+    barrier through flags in peer memory then makes the whole CLUT valid on every rank. Returns a (side, side, 3) uint8 CUDA
     tensor that stays valid until the second next call. Falls back to `generate_lut` (all-gather)
     for remappers the fused entry point does not take, and for a single rank."""
     import torch.distributed as dist
@@ -213,8 +242,9 @@ def generate_lut_fused(remapper, level, group=None, stream=None):
     peers = _peer_luts.get(key)
     if peers is None:
         peers = _peer_luts[key] = PeerLut(3 * side * side, group)
-    mine, ptrs = peers.next()
-    _native.check(_native.lib().lutgen_cuda_generate_lut_shard_multi_dev(remapper._h, level, ptrs, len(ptrs), peers.rank, world, _stream(stream)))
+    mine, ptrs, mc = peers.next()
+    _native.check(_native.lib().lutgen_cuda_generate_lut_shard_mc_dev(remapper._h, level, ptrs, len(ptrs), mc or None, peers.rank, world,
+                                                                     _stream(stream)))
     peers.barrier(stream)
     return mine.view(side, side, 3)
 

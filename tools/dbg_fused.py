@@ -63,14 +63,17 @@ from lutgen_rs_b200 import _native
 peers = device._peer_luts[(side, id(None))]
 r0, r1, _ = device.shard_rows(side, world, rank)
 def rows_multi():
-    mine, ptrs = peers.next()
+    mine, ptrs, mc = peers.next()
     _native.check(_native.lib().lutgen_cuda_generate_lut_rows_multi_dev(r._h, 16, ptrs, len(ptrs), int(r0), int(r1), torch.cuda.current_stream().cuda_stream))
 def shard_multi():
-    mine, ptrs = peers.next()
+    mine, ptrs, mc = peers.next()
     _native.check(_native.lib().lutgen_cuda_generate_lut_shard_multi_dev(r._h, 16, ptrs, len(ptrs), rank, world, torch.cuda.current_stream().cuda_stream))
+def shard_mc():
+    mine, ptrs, mc = peers.next()
+    _native.check(_native.lib().lutgen_cuda_generate_lut_shard_mc_dev(r._h, 16, ptrs, len(ptrs), mc or None, rank, world, torch.cuda.current_stream().cuda_stream))
 def rows_local():
     device.generate_lut_rows_(r, 16, out, r0, r1)
-for fn, label in ((rows_local, "rows, local only"), (rows_multi, "rows, all destinations (no barrier)"), (shard_multi, "interleaved shard, all destinations (no barrier)"),
+for fn, label in ((rows_local, "rows, local only"), (rows_multi, "rows, all destinations (no barrier)"), (shard_multi, "interleaved shard, all destinations (no barrier)"), (shard_mc, "interleaved shard, multicast (no barrier)"),
                   (lambda: dist.barrier(), "dist.barrier"), (lambda: peers.barrier(), "peer-memory barrier")):
     for _ in range(5):
         fn()
