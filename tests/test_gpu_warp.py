@@ -129,3 +129,52 @@ def test_palette_colours_pass_through_with_big_palettes():
     lut = interpolation.ShepardRemapper(pal, 4.0, 16, 1.0, False).generate_lut(16).reshape(-1, 3)
     idx = pal[:, 0].astype(np.int64) + 256 * pal[:, 1].astype(np.int64) + 65536 * pal[:, 2].astype(np.int64)
     assert (lut[idx] == pal).all()
+
+
+@pytest.mark.parametrize("n,nearest,level", [(26, 16, 16), (26, 16, 9), (120, 16, 8), (300, 16, 6), (40, 0, 6)])
+def test_interleaved_shards_tile_the_clut(palettes, n, nearest, level):
+    """lutgen_cuda_generate_lut_shard_multi_dev: shard i of c takes every c-th tile hand-out of the
+    warp-tile kernels (or the shard's rows on the other kernels); the c launches together must write
+    every entry exactly as one launch does. One GPU stands in for the c ranks (one destination)."""
+    import ctypes as C
+
+    import torch
+    from lutgen_rs_b200 import _native, device
+    device.init(0)
+    pal = palettes["catppuccin_mocha"] if n == 26 else synthetic_palette(n, seed=n)
+    side = level ** 3
+    s = torch.cuda.current_stream().cuda_stream
+    for r in (interpolation.GaussianRemapper(pal, 128.0, nearest, 1.0, False), interpolation.NearestNeighborRemapper(pal, 1.0, False)):
+        whole = torch.from_numpy(r.generate_lut(level)).cuda().reshape(-1)
+        for count in (2, 3, 8):
+            lut = torch.full((3 * side * side,), 7, dtype=torch.uint8, device="cuda")
+            ptrs = (C.c_void_p * 1)(lut.data_ptr())
+            for idx in range(count):
+                _native.check(_native.lib().lutgen_cuda_generate_lut_shard_multi_dev(r._h, level, ptrs, 1, idx, count, s))
+            torch.cuda.synchronize()
+            assert torch.equal(lut, whole), (count, int((lut != whole).sum()))
+
+
+def test_multi_destination_rows_write_every_copy(palettes):
+    """lutgen_cuda_generate_lut_rows_multi_dev with several destinations on ONE GPU (the peers'
+    buffers of a multi-GPU job are ordinary device pointers to the kernel): every copy gets the rows,
+    through the staged word stores (level 16, 8) and the entry-by-entry path (level 9)."""
+    import ctypes as C
+
+    import torch
+    from lutgen_rs_b200 import _native, device
+    device.init(0)
+    pal = palettes["nord"]
+    s = torch.cuda.current_stream().cuda_stream
+    for level, rows in ((16, (1000, 2000)), (8, (0, 512)), (9, (3, 700))):
+        side = level ** 3
+        for r in (interpolation.GaussianRemapper(pal, 128.0, 16, 1.0, False), interpolation.NearestNeighborRemapper(pal, 1.0, False),
+                  interpolation.ShepardRemapper(synthetic_palette(80, 3), 4.0, 16, 1.0, False)):
+            ref = torch.zeros(3 * side * side, dtype=torch.uint8, device="cuda")
+            device.generate_lut_rows_(r, level, ref, rows[0], rows[1])
+            copies = [torch.zeros(3 * side * side, dtype=torch.uint8, device="cuda") for _ in range(4)]
+            ptrs = (C.c_void_p * 4)(*[c.data_ptr() for c in copies])
+            _native.check(_native.lib().lutgen_cuda_generate_lut_rows_multi_dev(r._h, level, ptrs, 4, rows[0], rows[1], s))
+            torch.cuda.synchronize()
+            for c in copies:
+                assert torch.equal(c, ref)
