@@ -443,10 +443,51 @@ def run_b200(args):
         apply_line["cpu_baseline"]["all_cores_value"] = v
         apply_line["cpu_baseline"]["all_cores"] = cores
 
+    # the other BASELINE.json configurations, device resident on one GPU (rank 0; a few repetitions
+    # each, after the timed regions above): evidence next to the headline, not part of `value`
+    other_configs = None
+    if rank == 0:
+        from conftest import synthetic_palette
+        pal256 = synthetic_palette(256, 1)
+
+        def ms_of(make, level, reps=5, evict_level=None):
+            side_ = level ** 3
+            buf = torch.empty(3 * side_ * side_, dtype=torch.uint8, device="cuda")
+            rm = make()
+            ts = []
+            for i in range(reps + 2):
+                if evict_level:
+                    # the blur remapper caches the blurred volume of the last level: ask for another one first
+                    device.generate_lut_rows_(rm, evict_level, buf, 0, evict_level ** 3)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                flush_l2()
+                a.record(stream)
+                device.generate_lut_rows_(rm, level, buf, 0, side_)
+                b.record(stream)
+                torch.cuda.synchronize()
+                if i >= 2:
+                    ts.append(a.elapsed_time(b))
+            return round(float(np.median(ts)), 4)
+
+        other_configs = {
+            "shepard_level16_256colours_nearest16_ms": ms_of(lambda: interpolation.ShepardRemapper(pal256, 4.0, 16, 1.0, False), 16),
+            "gaussian_sampling_level12_512iter_256colours_ms": ms_of(
+                lambda: interpolation.GaussianSamplingRemapper(pal256, 0.0, 20.0, 512, 1.0, 42080085, False), 12),
+            "nearest_neighbor_level16_ms": ms_of(lambda: interpolation.NearestNeighborRemapper(pal, 1.0, False), 16),
+            "gaussian_blur_level16_radius8_ms": ms_of(lambda: interpolation.GaussianBlurRemapper(pal, 8.0, 1.0, False), 16, reps=3, evict_level=4),
+            "gaussian_rbf_level8_ms": ms_of(lambda: interpolation.GaussianRemapper(pal, 128.0, 16, 1.0, False), 8),
+            "gaussian_rbf_level12_ms": ms_of(lambda: interpolation.GaussianRemapper(pal, 128.0, 16, 1.0, False), 12),
+            "what": "ms per whole CLUT on ONE GPU, device resident, L2 flushed (BASELINE.json configs 3, 4, 1 and SURVEY 8f#1)",
+        }
+    if world > 1:
+        barrier()
+
     top, other, other_key = (gen_line, apply_line, "apply") if args.workload == "generate" else (apply_line, gen_line, "generate")
     line = dict(top)
     line.update({"n_gpus": world, "steps": steps, "warmup": warmup, "higher_is_better": True, "vs_baseline": None,
                  "data": "synthetic", "clocks": clocks, other_key: other})
+    if other_configs is not None:
+        line["other_configs"] = other_configs
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -355,9 +355,15 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
     a.ntiles_global = a.ntiles;
     a.shard_index = 0;
     a.shard_count = 1;
+    // hand-outs of WT_BATCH warp tiles keep neighbouring tiles in one warp (and feed the 96-byte row stores of
+    // the MULTI variant); small ranges take single tiles so that every SM gets work
+    {
+        const uint32_t share = a.ntiles / (MODE == FRONT_LUT && f.shard_count > 1 ? f.shard_count : 1u);
+        a.batch = share >= (uint32_t)g.sm_count * WT_WARPS * 3u * WT_BATCH ? (uint32_t)WT_BATCH : 1u;
+    }
     if (MODE == FRONT_LUT && f.shard_count > 1) {
-        // hand-outs (WT_BATCH warp tiles, or one CTA tile) index, index + count, ...
-        const uint32_t per = BIG ? 1u : (uint32_t)WT_BATCH, handouts = (a.ntiles_global + per - 1) / per;
+        // hand-outs (a.batch warp tiles, or one CTA tile) index, index + count, ...
+        const uint32_t per = BIG ? 1u : a.batch, handouts = (a.ntiles_global + per - 1) / per;
         a.shard_index = f.shard_index;
         a.shard_count = f.shard_count;
         a.ntiles = handouts > f.shard_index ? ((handouts - f.shard_index + f.shard_count - 1) / f.shard_count) * per : 0;
@@ -382,7 +388,7 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
         per_sm[multi] = v < 1 ? 1 : v;
     }
     unsigned grid = (unsigned)per_sm[multi] * (unsigned)g.sm_count;
-    unsigned need = BIG ? a.ntiles : blocks_for(a.ntiles, WT_WARPS * WT_BATCH);
+    unsigned need = BIG ? a.ntiles : blocks_for(a.ntiles, WT_WARPS * a.batch);
     if (grid > need) grid = need;
     CU_TRY(cudaMemsetAsync(r->flag_count, 0, 2 * sizeof(uint32_t), s));
     if (BIG) {

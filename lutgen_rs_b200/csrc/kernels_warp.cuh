@@ -59,7 +59,8 @@ struct WarpArgs {
     uint32_t b_lo;            // first blue plane covered (multiple of EPT)
     uint32_t ntiles;          // tiles this launch walks (local numbering)
     uint32_t ntiles_global;   // tiles of the whole range
-    uint32_t shard_index, shard_count;  // this launch takes hand-outs index, index + count, ... (1 hand-out = WT_BATCH warp tiles / 1 CTA tile)
+    uint32_t shard_index, shard_count;  // this launch takes hand-outs index, index + count, ... (1 hand-out = `batch` warp tiles / 1 CTA tile)
+    uint32_t batch;           // warp tiles per hand-out: WT_BATCH, or 1 when the range has too few tiles to fill the GPU otherwise
     uint32_t* flag_list;
     uint32_t* flag_count;
     uint32_t* tile_counter;   // zeroed before the launch
@@ -771,10 +772,10 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
 
     for (;;) {
         uint32_t t0 = 0;
-        if (lane == 0) t0 = atomicAdd(a.tile_counter, (uint32_t)WT_BATCH);
+        if (lane == 0) t0 = atomicAdd(a.tile_counter, a.batch);
         t0 = __shfl_sync(FULL, t0, 0);
         if (t0 >= a.ntiles) break;
-        if (a.shard_count > 1) t0 = ((t0 / (uint32_t)WT_BATCH) * a.shard_count + a.shard_index) * (uint32_t)WT_BATCH;
+        if (a.shard_count > 1) t0 = ((t0 / a.batch) * a.shard_count + a.shard_index) * a.batch;
         if (t0 >= a.ntiles_global) break;
         uint32_t ir = 0, ig = 0, ib = 0;
         if (BRICK) {
@@ -782,7 +783,7 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
             wt_divmod(t0, a.tiles_r, a.inv_tiles_r, rest, ir);
             wt_divmod(rest, a.tiles_g, a.inv_tiles_g, ib, ig);
         }
-        const uint32_t t1 = min(t0 + (uint32_t)WT_BATCH, a.ntiles_global);
+        const uint32_t t1 = min(t0 + a.batch, a.ntiles_global);
         WtStage sg;
         sg.extras = s_extra;
         sg.buf = s_stage[MULTI ? warp : 0];
