@@ -136,17 +136,26 @@ __global__ void __launch_bounds__(256) k_sampling(Front f, const uint32_t* __res
         for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) s_off[j] = offsets[base + j];
         __syncthreads();
         if (live) {
+            // (r, g) and (b, 0) as signed 16-bit pairs: one VIADDMNMX.S16x2.RELU per pair is
+            // sat_u8(c + o) for two channels (add, min with 255, max with 0), one PRMT gathers the three
+            // bytes into the table index, three IDP.4A pick the result's channels into their sums. The
+            // kernel was bound by the ALU pipe (87 %) at 23 instructions per iteration; this is 9.
+            const uint32_t c_rg = (uint32_t)r0 | ((uint32_t)g0 << 16), c_b = (uint32_t)b0;
+            const uint2* s_off2 = reinterpret_cast<const uint2*>(s_off);   // short4 (x, y, z, w) = {x | y << 16, z | w << 16}
 #pragma unroll 4
             for (uint32_t j = 0; j < m; ++j) {
-                short4 o = s_off[j];
-                uint32_t idx = clamp255(r0 + o.x) | (clamp255(g0 + o.y) << 8) | (clamp255(b0 + o.z) << 16);
+                const uint2 o = s_off2[j];
+                const uint32_t x_rg = __viaddmin_s16x2_relu(c_rg, o.x, 0x00ff00ffu), x_b = __viaddmin_s16x2_relu(c_b, o.y, 0x00ff00ffu);
+                const uint32_t idx = __byte_perm(x_rg, x_b, 0x7420);   // R = x_rg byte 0, G = x_rg byte 2, B = x_b byte 0, 0
                 uint32_t v = __ldg(nn_table + idx);
                 if (EXACT_F64) {
                     mr = __dadd_rn(mr, s_div[v & 255u]);
                     mg = __dadd_rn(mg, s_div[(v >> 8) & 255u]);
                     mb = __dadd_rn(mb, s_div[(v >> 16) & 255u]);
                 } else {
-                    sr += v & 255u; sg += (v >> 8) & 255u; sb += (v >> 16) & 255u;
+                    sr = __dp4a(v, 0x00000001u, sr);
+                    sg = __dp4a(v, 0x00000100u, sg);
+                    sb = __dp4a(v, 0x00010000u, sb);
                 }
             }
         }
