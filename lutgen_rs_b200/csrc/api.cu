@@ -595,8 +595,8 @@ int ensure_blur_volume(const lutgen_remapper* r, uint32_t level, cudaStream_t s)
             CU_TRY(blur_set_attributes());
             attr_done = true;
         }
-        const int stage_pal = (size_t)r->n * 12 <= 64 * 1024;
-        const size_t smem_nn = 1024 + (stage_pal ? (size_t)r->n * 12 : 0);
+        const int stage_pal = (size_t)r->n * 28 <= 64 * 1024;   // palette (3 floats) + expanded form (4 floats) per colour
+        const size_t smem_nn = 1024 + (stage_pal ? (size_t)r->n * 28 + 32 : 0);
         blur_launch_nn_volume(grid_nn, smem_nn, s, a, size, ch, r->blur_chan, r->blur_pal3, r->blur_out3, r->n, lum, threshold_sq, g.tables, stage_pal);
         LAUNCH_CHECK();
         const int klen = r->blur_klen;
@@ -1480,7 +1480,7 @@ int lutgen_cuda_srgb_to_oklab_fast(const uint8_t* rgb, size_t n, float* out_lab)
     float* dout = (float*)g.misc.p;
     uint8_t* din = (uint8_t*)g.misc.p + 12 * n;
     CU_TRY(cudaMemcpyAsync(din, rgb, 3 * n, cudaMemcpyHostToDevice, g.stream));
-    k_srgb_to_oklab_fast<<<blocks_for(n, 256), 256, 0, g.stream>>>(din, n, dout, g.tables);
+    k_srgb_to_oklab_fast<<<blocks_for((n + 1) / 2, 256), 256, 0, g.stream>>>(din, n, dout, g.tables);
     LAUNCH_CHECK();
     CU_TRY(cudaMemcpyAsync(out_lab, dout, 12 * n, cudaMemcpyDeviceToHost, g.stream));
     CU_TRY(cudaStreamSynchronize(g.stream));

@@ -117,6 +117,36 @@ __device__ __forceinline__ Lab linear_to_oklab_fast(float r, float g, float b) {
     return o;
 }
 
+// Packed f32x2 arithmetic (FFMA2 / FMUL2 / FADD2, sm_100a): two values per instruction; a scalar
+// operand is broadcast for free. Used by the +-1 LSB kernels and by decisions that are re-checked exactly.
+typedef float2 f2;
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 splat(float x) { return make_float2(x, x); }
+
+// x^(1/3) for two LMS values >= 0: MUFU seed for x^(-1/3) + one Newton step, as cbrtf_fast, with the
+// zero guard folded into a clamp (cbrt(1e-30) = 1e-10 is zero at Oklab's resolution).
+__device__ __forceinline__ f2 cbrt2(f2 x) {
+    x.x = fmaxf(x.x, 1e-30f);
+    x.y = fmaxf(x.y, 1e-30f);
+    f2 lg = make_float2(lg2_approx(x.x), lg2_approx(x.y));
+    lg = mul2(lg, splat(-0.33333334f));
+    f2 t = make_float2(ex2_approx(lg.x), ex2_approx(lg.y));
+    f2 v = mul2(mul2(x, t), mul2(t, t));           // x t^3
+    f2 r = fma2(v, splat(-1.0f), splat(1.0f));      // 1 - x t^3
+    t = fma2(mul2(t, splat(0.33333334f)), r, t);
+    return mul2(mul2(x, t), t);
+}
+
+// Two entries' Oklab from their LMS values.
+__device__ __forceinline__ void lms_to_lab2(f2 l, f2 m, f2 s, float lum, f2& L, f2& A, f2& B) {
+    f2 l_ = cbrt2(l), m_ = cbrt2(m), s_ = cbrt2(s);
+    L = mul2(fma2(splat(0.2104542553f), l_, fma2(splat(0.7936177850f), m_, mul2(splat(-0.0040720468f), s_))), splat(lum));
+    A = fma2(splat(1.9779984951f), l_, fma2(splat(-2.4285922050f), m_, mul2(splat(0.4505937099f), s_)));
+    B = fma2(splat(0.0259040371f), l_, fma2(splat(0.7827717662f), m_, mul2(splat(-0.8086757660f), s_)));
+}
+
 // oklab::oklab_to_linear_srgb, exact evaluation order.
 __device__ __forceinline__ void oklab_to_linear_exact(Lab c, float& r, float& g, float& b) {
     float l_ = __fadd_rn(__fadd_rn(c.l, __fmul_rn(0.3963377774f, c.a)), __fmul_rn(0.2158037573f, c.b));

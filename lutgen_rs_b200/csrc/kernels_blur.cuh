@@ -52,20 +52,51 @@ __device__ __forceinline__ float2 blur_sub2(float2 a, float b) { return __ffma2_
 // product before it adds.
 __device__ __forceinline__ float2 blur_add2(float2 a, float2 b, float one) { return __ffma2_rn(a, make_float2(one, one), b); }
 
+// The exact per-cell scan: the reference's f32 arithmetic operation for operation (exact Oklab, sq_dist
+// rounded as written). M = smallest distance, I = first index reaching it, S2 = second smallest.
+__device__ __forceinline__ void blur_scan_exact(float lr, float lg, float lb, float lum, const float* __restrict__ pal, uint32_t n, float& c0, float& c1,
+                                                float& c2, float& M, float& S2, uint32_t& I) {
+    const Lab o = linear_to_oklab_exact(lr, lg, lb);
+    c0 = __fmul_rn(o.l, lum); c1 = o.a; c2 = o.b;
+    float best = INFINITY, second = INFINITY;
+    uint32_t bi = 0;
+    for (uint32_t t = 0; t < n; ++t) {
+        const float d = blur_sq_dist(c0, c1, c2, pal + 3 * t);
+        const bool better = d < best;
+        second = better ? best : fminf(second, d);
+        best = better ? d : best;
+        bi = better ? t : bi;
+    }
+    M = best; S2 = second; I = bi;
+}
+
+// Per cell the kernel first decides with the FAST arithmetic of the +-1 LSB kernels (Oklab within
+// 3e-6 of the exact one, expanded distance |p|^2 - 2 p.c, packed f32x2 for the lane's two cells):
+// if the two smallest distances are further apart than that arithmetic can be wrong, and no second
+// colour comes near the early-exit threshold, the nearest colour is I whatever the hint and whatever
+// the last bits of the reference's own rounding. Every other cell (a fraction of a percent) is
+// rescanned with the exact arithmetic above before anything is decided.
 __global__ void __launch_bounds__(BLUR_ROW_WARPS * 32) k_blur_nn_volume(float* __restrict__ colors, uint32_t size, uint32_t ch, const uint8_t* __restrict__ chan,
                                                                          const float* __restrict__ pal3, const float* __restrict__ out3, uint32_t n,
                                                                          float lum, float threshold_sq, const ColorTables* __restrict__ tables,
                                                                          int stage_palette, float one) {
-    extern __shared__ float s_blur_nn[];   // decode[256] | palette 3n (when it fits)
+    extern __shared__ __align__(16) float s_blur_nn[];   // decode[256] | when it fits: palette 3n | q 4n (-2p, |p|^2)
     float* s_decode = s_blur_nn;
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_decode[i] = tables->decode[i];
-    if (stage_palette)
+    float4* s_q = reinterpret_cast<float4*>(s_blur_nn + 256 + ((3 * n + 3) & ~3u));
+    if (stage_palette) {
         for (uint32_t i = threadIdx.x; i < 3 * n; i += blockDim.x) s_blur_nn[256 + i] = pal3[i];
+        for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {
+            const float x = pal3[3 * t], y = pal3[3 * t + 1], z = pal3[3 * t + 2];
+            s_q[t] = make_float4(-2.f * x, -2.f * y, -2.f * z, fmaf(x, x, fmaf(y, y, z * z)));
+        }
+    }
     const float* __restrict__ s_pal = stage_palette ? s_blur_nn + 256 : pal3;
     __syncthreads();
     const uint32_t FULL = 0xffffffffu;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rows = size * size;
+    (void)one;
     for (uint32_t row = blockIdx.x * BLUR_ROW_WARPS + warp; row < rows; row += gridDim.x * BLUR_ROW_WARPS) {
         const uint32_t r = row / size, g = row % size;
         const float lr = s_decode[chan[r]], lg = s_decode[chan[g]];
@@ -73,31 +104,60 @@ __global__ void __launch_bounds__(BLUR_ROW_WARPS * 32) k_blur_nn_volume(float* _
         for (uint32_t b0 = 0; b0 < size; b0 += 64) {
             // cells b0 + lane (x) and b0 + 32 + lane (y); past the end they repeat the last cell
             const uint32_t bx = min(b0 + lane, size - 1), by = min(b0 + 32 + lane, size - 1);
-            Lab ox = linear_to_oklab_exact(lr, lg, s_decode[chan[bx]]), oy = linear_to_oklab_exact(lr, lg, s_decode[chan[by]]);
-            const float2 c0 = make_float2(__fmul_rn(ox.l, lum), __fmul_rn(oy.l, lum)), c1 = make_float2(ox.a, oy.a), c2 = make_float2(ox.b, oy.b);
+            const float lbx = s_decode[chan[bx]], lby = s_decode[chan[by]];
             float2 best = make_float2(INFINITY, INFINITY), second = best;
             uint32_t ix = 0, iy = 0;
+            bool riskx = true, risky = true;
+            if (stage_palette) {
+                // fast decision
+                const f2 linb = make_float2(lbx, lby);
+                const float pl = fmaf(0.5363325363f, lg, 0.4122214708f * lr), pm = fmaf(0.6806995451f, lg, 0.2119034982f * lr),
+                            ps = fmaf(0.2817188376f, lg, 0.0883024619f * lr);
+                f2 L, A, B;
+                lms_to_lab2(fma2(splat(0.0514459929f), linb, splat(pl)), fma2(splat(0.1073969566f), linb, splat(pm)),
+                            fma2(splat(0.6299787005f), linb, splat(ps)), lum, L, A, B);
 #pragma unroll 2
-            for (uint32_t t = 0; t < n; ++t) {
-                // sq_dist, gaussian_blur.rs:504-510: (dl*dl + da*da) + db*db, every operation rounded
-                const float2 dl = blur_sub2(c0, s_pal[3 * t]), da = blur_sub2(c1, s_pal[3 * t + 1]), db = blur_sub2(c2, s_pal[3 * t + 2]);
-                const float2 d = blur_add2(blur_add2(__fmul2_rn(dl, dl), __fmul2_rn(da, da), one), __fmul2_rn(db, db), one);
-                const bool bx_ = d.x < best.x, by_ = d.y < best.y;
-                second.x = bx_ ? best.x : fminf(second.x, d.x);
-                second.y = by_ ? best.y : fminf(second.y, d.y);
-                best.x = bx_ ? d.x : best.x;
-                best.y = by_ ? d.y : best.y;
-                ix = bx_ ? t : ix;
-                iy = by_ ? t : iy;
+                for (uint32_t t = 0; t < n; ++t) {
+                    const float4 q = s_q[t];
+                    const f2 d = fma2(splat(q.x), L, fma2(splat(q.y), A, fma2(splat(q.z), B, splat(q.w))));   // d - |c|^2
+                    const bool bx_ = d.x < best.x, by_ = d.y < best.y;
+                    second.x = bx_ ? best.x : fminf(second.x, d.x);
+                    second.y = by_ ? best.y : fminf(second.y, d.y);
+                    best.x = bx_ ? d.x : best.x;
+                    best.y = by_ ? d.y : best.y;
+                    ix = bx_ ? t : ix;
+                    iy = by_ ? t : iy;
+                }
+                // |c|^2 back in; what the fast arithmetic can be off by: the conversion (3e-6 per coordinate,
+                // 2 sqrt(d) of it in a distance) and the rounding of the expansion
+                const f2 cc = fma2(L, L, fma2(A, A, mul2(B, B)));
+                const f2 d2 = add2(second, cc), gap = make_float2(second.x - best.x, second.y - best.y);
+                const float mx = 2.24e-5f * sqrtf(fmaxf(d2.x, 0.f)) + 3e-6f, my = 2.24e-5f * sqrtf(fmaxf(d2.y, 0.f)) + 3e-6f;
+                riskx = !(gap.x > mx) || !(d2.x > threshold_sq + mx);
+                risky = !(gap.y > my) || !(d2.y > threshold_sq + my);
+            }
+            float c0x = 0.f, c1x = 0.f, c2x = 0.f, c0y = 0.f, c1y = 0.f, c2y = 0.f;
+            bool ambx = false, amby = false;
+            if (riskx) {
+                float M, S2;
+                blur_scan_exact(lr, lg, lbx, lum, s_pal, n, c0x, c1x, c2x, M, S2, ix);
+                best.x = M;
+                ambx = S2 == M || S2 < threshold_sq;
+            }
+            if (risky) {
+                float M, S2;
+                blur_scan_exact(lr, lg, lby, lum, s_pal, n, c0y, c1y, c2y, M, S2, iy);
+                best.y = M;
+                amby = S2 == M || S2 < threshold_sq;
             }
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const uint32_t cell = b0 + 32u * half + lane;
                 if (b0 + 32u * half >= size) break;  // uniform
-                const float M = half ? best.y : best.x, S2 = half ? second.y : second.x;
+                const float M = half ? best.y : best.x;   // exact where the cell is ambiguous
                 const uint32_t I = half ? iy : ix;
                 const bool in_row = cell < size;
-                const bool amb = in_row && (S2 == M || S2 < threshold_sq);
+                const bool amb = in_row && (half ? amby : ambx);
                 uint32_t res = I;
                 uint32_t am = __ballot_sync(FULL, amb);
                 while (am) {
@@ -107,8 +167,7 @@ __global__ void __launch_bounds__(BLUR_ROW_WARPS * 32) k_blur_nn_volume(float* _
                     const uint32_t prev = __shfl_sync(FULL, res, j == 0 ? 0 : j - 1);
                     const uint32_t h = j == 0 ? hint : prev;
                     if (lane == j && h != I) {
-                        const float cc0 = half ? c0.y : c0.x, cc1 = half ? c1.y : c1.x, cc2 = half ? c2.y : c2.x;
-                        const float dh = blur_sq_dist(cc0, cc1, cc2, s_pal + 3 * h);
+                        const float dh = blur_sq_dist(half ? c0y : c0x, half ? c1y : c1x, half ? c2y : c2x, s_pal + 3 * h);
                         if (dh < threshold_sq || dh == M) res = h;
                     }
                 }

@@ -718,11 +718,26 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_remap_fast(const FastArgs a
 }
 
 // Diagnostics: the fast f32 Oklab conversion for arrays (tests bound its distance to the exact one).
+// Colours 2i and 2i + 1 go through the packed conversion of the warp-tile and blur kernels, in the form
+// those kernels use it (partial sums over r and g, then b); an odd tail through the scalar one.
 __global__ void k_srgb_to_oklab_fast(const uint8_t* __restrict__ rgb, size_t n, float* __restrict__ out, const ColorTables* __restrict__ tables) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     if (i >= n) return;
-    Lab o = linear_to_oklab_fast(tables->decode[rgb[3 * i]], tables->decode[rgb[3 * i + 1]], tables->decode[rgb[3 * i + 2]]);
-    out[3 * i] = o.l; out[3 * i + 1] = o.a; out[3 * i + 2] = o.b;
+    if (i + 1 >= n) {
+        Lab o = linear_to_oklab_fast(tables->decode[rgb[3 * i]], tables->decode[rgb[3 * i + 1]], tables->decode[rgb[3 * i + 2]]);
+        out[3 * i] = o.l; out[3 * i + 1] = o.a; out[3 * i + 2] = o.b;
+        return;
+    }
+    const f2 r = make_float2(tables->decode[rgb[3 * i]], tables->decode[rgb[3 * i + 3]]);
+    const f2 g = make_float2(tables->decode[rgb[3 * i + 1]], tables->decode[rgb[3 * i + 4]]);
+    const f2 b = make_float2(tables->decode[rgb[3 * i + 2]], tables->decode[rgb[3 * i + 5]]);
+    const f2 pl = fma2(splat(0.5363325363f), g, mul2(splat(0.4122214708f), r));
+    const f2 pm = fma2(splat(0.6806995451f), g, mul2(splat(0.2119034982f), r));
+    const f2 ps = fma2(splat(0.2817188376f), g, mul2(splat(0.0883024619f), r));
+    f2 L, A, B;
+    lms_to_lab2(fma2(splat(0.0514459929f), b, pl), fma2(splat(0.1073969566f), b, pm), fma2(splat(0.6299787005f), b, ps), 1.0f, L, A, B);
+    out[3 * i] = L.x; out[3 * i + 1] = A.x; out[3 * i + 2] = B.x;
+    out[3 * i + 3] = L.y; out[3 * i + 4] = A.y; out[3 * i + 5] = B.y;
 }
 
 }  // namespace lutgen

@@ -70,12 +70,6 @@ struct WarpArgs {
                               // 2 = 16-byte aligned (whole hand-outs leave as 16-byte pieces), 0 = byte stores
 };
 
-typedef float2 f2;
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ f2 splat(float x) { return make_float2(x, x); }
-
 __device__ __forceinline__ float rcp_approx(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -85,28 +79,6 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     float y;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
-}
-
-// x^(1/3) for two LMS values >= 0: MUFU seed for x^(-1/3) + one Newton step, as cbrtf_fast, with the
-// zero guard folded into a clamp (cbrt(1e-30) = 1e-10 is zero at Oklab's resolution).
-__device__ __forceinline__ f2 cbrt2(f2 x) {
-    x.x = fmaxf(x.x, 1e-30f);
-    x.y = fmaxf(x.y, 1e-30f);
-    f2 lg = make_float2(lg2_approx(x.x), lg2_approx(x.y));
-    lg = mul2(lg, splat(-0.33333334f));
-    f2 t = make_float2(ex2_approx(lg.x), ex2_approx(lg.y));
-    f2 v = mul2(mul2(x, t), mul2(t, t));           // x t^3
-    f2 r = fma2(v, splat(-1.0f), splat(1.0f));      // 1 - x t^3
-    t = fma2(mul2(t, splat(0.33333334f)), r, t);
-    return mul2(mul2(x, t), t);
-}
-
-// Two entries' Oklab from their LMS values.
-__device__ __forceinline__ void lms_to_lab2(f2 l, f2 m, f2 s, float lum, f2& L, f2& A, f2& B) {
-    f2 l_ = cbrt2(l), m_ = cbrt2(m), s_ = cbrt2(s);
-    L = mul2(fma2(splat(0.2104542553f), l_, fma2(splat(0.7936177850f), m_, mul2(splat(-0.0040720468f), s_))), splat(lum));
-    A = fma2(splat(1.9779984951f), l_, fma2(splat(-2.4285922050f), m_, mul2(splat(0.4505937099f), s_)));
-    B = fma2(splat(0.0259040371f), l_, fma2(splat(0.7827717662f), m_, mul2(splat(-0.8086757660f), s_)));
 }
 
 __device__ __forceinline__ void oklab_to_linear2(f2 L, f2 A, f2 B, f2& r, f2& g, f2& b) {
