@@ -59,6 +59,15 @@ def load_palette():
         return np.array(json.load(f)["catppuccin_mocha"], np.uint8)
 
 
+def profiled_traffic():
+    """DRAM bytes per launch of the two headline kernels from this round's ncu --set full captures."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -392,7 +401,9 @@ def run_b200(args):
         "e2e": {"value": entries / gen_e2e_t, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 3 * entries,
                 "ms_per_step": gen_e2e_t * 1e3},
         "roofline": {"bound": "fp32", "achieved": gen_achieved, "peak": fp32.value, "unit": "TFLOP/s",
-                     "frac": gen_achieved / fp32.value if fp32.value else None, "traffic": None,
+                     "frac": gen_achieved / fp32.value if fp32.value else None,
+                     "traffic": profiled_traffic().get("k_remap_warp_level16_bytes_per_launch") if world == 1 else None,
+                     "traffic_note": "DRAM bytes of one k_remap_warp launch (ncu --set full, profiles/r1_traffic.json): the CLUT it writes stays in L2",
                      "peak_source": "on-box FFMA micro-benchmark (lutgen_cuda_measure_peaks), this run",
                      "mufu_peak_tops": mufu.value, "kernel_ms": gen_kernel_t * 1e3,
                      "algorithmic_flops_per_entry": GEN_FLOPS_PER_ENTRY,
@@ -418,7 +429,9 @@ def run_b200(args):
                 "h2d_bytes_per_step": e2e_frames * FRAME_PIX * 4 + lut8_host.size, "d2h_bytes_per_step": e2e_frames * FRAME_PIX * 4,
                 "ms_per_step": apply_e2e_t * 1e3},
         "roofline": {"bound": "hbm", "achieved": apply_bw, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": apply_bw / peaks["hbm_gbs"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})"},
+                     "frac": apply_bw / peaks["hbm_gbs"],
+                     "traffic": (profiled_traffic().get("k_apply_bytes_per_pixel") or 0) * apply_pix or None,
+                     "peak_source": f"MEASURED_PEAKS.json ({peak_kind})"},
         "config": {"workload": f"apply level-8 CLUT in place to {frames_per_gpu} x 3840x2160 RGBA8 frames per GPU, uniform random pixels "
                                "(worst case: every gather is its own 32 B L2 sector)",
                    "level": LEVEL_APPLY, "frames_per_gpu": frames_per_gpu,
