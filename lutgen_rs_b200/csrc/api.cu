@@ -319,6 +319,12 @@ int warp_path(const lutgen_remapper* r, uint32_t n, uint32_t k) {
 
 template <int KIND, int MODE, int EPT, bool BIG>
 int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const FastArgs& fa) {
+    // NearestNeighbor on fine grids: tiles 8 planes deep (two groups per lane, one classification), 10 % faster.
+    // Measured and rejected for the RBF kinds (the larger box leaves more colours to choose from per entry:
+    // level-16 Gaussian 0.306 -> 0.342 ms) and for coarse grids (level 8: 0.076 -> 0.127 ms).
+    constexpr int GROUPS_LEAN = (!BIG && MODE != FRONT_IMAGE && KIND == KIND_NN) ? 2 : 1;
+    const bool multi = MODE == FRONT_LUT && f.nextra > 0;
+    const bool deep = GROUPS_LEAN == 2 && !multi && f.cs >= 128 && !getenv("LUTGEN_CUDA_WARP_SHALLOW");
     WarpArgs a{};
     a.f = f;
     a.pal = fa.pal; a.pal_rgb = fa.pal_rgb; a.pal_ab = fa.pal_ab;
@@ -335,7 +341,7 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
         if (const char* e = getenv("LUTGEN_CUDA_STORE")) a.words_ok = std::min(a.words_ok, atoi(e));  // 0 bytes, 1 tile words, 2 hand-out rows
     }
     // BIG: the CTA's eight warp tiles form one 16 x 8 x 2 EPT CTA tile (or 256 EPT pixels)
-    const uint32_t tr = BIG ? 16 : 8, tg = BIG ? 8 : 4, tb = BIG ? 2 * EPT : EPT, tpix = (BIG ? 256u : 32u) * EPT;
+    const uint32_t tr = BIG ? 16 : 8, tg = BIG ? 8 : 4, tb = BIG ? 2 * EPT : (deep ? 2 * EPT : EPT), tpix = (BIG ? 256u : 32u) * EPT;
     if (MODE == FRONT_IMAGE) {
         a.tiles_r = a.tiles_g = 1;
         a.inv_tiles_r = a.inv_tiles_g = 1.0f;
@@ -374,20 +380,21 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
     }
     // MULTI: the variant that stages tiles and writes them to several destinations (multi-GPU); a single
     // destination takes the leaner kernel (the extra code costs instruction-cache misses)
-    const bool multi = MODE == FRONT_LUT && f.nextra > 0;
-    static int per_sm[2] = {0, 0};  // per instantiation
-    if (per_sm[multi] == 0) {
+    const int variant = multi ? 1 : (deep ? 2 : 0);
+    static int per_sm[3] = {0, 0, 0};  // per instantiation
+    if (per_sm[variant] == 0) {
         int v = 0;
         if (BIG) {
             if (multi) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp_big<KIND, MODE, EPT, MODE == FRONT_LUT>, WT_THREADS, 0));
             else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp_big<KIND, MODE, EPT, false>, WT_THREADS, 0));
         } else {
-            if (multi) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, MODE == FRONT_LUT>, WT_THREADS, 0));
-            else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, false>, WT_THREADS, 0));
+            if (multi) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, MODE == FRONT_LUT, 1>, WT_THREADS, 0));
+            else if (deep) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, false, GROUPS_LEAN>, WT_THREADS, 0));
+            else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, false, 1>, WT_THREADS, 0));
         }
-        per_sm[multi] = v < 1 ? 1 : v;
+        per_sm[variant] = v < 1 ? 1 : v;
     }
-    unsigned grid = (unsigned)per_sm[multi] * (unsigned)g.sm_count;
+    unsigned grid = (unsigned)per_sm[variant] * (unsigned)g.sm_count;
     unsigned need = BIG ? a.ntiles : blocks_for(a.ntiles, WT_WARPS * a.batch);
     if (grid > need) grid = need;
     CU_TRY(cudaMemsetAsync(r->flag_count, 0, 2 * sizeof(uint32_t), s));
@@ -395,8 +402,9 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
         if (multi) k_remap_warp_big<KIND, MODE, EPT, MODE == FRONT_LUT><<<grid, WT_THREADS, 0, s>>>(a);
         else k_remap_warp_big<KIND, MODE, EPT, false><<<grid, WT_THREADS, 0, s>>>(a);
     } else {
-        if (multi) k_remap_warp<KIND, MODE, EPT, MODE == FRONT_LUT><<<grid, WT_THREADS, 0, s>>>(a);
-        else k_remap_warp<KIND, MODE, EPT, false><<<grid, WT_THREADS, 0, s>>>(a);
+        if (multi) k_remap_warp<KIND, MODE, EPT, MODE == FRONT_LUT, 1><<<grid, WT_THREADS, 0, s>>>(a);
+        else if (deep) k_remap_warp<KIND, MODE, EPT, false, GROUPS_LEAN><<<grid, WT_THREADS, 0, s>>>(a);
+        else k_remap_warp<KIND, MODE, EPT, false, 1><<<grid, WT_THREADS, 0, s>>>(a);
     }
     LAUNCH_CHECK();
     return LUTGEN_OK;

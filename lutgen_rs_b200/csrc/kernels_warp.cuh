@@ -354,29 +354,40 @@ __device__ __forceinline__ void wt_convert_image(const WarpArgs& a, const WtShar
     }
 }
 
-// The tile's Oklab bounding box (warp reduction), inflated by PAD.
+// Per-lane extent of the tile's colours, then the tile's Oklab bounding box (warp reduction), inflated by PAD.
 template <int EPT>
-__device__ __forceinline__ void wt_box(WtTile<EPT>& T) {
+__device__ __forceinline__ void wt_minmax(const WtTile<EPT>& T, float (&mn)[3], float (&mx)[3], bool first) {
     constexpr int NP = EPT / 2;
-    constexpr uint32_t FULL = 0xffffffffu;
-    float mn[3] = {fminf(T.Lp[0].x, T.Lp[0].y), fminf(T.Ap[0].x, T.Ap[0].y), fminf(T.Bp[0].x, T.Bp[0].y)};
-    float mx[3] = {fmaxf(T.Lp[0].x, T.Lp[0].y), fmaxf(T.Ap[0].x, T.Ap[0].y), fmaxf(T.Bp[0].x, T.Bp[0].y)};
+    if (first) {
+        mn[0] = mx[0] = T.Lp[0].x; mn[1] = mx[1] = T.Ap[0].x; mn[2] = mx[2] = T.Bp[0].x;
+    }
 #pragma unroll
-    for (int i = 1; i < NP; ++i) {
+    for (int i = 0; i < NP; ++i) {
         mn[0] = fminf(mn[0], fminf(T.Lp[i].x, T.Lp[i].y)); mx[0] = fmaxf(mx[0], fmaxf(T.Lp[i].x, T.Lp[i].y));
         mn[1] = fminf(mn[1], fminf(T.Ap[i].x, T.Ap[i].y)); mx[1] = fmaxf(mx[1], fmaxf(T.Ap[i].x, T.Ap[i].y));
         mn[2] = fminf(mn[2], fminf(T.Bp[i].x, T.Bp[i].y)); mx[2] = fmaxf(mx[2], fmaxf(T.Bp[i].x, T.Bp[i].y));
     }
+}
+
+__device__ __forceinline__ void wt_box_reduce(const float (&mn)[3], const float (&mx)[3], float (&lo)[3], float (&hi)[3]) {
+    constexpr uint32_t FULL = 0xffffffffu;
     // warp reduction on integer keys: a, b + 2 are positive floats (|a|, |b| < 0.5 inside the sRGB
     // gamut; the 1.2e-7 rounding disappears in PAD); L*lum can be large and goes through f2key
     const float PAD = 2e-5f;
-    T.lo[0] = key2f(__reduce_min_sync(FULL, f2key(mn[0]))) - PAD;
-    T.hi[0] = key2f(__reduce_max_sync(FULL, f2key(mx[0]))) + PAD;
+    lo[0] = key2f(__reduce_min_sync(FULL, f2key(mn[0]))) - PAD;
+    hi[0] = key2f(__reduce_max_sync(FULL, f2key(mx[0]))) + PAD;
 #pragma unroll
     for (int c = 1; c < 3; ++c) {
-        T.lo[c] = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(mn[c] + 2.0f))) - 2.0f - PAD;
-        T.hi[c] = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(mx[c] + 2.0f))) - 2.0f + PAD;
+        lo[c] = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(mn[c] + 2.0f))) - 2.0f - PAD;
+        hi[c] = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(mx[c] + 2.0f))) - 2.0f + PAD;
     }
+}
+
+template <int EPT>
+__device__ __forceinline__ void wt_box(WtTile<EPT>& T) {
+    float mn[3], mx[3];
+    wt_minmax<EPT>(T, mn, mx, true);
+    wt_box_reduce(mn, mx, T.lo, T.hi);
 }
 
 // What the list holds for palette colour p (header).
@@ -691,9 +702,14 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
 
 // ---------------------------------------------------------------------------------------------
 // Palettes of at most 32 colours: every warp on its own, one palette colour per lane.
-template <int KIND, int MODE, int EPT, bool MULTI>
+// GROUPS = 2 (brick front ends, single destination): the tile is 8 blue planes deep, two groups of four
+// entries per lane that share ONE classification -- the second group's Oklab values wait in shared memory
+// while the first is processed. Halves the classification's share of the work for a slightly larger box.
+template <int KIND, int MODE, int EPT, bool MULTI, int GROUPS>
 __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpArgs a) {
     static_assert(EPT == 4, "entries are processed in two pairs (wt_store_entries takes four results)");
+    static_assert(GROUPS == 1 || (GROUPS == 2 && MODE != FRONT_IMAGE && !MULTI), "two groups: brick tiles of the lean kernel only");
+    constexpr uint32_t TD = (uint32_t)EPT * GROUPS;   // blue planes per tile
     constexpr uint32_t FULL = 0xffffffffu;
     constexpr bool BRICK = MODE != FRONT_IMAGE;
     __shared__ SmemTables st;
@@ -703,6 +719,7 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
     __shared__ __align__(8) float2 s_bnd[WT_WARPS][WT_MAX_N];
     __shared__ uint32_t s_cidx[WT_WARPS][WT_MAX_N];
     __shared__ uint32_t s_hit[WT_WARPS][FAST_MAX_HITS];
+    __shared__ f2 s_stash[GROUPS == 2 ? WT_WARPS : 1][6][GROUPS == 2 ? 32 : 1];   // the second group's Lp, Ap, Bp pairs
     __shared__ __align__(16) uint32_t s_stage[MULTI ? WT_WARPS : 1][MULTI ? EPT * 24 * WT_BATCH : 1];
     __shared__ uint8_t* s_extra[LUTGEN_MAX_PEERS];
 
@@ -769,18 +786,36 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
             // ---- 1. colours of this tile -> Oklab (register pairs), bounding box ----------------
             WtTile<EPT> T;
             sg.slot = sg.defer ? t - t0 : 0u;
+            uint32_t valid1 = 0, tile_b0 = 0;
             if (BRICK) {
-                const uint32_t r0 = ir * 8u, g0 = ig * 4u, b0 = a.b_lo + ib * (uint32_t)EPT;
+                const uint32_t r0 = ir * 8u, g0 = ig * 4u, b0 = a.b_lo + ib * TD;
+                tile_b0 = b0;
                 if (++ir == a.tiles_r) { ir = 0; if (++ig == a.tiles_g) { ig = 0; ++ib; } }
                 const uint32_t first = (b0 * cs + g0) * cs + r0;
-                const uint32_t last = (min(b0 + EPT - 1, csm1) * cs + min(g0 + 3u, csm1)) * cs + min(r0 + 7u, csm1);
+                const uint32_t last = (min(b0 + TD - 1, csm1) * cs + min(g0 + 3u, csm1)) * cs + min(r0 + 7u, csm1);
                 if (b0 > csm1 || last < begin || first >= end) continue;  // uniform
+                float mn[3], mx[3];
+                if (GROUPS == 2) {
+                    // second group first: its colours go to the stash, its extent into the box
+                    wt_convert_brick<EPT>(a, sh, lane, r0, g0, b0 + (uint32_t)EPT, T);
+                    wt_minmax<EPT>(T, mn, mx, true);
+                    valid1 = T.valid_mask;
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < EPT / 2; ++i) {
+                        s_stash[warp][i][lane] = T.Lp[i]; s_stash[warp][2 + i][lane] = T.Ap[i]; s_stash[warp][4 + i][lane] = T.Bp[i];
+                    }
+                }
                 wt_convert_brick<EPT>(a, sh, lane, r0, g0, b0, T);
+                wt_minmax<EPT>(T, mn, mx, GROUPS == 1);
+                if (GROUPS == 2) T.bhi[2] = s_chv[min(b0 + TD - 1, csm1)];
+                if (!__any_sync(FULL, (T.valid_mask | valid1) != 0)) continue;
+                wt_box_reduce(mn, mx, T.lo, T.hi);
             } else {
                 wt_convert_image<EPT>(a, sh, lane, t * (32u * EPT), T);
+                if (!__any_sync(FULL, T.valid_mask != 0)) continue;
+                wt_box<EPT>(T);
             }
-            if (!__any_sync(FULL, T.valid_mask != 0)) continue;
-            wt_box<EPT>(T);
 
             // ---- 2.-4. classification, one palette colour per lane --------------------------------
             WtClass cl;
@@ -848,7 +883,21 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
             }
             // ---- 5. per entry ------------------------------------------------------------------
             if (MULTI && t == t0) { batch_flat0 = __shfl_sync(FULL, T.slot0, 0); batch_step = T.slot_step; }
-            wt_entries<KIND, MODE, EPT, MULTI>(a, st, T, cl, cand, cidx, hits, sg);
+#pragma unroll 1
+            for (int grp = 0; grp < GROUPS; ++grp) {
+                if (GROUPS == 2 && grp == 1) {
+                    // the second group: same classification, its own colours
+#pragma unroll
+                    for (int i = 0; i < EPT / 2; ++i) {
+                        T.Lp[i] = s_stash[warp][i][lane]; T.Ap[i] = s_stash[warp][2 + i][lane]; T.Bp[i] = s_stash[warp][4 + i][lane];
+                    }
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e) T.Bq[e] = s_chv[min(tile_b0 + (uint32_t)EPT + e, csm1)];
+                    T.slot0 += (uint32_t)EPT * T.slot_step;
+                    T.valid_mask = valid1;
+                }
+                wt_entries<KIND, MODE, EPT, MULTI>(a, st, T, cl, cand, cidx, hits, sg);
+            }
         }
         if (MULTI && sg.staged) {
             __syncwarp();
