@@ -580,7 +580,7 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
         return;
     }
     uint32_t flag_mask = 0;
-    if (KIND == KIND_NN) {
+    if constexpr (KIND == KIND_NN) {
         uint32_t best_j[EPT];
         uint32_t risky_mask = 0;
 #pragma unroll
@@ -631,8 +631,7 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
         wt_store<MODE, EPT, MULTI>(a, T, res, T.valid_mask & ~risky_mask, stage);
         if (flag_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, flag_mask, T.slot0, T.slot_step);
         return;
-    }
-
+    } else {
     f2 n0[NP], n1[NP], n2[NP], den[NP], cc[NP];
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
@@ -698,6 +697,7 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
     }
     wt_store<MODE, EPT, MULTI>(a, T, res, smask, stage);
     if (flag_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, flag_mask, T.slot0, T.slot_step);
+    }  // RBF kinds
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -950,7 +950,6 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp_big(const Wa
     __shared__ uint32_t s_riv[WT_WARPS][WB_MAX_M];
     __shared__ __align__(16) float4 s_surv[WB_MAX_N];   // survivors of the CTA level (palette order)
     __shared__ uint32_t s_sidx[WB_MAX_N];               // their palette indices
-    __shared__ uint32_t s_srgb[WB_MAX_N];               // their packed sRGB
     __shared__ uint32_t s_hit[FAST_MAX_HITS];
     __shared__ uint32_t s_stage[MULTI ? WT_WARPS : 1][MULTI ? EPT * 24 : 1];
     __shared__ uint8_t* s_extra[LUTGEN_MAX_PEERS];
