@@ -145,11 +145,11 @@ public:
     void par_remap_image_with_interrupt(RgbaImage& image, const std::atomic<bool>& abort) const { remap_image_with_interrupt(image, abort); }
 
     // GenerateLut::generate_lut / par_generate_lut            lib.rs:136-147
-    RgbImage generate_lut(uint8_t level) const { return *generate(level, nullptr); }
-    RgbImage par_generate_lut(uint8_t level) const { return generate_lut(level); }
+    RgbImage generate_lut(uint8_t level) const { return *generate(level, nullptr, true); }
+    RgbImage par_generate_lut(uint8_t level) const { return *generate(level, nullptr, false); }
     // GenerateLut::*_with_interrupt -> Option<RgbImage>       lib.rs:149-170
-    std::optional<RgbImage> generate_lut_with_interrupt(uint8_t level, const std::atomic<bool>& abort) const { return generate(level, &abort); }
-    std::optional<RgbImage> par_generate_lut_with_interrupt(uint8_t level, const std::atomic<bool>& abort) const { return generate(level, &abort); }
+    std::optional<RgbImage> generate_lut_with_interrupt(uint8_t level, const std::atomic<bool>& abort) const { return generate(level, &abort, true); }
+    std::optional<RgbImage> par_generate_lut_with_interrupt(uint8_t level, const std::atomic<bool>& abort) const { return generate(level, &abort, false); }
 
     const lutgen_remapper* handle() const { return handle_; }
 
@@ -170,12 +170,15 @@ protected:
     lutgen_remapper* handle_ = nullptr;
 
 private:
-    std::optional<RgbImage> generate(uint8_t level, const std::atomic<bool>* abort) const {
+    std::optional<RgbImage> generate(uint8_t level, const std::atomic<bool>* abort, bool sequential = false) const {
         bool ok = level >= 2 && level <= 33;
         uint32_t side = ok ? (uint32_t)level * level * level : 1;
         RgbImage out(side, side);
-        if (detail::check(lutgen_cuda_generate_lut(handle_, level, out.data.data(), abort ? detail::flag_ptr(abort) : nullptr)))
-            return std::nullopt;
+        const volatile uint8_t* flag = abort ? detail::flag_ptr(abort) : nullptr;
+        // the sequential spellings differ from the par_* ones for GaussianBlurRemapper only (hint chain across rows)
+        int rc = sequential ? lutgen_cuda_generate_lut_sequential(handle_, level, out.data.data(), flag)
+                            : lutgen_cuda_generate_lut(handle_, level, out.data.data(), flag);
+        if (detail::check(rc)) return std::nullopt;
         return out;
     }
 };
@@ -235,7 +238,8 @@ public:
 
 // GaussianBlurRemapper::new(palette, radius, lum_factor, preserve)                gaussian_blur.rs:34-53
 // The CLI's and Studio's default. Like the reference type it implements GenerateLut only
-// (gaussian_blur.rs:512-541): the remap_* members are not exposed.
+// (gaussian_blur.rs:512-541): the remap_* members are not exposed. generate_lut* follow
+// generate_lut_inner (hint carried across rows), par_generate_lut* follow par_generate_lut_inner.
 class GaussianBlurRemapper : private InterpolatedRemapper {
 public:
     GaussianBlurRemapper(const Palette& palette, double radius, double lum_factor, bool preserve) {

@@ -143,6 +143,14 @@ LUTGEN_API int lutgen_cuda_remapper_destroy(lutgen_remapper* r);
  * unspecified (the reference returns None, lib.rs:149-170). */
 LUTGEN_API int lutgen_cuda_generate_lut(const lutgen_remapper* r, uint8_t level, uint8_t* out_rgb,
                                         const volatile uint8_t* abort_flag);
+
+/* GenerateLut::generate_lut / generate_lut_with_interrupt, the SEQUENTIAL spellings (lib.rs:113-132). Identical to
+ * lutgen_cuda_generate_lut for every remapper but GaussianBlurRemapper, whose sequential generate_lut_inner carries
+ * the nearest-neighbour hint from the end of one (r, g) row into the next (gaussian_blur.rs:213) where
+ * par_generate_lut_inner restarts it (l.339): the two differ in cells that lie within the early-exit threshold of
+ * two palette colours. The par_* spellings bind lutgen_cuda_generate_lut. */
+LUTGEN_API int lutgen_cuda_generate_lut_sequential(const lutgen_remapper* r, uint8_t level, uint8_t* out_rgb,
+                                                   const volatile uint8_t* abort_flag);
 /* Row shard of the same: rows [row_begin, row_end) of the level^3 x level^3 CLUT
  * are written at their place inside the full-size device image lut_rgb_dev
  * (3*level^6 B). This is the unit the multi-GPU path all-gathers. */

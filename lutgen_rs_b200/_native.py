@@ -28,6 +28,7 @@ EXPORTS = [
     "lutgen_cuda_generate_lut_rows_multi_dev", "lutgen_cuda_device_alloc", "lutgen_cuda_device_free",
     "lutgen_cuda_ipc_export", "lutgen_cuda_ipc_import", "lutgen_cuda_ipc_close",
     "lutgen_cuda_generate_lut_shard_multi_dev", "lutgen_cuda_peer_barrier_dev", "lutgen_cuda_generate_lut_shard_mc_dev",
+    "lutgen_cuda_generate_lut_sequential",
 ]
 
 
@@ -96,6 +97,7 @@ def load():
             "lutgen_cuda_remapper_create": ([C.POINTER(RemapperDesc), C.POINTER(vp)], i32),
             "lutgen_cuda_remapper_destroy": ([vp], i32),
             "lutgen_cuda_generate_lut": ([vp, u8, vp, vp], i32),
+            "lutgen_cuda_generate_lut_sequential": ([vp, u8, vp, vp], i32),
             "lutgen_cuda_generate_lut_rows_dev": ([vp, u8, vp, u32, u32, vp], i32),
             "lutgen_cuda_remap_image": ([vp, vp, sz, vp], i32),
             "lutgen_cuda_remap_image_dev": ([vp, vp, sz, vp], i32),

@@ -156,6 +156,8 @@ struct lutgen_remapper {
     mutable size_t blur_vol_cap = 0;
     mutable uint8_t* blur_chan = nullptr;
     mutable int blur_level = 0;       // level whose blurred volume sits in blur_vol[blur_result]
+    mutable int blur_sequential = 0;  // ... computed with generate_lut_inner's (1) or par_generate_lut_inner's (0) hint rule
+    mutable uint32_t* blur_ends = nullptr;  // sequential mode: 2 x size^2 row-end hints + 1 change counter
     mutable int blur_result = 0;
     mutable cudaEvent_t blur_ev = nullptr;
 };
@@ -565,10 +567,10 @@ int launch_sampling(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
 // ---- GaussianBlurRemapper -----------------------------------------------------------------
 // generate_lut_inner / par_generate_lut_inner, gaussian_blur.rs:197-431 (par semantics: the NN
 // hint restarts per (r, g) row, which is what the CLI and Studio call).
-int ensure_blur_volume(const lutgen_remapper* r, uint32_t level, cudaStream_t s) {
+int ensure_blur_volume(const lutgen_remapper* r, uint32_t level, int sequential, cudaStream_t s) {
     std::unique_lock<std::mutex> lk(r->mu);
     if (!r->blur_ev) CU_TRY(cudaEventCreateWithFlags(&r->blur_ev, cudaEventDisableTiming));
-    if (r->blur_level != (int)level) {
+    if (r->blur_level != (int)level || r->blur_sequential != sequential) {
         const uint32_t size = level * level, ch = r->d.preserve ? 2u : 3u;
         const size_t cells = (size_t)size * size * size, bytes = cells * ch * sizeof(float);
         if (r->blur_vol_cap < bytes) {
@@ -605,8 +607,30 @@ int ensure_blur_volume(const lutgen_remapper* r, uint32_t level, cudaStream_t s)
         }
         const int stage_pal = (size_t)r->n * 28 <= 64 * 1024;   // palette (3 floats) + expanded form (4 floats) per colour
         const size_t smem_nn = 1024 + (stage_pal ? (size_t)r->n * 28 + 32 : 0);
-        blur_launch_nn_volume(grid_nn, smem_nn, s, a, size, ch, r->blur_chan, r->blur_pal3, r->blur_out3, r->n, lum, threshold_sq, g.tables, stage_pal);
-        LAUNCH_CHECK();
+        if (!sequential) {
+            blur_launch_nn_volume(grid_nn, smem_nn, s, a, size, ch, r->blur_chan, r->blur_pal3, r->blur_out3, r->n, lum, threshold_sq, g.tables, stage_pal,
+                                  nullptr, nullptr, nullptr);
+            LAUNCH_CHECK();
+        } else {
+            // generate_lut_inner: the hint runs on from row to row (gaussian_blur.rs:213). Passes until no row's
+            // final hint changes; the first pass starts every row from 0 like the parallel variant does.
+            if (r->blur_ends) { CU_TRY(cudaFree(r->blur_ends)); r->blur_ends = nullptr; }
+            CU_TRY(cudaMalloc((void**)&r->blur_ends, sizeof(uint32_t) * (2 * (size_t)rows + 1)));
+            CU_TRY(cudaMemsetAsync(r->blur_ends, 0, sizeof(uint32_t) * (2 * (size_t)rows + 1), s));
+            uint32_t* ends[2] = {r->blur_ends, r->blur_ends + rows};
+            uint32_t* changed = r->blur_ends + 2 * (size_t)rows;
+            for (uint32_t pass = 0;; ++pass) {
+                if (pass > rows + 1) return fail(LUTGEN_ERR_CUDA, "blur: the row hint chain did not settle");
+                CU_TRY(cudaMemsetAsync(changed, 0, sizeof(uint32_t), s));
+                blur_launch_nn_volume(grid_nn, smem_nn, s, a, size, ch, r->blur_chan, r->blur_pal3, r->blur_out3, r->n, lum, threshold_sq, g.tables,
+                                      stage_pal, ends[pass & 1], ends[(pass & 1) ^ 1], changed);
+                LAUNCH_CHECK();
+                uint32_t nchanged = 0;
+                CU_TRY(cudaMemcpyAsync(&nchanged, changed, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+                CU_TRY(cudaStreamSynchronize(s));
+                if (nchanged == 0) break;
+            }
+        }
         const int klen = r->blur_klen;
         // columns per CTA: an even number that keeps tile + taps within ~48 KB (several CTAs per SM),
         // but never fewer than one cell's channels; the B pass takes whole rows (ch columns each)
@@ -648,6 +672,7 @@ int ensure_blur_volume(const lutgen_remapper* r, uint32_t level, cudaStream_t s)
         }
         r->blur_result = 1;
         r->blur_level = (int)level;
+        r->blur_sequential = sequential;
         CU_TRY(cudaEventRecord(r->blur_ev, s));
     }
     CU_TRY(cudaStreamWaitEvent(s, r->blur_ev, 0));
@@ -657,7 +682,7 @@ int ensure_blur_volume(const lutgen_remapper* r, uint32_t level, cudaStream_t s)
 int launch_blur_lut(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
     uint32_t level = 2;
     while (level * level < f.cs) ++level;
-    int rc = ensure_blur_volume(r, level, s);
+    int rc = ensure_blur_volume(r, level, f.sequential, s);
     if (rc != LUTGEN_OK) return rc;
     if (f.count == 0) return LUTGEN_OK;
     const uint32_t ch = r->d.preserve ? 2u : 3u;
@@ -1017,6 +1042,7 @@ int lutgen_cuda_remapper_destroy(lutgen_remapper* r) {
         cudaFree(r->blur_vol[0]);
         cudaFree(r->blur_vol[1]);
         cudaFree(r->blur_chan);
+        cudaFree(r->blur_ends);
         if (r->blur_ev) cudaEventDestroy(r->blur_ev);
     }
     delete r;
@@ -1175,8 +1201,19 @@ int lutgen_cuda_sampling_set_noise(lutgen_remapper* r, const double* noise) {
     return rc;
 }
 
+namespace {
+int generate_lut_rows_impl(const lutgen_remapper* r, uint8_t level, uint8_t* lut_rgb_dev, uint32_t row_begin, uint32_t row_end, void* stream,
+                           int sequential);
+}
+
 int lutgen_cuda_generate_lut_rows_dev(const lutgen_remapper* r, uint8_t level, uint8_t* lut_rgb_dev, uint32_t row_begin, uint32_t row_end,
                                       void* stream) {
+    return generate_lut_rows_impl(r, level, lut_rgb_dev, row_begin, row_end, stream, 0);
+}
+
+namespace {
+int generate_lut_rows_impl(const lutgen_remapper* r, uint8_t level, uint8_t* lut_rgb_dev, uint32_t row_begin, uint32_t row_end, void* stream,
+                           int sequential) {
     int rc = ensure_ready();
     if (rc) return rc;
     if (!r || !lut_rgb_dev) return fail(LUTGEN_ERR_INVALID, "NULL argument");
@@ -1190,9 +1227,21 @@ int lutgen_cuda_generate_lut_rows_dev(const lutgen_remapper* r, uint8_t level, u
     f.count = (unsigned long long)(row_end - row_begin) * side;
     f.cs = (uint32_t)level * level;
     f.csm1 = f.cs - 1;
+    f.sequential = sequential;
     rc = launch_remap<FRONT_LUT>(f, r, s);
     if (rc) return rc;
     return LUTGEN_OK;
+}
+
+int generate_lut_impl(const lutgen_remapper* r, uint8_t level, uint8_t* out_rgb, const volatile uint8_t* abort_flag, int sequential);
+}  // namespace
+
+int lutgen_cuda_generate_lut(const lutgen_remapper* r, uint8_t level, uint8_t* out_rgb, const volatile uint8_t* abort_flag) {
+    return generate_lut_impl(r, level, out_rgb, abort_flag, 0);
+}
+
+int lutgen_cuda_generate_lut_sequential(const lutgen_remapper* r, uint8_t level, uint8_t* out_rgb, const volatile uint8_t* abort_flag) {
+    return generate_lut_impl(r, level, out_rgb, abort_flag, 1);
 }
 
 int lutgen_cuda_generate_lut_rows_multi_dev(const lutgen_remapper* r, uint8_t level, uint8_t* const* luts_rgb_dev, int nluts, uint32_t row_begin,
@@ -1324,7 +1373,8 @@ int lutgen_cuda_ipc_close(void* dev_ptr) {
     return LUTGEN_OK;
 }
 
-int lutgen_cuda_generate_lut(const lutgen_remapper* r, uint8_t level, uint8_t* out_rgb, const volatile uint8_t* abort_flag) {
+namespace {
+int generate_lut_impl(const lutgen_remapper* r, uint8_t level, uint8_t* out_rgb, const volatile uint8_t* abort_flag, int sequential) {
     int rc = ensure_ready();
     if (rc) return rc;
     if (!r || !out_rgb) return fail(LUTGEN_ERR_INVALID, "NULL argument");
@@ -1350,7 +1400,7 @@ int lutgen_cuda_generate_lut(const lutgen_remapper* r, uint8_t level, uint8_t* o
     for (uint32_t c = 0; c < chunks && result == LUTGEN_OK; ++c) {
         uint32_t r0 = (uint32_t)((uint64_t)ngroups * c / chunks) * group, r1 = (uint32_t)((uint64_t)ngroups * (c + 1) / chunks) * group;
         if (r1 > side) r1 = side;
-        rc = lutgen_cuda_generate_lut_rows_dev(r, level, (uint8_t*)g.lut_rgb.p, r0, r1, g.stream);
+        rc = generate_lut_rows_impl(r, level, (uint8_t*)g.lut_rgb.p, r0, r1, g.stream, sequential);
         if (rc) { result = rc; break; }
         cudaError_t e = cudaEventRecord(done[c], g.stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(copy_stream, done[c], 0);
@@ -1370,6 +1420,7 @@ int lutgen_cuda_generate_lut(const lutgen_remapper* r, uint8_t level, uint8_t* o
     if (abort_flag && *abort_flag) return LUTGEN_ABORTED;
     return LUTGEN_OK;
 }
+}  // namespace
 
 int lutgen_cuda_remap_image_dev(const lutgen_remapper* r, uint8_t* rgba_dev, size_t npix, void* stream) {
     int rc = ensure_ready();

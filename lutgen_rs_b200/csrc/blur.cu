@@ -15,8 +15,10 @@ void blur_launch_palette(unsigned grid, cudaStream_t s, const uint8_t* pal_rgb4,
 }
 
 void blur_launch_nn_volume(unsigned grid, size_t smem, cudaStream_t s, float* colors, uint32_t size, uint32_t ch, const uint8_t* chan, const float* pal3,
-                           const float* out3, uint32_t n, float lum, float threshold_sq, const ColorTables* tables, int stage_palette) {
-    k_blur_nn_volume<<<grid, BLUR_ROW_WARPS * 32, smem, s>>>(colors, size, ch, chan, pal3, out3, n, lum, threshold_sq, tables, stage_palette, 1.0f);
+                           const float* out3, uint32_t n, float lum, float threshold_sq, const ColorTables* tables, int stage_palette,
+                           const uint32_t* end_prev, uint32_t* end_cur, uint32_t* changed) {
+    k_blur_nn_volume<<<grid, BLUR_ROW_WARPS * 32, smem, s>>>(colors, size, ch, chan, pal3, out3, n, lum, threshold_sq, tables, stage_palette, 1.0f,
+                                                             end_prev, end_cur, changed);
 }
 
 void blur_launch_axis(unsigned grid, size_t smem, cudaStream_t s, const float* src, float* dst, const BlurAxis& P, const float* kernel, int klen) {

@@ -79,7 +79,14 @@ __device__ __forceinline__ void blur_scan_exact(float lr, float lg, float lb, fl
 __global__ void __launch_bounds__(BLUR_ROW_WARPS * 32) k_blur_nn_volume(float* __restrict__ colors, uint32_t size, uint32_t ch, const uint8_t* __restrict__ chan,
                                                                          const float* __restrict__ pal3, const float* __restrict__ out3, uint32_t n,
                                                                          float lum, float threshold_sq, const ColorTables* __restrict__ tables,
-                                                                         int stage_palette, float one) {
+                                                                         int stage_palette, float one, const uint32_t* __restrict__ end_prev,
+                                                                         uint32_t* __restrict__ end_cur, uint32_t* __restrict__ changed) {
+    // end_prev / end_cur / changed (all NULL for par_generate_lut_inner, where every row starts from
+    // hint 0): generate_lut_inner carries the hint from the last cell of a row into the next row
+    // (gaussian_blur.rs:213). Rows are computed in parallel here, so the sequential chain is reached by
+    // iteration: a row starts from end_prev[row - 1], the hint the previous pass left at the end of the
+    // row before it, writes its own end to end_cur[row] and counts a change; the host repeats the pass
+    // until nothing changes (the starting hint matters only in ambiguous cells: two passes in practice).
     extern __shared__ __align__(16) float s_blur_nn[];   // decode[256] | when it fits: palette 3n | q 4n (-2p, |p|^2)
     float* s_decode = s_blur_nn;
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_decode[i] = tables->decode[i];
@@ -100,7 +107,7 @@ __global__ void __launch_bounds__(BLUR_ROW_WARPS * 32) k_blur_nn_volume(float* _
     for (uint32_t row = blockIdx.x * BLUR_ROW_WARPS + warp; row < rows; row += gridDim.x * BLUR_ROW_WARPS) {
         const uint32_t r = row / size, g = row % size;
         const float lr = s_decode[chan[r]], lg = s_decode[chan[g]];
-        uint32_t hint = 0;  // result of the previous cell
+        uint32_t hint = (end_prev && row > 0) ? end_prev[row - 1] : 0u;  // result of the previous cell
         for (uint32_t b0 = 0; b0 < size; b0 += 64) {
             // cells b0 + lane (x) and b0 + 32 + lane (y); past the end they repeat the last cell
             const uint32_t bx = min(b0 + lane, size - 1), by = min(b0 + 32 + lane, size - 1);
@@ -180,6 +187,10 @@ __global__ void __launch_bounds__(BLUR_ROW_WARPS * 32) k_blur_nn_volume(float* _
                     else { dst[0] = t[0]; dst[1] = t[1]; dst[2] = t[2]; }
                 }
             }
+        }
+        if (end_cur && lane == 0) {
+            if (end_prev[row] != hint) atomicAdd(changed, 1u);
+            end_cur[row] = hint;
         }
     }
 }

@@ -44,6 +44,8 @@ struct Front {
     // walk tiles take every shard_count-th hand-out (balanced whatever the colours cost); the others
     // are given the shard's contiguous rows instead (api.cu: rows_of_shard).
     uint32_t shard_index, shard_count;
+    // GaussianBlurRemapper only: generate_lut_inner's hint chain across rows instead of par_generate_lut_inner's
+    int sequential;
 };
 
 struct RemapParams {

@@ -92,10 +92,21 @@ class InterpolatedRemapper:
     par_remap_image_with_interrupt = remap_image_with_interrupt
 
     # -- GenerateLut ---------------------------------------------------------
+    # The sequential and the par_* spellings (lib.rs:113-132) bind two entry points: they only differ
+    # for GaussianBlurRemapper, whose sequential variant carries its hint across rows.
     def generate_lut(self, level, out=None):
-        return self.generate_lut_with_interrupt(level, None, out=out)
+        return self._generate(level, None, out, sequential=True)
 
     def generate_lut_with_interrupt(self, level, abort, out=None):
+        return self._generate(level, abort, out, sequential=True)
+
+    def par_generate_lut(self, level, out=None):
+        return self._generate(level, None, out, sequential=False)
+
+    def par_generate_lut_with_interrupt(self, level, abort, out=None):
+        return self._generate(level, abort, out, sequential=False)
+
+    def _generate(self, level, abort, out, sequential):
         """`out` (optional, not in the reference): a preallocated (n, n, 3) uint8 array to fill,
         e.g. page-locked memory so the device-to-host copy is a single DMA."""
         level = int(level)
@@ -106,11 +117,10 @@ class InterpolatedRemapper:
             out = np.empty((n, n, 3), np.uint8)
         elif out.dtype != np.uint8 or out.size != 3 * n * n or not out.flags.c_contiguous:
             raise TypeError("out must be a contiguous uint8 array of 3*level^6 bytes")
-        aborted = _native.check(_native.lib().lutgen_cuda_generate_lut(self._h, level, _ptr(out), _abort_ptr(abort)))
+        L = _native.lib()
+        fn = L.lutgen_cuda_generate_lut_sequential if sequential else L.lutgen_cuda_generate_lut
+        aborted = _native.check(fn(self._h, level, _ptr(out), _abort_ptr(abort)))
         return None if aborted else out
-
-    par_generate_lut = generate_lut
-    par_generate_lut_with_interrupt = generate_lut_with_interrupt
 
 
 class GaussianRemapper(InterpolatedRemapper):
@@ -171,8 +181,9 @@ class GaussianBlurRemapper(InterpolatedRemapper):
 
     The CLI's and Studio's default algorithm. Like the reference type it implements `GenerateLut`
     only (gaussian_blur.rs:512-541): the `remap_*` methods of `InterpolatedRemapper` do not exist on
-    it. All four generate spellings follow `par_generate_lut_inner` (the nearest-neighbour hint
-    restarts per (r, g) row), which is what the reference's callers use.
+    it. `par_generate_lut*` follow `par_generate_lut_inner` (the nearest-neighbour hint restarts per
+    (r, g) row; what the CLI and Studio call), `generate_lut*` follow `generate_lut_inner` (the hint
+    carries on from row to row).
     """
     _kind = _native.BLUR
 

@@ -58,10 +58,41 @@ def test_blur_degenerate_radii(palettes, radius):
 def test_blur_sequential_hint_variant_agrees_here(palettes):
     """generate_lut_inner carries the NN hint across rows, par_generate_lut_inner restarts it; the two
     can only differ where a stale hint is within the early-exit threshold. Record that they agree on
-    the CLI default configuration (the GPU follows the par variant, which the callers use)."""
+    the CLI default configuration (the tests below use a palette where they do not)."""
     pal = palettes["catppuccin_mocha"]
     orc = O.Remapper(O.BLUR, pal, param=8.0, lum_factor=1.0, preserve=False)
     assert (orc.generate_lut(8) == orc.generate_lut(8, sequential_hints=True)).all()
+
+
+def _near_duplicate_palette():
+    """Colours a few sRGB steps apart: at coarse levels the early-exit threshold 0.5/size^2 reaches
+    from one to the other, so the nearest-neighbour hint decides and the two variants differ."""
+    base = np.array([[200, 60, 60], [60, 200, 60], [60, 60, 200], [128, 128, 128], [20, 20, 20], [240, 240, 240]], np.int16)
+    near = base + np.array([[3, -2, 2], [-3, 2, 1], [2, 3, -2], [2, 2, 2], [3, 3, 3], [-3, -3, -3]], np.int16)
+    near2 = base + np.array([[-2, 3, -3], [2, -3, -2], [-3, -2, 3], [-3, -3, -3], [5, 4, 6], [-6, -5, -4]], np.int16)
+    return np.concatenate([base, near, near2]).clip(0, 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("level,radius,preserve", [(3, 1.0, False), (4, 2.0, False), (5, 1.5, True), (6, 3.0, False)])
+def test_blur_sequential_variant_follows_generate_lut_inner(level, radius, preserve):
+    """generate_lut (sequential: the hint carries on from row to row, gaussian_blur.rs:213) against
+    the oracle's sequential restatement, on a palette where it differs from the parallel variant;
+    par_generate_lut on the same palette against the parallel restatement."""
+    pal = _near_duplicate_palette()
+    r = interpolation.GaussianBlurRemapper(pal, radius, 1.0, preserve)
+    orc = O.Remapper(O.BLUR, pal, param=radius, lum_factor=1.0, preserve=preserve)
+    want_seq, want_par = orc.generate_lut(level, sequential_hints=True), orc.generate_lut(level)
+    got_seq, got_par = r.generate_lut(level), r.par_generate_lut(level)
+    assert (got_par == want_par).all(), int((got_par != want_par).sum())
+    assert (got_seq == want_seq).all(), int((got_seq != want_seq).sum())
+    # and alternating between them does not serve one from the other's cached volume
+    assert (r.par_generate_lut(level) == want_par).all() and (r.generate_lut(level) == want_seq).all()
+
+
+def test_blur_the_two_variants_do_differ_somewhere():
+    pal = _near_duplicate_palette()
+    orc = O.Remapper(O.BLUR, pal, param=1.0, lum_factor=1.0, preserve=False)
+    assert any((orc.generate_lut(lv) != orc.generate_lut(lv, sequential_hints=True)).any() for lv in (3, 4, 5, 6))
 
 
 def test_blur_generate_variants_and_interrupt(palettes):
