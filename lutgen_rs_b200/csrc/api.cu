@@ -636,13 +636,14 @@ int ensure_blur_volume(const lutgen_remapper* r, uint32_t level, int sequential,
         // but never fewer than one cell's channels; the B pass takes whole rows (ch columns each)
         auto launch_axis = [&](const float* src, float* dst, BlurAxis P, uint32_t outers) -> int {
             P.groups = (P.total_cols + P.cols - 1) / P.cols;
-            size_t smem = ((size_t)P.size * P.pitch + (size_t)klen + 4) * sizeof(float);
-            if (smem > 200 * 1024) return fail(LUTGEN_ERR_UNSUPPORTED, "blur: %zu bytes of shared memory per tile (level %u, radius %g)", smem, level, r->d.param);
+            // tile rows: `size` positions + the replicated rows either side; zero-padded weights behind it
+            size_t smem = ((size_t)((P.size + 3u) / 4u * 4u + 2u * (uint32_t)(klen / 2) + 3u) * P.pitch + (size_t)((klen + 6) / 4 * 4 + 4)) * sizeof(float);
+            if (smem > 227 * 1024) return fail(LUTGEN_ERR_UNSUPPORTED, "blur: %zu bytes of shared memory per tile (level %u, radius %g)", smem, level, r->d.param);
             blur_launch_axis(P.groups * outers, smem, s, src, dst, P, r->blur_kernel, klen);
             LAUNCH_CHECK();
             return LUTGEN_OK;
         };
-        uint32_t want = 12288u / size;
+        uint32_t want = 12288u / (size + 2u * (uint32_t)(klen / 2) + 6u);
         if (want > 32) want = 32;
         if (want < 2) want = 2;
         {   // pass 1: B axis (innermost)

@@ -7,7 +7,7 @@ namespace lutgen {
 cudaError_t blur_set_attributes() {
     cudaError_t e = cudaFuncSetAttribute(k_blur_nn_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_blur_axis, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    return cudaFuncSetAttribute(k_blur_axis, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
 void blur_launch_palette(unsigned grid, cudaStream_t s, const uint8_t* pal_rgb4, uint32_t n, float lum, const float* decode, float* pal3, float* out3) {

@@ -199,109 +199,81 @@ __global__ void __launch_bounds__(BLUR_ROW_WARPS * 32) k_blur_nn_volume(float* _
 // accumulated in tap order with a rounded multiply and a rounded add per tap (no FMA: blur_add2).
 //
 // One thread produces 4 consecutive positions p0 .. p0+3 of TWO neighbouring columns, as float2
-// accumulators (FMUL2 + FADD2: the two columns share the weight, which is the scalar operand).
-// Output q's tap k reads position clamp(p0 + q + k - half); stepping j = q + k, every output needs
-// the SAME input row clamp(p0 + j - half) at step j (with its own weight kw[j - q]), and each
-// output still meets its taps in increasing k. So one 8-byte shared-memory load and one clamp serve
-// 8 outputs, and the sums are bit-identical to the one-output-at-a-time loop.
+// accumulators (FMUL2 + FFMA2 via blur_add2: the two columns share the weight, which is the scalar
+// operand). Output q's tap k reads position clamp(p0 + q + k - half); stepping j = q + k, every output
+// needs the SAME input row clamp(p0 + j - half) at step j (with its own weight kw[j - q]), and each
+// output still meets its taps in increasing k. So one 8-byte shared-memory load serves 8 outputs, and
+// the sums are bit-identical to the one-output-at-a-time loop.
+//
+// Two things keep the loop uniform. (1) The tile carries `half` replicated rows before position 0 and
+// half + 3 after position size-1, so the clamp is done once, at staging, and the input address just
+// advances by `pitch`. (2) The weights are zero-padded (three before, up to six after): steps at which
+// an output is outside its window add +0.0 * v, which leaves a sum unchanged bit for bit -- v is
+// finite (a volume is either finite or NaN throughout: its cells are palette colours or blurs of
+// them), s never is -0.0 (it starts at +0.0), and a NaN sum stays NaN.
 constexpr int BLUR_R = 4;
 
-// INTERIOR: the whole window p0 - half .. p0 + 3 + half lies inside the line, so the clamp is the
-// identity and the input address just advances by `pitch` per step.
-template <bool INTERIOR>
-__device__ __forceinline__ void blur_taps4x2(const float* __restrict__ colp, uint32_t pitch, int pos0, int maxpos,
-                                             const float* __restrict__ kw, int klen, int half, float one, float2 (&out)[BLUR_R]) {
+__device__ __forceinline__ void blur_taps4x2(const float* __restrict__ row0, uint32_t pitch, const float* __restrict__ kwz, int steps, float one,
+                                             float2 (&out)[BLUR_R]) {
+    // row0: the input row of step 0 (position p0 - half); kwz[j] = kw[j] for 0 <= j < klen, else 0 (j < steps + 4)
     float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
     // weights live in four registers named by j mod 4 (ra = kw[j] for j = 0 mod 4, ...): no shifting
-    float ra = 0.0f, rb = 0.0f, rc = 0.0f, rd = 0.0f;
-    const int steps = klen + BLUR_R - 1;
-    const float* ptr = colp + (ptrdiff_t)(pos0 - half) * (ptrdiff_t)pitch;  // INTERIOR: input of the current step
-#define BLUR_IN(J) (*reinterpret_cast<const float2*>(INTERIOR ? ptr + (uint32_t)(J) * pitch : colp + (uint32_t)min(max(pos0 + (J) - half, 0), maxpos) * pitch))
+    float ra, rb = 0.0f, rc = 0.0f, rd = 0.0f;
 #define BLUR_ACC(S, W, V) S = blur_add2(S, __fmul2_rn(make_float2(W, W), V), one)
-    int j = 0;
-    for (; j < 4 && j < steps; ++j) {  // head: outputs join one by one
-        float2 v = BLUR_IN(j);
-        float w = j < klen ? kw[j] : 0.0f;
-        if (j == 0) ra = w; else if (j == 1) rb = w; else if (j == 2) rc = w; else rd = w;
-        if (j < klen) BLUR_ACC(s0, w, v);
-        if (j >= 1 && j - 1 < klen) BLUR_ACC(s1, (j == 1 ? ra : j == 2 ? rb : rc), v);
-        if (j >= 2 && j - 2 < klen) BLUR_ACC(s2, (j == 2 ? ra : rb), v);
-        if (j >= 3 && j - 3 < klen) BLUR_ACC(s3, ra, v);
-    }
-    if (INTERIOR) {
-        // body: every output active, no predicates; `q` walks the input rows, `kq` the weights
-        const float* q = ptr + (uint32_t)j * pitch;
-        const float* kq = kw + j;
-        const uint32_t p4 = 4u * pitch;
+    const float* q = row0;
+    const float* kq = kwz;
+    const uint32_t p4 = 4u * pitch;
 #pragma unroll 1
-        for (; j + 3 < klen; j += 4, q += p4, kq += 4) {
-            const float2 v0 = *reinterpret_cast<const float2*>(q), v1 = *reinterpret_cast<const float2*>(q + pitch);
-            const float2 v2 = *reinterpret_cast<const float2*>(q + 2u * pitch), v3 = *reinterpret_cast<const float2*>(q + 3u * pitch);
-            ra = kq[0]; BLUR_ACC(s0, ra, v0); BLUR_ACC(s1, rd, v0); BLUR_ACC(s2, rc, v0); BLUR_ACC(s3, rb, v0);
-            rb = kq[1]; BLUR_ACC(s0, rb, v1); BLUR_ACC(s1, ra, v1); BLUR_ACC(s2, rd, v1); BLUR_ACC(s3, rc, v1);
-            rc = kq[2]; BLUR_ACC(s0, rc, v2); BLUR_ACC(s1, rb, v2); BLUR_ACC(s2, ra, v2); BLUR_ACC(s3, rd, v2);
-            rd = kq[3]; BLUR_ACC(s0, rd, v3); BLUR_ACC(s1, rc, v3); BLUR_ACC(s2, rb, v3); BLUR_ACC(s3, ra, v3);
-        }
-    } else {
-#pragma unroll 1
-        for (; j + 3 < klen; j += 4) {
-            float2 v0 = BLUR_IN(j), v1 = BLUR_IN(j + 1), v2 = BLUR_IN(j + 2), v3 = BLUR_IN(j + 3);
-            ra = kw[j];     BLUR_ACC(s0, ra, v0); BLUR_ACC(s1, rd, v0); BLUR_ACC(s2, rc, v0); BLUR_ACC(s3, rb, v0);
-            rb = kw[j + 1]; BLUR_ACC(s0, rb, v1); BLUR_ACC(s1, ra, v1); BLUR_ACC(s2, rd, v1); BLUR_ACC(s3, rc, v1);
-            rc = kw[j + 2]; BLUR_ACC(s0, rc, v2); BLUR_ACC(s1, rb, v2); BLUR_ACC(s2, ra, v2); BLUR_ACC(s3, rd, v2);
-            rd = kw[j + 3]; BLUR_ACC(s0, rd, v3); BLUR_ACC(s1, rc, v3); BLUR_ACC(s2, rb, v3); BLUR_ACC(s3, ra, v3);
-        }
+    for (int j = 0; j < steps; j += 4, q += p4, kq += 4) {
+        const float2 v0 = *reinterpret_cast<const float2*>(q), v1 = *reinterpret_cast<const float2*>(q + pitch);
+        const float2 v2 = *reinterpret_cast<const float2*>(q + 2u * pitch), v3 = *reinterpret_cast<const float2*>(q + 3u * pitch);
+        ra = kq[0]; BLUR_ACC(s0, ra, v0); BLUR_ACC(s1, rd, v0); BLUR_ACC(s2, rc, v0); BLUR_ACC(s3, rb, v0);
+        rb = kq[1]; BLUR_ACC(s0, rb, v1); BLUR_ACC(s1, ra, v1); BLUR_ACC(s2, rd, v1); BLUR_ACC(s3, rc, v1);
+        rc = kq[2]; BLUR_ACC(s0, rc, v2); BLUR_ACC(s1, rb, v2); BLUR_ACC(s2, ra, v2); BLUR_ACC(s3, rd, v2);
+        rd = kq[3]; BLUR_ACC(s0, rd, v3); BLUR_ACC(s1, rc, v3); BLUR_ACC(s2, rb, v3); BLUR_ACC(s3, ra, v3);
     }
-    for (; j < steps; ++j) {  // tail: outputs leave one by one; j is a multiple of 4 at entry
-        float2 v = BLUR_IN(j);
-        const int m = j & 3;
-        float w = j < klen ? kw[j] : 0.0f;
-        if (m == 0) ra = w; else if (m == 1) rb = w; else if (m == 2) rc = w; else rd = w;
-        // weight of output q at step j is kw[j - q], held in the register named (j - q) mod 4
-        float w1 = m == 0 ? rd : m == 1 ? ra : m == 2 ? rb : rc;
-        float w2 = m == 0 ? rc : m == 1 ? rd : m == 2 ? ra : rb;
-        float w3 = m == 0 ? rb : m == 1 ? rc : m == 2 ? rd : ra;
-        if (j < klen) BLUR_ACC(s0, w, v);
-        if (j >= 1 && j - 1 < klen) BLUR_ACC(s1, w1, v);
-        if (j >= 2 && j - 2 < klen) BLUR_ACC(s2, w2, v);
-        if (j >= 3 && j - 3 < klen) BLUR_ACC(s3, w3, v);
-    }
-#undef BLUR_IN
 #undef BLUR_ACC
     out[0] = s0; out[1] = s1; out[2] = s2; out[3] = s3;
 }
 
 // One blur pass along one axis of the [r][g][b][ch] volume, whatever the axis. Position p of the
 // axis is `pstride` floats from position p-1. A CTA owns `cols` columns of one outer slab and
-// stages all `size` positions of them: tile[p][c], c fastest, `pitch` floats per row. Column c of a
-// slab lives at (c / cpl) * run_stride + (c % cpl): runs of `cpl` contiguous floats (cpl = 0: the
-// whole slab is one run).
+// stages all `size` positions of them (plus the replicated rows): tile[p + half][c], c fastest,
+// `pitch` floats per row. Column c of a slab lives at (c / cpl) * run_stride + (c % cpl): runs of
+// `cpl` contiguous floats (cpl = 0: the whole slab is one run).
 //   B axis: pstride ch,         columns = (row, channel): cpl ch, run_stride size*ch, one slab
 //   R axis: pstride size^2*ch,  columns = the size^2*ch floats of a (g, b, channel) plane, one slab
 //   G axis: pstride size*ch,    columns = the size*ch floats of a (b, channel) line, one slab per r
+// rows of a tile: the positions rounded up to whole blocks of BLUR_R (the last block's spare outputs read on), half before, half + 3 after
+__host__ __device__ inline uint32_t blur_tile_rows(uint32_t size, int klen) { return (size + 3u) / 4u * 4u + 2u * (uint32_t)(klen / 2) + 3u; }
+__host__ __device__ inline uint32_t blur_kwz_len(int klen) { return (uint32_t)((klen + 3 + 3) / 4 * 4 + 4); }
+
 __global__ void __launch_bounds__(256) k_blur_axis(const float* __restrict__ src, float* __restrict__ dst, const BlurAxis P,
                                                     const float* __restrict__ kernel, int klen, float one) {
     extern __shared__ __align__(16) float s_blur[];
-    float* s_tile = s_blur;                                   // size * pitch, 8-byte aligned rows
-    float* s_kw = s_blur + (size_t)P.size * P.pitch;
+    const int half = klen / 2;
+    const uint32_t trows = blur_tile_rows(P.size, klen);
+    float* s_tile = s_blur;                                   // trows * pitch, 8-byte aligned rows
+    float* s_kwz = s_blur + (size_t)trows * P.pitch;          // zero-padded weights
+    float* s_body = s_tile + (size_t)half * P.pitch;          // row of position 0
     const uint32_t outer = blockIdx.x / P.groups, grp = blockIdx.x % P.groups;
     const uint32_t col0 = grp * P.cols, ncols = min(P.cols, P.total_cols - col0);
     const uint32_t cpl = P.cpl ? P.cpl : P.total_cols;
     const size_t base = (size_t)outer * P.outer_stride + (size_t)(col0 / cpl) * P.run_stride + (col0 % cpl);
-    for (int i = threadIdx.x; i < klen; i += blockDim.x) s_kw[i] = kernel[i];
+    for (uint32_t i = threadIdx.x; i < blur_kwz_len(klen); i += blockDim.x) s_kwz[i] = (int)i < klen ? kernel[i] : 0.0f;
     if (P.cpl == 0) {
         // the columns are contiguous floats: thread = (row of the wave, column), waves of 256 / cols rows
         const uint32_t c = threadIdx.x % P.cols, prow = threadIdx.x / P.cols, pstep = blockDim.x / P.cols;
         if (c < ncols && prow < pstep) {
             const float* q = src + base + c;
-            for (uint32_t p = prow; p < P.size; p += pstep) s_tile[p * P.pitch + c] = q[(size_t)p * P.pstride];
+            for (uint32_t p = prow; p < P.size; p += pstep) s_body[p * P.pitch + c] = q[(size_t)p * P.pstride];
         }
     } else {
         // runs of cpl (= channels: 2 or 3) columns, each run one contiguous row of size * cpl floats
         const uint32_t rcols = P.cpl, nruns = (ncols + rcols - 1) / rcols, per_run = P.size * rcols;
         for (uint32_t run = 0; run < nruns; ++run) {
             const float* q = src + base + (size_t)run * P.run_stride;
-            float* t = s_tile + run * rcols;
+            float* t = s_body + run * rcols;
             for (uint32_t x = threadIdx.x; x < per_run; x += blockDim.x) {
                 const uint32_t p = rcols == 3 ? x / 3u : (rcols == 2 ? x >> 1 : x / rcols), cc = x - p * rcols;
                 if (run * rcols + cc < ncols) t[p * P.pitch + cc] = q[x];
@@ -309,7 +281,17 @@ __global__ void __launch_bounds__(256) k_blur_axis(const float* __restrict__ src
         }
     }
     __syncthreads();
-    const int half = klen / 2, maxpos = (int)P.size - 1;
+    {
+        // the clamp of the reference, once: rows before position 0 repeat it, rows after size-1 repeat that
+        const uint32_t npad = trows - P.size, wcols = (ncols + 1u) & ~1u;
+        for (uint32_t i = threadIdx.x; i < npad * wcols; i += blockDim.x) {
+            const uint32_t k = i / wcols, c = i - k * wcols;
+            const bool lo = k < (uint32_t)half;
+            const uint32_t row = lo ? k : P.size + k;                       // in tile rows: [0, half) and [half + size, trows)
+            s_tile[row * P.pitch + c] = lo ? s_body[c] : s_body[(P.size - 1) * P.pitch + c];
+        }
+    }
+    __syncthreads();
     const uint32_t pblocks = (P.size + BLUR_R - 1) / BLUR_R, npairs = (ncols + 1) / 2;
     const uint32_t pair = threadIdx.x % npairs, pb0 = threadIdx.x / npairs, pbstep = blockDim.x / npairs;
     if (pb0 >= pbstep) return;  // blockDim.x is not a multiple of npairs: the remainder threads idle
@@ -318,13 +300,11 @@ __global__ void __launch_bounds__(256) k_blur_axis(const float* __restrict__ src
     const size_t offA = base + (size_t)(c / rcols) * P.run_stride + (c % rcols);
     const size_t offB = base + (size_t)((c + 1) / rcols) * P.run_stride + ((c + 1) % rcols);
     const bool hasB = c + 1 < ncols;
+    const int steps = klen ? (klen + BLUR_R - 1 + 3) / 4 * 4 : 0;   // klen + 3 steps, in fours; no taps: the sums stay 0.0
     for (uint32_t pb = pb0; pb < pblocks; pb += pbstep) {
         float2 o[BLUR_R];
-        const int pos0 = (int)(pb * BLUR_R);
-        if (pos0 - half >= 0 && pos0 + klen + BLUR_R - 2 - half <= maxpos)
-            blur_taps4x2<true>(s_tile + c, P.pitch, pos0, maxpos, s_kw, klen, half, one, o);
-        else
-            blur_taps4x2<false>(s_tile + c, P.pitch, pos0, maxpos, s_kw, klen, half, one, o);
+        // step 0 reads position pb*4 - half = tile row pb*4
+        blur_taps4x2(s_tile + (size_t)(pb * BLUR_R) * P.pitch + c, P.pitch, s_kwz, steps, one, o);
 #pragma unroll
         for (int q = 0; q < BLUR_R; ++q) {
             const uint32_t pq = pb * BLUR_R + q;
