@@ -636,15 +636,25 @@ int ensure_blur_volume(const lutgen_remapper* r, uint32_t level, int sequential,
         // but never fewer than one cell's channels; the B pass takes whole rows (ch columns each)
         auto launch_axis = [&](const float* src, float* dst, BlurAxis P, uint32_t outers) -> int {
             P.groups = (P.total_cols + P.cols - 1) / P.cols;
-            // tile rows: `size` positions + the replicated rows either side; zero-padded weights behind it
-            size_t smem = ((size_t)((P.size + 3u) / 4u * 4u + 2u * (uint32_t)(klen / 2) + 3u) * P.pitch + (size_t)((klen + 6) / 4 * 4 + 4)) * sizeof(float);
+            // rows 4 apart (two position blocks handled by one warp) must not share banks: pitch = 4 mod 8 floats
+            P.pitch = P.cols + ((12u - (P.cols & 7u)) & 7u);
+            // two tiles (double buffer): `size` positions rounded up to blocks of 4 + the replicated rows either
+            // side, each; zero-padded weights behind them
+            const size_t tile = (size_t)((P.size + 3u) / 4u * 4u + 2u * (uint32_t)(klen / 2) + 3u) * P.pitch;
+            size_t smem = (2 * tile + (size_t)((klen + 6) / 4 * 4 + 4)) * sizeof(float);
             if (smem > 227 * 1024) return fail(LUTGEN_ERR_UNSUPPORTED, "blur: %zu bytes of shared memory per tile (level %u, radius %g)", smem, level, r->d.param);
-            blur_launch_axis(P.groups * outers, smem, s, src, dst, P, r->blur_kernel, klen);
+            const uint32_t ntiles = P.groups * outers;
+            unsigned per_sm = (unsigned)((227 * 1024) / (smem + 1024));
+            if (per_sm > 8) per_sm = 8;
+            if (per_sm < 1) per_sm = 1;
+            unsigned grid = per_sm * (unsigned)g.sm_count;
+            if (grid > ntiles) grid = ntiles;
+            blur_launch_axis(grid, smem, s, src, dst, P, ntiles, r->blur_kernel, klen);
             LAUNCH_CHECK();
             return LUTGEN_OK;
         };
-        uint32_t want = 12288u / (size + 2u * (uint32_t)(klen / 2) + 6u);
-        if (want > 32) want = 32;
+        uint32_t want = 6144u / (size + 2u * (uint32_t)(klen / 2) + 6u);   // two buffers of ~24 KB: four CTAs per SM
+        if (want > 16) want = 16;
         if (want < 2) want = 2;
         {   // pass 1: B axis (innermost)
             BlurAxis P{};
@@ -652,7 +662,7 @@ int ensure_blur_volume(const lutgen_remapper* r, uint32_t level, int sequential,
             if (lines < 1) lines = 1;
             if ((lines * ch) & 1u) ++lines;  // an even number of columns per full tile
             P.size = size; P.pstride = ch; P.cols = lines * ch;
-            P.pitch = P.cols + ((2 * ch + 32 - (P.cols & 31u)) & 31u);  // even, = 2 ch mod 32: staging conflicts stay 2-way
+            P.pitch = P.cols;  // even; the staging is asynchronous (cp.async), its bank conflicts are off the critical path
             P.cpl = ch; P.run_stride = size * ch; P.total_cols = rows * ch; P.outer_stride = 0;
             int rc = launch_axis(a, b, P, 1);
             if (rc) return rc;

@@ -21,8 +21,9 @@ void blur_launch_nn_volume(unsigned grid, size_t smem, cudaStream_t s, float* co
                                                              end_prev, end_cur, changed);
 }
 
-void blur_launch_axis(unsigned grid, size_t smem, cudaStream_t s, const float* src, float* dst, const BlurAxis& P, const float* kernel, int klen) {
-    k_blur_axis<<<grid, 256, smem, s>>>(src, dst, P, kernel, klen, 1.0f);
+void blur_launch_axis(unsigned grid, size_t smem, cudaStream_t s, const float* src, float* dst, const BlurAxis& P, uint32_t ntiles, const float* kernel,
+                      int klen) {
+    k_blur_axis<<<grid, 256, smem, s>>>(src, dst, P, ntiles, kernel, klen, 1.0f);
 }
 
 void blur_launch_to_lut(unsigned grid, cudaStream_t s, const float* colors, uint32_t size, uint32_t ch, const uint8_t* chan, uint8_t* out_rgb,

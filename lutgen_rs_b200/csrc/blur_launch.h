@@ -25,7 +25,8 @@ void blur_launch_palette(unsigned grid, cudaStream_t s, const uint8_t* pal_rgb4,
 void blur_launch_nn_volume(unsigned grid, size_t smem, cudaStream_t s, float* colors, uint32_t size, uint32_t ch, const uint8_t* chan, const float* pal3,
                            const float* out3, uint32_t n, float lum, float threshold_sq, const ColorTables* tables, int stage_palette,
                            const uint32_t* end_prev, uint32_t* end_cur, uint32_t* changed);
-void blur_launch_axis(unsigned grid, size_t smem, cudaStream_t s, const float* src, float* dst, const BlurAxis& P, const float* kernel, int klen);
+void blur_launch_axis(unsigned grid, size_t smem, cudaStream_t s, const float* src, float* dst, const BlurAxis& P, uint32_t ntiles, const float* kernel,
+                      int klen);
 void blur_launch_to_lut(unsigned grid, cudaStream_t s, const float* colors, uint32_t size, uint32_t ch, const uint8_t* chan, uint8_t* out_rgb,
                         unsigned long long begin, unsigned long long count, uint32_t b_first, uint32_t tiles_r, uint32_t ntiles, const ColorTables* tables);
 
