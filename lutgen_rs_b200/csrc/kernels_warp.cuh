@@ -759,11 +759,14 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
     uint32_t* cidx = s_cidx[warp];
     uint32_t* hits = s_hit[warp];
 
+    // the hand-out after the current one is requested before the current one is processed: the atomic's
+    // round trip (1.6 % of the stall samples when taken at the point of use) hides behind a hand-out's work
+    uint32_t ticket = 0;
+    if (lane == 0) ticket = atomicAdd(a.tile_counter, a.batch);
     for (;;) {
-        uint32_t t0 = 0;
-        if (lane == 0) t0 = atomicAdd(a.tile_counter, a.batch);
-        t0 = __shfl_sync(FULL, t0, 0);
+        uint32_t t0 = __shfl_sync(FULL, ticket, 0);
         if (t0 >= a.ntiles) break;
+        if (lane == 0) ticket = atomicAdd(a.tile_counter, a.batch);
         if (a.shard_count > 1) t0 = ((t0 / a.batch) * a.shard_count + a.shard_index) * a.batch;
         if (t0 >= a.ntiles_global) break;
         uint32_t ir = 0, ig = 0, ib = 0;
