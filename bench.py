@@ -266,6 +266,19 @@ def run_b200(args):
     lut16 = torch.empty(per * world * side * 3, dtype=torch.uint8, device="cuda")
 
     fused = world > 1 and not os.environ.get("LUTGEN_BENCH_ALLGATHER")
+    if fused:
+        # the fused form needs the ranks' buffers mapped into each other (symmetric memory or CUDA IPC); if a box
+        # cannot do that, every rank falls back to the all-gather form together
+        try:
+            device.generate_lut_fused(remapper, LEVEL_GEN)
+            torch.cuda.synchronize()
+            ok = 1
+        except Exception as e:  # noqa: BLE001
+            print(f"rank {rank}: fused generation unavailable ({e!r}); using the all-gather form", file=sys.stderr)
+            ok = 0
+        t_ok = torch.tensor([ok], device="cuda")
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        fused = bool(int(t_ok.item()))
 
     def gen_step():
         # N > 1: every rank computes its share of the tiles and stores it into all ranks' CLUT buffers
