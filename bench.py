@@ -471,8 +471,10 @@ def run_b200(args):
 
     # the other BASELINE.json configurations, device resident on one GPU (rank 0; a few repetitions
     # each, after the timed regions above): evidence next to the headline, not part of `value`
+    # N = 1 only: with peer mappings in place (N > 1) a cudaMalloc on one rank has to be mapped into the peers,
+    # which cannot answer while they wait inside an NCCL kernel -- a rank must not work alone between collectives
     other_configs = None
-    if rank == 0:
+    if world == 1:
         from conftest import synthetic_palette
         pal256 = synthetic_palette(256, 1)
 
@@ -505,9 +507,6 @@ def run_b200(args):
             "gaussian_rbf_level12_ms": ms_of(lambda: interpolation.GaussianRemapper(pal, 128.0, 16, 1.0, False), 12),
             "what": "ms per whole CLUT on ONE GPU, device resident, L2 flushed (BASELINE.json configs 3, 4, 1 and SURVEY 8f#1)",
         }
-    if world > 1:
-        barrier()
-
     top, other, other_key = (gen_line, apply_line, "apply") if args.workload == "generate" else (apply_line, gen_line, "generate")
     line = dict(top)
     line.update({"n_gpus": world, "steps": steps, "warmup": warmup, "higher_is_better": True, "vs_baseline": None,
