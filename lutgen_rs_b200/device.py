@@ -236,7 +236,11 @@ def generate_lut_fused(remapper, level, group=None, stream=None):
     level = int(level)
     side = level ** 3
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
-    if world == 1 or world > PeerLut.MAX_WORLD or remapper._kind in (_native.SAMPLING, _native.BLUR):
+    # measured (tools/time_config3.py, 8 GPUs): with 256 colours the two-level kernel's per-tile 24-byte stores make
+    # the fused form slightly slower than the collective (0.47 vs 0.44 ms), so palettes beyond the small-palette
+    # kernel's 32 colours take the all-gather
+    if (world == 1 or world > PeerLut.MAX_WORLD or remapper._kind in (_native.SAMPLING, _native.BLUR)
+            or len(remapper._palette) > 32):
         return generate_lut(remapper, level, group=group, stream=stream)
     key = (side, id(group))
     peers = _peer_luts.get(key)
