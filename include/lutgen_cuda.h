@@ -212,6 +212,36 @@ LUTGEN_API int lutgen_cuda_remap_image_dev(const lutgen_remapper* r, uint8_t* rg
 LUTGEN_API int lutgen_cuda_sampling_get_noise(const lutgen_remapper* r, double* noise_out);
 LUTGEN_API int lutgen_cuda_sampling_set_noise(lutgen_remapper* r, const double* noise);
 
+/* ---- PNG writer around the path -------------------------- */
+
+/* `RgbImage::save(path)` / `RgbaImage::save(path)` with a .png path (crates/cli/src/main.rs:767, 811,
+ * 839: `lut.save(&path)`; 862-871: `image.save(&path)`), i.e. the `image` crate's PNG encoder: the
+ * bytes of a PNG file (8 bits per sample, colour type 0 / 4 / 2 / 6 for channels 1 / 2 / 3 / 4, no
+ * interlace, adaptive row filters, one zlib stream split over several IDAT chunks) for a tightly
+ * packed height x width x channels image. Lossless: any PNG reader returns the input pixels; the
+ * bytes themselves differ from the `image` crate's, as two encoders' always do. The caller writes
+ * them to the file.
+ *
+ * lutgen_cuda_png_bound: the largest size the encoder can produce for such an image.
+ * lutgen_cuda_encode_png: host pixels in, host bytes out. *out_len receives the file size; if that
+ *   exceeds `capacity`, nothing is written and LUTGEN_ERR_INVALID is returned (retry with *out_len,
+ *   or pass lutgen_cuda_png_bound() up front).
+ * lutgen_cuda_encode_png_dev: device pixels in, device bytes out, `capacity` must be at least
+ *   lutgen_cuda_png_bound(); enqueues on `stream` and, unlike the other _dev calls, synchronises that
+ *   stream once at the end to return the size in *out_len (host). */
+LUTGEN_API int lutgen_cuda_png_bound(uint32_t width, uint32_t height, int channels, size_t* bound);
+LUTGEN_API int lutgen_cuda_encode_png(const uint8_t* pixels, uint32_t width, uint32_t height, int channels, uint8_t* out,
+                                      size_t capacity, size_t* out_len);
+LUTGEN_API int lutgen_cuda_encode_png_dev(const uint8_t* pixels_dev, uint32_t width, uint32_t height, int channels,
+                                          uint8_t* out_dev, size_t capacity, size_t* out_len, void* stream);
+
+/* GenerateLut::par_generate_lut followed by `lut.save(path)` (crates/cli/src/main.rs:742-767, the
+ * whole of `lutgen generate` after argument parsing): the CLUT is generated and encoded on the device
+ * and only the PNG bytes cross PCIe. Same return values as lutgen_cuda_generate_lut; *out_len and
+ * `capacity` as in lutgen_cuda_encode_png (bound: lutgen_cuda_png_bound(level^3, level^3, 3)). */
+LUTGEN_API int lutgen_cuda_generate_lut_png(const lutgen_remapper* r, uint8_t level, uint8_t* out, size_t capacity,
+                                            size_t* out_len, const volatile uint8_t* abort_flag);
+
 /* ---- oklab (third-party arithmetic on the path; oklab 1.1.2) --------------- */
 
 /* oklab::srgb_to_oklab for n colours: in n x [u8;3], out n x [f32;3] (l, a, b). */

@@ -19,6 +19,7 @@
 #include "../../include/lutgen_cuda.h"
 #include "kernels_apply.cuh"
 #include "blur_launch.h"
+#include "png_launch.h"
 #include "kernels_exact.cuh"
 #include "kernels_fast.cuh"
 #include "kernels_warp.cuh"
@@ -90,6 +91,7 @@ struct Ctx {
     DevBuf frame;                   // RGBA8 image scratch
     DevBuf batch_frames[kBatchStreams];
     DevBuf misc;
+    DevBuf png_in, png_out, png_scratch;  // PNG writer: pixels (host API), file bytes, per-piece scratch
     uint32_t* stats = nullptr;      // device [128], only with LUTGEN_CUDA_STATS set
 } g;
 
@@ -855,6 +857,10 @@ int lutgen_cuda_shutdown(void) {
     g.lut_rgbx.release();
     g.frame.release();
     g.misc.release();
+    g.png_in.release();
+    g.png_out.release();
+    g.png_scratch.release();
+    png_release();
     for (int i = 0; i < kBatchStreams; ++i) {
         g.batch_frames[i].release();
         if (g.batch_streams[i]) cudaStreamDestroy(g.batch_streams[i]);
@@ -1432,6 +1438,102 @@ int generate_lut_impl(const lutgen_remapper* r, uint8_t level, uint8_t* out_rgb,
     return LUTGEN_OK;
 }
 }  // namespace
+
+// ---------------------------------------------------------------------------
+// PNG writer (png.cu)
+// ---------------------------------------------------------------------------
+namespace {
+int png_args_ok(uint32_t width, uint32_t height, int channels) {
+    if (channels < 1 || channels > 4) return fail(LUTGEN_ERR_INVALID, "%d channels (1..4)", channels);
+    if (width == 0 || height == 0) return fail(LUTGEN_ERR_INVALID, "empty image (%u x %u): PNG has no zero-sized images", width, height);
+    if ((unsigned long long)width * channels >= (1ull << 31) || (unsigned long long)height * ((unsigned long long)width * channels + 1ull) >= (1ull << 40))
+        return fail(LUTGEN_ERR_UNSUPPORTED, "image of %u x %u x %d is beyond the encoder's limits", width, height, channels);
+    return LUTGEN_OK;
+}
+
+// pixels already on the device (g.mu held): encode into g.png_out, size in *total (host), synchronises `s`.
+int png_encode_locked(const uint8_t* pixels_dev, uint32_t width, uint32_t height, int channels, uint8_t* out_dev, size_t* total, cudaStream_t s) {
+    CU_TRY(g.png_scratch.reserve(png_scratch_bytes(width, height, (uint32_t)channels)));
+    unsigned long long* total_dev = static_cast<unsigned long long*>(g.png_scratch.p);  // the scratch block starts with the file size
+    unsigned launches = 0;
+    cudaError_t e = png_encode_async(pixels_dev, width, height, (uint32_t)channels, out_dev, g.png_scratch.p, s, &launches);
+    g_launches.fetch_add(launches, std::memory_order_relaxed);
+    if (e != cudaSuccess) return fail(LUTGEN_ERR_CUDA, "PNG encoder launch failed: %s", cudaGetErrorString(e));
+    unsigned long long t = 0;
+    CU_TRY(cudaMemcpyAsync(&t, total_dev, sizeof t, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    *total = (size_t)t;
+    return LUTGEN_OK;
+}
+}  // namespace
+
+int lutgen_cuda_png_bound(uint32_t width, uint32_t height, int channels, size_t* bound) {
+    if (!bound) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    int rc = png_args_ok(width, height, channels);
+    if (rc) return rc;
+    *bound = (size_t)png_bound(width, height, (uint32_t)channels);
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_encode_png_dev(const uint8_t* pixels_dev, uint32_t width, uint32_t height, int channels, uint8_t* out_dev, size_t capacity,
+                               size_t* out_len, void* stream) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!pixels_dev || !out_dev || !out_len) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    rc = png_args_ok(width, height, channels);
+    if (rc) return rc;
+    if (capacity < png_bound(width, height, (uint32_t)channels))
+        return fail(LUTGEN_ERR_INVALID, "out_dev holds %zu bytes, lutgen_cuda_png_bound() asks for %llu", capacity,
+                    png_bound(width, height, (uint32_t)channels));
+    std::lock_guard<std::mutex> lk(g.mu);
+    return png_encode_locked(pixels_dev, width, height, channels, out_dev, out_len, (cudaStream_t)stream);
+}
+
+int lutgen_cuda_encode_png(const uint8_t* pixels, uint32_t width, uint32_t height, int channels, uint8_t* out, size_t capacity, size_t* out_len) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!pixels || !out || !out_len) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    rc = png_args_ok(width, height, channels);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g.mu);
+    size_t bytes = (size_t)width * height * channels;
+    CU_TRY(g.png_in.reserve(bytes));
+    CU_TRY(g.png_out.reserve((size_t)png_bound(width, height, (uint32_t)channels)));
+    CU_TRY(cudaMemcpyAsync(g.png_in.p, pixels, bytes, cudaMemcpyHostToDevice, g.stream));
+    size_t total = 0;
+    rc = png_encode_locked((const uint8_t*)g.png_in.p, width, height, channels, (uint8_t*)g.png_out.p, &total, g.stream);
+    if (rc) return rc;
+    *out_len = total;
+    if (total > capacity) return fail(LUTGEN_ERR_INVALID, "the PNG is %zu bytes, the buffer holds %zu", total, capacity);
+    CU_TRY(cudaMemcpyAsync(out, g.png_out.p, total, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_generate_lut_png(const lutgen_remapper* r, uint8_t level, uint8_t* out, size_t capacity, size_t* out_len,
+                                 const volatile uint8_t* abort_flag) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!r || !out || !out_len) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33", level);
+    if (abort_flag && *abort_flag) return LUTGEN_ABORTED;
+    std::lock_guard<std::mutex> lk(g.mu);
+    const uint32_t side = (uint32_t)level * level * level;
+    CU_TRY(g.lut_rgb.reserve(3 * lut_entries(level)));
+    CU_TRY(g.png_out.reserve((size_t)png_bound(side, side, 3)));
+    rc = generate_lut_rows_impl(r, level, (uint8_t*)g.lut_rgb.p, 0, side, g.stream, 0);
+    if (rc) return rc;
+    size_t total = 0;
+    rc = png_encode_locked((const uint8_t*)g.lut_rgb.p, side, side, 3, (uint8_t*)g.png_out.p, &total, g.stream);
+    if (rc) return rc;
+    if (abort_flag && *abort_flag) return LUTGEN_ABORTED;
+    *out_len = total;
+    if (total > capacity) return fail(LUTGEN_ERR_INVALID, "the PNG is %zu bytes, the buffer holds %zu", total, capacity);
+    CU_TRY(cudaMemcpyAsync(out, g.png_out.p, total, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    if (abort_flag && *abort_flag) return LUTGEN_ABORTED;
+    return LUTGEN_OK;
+}
 
 int lutgen_cuda_remap_image_dev(const lutgen_remapper* r, uint8_t* rgba_dev, size_t npix, void* stream) {
     int rc = ensure_ready();

@@ -1,0 +1,775 @@
+// png_core.h -- PNG encoding of an RGB8/RGBA8 image as a data-parallel pipeline (SURVEY 8(f) row 2:
+// the `lut.save(path)` / `image.save(path)` calls of crates/cli/src/main.rs:767, 811, 839, 862, which
+// after the kernels are where `lutgen generate` / `lutgen apply` spend their wall time).
+//
+// What is produced is an ordinary PNG: signature, IHDR, IDAT..., IEND; 8 bits per sample, no
+// interlace, per-row adaptive filter (minimum sum of absolute residuals, the heuristic the `png`
+// crate's Adaptive mode uses), one zlib stream. The zlib stream is cut into CHUNK-byte pieces of the
+// filtered scanline stream; every piece is compressed independently by one CTA into one deflate block
+// with its own dynamic Huffman code and ends on a byte boundary (an empty stored block, the same
+// device `pigz` uses), so pieces concatenate without bit shifting and each travels in its own IDAT
+// chunk with its own CRC. Matches are restricted to distance = bytes-per-pixel (runs of identical
+// filtered pixels, which is what filtered CLUTs and photographs mostly offer; the `image` crate's
+// default "fast" mode is of the same kind), which makes the tokenisation a function of run boundaries
+// alone -- no sequential dependency, every thread tokenises its own 64 bytes.
+//
+// Everything in this header is plain integer C++ that compiles for the host as well: the per-thread
+// phases are written against an executor (`par(f)`: run f(t) for every thread t of the CTA, then
+// barrier), the CUDA kernels instantiate it with threadIdx/__syncthreads, and tests/png_sim.cpp
+// instantiates it with a loop, so the unit tests here exercise the very code the GPU runs (there is
+// no GPU in the development container). The host build is TEST infrastructure only; the product path
+// (lutgen_cuda_encode_png*) has no CPU route.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define LPNG_HD __host__ __device__ __forceinline__
+#define LPNG_HDN __host__ __device__ inline
+#else
+#define LPNG_HD inline
+#define LPNG_HDN inline
+#endif
+
+namespace lpng {
+
+constexpr int SEG = 64;                  // stream bytes tokenised by one thread
+constexpr int THREADS = 256;             // threads per CTA
+constexpr int CHUNK = SEG * THREADS;     // stream bytes per deflate block
+constexpr int MIN_RUN = 4;               // shortest run worth a match
+constexpr int MAX_MATCH = 258;
+constexpr int NLITLEN = 286;             // literal/length symbols in use
+constexpr int NSYM = 288;
+constexpr int EOB = 256;
+constexpr int MAX_BITS = 15;
+constexpr int OUT_BYTES = CHUNK + 32;    // zlib header + stored-block header + CHUNK, rounded up
+constexpr int OUT_WORDS = OUT_BYTES / 4;
+constexpr int F_BYTES = CHUNK + (CHUNK >> 6) * 4;  // one pad word per 64 bytes: thread stride 17 words
+constexpr int CRC_SLICE = 68;            // bytes per thread in the CRC pass (17 words: conflict free)
+constexpr uint32_t CRC_POLY = 0xEDB88320u;
+constexpr uint32_t ADLER_MOD = 65521u;
+constexpr int BIG = 1 << 30;
+constexpr int HIST_REPLICAS = 8;         // histogram copies (in the not yet used output buffer) against same-symbol contention
+constexpr int HIST_PITCH = NSYM + 1;     // odd: the copies of one symbol sit in different banks
+constexpr int PNG_HEADER_BYTES = 33;     // signature + IHDR chunk
+constexpr int PNG_TRAILER_BYTES = 16 + 12;  // adler IDAT + IEND
+
+static_assert(HIST_REPLICAS * HIST_PITCH <= OUT_WORDS, "histogram copies must fit in the output buffer");
+
+LPNG_HD int pad(int o) { return o + ((o >> 6) << 2); }
+
+LPNG_HD int clz64(unsigned long long v) {
+#ifdef __CUDA_ARCH__
+    return __clzll((long long)v);
+#else
+    return __builtin_clzll(v);
+#endif
+}
+LPNG_HD int ctz64(unsigned long long v) {
+#ifdef __CUDA_ARCH__
+    return __ffsll((long long)v) - 1;
+#else
+    return __builtin_ctzll(v);
+#endif
+}
+LPNG_HD void atomic_add(uint32_t* p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+    atomicAdd(p, v);
+#else
+    *p += v;
+#endif
+}
+LPNG_HD void atomic_or(uint32_t* p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// CRC-32 (PNG / zlib polynomial, reflected). Polynomials over GF(2) are held bit-reflected: bit 31
+// is the coefficient of x^0. crc_update is linear in (state, byte), so the state after a message is
+// the XOR of the states of its slices, each multiplied by x^(8 * bytes that follow it).
+// ---------------------------------------------------------------------------------------------
+LPNG_HD uint32_t gf_mul(uint32_t a, uint32_t b) {
+    uint32_t p = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
+    for (int i = 0; i < 32; ++i) {
+        if (a & (0x80000000u >> i)) p ^= b;
+        b = (b >> 1) ^ ((b & 1u) ? CRC_POLY : 0u);
+    }
+    return p;
+}
+
+struct Tables {
+    uint32_t crc[256];
+    uint32_t xs[8];  // x^(8 * CRC_SLICE * 2^j) mod P
+};
+
+inline uint32_t gf_xpow(unsigned long long n) {  // x^n mod P (host: table construction)
+    uint32_t r = 0x80000000u, b = 0x40000000u;
+    while (n) {
+        if (n & 1) r = gf_mul(r, b);
+        b = gf_mul(b, b);
+        n >>= 1;
+    }
+    return r;
+}
+
+inline void make_tables(Tables& T) {
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? CRC_POLY : 0u);
+        T.crc[i] = c;
+    }
+    for (int j = 0; j < 8; ++j) T.xs[j] = gf_xpow((unsigned long long)(8 * CRC_SLICE) << j);
+}
+
+LPNG_HD uint32_t crc_bitwise(uint32_t state, uint32_t byte) {  // table-free (a handful of header bytes)
+    state ^= byte;
+    for (int k = 0; k < 8; ++k) state = (state >> 1) ^ ((state & 1u) ? CRC_POLY : 0u);
+    return state;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scanline filters (PNG specification, section 9).
+// ---------------------------------------------------------------------------------------------
+struct Image {
+    const uint8_t* px;        // height x width x bpp, tightly packed
+    const uint8_t* filters;   // height filter types (0..4), chosen by choose_filter
+    uint32_t width, height, bpp, rb;  // rb = width * bpp
+    unsigned long long stream_bytes;  // height * (rb + 1)
+};
+
+LPNG_HD int paeth(int a, int b, int c) {
+    int p = a + b - c;
+    int pa = p > a ? p - a : a - p, pb = p > b ? p - b : b - p, pc = p > c ? p - c : c - p;
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+
+LPNG_HD uint8_t filter_value(int ft, int cur, int a, int b, int c) {
+    int pred = ft == 0 ? 0 : ft == 1 ? a : ft == 2 ? b : ft == 3 ? ((a + b) >> 1) : paeth(a, b, c);
+    return (uint8_t)(cur - pred);
+}
+
+// Neighbourhood of byte x of row y: left (a), up (b), up-left (c); 0 outside the image.
+LPNG_HD void neighbours(const Image& im, uint32_t y, uint32_t x, int& cur, int& a, int& b, int& c) {
+    const uint8_t* row = im.px + (size_t)y * im.rb;
+    cur = row[x];
+    a = x >= im.bpp ? row[x - im.bpp] : 0;
+    if (y > 0) {
+        const uint8_t* prow = row - im.rb;
+        b = prow[x];
+        c = x >= im.bpp ? prow[x - im.bpp] : 0;
+    } else {
+        b = 0;
+        c = 0;
+    }
+}
+
+// Adds the absolute (signed-byte) residual of byte x of row y under each of the five filters.
+LPNG_HD void filter_costs(const Image& im, uint32_t y, uint32_t x, uint32_t cost[5]) {
+    int cur, a, b, c;
+    neighbours(im, y, x, cur, a, b, c);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int ft = 0; ft < 5; ++ft) {
+        int r = (int8_t)filter_value(ft, cur, a, b, c);
+        cost[ft] += (uint32_t)(r < 0 ? -r : r);
+    }
+}
+
+LPNG_HD int pick_filter(const uint32_t cost[5]) {
+    int best = 0;
+    for (int ft = 1; ft < 5; ++ft)
+        if (cost[ft] < cost[best]) best = ft;
+    return best;
+}
+
+// Byte `col` of filtered scanline y (col 0 is the filter-type byte).
+LPNG_HD uint8_t stream_byte(const Image& im, uint32_t y, uint32_t col) {
+    int ft = im.filters[y];
+    if (col == 0) return (uint8_t)ft;
+    int cur, a, b, c;
+    neighbours(im, y, col - 1, cur, a, b, c);
+    return filter_value(ft, cur, a, b, c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deflate pieces (RFC 1951).
+// ---------------------------------------------------------------------------------------------
+LPNG_HD int ilog2(uint32_t v) {  // v > 0
+#ifdef __CUDA_ARCH__
+    return 31 - __clz((int)v);
+#else
+    return 31 - __builtin_clz(v);
+#endif
+}
+
+LPNG_HD int length_symbol(int len, int& extra_bits, int& extra) {  // len in 3..258
+    extra_bits = 0;
+    extra = 0;
+    if (len == MAX_MATCH) return 285;
+    int l = len - 3;
+    if (l < 8) return 257 + l;
+    extra_bits = ilog2((uint32_t)l) - 2;
+    extra = l & ((1 << extra_bits) - 1);
+    return 257 + 4 * extra_bits + 4 + ((l >> extra_bits) - 4);
+}
+
+LPNG_HD uint32_t bit_reverse(uint32_t v, int n) {
+    uint32_t r = 0;
+    for (int i = 0; i < n; ++i) r |= ((v >> i) & 1u) << (n - 1 - i);
+    return r;
+}
+
+struct ChunkMeta {
+    uint32_t n_out;    // compressed bytes of this piece (what its IDAT chunk carries)
+    uint32_t crc;      // CRC-32 of "IDAT" + those bytes
+    uint32_t adler_a;  // sum of the piece's stream bytes mod 65521
+    uint32_t adler_b;  // sum of (m - i) * byte_i mod 65521
+    uint32_t m;        // stream bytes in the piece
+};
+
+// CTA-shared state of one piece.
+struct Shared {
+    uint32_t f[F_BYTES / 4];   // filtered stream bytes, padded layout (pad())
+    uint32_t out[OUT_WORDS];   // compressed piece, LSB-first bit stream
+    uint32_t hist[NSYM];
+    uint32_t node_freq[2 * NSYM];
+    uint16_t node_parent[2 * NSYM];
+    uint16_t order[NSYM];      // used symbols by ascending (frequency, symbol)
+    uint16_t code[NSYM];       // canonical codes, bit reversed (ready for the LSB-first stream)
+    uint8_t len[NSYM];
+    unsigned long long eq[THREADS];  // bit k: stream byte lo+k equals the byte bpp before it
+    int sa[THREADS], sb[THREADS], ta[THREADS], tb[THREADS];  // run-boundary scans (kept until the last sweep)
+    int bits[THREADS];               // token bits per thread, then their inclusive prefix sums
+    uint32_t adler_a[THREADS], adler_b[THREADS];
+    uint32_t crc[THREADS];
+    uint32_t crc_table[256];
+    int nused, nlit, stored, n_out;
+    uint32_t header_bits, data_bits, chunk_a, chunk_b;
+};
+
+// out |= v << bitpos (v at most 32 bits wide)
+LPNG_HD void or_bits(uint32_t* out, uint32_t bitpos, uint32_t v) {
+    uint32_t w = bitpos >> 5, sh = bitpos & 31u;
+    atomic_or(&out[w], v << sh);
+    if (sh && (v >> (32u - sh))) atomic_or(&out[w + 1], v >> (32u - sh));
+}
+
+struct HistSink {
+    uint32_t* hist;
+    LPNG_HD void lit(int b) { atomic_add(&hist[b], 1u); }
+    LPNG_HD void match(int len) {
+        int eb, ex;
+        atomic_add(&hist[length_symbol(len, eb, ex)], 1u);
+    }
+};
+
+struct CountSink {
+    const uint8_t* len;
+    uint32_t bits;
+    LPNG_HD void lit(int b) { bits += len[b]; }
+    LPNG_HD void match(int l) {
+        int eb, ex;
+        int s = length_symbol(l, eb, ex);
+        bits += len[s] + eb + 1;
+    }
+};
+
+// Appends to the bit stream from a given bit offset: the first and the last word a thread touches
+// are shared with its neighbours (atomic OR into the zeroed buffer), the words between are its own.
+struct EmitSink {
+    uint32_t* out;
+    const uint8_t* len;
+    const uint16_t* code;
+    unsigned long long acc;
+    int nacc;
+    uint32_t w;
+    bool first;
+    uint32_t dist_bit;
+    LPNG_HD void begin(uint32_t bitpos) {
+        acc = 0;
+        nacc = (int)(bitpos & 31u);
+        w = bitpos >> 5;
+        first = true;
+    }
+    LPNG_HD void put(uint32_t v, int n) {
+        acc |= (unsigned long long)v << nacc;
+        nacc += n;
+        if (nacc >= 32) {
+            if (first) {
+                atomic_or(&out[w], (uint32_t)acc);
+                first = false;
+            } else {
+                out[w] = (uint32_t)acc;
+            }
+            ++w;
+            acc >>= 32;
+            nacc -= 32;
+        }
+    }
+    LPNG_HD void end() {
+        if (nacc > 0 && (uint32_t)acc) atomic_or(&out[w], (uint32_t)acc);
+    }
+    LPNG_HD void lit(int b) { put(code[b], len[b]); }
+    LPNG_HD void match(int l) {
+        int eb, ex;
+        int s = length_symbol(l, eb, ex);
+        put(code[s], len[s]);
+        if (eb) put((uint32_t)ex, eb);
+        put(dist_bit, 1);
+    }
+};
+
+// Tokens that START in thread t's 64 bytes. A maximal interval [s, e) of positions whose byte equals
+// the byte bpp before it is a run; a run of at least MIN_RUN bytes is cut into matches of 258 bytes
+// from its start (a tail shorter than 3 bytes goes out as literals), everything else is a literal.
+// s and e come from the thread's own bit mask or, when the run crosses its segment's ends, from the
+// scanned neighbours' masks (last0 / next0), so no thread waits for another.
+template <class Sink>
+LPNG_HD void sweep(const Shared& S, int t, int m, Sink& sink) {
+    const int lo = t * SEG;
+    int n = m - lo;
+    if (n <= 0) return;
+    if (n > SEG) n = SEG;
+    const uint8_t* fb = reinterpret_cast<const uint8_t*>(S.f);
+    const unsigned long long eq = S.eq[t];
+    const unsigned long long valid = n == 64 ? ~0ull : ((1ull << n) - 1ull);
+    const unsigned long long zeros = ~eq & valid;
+    const int last0 = t > 0 ? S.sa[t - 1] : -1;
+    int next0 = t + 1 < THREADS ? S.sb[t + 1] : BIG;
+    if (next0 > m) next0 = m;
+    int k = 0;
+    while (k < n) {
+        if (!((eq >> k) & 1ull)) {
+            sink.lit(fb[pad(lo + k)]);
+            ++k;
+            continue;
+        }
+        unsigned long long below = zeros & ((1ull << k) - 1ull);
+        int s = below ? lo + 64 - clz64(below) : last0 + 1;
+        unsigned long long above = zeros >> k;
+        int e = above ? lo + k + ctz64(above) : next0;
+        int kend = e - lo < n ? e - lo : n;
+        if (e - s < MIN_RUN) {
+            for (; k < kend; ++k) sink.lit(fb[pad(lo + k)]);
+            continue;
+        }
+        for (; k < kend; ++k) {
+            int off = lo + k - s;
+            int r = off % MAX_MATCH;
+            int pst = lo + k - r;
+            int plen = e - pst < MAX_MATCH ? e - pst : MAX_MATCH;
+            if (plen < 3)
+                sink.lit(fb[pad(lo + k)]);
+            else if (r == 0)
+                sink.match(plen);
+        }
+    }
+}
+
+// S.order = used symbols by ascending (frequency, symbol): thread t places its own symbols by counting
+// the symbols that come before them.
+LPNG_HD void rank_symbols(Shared& S, int t) {
+    for (int s = t; s < NLITLEN; s += THREADS) {
+        uint32_t f = S.hist[s];
+        if (!f) continue;
+        int r = 0;
+        for (int u = 0; u < NLITLEN; ++u) {
+            uint32_t fu = S.hist[u];
+            r += (fu && (fu < f || (fu == f && u < s))) ? 1 : 0;
+        }
+        S.order[r] = (uint16_t)s;
+    }
+}
+
+// Code lengths (at most MAX_BITS) and canonical codes from S.hist; one thread. Huffman's algorithm
+// with two queues over the frequency-sorted symbols (S.order), depths read off the parent links,
+// over-long codes folded into MAX_BITS and the Kraft sum repaired by demoting shorter codes, lengths
+// then handed out again in frequency order.
+LPNG_HDN void build_code(Shared& S) {
+    int n = 0, nlit = 0;
+    for (int s = 0; s < NLITLEN; ++s)
+        if (S.hist[s]) {
+            ++n;
+            nlit = s + 1;
+        }
+    S.nused = n;
+    S.nlit = nlit < 257 ? 257 : nlit;
+    for (int i = 0; i < n; ++i) S.node_freq[i] = S.hist[S.order[i]];
+    int li = 0, ii = n, nn = n;
+    while (nn < 2 * n - 1) {
+        int a, b;
+        if (li < n && (ii >= nn || S.node_freq[li] <= S.node_freq[ii])) a = li++; else a = ii++;
+        if (li < n && (ii >= nn || S.node_freq[li] <= S.node_freq[ii])) b = li++; else b = ii++;
+        S.node_freq[nn] = S.node_freq[a] + S.node_freq[b];
+        S.node_parent[a] = (uint16_t)nn;
+        S.node_parent[b] = (uint16_t)nn;
+        ++nn;
+    }
+    // depths, root first (parents have larger indices than their children); node_freq is reused
+    uint32_t cnt[MAX_BITS + 2];
+    for (int i = 0; i <= MAX_BITS + 1; ++i) cnt[i] = 0;
+    S.node_freq[2 * n - 2] = 0;
+    for (int i = 2 * n - 3; i >= 0; --i) {
+        uint32_t d = S.node_freq[S.node_parent[i]] + 1;
+        S.node_freq[i] = d;
+        if (i < n) ++cnt[d > MAX_BITS ? MAX_BITS : d];
+    }
+    uint32_t total = 0;
+    for (int i = 1; i <= MAX_BITS; ++i) total += cnt[i] << (MAX_BITS - i);
+    while (total > (1u << MAX_BITS)) {
+        --cnt[MAX_BITS];
+        for (int i = MAX_BITS - 1; i >= 1; --i)
+            if (cnt[i]) {
+                --cnt[i];
+                cnt[i + 1] += 2;
+                break;
+            }
+        --total;
+    }
+    int i = n - 1;  // most frequent symbol first, shortest length first
+    for (int l = 1; l <= MAX_BITS; ++l)
+        for (uint32_t c = 0; c < cnt[l]; ++c) S.len[S.order[i--]] = (uint8_t)l;
+    uint32_t next[MAX_BITS + 2];
+    uint32_t code = 0;
+    cnt[0] = 0;
+    for (int l = 1; l <= MAX_BITS; ++l) {
+        code = (code + cnt[l - 1]) << 1;
+        next[l] = code;
+    }
+    for (int s = 0; s < NLITLEN; ++s) {
+        int l = S.len[s];
+        if (l) S.code[s] = (uint16_t)bit_reverse(next[l]++, l);
+    }
+}
+
+// Executors run `f(t)` for t in 0..THREADS and then synchronise: see png.cu (CTA) and tests/png_sim.cpp (loop).
+
+// One piece of the filtered stream -> one byte-aligned deflate block in `slot` (OUT_WORDS words) + its meta data.
+template <class Exec>
+LPNG_HDN void encode_chunk(Exec& ex, Shared& S, const Image& im, const Tables& T, uint32_t chunk, uint32_t nchunks, uint32_t* slot,
+                                  ChunkMeta* meta) {
+    const unsigned long long c0 = (unsigned long long)chunk * CHUNK;
+    const unsigned long long left = im.stream_bytes - c0;
+    const int m = left < (unsigned long long)CHUNK ? (int)left : CHUNK;
+    const int bpp = (int)im.bpp;
+    const bool final_chunk = chunk + 1 == nchunks;
+    const uint32_t base_bits = chunk == 0 ? 16u : 0u;  // the zlib header rides in front of the first piece
+    uint8_t* fb = reinterpret_cast<uint8_t*>(S.f);
+    const int dsym = bpp - 1;                // distance symbol of distance bpp (1..4 -> 0..3)
+    const int dother = dsym == 0 ? 1 : 0;    // second distance code, so that the distance code is complete
+    const int ndist = dsym + 1 > 2 ? dsym + 1 : 2;
+
+    // 1. filtered stream bytes into shared memory (consecutive threads take consecutive bytes)
+    ex.par([&](int t) {
+        for (int w = t; w < OUT_WORDS; w += THREADS) S.out[w] = 0;
+        for (int w = t; w < NSYM; w += THREADS) S.len[w] = 0;
+        S.crc_table[t] = T.crc[t];
+        const uint32_t stride = im.rb + 1;
+        unsigned long long i = c0 + (unsigned)t;
+        uint32_t y = (uint32_t)(i / stride);
+        uint32_t col = (uint32_t)(i - (unsigned long long)y * stride);
+        for (int o = t; o < m; o += THREADS) {
+            fb[pad(o)] = stream_byte(im, y, col);
+            col += THREADS;
+            while (col >= stride) {
+                col -= stride;
+                ++y;
+            }
+        }
+    });
+
+    // 2. run structure of each thread's 64 bytes, Adler partial sums
+    ex.par([&](int t) {
+        const int lo = t * SEG;
+        int n = m - lo;
+        n = n < 0 ? 0 : (n > SEG ? SEG : n);
+        unsigned long long eq = 0;
+        uint32_t A = 0, B = 0;
+        for (int k = 0; k < n; ++k) {
+            int pos = lo + k;
+            uint32_t v = fb[pad(pos)];
+            if (pos >= bpp && v == fb[pad(pos - bpp)]) eq |= 1ull << k;
+            A += v;
+            B += (uint32_t)(n - k) * v;
+        }
+        S.eq[t] = eq;
+        const unsigned long long valid = n == 64 ? ~0ull : ((1ull << n) - 1ull);
+        const unsigned long long zeros = ~eq & valid;
+        S.sa[t] = zeros ? lo + 63 - clz64(zeros) : -1;   // last position that is not in a run
+        S.sb[t] = zeros ? lo + ctz64(zeros) : BIG;       // first such position
+        S.adler_a[t] = A;
+        S.adler_b[t] = B;
+    });
+    // inclusive scans: sa[t] = last non-run position at or before segment t, sb[t] = first at or after it
+    for (int d = 1; d < THREADS; d <<= 1) {
+        ex.par([&](int t) {
+            int a = S.sa[t], b = S.sb[t];
+            if (t - d >= 0 && S.sa[t - d] > a) a = S.sa[t - d];
+            if (t + d < THREADS && S.sb[t + d] < b) b = S.sb[t + d];
+            S.ta[t] = a;
+            S.tb[t] = b;
+        });
+        ex.par([&](int t) {
+            S.sa[t] = S.ta[t];
+            S.sb[t] = S.tb[t];
+        });
+    }
+
+    // 3. symbol frequencies, counted into HIST_REPLICAS copies held in the (still zero) output buffer
+    ex.par([&](int t) {
+        HistSink h{S.out + (t % HIST_REPLICAS) * HIST_PITCH};
+        sweep(S, t, m, h);
+    });
+    ex.par([&](int t) {
+        for (int s = t; s < NSYM; s += THREADS) {
+            uint32_t f = s == EOB ? 1u : 0u;
+            for (int r = 0; r < HIST_REPLICAS; ++r) f += S.out[r * HIST_PITCH + s];
+            S.hist[s] = f;
+        }
+    });
+    // 4. used symbols sorted by (frequency, symbol): every thread ranks its own symbols
+    ex.par([&](int t) { rank_symbols(S, t); });
+    // 5. the code (one thread) while another thread folds the Adler partial sums
+    ex.par([&](int t) {
+        if (t == 0) build_code(S);
+        if (t == 32) {
+            unsigned long long a = 0, b = 0;
+            for (int u = 0; u < THREADS; ++u) {
+                int n = m - u * SEG;
+                if (n <= 0) break;
+                if (n > SEG) n = SEG;
+                b += (unsigned long long)n * a + S.adler_b[u];
+                a += S.adler_a[u];
+            }
+            S.chunk_a = (uint32_t)(a % ADLER_MOD);
+            S.chunk_b = (uint32_t)(b % ADLER_MOD);
+        }
+    });
+    // 6. bits per thread, prefix sums
+    ex.par([&](int t) {
+        CountSink c{S.len, 0u};
+        sweep(S, t, m, c);
+        S.bits[t] = (int)c.bits;
+        for (int w = t; w < HIST_REPLICAS * HIST_PITCH; w += THREADS) S.out[w] = 0;  // the output buffer again
+    });
+    for (int d = 1; d < THREADS; d <<= 1) {
+        ex.par([&](int t) { S.crc[t] = (uint32_t)(S.bits[t] + (t - d >= 0 ? S.bits[t - d] : 0)); });
+        ex.par([&](int t) { S.bits[t] = (int)S.crc[t]; });
+    }
+    // 7. dynamic block or stored block, whichever is shorter
+    ex.par([&](int t) {
+        if (t != 0) return;
+        S.header_bits = 17u + 57u + 4u * (uint32_t)(S.nlit + ndist);
+        S.data_bits = (uint32_t)S.bits[THREADS - 1];
+        uint32_t end = base_bits + S.header_bits + S.data_bits + S.len[EOB];
+        uint32_t n_dyn = final_chunk ? (end + 7u) / 8u : (end + 3u + 7u) / 8u + 4u;
+        uint32_t n_sto = base_bits / 8u + 5u + (uint32_t)m;
+        S.stored = n_sto < n_dyn;
+        S.n_out = (int)(S.stored ? n_sto : n_dyn);
+    });
+    // 8. the bit stream
+    ex.par([&](int t) {
+        uint8_t* ob = reinterpret_cast<uint8_t*>(S.out);
+        if (S.stored) {
+            const int hb = (int)(base_bits / 8u);
+            if (t == 0) {
+                if (chunk == 0) {
+                    ob[0] = 0x78;
+                    ob[1] = 0x01;
+                }
+                ob[hb] = final_chunk ? 1 : 0;
+                ob[hb + 1] = (uint8_t)(m & 255);
+                ob[hb + 2] = (uint8_t)(m >> 8);
+                ob[hb + 3] = (uint8_t)(~m & 255);
+                ob[hb + 4] = (uint8_t)((~m >> 8) & 255);
+            }
+            for (int o = t; o < m; o += THREADS) ob[hb + 5 + o] = fb[pad(o)];
+            return;
+        }
+        const uint32_t hdr = base_bits;
+        if (t == 0) {
+            if (chunk == 0) or_bits(S.out, 0, 0x0178u);
+            uint32_t h17 = (final_chunk ? 1u : 0u) | (2u << 1) | ((uint32_t)(S.nlit - 257) << 3) | ((uint32_t)(ndist - 1) << 8) | (15u << 13);
+            or_bits(S.out, hdr, h17);
+            // code-length code: symbols 16, 17, 18 unused, lengths 0..15 all four bits (a complete code)
+            for (int j = 0; j < 16; ++j) or_bits(S.out, hdr + 17u + 9u + 3u * (uint32_t)j, 4u);
+            // end of block, then (unless this is the last piece) an empty stored block to reach a byte boundary
+            uint32_t eob = hdr + S.header_bits + S.data_bits;
+            or_bits(S.out, eob, S.code[EOB]);
+            if (!final_chunk) {
+                uint32_t bs = (eob + S.len[EOB] + 3u + 7u) / 8u;
+                or_bits(S.out, 8u * (bs + 2u), 0xFFFFu);
+            }
+        }
+        for (int q = t; q < S.nlit + ndist; q += THREADS) {
+            int l = q < S.nlit ? S.len[q] : ((q - S.nlit == dsym || q - S.nlit == dother) ? 1 : 0);
+            or_bits(S.out, hdr + 74u + 4u * (uint32_t)q, bit_reverse((uint32_t)l, 4));
+        }
+        EmitSink e;
+        e.out = S.out;
+        e.len = S.len;
+        e.code = S.code;
+        e.dist_bit = dsym > dother ? 1u : 0u;
+        e.begin(hdr + S.header_bits + (t > 0 ? (uint32_t)S.bits[t - 1] : 0u));
+        sweep(S, t, m, e);
+        e.end();
+    });
+    // 9. CRC-32 of "IDAT" + piece. The register's 0xFFFFFFFF start equals complementing the first four
+    // message bytes; slices are counted from the END of the message so every slice but the first is full
+    // and the tree below multiplies by the same power of x at each level.
+    ex.par([&](int t) {
+        const uint8_t* ob = reinterpret_cast<const uint8_t*>(S.out);
+        const int total = S.n_out + 4;
+        int hi = total - CRC_SLICE * t, lo = hi - CRC_SLICE;
+        if (lo < 0) lo = 0;
+        uint32_t s = 0;
+        for (int p = lo; p < hi; ++p) {
+            uint32_t byte = p < 4 ? (uint32_t)(uint8_t)~"IDAT"[p] : ob[p - 4];
+            s = S.crc_table[(s ^ byte) & 255u] ^ (s >> 8);
+        }
+        S.crc[t] = s;
+    });
+    for (int d = 1, j = 0; d < THREADS; d <<= 1, ++j) {
+        ex.par([&](int t) {
+            if ((t & (2 * d - 1)) == 0) {
+                uint32_t earlier = S.crc[t + d];
+                if (earlier) S.crc[t] ^= gf_mul(earlier, T.xs[j]);
+            }
+        });
+    }
+    // 10. out
+    ex.par([&](int t) {
+        for (int w = t; w < (S.n_out + 3) / 4; w += THREADS) slot[w] = S.out[w];
+        if (t == 0) {
+            meta->n_out = (uint32_t)S.n_out;
+            meta->crc = ~S.crc[0];
+            meta->adler_a = S.chunk_a;
+            meta->adler_b = S.chunk_b;
+            meta->m = (uint32_t)m;
+        }
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+// Assembly: where each IDAT chunk goes, the Adler-32 of the whole stream, the fixed chunks.
+// ---------------------------------------------------------------------------------------------
+struct AdlerPart {
+    uint32_t len, a, b;  // all mod 65521
+};
+LPNG_HD AdlerPart adler_join(AdlerPart x, AdlerPart y) {  // x first, then y
+    AdlerPart r;
+    r.len = (x.len + y.len) % ADLER_MOD;
+    r.a = (x.a + y.a) % ADLER_MOD;
+    r.b = (uint32_t)(((unsigned long long)x.b + y.b + (unsigned long long)y.len * x.a) % ADLER_MOD);
+    return r;
+}
+
+struct LayoutShared {
+    unsigned long long sum[THREADS], tsum[THREADS];
+    AdlerPart ad[THREADS], tad[THREADS];
+};
+
+LPNG_HD void put_be32(uint8_t* p, uint32_t v) {
+    p[0] = (uint8_t)(v >> 24);
+    p[1] = (uint8_t)(v >> 16);
+    p[2] = (uint8_t)(v >> 8);
+    p[3] = (uint8_t)v;
+}
+
+LPNG_HD int color_type(uint32_t bpp) { return bpp == 1 ? 0 : bpp == 2 ? 4 : bpp == 3 ? 2 : 6; }
+
+// offsets[c] = file offset of piece c's IDAT chunk; writes signature, IHDR, the Adler IDAT and IEND; *total = file size.
+template <class Exec>
+LPNG_HDN void layout(Exec& ex, LayoutShared& L, const ChunkMeta* meta, uint32_t nchunks, uint32_t width, uint32_t height, uint32_t bpp,
+                            unsigned long long* offsets, uint8_t* out, unsigned long long* total) {
+    const uint32_t per = (nchunks + THREADS - 1) / THREADS;
+    ex.par([&](int t) {
+        unsigned long long s = 0;
+        AdlerPart a{0, 0, 0};
+        uint32_t c0 = (uint32_t)t * per, c1 = c0 + per < nchunks ? c0 + per : nchunks;
+        for (uint32_t c = c0; c < c1; ++c) {
+            s += 12ull + meta[c].n_out;
+            a = adler_join(a, AdlerPart{meta[c].m % ADLER_MOD, meta[c].adler_a, meta[c].adler_b});
+        }
+        L.sum[t] = s;
+        L.ad[t] = a;
+    });
+    for (int d = 1; d < THREADS; d <<= 1) {
+        ex.par([&](int t) {
+            L.tsum[t] = L.sum[t] + (t - d >= 0 ? L.sum[t - d] : 0ull);
+            L.tad[t] = t - d >= 0 ? adler_join(L.ad[t - d], L.ad[t]) : L.ad[t];
+        });
+        ex.par([&](int t) {
+            L.sum[t] = L.tsum[t];
+            L.ad[t] = L.tad[t];
+        });
+    }
+    ex.par([&](int t) {
+        unsigned long long off = PNG_HEADER_BYTES + (t > 0 ? L.sum[t - 1] : 0ull);
+        uint32_t c0 = (uint32_t)t * per, c1 = c0 + per < nchunks ? c0 + per : nchunks;
+        for (uint32_t c = c0; c < c1; ++c) {
+            offsets[c] = off;
+            off += 12ull + meta[c].n_out;
+        }
+        if (t != 0) return;
+        out[0] = 0x89; out[1] = 'P'; out[2] = 'N'; out[3] = 'G';
+        out[4] = 0x0D; out[5] = 0x0A; out[6] = 0x1A; out[7] = 0x0A;
+        uint8_t* p = out + 8;
+        put_be32(p, 13);
+        p[4] = 'I'; p[5] = 'H'; p[6] = 'D'; p[7] = 'R';
+        put_be32(p + 8, width);
+        put_be32(p + 12, height);
+        p[16] = 8;
+        p[17] = (uint8_t)color_type(bpp);
+        p[18] = 0; p[19] = 0; p[20] = 0;
+        uint32_t s = 0xFFFFFFFFu;
+        for (int i = 4; i < 21; ++i) s = crc_bitwise(s, p[i]);
+        put_be32(p + 21, ~s);
+        // zlib trailer in an IDAT chunk of its own: Adler-32 of the whole filtered stream
+        AdlerPart w = L.ad[THREADS - 1];
+        uint32_t s1 = (1u + w.a) % ADLER_MOD, s2 = (w.len + w.b) % ADLER_MOD;
+        p = out + PNG_HEADER_BYTES + L.sum[THREADS - 1];
+        put_be32(p, 4);
+        p[4] = 'I'; p[5] = 'D'; p[6] = 'A'; p[7] = 'T';
+        put_be32(p + 8, (s2 << 16) | s1);
+        s = 0xFFFFFFFFu;
+        for (int i = 4; i < 12; ++i) s = crc_bitwise(s, p[i]);
+        put_be32(p + 12, ~s);
+        p += 16;
+        put_be32(p, 0);
+        p[4] = 'I'; p[5] = 'E'; p[6] = 'N'; p[7] = 'D';
+        put_be32(p + 8, 0xAE426082u);
+        *total = PNG_HEADER_BYTES + L.sum[THREADS - 1] + PNG_TRAILER_BYTES;
+    });
+}
+
+// Piece c's IDAT chunk at its place: length, type, bytes, CRC.
+template <class Exec>
+LPNG_HDN void place_chunk(Exec& ex, const ChunkMeta& mt, const uint32_t* slot, uint8_t* dst) {
+    ex.par([&](int t) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(slot);
+        for (uint32_t o = (uint32_t)t; o < mt.n_out; o += THREADS) dst[8 + o] = src[o];
+        if (t == 0) {
+            put_be32(dst, mt.n_out);
+            dst[4] = 'I'; dst[5] = 'D'; dst[6] = 'A'; dst[7] = 'T';
+            put_be32(dst + 8 + mt.n_out, mt.crc);
+        }
+    });
+}
+
+// Upper bound of the file size (every piece stored).
+inline unsigned long long png_bound(uint32_t width, uint32_t height, uint32_t bpp) {
+    unsigned long long stream = (unsigned long long)height * ((unsigned long long)width * bpp + 1ull);
+    unsigned long long nchunks = (stream + CHUNK - 1) / CHUNK;
+    return PNG_HEADER_BYTES + stream + nchunks * (12ull + 5ull) + 2ull + PNG_TRAILER_BYTES;
+}
+
+}  // namespace lpng

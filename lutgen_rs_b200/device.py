@@ -271,6 +271,26 @@ def remap_image_(remapper, rgba, stream=None):
     return rgba
 
 
+def encode_png_(image, out=None, stream=None):
+    """PNG file bytes of a device image ((h, w, c) uint8 tensor, c in 1..4) into a device buffer, without the
+    pixels or the file visiting the host (lutgen_cuda_encode_png_dev). Returns a view of `out` of the file's
+    length; `out` (optional) must hold lutgen_rs_b200.png.bound(w, h, c) bytes."""
+    import ctypes as C
+
+    from . import png
+    _check_u8(image, "image")
+    if image.dim() == 2:
+        image = image.unsqueeze(-1)
+    h, w, c = image.shape
+    need = png.bound(w, h, c)
+    if out is None:
+        out = torch.empty(need, dtype=torch.uint8, device=image.device)
+    _check_u8(out, "out")
+    n = C.c_size_t(0)
+    _native.check(_native.lib().lutgen_cuda_encode_png_dev(image.data_ptr(), w, h, c, out.data_ptr(), out.numel(), C.byref(n), _stream(stream)))
+    return out[:n.value]
+
+
 def shard_frames(nframes, world, rank):
     """Contiguous frame shard for batched apply / remap (no exchange afterwards)."""
     per = -(-nframes // world)

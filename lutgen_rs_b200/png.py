@@ -1,0 +1,60 @@
+"""PNG writer around the path: what `RgbImage::save(path)` / `RgbaImage::save(path)`
+do for the reference's callers (crates/cli/src/main.rs:767, 811, 839 `lut.save(&path)`; 862-871
+`image.save(&path)`), with the encoding done by the CUDA kernels of csrc/png.cu through the C ABI
+(lutgen_cuda_encode_png*). Lossless: any PNG reader returns the pixels that went in. No CPU route.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native
+from .identity import _ptr
+
+
+def _as_image(image):
+    a = np.asarray(image)
+    if a.dtype != np.uint8 or a.ndim not in (2, 3):
+        raise TypeError("image must be a uint8 array of shape (h, w) or (h, w, channels)")
+    if a.ndim == 2:
+        a = a[:, :, None]
+    if not 1 <= a.shape[2] <= 4:
+        raise TypeError("1 to 4 channels (grey, grey+alpha, RGB, RGBA)")
+    return np.ascontiguousarray(a)
+
+
+def bound(width, height, channels):
+    """Largest file the encoder can produce for such an image (lutgen_cuda_png_bound)."""
+    n = C.c_size_t(0)
+    _native.check(_native.load().lutgen_cuda_png_bound(int(width), int(height), int(channels), C.byref(n)))
+    return n.value
+
+
+def encode(image):
+    """PNG file bytes of a (h, w[, c]) uint8 image (`image::ImageBuffer::save` with a .png path, minus the file)."""
+    a = _as_image(image)
+    h, w, c = a.shape
+    out = np.empty(bound(w, h, c), np.uint8)
+    n = C.c_size_t(0)
+    _native.check(_native.lib().lutgen_cuda_encode_png(_ptr(a), w, h, c, _ptr(out), out.size, C.byref(n)))
+    return out[:n.value].tobytes()
+
+
+def save(image, path):
+    """`image.save(path)` for a .png path."""
+    data = encode(image)
+    with open(path, "wb") as f:
+        f.write(data)
+
+
+def generate_lut_png(remapper, level, abort=None):
+    """`remapper.par_generate_lut(level)` followed by `lut.save(path)` (crates/cli/src/main.rs:742-767) with the
+    CLUT never leaving the device: returns the PNG bytes, or None if `abort` was seen set."""
+    from .interpolation import _abort_ptr
+    level = int(level)
+    if not 0 <= level <= 255:
+        raise OverflowError("level is a u8")
+    side = level ** 3 if 2 <= level <= 33 else 1
+    out = np.empty(bound(side, side, 3), np.uint8)
+    n = C.c_size_t(0)
+    aborted = _native.check(_native.lib().lutgen_cuda_generate_lut_png(remapper._h, level, _ptr(out), out.size, C.byref(n), _abort_ptr(abort)))
+    return None if aborted else out[:n.value].tobytes()
