@@ -79,6 +79,20 @@ LPNG_HD void atomic_add(uint32_t* p, uint32_t v) {
     *p += v;
 #endif
 }
+LPNG_HD uint32_t atomic_inc(uint32_t* p) {  // returns the old value
+#ifdef __CUDA_ARCH__
+    return atomicAdd(p, 1u);
+#else
+    return (*p)++;
+#endif
+}
+LPNG_HD void atomic_max(int* p, int v) {
+#ifdef __CUDA_ARCH__
+    atomicMax(p, v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
 LPNG_HD void atomic_or(uint32_t* p, uint32_t v) {
 #ifdef __CUDA_ARCH__
     atomicOr(p, v);
@@ -170,6 +184,20 @@ LPNG_HD void neighbours(const Image& im, uint32_t y, uint32_t x, int& cur, int& 
     }
 }
 
+// Filtered byte x of a row under filter ft (prow: the row above, or null).
+LPNG_HD uint8_t row_byte(int ft, const uint8_t* row, const uint8_t* prow, uint32_t x, uint32_t bpp) {
+    const int cur = row[x];
+    if (ft == 0) return (uint8_t)cur;
+    const bool left = x >= bpp;
+    if (ft == 1) return (uint8_t)(cur - (left ? row[x - bpp] : 0));
+    const int b = prow ? prow[x] : 0;
+    if (ft == 2) return (uint8_t)(cur - b);
+    const int a = left ? row[x - bpp] : 0;
+    if (ft == 3) return (uint8_t)(cur - ((a + b) >> 1));
+    const int c = (left && prow) ? prow[x - bpp] : 0;
+    return (uint8_t)(cur - paeth(a, b, c));
+}
+
 // Adds the absolute (signed-byte) residual of byte x of row y under each of the five filters.
 LPNG_HD void filter_costs(const Image& im, uint32_t y, uint32_t x, uint32_t cost[5]) {
     int cur, a, b, c;
@@ -221,10 +249,17 @@ LPNG_HD int length_symbol(int len, int& extra_bits, int& extra) {  // len in 3..
     return 257 + 4 * extra_bits + 4 + ((l >> extra_bits) - 4);
 }
 
-LPNG_HD uint32_t bit_reverse(uint32_t v, int n) {
-    uint32_t r = 0;
-    for (int i = 0; i < n; ++i) r |= ((v >> i) & 1u) << (n - 1 - i);
-    return r;
+LPNG_HD uint32_t bit_reverse(uint32_t v, int n) {  // the low n bits of v, reversed (n in 1..32)
+#ifdef __CUDA_ARCH__
+    return __brev(v) >> (32 - n);
+#else
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+    v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
+    v = (v >> 16) | (v << 16);
+    return v >> (32 - n);
+#endif
 }
 
 struct ChunkMeta {
@@ -242,16 +277,20 @@ struct Shared {
     uint32_t hist[NSYM];
     uint32_t node_freq[2 * NSYM];
     uint16_t node_parent[2 * NSYM];
+    uint16_t used[NSYM];       // used symbols, any order
     uint16_t order[NSYM];      // used symbols by ascending (frequency, symbol)
+    uint32_t next_code[MAX_BITS + 1];  // first canonical code of each length
     uint16_t code[NSYM];       // canonical codes, bit reversed (ready for the LSB-first stream)
     uint8_t len[NSYM];
     unsigned long long eq[THREADS];  // bit k: stream byte lo+k equals the byte bpp before it
+    unsigned long long ev[THREADS];  // bit k: a token starts at stream byte lo+k
+    unsigned long long ms[THREADS];  // ... and that token is a match
     int sa[THREADS], sb[THREADS], ta[THREADS], tb[THREADS];  // run-boundary scans (kept until the last sweep)
-    int bits[THREADS];               // token bits per thread, then their inclusive prefix sums
-    uint32_t adler_a[THREADS], adler_b[THREADS];
-    uint32_t crc[THREADS];
+    int bits[THREADS];               // Adler partial sums (b); later token bits per thread and their inclusive prefix sums
+    uint32_t crc[THREADS];           // Adler partial sums (a); later scan scratch, then CRC partial states
     uint32_t crc_table[256];
-    int nused, nlit, stored, n_out;
+    uint32_t nused;
+    int nlit, stored, n_out;
     uint32_t header_bits, data_bits, chunk_a, chunk_b;
 };
 
@@ -331,77 +370,135 @@ struct EmitSink {
 // the byte bpp before it is a run; a run of at least MIN_RUN bytes is cut into matches of 258 bytes
 // from its start (a tail shorter than 3 bytes goes out as literals), everything else is a literal.
 // s and e come from the thread's own bit mask or, when the run crosses its segment's ends, from the
-// scanned neighbours' masks (last0 / next0), so no thread waits for another.
+// scanned neighbours' masks (sa / sb), so no thread waits for another.
+struct RunEnds {
+    int s, e;
+};
+
+// The run that contains position lo+k (bit k of eq set).
+LPNG_HD RunEnds run_of(const Shared& S, int t, int m, int k) {
+    const int lo = t * SEG;
+    int n = m - lo;
+    if (n > SEG) n = SEG;
+    const unsigned long long valid = n == 64 ? ~0ull : ((1ull << n) - 1ull);
+    const unsigned long long zeros = ~S.eq[t] & valid;
+    const unsigned long long below = zeros & ((1ull << k) - 1ull);
+    const unsigned long long above = zeros >> k;
+    RunEnds r;
+    r.s = below ? lo + 64 - clz64(below) : (t > 0 ? S.sa[t - 1] : -1) + 1;
+    if (above) {
+        r.e = lo + k + ctz64(above);
+    } else {
+        int next0 = t + 1 < THREADS ? S.sb[t + 1] : BIG;
+        r.e = next0 > m ? m : next0;
+    }
+    return r;
+}
+
+// Where the matches of run [s, e) end: its last 1 or 2 bytes, if 258 does not divide the rest, are literals.
+LPNG_HD int match_end(int s, int e) {
+    const int rem = (e - s) % MAX_MATCH;
+    return e - (rem < 3 ? rem : 0);
+}
+
+// S.ev[t] / S.ms[t]: which of thread t's 64 positions start a token, and which of those start a match.
+// Positions in runs of at least MIN_RUN bytes are found with shifts of the thread's mask widened by
+// three positions on either side (whether a position's run has four bytes depends on nothing farther);
+// what is left is a literal. Each long run then contributes at most one match start to these 64 bytes.
+LPNG_HD void classify(Shared& S, int t, int m) {
+    const int lo = t * SEG;
+    int n = m - lo;
+    if (n <= 0) {
+        S.ev[t] = 0;
+        S.ms[t] = 0;
+        return;
+    }
+    if (n > SEG) n = SEG;
+    const unsigned long long E = S.eq[t];
+    const unsigned long long valid = n == 64 ? ~0ull : ((1ull << n) - 1ull);
+    const unsigned long long P3 = t > 0 ? S.eq[t - 1] >> 61 : 0ull;
+    const unsigned long long N3 = t + 1 < THREADS ? (S.eq[t + 1] & 7ull) : 0ull;
+    // window: bit i <-> position lo - 3 + i, 70 bits in (wl, wh)
+    unsigned long long wl = P3 | (E << 3), wh = (E >> 61) | (N3 << 3);
+    // pairs, then fours: bit i set if positions i..i+3 are all in runs
+    unsigned long long bl = wl & ((wl >> 1) | (wh << 63)), bh = wh & (wh >> 1);
+    unsigned long long al = bl & ((bl >> 2) | (bh << 62)), ah = bh & (bh >> 2);
+    // spread each four back over its positions
+    unsigned long long cl = al | (al << 1), ch = ah | (ah << 1) | (al >> 63);
+    unsigned long long ll = cl | (cl << 2), lh = ch | (ch << 2) | (cl >> 62);
+    const unsigned long long longrun = ((ll >> 3) | (lh << 61)) & valid;
+    unsigned long long ev = valid & ~longrun, ms = 0;
+    unsigned long long rest = longrun;
+    while (rest) {
+        const int a = ctz64(rest);
+        const unsigned long long inv = ~longrun >> a;  // bit 0 is clear
+        const int b = inv ? a + ctz64(inv) : 64;
+        const RunEnds r = run_of(S, t, m, a);
+        const int mend = match_end(r.s, r.e);
+        const int pos = lo + a, stop = lo + b;
+        const int p = r.s + ((pos - r.s + MAX_MATCH - 1) / MAX_MATCH) * MAX_MATCH;
+        if (p < stop && p < mend) {
+            ev |= 1ull << (p - lo);
+            ms |= 1ull << (p - lo);
+        }
+        for (int q = pos > mend ? pos : mend; q < stop; ++q) ev |= 1ull << (q - lo);
+        rest = b >= 64 ? 0ull : (rest & ~((1ull << b) - 1ull));
+    }
+    S.ev[t] = ev;
+    S.ms[t] = ms;
+}
+
 template <class Sink>
 LPNG_HD void sweep(const Shared& S, int t, int m, Sink& sink) {
     const int lo = t * SEG;
-    int n = m - lo;
-    if (n <= 0) return;
-    if (n > SEG) n = SEG;
     const uint8_t* fb = reinterpret_cast<const uint8_t*>(S.f);
-    const unsigned long long eq = S.eq[t];
-    const unsigned long long valid = n == 64 ? ~0ull : ((1ull << n) - 1ull);
-    const unsigned long long zeros = ~eq & valid;
-    const int last0 = t > 0 ? S.sa[t - 1] : -1;
-    int next0 = t + 1 < THREADS ? S.sb[t + 1] : BIG;
-    if (next0 > m) next0 = m;
-    int k = 0;
-    while (k < n) {
-        if (!((eq >> k) & 1ull)) {
+    unsigned long long ev = S.ev[t];
+    const unsigned long long ms = S.ms[t];
+    while (ev) {
+        const int k = ctz64(ev);
+        ev &= ev - 1ull;
+        if ((ms >> k) & 1ull) {
+            const RunEnds r = run_of(S, t, m, k);
+            const int left = match_end(r.s, r.e) - (lo + k);
+            sink.match(left < MAX_MATCH ? left : MAX_MATCH);
+        } else {
             sink.lit(fb[pad(lo + k)]);
-            ++k;
-            continue;
-        }
-        unsigned long long below = zeros & ((1ull << k) - 1ull);
-        int s = below ? lo + 64 - clz64(below) : last0 + 1;
-        unsigned long long above = zeros >> k;
-        int e = above ? lo + k + ctz64(above) : next0;
-        int kend = e - lo < n ? e - lo : n;
-        if (e - s < MIN_RUN) {
-            for (; k < kend; ++k) sink.lit(fb[pad(lo + k)]);
-            continue;
-        }
-        for (; k < kend; ++k) {
-            int off = lo + k - s;
-            int r = off % MAX_MATCH;
-            int pst = lo + k - r;
-            int plen = e - pst < MAX_MATCH ? e - pst : MAX_MATCH;
-            if (plen < 3)
-                sink.lit(fb[pad(lo + k)]);
-            else if (r == 0)
-                sink.match(plen);
         }
     }
 }
 
-// S.order = used symbols by ascending (frequency, symbol): thread t places its own symbols by counting
-// the symbols that come before them.
+// Used symbols, in any order, into S.used (S.nused and S.nlit start at 0 / 257).
+LPNG_HD void collect_symbols(Shared& S, int t) {
+    for (int s = t; s < NLITLEN; s += THREADS)
+        if (S.hist[s]) {
+            S.used[atomic_inc(&S.nused)] = (uint16_t)s;
+            if (s >= 257) atomic_max(&S.nlit, s + 1);
+        }
+}
+
+// S.order = used symbols by ascending (frequency, symbol): thread t places the t-th used symbol by
+// counting the used symbols that come before it.
 LPNG_HD void rank_symbols(Shared& S, int t) {
-    for (int s = t; s < NLITLEN; s += THREADS) {
-        uint32_t f = S.hist[s];
-        if (!f) continue;
+    const int n = (int)S.nused;
+    for (int i = t; i < n; i += THREADS) {
+        const int s = S.used[i];
+        const uint32_t f = S.hist[s];
         int r = 0;
-        for (int u = 0; u < NLITLEN; ++u) {
-            uint32_t fu = S.hist[u];
-            r += (fu && (fu < f || (fu == f && u < s))) ? 1 : 0;
+        for (int j = 0; j < n; ++j) {
+            const int u = S.used[j];
+            const uint32_t fu = S.hist[u];
+            r += (fu < f || (fu == f && u < s)) ? 1 : 0;
         }
         S.order[r] = (uint16_t)s;
     }
 }
 
-// Code lengths (at most MAX_BITS) and canonical codes from S.hist; one thread. Huffman's algorithm
-// with two queues over the frequency-sorted symbols (S.order), depths read off the parent links,
-// over-long codes folded into MAX_BITS and the Kraft sum repaired by demoting shorter codes, lengths
-// then handed out again in frequency order.
+// Code lengths (at most MAX_BITS) from S.hist and the first canonical code of every length; one thread.
+// Huffman's algorithm with two queues over the frequency-sorted symbols (S.order), depths read off the
+// parent links, over-long codes folded into MAX_BITS and the Kraft sum repaired by demoting shorter
+// codes, lengths then handed out again in frequency order.
 LPNG_HDN void build_code(Shared& S) {
-    int n = 0, nlit = 0;
-    for (int s = 0; s < NLITLEN; ++s)
-        if (S.hist[s]) {
-            ++n;
-            nlit = s + 1;
-        }
-    S.nused = n;
-    S.nlit = nlit < 257 ? 257 : nlit;
+    const int n = (int)S.nused;
     for (int i = 0; i < n; ++i) S.node_freq[i] = S.hist[S.order[i]];
     int li = 0, ii = n, nn = n;
     while (nn < 2 * n - 1) {
@@ -437,16 +534,27 @@ LPNG_HDN void build_code(Shared& S) {
     int i = n - 1;  // most frequent symbol first, shortest length first
     for (int l = 1; l <= MAX_BITS; ++l)
         for (uint32_t c = 0; c < cnt[l]; ++c) S.len[S.order[i--]] = (uint8_t)l;
-    uint32_t next[MAX_BITS + 2];
     uint32_t code = 0;
     cnt[0] = 0;
+    S.next_code[0] = 0;
     for (int l = 1; l <= MAX_BITS; ++l) {
         code = (code + cnt[l - 1]) << 1;
-        next[l] = code;
+        S.next_code[l] = code;
     }
-    for (int s = 0; s < NLITLEN; ++s) {
-        int l = S.len[s];
-        if (l) S.code[s] = (uint16_t)bit_reverse(next[l]++, l);
+}
+
+// Canonical codes: within one length, codes ascend with the symbol. Thread t places the t-th used symbol.
+LPNG_HD void assign_codes(Shared& S, int t) {
+    const int n = (int)S.nused;
+    for (int i = t; i < n; i += THREADS) {
+        const int s = S.used[i];
+        const int l = S.len[s];
+        uint32_t before = 0;
+        for (int j = 0; j < n; ++j) {
+            const int u = S.used[j];
+            before += (S.len[u] == l && u < s) ? 1u : 0u;
+        }
+        S.code[s] = (uint16_t)bit_reverse(S.next_code[l] + before, l);
     }
 }
 
@@ -471,18 +579,25 @@ LPNG_HDN void encode_chunk(Exec& ex, Shared& S, const Image& im, const Tables& T
     ex.par([&](int t) {
         for (int w = t; w < OUT_WORDS; w += THREADS) S.out[w] = 0;
         for (int w = t; w < NSYM; w += THREADS) S.len[w] = 0;
+        if (t == 0) {
+            S.nused = 0;
+            S.nlit = 257;
+        }
         S.crc_table[t] = T.crc[t];
+        // row by row (filter type, row pointers and bounds are then the same for the whole CTA)
         const uint32_t stride = im.rb + 1;
-        unsigned long long i = c0 + (unsigned)t;
-        uint32_t y = (uint32_t)(i / stride);
-        uint32_t col = (uint32_t)(i - (unsigned long long)y * stride);
-        for (int o = t; o < m; o += THREADS) {
-            fb[pad(o)] = stream_byte(im, y, col);
-            col += THREADS;
-            while (col >= stride) {
-                col -= stride;
-                ++y;
+        uint32_t y = (uint32_t)(c0 / stride);
+        uint32_t col = (uint32_t)(c0 - (unsigned long long)y * stride);
+        for (int o = 0; o < m; ++y, col = 0) {
+            const int cnt = (int)(stride - col) < m - o ? (int)(stride - col) : m - o;
+            const int ft = im.filters[y];
+            const uint8_t* row = im.px + (size_t)y * im.rb;
+            const uint8_t* prow = y > 0 ? row - im.rb : nullptr;
+            for (int i = t; i < cnt; i += THREADS) {
+                const uint32_t cc = col + (uint32_t)i;
+                fb[pad(o + i)] = cc == 0 ? (uint8_t)ft : row_byte(ft, row, prow, cc - 1, im.bpp);
             }
+            o += cnt;
         }
     });
 
@@ -505,8 +620,8 @@ LPNG_HDN void encode_chunk(Exec& ex, Shared& S, const Image& im, const Tables& T
         const unsigned long long zeros = ~eq & valid;
         S.sa[t] = zeros ? lo + 63 - clz64(zeros) : -1;   // last position that is not in a run
         S.sb[t] = zeros ? lo + ctz64(zeros) : BIG;       // first such position
-        S.adler_a[t] = A;
-        S.adler_b[t] = B;
+        S.crc[t] = A;
+        S.bits[t] = (int)B;
     });
     // inclusive scans: sa[t] = last non-run position at or before segment t, sb[t] = first at or after it
     for (int d = 1; d < THREADS; d <<= 1) {
@@ -523,8 +638,9 @@ LPNG_HDN void encode_chunk(Exec& ex, Shared& S, const Image& im, const Tables& T
         });
     }
 
-    // 3. symbol frequencies, counted into HIST_REPLICAS copies held in the (still zero) output buffer
+    // 3. token starts, then symbol frequencies, counted into HIST_REPLICAS copies held in the (still zero) output buffer
     ex.par([&](int t) {
+        classify(S, t, m);
         HistSink h{S.out + (t % HIST_REPLICAS) * HIST_PITCH};
         sweep(S, t, m, h);
     });
@@ -536,6 +652,7 @@ LPNG_HDN void encode_chunk(Exec& ex, Shared& S, const Image& im, const Tables& T
         }
     });
     // 4. used symbols sorted by (frequency, symbol): every thread ranks its own symbols
+    ex.par([&](int t) { collect_symbols(S, t); });
     ex.par([&](int t) { rank_symbols(S, t); });
     // 5. the code (one thread) while another thread folds the Adler partial sums
     ex.par([&](int t) {
@@ -546,13 +663,14 @@ LPNG_HDN void encode_chunk(Exec& ex, Shared& S, const Image& im, const Tables& T
                 int n = m - u * SEG;
                 if (n <= 0) break;
                 if (n > SEG) n = SEG;
-                b += (unsigned long long)n * a + S.adler_b[u];
-                a += S.adler_a[u];
+                b += (unsigned long long)n * a + (uint32_t)S.bits[u];
+                a += S.crc[u];
             }
             S.chunk_a = (uint32_t)(a % ADLER_MOD);
             S.chunk_b = (uint32_t)(b % ADLER_MOD);
         }
     });
+    ex.par([&](int t) { assign_codes(S, t); });
     // 6. bits per thread, prefix sums
     ex.par([&](int t) {
         CountSink c{S.len, 0u};

@@ -72,8 +72,12 @@ void lpng_sim_code(const uint32_t* hist, uint8_t* len, uint16_t* code) {
         S->hist[s] = s < NLITLEN ? hist[s] : 0;
         S->len[s] = 0;
     }
+    S->nused = 0;
+    S->nlit = 257;
+    for (int t = 0; t < THREADS; ++t) collect_symbols(*S, t);
     for (int t = 0; t < THREADS; ++t) rank_symbols(*S, t);
     build_code(*S);
+    for (int t = 0; t < THREADS; ++t) assign_codes(*S, t);
     for (int s = 0; s < NLITLEN; ++s) {
         len[s] = S->len[s];
         code[s] = S->len[s] ? S->code[s] : 0;
