@@ -524,6 +524,49 @@ def run_b200(args):
         other_configs["direct_remap_image_first_call_ms"] = round(ts[0], 3)
         other_configs["direct_remap_image_what"] = (f"GaussianRemapper.remap_image on {nfr} photo-like 4K RGBA frames in one call, device resident; "
                                                     "the first call includes tabulating the remapper over the sRGB cube")
+        # the PNG writer around the path (`lut.save(path)`): the headline CLUT encoded on the device,
+        # `lutgen generate` end to end as generate + encode + download of the PNG bytes, and a CPU PNG encoder beside it.
+        from lutgen_rs_b200 import png as lpng
+        side16 = 16 ** 3
+        clut = torch.empty((side16, side16, 3), dtype=torch.uint8, device="cuda")
+        device.generate_lut_rows_(rm, 16, clut.view(-1), 0, side16)
+        png_out = torch.empty(lpng.bound(side16, side16, 3), dtype=torch.uint8, device="cuda")
+        ts = []
+        for i in range(6):
+            flush_l2()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            view = device.encode_png_(clut, png_out, stream)
+            b.record(stream)
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        other_configs["png_encode_level16_clut_ms"] = round(float(np.median(ts[1:])), 3)
+        other_configs["png_encode_level16_clut_bytes"] = int(view.numel())
+        other_configs["png_encode_level16_clut_gb_per_s_of_pixels"] = round(clut.numel() / (float(np.median(ts[1:])) * 1e-3) / 1e9, 1)
+        ts = []
+        for i in range(4):
+            t0 = time.perf_counter()
+            data = lpng.generate_lut_png(rm, 16)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        other_configs["generate_lut_png_level16_host_to_host_ms"] = round(float(np.median(ts[1:])), 2)
+        if not args.no_cpu:
+            try:
+                import io
+
+                from PIL import Image
+                host = clut.cpu().numpy()
+                assert (np.array(Image.open(io.BytesIO(data))) == host).all(), "PNG does not decode to the CLUT"
+                t0 = time.perf_counter()
+                bio = io.BytesIO()
+                Image.fromarray(host).save(bio, "PNG", compress_level=1)
+                other_configs["cpu_png_encode_level16_clut_ms"] = round((time.perf_counter() - t0) * 1e3, 1)
+                other_configs["cpu_png_encode_level16_clut_bytes"] = len(bio.getvalue())
+            except ImportError:
+                pass
+        other_configs["png_what"] = ("PNG file bytes of the level-16 headline CLUT: device resident (L2 flushed), then generate + encode + "
+                                     "download through lutgen_cuda_generate_lut_png with pageable host memory; cpu_* = PIL (zlib level 1, one "
+                                     "thread) on the same CLUT, checked to decode to the same pixels -- the reference's `image` crate "
+                                     "encoder cannot run here")
     top, other, other_key = (gen_line, apply_line, "apply") if args.workload == "generate" else (apply_line, gen_line, "generate")
     line = dict(top)
     line.update({"n_gpus": world, "steps": steps, "warmup": warmup, "higher_is_better": True, "vs_baseline": None,

@@ -21,6 +21,7 @@
 #include <array>
 #include <atomic>
 #include <cstdint>
+#include <cstdio>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -120,6 +121,32 @@ inline void correct_images(std::vector<RgbaImage*>& images, const RgbImage& hald
 }
 
 }  // namespace identity
+
+// `image.save(path)` for a .png path (the `image` crate's PNG writer as the reference's callers use it,
+// crates/cli/src/main.rs:767, 811, 839, 862), encoded by the CUDA library.
+namespace png {
+
+template <int CH>
+inline std::vector<uint8_t> encode(const Image<CH>& image) {
+    detail::ensure_init();
+    size_t bound = 0, len = 0;
+    detail::check(lutgen_cuda_png_bound(image.width, image.height, CH, &bound));
+    std::vector<uint8_t> file(bound);
+    detail::check(lutgen_cuda_encode_png(image.data.data(), image.width, image.height, CH, file.data(), file.size(), &len));
+    file.resize(len);
+    return file;
+}
+
+template <int CH>
+inline void save(const Image<CH>& image, const std::string& path) {
+    std::vector<uint8_t> file = encode(image);
+    std::FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) throw Error("cannot open " + path);
+    size_t n = std::fwrite(file.data(), 1, file.size(), f);
+    if (std::fclose(f) != 0 || n != file.size()) throw Error("cannot write " + path);
+}
+
+}  // namespace png
 
 namespace interpolation {
 

@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(FILTER_WARPS * 32) k_png_choose_filters(lpng::
     const uint32_t y = blockIdx.x * FILTER_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
     if (y >= im.height) return;
     uint32_t cost[5] = {0u, 0u, 0u, 0u, 0u};
-    for (uint32_t x = lane; x < im.rb; x += 32u) lpng::filter_costs(im, y, x, cost);
+    const uint8_t* row = im.px + (size_t)y * im.rb;
+    lpng::row_costs(row, y > 0 ? row - im.rb : nullptr, im.rb, im.bpp, lane, 32u, cost);
 #pragma unroll
     for (int ft = 0; ft < 5; ++ft)
 #pragma unroll

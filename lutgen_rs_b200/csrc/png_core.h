@@ -72,6 +72,13 @@ LPNG_HD int ctz64(unsigned long long v) {
     return __builtin_ctzll(v);
 #endif
 }
+LPNG_HD int ctz32(uint32_t v) {  // v != 0
+#ifdef __CUDA_ARCH__
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
 LPNG_HD void atomic_add(uint32_t* p, uint32_t v) {
 #ifdef __CUDA_ARCH__
     atomicAdd(p, v);
@@ -164,50 +171,50 @@ LPNG_HD int paeth(int a, int b, int c) {
     return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
 }
 
-LPNG_HD uint8_t filter_value(int ft, int cur, int a, int b, int c) {
-    int pred = ft == 0 ? 0 : ft == 1 ? a : ft == 2 ? b : ft == 3 ? ((a + b) >> 1) : paeth(a, b, c);
-    return (uint8_t)(cur - pred);
-}
-
-// Neighbourhood of byte x of row y: left (a), up (b), up-left (c); 0 outside the image.
-LPNG_HD void neighbours(const Image& im, uint32_t y, uint32_t x, int& cur, int& a, int& b, int& c) {
-    const uint8_t* row = im.px + (size_t)y * im.rb;
-    cur = row[x];
-    a = x >= im.bpp ? row[x - im.bpp] : 0;
-    if (y > 0) {
-        const uint8_t* prow = row - im.rb;
-        b = prow[x];
-        c = x >= im.bpp ? prow[x - im.bpp] : 0;
-    } else {
-        b = 0;
-        c = 0;
+// Bytes [xbase, xbase + ndata) of a row under filter FT into the padded stream buffer at offset obase
+// (prow: the row above, or null); thread t of the CTA takes every THREADS-th byte.
+template <int FT>
+LPNG_HD void filter_span(uint8_t* fb, int obase, const uint8_t* row, const uint8_t* prow, uint32_t xbase, int ndata, uint32_t bpp, int t) {
+    for (int i = t; i < ndata; i += THREADS) {
+        const uint32_t x = xbase + (uint32_t)i;
+        const int cur = row[x];
+        int pred = 0;
+        if (FT == 1) {
+            pred = x >= bpp ? row[x - bpp] : 0;
+        } else if (FT == 2) {
+            pred = prow ? prow[x] : 0;
+        } else if (FT == 3) {
+            const int a = x >= bpp ? row[x - bpp] : 0, b = prow ? prow[x] : 0;
+            pred = (a + b) >> 1;
+        } else if (FT == 4) {
+            const bool left = x >= bpp;
+            const int a = left ? row[x - bpp] : 0, b = prow ? prow[x] : 0, c = (left && prow) ? prow[x - bpp] : 0;
+            pred = paeth(a, b, c);
+        }
+        fb[pad(obase + i)] = (uint8_t)(cur - pred);
     }
 }
 
-// Filtered byte x of a row under filter ft (prow: the row above, or null).
-LPNG_HD uint8_t row_byte(int ft, const uint8_t* row, const uint8_t* prow, uint32_t x, uint32_t bpp) {
-    const int cur = row[x];
-    if (ft == 0) return (uint8_t)cur;
-    const bool left = x >= bpp;
-    if (ft == 1) return (uint8_t)(cur - (left ? row[x - bpp] : 0));
-    const int b = prow ? prow[x] : 0;
-    if (ft == 2) return (uint8_t)(cur - b);
-    const int a = left ? row[x - bpp] : 0;
-    if (ft == 3) return (uint8_t)(cur - ((a + b) >> 1));
-    const int c = (left && prow) ? prow[x - bpp] : 0;
-    return (uint8_t)(cur - paeth(a, b, c));
+// |signed byte| of a residual given mod 256.
+LPNG_HD uint32_t abs_residual(int r) {
+    const uint32_t u = (uint32_t)r & 255u;
+    return u < 256u - u ? u : 256u - u;
 }
 
-// Adds the absolute (signed-byte) residual of byte x of row y under each of the five filters.
-LPNG_HD void filter_costs(const Image& im, uint32_t y, uint32_t x, uint32_t cost[5]) {
-    int cur, a, b, c;
-    neighbours(im, y, x, cur, a, b, c);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int ft = 0; ft < 5; ++ft) {
-        int r = (int8_t)filter_value(ft, cur, a, b, c);
-        cost[ft] += (uint32_t)(r < 0 ? -r : r);
+// Adds, for bytes first, first + step, ... of a row, the absolute (signed-byte) residual under each of the
+// five filters (prow: the row above, or null).
+LPNG_HD void row_costs(const uint8_t* row, const uint8_t* prow, uint32_t rb, uint32_t bpp, uint32_t first, uint32_t step, uint32_t cost[5]) {
+    for (uint32_t x = first; x < rb; x += step) {
+        const bool left = x >= bpp;
+        const int cur = row[x];
+        const int a = left ? row[x - bpp] : 0;
+        const int b = prow ? prow[x] : 0;
+        const int c = (left && prow) ? prow[x - bpp] : 0;
+        cost[0] += abs_residual(cur);
+        cost[1] += abs_residual(cur - a);
+        cost[2] += abs_residual(cur - b);
+        cost[3] += abs_residual(cur - ((a + b) >> 1));
+        cost[4] += abs_residual(cur - paeth(a, b, c));
     }
 }
 
@@ -216,15 +223,6 @@ LPNG_HD int pick_filter(const uint32_t cost[5]) {
     for (int ft = 1; ft < 5; ++ft)
         if (cost[ft] < cost[best]) best = ft;
     return best;
-}
-
-// Byte `col` of filtered scanline y (col 0 is the filter-type byte).
-LPNG_HD uint8_t stream_byte(const Image& im, uint32_t y, uint32_t col) {
-    int ft = im.filters[y];
-    if (col == 0) return (uint8_t)ft;
-    int cur, a, b, c;
-    neighbours(im, y, col - 1, cur, a, b, c);
-    return filter_value(ft, cur, a, b, c);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -280,7 +278,7 @@ struct Shared {
     uint16_t used[NSYM];       // used symbols, any order
     uint16_t order[NSYM];      // used symbols by ascending (frequency, symbol)
     uint32_t next_code[MAX_BITS + 1];  // first canonical code of each length
-    uint16_t code[NSYM];       // canonical codes, bit reversed (ready for the LSB-first stream)
+    uint32_t codelen[NSYM];    // canonical code, bit reversed (ready for the LSB-first stream) | length << 16
     uint8_t len[NSYM];
     unsigned long long eq[THREADS];  // bit k: stream byte lo+k equals the byte bpp before it
     unsigned long long ev[THREADS];  // bit k: a token starts at stream byte lo+k
@@ -325,9 +323,8 @@ struct CountSink {
 // are shared with its neighbours (atomic OR into the zeroed buffer), the words between are its own.
 struct EmitSink {
     uint32_t* out;
-    const uint8_t* len;
-    const uint16_t* code;
-    unsigned long long acc;
+    const uint32_t* codelen;
+    uint32_t acc;
     int nacc;
     uint32_t w;
     bool first;
@@ -338,31 +335,33 @@ struct EmitSink {
         w = bitpos >> 5;
         first = true;
     }
-    LPNG_HD void put(uint32_t v, int n) {
-        acc |= (unsigned long long)v << nacc;
+    LPNG_HD void put(uint32_t v, int n) {  // the low n bits of v (n in 1..32, nothing above them)
+        acc |= v << nacc;
         nacc += n;
         if (nacc >= 32) {
             if (first) {
-                atomic_or(&out[w], (uint32_t)acc);
+                atomic_or(&out[w], acc);
                 first = false;
             } else {
-                out[w] = (uint32_t)acc;
+                out[w] = acc;
             }
             ++w;
-            acc >>= 32;
             nacc -= 32;
+            acc = nacc ? v >> (n - nacc) : 0u;
         }
     }
     LPNG_HD void end() {
-        if (nacc > 0 && (uint32_t)acc) atomic_or(&out[w], (uint32_t)acc);
+        if (nacc > 0 && acc) atomic_or(&out[w], acc);
     }
-    LPNG_HD void lit(int b) { put(code[b], len[b]); }
-    LPNG_HD void match(int l) {
+    LPNG_HD void lit(int b) {
+        const uint32_t cl = codelen[b];
+        put(cl & 0xFFFFu, (int)(cl >> 16));
+    }
+    LPNG_HD void match(int l) {  // length code, its extra bits and the one-bit distance code in one go (at most 21 bits)
         int eb, ex;
-        int s = length_symbol(l, eb, ex);
-        put(code[s], len[s]);
-        if (eb) put((uint32_t)ex, eb);
-        put(dist_bit, 1);
+        const uint32_t cl = codelen[length_symbol(l, eb, ex)];
+        const int n0 = (int)(cl >> 16);
+        put((cl & 0xFFFFu) | ((uint32_t)ex << n0) | (dist_bit << (n0 + eb)), n0 + eb + 1);
     }
 };
 
@@ -393,6 +392,11 @@ LPNG_HD RunEnds run_of(const Shared& S, int t, int m, int k) {
         r.e = next0 > m ? m : next0;
     }
     return r;
+}
+
+// True if the run containing position lo+k (bit k of eq set) starts exactly there.
+LPNG_HD bool run_starts_at(const Shared& S, int t, int k) {
+    return k > 0 ? !((S.eq[t] >> (k - 1)) & 1ull) : (t == 0 || !(S.eq[t - 1] >> 63));
 }
 
 // Where the matches of run [s, e) end: its last 1 or 2 bytes, if 258 does not divide the rest, are literals.
@@ -433,36 +437,49 @@ LPNG_HD void classify(Shared& S, int t, int m) {
         const int a = ctz64(rest);
         const unsigned long long inv = ~longrun >> a;  // bit 0 is clear
         const int b = inv ? a + ctz64(inv) : 64;
-        const RunEnds r = run_of(S, t, m, a);
-        const int mend = match_end(r.s, r.e);
-        const int pos = lo + a, stop = lo + b;
-        const int p = r.s + ((pos - r.s + MAX_MATCH - 1) / MAX_MATCH) * MAX_MATCH;
-        if (p < stop && p < mend) {
-            ev |= 1ull << (p - lo);
-            ms |= 1ull << (p - lo);
+        if (b < 64 && run_starts_at(S, t, a)) {  // the run lies inside these 64 bytes: one match from its start
+            ev |= 1ull << a;
+            ms |= 1ull << a;
+        } else {
+            const RunEnds r = run_of(S, t, m, a);
+            const int mend = match_end(r.s, r.e);
+            const int pos = lo + a, stop = lo + b;
+            const int p = r.s + ((pos - r.s + MAX_MATCH - 1) / MAX_MATCH) * MAX_MATCH;
+            if (p < stop && p < mend) {
+                ev |= 1ull << (p - lo);
+                ms |= 1ull << (p - lo);
+            }
+            for (int q = pos > mend ? pos : mend; q < stop; ++q) ev |= 1ull << (q - lo);
         }
-        for (int q = pos > mend ? pos : mend; q < stop; ++q) ev |= 1ull << (q - lo);
         rest = b >= 64 ? 0ull : (rest & ~((1ull << b) - 1ull));
     }
     S.ev[t] = ev;
     S.ms[t] = ms;
 }
 
+// Length of the match that starts at position lo+k.
+LPNG_HD int match_length(const Shared& S, int t, int m, int k) {
+    const unsigned long long rest = ~S.eq[t] >> k;  // bit 0 clear; bits past the data are set
+    if (rest && run_starts_at(S, t, k)) return ctz64(rest);  // the whole run lies in these 64 bytes: one match
+    const RunEnds r = run_of(S, t, m, k);
+    const int left = match_end(r.s, r.e) - (t * SEG + k);
+    return left < MAX_MATCH ? left : MAX_MATCH;
+}
+
 template <class Sink>
 LPNG_HD void sweep(const Shared& S, int t, int m, Sink& sink) {
-    const int lo = t * SEG;
-    const uint8_t* fb = reinterpret_cast<const uint8_t*>(S.f);
-    unsigned long long ev = S.ev[t];
-    const unsigned long long ms = S.ms[t];
-    while (ev) {
-        const int k = ctz64(ev);
-        ev &= ev - 1ull;
-        if ((ms >> k) & 1ull) {
-            const RunEnds r = run_of(S, t, m, k);
-            const int left = match_end(r.s, r.e) - (lo + k);
-            sink.match(left < MAX_MATCH ? left : MAX_MATCH);
-        } else {
-            sink.lit(fb[pad(lo + k)]);
+    const uint8_t* seg = reinterpret_cast<const uint8_t*>(S.f) + pad(t * SEG);  // a thread's 64 bytes are contiguous
+    const unsigned long long ev = S.ev[t], ms = S.ms[t];
+    for (int h = 0; h < 2; ++h) {
+        uint32_t e = (uint32_t)(ev >> (32 * h));
+        const uint32_t mh = (uint32_t)(ms >> (32 * h));
+        while (e) {
+            const int k = ctz32(e);
+            e &= e - 1u;
+            if ((mh >> k) & 1u)
+                sink.match(match_length(S, t, m, k + 32 * h));
+            else
+                sink.lit(seg[k + 32 * h]);
         }
     }
 }
@@ -554,7 +571,7 @@ LPNG_HD void assign_codes(Shared& S, int t) {
             const int u = S.used[j];
             before += (S.len[u] == l && u < s) ? 1u : 0u;
         }
-        S.code[s] = (uint16_t)bit_reverse(S.next_code[l] + before, l);
+        S.codelen[s] = bit_reverse(S.next_code[l] + before, l) | ((uint32_t)l << 16);
     }
 }
 
@@ -593,9 +610,15 @@ LPNG_HDN void encode_chunk(Exec& ex, Shared& S, const Image& im, const Tables& T
             const int ft = im.filters[y];
             const uint8_t* row = im.px + (size_t)y * im.rb;
             const uint8_t* prow = y > 0 ? row - im.rb : nullptr;
-            for (int i = t; i < cnt; i += THREADS) {
-                const uint32_t cc = col + (uint32_t)i;
-                fb[pad(o + i)] = cc == 0 ? (uint8_t)ft : row_byte(ft, row, prow, cc - 1, im.bpp);
+            const int lead = col == 0 ? 1 : 0;  // the row's filter-type byte opens this span
+            if (lead && t == 0) fb[pad(o)] = (uint8_t)ft;
+            const uint32_t xbase = col == 0 ? 0u : col - 1u;
+            switch (ft) {
+                case 0: filter_span<0>(fb, o + lead, row, prow, xbase, cnt - lead, im.bpp, t); break;
+                case 1: filter_span<1>(fb, o + lead, row, prow, xbase, cnt - lead, im.bpp, t); break;
+                case 2: filter_span<2>(fb, o + lead, row, prow, xbase, cnt - lead, im.bpp, t); break;
+                case 3: filter_span<3>(fb, o + lead, row, prow, xbase, cnt - lead, im.bpp, t); break;
+                default: filter_span<4>(fb, o + lead, row, prow, xbase, cnt - lead, im.bpp, t); break;
             }
             o += cnt;
         }
@@ -721,7 +744,7 @@ LPNG_HDN void encode_chunk(Exec& ex, Shared& S, const Image& im, const Tables& T
             for (int j = 0; j < 16; ++j) or_bits(S.out, hdr + 17u + 9u + 3u * (uint32_t)j, 4u);
             // end of block, then (unless this is the last piece) an empty stored block to reach a byte boundary
             uint32_t eob = hdr + S.header_bits + S.data_bits;
-            or_bits(S.out, eob, S.code[EOB]);
+            or_bits(S.out, eob, S.codelen[EOB] & 0xFFFFu);
             if (!final_chunk) {
                 uint32_t bs = (eob + S.len[EOB] + 3u + 7u) / 8u;
                 or_bits(S.out, 8u * (bs + 2u), 0xFFFFu);
@@ -733,8 +756,7 @@ LPNG_HDN void encode_chunk(Exec& ex, Shared& S, const Image& im, const Tables& T
         }
         EmitSink e;
         e.out = S.out;
-        e.len = S.len;
-        e.code = S.code;
+        e.codelen = S.codelen;
         e.dist_bit = dsym > dother ? 1u : 0u;
         e.begin(hdr + S.header_bits + (t > 0 ? (uint32_t)S.bits[t - 1] : 0u));
         sweep(S, t, m, e);

@@ -124,6 +124,16 @@ int main() {
         RgbImage lut = ok.generate_lut(3);
         EXPECT(lut.width == 27);
     }
+    // png::encode: signature, IHDR geometry, IEND at the end (decoding is checked in tests/test_gpu_png.py)
+    {
+        RgbImage id = identity::generate(4);
+        std::vector<uint8_t> file = png::encode(id);
+        static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+        EXPECT(file.size() > 57 && std::memcmp(file.data(), sig, 8) == 0);
+        EXPECT(std::memcmp(file.data() + 12, "IHDR", 4) == 0 && file[18] == 0 && file[19] == 64 && file[22] == 0 && file[23] == 64);
+        EXPECT(file[24] == 8 && file[25] == 2);
+        EXPECT(std::memcmp(file.data() + file.size() - 8, "IEND", 4) == 0);
+    }
     if (failures == 0) std::printf("host mirror OK\n");
     return failures ? 1 : 0;
 }

@@ -36,7 +36,8 @@ int lpng_sim_encode(const uint8_t* px, uint32_t width, uint32_t height, uint32_t
     Image im{px, filters.data(), width, height, bpp, width * bpp, (unsigned long long)height * ((unsigned long long)width * bpp + 1ull)};
     for (uint32_t y = 0; y < height; ++y) {  // one warp per row on the GPU (k_png_choose_filters)
         uint32_t cost[5] = {0, 0, 0, 0, 0};
-        for (uint32_t x = 0; x < im.rb; ++x) filter_costs(im, y, x, cost);
+        const uint8_t* row = px + (size_t)y * im.rb;
+        for (uint32_t lane = 0; lane < 32; ++lane) row_costs(row, y > 0 ? row - im.rb : nullptr, im.rb, bpp, lane, 32, cost);
         filters[y] = (uint8_t)pick_filter(cost);
     }
     if (filters_out) memcpy(filters_out, filters.data(), height);
@@ -80,7 +81,7 @@ void lpng_sim_code(const uint32_t* hist, uint8_t* len, uint16_t* code) {
     for (int t = 0; t < THREADS; ++t) assign_codes(*S, t);
     for (int s = 0; s < NLITLEN; ++s) {
         len[s] = S->len[s];
-        code[s] = S->len[s] ? S->code[s] : 0;
+        code[s] = S->len[s] ? (uint16_t)(S->codelen[s] & 0xFFFFu) : 0;
     }
     delete S;
 }
