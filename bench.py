@@ -564,7 +564,7 @@ def run_b200(args):
             except ImportError:
                 pass
         other_configs["png_what"] = ("PNG file bytes of the level-16 headline CLUT: device resident (L2 flushed), then generate + encode + "
-                                     "download through lutgen_cuda_generate_lut_png with pageable host memory; cpu_* = PIL (zlib level 1, one "
+                                     "download through lutgen_cuda_generate_lut_png into a page-locked buffer, copied into a Python bytes object; cpu_* = PIL (zlib level 1, one "
                                      "thread) on the same CLUT, checked to decode to the same pixels -- the reference's `image` crate "
                                      "encoder cannot run here")
     top, other, other_key = (gen_line, apply_line, "apply") if args.workload == "generate" else (apply_line, gen_line, "generate")

@@ -4,6 +4,7 @@ do for the reference's callers (crates/cli/src/main.rs:767, 811, 839 `lut.save(&
 (lutgen_cuda_encode_png*). Lossless: any PNG reader returns the pixels that went in. No CPU route.
 """
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -22,6 +23,25 @@ def _as_image(image):
     return np.ascontiguousarray(a)
 
 
+_stage_lock = threading.Lock()
+_stage = None  # (pointer, capacity, uint8 view): page-locked landing zone for the file bytes, grown on demand
+
+
+def _staging(nbytes):
+    """A page-locked buffer of at least nbytes (lutgen_cuda_host_alloc): the download of the file is then one
+    DMA instead of a staged copy into pageable memory. Call with _stage_lock held."""
+    global _stage
+    if _stage is None or _stage[1] < nbytes:
+        L = _native.lib()
+        if _stage is not None:
+            L.lutgen_cuda_host_free(_stage[0])
+            _stage = None
+        p = C.c_void_p()
+        _native.check(L.lutgen_cuda_host_alloc(nbytes, C.byref(p)))
+        _stage = (p, nbytes, np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(p.value)))
+    return _stage[2]
+
+
 def bound(width, height, channels):
     """Largest file the encoder can produce for such an image (lutgen_cuda_png_bound)."""
     n = C.c_size_t(0)
@@ -33,10 +53,11 @@ def encode(image):
     """PNG file bytes of a (h, w[, c]) uint8 image (`image::ImageBuffer::save` with a .png path, minus the file)."""
     a = _as_image(image)
     h, w, c = a.shape
-    out = np.empty(bound(w, h, c), np.uint8)
     n = C.c_size_t(0)
-    _native.check(_native.lib().lutgen_cuda_encode_png(_ptr(a), w, h, c, _ptr(out), out.size, C.byref(n)))
-    return out[:n.value].tobytes()
+    with _stage_lock:
+        out = _staging(bound(w, h, c))
+        _native.check(_native.lib().lutgen_cuda_encode_png(_ptr(a), w, h, c, _ptr(out), out.size, C.byref(n)))
+        return out[:n.value].tobytes()
 
 
 def save(image, path):
@@ -54,7 +75,8 @@ def generate_lut_png(remapper, level, abort=None):
     if not 0 <= level <= 255:
         raise OverflowError("level is a u8")
     side = level ** 3 if 2 <= level <= 33 else 1
-    out = np.empty(bound(side, side, 3), np.uint8)
     n = C.c_size_t(0)
-    aborted = _native.check(_native.lib().lutgen_cuda_generate_lut_png(remapper._h, level, _ptr(out), out.size, C.byref(n), _abort_ptr(abort)))
-    return None if aborted else out[:n.value].tobytes()
+    with _stage_lock:
+        out = _staging(bound(side, side, 3))
+        aborted = _native.check(_native.lib().lutgen_cuda_generate_lut_png(remapper._h, level, _ptr(out), out.size, C.byref(n), _abort_ptr(abort)))
+        return None if aborted else out[:n.value].tobytes()
