@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(FILTER_WARPS * 32) k_png_choose_filters(lpng::
     if (lane == 0) filters[y] = (uint8_t)lpng::pick_filter(cost);
 }
 
-__global__ void __launch_bounds__(lpng::THREADS, 4)
+__global__ void __launch_bounds__(lpng::THREADS, 5)
     k_png_deflate(lpng::Image im, const lpng::Tables* tables, uint32_t nchunks, uint32_t* slots, lpng::ChunkMeta* meta) {
     extern __shared__ uint4 png_smem[];
     lpng::Shared& S = *reinterpret_cast<lpng::Shared*>(png_smem);

@@ -268,29 +268,40 @@ struct ChunkMeta {
     uint32_t m;        // stream bytes in the piece
 };
 
-// CTA-shared state of one piece.
+// CTA-shared state of one piece. 45.6 KB: five CTAs per SM (5 x (45.6 + 1) KB of the SM's 228 KB).
 struct Shared {
     uint32_t f[F_BYTES / 4];   // filtered stream bytes, padded layout (pad())
-    uint32_t out[OUT_WORDS];   // compressed piece, LSB-first bit stream
-    uint32_t hist[NSYM];
-    uint32_t node_freq[2 * NSYM];
-    uint16_t node_parent[2 * NSYM];
-    uint16_t used[NSYM];       // used symbols, any order
-    uint16_t order[NSYM];      // used symbols by ascending (frequency, symbol)
+    uint32_t out[OUT_WORDS];   // compressed piece, LSB-first bit stream; before that: histogram copies and Scratch
+    union {
+        uint32_t hist[NSYM];     // symbol frequencies, until the code lengths are known
+        uint32_t codelen[NSYM];  // then: canonical code, bit reversed (ready for the LSB-first stream) | length << 16
+    };
     uint32_t next_code[MAX_BITS + 1];  // first canonical code of each length
-    uint32_t codelen[NSYM];    // canonical code, bit reversed (ready for the LSB-first stream) | length << 16
     uint8_t len[NSYM];
     unsigned long long eq[THREADS];  // bit k: stream byte lo+k equals the byte bpp before it
     unsigned long long ev[THREADS];  // bit k: a token starts at stream byte lo+k
     unsigned long long ms[THREADS];  // ... and that token is a match
-    int sa[THREADS], sb[THREADS], ta[THREADS], tb[THREADS];  // run-boundary scans (kept until the last sweep)
+    int sa[THREADS], sb[THREADS];    // run-boundary scans (kept until the last sweep)
     int bits[THREADS];               // Adler partial sums (b); later token bits per thread and their inclusive prefix sums
     uint32_t crc[THREADS];           // Adler partial sums (a); later scan scratch, then CRC partial states
-    uint32_t crc_table[256];
     uint32_t nused;
     int nlit, stored, n_out;
     uint32_t header_bits, data_bits, chunk_a, chunk_b;
 };
+
+// What is only needed before the bit stream is written lives in the upper part of the output buffer
+// (the histogram copies take the lower part); the buffer is cleared again before emission.
+struct Scratch {
+    int ta[THREADS], tb[THREADS];   // scan double buffers
+    uint32_t node_freq[2 * NSYM];   // Huffman tree: frequencies, then depths
+    uint16_t node_parent[2 * NSYM];
+    uint16_t used[NSYM];            // used symbols, any order
+    uint16_t order[NSYM];           // used symbols by ascending (frequency, symbol)
+};
+static_assert(sizeof(uint32_t) * HIST_REPLICAS * HIST_PITCH + sizeof(Scratch) <= OUT_BYTES, "histogram copies + scratch must fit in the output buffer");
+static_assert(sizeof(Shared) <= 45670, "five CTAs per SM");
+
+LPNG_HD Scratch& scratch(Shared& S) { return *reinterpret_cast<Scratch*>(S.out + HIST_REPLICAS * HIST_PITCH); }
 
 // out |= v << bitpos (v at most 32 bits wide)
 LPNG_HD void or_bits(uint32_t* out, uint32_t bitpos, uint32_t v) {
@@ -466,6 +477,30 @@ LPNG_HD int match_length(const Shared& S, int t, int m, int k) {
     return left < MAX_MATCH ? left : MAX_MATCH;
 }
 
+// The same tokens with all literals first and all matches after them: for the sinks that do not care about
+// order (histogram, bit count) this keeps each loop body uniform across the lanes of a warp.
+template <class Sink>
+LPNG_HD void sweep_unordered(const Shared& S, int t, int m, Sink& sink) {
+    const uint8_t* seg = reinterpret_cast<const uint8_t*>(S.f) + pad(t * SEG);
+    const unsigned long long ev = S.ev[t], ms = S.ms[t];
+    for (int h = 0; h < 2; ++h) {
+        uint32_t e = (uint32_t)((ev & ~ms) >> (32 * h));
+        while (e) {
+            const int k = ctz32(e);
+            e &= e - 1u;
+            sink.lit(seg[k + 32 * h]);
+        }
+    }
+    for (int h = 0; h < 2; ++h) {
+        uint32_t e = (uint32_t)(ms >> (32 * h));
+        while (e) {
+            const int k = ctz32(e);
+            e &= e - 1u;
+            sink.match(match_length(S, t, m, k + 32 * h));
+        }
+    }
+}
+
 template <class Sink>
 LPNG_HD void sweep(const Shared& S, int t, int m, Sink& sink) {
     const uint8_t* seg = reinterpret_cast<const uint8_t*>(S.f) + pad(t * SEG);  // a thread's 64 bytes are contiguous
@@ -484,56 +519,59 @@ LPNG_HD void sweep(const Shared& S, int t, int m, Sink& sink) {
     }
 }
 
-// Used symbols, in any order, into S.used (S.nused and S.nlit start at 0 / 257).
+// Used symbols, in any order, into X.used (S.nused and S.nlit start at 0 / 257).
 LPNG_HD void collect_symbols(Shared& S, int t) {
+    Scratch& X = scratch(S);
     for (int s = t; s < NLITLEN; s += THREADS)
         if (S.hist[s]) {
-            S.used[atomic_inc(&S.nused)] = (uint16_t)s;
+            X.used[atomic_inc(&S.nused)] = (uint16_t)s;
             if (s >= 257) atomic_max(&S.nlit, s + 1);
         }
 }
 
-// S.order = used symbols by ascending (frequency, symbol): thread t places the t-th used symbol by
+// X.order = used symbols by ascending (frequency, symbol): thread t places the t-th used symbol by
 // counting the used symbols that come before it.
 LPNG_HD void rank_symbols(Shared& S, int t) {
+    Scratch& X = scratch(S);
     const int n = (int)S.nused;
     for (int i = t; i < n; i += THREADS) {
-        const int s = S.used[i];
+        const int s = X.used[i];
         const uint32_t f = S.hist[s];
         int r = 0;
         for (int j = 0; j < n; ++j) {
-            const int u = S.used[j];
+            const int u = X.used[j];
             const uint32_t fu = S.hist[u];
             r += (fu < f || (fu == f && u < s)) ? 1 : 0;
         }
-        S.order[r] = (uint16_t)s;
+        X.order[r] = (uint16_t)s;
     }
 }
 
 // Code lengths (at most MAX_BITS) from S.hist and the first canonical code of every length; one thread.
-// Huffman's algorithm with two queues over the frequency-sorted symbols (S.order), depths read off the
+// Huffman's algorithm with two queues over the frequency-sorted symbols (X.order), depths read off the
 // parent links, over-long codes folded into MAX_BITS and the Kraft sum repaired by demoting shorter
 // codes, lengths then handed out again in frequency order.
 LPNG_HDN void build_code(Shared& S) {
+    Scratch& X = scratch(S);
     const int n = (int)S.nused;
-    for (int i = 0; i < n; ++i) S.node_freq[i] = S.hist[S.order[i]];
+    for (int i = 0; i < n; ++i) X.node_freq[i] = S.hist[X.order[i]];
     int li = 0, ii = n, nn = n;
     while (nn < 2 * n - 1) {
         int a, b;
-        if (li < n && (ii >= nn || S.node_freq[li] <= S.node_freq[ii])) a = li++; else a = ii++;
-        if (li < n && (ii >= nn || S.node_freq[li] <= S.node_freq[ii])) b = li++; else b = ii++;
-        S.node_freq[nn] = S.node_freq[a] + S.node_freq[b];
-        S.node_parent[a] = (uint16_t)nn;
-        S.node_parent[b] = (uint16_t)nn;
+        if (li < n && (ii >= nn || X.node_freq[li] <= X.node_freq[ii])) a = li++; else a = ii++;
+        if (li < n && (ii >= nn || X.node_freq[li] <= X.node_freq[ii])) b = li++; else b = ii++;
+        X.node_freq[nn] = X.node_freq[a] + X.node_freq[b];
+        X.node_parent[a] = (uint16_t)nn;
+        X.node_parent[b] = (uint16_t)nn;
         ++nn;
     }
     // depths, root first (parents have larger indices than their children); node_freq is reused
     uint32_t cnt[MAX_BITS + 2];
     for (int i = 0; i <= MAX_BITS + 1; ++i) cnt[i] = 0;
-    S.node_freq[2 * n - 2] = 0;
+    X.node_freq[2 * n - 2] = 0;
     for (int i = 2 * n - 3; i >= 0; --i) {
-        uint32_t d = S.node_freq[S.node_parent[i]] + 1;
-        S.node_freq[i] = d;
+        uint32_t d = X.node_freq[X.node_parent[i]] + 1;
+        X.node_freq[i] = d;
         if (i < n) ++cnt[d > MAX_BITS ? MAX_BITS : d];
     }
     uint32_t total = 0;
@@ -550,7 +588,7 @@ LPNG_HDN void build_code(Shared& S) {
     }
     int i = n - 1;  // most frequent symbol first, shortest length first
     for (int l = 1; l <= MAX_BITS; ++l)
-        for (uint32_t c = 0; c < cnt[l]; ++c) S.len[S.order[i--]] = (uint8_t)l;
+        for (uint32_t c = 0; c < cnt[l]; ++c) S.len[X.order[i--]] = (uint8_t)l;
     uint32_t code = 0;
     cnt[0] = 0;
     S.next_code[0] = 0;
@@ -562,13 +600,14 @@ LPNG_HDN void build_code(Shared& S) {
 
 // Canonical codes: within one length, codes ascend with the symbol. Thread t places the t-th used symbol.
 LPNG_HD void assign_codes(Shared& S, int t) {
+    Scratch& X = scratch(S);
     const int n = (int)S.nused;
     for (int i = t; i < n; i += THREADS) {
-        const int s = S.used[i];
+        const int s = X.used[i];
         const int l = S.len[s];
         uint32_t before = 0;
         for (int j = 0; j < n; ++j) {
-            const int u = S.used[j];
+            const int u = X.used[j];
             before += (S.len[u] == l && u < s) ? 1u : 0u;
         }
         S.codelen[s] = bit_reverse(S.next_code[l] + before, l) | ((uint32_t)l << 16);
@@ -588,6 +627,7 @@ LPNG_HDN void encode_chunk(Exec& ex, Shared& S, const Image& im, const Tables& T
     const bool final_chunk = chunk + 1 == nchunks;
     const uint32_t base_bits = chunk == 0 ? 16u : 0u;  // the zlib header rides in front of the first piece
     uint8_t* fb = reinterpret_cast<uint8_t*>(S.f);
+    Scratch& X = scratch(S);
     const int dsym = bpp - 1;                // distance symbol of distance bpp (1..4 -> 0..3)
     const int dother = dsym == 0 ? 1 : 0;    // second distance code, so that the distance code is complete
     const int ndist = dsym + 1 > 2 ? dsym + 1 : 2;
@@ -600,7 +640,6 @@ LPNG_HDN void encode_chunk(Exec& ex, Shared& S, const Image& im, const Tables& T
             S.nused = 0;
             S.nlit = 257;
         }
-        S.crc_table[t] = T.crc[t];
         // row by row (filter type, row pointers and bounds are then the same for the whole CTA)
         const uint32_t stride = im.rb + 1;
         uint32_t y = (uint32_t)(c0 / stride);
@@ -631,12 +670,33 @@ LPNG_HDN void encode_chunk(Exec& ex, Shared& S, const Image& im, const Tables& T
         n = n < 0 ? 0 : (n > SEG ? SEG : n);
         unsigned long long eq = 0;
         uint32_t A = 0, B = 0;
-        for (int k = 0; k < n; ++k) {
-            int pos = lo + k;
-            uint32_t v = fb[pad(pos)];
-            if (pos >= bpp && v == fb[pad(pos - bpp)]) eq |= 1ull << k;
-            A += v;
-            B += (uint32_t)(n - k) * v;
+        if (n == SEG) {
+            // a full segment, four bytes at a time (little endian: byte k of the segment is byte k & 3 of word k >> 2)
+            const uint32_t* w = S.f + (SEG / 4 + 1) * t;
+            uint32_t prev = t > 0 ? w[-2] : 0u;  // stream bytes lo-4 .. lo-1 (the word before is the pad word)
+            const int sh = 8 * bpp;
+            for (int j = 0; j < SEG / 4; ++j) {
+                const uint32_t x = w[j];
+                const uint32_t y = bpp == 4 ? prev : ((prev >> (32 - sh)) | (x << sh));  // the bytes bpp before
+                const uint32_t z = x ^ y;
+                uint32_t zero = ~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z | 0x7F7F7F7Fu) >> 7;  // bit 8i set: byte i of z is zero
+                zero = (zero | (zero >> 7) | (zero >> 14) | (zero >> 21)) & 15u;
+                eq |= (unsigned long long)zero << (4 * j);
+                const uint32_t pair = (x & 0x00FF00FFu) + ((x >> 8) & 0x00FF00FFu);
+                const uint32_t sum = (pair & 0xFFFFu) + (pair >> 16);
+                A += sum;
+                B += (uint32_t)(SEG - 4 * j) * sum - (((x >> 8) & 255u) + 2u * ((x >> 16) & 255u) + 3u * (x >> 24));
+                prev = x;
+            }
+            if (t == 0) eq &= ~((1ull << bpp) - 1ull);  // nothing lies bpp before the first bytes of the piece
+        } else {
+            for (int k = 0; k < n; ++k) {
+                int pos = lo + k;
+                uint32_t v = fb[pad(pos)];
+                if (pos >= bpp && v == fb[pad(pos - bpp)]) eq |= 1ull << k;
+                A += v;
+                B += (uint32_t)(n - k) * v;
+            }
         }
         S.eq[t] = eq;
         const unsigned long long valid = n == 64 ? ~0ull : ((1ull << n) - 1ull);
@@ -652,12 +712,12 @@ LPNG_HDN void encode_chunk(Exec& ex, Shared& S, const Image& im, const Tables& T
             int a = S.sa[t], b = S.sb[t];
             if (t - d >= 0 && S.sa[t - d] > a) a = S.sa[t - d];
             if (t + d < THREADS && S.sb[t + d] < b) b = S.sb[t + d];
-            S.ta[t] = a;
-            S.tb[t] = b;
+            X.ta[t] = a;
+            X.tb[t] = b;
         });
         ex.par([&](int t) {
-            S.sa[t] = S.ta[t];
-            S.sb[t] = S.tb[t];
+            S.sa[t] = X.ta[t];
+            S.sb[t] = X.tb[t];
         });
     }
 
@@ -665,7 +725,7 @@ LPNG_HDN void encode_chunk(Exec& ex, Shared& S, const Image& im, const Tables& T
     ex.par([&](int t) {
         classify(S, t, m);
         HistSink h{S.out + (t % HIST_REPLICAS) * HIST_PITCH};
-        sweep(S, t, m, h);
+        sweep_unordered(S, t, m, h);
     });
     ex.par([&](int t) {
         for (int s = t; s < NSYM; s += THREADS) {
@@ -697,9 +757,9 @@ LPNG_HDN void encode_chunk(Exec& ex, Shared& S, const Image& im, const Tables& T
     // 6. bits per thread, prefix sums
     ex.par([&](int t) {
         CountSink c{S.len, 0u};
-        sweep(S, t, m, c);
+        sweep_unordered(S, t, m, c);
         S.bits[t] = (int)c.bits;
-        for (int w = t; w < HIST_REPLICAS * HIST_PITCH; w += THREADS) S.out[w] = 0;  // the output buffer again
+        for (int w = t; w < OUT_WORDS; w += THREADS) S.out[w] = 0;  // histogram copies and scratch are done with: the output buffer again
     });
     for (int d = 1; d < THREADS; d <<= 1) {
         ex.par([&](int t) { S.crc[t] = (uint32_t)(S.bits[t] + (t - d >= 0 ? S.bits[t - d] : 0)); });
@@ -773,7 +833,7 @@ LPNG_HDN void encode_chunk(Exec& ex, Shared& S, const Image& im, const Tables& T
         uint32_t s = 0;
         for (int p = lo; p < hi; ++p) {
             uint32_t byte = p < 4 ? (uint32_t)(uint8_t)~"IDAT"[p] : ob[p - 4];
-            s = S.crc_table[(s ^ byte) & 255u] ^ (s >> 8);
+            s = T.crc[(s ^ byte) & 255u] ^ (s >> 8);
         }
         S.crc[t] = s;
     });
