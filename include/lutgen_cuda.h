@@ -242,6 +242,13 @@ LUTGEN_API int lutgen_cuda_encode_png_dev(const uint8_t* pixels_dev, uint32_t wi
 LUTGEN_API int lutgen_cuda_generate_lut_png(const lutgen_remapper* r, uint8_t level, uint8_t* out, size_t capacity,
                                             size_t* out_len, const volatile uint8_t* abort_flag);
 
+/* identity::correct_image followed by `image.save(path)` (crates/cli/src/main.rs:852-871, what `lutgen apply`
+ * does with a still image): the frame is uploaded once, corrected and encoded on the device, and only the PNG
+ * bytes come back (an RGBA PNG, alpha as it went in). `rgba` is not modified. *out_len / `capacity` as in
+ * lutgen_cuda_encode_png (bound: lutgen_cuda_png_bound(width, height, 4)). */
+LUTGEN_API int lutgen_cuda_apply_hald_png(const uint8_t* rgba, uint32_t width, uint32_t height, const uint8_t* lut_rgb,
+                                          uint8_t level, uint8_t* out, size_t capacity, size_t* out_len);
+
 /* ---- oklab (third-party arithmetic on the path; oklab 1.1.2) --------------- */
 
 /* oklab::srgb_to_oklab for n colours: in n x [u8;3], out n x [f32;3] (l, a, b). */

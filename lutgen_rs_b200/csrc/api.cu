@@ -1535,6 +1535,33 @@ int lutgen_cuda_generate_lut_png(const lutgen_remapper* r, uint8_t level, uint8_
     return LUTGEN_OK;
 }
 
+int lutgen_cuda_apply_hald_png(const uint8_t* rgba, uint32_t width, uint32_t height, const uint8_t* lut_rgb, uint8_t level, uint8_t* out,
+                               size_t capacity, size_t* out_len) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33", level);
+    if (!rgba || !lut_rgb || !out || !out_len) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    rc = png_args_ok(width, height, 4);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g.mu);
+    const size_t npix = (size_t)width * height, lut_bytes = 3 * lut_entries(level);
+    CU_TRY(g.lut_rgb.reserve(lut_bytes));
+    CU_TRY(g.frame.reserve(npix * 4));
+    CU_TRY(g.png_out.reserve((size_t)png_bound(width, height, 4)));
+    CU_TRY(cudaMemcpyAsync(g.lut_rgb.p, lut_rgb, lut_bytes, cudaMemcpyHostToDevice, g.stream));
+    CU_TRY(cudaMemcpyAsync(g.frame.p, rgba, npix * 4, cudaMemcpyHostToDevice, g.stream));
+    rc = lutgen_cuda_apply_hald_dev((uint8_t*)g.frame.p, npix, (const uint8_t*)g.lut_rgb.p, level, g.stream);
+    if (rc) return rc;
+    size_t total = 0;
+    rc = png_encode_locked((const uint8_t*)g.frame.p, width, height, 4, (uint8_t*)g.png_out.p, &total, g.stream);
+    if (rc) return rc;
+    *out_len = total;
+    if (total > capacity) return fail(LUTGEN_ERR_INVALID, "the PNG is %zu bytes, the buffer holds %zu", total, capacity);
+    CU_TRY(cudaMemcpyAsync(out, g.png_out.p, total, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    return LUTGEN_OK;
+}
+
 int lutgen_cuda_remap_image_dev(const lutgen_remapper* r, uint8_t* rgba_dev, size_t npix, void* stream) {
     int rc = ensure_ready();
     if (rc) return rc;

@@ -80,3 +80,23 @@ def generate_lut_png(remapper, level, abort=None):
         out = _staging(bound(side, side, 3))
         aborted = _native.check(_native.lib().lutgen_cuda_generate_lut_png(remapper._h, level, _ptr(out), out.size, C.byref(n), _abort_ptr(abort)))
         return None if aborted else out[:n.value].tobytes()
+
+
+def correct_image_png(image, hald_clut, level=None):
+    """`identity::correct_image(&mut image, &lut)` followed by `image.save(path)` (what `lutgen apply` does with a
+    still image, crates/cli/src/main.rs:852-871) with the frame staying on the device in between: returns the PNG
+    bytes of the corrected (h, w, 4) uint8 image; `image` itself is left as it is."""
+    from .identity import _as_lut, _check_rgba, detect_level
+    lut = _as_lut(hald_clut)
+    if level is None:
+        level = detect_level(lut)
+    _check_rgba(image)
+    if image.ndim != 3:
+        raise TypeError("image must have shape (h, w, 4)")
+    a = np.ascontiguousarray(image)
+    h, w = a.shape[0], a.shape[1]
+    n = C.c_size_t(0)
+    with _stage_lock:
+        out = _staging(bound(w, h, 4))
+        _native.check(_native.lib().lutgen_cuda_apply_hald_png(_ptr(a), w, h, _ptr(lut), int(level), _ptr(out), out.size, C.byref(n)))
+        return out[:n.value].tobytes()

@@ -108,6 +108,24 @@ def test_png_level16_clut_and_4k_frame(palettes):
     assert len(data) < 0.7 * frame.size
 
 
+def test_correct_image_png_is_correct_then_encode(palettes):
+    """`lutgen apply` on a still image (crates/cli/src/main.rs:852-871): correct_image + save, fused."""
+    from lutgen_rs_b200 import identity
+    lut = interpolation.GaussianRemapper(palettes["catppuccin_mocha"], 128.0, 16, 1.0, False).par_generate_lut(8)
+    rng = np.random.default_rng(12)
+    img = rng.integers(0, 256, (123, 457, 4), dtype=np.uint8)
+    before = img.copy()
+    data = png.correct_image_png(img, lut)
+    assert (img == before).all()
+    want = O.correct_image(before, lut, 8)
+    assert (_pil(data) == want).all()
+    corrected = before.copy()
+    identity.correct_image(corrected, lut)
+    assert data == png.encode(corrected)
+    with pytest.raises(lg.LutgenPanic):
+        png.correct_image_png(img, lut[:100])
+
+
 def test_png_device_entry_point(palettes):
     import torch
     from lutgen_rs_b200 import device
