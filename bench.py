@@ -549,6 +549,15 @@ def run_b200(args):
             data = lpng.generate_lut_png(rm, 16)
             ts.append((time.perf_counter() - t0) * 1e3)
         other_configs["generate_lut_png_level16_host_to_host_ms"] = round(float(np.median(ts[1:])), 2)
+        # `lutgen apply` on a still image: upload a 4K RGBA frame, correct it with the level-8 CLUT, download its PNG
+        frame_host = pristine_photo[0].cpu().numpy().reshape(FRAME_H, FRAME_W, 4)
+        ts = []
+        for i in range(4):
+            t0 = time.perf_counter()
+            fdata = lpng.correct_image_png(frame_host, lut8_host, LEVEL_APPLY)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        other_configs["correct_image_png_4k_frame_host_to_host_ms"] = round(float(np.median(ts[1:])), 2)
+        other_configs["correct_image_png_4k_frame_bytes"] = len(fdata)
         if not args.no_cpu:
             try:
                 import io
@@ -564,7 +573,8 @@ def run_b200(args):
             except ImportError:
                 pass
         other_configs["png_what"] = ("PNG file bytes of the level-16 headline CLUT: device resident (L2 flushed), then generate + encode + "
-                                     "download through lutgen_cuda_generate_lut_png into a page-locked buffer, copied into a Python bytes object; cpu_* = PIL (zlib level 1, one "
+                                     "download through lutgen_cuda_generate_lut_png into a page-locked buffer, copied into a Python bytes object; "
+                                     "correct_image_png_* = a photo-like 4K RGBA frame from pageable host memory through lutgen_cuda_apply_hald_png; cpu_* = PIL (zlib level 1, one "
                                      "thread) on the same CLUT, checked to decode to the same pixels -- the reference's `image` crate "
                                      "encoder cannot run here")
     top, other, other_key = (gen_line, apply_line, "apply") if args.workload == "generate" else (apply_line, gen_line, "generate")

@@ -5,6 +5,9 @@ that is tests/; this only gives memcheck / racecheck / initcheck something to lo
 
     compute-sanitizer --tool memcheck  python tools/sanitize.py
     compute-sanitizer --tool racecheck python tools/sanitize.py
+
+(The GPU pool this round ran on has compute-sanitizer closed -- gpurun answers "closed on this pool" -- so the
+driver has only been run bare there; it is kept for a box where the tool is available.)
 """
 import json
 import os
@@ -17,7 +20,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from conftest import synthetic_palette  # noqa: E402
-from lutgen_rs_b200 import _native, identity, interpolation  # noqa: E402
+from lutgen_rs_b200 import _native, identity, interpolation, png  # noqa: E402
 
 
 def main():
@@ -58,6 +61,12 @@ def main():
     b.par_generate_lut(6)
     b.generate_lut(5)
     interpolation.GaussianBlurRemapper(pal, 8.0, 0.7, True).par_generate_lut(4)
+    # PNG writer: dynamic-Huffman pieces (CLUT), stored pieces (noise), several pieces, grey and RGBA
+    png.encode(lut)
+    png.encode(img)
+    png.encode(np.zeros((3, 9000, 1), np.uint8))
+    png.generate_lut_png(interpolation.NearestNeighborRemapper(pal, 1.0, False), 6)
+    png.correct_image_png(img, lut)
     print(f"sanitize driver done: {_native.launch_count() - before} kernel launches")
 
 
