@@ -274,7 +274,7 @@ struct Shared {
     uint32_t out[OUT_WORDS];   // compressed piece, LSB-first bit stream; before that: histogram copies and Scratch
     union {
         uint32_t hist[NSYM];     // symbol frequencies, until the code lengths are known
-        uint32_t codelen[NSYM];  // then: canonical code, bit reversed (ready for the LSB-first stream) | length << 16
+        uint32_t codelen[NSYM];  // then: canonical code, bit reversed (ready for the LSB-first stream) | length << 16 | header position << 20
     };
     uint32_t next_code[MAX_BITS + 1];  // first canonical code of each length
     uint8_t len[NSYM];
@@ -366,12 +366,12 @@ struct EmitSink {
     }
     LPNG_HD void lit(int b) {
         const uint32_t cl = codelen[b];
-        put(cl & 0xFFFFu, (int)(cl >> 16));
+        put(cl & 0xFFFFu, (int)((cl >> 16) & 15u));
     }
     LPNG_HD void match(int l) {  // length code, its extra bits and the one-bit distance code in one go (at most 21 bits)
         int eb, ex;
         const uint32_t cl = codelen[length_symbol(l, eb, ex)];
-        const int n0 = (int)(cl >> 16);
+        const int n0 = (int)((cl >> 16) & 15u);
         put((cl & 0xFFFFu) | ((uint32_t)ex << n0) | (dist_bit << (n0 + eb)), n0 + eb + 1);
     }
 };
@@ -598,6 +598,12 @@ LPNG_HDN void build_code(Shared& S) {
     }
 }
 
+// The block header (RFC 1951, 3.2.7) uses one fixed code for the code lengths: length 0 costs one bit, lengths
+// 1..15 (and the unused zero-run symbol 18, which completes the code) five bits; symbols 16 and 17 are left out.
+// Canonical codes of that code: 0 -> "0", L -> 15 + L in five bits. Most of the 257+ lengths are 0, so a header
+// is about 70 bytes instead of the 150 a flat four-bit code would take.
+constexpr uint32_t HEADER_FIXED_BITS = 17u + 19u * 3u;  // BFINAL, BTYPE, HLIT, HDIST, HCLEN, then 19 three-bit lengths
+
 // Canonical codes: within one length, codes ascend with the symbol. Thread t places the t-th used symbol.
 LPNG_HD void assign_codes(Shared& S, int t) {
     Scratch& X = scratch(S);
@@ -605,12 +611,15 @@ LPNG_HD void assign_codes(Shared& S, int t) {
     for (int i = t; i < n; i += THREADS) {
         const int s = X.used[i];
         const int l = S.len[s];
-        uint32_t before = 0;
+        uint32_t before = 0, below = 0;
         for (int j = 0; j < n; ++j) {
             const int u = X.used[j];
             before += (S.len[u] == l && u < s) ? 1u : 0u;
+            below += u < s ? 1u : 0u;
         }
-        S.codelen[s] = bit_reverse(S.next_code[l] + before, l) | ((uint32_t)l << 16);
+        // where the symbol's code length goes in the block header: one bit per unused symbol before it, five per used one
+        const uint32_t hpos = HEADER_FIXED_BITS + (uint32_t)s + 4u * below;
+        S.codelen[s] = bit_reverse(S.next_code[l] + before, l) | ((uint32_t)l << 16) | (hpos << 20);
     }
 }
 
@@ -768,7 +777,7 @@ LPNG_HDN void encode_chunk(Exec& ex, Shared& S, const Image& im, const Tables& T
     // 7. dynamic block or stored block, whichever is shorter
     ex.par([&](int t) {
         if (t != 0) return;
-        S.header_bits = 17u + 57u + 4u * (uint32_t)(S.nlit + ndist);
+        S.header_bits = HEADER_FIXED_BITS + (uint32_t)(S.nlit + ndist) + 4u * (S.nused + 2u);
         S.data_bits = (uint32_t)S.bits[THREADS - 1];
         uint32_t end = base_bits + S.header_bits + S.data_bits + S.len[EOB];
         uint32_t n_dyn = final_chunk ? (end + 7u) / 8u : (end + 3u + 7u) / 8u + 4u;
@@ -800,8 +809,10 @@ LPNG_HDN void encode_chunk(Exec& ex, Shared& S, const Image& im, const Tables& T
             if (chunk == 0) or_bits(S.out, 0, 0x0178u);
             uint32_t h17 = (final_chunk ? 1u : 0u) | (2u << 1) | ((uint32_t)(S.nlit - 257) << 3) | ((uint32_t)(ndist - 1) << 8) | (15u << 13);
             or_bits(S.out, hdr, h17);
-            // code-length code: symbols 16, 17, 18 unused, lengths 0..15 all four bits (a complete code)
-            for (int j = 0; j < 16; ++j) or_bits(S.out, hdr + 17u + 9u + 3u * (uint32_t)j, 4u);
+            // lengths of the code-length code in the order 16, 17, 18, 0, 8, 7, ...: 0, 0, 5, 1, then 5 for 1..15
+            or_bits(S.out, hdr + 17u + 6u, 5u);
+            or_bits(S.out, hdr + 17u + 9u, 1u);
+            for (int j = 4; j < 19; ++j) or_bits(S.out, hdr + 17u + 3u * (uint32_t)j, 5u);
             // end of block, then (unless this is the last piece) an empty stored block to reach a byte boundary
             uint32_t eob = hdr + S.header_bits + S.data_bits;
             or_bits(S.out, eob, S.codelen[EOB] & 0xFFFFu);
@@ -810,9 +821,13 @@ LPNG_HDN void encode_chunk(Exec& ex, Shared& S, const Image& im, const Tables& T
                 or_bits(S.out, 8u * (bs + 2u), 0xFFFFu);
             }
         }
-        for (int q = t; q < S.nlit + ndist; q += THREADS) {
-            int l = q < S.nlit ? S.len[q] : ((q - S.nlit == dsym || q - S.nlit == dother) ? 1 : 0);
-            or_bits(S.out, hdr + 74u + 4u * (uint32_t)q, bit_reverse((uint32_t)l, 4));
+        for (int q = t; q < S.nlit; q += THREADS)  // used literal/length symbols: their lengths (unused ones are single 0 bits)
+            if (S.len[q]) or_bits(S.out, hdr + (S.codelen[q] >> 20), bit_reverse(15u + S.len[q], 5));
+        if (t == 0) {  // the two distance codes of length 1
+            const uint32_t dbase = hdr + HEADER_FIXED_BITS + (uint32_t)S.nlit + 4u * S.nused;
+            const int d0 = dsym < dother ? dsym : dother, d1 = dsym < dother ? dother : dsym;
+            or_bits(S.out, dbase + (uint32_t)d0, bit_reverse(16u, 5));
+            or_bits(S.out, dbase + (uint32_t)d1 + 4u, bit_reverse(16u, 5));
         }
         EmitSink e;
         e.out = S.out;
