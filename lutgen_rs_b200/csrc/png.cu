@@ -2,13 +2,14 @@
 // (replaces the `image` crate's PNG writer behind `lut.save(path)` /
 // `image.save(path)`, crates/cli/src/main.rs:767, 811, 839, 862).
 //
-//   k_png_choose_filters  one warp per scanline: the five filters' absolute residual sums, the smallest wins
+//   k_png_choose_filters  four warps per scanline: the five filters' absolute residual sums, the smallest wins
 //   k_png_deflate         one CTA per 16 KB piece of the filtered stream: filter, run detection, histogram,
 //                         Huffman code, bit stream, CRC-32 and Adler-32 parts, all in shared memory
 //   k_png_layout          one CTA: prefix sums of the piece sizes, Adler-32 of the stream, fixed chunks
 //   k_png_place           one CTA per piece: its IDAT chunk copied to its place in the file
 #include "png_launch.h"
 
+#include <cstdlib>
 #include <mutex>
 
 #include "png_core.h"
@@ -28,19 +29,42 @@ struct CtaExec {
     }
 };
 
-constexpr int FILTER_WARPS = 8;
+constexpr int FILTER_WARPS = 8;  // warps per CTA
 
+// SPLIT warps share one scanline (one warp per 12 KB row does not keep enough loads in flight to fill the SM).
+template <int SPLIT>
 __global__ void __launch_bounds__(FILTER_WARPS * 32) k_png_choose_filters(lpng::Image im, uint8_t* filters) {
-    const uint32_t y = blockIdx.x * FILTER_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
-    if (y >= im.height) return;
+    constexpr int ROWS = FILTER_WARPS / SPLIT;
+    __shared__ uint32_t part[FILTER_WARPS][5];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t y = blockIdx.x * ROWS + warp / SPLIT, piece = warp % SPLIT;
     uint32_t cost[5] = {0u, 0u, 0u, 0u, 0u};
-    const uint8_t* row = im.px + (size_t)y * im.rb;
-    lpng::row_costs(row, y > 0 ? row - im.rb : nullptr, im.rb, im.bpp, lane, 32u, cost);
+    if (y < im.height) {
+        const uint8_t* row = im.px + (size_t)y * im.rb;
+        lpng::row_costs(row, y > 0 ? row - im.rb : nullptr, im.rb, im.bpp, piece * 32u + lane, 32u * SPLIT, cost);
+    }
 #pragma unroll
-    for (int ft = 0; ft < 5; ++ft)
+    for (int ft = 0; ft < 5; ++ft) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) cost[ft] += __shfl_xor_sync(0xFFFFFFFFu, cost[ft], d);
-    if (lane == 0) filters[y] = (uint8_t)lpng::pick_filter(cost);
+        if (lane == 0) part[warp][ft] = cost[ft];
+    }
+    __syncthreads();
+    if (piece == 0 && lane == 0 && y < im.height) {
+        uint32_t total[5];
+#pragma unroll
+        for (int ft = 0; ft < 5; ++ft) {
+            total[ft] = 0;
+            for (int p = 0; p < SPLIT; ++p) total[ft] += part[warp + p][ft];
+        }
+        filters[y] = (uint8_t)lpng::pick_filter(total);
+    }
+}
+
+template <int SPLIT>
+void launch_choose_filters(const lpng::Image& im, uint8_t* filters, cudaStream_t s) {
+    constexpr int ROWS = FILTER_WARPS / SPLIT;
+    k_png_choose_filters<SPLIT><<<(im.height + ROWS - 1) / ROWS, FILTER_WARPS * 32, 0, s>>>(im, filters);
 }
 
 __global__ void __launch_bounds__(lpng::THREADS, 5)
@@ -131,7 +155,15 @@ cudaError_t png_encode_async(const uint8_t* pixels_dev, uint32_t width, uint32_t
     unsigned long long* offsets = reinterpret_cast<unsigned long long*>(base + L.offsets);
     uint32_t* slots = reinterpret_cast<uint32_t*>(base + L.slots);
     lpng::Image im{pixels_dev, filters, width, height, bpp, width * bpp, (unsigned long long)height * ((unsigned long long)width * bpp + 1ull)};
-    k_png_choose_filters<<<(height + FILTER_WARPS - 1) / FILTER_WARPS, FILTER_WARPS * 32, 0, s>>>(im, filters);
+    // warps per scanline: LUTGEN_CUDA_PNG_SPLIT (1, 2, 4, 8) overrides the default, for measurements
+    int split = 4;
+    if (const char* e = std::getenv("LUTGEN_CUDA_PNG_SPLIT")) split = std::atoi(e);
+    switch (split) {
+        case 1: launch_choose_filters<1>(im, filters, s); break;
+        case 2: launch_choose_filters<2>(im, filters, s); break;
+        case 8: launch_choose_filters<8>(im, filters, s); break;
+        default: launch_choose_filters<4>(im, filters, s); break;
+    }
     k_png_deflate<<<L.nchunks, lpng::THREADS, sizeof(lpng::Shared), s>>>(im, g_png_tables, L.nchunks, slots, meta);
     k_png_layout<<<1, lpng::THREADS, 0, s>>>(meta, L.nchunks, width, height, bpp, offsets, out_dev, total_dev);
     k_png_place<<<L.nchunks, lpng::THREADS, 0, s>>>(meta, slots, offsets, out_dev);

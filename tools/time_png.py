@@ -37,6 +37,12 @@ def main():
     ms, view = timed(lambda: device.encode_png_(lut, out))
     print(f"level-16 CLUT: {ms:.3f} ms per encode on the device, {view.numel()} bytes ({view.numel() / lut.numel():.3f} of raw), "
           f"{lut.numel() / ms / 1e6:.1f} GB/s of pixels")
+    ref = view.cpu().numpy().tobytes()
+    for split in ("1", "2", "4", "8"):
+        os.environ["LUTGEN_CUDA_PNG_SPLIT"] = split
+        ms, view = timed(lambda: device.encode_png_(lut, out), 6)
+        print(f"  LUTGEN_CUDA_PNG_SPLIT={split}: {ms:.3f} ms, same bytes: {view.cpu().numpy().tobytes() == ref}")
+    del os.environ["LUTGEN_CUDA_PNG_SPLIT"]
     t = time.perf_counter()
     data = png.generate_lut_png(r, 16)
     t1 = time.perf_counter() - t
