@@ -268,7 +268,9 @@ struct ChunkMeta {
     uint32_t m;        // stream bytes in the piece
 };
 
-// CTA-shared state of one piece. 45.6 KB: five CTAs per SM (5 x (45.6 + 1) KB of the SM's 228 KB).
+// CTA-shared state of one piece: 45,600 bytes. (Five CTAs per SM need at most 45,568: each CTA's allocation is
+// this + 1 KB rounded up to 128 bytes, and 5 x 46,720 is 128 bytes more than the SM's 228 KB -- ncu reports a
+// limit of four. Moving 32 more bytes into Scratch would tip it; not done, not measured.)
 struct Shared {
     uint32_t f[F_BYTES / 4];   // filtered stream bytes, padded layout (pad())
     uint32_t out[OUT_WORDS];   // compressed piece, LSB-first bit stream; before that: histogram copies and Scratch
@@ -299,7 +301,7 @@ struct Scratch {
     uint16_t order[NSYM];           // used symbols by ascending (frequency, symbol)
 };
 static_assert(sizeof(uint32_t) * HIST_REPLICAS * HIST_PITCH + sizeof(Scratch) <= OUT_BYTES, "histogram copies + scratch must fit in the output buffer");
-static_assert(sizeof(Shared) <= 45670, "five CTAs per SM");
+static_assert(sizeof(Shared) <= 45670, "keep the shared state near the five-CTAs-per-SM size");
 
 LPNG_HD Scratch& scratch(Shared& S) { return *reinterpret_cast<Scratch*>(S.out + HIST_REPLICAS * HIST_PITCH); }
 

@@ -182,5 +182,5 @@ def test_deep_code_reaches_the_stream():
     _roundtrip(vals.reshape(1, -1, 1))
 
 
-def test_shared_state_fits_five_ctas_per_sm():
-    assert P.lib().lpng_sim_shared_bytes() <= 45670  # 5 x (this + 1 KB) <= 228 KB
+def test_shared_state_size():
+    assert P.lib().lpng_sim_shared_bytes() <= 45670  # four CTAs per SM today; 45,568 would allow five
