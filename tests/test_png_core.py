@@ -184,3 +184,52 @@ def test_deep_code_reaches_the_stream():
 
 def test_shared_state_size():
     assert P.lib().lpng_sim_shared_bytes() <= 45670  # four CTAs per SM today; 45,568 would allow five
+
+
+def test_random_images_round_trip():
+    """Seeded fuzz over geometry and content kinds (noise, few-valued, smooth, repeated rows, constant blocks)."""
+    rng = np.random.default_rng(20261019)
+    for trial in range(40):
+        c = int(rng.integers(1, 5))
+        h = int(rng.integers(1, 90))
+        w = int(rng.integers(1, 700))
+        kind = trial % 5
+        if kind == 0:
+            img = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+        elif kind == 1:
+            img = (rng.integers(0, 3, (h, w, c)) * rng.integers(1, 80)).astype(np.uint8)
+        elif kind == 2:
+            yy, xx = np.mgrid[0:h, 0:w]
+            img = np.stack([(xx * (k + 1) + yy * (3 - k)) // (k + 2) for k in range(c)], -1).astype(np.uint8)
+        elif kind == 3:
+            row = rng.integers(0, 256, (1, w, c), dtype=np.uint8)
+            img = np.repeat(row, h, axis=0)
+            img[rng.integers(0, h)] ^= 1
+        else:
+            img = np.zeros((h, w, c), np.uint8)
+            for _ in range(6):
+                y0, x0 = int(rng.integers(0, h)), int(rng.integers(0, w))
+                img[y0:y0 + int(rng.integers(1, 40)), x0:x0 + int(rng.integers(1, 300))] = rng.integers(0, 256, c)
+        data, filters, stored = P.encode(img)
+        assert (_pil(data) == img).all(), (trial, img.shape, kind)
+        if img.size < 40000:
+            dec, f2, _ = P.decode(data)
+            assert (dec == img).all() and (f2 == filters).all(), (trial, img.shape, kind)
+
+
+def test_python_mirror_checks_its_arguments_without_a_gpu():
+    """lutgen_rs_b200.png: what does not need the device (bounds, argument errors)."""
+    from lutgen_rs_b200 import png
+    assert png.bound(4096, 4096, 3) == P.lib().lpng_sim_bound(4096, 4096, 3)
+    assert png.bound(1, 1, 1) >= 8 + 25 + 12 + 2 + 5 + 2 + 16 + 12
+    with pytest.raises(TypeError):
+        png.encode(np.zeros((4, 4, 5), np.uint8))
+    with pytest.raises(TypeError):
+        png.encode(np.zeros((4, 4, 3), np.float32))
+    with pytest.raises(TypeError):
+        png.encode(np.zeros((2, 2, 2, 3), np.uint8))
+    import lutgen_rs_b200 as lg
+    with pytest.raises(lg.LutgenPanic):
+        png.bound(0, 4, 3)
+    with pytest.raises(lg.LutgenPanic):
+        png.bound(4, 4, 7)
