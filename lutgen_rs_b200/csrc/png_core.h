@@ -36,7 +36,7 @@ namespace lpng {
 constexpr int SEG = 64;                  // stream bytes tokenised by one thread
 constexpr int THREADS = 256;             // threads per CTA
 constexpr int CHUNK = SEG * THREADS;     // stream bytes per deflate block
-constexpr int MIN_RUN = 4;               // shortest run worth a match
+constexpr int MIN_RUN = 4;               // shortest run worth a match (classify() hard-wires it in its shifts)
 constexpr int MAX_MATCH = 258;
 constexpr int NLITLEN = 286;             // literal/length symbols in use
 constexpr int NSYM = 288;
@@ -437,6 +437,7 @@ LPNG_HD void classify(Shared& S, int t, int m) {
     const unsigned long long N3 = t + 1 < THREADS ? (S.eq[t + 1] & 7ull) : 0ull;
     // window: bit i <-> position lo - 3 + i, 70 bits in (wl, wh)
     unsigned long long wl = P3 | (E << 3), wh = (E >> 61) | (N3 << 3);
+    static_assert(MIN_RUN == 4, "the shifts below find runs of exactly four or more");
     // pairs, then fours: bit i set if positions i..i+3 are all in runs
     unsigned long long bl = wl & ((wl >> 1) | (wh << 63)), bh = wh & (wh >> 1);
     unsigned long long al = bl & ((bl >> 2) | (bh << 62)), ah = bh & (bh >> 2);
