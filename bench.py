@@ -577,6 +577,28 @@ def run_b200(args):
                                      "correct_image_png_* = a photo-like 4K RGBA frame from pageable host memory through lutgen_cuda_apply_hald_png; cpu_* = PIL (zlib level 1, one "
                                      "thread) on the same CLUT, checked to decode to the same pixels -- the reference's `image` crate "
                                      "encoder cannot run here")
+        # palette extraction (k-means in Oklab) on a 1080p crop of a photo-like frame, host to host;
+        # first measured by this run -- a failure here must not take the line down
+        try:
+            from lutgen_rs_b200 import extract as lextract
+            crop = np.ascontiguousarray(frame_host[:1080, :1920, :3])
+            ts = []
+            for i in range(4):
+                t0 = time.perf_counter()
+                pal16 = lextract.extract_palette(crop, 16, 16)
+                ts.append((time.perf_counter() - t0) * 1e3)
+            other_configs["extract_palette_1080p_16colours_16iters_host_to_host_ms"] = round(float(np.median(ts[1:])), 2)
+            other_configs["extract_palette_colours"] = int(len(pal16))
+            if not args.no_cpu:
+                import oracle_lib as O_ext  # the checker / CPU baseline leg only
+                t0 = time.perf_counter()
+                want16 = O_ext.extract_palette(crop, 16, 16)
+                other_configs["cpu_extract_palette_1080p_ms"] = round((time.perf_counter() - t0) * 1e3, 1)
+                other_configs["extract_palette_matches_cpu_restatement"] = bool(pal16.shape == want16.shape and (pal16 == want16).all())
+            other_configs["extract_what"] = ("deterministic k-means in Oklab (csrc/extract_core.h), NOT the reference's quantette palette (parity "
+                                             "unpinned); cpu_* = the oracle's one-thread restatement of the same specification")
+        except Exception as e:  # noqa: BLE001
+            other_configs["extract_error"] = f"{type(e).__name__}: {e}"
     top, other, other_key = (gen_line, apply_line, "apply") if args.workload == "generate" else (apply_line, gen_line, "generate")
     line = dict(top)
     line.update({"n_gpus": world, "steps": steps, "warmup": warmup, "higher_is_better": True, "vs_baseline": None,

@@ -249,6 +249,19 @@ LUTGEN_API int lutgen_cuda_generate_lut_png(const lutgen_remapper* r, uint8_t le
 LUTGEN_API int lutgen_cuda_apply_hald_png(const uint8_t* rgba, uint32_t width, uint32_t height, const uint8_t* lut_rgb,
                                           uint8_t level, uint8_t* out, size_t capacity, size_t* out_len);
 
+/* ---- palette extraction next to the path ------------------- */
+
+/* `lutgen extract` (crates/cli/src/main.rs:772-815): a palette of at most `color_count` (1..=256; the CLI's
+ * argument is a u8) colours for an RGB8 image by k-means in Oklab -- the role of
+ * quantette::PalettePipeline::{colorspace(Oklab), quantize_method(kmeans()), palette_size(n), palette_par()}.
+ * NOT quantette's palette: that crate is not vendored under the reference and nothing there pins its output;
+ * this is the deterministic k-means specified in csrc/extract_core.h (distinct colours weighted by pixel count,
+ * weighted-maximin seeding, `iterations` Lloyd passes in fixed-point integers), bit exact with its restatement
+ * in oracle/. palette_rgb receives *count_out <= color_count colours (fewer when the image has fewer distinct
+ * colours). */
+LUTGEN_API int lutgen_cuda_extract_palette(const uint8_t* rgb, size_t npix, uint32_t color_count, uint32_t iterations,
+                                           uint8_t* palette_rgb, uint32_t* count_out);
+
 /* ---- oklab (third-party arithmetic on the path; oklab 1.1.2) --------------- */
 
 /* oklab::srgb_to_oklab for n colours: in n x [u8;3], out n x [f32;3] (l, a, b). */

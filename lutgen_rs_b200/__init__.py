@@ -11,13 +11,13 @@ hand-written CUDA kernels). There is no CPU fallback; without an sm_100 GPU ever
 compute call raises. `lutgen_rs_b200.device` holds the device-resident / multi-GPU
 entry points (torch tensors, torch.distributed over NCCL).
 """
-from . import _native, identity, interpolation, png
+from . import _native, extract, identity, interpolation, png
 from ._native import LutgenError, LutgenPanic
 from .interpolation import (AbortFlag, GaussianBlurRemapper, GaussianRemapper, GaussianSamplingRemapper, InterpolatedRemapper,
                             LinearRemapper, NearestNeighborRemapper, ShepardRemapper)
 
 __all__ = [
-    "identity", "interpolation", "png", "LutgenError", "LutgenPanic", "AbortFlag", "InterpolatedRemapper",
+    "identity", "interpolation", "png", "extract", "LutgenError", "LutgenPanic", "AbortFlag", "InterpolatedRemapper",
     "GaussianRemapper", "GaussianBlurRemapper", "ShepardRemapper", "LinearRemapper", "NearestNeighborRemapper",
     "GaussianSamplingRemapper",
 ]

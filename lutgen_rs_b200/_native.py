@@ -30,7 +30,7 @@ EXPORTS = [
     "lutgen_cuda_generate_lut_shard_multi_dev", "lutgen_cuda_peer_barrier_dev", "lutgen_cuda_generate_lut_shard_mc_dev",
     "lutgen_cuda_generate_lut_sequential",
     "lutgen_cuda_png_bound", "lutgen_cuda_encode_png", "lutgen_cuda_encode_png_dev", "lutgen_cuda_generate_lut_png",
-    "lutgen_cuda_apply_hald_png",
+    "lutgen_cuda_apply_hald_png", "lutgen_cuda_extract_palette",
 ]
 
 
@@ -124,6 +124,7 @@ def load():
             "lutgen_cuda_encode_png_dev": ([vp, u32, u32, i32, vp, sz, C.POINTER(sz), vp], i32),
             "lutgen_cuda_generate_lut_png": ([vp, u8, vp, sz, C.POINTER(sz), vp], i32),
             "lutgen_cuda_apply_hald_png": ([vp, u32, u32, vp, u8, vp, sz, C.POINTER(sz)], i32),
+            "lutgen_cuda_extract_palette": ([vp, sz, u32, u32, vp, C.POINTER(u32)], i32),
         }
         for name, (args, res) in sig.items():
             fn = getattr(L, name)

@@ -23,6 +23,7 @@
 #include "kernels_exact.cuh"
 #include "kernels_fast.cuh"
 #include "kernels_warp.cuh"
+#include "kernels_extract.cuh"
 
 using namespace lutgen;
 
@@ -92,6 +93,7 @@ struct Ctx {
     DevBuf batch_frames[kBatchStreams];
     DevBuf misc;
     DevBuf png_in, png_out, png_scratch;  // PNG writer: pixels (host API), file bytes, per-piece scratch
+    DevBuf extract;                       // palette extraction: histogram, point list, centroids
     uint32_t* stats = nullptr;      // device [128], only with LUTGEN_CUDA_STATS set
 } g;
 
@@ -860,6 +862,7 @@ int lutgen_cuda_shutdown(void) {
     g.png_in.release();
     g.png_out.release();
     g.png_scratch.release();
+    g.extract.release();
     png_release();
     for (int i = 0; i < kBatchStreams; ++i) {
         g.batch_frames[i].release();
@@ -1559,6 +1562,96 @@ int lutgen_cuda_apply_hald_png(const uint8_t* rgba, uint32_t width, uint32_t hei
     if (total > capacity) return fail(LUTGEN_ERR_INVALID, "the PNG is %zu bytes, the buffer holds %zu", total, capacity);
     CU_TRY(cudaMemcpyAsync(out, g.png_out.p, total, cudaMemcpyDeviceToHost, g.stream));
     CU_TRY(cudaStreamSynchronize(g.stream));
+    return LUTGEN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// palette extraction (kernels_extract.cuh over extract_core.h)
+// ---------------------------------------------------------------------------
+int lutgen_cuda_extract_palette(const uint8_t* rgb, size_t npix, uint32_t color_count, uint32_t iterations, uint8_t* palette_rgb, uint32_t* count_out) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!palette_rgb || !count_out || (npix && !rgb)) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    if (color_count == 0 || color_count > lext::MAX_COLORS) return fail(LUTGEN_ERR_INVALID, "color_count %u outside 1..=%u", color_count, lext::MAX_COLORS);
+    if (npix >= (1ull << 32)) return fail(LUTGEN_ERR_UNSUPPORTED, "more than 2^32 pixels in one call");
+    *count_out = 0;
+    if (npix == 0) return LUTGEN_OK;
+    std::lock_guard<std::mutex> lk(g.mu);
+    const size_t cap = npix < lext::NKEYS ? npix : lext::NKEYS;  // at most this many distinct colours
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += up(bytes);
+        return o;
+    };
+    const size_t o_counts = take(sizeof(uint32_t) * lext::NKEYS), o_in = take(3 * npix), o_keys = take(4 * cap), o_weights = take(4 * cap),
+                 o_list = take(3 * cap), o_lab = take(12 * cap), o_q = take(12 * cap), o_dmin = take(8 * cap),
+                 o_small = take(4096 + 12 * lext::MAX_COLORS + 32 * lext::MAX_COLORS + 12 * lext::MAX_COLORS + 3 * lext::MAX_COLORS);
+    CU_TRY(g.extract.reserve(off));
+    uint8_t* base = (uint8_t*)g.extract.p;
+    uint32_t* counts = (uint32_t*)(base + o_counts);
+    uint8_t* in = base + o_in;
+    uint32_t* keys = (uint32_t*)(base + o_keys);
+    uint32_t* weights = (uint32_t*)(base + o_weights);
+    uint8_t* list = base + o_list;
+    float* lab = (float*)(base + o_lab);
+    int32_t* q = (int32_t*)(base + o_q);
+    unsigned long long* dmin = (unsigned long long*)(base + o_dmin);
+    // small block: seed (16 B) | n_points | n_centroids | ... | centroids | sums | out_lab | out_rgb
+    uint8_t* small = base + o_small;
+    lext::Seed* seed = (lext::Seed*)small;
+    uint32_t* n_points = (uint32_t*)(small + 64);
+    uint32_t* n_centroids = (uint32_t*)(small + 128);
+    int32_t* centroids = (int32_t*)(small + 4096);
+    long long* sums = (long long*)(small + 4096 + 12 * lext::MAX_COLORS);
+    float* out_lab = (float*)(small + 4096 + 12 * lext::MAX_COLORS + 32 * lext::MAX_COLORS);
+    uint8_t* out_rgb = small + 4096 + 12 * lext::MAX_COLORS + 32 * lext::MAX_COLORS + 12 * lext::MAX_COLORS;
+    cudaStream_t s = g.stream;
+    CU_TRY(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * lext::NKEYS, s));
+    CU_TRY(cudaMemsetAsync(small, 0, up(4096 + 12 * lext::MAX_COLORS + 32 * lext::MAX_COLORS + 12 * lext::MAX_COLORS + 3 * lext::MAX_COLORS), s));
+    CU_TRY(cudaMemcpyAsync(in, rgb, 3 * npix, cudaMemcpyHostToDevice, s));
+    k_ext_hist<<<blocks_for(npix, EXT_THREADS), EXT_THREADS, 0, s>>>(in, npix, counts);
+    LAUNCH_CHECK();
+    k_ext_compact<<<lext::NKEYS / EXT_THREADS, EXT_THREADS, 0, s>>>(counts, n_points, keys, weights, list);
+    LAUNCH_CHECK();
+    uint32_t n = 0;
+    CU_TRY(cudaMemcpyAsync(&n, n_points, sizeof n, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    if (n == 0 || n > cap) return fail(LUTGEN_ERR_CUDA, "palette extraction: %u distinct colours out of %zu pixels", n, npix);
+    const unsigned grid = blocks_for(n, EXT_THREADS);
+    k_srgb_to_oklab<<<grid, 256, 0, s>>>(list, n, lab, g.tables);
+    LAUNCH_CHECK();
+    k_ext_quantise<<<grid, EXT_THREADS, 0, s>>>(lab, n, q, dmin);
+    LAUNCH_CHECK();
+    const uint32_t k = color_count < n ? color_count : n;
+    for (uint32_t j = 0; j < k; ++j) {
+        CU_TRY(cudaMemsetAsync(seed, 0, sizeof(lext::Seed), s));
+        k_ext_seed_score<<<grid, EXT_THREADS, 0, s>>>(n, j, q, weights, centroids, n_centroids, dmin, seed);
+        LAUNCH_CHECK();
+        k_ext_seed_pick<<<grid, EXT_THREADS, 0, s>>>(n, j, keys, weights, n_centroids, dmin, seed);
+        LAUNCH_CHECK();
+        k_ext_seed_commit<<<grid, EXT_THREADS, 0, s>>>(n, j, keys, q, weights, dmin, seed, centroids, n_centroids);
+        LAUNCH_CHECK();
+    }
+    for (uint32_t it = 0; it < iterations; ++it) {
+        k_ext_assign<<<grid, EXT_THREADS, 0, s>>>(n, q, weights, centroids, n_centroids, sums);
+        LAUNCH_CHECK();
+        k_ext_update<<<1, EXT_THREADS, 0, s>>>(n_centroids, sums, centroids);
+        LAUNCH_CHECK();
+    }
+    k_ext_output<<<1, EXT_THREADS, 0, s>>>(centroids, out_lab);
+    LAUNCH_CHECK();
+    k_oklab_to_srgb<<<1, 256, 0, s>>>(out_lab, lext::MAX_COLORS, out_rgb, g.tables);
+    LAUNCH_CHECK();
+    uint32_t found = 0;
+    uint8_t host_rgb[3 * lext::MAX_COLORS];
+    CU_TRY(cudaMemcpyAsync(&found, n_centroids, sizeof found, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(host_rgb, out_rgb, sizeof host_rgb, cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    if (found > k) return fail(LUTGEN_ERR_CUDA, "palette extraction: %u centroids for %u requested", found, k);
+    std::memcpy(palette_rgb, host_rgb, 3 * (size_t)found);
+    *count_out = found;
     return LUTGEN_OK;
 }
 

@@ -725,3 +725,117 @@ ORACLE_API int lutgen_oracle_max_threads(void) {
     return 1;
 #endif
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Palette extraction (`lutgen extract`, crates/cli/src/main.rs:772-815).
+ *
+ * PARITY UNPINNED against the reference: its `quantette` dependency (PalettePipeline, ColorSpace::Oklab,
+ * QuantizeMethod::kmeans) is not vendored, no test or fixture of the reference pins its output, and its
+ * sampled online k-means cannot be restated from the call site. This is the restatement of the
+ * deterministic k-means SPECIFIED in lutgen_rs_b200/csrc/extract_core.h (distinct colours weighted by
+ * pixel count, 16.16 fixed-point Oklab, weighted-maximin seeding, Lloyd iterations in integers), written
+ * independently of the kernels: a sorted list of distinct colours and plain loops.
+ * Returns the number of colours written to out_rgb (at most color_count).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    uint32_t key, w;
+    int32_t q[3];
+} extract_point;
+
+static uint64_t extract_dist(const int32_t* a, const int32_t* b) {
+    uint64_t d = 0;
+    for (int c = 0; c < 3; ++c) {
+        int64_t t = (int64_t)a[c] - (int64_t)b[c];
+        d += (uint64_t)(t * t);
+    }
+    return d;
+}
+
+ORACLE_API uint32_t lutgen_oracle_extract_palette(const uint8_t* rgb, size_t npix, uint32_t color_count, uint32_t iterations, uint8_t* out_rgb) {
+    init_tables();
+    if (npix == 0 || color_count == 0) return 0;
+    if (color_count > 256) color_count = 256;
+    uint32_t* counts = (uint32_t*)calloc((size_t)1 << 24, sizeof(uint32_t));
+    for (size_t i = 0; i < npix; ++i) counts[(uint32_t)rgb[3 * i] | ((uint32_t)rgb[3 * i + 1] << 8) | ((uint32_t)rgb[3 * i + 2] << 16)]++;
+    size_t n = 0;
+    for (uint32_t key = 0; key < (1u << 24); ++key) n += counts[key] != 0;
+    extract_point* p = (extract_point*)malloc(n * sizeof(extract_point));
+    uint64_t* dmin = (uint64_t*)malloc(n * sizeof(uint64_t));
+    size_t m = 0;
+    for (uint32_t key = 0; key < (1u << 24); ++key) { /* ascending key: the first maximum found is the tie winner */
+        if (!counts[key]) continue;
+        oklab_t o = srgb_to_oklab((uint8_t)key, (uint8_t)(key >> 8), (uint8_t)(key >> 16));
+        p[m].key = key;
+        p[m].w = counts[key];
+        p[m].q[0] = (int32_t)lrintf(o.l * 65536.0f);
+        p[m].q[1] = (int32_t)lrintf(o.a * 65536.0f);
+        p[m].q[2] = (int32_t)lrintf(o.b * 65536.0f);
+        dmin[m] = UINT64_MAX;
+        ++m;
+    }
+    free(counts);
+    int32_t cent[256][3];
+    uint32_t k = 0;
+    /* seeding */
+    {
+        size_t best = 0;
+        for (size_t i = 1; i < n; ++i)
+            if (p[i].w > p[best].w) best = i;
+        memcpy(cent[0], p[best].q, sizeof cent[0]);
+        k = 1;
+    }
+    while (k < color_count) {
+        uint64_t best_score = 0;
+        size_t best = 0;
+        for (size_t i = 0; i < n; ++i) {
+            uint64_t d = extract_dist(p[i].q, cent[k - 1]);
+            if (d < dmin[i]) dmin[i] = d;
+            uint64_t w = p[i].w < 65535u ? p[i].w : 65535u;
+            uint64_t score = w * dmin[i];
+            if (score > best_score) {
+                best_score = score;
+                best = i;
+            }
+        }
+        if (best_score == 0) break; /* every point sits on a centroid */
+        memcpy(cent[k], p[best].q, sizeof cent[k]);
+        ++k;
+    }
+    /* Lloyd */
+    for (uint32_t it = 0; it < iterations; ++it) {
+        int64_t sum[256][4];
+        memset(sum, 0, sizeof sum);
+        for (size_t i = 0; i < n; ++i) {
+            uint32_t bj = 0;
+            uint64_t bd = extract_dist(p[i].q, cent[0]);
+            for (uint32_t j = 1; j < k; ++j) {
+                uint64_t d = extract_dist(p[i].q, cent[j]);
+                if (d < bd) {
+                    bd = d;
+                    bj = j;
+                }
+            }
+            for (int c = 0; c < 3; ++c) sum[bj][c] += (int64_t)p[i].w * p[i].q[c];
+            sum[bj][3] += p[i].w;
+        }
+        int moved = 0;
+        for (uint32_t j = 0; j < k; ++j) {
+            int64_t w = sum[j][3];
+            if (w <= 0) continue;
+            for (int c = 0; c < 3; ++c) {
+                int64_t s = sum[j][c];
+                int32_t v = (int32_t)(s >= 0 ? (2 * s + w) / (2 * w) : -((-2 * s + w) / (2 * w)));
+                moved |= v != cent[j][c];
+                cent[j][c] = v;
+            }
+        }
+        if (!moved) break; /* a fixed point: further passes change nothing */
+    }
+    for (uint32_t j = 0; j < k; ++j) {
+        oklab_t c = {(float)cent[j][0] * (1.0f / 65536.0f), (float)cent[j][1] * (1.0f / 65536.0f), (float)cent[j][2] * (1.0f / 65536.0f)};
+        oklab_to_srgb(c, out_rgb + 3 * j);
+    }
+    free(p);
+    free(dmin);
+    return k;
+}

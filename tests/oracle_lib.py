@@ -71,6 +71,8 @@ def lib():
         L.lutgen_oracle_max_threads.restype = i32
         L.lutgen_oracle_blur_generate.argtypes = [vp, u8, vp, i32, i32]
         L.lutgen_oracle_blur_generate.restype = i32
+        L.lutgen_oracle_extract_palette.argtypes = [vp, sz, u32, u32, vp]
+        L.lutgen_oracle_extract_palette.restype = u32
         _lib = L
     return _lib
 
@@ -108,6 +110,15 @@ def correct_image(rgba, lut, level, threads=1):
     lut = np.ascontiguousarray(lut, np.uint8)
     lib().lutgen_oracle_correct_image(_ptr(out), out.size // 4, _ptr(lut), level, threads)
     return out
+
+
+def extract_palette(rgb, color_count, iterations=16):
+    """The oracle's restatement of the deterministic k-means of lutgen_rs_b200/csrc/extract_core.h (parity with the
+    reference's quantette dependency is unpinned, see there). rgb: (..., 3) uint8. Returns (k, 3) uint8."""
+    rgb = np.ascontiguousarray(rgb, np.uint8).reshape(-1, 3)
+    out = np.zeros((256, 3), np.uint8)
+    k = lib().lutgen_oracle_extract_palette(_ptr(rgb), rgb.shape[0], int(color_count), int(iterations), _ptr(out))
+    return out[:k].copy()
 
 
 def srgb_to_oklab(rgb):

@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from conftest import synthetic_palette  # noqa: E402
-from lutgen_rs_b200 import _native, identity, interpolation, png  # noqa: E402
+from lutgen_rs_b200 import _native, extract, identity, interpolation, png  # noqa: E402
 
 
 def main():
@@ -67,6 +67,7 @@ def main():
     png.encode(np.zeros((3, 9000, 1), np.uint8))
     png.generate_lut_png(interpolation.NearestNeighborRemapper(pal, 1.0, False), 6)
     png.correct_image_png(img, lut)
+    extract.extract_palette(img[:, :, :3], 8, 4)
     print(f"sanitize driver done: {_native.launch_count() - before} kernel launches")
 
 
