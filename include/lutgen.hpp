@@ -148,6 +148,22 @@ inline void save(const Image<CH>& image, const std::string& path) {
 
 }  // namespace png
 
+// `lutgen extract` (crates/cli/src/main.rs:772-815): the role of quantette's PalettePipeline with
+// ColorSpace::Oklab and QuantizeMethod::kmeans() -- a deterministic k-means in Oklab, NOT quantette's palette
+// (see lutgen_cuda_extract_palette in lutgen_cuda.h).
+namespace extract {
+
+inline std::vector<std::array<uint8_t, 3>> palette(const RgbImage& image, uint32_t color_count, uint32_t iterations = 16) {
+    detail::ensure_init();
+    std::vector<std::array<uint8_t, 3>> out(color_count ? color_count : 1);
+    uint32_t n = 0;
+    detail::check(lutgen_cuda_extract_palette(image.data.data(), image.pixels(), color_count, iterations, out.front().data(), &n));
+    out.resize(n);
+    return out;
+}
+
+}  // namespace extract
+
 namespace interpolation {
 
 // trait InterpolatedRemapper (interpolation/mod.rs:23-61) + the GenerateLut blanket impl (lib.rs:135-171).
