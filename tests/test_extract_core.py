@@ -95,3 +95,21 @@ def test_python_mirror_checks_its_arguments_without_a_gpu():
         extract.extract_palette(np.zeros((4, 4, 3), np.float32), 8)
     with pytest.raises(OverflowError):
         extract.extract_palette(np.zeros((4, 4, 3), np.uint8), -1)
+
+
+def test_tie_heavy_random_inputs():
+    """Seeded fuzz on tiny images whose colours repeat, collide on coarse grids or sit a step apart: the tie rules
+    (smallest key in the seeding, lowest index in the assignment) are what decides here."""
+    rng = np.random.default_rng(123)
+    for trial in range(150):
+        ncol = int(rng.integers(1, 12))
+        base = rng.integers(0, 256, (ncol, 3))
+        if trial % 3 == 0:
+            base = (base // 64) * 64
+        if trial % 3 == 1:
+            base = rng.integers(100, 104, (ncol, 3))
+        idx = rng.integers(0, ncol, int(rng.integers(1, 60)))
+        img = base[idx].astype(np.uint8).reshape(1, -1, 3)
+        k, it = int(rng.integers(1, 10)), int(rng.integers(0, 6))
+        want, got = O.extract_palette(img, k, it), S.extract_palette(img, k, it, seed=trial)
+        assert want.shape == got.shape and (want == got).all(), (trial, k, it)
