@@ -233,3 +233,28 @@ def test_python_mirror_checks_its_arguments_without_a_gpu():
         png.bound(0, 4, 3)
     with pytest.raises(lg.LutgenPanic):
         png.bound(4, 4, 7)
+
+
+def test_written_files_match_the_committed_digests():
+    """tests/golden/png_files.json (made by tests/golden/make_png_golden.py) pins the bytes the encoder writes for
+    four small images, and png_identity_level3.png is one of those files, readable by anything."""
+    import hashlib
+    import json
+    import os
+    import sys
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, golden)
+    import make_png_golden
+    with open(os.path.join(golden, "png_files.json")) as f:
+        want = json.load(f)
+    for name, img in make_png_golden.images().items():
+        w = want[name]
+        if hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest() != w["pixels_sha256"]:
+            pytest.skip(f"{name}: this machine's oracle produces other pixels than the one that wrote the digests")
+        data = P.encode(img)[0]
+        assert len(data) == w["png_bytes"] and hashlib.sha256(data).hexdigest() == w["png_sha256"], name
+    with open(os.path.join(golden, "png_identity_level3.png"), "rb") as f:
+        data = f.read()
+    import oracle_lib as O
+    assert (_pil(data) == O.identity(3)).all()
+    assert data == P.encode(O.identity(3))[0]
