@@ -113,3 +113,29 @@ def test_tie_heavy_random_inputs():
         k, it = int(rng.integers(1, 10)), int(rng.integers(0, 6))
         want, got = O.extract_palette(img, k, it), S.extract_palette(img, k, it, seed=trial)
         assert want.shape == got.shape and (want == got).all(), (trial, k, it)
+
+
+def _golden_images():
+    rng = np.random.default_rng(2026)
+    return {
+        "random_40x50": rng.integers(0, 256, (40, 50, 3), dtype=np.uint8),
+        "three_tones": np.concatenate([np.tile(np.array([[200, 30, 30]], np.uint8), (500, 1)), np.tile(np.array([[10, 10, 250]], np.uint8), (30, 1)),
+                                       rng.integers(90, 110, (200, 3)).astype(np.uint8)]).reshape(-1, 1, 3),
+    }
+
+
+def test_palettes_match_the_committed_ones():
+    """tests/golden/extract_palettes.json: palettes of two integer-generated images, written by the oracle when the
+    specification was fixed. They pin the SPECIFICATION (seeding, tie rules, rounding) from round to round; they say
+    nothing about the reference's quantette palettes (parity unpinned)."""
+    import hashlib
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "extract_palettes.json")) as f:
+        want = json.load(f)
+    for name, img in _golden_images().items():
+        w = want[name]
+        assert hashlib.sha256(np.ascontiguousarray(img).tobytes()).hexdigest() == w["pixels_sha256"], "numpy's generator changed?"
+        for k, it, key in ((8, 16, "k8_iters16"), (3, 0, "k3_iters0")):
+            assert O.extract_palette(img, k, it).tolist() == w[key], (name, key)
+            assert S.extract_palette(img, k, it, seed=5).tolist() == w[key], (name, key)
