@@ -13,15 +13,41 @@
 #include "../lutgen_rs_b200/csrc/png_core.h"
 
 namespace {
+// Order in which the "threads" of a phase run: 0 ascending, 1 descending, 2 a different pseudo-random permutation in
+// every phase. A phase whose outcome depends on this order has a race (a thread reading what another writes in the
+// same phase, or two plain writes to one place) -- on the GPU the order is anybody's guess -- so the tests demand the
+// same file for all three.
+int g_order = 0;
+
 struct LoopExec {
+    unsigned long long state = 0x9E3779B97F4A7C15ull;
     template <class F>
     void par(F f) {
-        for (int t = 0; t < lpng::THREADS; ++t) f(t);
+        if (g_order == 0) {
+            for (int t = 0; t < lpng::THREADS; ++t) f(t);
+        } else if (g_order == 1) {
+            for (int t = lpng::THREADS; t-- > 0;) f(t);
+        } else {
+            int order[lpng::THREADS];
+            for (int t = 0; t < lpng::THREADS; ++t) order[t] = t;
+            for (int i = lpng::THREADS; i > 1; --i) {
+                state ^= state << 13;
+                state ^= state >> 7;
+                state ^= state << 17;
+                int j = (int)(state % (unsigned)i);
+                int tmp = order[i - 1];
+                order[i - 1] = order[j];
+                order[j] = tmp;
+            }
+            for (int t = 0; t < lpng::THREADS; ++t) f(order[t]);
+        }
     }
 };
 }  // namespace
 
 extern "C" {
+
+void lpng_sim_set_order(int mode) { g_order = mode; }
 
 unsigned long long lpng_sim_bound(uint32_t width, uint32_t height, uint32_t bpp) { return lpng::png_bound(width, height, bpp); }
 

@@ -33,7 +33,13 @@ def lib():
         _lib.lpng_sim_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_ulonglong, C.POINTER(C.c_ulonglong),
                                          C.c_void_p, C.POINTER(C.c_uint32)]
         _lib.lpng_sim_shared_bytes.restype = C.c_uint32
+        _lib.lpng_sim_set_order.argtypes = [C.c_int]
     return _lib
+
+
+def set_order(mode):
+    """Order in which the threads of each phase run on the host: 0 ascending, 1 descending, 2 scrambled per phase."""
+    lib().lpng_sim_set_order(int(mode))
 
 
 def encode(img):

@@ -258,3 +258,23 @@ def test_written_files_match_the_committed_digests():
     import oracle_lib as O
     assert (_pil(data) == O.identity(3)).all()
     assert data == P.encode(O.identity(3))[0]
+
+
+def test_no_phase_depends_on_the_order_of_its_threads():
+    """The host executor runs the 256 threads of a phase one after the other; on the GPU they run in any order. A
+    phase in which a thread reads what another one writes (a missing barrier), or two threads plainly write one place,
+    gives an order-dependent result: demand the same file for ascending, descending and per-phase scrambled orders."""
+    rng = np.random.default_rng(31)
+    g = (np.arange(300)[None, :, None] * 2 + np.arange(70)[:, None, None] + np.zeros((1, 1, 3))).astype(np.uint8)
+    imgs = [rng.integers(0, 256, (30, 200, 3), dtype=np.uint8), (rng.integers(0, 3, (60, 500, 4)) * 60).astype(np.uint8), g,
+            np.full((20, 9000, 1), 3, np.uint8), np.repeat(rng.integers(0, 256, (1, 700, 3), dtype=np.uint8), 40, axis=0)]
+    try:
+        for img in imgs:
+            files = []
+            for mode in (0, 1, 2):
+                P.set_order(mode)
+                files.append(P.encode(img)[0])
+            assert files[0] == files[1] == files[2]
+            assert (_pil(files[2]) == img).all()
+    finally:
+        P.set_order(0)
