@@ -278,3 +278,25 @@ def test_no_phase_depends_on_the_order_of_its_threads():
             assert (_pil(files[2]) == img).all()
     finally:
         P.set_order(0)
+
+
+def test_more_pieces_than_layout_threads():
+    """More than 256 pieces: every thread of the layout pass (offsets, Adler-32 fold) then owns several of them."""
+    rng = np.random.default_rng(8)
+    img = (rng.integers(0, 4, (1300, 1200, 3)) * 30).astype(np.uint8)
+    img[200:900, 100:1100] = 17
+    data, _, stored = P.encode(img)
+    assert (img.shape[0] * (img.shape[1] * 3 + 1) + CHUNK - 1) // CHUNK > 256
+    assert (_pil(data) == img).all()
+    # chunk CRCs, chunk count and the Adler-32 through the specification reader's front half
+    import struct
+    import zlib
+    pos, idat = 8, []
+    while pos < len(data):
+        ln, typ = struct.unpack(">I4s", data[pos:pos + 8])
+        assert zlib.crc32(data[pos + 4:pos + 8 + ln]) == struct.unpack(">I", data[pos + 8 + ln:pos + 12 + ln])[0]
+        if typ == b"IDAT":
+            idat.append(data[pos + 8:pos + 8 + ln])
+        pos += 12 + ln
+    assert len(idat) == (img.shape[0] * (img.shape[1] * 3 + 1) + CHUNK - 1) // CHUNK + 1
+    assert len(zlib.decompress(b"".join(idat))) == img.shape[0] * (img.shape[1] * 3 + 1)
