@@ -256,7 +256,7 @@ LUTGEN_API int lutgen_cuda_apply_hald_png(const uint8_t* rgba, uint32_t width, u
  * quantette::PalettePipeline::{colorspace(Oklab), quantize_method(kmeans()), palette_size(n), palette_par()}.
  * NOT quantette's palette: that crate is not vendored under the reference and nothing there pins its output;
  * this is the deterministic k-means specified in csrc/extract_core.h (distinct colours weighted by pixel count,
- * weighted-maximin seeding, `iterations` Lloyd passes in fixed-point integers), bit exact with its restatement
+ * weighted-maximin seeding, `iterations` (at most 1000) Lloyd passes in fixed-point integers), bit exact with its restatement
  * in oracle/. palette_rgb receives *count_out <= color_count colours (fewer when the image has fewer distinct
  * colours). */
 LUTGEN_API int lutgen_cuda_extract_palette(const uint8_t* rgb, size_t npix, uint32_t color_count, uint32_t iterations,

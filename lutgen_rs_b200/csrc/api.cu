@@ -1574,6 +1574,7 @@ int lutgen_cuda_extract_palette(const uint8_t* rgb, size_t npix, uint32_t color_
     if (!palette_rgb || !count_out || (npix && !rgb)) return fail(LUTGEN_ERR_INVALID, "NULL argument");
     if (color_count == 0 || color_count > lext::MAX_COLORS) return fail(LUTGEN_ERR_INVALID, "color_count %u outside 1..=%u", color_count, lext::MAX_COLORS);
     if (npix >= (1ull << 32)) return fail(LUTGEN_ERR_UNSUPPORTED, "more than 2^32 pixels in one call");
+    if (iterations > 1000) return fail(LUTGEN_ERR_INVALID, "%u Lloyd passes (at most 1000; two launches each)", iterations);
     *count_out = 0;
     if (npix == 0) return LUTGEN_OK;
     std::lock_guard<std::mutex> lk(g.mu);
