@@ -235,7 +235,7 @@ LUTGEN_API int lutgen_cuda_encode_png(const uint8_t* pixels, uint32_t width, uin
 LUTGEN_API int lutgen_cuda_encode_png_dev(const uint8_t* pixels_dev, uint32_t width, uint32_t height, int channels,
                                           uint8_t* out_dev, size_t capacity, size_t* out_len, void* stream);
 
-/* GenerateLut::par_generate_lut followed by `lut.save(path)` (crates/cli/src/main.rs:742-767, the
+/* GenerateLut::par_generate_lut followed by `lut.save(path)` (crates/cli/src/main.rs:756-768, the
  * whole of `lutgen generate` after argument parsing): the CLUT is generated and encoded on the device
  * and only the PNG bytes cross PCIe. Same return values as lutgen_cuda_generate_lut; *out_len and
  * `capacity` as in lutgen_cuda_encode_png (bound: lutgen_cuda_png_bound(level^3, level^3, 3)). */

@@ -68,7 +68,7 @@ def save(image, path):
 
 
 def generate_lut_png(remapper, level, abort=None):
-    """`remapper.par_generate_lut(level)` followed by `lut.save(path)` (crates/cli/src/main.rs:742-767) with the
+    """`remapper.par_generate_lut(level)` followed by `lut.save(path)` (crates/cli/src/main.rs:756-768) with the
     CLUT never leaving the device: returns the PNG bytes, or None if `abort` was seen set."""
     from .interpolation import _abort_ptr
     level = int(level)
