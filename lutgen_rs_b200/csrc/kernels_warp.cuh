@@ -3,7 +3,7 @@
 // tile instead of one CTA, and the arithmetic in packed f32x2 (FFMA2 / FMUL2 / FADD2, sm_100a).
 //
 // Why a warp per tile: the smaller the tile, the tighter its Oklab bounding box and the fewer
-// palette colours are left UNCERTAIN at the k-boundary (tools/sim_tiles.py: 6.9 per 8x8x16 CTA tile,
+// palette colours are left UNCERTAIN at the k-boundary (tests/tools/sim_tiles.py: 6.9 per 8x8x16 CTA tile,
 // 2.7 per 8x4x4 warp tile for the headline configuration); per-entry selection among the uncertain
 // colours was the most expensive part of the CTA kernel. A warp classifies a 26-colour palette in
 // ~200 instructions (one colour per lane, ranks from one broadcast loop), needs no CTA barrier,

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Off-by-one bytes of the GPU CLUTs against the reference's golden CLUT images (tests/golden)."""
 import json, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from lutgen_rs_b200 import interpolation

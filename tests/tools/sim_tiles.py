@@ -3,7 +3,7 @@
 different brick shapes: how many palette colours end up IN / UNCERTAIN per tile, how many have to be
 chosen per entry. Design aid only (numpy; uses the oracle's Oklab conversion).
 
-    python tools/sim_tiles.py [palette] [k] [shape] [level]
+    python tests/tools/sim_tiles.py [palette] [k] [shape] [level]
 """
 import json
 import os
@@ -11,7 +11,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_lib as O  # noqa: E402
 from conftest import synthetic_palette  # noqa: E402
