@@ -52,6 +52,19 @@ GEN_PARAMS = dict(shape=128.0, nearest=16, lum=1.0, preserve=False)
 GEN_N, GEN_K = 26, 16
 GEN_FLOPS_PER_ENTRY = 8 * GEN_N + 9 * GEN_K + 77
 APPLY_BYTES_PER_PIXEL = 8  # 4 read + 4 written, in place; CLUT traffic is cache resident
+# config.workload: the SAME string in both arms (b200 and reference); how a run executes it goes into other config keys
+GEN_WORKLOAD = ("generate level-16 Gaussian RBF CLUT (16,777,216 entries), catppuccin-mocha 26 colours, shape 128, nearest 16, "
+                "lum 1.0, preserve off")
+APPLY_WORKLOAD = "apply level-8 CLUT in place to 3840x2160 RGBA8 frames, uniform random pixels"
+
+
+def host_threads():
+    """Host cores this process may run on. NOT omp_get_max_threads(): torch.distributed.run exports
+    OMP_NUM_THREADS=1 to its workers, which would make the CPU arm single-threaded for N >= 2."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def load_palette():
@@ -123,20 +136,18 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------- reference arm / CPU baseline
 def cpu_generate(steps, warmup, threads):
-    """Oracle port of par_generate_lut on a bounded sample: 8 bands of 64 rows spread over the
-    level-16 CLUT (1/8 of its 4096 rows = 2,097,152 entries per step)."""
+    """Oracle port of par_generate_lut (lib.rs:143-147): the WHOLE level-16 CLUT per step, `threads` OpenMP
+    threads passed explicitly (num_threads clause: the environment's OMP_NUM_THREADS does not apply)."""
     import oracle_lib as O
     pal = load_palette()
     r = O.Remapper(O.GAUSSIAN, pal, param=GEN_PARAMS["shape"], nearest=GEN_PARAMS["nearest"], lum_factor=GEN_PARAMS["lum"],
                    preserve=GEN_PARAMS["preserve"])
     side = LEVEL_GEN ** 3
     out = np.zeros((side, side, 3), np.uint8)
-    bands = [(i * 512, i * 512 + 64) for i in range(8)]
-    entries = sum(b - a for a, b in bands) * side
+    entries = side * side
 
     def step():
-        for a, b in bands:
-            O.lib().lutgen_oracle_generate_lut_rows(r._h, LEVEL_GEN, out.ctypes.data, a, b, threads)
+        O.lib().lutgen_oracle_generate_lut_rows(r._h, LEVEL_GEN, out.ctypes.data, 0, side, threads)
 
     for _ in range(warmup):
         step()
@@ -144,7 +155,7 @@ def cpu_generate(steps, warmup, threads):
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    return entries / dt, dt, "8 bands x 64 rows of the level-16 CLUT (2,097,152 of 16,777,216 entries) per step"
+    return entries / dt, dt, f"the whole level-16 CLUT (16,777,216 entries) per step, {steps} steps after {warmup} warm-up", out
 
 
 def cpu_apply(steps, warmup, threads):
@@ -169,28 +180,33 @@ def cpu_apply(steps, warmup, threads):
 
 
 def run_reference(args):
+    """The reference's own CPU path for the same metric/config, timed on this box's host cores: the C restatement in
+    oracle/ ("port": the reference is Rust and cannot be built here). Runs exactly the steps / warm-up it prints."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle_lib as O
-    cores = O.max_threads()
+    cores = host_threads()
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    gen_v, gen_dt, gen_sample = cpu_generate(min(steps, 5), min(warmup, 1), cores)
-    app_v, app_dt, app_sample = cpu_apply(min(steps, 10), min(warmup, 2), 1)
+    gen_v, gen_dt, gen_sample, _ = cpu_generate(steps, warmup, cores)
+    app_v, app_dt, app_sample = cpu_apply(steps, warmup, 1)
+    app_all_v, _, _ = cpu_apply(min(steps, 5), 1, cores)
     gen = {"metric": "LUT entries/s (level-16 Gaussian RBF)", "value": gen_v, "unit": "entries/s", "ms_per_step": gen_dt * 1e3,
            "cpu_baseline": {"value": gen_v, "unit": "entries/s", "cores": cores, "kind": "port", "sample": gen_sample},
            "e2e": {"value": gen_v, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "config": {"workload": "generate level-16 Gaussian RBF CLUT, catppuccin-mocha (26 colours), shape 128, nearest 16, lum 1.0"}}
+           "config": {"workload": GEN_WORKLOAD, "level": LEVEL_GEN, "host_threads": cores}}
     app = {"metric": "LUT apply Gpix/s", "value": app_v, "unit": "Gpix/s", "ms_per_step": app_dt * 1e3,
-           "cpu_baseline": {"value": app_v, "unit": "Gpix/s", "cores": 1, "kind": "port", "sample": app_sample},
+           "cpu_baseline": {"value": app_v, "unit": "Gpix/s", "cores": 1, "kind": "port", "sample": app_sample,
+                            "all_cores_value": app_all_v, "all_cores": cores},
            "e2e": {"value": app_v, "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "config": {"workload": "apply level-8 CLUT to 3840x2160 RGBA8 (uniform random pixels)"}}
+           "config": {"workload": APPLY_WORKLOAD, "level": LEVEL_APPLY, "frames_per_step": 1, "host_threads": 1}}
     top, other, other_key = (gen, app, "apply") if args.workload == "generate" else (app, gen, "generate")
     line = dict(top)
     line.update({"impl": "reference", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "higher_is_better": True,
                  "scaling": "strong" if args.workload == "generate" else "weak", "vs_baseline": None,
                  "dtype": "f32/f64" if args.workload == "generate" else "u8", "data": "synthetic",
-                 "note": "CPU restatement of the reference algorithm (oracle/), not the Rust binary: no Rust toolchain here",
+                 "note": "CPU restatement of the reference algorithm (oracle/), not the Rust binary: no Rust toolchain here; "
+                         f"{cores} OpenMP threads passed explicitly (schedule(dynamic), as rayon's par_pixels_mut); apply is one thread as "
+                         "identity.rs:71-78 is",
                  other_key: other})
     print(json.dumps(line), flush=True)
 
@@ -329,7 +345,11 @@ def run_b200(args):
 
     def gen_e2e():
         if world == 1:
-            remapper.generate_lut(LEVEL_GEN, out=lut16_host.numpy())
+            # as `lutgen generate` does (crates/cli/src/main.rs:334-348): the remapper is built per invocation, so its
+            # construction (palette upload + Oklab conversion on the device) is inside the timed region
+            rm = interpolation.GaussianRemapper(pal, GEN_PARAMS["shape"], GEN_PARAMS["nearest"], GEN_PARAMS["lum"], GEN_PARAMS["preserve"])
+            rm.generate_lut(LEVEL_GEN, out=lut16_host.numpy())
+            del rm
         else:
             full = device.generate_lut_fused(remapper, LEVEL_GEN) if fused else device.generate_lut(remapper, LEVEL_GEN, out=lut16)
             if rank == 0:
@@ -346,6 +366,38 @@ def run_b200(args):
     gen_e2e()
     apply_e2e()
     barrier()
+
+    # ---------------- output checks (outside every timed region) ----------------
+    # N > 1: every rank's exchanged CLUT (fused and all-gather forms) must equal, byte for byte, what ONE GPU generates
+    checks = {}
+    ref16 = torch.empty(side * side * 3, dtype=torch.uint8, device="cuda")
+    device.generate_lut_rows_(remapper, LEVEL_GEN, ref16, 0, side)
+    torch.cuda.synchronize()
+    if world > 1:
+        same_fused = 1
+        if fused:
+            got = device.generate_lut_fused(remapper, LEVEL_GEN)
+            torch.cuda.synchronize()
+            same_fused = int(torch.equal(got.reshape(-1), ref16))
+        got = device.generate_lut(remapper, LEVEL_GEN, out=lut16)
+        torch.cuda.synchronize()
+        same_ag = int(torch.equal(got.reshape(-1), ref16))
+        t_same = torch.tensor([same_fused, same_ag], device="cuda")
+        dist.all_reduce(t_same, op=dist.ReduceOp.MIN)
+        if fused:
+            checks["fused_matches_single_gpu"] = bool(int(t_same[0].item()))
+        checks["allgather_matches_single_gpu"] = bool(int(t_same[1].item()))
+        if not all(checks.values()):
+            if rank == 0:
+                print(json.dumps({"error": "multi-GPU CLUT differs from the one-GPU CLUT", **checks}), flush=True)
+            dist.destroy_process_group()
+            sys.exit(2)
+    ref16_host = ref16.cpu().numpy().reshape(side, side, 3) if rank == 0 else None
+    exchange_route = "n/a"
+    if fused:
+        peers = next(iter(device._peer_luts.values()), None)
+        exchange_route = "NVSwitch multicast address of torch symmetric memory, multimem.st" if (peers and peers._mc[0]) else (
+            "peer mappings of torch symmetric memory" if (peers and peers._symm) else "CUDA IPC peer mappings")
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -411,8 +463,10 @@ def run_b200(args):
         "metric": "LUT entries/s (level-16 Gaussian RBF)", "value": entries / gen_t, "unit": "entries/s",
         "ms_per_step": gen_t * 1e3, "scaling": "strong", "dtype": "f32 (f64 on flagged near-ties)",
         "gpu_launches": int(gen_launches),
-        "e2e": {"value": entries / gen_e2e_t, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 3 * entries,
-                "ms_per_step": gen_e2e_t * 1e3},
+        "e2e": {"value": entries / gen_e2e_t, "unit": "entries/s", "h2d_bytes_per_step": 4 * len(pal), "d2h_bytes_per_step": 3 * entries,
+                "ms_per_step": gen_e2e_t * 1e3,
+                "what": "GaussianRemapper(palette, ...) constructed (palette upload: 4 bytes per colour), generate_lut(16) into a page-locked "
+                        "host buffer, remapper dropped -- every step"},
         "roofline": {"bound": "fp32", "achieved": gen_achieved, "peak": fp32.value, "unit": "TFLOP/s",
                      "frac": gen_achieved / fp32.value if fp32.value else None,
                      "traffic": profiled_traffic().get("k_remap_warp_level16_bytes_per_launch") if world == 1 else None,
@@ -422,13 +476,12 @@ def run_b200(args):
                      "algorithmic_flops_per_entry": GEN_FLOPS_PER_ENTRY,
                      "step_ms_each": [round(t * 1e3, 4) for t in gen_times],
                      "kernel_ms_each": [round(t * 1e3, 4) for t in gen_kernel_times]},
-        "config": {"workload": "generate level-16 Gaussian RBF CLUT (16,777,216 entries), catppuccin-mocha 26 colours, "
-                               "shape 128, nearest 16, lum 1.0, preserve off; "
-                               + ("one GPU" if world == 1 else
-                                  ("tiles interleaved over ranks, results stored into every rank's buffer over NVLink by the kernel "
-                                   "(CUDA IPC peer memory) + peer-memory barrier" if fused else
-                                   "rows sharded over ranks + in-place NCCL all-gather")),
-                   "level": LEVEL_GEN, "l2": "flushed between timed iterations (512 MiB fill)"},
+        "config": {"workload": GEN_WORKLOAD, "level": LEVEL_GEN,
+                   "execution": ("one GPU" if world == 1 else
+                                 (f"tiles interleaved over {world} ranks; the kernel stores its results into every rank's buffer over NVLink "
+                                  f"({exchange_route}) and signals a peer-memory barrier" if fused else
+                                  "rows sharded over ranks + in-place NCCL all-gather")),
+                   "l2": "flushed between timed iterations (512 MiB fill)"},
     }
     if gen_ag_t is not None:
         gen_line["allgather_variant"] = {"ms_per_step": gen_ag_t * 1e3, "value": entries / gen_ag_t,
@@ -445,9 +498,8 @@ def run_b200(args):
                      "frac": apply_bw / peaks["hbm_gbs"],
                      "traffic": (profiled_traffic().get("k_apply_bytes_per_pixel") or 0) * apply_pix or None,
                      "peak_source": f"MEASURED_PEAKS.json ({peak_kind})"},
-        "config": {"workload": f"apply level-8 CLUT in place to {frames_per_gpu} x 3840x2160 RGBA8 frames per GPU, uniform random pixels "
-                               "(worst case: every gather is its own 32 B L2 sector)",
-                   "level": LEVEL_APPLY, "frames_per_gpu": frames_per_gpu,
+        "config": {"workload": APPLY_WORKLOAD, "level": LEVEL_APPLY, "frames_per_gpu": frames_per_gpu,
+                   "note": "uniform random pixels are the worst case: every gather is its own 32 B L2 sector",
                    "l2": f"batch is {apply_pix * 4 >> 20} MiB per GPU, larger than the 126 MB L2; frames restored (untimed) before every step"},
     }
     photo_bw = apply_pix * APPLY_BYTES_PER_PIXEL / photo_t / 1e9
@@ -459,9 +511,18 @@ def run_b200(args):
     # CPU baseline (rank 0, N = 1 only): oracle port on the host cores, bounded sample
     if world == 1 and not args.no_cpu:
         import oracle_lib as O
-        cores = O.max_threads()
-        v, _, sample = cpu_generate(2, 1, cores)
+        cores = host_threads()
+        v, _, sample, oracle_lut = cpu_generate(3, 1, cores)
         gen_line["cpu_baseline"] = {"value": v, "unit": "entries/s", "cores": cores, "kind": "port", "sample": sample}
+        diff = np.abs(ref16_host.astype(np.int16) - oracle_lut.astype(np.int16))
+        checks["generate_vs_oracle"] = {"max_lsb": int(diff.max()), "bytes_off_by_one": int((diff == 1).sum()), "bytes": int(diff.size),
+                                        "checked": "the whole level-16 CLUT of the timed remapper against the CPU oracle (contract: +-1 LSB)"}
+        assert diff.max() <= 1, "generated CLUT differs from the oracle by more than 1 LSB"
+        one = frames[0].cpu().numpy().reshape(-1, 4)   # a frame the timed apply step produced
+        src = pristine_photo[0].cpu().numpy().reshape(-1, 4)
+        want = O.correct_image(src.reshape(FRAME_H, FRAME_W, 4), lut8_host, LEVEL_APPLY).reshape(-1, 4)
+        checks["apply_vs_oracle"] = {"bit_exact": bool((one == want).all()), "checked": "one photo-like 4K frame of the timed batch against the CPU oracle"}
+        assert checks["apply_vs_oracle"]["bit_exact"], "applied frame differs from the oracle"
         v, _, sample = cpu_apply(5, 1, 1)
         apply_line["cpu_baseline"] = {"value": v, "unit": "Gpix/s", "cores": 1, "kind": "port",
                                       "sample": sample + " (single thread, as identity.rs:71-78)"}
@@ -602,7 +663,8 @@ def run_b200(args):
     top, other, other_key = (gen_line, apply_line, "apply") if args.workload == "generate" else (apply_line, gen_line, "generate")
     line = dict(top)
     line.update({"n_gpus": world, "steps": steps, "warmup": warmup, "higher_is_better": True, "vs_baseline": None,
-                 "data": "synthetic", "clocks": clocks, other_key: other})
+                 "data": "synthetic", "clocks": clocks, "checks": checks, other_key: other})
+    line.update({k: v for k, v in checks.items() if isinstance(v, bool)})
     if other_configs is not None:
         line["other_configs"] = other_configs
     print(json.dumps(line), flush=True)

@@ -181,6 +181,20 @@ LUTGEN_API int lutgen_cuda_generate_lut_shard_multi_dev(const lutgen_remapper* r
 LUTGEN_API int lutgen_cuda_generate_lut_shard_mc_dev(const lutgen_remapper* r, uint8_t level, uint8_t* const* luts_rgb_dev, int nluts,
                                                      uint8_t* multicast_lut, uint32_t shard_index, uint32_t shard_count, void* stream);
 
+/* The whole exchange in ONE launch: as lutgen_cuda_generate_lut_shard_mc_dev (shard `shard_index` of
+ * `shard_count` = nluts, luts_rgb_dev[0] this GPU's copy), and the kernel's last thread block -- the one that
+ * knows all of this GPU's stores to the peers have been issued -- publishes the rank's step number in every
+ * rank's flag array and waits for all ranks' numbers in its own: when the kernel ends, the CLUT is complete
+ * on this GPU. barrier_flags_dev_table: DEVICE array of nluts pointers, entry i = rank i's flag array of 16
+ * u32 (zero before the first step, mapped into this process; slots 0..7 are written by the peers, word 8 is
+ * the owner's step counter). Every rank must launch it once per step, all ranks' kernels running at the same
+ * time (one GPU per rank). NULL: no barrier (the call above). Palettes of at most 32 colours, RBF /
+ * NearestNeighbor remappers; others: LUTGEN_ERR_UNSUPPORTED (use rows + all-gather).
+ * Mirrors GenerateLut::par_generate_lut (crates/lib/src/lib.rs:143-147) for one CLUT shared by G GPUs. */
+LUTGEN_API int lutgen_cuda_generate_lut_exchange_dev(const lutgen_remapper* r, uint8_t level, uint8_t* const* luts_rgb_dev, int nluts,
+                                                     uint8_t* multicast_lut, uint32_t shard_index, uint32_t shard_count,
+                                                     unsigned* const* barrier_flags_dev_table, void* stream);
+
 /* Barrier between the per-GPU processes through flags in peer memory. flags_dev_table: DEVICE array of
  * nranks pointers, entry i = rank i's flag array (>= nranks zero-initialised u32, mapped into this process);
  * epoch must grow by one per barrier. Orders this GPU's earlier writes to peer buffers before the peers'

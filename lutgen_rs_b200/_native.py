@@ -28,6 +28,7 @@ EXPORTS = [
     "lutgen_cuda_generate_lut_rows_multi_dev", "lutgen_cuda_device_alloc", "lutgen_cuda_device_free",
     "lutgen_cuda_ipc_export", "lutgen_cuda_ipc_import", "lutgen_cuda_ipc_close",
     "lutgen_cuda_generate_lut_shard_multi_dev", "lutgen_cuda_peer_barrier_dev", "lutgen_cuda_generate_lut_shard_mc_dev",
+    "lutgen_cuda_generate_lut_exchange_dev",
     "lutgen_cuda_generate_lut_sequential",
     "lutgen_cuda_png_bound", "lutgen_cuda_encode_png", "lutgen_cuda_encode_png_dev", "lutgen_cuda_generate_lut_png",
     "lutgen_cuda_apply_hald_png", "lutgen_cuda_extract_palette",
@@ -113,6 +114,7 @@ def load():
             "lutgen_cuda_generate_lut_rows_multi_dev": ([vp, u8, C.POINTER(vp), i32, u32, u32, vp], i32),
             "lutgen_cuda_generate_lut_shard_multi_dev": ([vp, u8, C.POINTER(vp), i32, u32, u32, vp], i32),
             "lutgen_cuda_generate_lut_shard_mc_dev": ([vp, u8, C.POINTER(vp), i32, vp, u32, u32, vp], i32),
+            "lutgen_cuda_generate_lut_exchange_dev": ([vp, u8, C.POINTER(vp), i32, vp, u32, u32, vp, vp], i32),
             "lutgen_cuda_peer_barrier_dev": ([vp, i32, i32, u32, vp], i32),
             "lutgen_cuda_device_alloc": ([sz, C.POINTER(vp)], i32),
             "lutgen_cuda_device_free": ([vp], i32),

@@ -95,7 +95,34 @@ struct Ctx {
     DevBuf png_in, png_out, png_scratch;  // PNG writer: pixels (host API), file bytes, per-piece scratch
     DevBuf extract;                       // palette extraction: histogram, point list, centroids
     uint32_t* stats = nullptr;      // device [128], only with LUTGEN_CUDA_STATS set
-} g;
+    // k_remap_warp's tile / finished-CTA counter pairs: zero between launches (the kernel's last CTA resets its
+    // pair), handed out round robin so that launches in flight on different streams do not share one
+    uint32_t* counters = nullptr;
+    std::atomic<uint32_t> counter_next{0};
+    int index = 0;                  // position in g_ctx
+};
+constexpr uint32_t kCounterPairs = 1024;
+
+// One context per GPU this process drives (ONE process, up to 8 devices). g_ctx[0] is the primary one:
+// every entry point runs on it unless it shards its work over the others itself (generate_lut, apply_hald_batch).
+// `g` is the calling thread's current context; UseCtx switches it (and the CUDA device) for a scope.
+constexpr int kMaxDevices = 8;
+Ctx g_ctx[kMaxDevices];
+int g_ndev = 0;
+thread_local Ctx* tl_ctx = &g_ctx[0];
+#define g (*tl_ctx)
+
+struct UseCtx {
+    Ctx* prev;
+    explicit UseCtx(int i) : prev(tl_ctx) {
+        tl_ctx = &g_ctx[i];
+        cudaSetDevice(tl_ctx->device);
+    }
+    ~UseCtx() {
+        tl_ctx = prev;
+        if (prev->ready) cudaSetDevice(prev->device);
+    }
+};
 
 int ensure_ready() {
     if (!g.ready) return fail(LUTGEN_ERR_NO_DEVICE, "lutgen_cuda_init has not succeeded in this process (no CPU fallback exists)");
@@ -121,6 +148,7 @@ struct lutgen_remapper {
     uint32_t n = 0;
     uint32_t k_eff = 0;              // 0: every colour
     std::vector<uint8_t> pal_host;   // n x 3
+    void* arena = nullptr;           // one stream-ordered allocation holding every palette array below (and the upal_* ones)
     uint8_t* pal_rgb4 = nullptr;     // device n x 4
     double* pal_lab = nullptr;       // device n x 3
     float* pal_ab = nullptr;         // device n x 2
@@ -328,15 +356,25 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
     // NearestNeighbor on fine grids: tiles 8 planes deep (two groups per lane, one classification), 10 % faster.
     // Measured and rejected for the RBF kinds (the larger box leaves more colours to choose from per entry:
     // level-16 Gaussian 0.306 -> 0.342 ms) and for coarse grids (level 8: 0.076 -> 0.127 ms).
-    constexpr int GROUPS_LEAN = (!BIG && MODE != FRONT_IMAGE && KIND == KIND_NN) ? 2 : 1;
+    constexpr int GROUPS_LEAN = (!BIG && MODE != FRONT_IMAGE) ? 2 : 1;
     const bool multi = MODE == FRONT_LUT && f.nextra > 0;
-    const bool deep = GROUPS_LEAN == 2 && !multi && f.cs >= 128 && !getenv("LUTGEN_CUDA_WARP_SHALLOW");
+    const bool deep = GROUPS_LEAN == 2 && !multi && f.cs >= 128 && !getenv("LUTGEN_CUDA_WARP_SHALLOW") &&
+                      (KIND == KIND_NN || getenv("LUTGEN_CUDA_WARP_DEEP"));
     WarpArgs a{};
     a.f = f;
     a.pal = fa.pal; a.pal_rgb = fa.pal_rgb; a.pal_ab = fa.pal_ab;
     a.n = fa.n; a.k = fa.k; a.preserve = fa.preserve; a.lum = fa.lum; a.inv_lum = fa.inv_lum; a.c1 = fa.c1;
     a.flag_list = fa.flag_list; a.flag_count = fa.flag_count; a.tile_counter = fa.tile_counter;
     a.stats = fa.stats; a.tables = fa.tables;
+    a.pal64 = KIND == KIND_NN ? r->upal_lab : r->pal_lab;
+    a.lum64 = r->d.lum_factor;
+    a.param64 = r->d.param;
+    a.rank_scale = (float)(32768.0 / (r->d.lum_factor * r->d.lum_factor + 1.0));   // squared Oklab distances stay below lum^2 + 1
+    if (!BIG) {
+        const uint32_t pair = g.counter_next.fetch_add(1, std::memory_order_relaxed) % kCounterPairs;
+        a.tile_counter = g.counters + 2 * pair;
+        a.done_counter = a.tile_counter + 1;
+    }
     a.words_ok = 0;
     if (MODE == FRONT_LUT && (f.cs & 3u) == 0) {
         uintptr_t bits = reinterpret_cast<uintptr_t>(f.out);
@@ -363,6 +401,8 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
         uint32_t b_lo = (uint32_t)(f.begin / plane) / tb * tb, b_hi = (uint32_t)((f.begin + f.count - 1) / plane);
         a.b_lo = b_lo;
         a.ntiles = a.tiles_r * a.tiles_g * ((b_hi - b_lo) / tb + 1);
+        const unsigned long long slab = plane * tb;
+        a.whole_tiles = (cs % tr == 0) && (cs % tg == 0) && (cs % tb == 0) && (f.begin % slab == 0) && (f.count % slab == 0);
     }
     a.ntiles_global = a.ntiles;
     a.shard_index = 0;
@@ -379,8 +419,8 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
         a.shard_index = f.shard_index;
         a.shard_count = f.shard_count;
         a.ntiles = handouts > f.shard_index ? ((handouts - f.shard_index + f.shard_count - 1) / f.shard_count) * per : 0;
-        if (a.ntiles == 0) {
-            CU_TRY(cudaMemsetAsync(r->flag_count, 0, 2 * sizeof(uint32_t), s));
+        if (a.ntiles == 0 && !(f.bar_nranks > 1)) {   // with a barrier the (empty) kernel still has to take part in it
+            if (BIG) CU_TRY(cudaMemsetAsync(r->flag_count, 0, 2 * sizeof(uint32_t), s));
             return LUTGEN_OK;
         }
     }
@@ -403,7 +443,15 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
     unsigned grid = (unsigned)per_sm[variant] * (unsigned)g.sm_count;
     unsigned need = BIG ? a.ntiles : blocks_for(a.ntiles, WT_WARPS * a.batch);
     if (grid > need) grid = need;
-    CU_TRY(cudaMemsetAsync(r->flag_count, 0, 2 * sizeof(uint32_t), s));
+    if (grid < 1) grid = 1;
+    a.tail_cut = a.ticket_end = a.ntiles;
+    if (!BIG && a.batch > 1 && a.shard_count == 1) {
+        // the last two tiles per resident warp go out one by one (k_remap_warp's ticket scheme)
+        const uint32_t singles = std::min(a.ntiles, grid * (uint32_t)WT_WARPS * 2u);
+        a.tail_cut = (a.ntiles - singles) / a.batch * a.batch;
+        a.ticket_end = a.tail_cut + (a.ntiles - a.tail_cut) * a.batch;
+    }
+    if (BIG) CU_TRY(cudaMemsetAsync(r->flag_count, 0, 2 * sizeof(uint32_t), s));
     if (BIG) {
         if (multi) k_remap_warp_big<KIND, MODE, EPT, MODE == FRONT_LUT><<<grid, WT_THREADS, 0, s>>>(a);
         else k_remap_warp_big<KIND, MODE, EPT, false><<<grid, WT_THREADS, 0, s>>>(a);
@@ -422,7 +470,8 @@ int launch_fast(const Front& f_in, const lutgen_remapper* r, cudaStream_t s) {
     const bool nn_ = KIND == KIND_NN;
     const Front f = (f_in.shard_count > 1 && !warp_path<KIND>(r, nn_ ? r->un : r->n, nn_ ? 1u : r->k_eff)) ? rows_of_shard(f_in) : f_in;
     if (f.count == 0) return LUTGEN_OK;
-    {
+    const int wp_kind = warp_path<KIND>(r, nn_ ? r->un : r->n, nn_ ? 1u : r->k_eff);
+    if (wp_kind != 1) {   // k_remap_warp resolves what it cannot decide itself: no work list, no second pass
         std::lock_guard<std::mutex> lk(r->mu);
         if (!r->flag_count) CU_TRY(cudaMalloc((void**)&r->flag_count, 64));
         if (r->flag_cap < f.count) {
@@ -457,8 +506,9 @@ int launch_fast(const Front& f_in, const lutgen_remapper* r, cudaStream_t s) {
     fl.list = r->flag_list;
     fl.list_count = r->flag_count;
     fl.list_mode = MODE;
-    if (const int wp = warp_path<KIND>(r, a.n, a.k)) {
-        int rc = wp == 1 ? launch_warp<KIND, MODE, 4, false>(f, r, s, a) : launch_warp<KIND, MODE, 4, true>(f, r, s, a);
+    if (const int wp = wp_kind) {
+        if (wp == 1) return launch_warp<KIND, MODE, 4, false>(f, r, s, a);
+        int rc = launch_warp<KIND, MODE, 4, true>(f, r, s, a);
         if (rc != LUTGEN_OK) return rc;
         if (nn) return launch_nn_exact<FRONT_LIST>(fl, r, s);
         return launch_rbf_exact_km<KIND < 3 ? KIND : 0, FRONT_LIST>(fl, r, s);
@@ -493,10 +543,10 @@ int launch_fast(const Front& f_in, const lutgen_remapper* r, cudaStream_t s) {
         grid = a.tiles_r * a.tiles_g * tiles_b;
     }
     size_t smem = fast_smem_bytes(a.n, a.ept * FAST_THREADS);
-    static bool attr_done = false;  // one flag per <KIND, MODE> instantiation
-    if (!attr_done) {
+    static bool attr_done[kMaxDevices] = {};  // per <KIND, MODE> instantiation and device
+    if (!attr_done[g.index]) {
         CU_TRY(cudaFuncSetAttribute(k_remap_fast<KIND, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_done = true;
+        attr_done[g.index] = true;
     }
     // persistent CTAs: as many as fit on the device at once, striding over the tiles
     a.ntiles = grid;
@@ -604,10 +654,10 @@ int ensure_blur_volume(const lutgen_remapper* r, uint32_t level, int sequential,
         unsigned rows = size * size;
         unsigned grid_nn = blocks_for(rows, BLUR_ROW_WARPS);
         if (grid_nn > (unsigned)g.sm_count * 8u) grid_nn = (unsigned)g.sm_count * 8u;
-        static bool attr_done = false;
-        if (!attr_done) {
+        static bool attr_done[kMaxDevices] = {};
+        if (!attr_done[g.index]) {
             CU_TRY(blur_set_attributes());
-            attr_done = true;
+            attr_done[g.index] = true;
         }
         const int stage_pal = (size_t)r->n * 28 <= 64 * 1024;   // palette (3 floats) + expanded form (4 floats) per colour
         const size_t smem_nn = 1024 + (stage_pal ? (size_t)r->n * 28 + 32 : 0);
@@ -811,22 +861,10 @@ int lutgen_cuda_device_count(int* count) {
     return LUTGEN_OK;
 }
 
-int lutgen_cuda_init(int device) {
-    std::lock_guard<std::mutex> lk(g.mu);
-    if (device < 0) {
-        const char* e = getenv("LUTGEN_CUDA_DEVICE");
-        if (!e) e = getenv("LOCAL_RANK");
-        device = e ? atoi(e) : 0;
-    }
-    if (g.ready) {
-        if (g.device == device) return LUTGEN_OK;
-        return fail(LUTGEN_ERR_INVALID, "already initialised on device %d (one process drives one GPU)", g.device);
-    }
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n == 0)
-        return fail(LUTGEN_ERR_NO_DEVICE, "no CUDA device: %s", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
-    if (device >= n) return fail(LUTGEN_ERR_NO_DEVICE, "device %d requested but only %d visible", device, n);
+namespace {
+// Everything one GPU needs: streams, colour tables, counters. `g` is the context being set up.
+int init_current_ctx(int device, int visible) {
+    if (device >= visible) return fail(LUTGEN_ERR_NO_DEVICE, "device %d requested but only %d visible", device, visible);
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10)
@@ -836,12 +874,24 @@ int lutgen_cuda_init(int device) {
     g.device = device;
     g.sm_count = prop.multiProcessorCount;
     CU_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    {
+        // stream-ordered allocations (remapper palettes) come from the default pool; never hand memory back at a sync
+        cudaMemPool_t pool;
+        CU_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;
+        CU_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     for (int i = 0; i < kBatchStreams; ++i) CU_TRY(cudaStreamCreateWithFlags(&g.batch_streams[i], cudaStreamNonBlocking));
     ColorTables host;
     for (int i = 0; i < 256; ++i) memcpy(&host.decode[i], &k_srgb_decode_bits[i], 4);
-    for (int i = 0; i < 104; ++i) host.encode[i] = k_srgb_encode_table[i];
+    for (int i = 0; i < 104; ++i) {
+        host.encode[i] = k_srgb_encode_table[i];
+        host.encode2[i] = srgb_encode2_entry(k_srgb_encode_table[i], (uint32_t)i);
+    }
     CU_TRY(cudaMalloc((void**)&g.tables, sizeof(ColorTables)));
     CU_TRY(cudaMemcpy(g.tables, &host, sizeof host, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMalloc((void**)&g.counters, 2 * kCounterPairs * sizeof(uint32_t)));
+    CU_TRY(cudaMemset(g.counters, 0, 2 * kCounterPairs * sizeof(uint32_t)));
     if (getenv("LUTGEN_CUDA_STATS")) {
         CU_TRY(cudaMalloc((void**)&g.stats, 128 * sizeof(uint32_t)));
         CU_TRY(cudaMemset(g.stats, 0, 128 * sizeof(uint32_t)));
@@ -850,9 +900,8 @@ int lutgen_cuda_init(int device) {
     return LUTGEN_OK;
 }
 
-int lutgen_cuda_shutdown(void) {
-    std::lock_guard<std::mutex> lk(g.mu);
-    if (!g.ready) return LUTGEN_OK;
+void release_current_ctx() {
+    if (!g.ready) return;
     cudaSetDevice(g.device);
     cudaDeviceSynchronize();
     g.lut_rgb.release();
@@ -863,7 +912,6 @@ int lutgen_cuda_shutdown(void) {
     g.png_out.release();
     g.png_scratch.release();
     g.extract.release();
-    png_release();
     for (int i = 0; i < kBatchStreams; ++i) {
         g.batch_frames[i].release();
         if (g.batch_streams[i]) cudaStreamDestroy(g.batch_streams[i]);
@@ -871,10 +919,109 @@ int lutgen_cuda_shutdown(void) {
     }
     if (g.tables) cudaFree(g.tables);
     g.tables = nullptr;
+    if (g.counters) cudaFree(g.counters);
+    g.counters = nullptr;
+    if (g.stats) cudaFree(g.stats);
+    g.stats = nullptr;
     if (g.stream) cudaStreamDestroy(g.stream);
     g.stream = nullptr;
     g.ready = false;
     g.device = -1;
+}
+
+std::mutex g_init_mu;
+}  // namespace
+
+int lutgen_cuda_init_devices(const int* devices, int ndevices) {
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    if (!devices || ndevices < 1) return fail(LUTGEN_ERR_INVALID, "no devices given");
+    if (ndevices > kMaxDevices) return fail(LUTGEN_ERR_UNSUPPORTED, "%d devices (limit %d)", ndevices, kMaxDevices);
+    for (int i = 0; i < ndevices; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j] || devices[i] < 0) return fail(LUTGEN_ERR_INVALID, "device list must name distinct, non-negative devices");
+    if (g_ndev > 0) {
+        bool same = g_ndev == ndevices;
+        for (int i = 0; same && i < ndevices; ++i) same = g_ctx[i].device == devices[i];
+        if (same) return LUTGEN_OK;
+        return fail(LUTGEN_ERR_INVALID, "already initialised on %d device(s), the first being device %d (lutgen_cuda_shutdown first)", g_ndev,
+                    g_ctx[0].device);
+    }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(LUTGEN_ERR_NO_DEVICE, "no CUDA device: %s", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    int rc = LUTGEN_OK;
+    for (int i = 0; i < ndevices && rc == LUTGEN_OK; ++i) {
+        Ctx* prev = tl_ctx;
+        tl_ctx = &g_ctx[i];
+        g.index = i;
+        rc = init_current_ctx(devices[i], n);
+        tl_ctx = prev;
+    }
+    if (rc != LUTGEN_OK) {
+        for (int i = 0; i < ndevices; ++i) {
+            Ctx* prev = tl_ctx;
+            tl_ctx = &g_ctx[i];
+            release_current_ctx();
+            tl_ctx = prev;
+        }
+        return rc;
+    }
+    g_ndev = ndevices;
+    cudaSetDevice(g_ctx[0].device);
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_device_count_in_use(int* count) {
+    if (!count) return fail(LUTGEN_ERR_INVALID, "count is NULL");
+    *count = g_ndev;
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_init(int device) {
+    if (device < 0) {
+        // LUTGEN_CUDA_DEVICES=0,1,2,3: this process shards generate_lut / apply_hald_batch over those GPUs (no caller changes)
+        if (const char* list = getenv("LUTGEN_CUDA_DEVICES")) {
+            int devs[kMaxDevices], nd = 0;
+            const char* q = list;
+            while (*q && nd < kMaxDevices) {
+                char* end = nullptr;
+                long v = strtol(q, &end, 10);
+                if (end == q) break;
+                devs[nd++] = (int)v;
+                q = (*end == ',') ? end + 1 : end;
+                if (*end != ',') break;
+            }
+            if (nd > 0) return lutgen_cuda_init_devices(devs, nd);
+        }
+        const char* e = getenv("LUTGEN_CUDA_DEVICE");
+        if (!e) e = getenv("LOCAL_RANK");
+        device = e ? atoi(e) : 0;
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_init_mu);
+        if (g_ndev > 0) {
+            if (g_ctx[0].device == device) return LUTGEN_OK;
+            return fail(LUTGEN_ERR_INVALID, "already initialised with device %d as the primary one", g_ctx[0].device);
+        }
+    }
+    return lutgen_cuda_init_devices(&device, 1);
+}
+
+int lutgen_cuda_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    if (g_ndev == 0) return LUTGEN_OK;
+    {
+        UseCtx u(0);
+        png_release();
+    }
+    for (int i = 0; i < g_ndev; ++i) {
+        Ctx* prev = tl_ctx;
+        tl_ctx = &g_ctx[i];
+        release_current_ctx();
+        tl_ctx = prev;
+    }
+    g_ndev = 0;
     return LUTGEN_OK;
 }
 
@@ -1041,19 +1188,12 @@ int lutgen_cuda_remapper_destroy(lutgen_remapper* r) {
     if (g.ready) {
         cudaSetDevice(g.device);
         cudaDeviceSynchronize();
-        cudaFree(r->pal_rgb4);
-        cudaFree(r->pal_lab);
-        cudaFree(r->pal_ab);
-        cudaFree(r->pal_lab32);
+        if (r->arena) cudaFreeAsync(r->arena, g.stream);   // back to the pool: creating the next remapper costs no cudaMalloc
         cudaFree(r->offsets);
         cudaFree(r->nn_table);
         cudaFree(r->flag_list);
         cudaFree(r->flag_count);
         cudaFree(r->full_table);
-        cudaFree(r->upal_rgb4);
-        cudaFree(r->upal_ab);
-        cudaFree(r->upal_lab32);
-        cudaFree(r->upal_lab);
         if (r->nn_table_ev) cudaEventDestroy(r->nn_table_ev);
         if (r->full_table_ev) cudaEventDestroy(r->full_table_ev);
         cudaFree(r->blur_pal3);
@@ -1112,10 +1252,26 @@ int lutgen_cuda_remapper_create(const lutgen_remapper_desc* desc, lutgen_remappe
         rgb4[4 * i + 1] = r->pal_host[3 * i + 1];
         rgb4[4 * i + 2] = r->pal_host[3 * i + 2];
     }
-    CU_TRY_R(cudaMalloc((void**)&r->pal_rgb4, 4 * na));
-    CU_TRY_R(cudaMalloc((void**)&r->pal_lab, sizeof(double) * 3 * na));
-    CU_TRY_R(cudaMalloc((void**)&r->pal_ab, sizeof(float) * 2 * na));
-    CU_TRY_R(cudaMalloc((void**)&r->pal_lab32, sizeof(float4) * na));
+    // one allocation from the device's stream-ordered pool (kept warm: lutgen_cuda_init sets its release threshold),
+    // carved into the palette arrays -- and a second set for the de-duplicated palette of the NearestNeighbor kinds.
+    // The CLI builds a remapper per invocation (crates/cli/src/main.rs:334-348): construction is on the end-to-end path.
+    {
+        auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+        const size_t per_set = up(4 * na) + up(sizeof(double) * 3 * na) + up(sizeof(float) * 2 * na) + up(sizeof(float4) * na);
+        const bool two = desc->kind == LUTGEN_NEAREST || desc->kind == LUTGEN_SAMPLING;
+        CU_TRY_R(cudaMallocAsync(&r->arena, per_set * (two ? 2 : 1), g.stream));
+        uint8_t* q = (uint8_t*)r->arena;
+        r->pal_rgb4 = q; q += up(4 * na);
+        r->pal_lab = (double*)q; q += up(sizeof(double) * 3 * na);
+        r->pal_ab = (float*)q; q += up(sizeof(float) * 2 * na);
+        r->pal_lab32 = (float4*)q; q += up(sizeof(float4) * na);
+        if (two) {
+            r->upal_rgb4 = q; q += up(4 * na);
+            r->upal_lab = (double*)q; q += up(sizeof(double) * 3 * na);
+            r->upal_ab = (float*)q; q += up(sizeof(float) * 2 * na);
+            r->upal_lab32 = (float4*)q;
+        }
+    }
     CU_TRY_R(cudaMemcpyAsync(r->pal_rgb4, rgb4.data(), 4 * na, cudaMemcpyHostToDevice, g.stream));
     if (n) {
         k_palette_setup<<<blocks_for(n, 128), 128, 0, g.stream>>>(r->pal_rgb4, r->n, desc->lum_factor, g.tables->decode, r->pal_lab, r->pal_ab,
@@ -1173,11 +1329,6 @@ int lutgen_cuda_remapper_create(const lutgen_remapper_desc* desc, lutgen_remappe
             u4.insert(u4.end(), {rgb4[4 * i], rgb4[4 * i + 1], rgb4[4 * i + 2], 0});
         }
         r->un = (uint32_t)seen.size();
-        size_t ua = r->un ? r->un : 1;
-        CU_TRY_R(cudaMalloc((void**)&r->upal_rgb4, 4 * ua));
-        CU_TRY_R(cudaMalloc((void**)&r->upal_lab, sizeof(double) * 3 * ua));
-        CU_TRY_R(cudaMalloc((void**)&r->upal_ab, sizeof(float) * 2 * ua));
-        CU_TRY_R(cudaMalloc((void**)&r->upal_lab32, sizeof(float4) * ua));
         if (r->un) {
             CU_TRY_R(cudaMemcpyAsync(r->upal_rgb4, u4.data(), 4 * (size_t)r->un, cudaMemcpyHostToDevice, g.stream));
             k_palette_setup<<<blocks_for(r->un, 128), 128, 0, g.stream>>>(r->upal_rgb4, r->un, desc->lum_factor, g.tables->decode, r->upal_lab,
@@ -1296,6 +1447,11 @@ int lutgen_cuda_generate_lut_shard_multi_dev(const lutgen_remapper* r, uint8_t l
 
 int lutgen_cuda_generate_lut_shard_mc_dev(const lutgen_remapper* r, uint8_t level, uint8_t* const* luts_rgb_dev, int nluts, uint8_t* multicast_lut,
                                           uint32_t shard_index, uint32_t shard_count, void* stream) {
+    return lutgen_cuda_generate_lut_exchange_dev(r, level, luts_rgb_dev, nluts, multicast_lut, shard_index, shard_count, nullptr, stream);
+}
+
+int lutgen_cuda_generate_lut_exchange_dev(const lutgen_remapper* r, uint8_t level, uint8_t* const* luts_rgb_dev, int nluts, uint8_t* multicast_lut,
+                                          uint32_t shard_index, uint32_t shard_count, unsigned* const* barrier_flags_dev_table, void* stream) {
     int rc = ensure_ready();
     if (rc) return rc;
     if (!r || !luts_rgb_dev || nluts < 1) return fail(LUTGEN_ERR_INVALID, "NULL argument");
@@ -1318,6 +1474,20 @@ int lutgen_cuda_generate_lut_shard_mc_dev(const lutgen_remapper* r, uint8_t leve
     f.shard_index = shard_index;
     f.shard_count = shard_count;
     f.mc = nluts > 1 ? multicast_lut : nullptr;
+    if (barrier_flags_dev_table) {
+        // only k_remap_warp's MULTI variant ends with the barrier: small palettes of the RBF / NearestNeighbor kinds
+        const bool nn = r->d.kind == LUTGEN_NEAREST;
+        const uint32_t n = nn ? r->un : r->n;
+        if (nluts < 2 || shard_count != (uint32_t)nluts || !r->fast_ok || n == 0 || n > (uint32_t)WT_MAX_N || getenv("LUTGEN_CUDA_NO_WARP"))
+            return fail(LUTGEN_ERR_UNSUPPORTED, "in-kernel exchange barrier: needs one shard per destination and a palette of at most %d colours on the warp-tile kernel", WT_MAX_N);
+        if (r->d.kind == LUTGEN_GAUSSIAN) {
+            double C = r->d.param * 1.4426950408889634;
+            if (!(C >= 1e-3 && C <= 2000.0)) return fail(LUTGEN_ERR_UNSUPPORTED, "in-kernel exchange barrier: Gaussian shape outside the warp-tile kernel's range");
+        }
+        f.bar_flags = barrier_flags_dev_table;
+        f.bar_nranks = nluts;
+        f.bar_rank = (int)shard_index;
+    }
     return launch_remap<FRONT_LUT>(f, r, (cudaStream_t)stream);
 }
 

@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(BLUR_ROW_WARPS * 32) k_blur_nn_volume(float* _
             if (stage_palette) {
                 // fast decision
                 const f2 linb = make_float2(lbx, lby);
-                const float pl = fmaf(0.5363325363f, lg, 0.4122214708f * lr), pm = fmaf(0.6806995451f, lg, 0.2119034982f * lr),
-                            ps = fmaf(0.2817188376f, lg, 0.0883024619f * lr);
+                const float pl = fmaf(0.5363325363f, lg, 0.4122214708f * lr) + LMS_FLOOR, pm = fmaf(0.6806995451f, lg, 0.2119034982f * lr) + LMS_FLOOR,
+                            ps = fmaf(0.2817188376f, lg, 0.0883024619f * lr) + LMS_FLOOR;
                 f2 L, A, B;
                 lms_to_lab2(fma2(splat(0.0514459929f), linb, splat(pl)), fma2(splat(0.1073969566f), linb, splat(pm)),
                             fma2(splat(0.6299787005f), linb, splat(ps)), lum, L, A, B);
@@ -393,9 +393,9 @@ __global__ void __launch_bounds__(256) k_blur_to_lut(const float* __restrict__ c
         float r, gg, b;
         oklab_to_linear_exact(o, r, gg, b);
         uint8_t* q = out_rgb + 3ull * px;
-        q[0] = (uint8_t)f32_to_srgb8(r, st.encode);
-        q[1] = (uint8_t)f32_to_srgb8(gg, st.encode);
-        q[2] = (uint8_t)f32_to_srgb8(b, st.encode);
+        q[0] = (uint8_t)f32_to_srgb8(r, st.encode2);
+        q[1] = (uint8_t)f32_to_srgb8(gg, st.encode2);
+        q[2] = (uint8_t)f32_to_srgb8(b, st.encode2);
     }
 }
 

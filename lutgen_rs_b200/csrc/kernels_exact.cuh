@@ -46,7 +46,15 @@ struct Front {
     uint32_t shard_index, shard_count;
     // GaussianBlurRemapper only: generate_lut_inner's hint chain across rows instead of par_generate_lut_inner's
     int sequential;
+    // FRONT_LUT, k_remap_warp only: the exchange's barrier, done by the kernel's last CTA once every CTA's stores to
+    // the peers are out. bar_flags: DEVICE table of bar_nranks pointers, entry i = rank i's flag array
+    // (LUTGEN_BAR_WORDS u32, zero at the start, mapped into this process): slot t < 8 is written by rank t with
+    // rank t's step number, word LUTGEN_BAR_EPOCH is the owner's own step counter. bar_nranks = 0: no barrier.
+    unsigned* const* bar_flags;
+    int bar_nranks, bar_rank;
 };
+constexpr int LUTGEN_BAR_EPOCH = 8;
+constexpr int LUTGEN_BAR_WORDS = 16;
 
 struct RemapParams {
     const double* pal_lab;  // N x 3: [l*lum, a, b], f32 Oklab widened (rbf.rs:29-35)
@@ -203,7 +211,7 @@ __global__ void __launch_bounds__(256) k_nn_exact(Front f, RemapParams P, const 
             Lab o = {c.l, P.pal_ab[2 * best], P.pal_ab[2 * best + 1]};
             float r, g, b;
             oklab_to_linear_exact(o, r, g, b);
-            front_store<MODE>(f, px, f32_to_srgb8(r, st.encode), f32_to_srgb8(g, st.encode), f32_to_srgb8(b, st.encode));
+            front_store<MODE>(f, px, f32_to_srgb8(r, st.encode2), f32_to_srgb8(g, st.encode2), f32_to_srgb8(b, st.encode2));
         }
     }
 }
@@ -346,7 +354,7 @@ __device__ __forceinline__ void rbf_exact_one(const Front& f, const RemapParams&
     o.b = __double2float_rn(__ddiv_rn(n2, den));
     float r, g, b;
     oklab_to_linear_exact(o, r, g, b);
-    front_store<MODE>(f, px, f32_to_srgb8(r, st.encode), f32_to_srgb8(g, st.encode), f32_to_srgb8(b, st.encode));
+    front_store<MODE>(f, px, f32_to_srgb8(r, st.encode2), f32_to_srgb8(g, st.encode2), f32_to_srgb8(b, st.encode2));
 }
 
 template <int KIND, int MODE>
@@ -371,9 +379,9 @@ __global__ void k_oklab_to_srgb(const float* __restrict__ lab, size_t n, uint8_t
     Lab c = {lab[3 * i], lab[3 * i + 1], lab[3 * i + 2]};
     float r, g, b;
     oklab_to_linear_exact(c, r, g, b);
-    out[3 * i] = (uint8_t)f32_to_srgb8(r, tables->encode);
-    out[3 * i + 1] = (uint8_t)f32_to_srgb8(g, tables->encode);
-    out[3 * i + 2] = (uint8_t)f32_to_srgb8(b, tables->encode);
+    out[3 * i] = (uint8_t)f32_to_srgb8(r, tables->encode2);
+    out[3 * i + 1] = (uint8_t)f32_to_srgb8(g, tables->encode2);
+    out[3 * i + 2] = (uint8_t)f32_to_srgb8(b, tables->encode2);
 }
 
 }  // namespace lutgen

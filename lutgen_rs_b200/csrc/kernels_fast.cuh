@@ -664,7 +664,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_remap_fast(const FastArgs a
                     Lab o = {ex.l, a.pal_ab[2 * idx], a.pal_ab[2 * idx + 1]};
                     float r, g, b;
                     oklab_to_linear_exact(o, r, g, b);
-                    front_store<MODE>(a.f, px, f32_to_srgb8(r, st.encode), f32_to_srgb8(g, st.encode), f32_to_srgb8(b, st.encode));
+                    front_store<MODE>(a.f, px, f32_to_srgb8(r, st.encode2), f32_to_srgb8(g, st.encode2), f32_to_srgb8(b, st.encode2));
                 }
                 continue;
             }
@@ -711,7 +711,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_remap_fast(const FastArgs a
             o.b = n2 * inv;
             float r, g, b;
             oklab_to_linear_fast(o, r, g, b);
-            front_store<MODE>(a.f, px, f32_to_srgb8(r, st.encode), f32_to_srgb8(g, st.encode), f32_to_srgb8(b, st.encode));
+            front_store<MODE>(a.f, px, f32_to_srgb8(r, st.encode2), f32_to_srgb8(g, st.encode2), f32_to_srgb8(b, st.encode2));
         }
         bid = next_bid;
     }
@@ -731,9 +731,9 @@ __global__ void k_srgb_to_oklab_fast(const uint8_t* __restrict__ rgb, size_t n, 
     const f2 r = make_float2(tables->decode[rgb[3 * i]], tables->decode[rgb[3 * i + 3]]);
     const f2 g = make_float2(tables->decode[rgb[3 * i + 1]], tables->decode[rgb[3 * i + 4]]);
     const f2 b = make_float2(tables->decode[rgb[3 * i + 2]], tables->decode[rgb[3 * i + 5]]);
-    const f2 pl = fma2(splat(0.5363325363f), g, mul2(splat(0.4122214708f), r));
-    const f2 pm = fma2(splat(0.6806995451f), g, mul2(splat(0.2119034982f), r));
-    const f2 ps = fma2(splat(0.2817188376f), g, mul2(splat(0.0883024619f), r));
+    const f2 pl = fma2(splat(0.5363325363f), g, fma2(splat(0.4122214708f), r, splat(LMS_FLOOR)));
+    const f2 pm = fma2(splat(0.6806995451f), g, fma2(splat(0.2119034982f), r, splat(LMS_FLOOR)));
+    const f2 ps = fma2(splat(0.2817188376f), g, fma2(splat(0.0883024619f), r, splat(LMS_FLOOR)));
     f2 L, A, B;
     lms_to_lab2(fma2(splat(0.0514459929f), b, pl), fma2(splat(0.1073969566f), b, pm), fma2(splat(0.6299787005f), b, ps), 1.0f, L, A, B);
     out[3 * i] = L.x; out[3 * i + 1] = A.x; out[3 * i + 2] = B.x;

@@ -19,10 +19,14 @@
 //                 UNCERTAIN, negligible colours dropped, "moot" tiles take every colour).
 //   accumulate  : the candidate list is walked once for the lane's EPT entries together (one
 //                 broadcast LDS.128 serves all of them).
-//   Gaussian    : the list holds q = (-2C p, C(|p|^2 - lbmin)), C = shape*log2(e), so that
-//                 s = C(d - lbmin) = q.xyz . c + q.w + C|c|^2 costs 3 FFMA2 + 1 FADD2 per pair,
-//                 w = ex2(-s), and the sums run over q.xyz (-2C is divided out once per entry).
-//   NN          : the same expansion ranks by d - |c|^2.
+//   centred     : everything per entry is relative to the centre m of the tile's Oklab box: an entry is
+//                 delta = c - m, a listed colour is p - m (small numbers: the expansion below loses no
+//                 precision to |c|^2, and needs no per-entry constant).
+//   Gaussian    : the list holds q = (-2C (p - m), C(|p - m|^2 - lbmin)), C = shape*log2(e), so that
+//                 s = C(d - lbmin - |delta|^2) = q.xyz . delta + q.w costs 3 FFMA2 per pair (|delta|^2 is
+//                 common to all colours of an entry: it cancels in num / den and in every comparison),
+//                 w = ex2(-s), and the sums run over q.xyz (-2C is divided out and m added once per entry).
+//   NN          : the same expansion ranks by d - |delta|^2.
 //   near-ties   : as in kernels_fast.cuh every decision closer than the f32 error bound (here a
 //                 per-tile constant) sends the entry to the exact f64 kernel's work list.
 //
@@ -30,6 +34,8 @@
 // kernel body at once. Everything rare or repeated per entry (selection networks, flagging) is out
 // of line, and loops that would unroll into kilobytes are kept rolled.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "kernels_fast.cuh"
 
 namespace lutgen {
@@ -54,6 +60,8 @@ struct WarpArgs {
     int preserve;
     float lum, inv_lum;
     float c1;                 // weight slope (kernels_fast.cuh header)
+    float rank_scale;         // squared distances times this fit fp16 with room to spare (k_remap_warp's rank counting)
+    int whole_tiles;          // brick front ends: no tile of the launch is cut by the cube's edge or by the range
     uint32_t tiles_r, tiles_g;
     float inv_tiles_r, inv_tiles_g;
     uint32_t b_lo;            // first blue plane covered (multiple of EPT)
@@ -61,15 +69,23 @@ struct WarpArgs {
     uint32_t ntiles_global;   // tiles of the whole range
     uint32_t shard_index, shard_count;  // this launch takes hand-outs index, index + count, ... (1 hand-out = `batch` warp tiles / 1 CTA tile)
     uint32_t batch;           // warp tiles per hand-out: WT_BATCH, or 1 when the range has too few tiles to fill the GPU otherwise
+    uint32_t tail_cut, ticket_end;   // k_remap_warp: single-tile hand-outs from ticket tail_cut on; tickets end at ticket_end
     uint32_t* flag_list;
     uint32_t* flag_count;
-    uint32_t* tile_counter;   // zeroed before the launch
+    uint32_t* tile_counter;   // zero at launch; k_remap_warp's last CTA zeroes it (and done_counter) again
+    uint32_t* done_counter;   // CTAs that have finished (k_remap_warp)
     uint32_t* stats;
     const ColorTables* tables;
+    // the reference's f64 arithmetic for entries the f32 path cannot decide (wt_exact_entry)
+    const double* pal64;      // n x 3: (l*lum, a, b), the f32 Oklab triple widened (rbf.rs:29-35)
+    double lum64, param64;
     int words_ok;             // FRONT_LUT, cs % 4 == 0: 1 = destinations 4-byte aligned (whole tiles leave as words),
                               // 2 = 16-byte aligned (whole hand-outs leave as 16-byte pieces), 0 = byte stores
 };
 
+__device__ __forceinline__ __half2 u32_as_half2(uint32_t v) {
+    return *reinterpret_cast<const __half2*>(&v);
+}
 __device__ __forceinline__ float rcp_approx(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -91,14 +107,13 @@ __device__ __forceinline__ void oklab_to_linear2(f2 L, f2 A, f2 B, f2& r, f2& g,
     b = fma2(splat(-0.0041960863f), l, fma2(splat(-0.7034186147f), m, mul2(splat(1.7076147010f), s)));
 }
 
-// Score of candidate q for two entries (smaller = nearer):
-//   Gaussian   C (d - lbmin)  = q.xyz . c + (q.w + C |c|^2)            (cc = C |c|^2)
-//   NN         d - |c|^2      = q.xyz . c + q.w
+// Score of candidate q for two entries (smaller = nearer); L, A, B are the entries' offsets from the tile centre:
+//   Gaussian   C (d - lbmin - |delta|^2)  = q.xyz . delta + q.w
+//   NN         d - |delta|^2              = q.xyz . delta + q.w
 //   Shepard / Linear  d       (differences: small distances keep their relative precision)
 template <int KIND>
-__device__ __forceinline__ f2 wt_score2(float4 q, f2 L, f2 A, f2 B, f2 cc) {
-    if (KIND == 0) return fma2(splat(q.x), L, fma2(splat(q.y), A, fma2(splat(q.z), B, add2(splat(q.w), cc))));
-    if (KIND == KIND_NN) return fma2(splat(q.x), L, fma2(splat(q.y), A, fma2(splat(q.z), B, splat(q.w))));
+__device__ __forceinline__ f2 wt_score2(float4 q, f2 L, f2 A, f2 B) {
+    if (KIND == 0 || KIND == KIND_NN) return fma2(splat(q.x), L, fma2(splat(q.y), A, fma2(splat(q.z), B, splat(q.w))));
     f2 dx = fma2(splat(q.x), splat(-1.0f), L), dy = fma2(splat(q.y), splat(-1.0f), A), dz = fma2(splat(q.z), splat(-1.0f), B);
     return fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
 }
@@ -112,82 +127,110 @@ __device__ __forceinline__ f2 wt_weight2(f2 s, float c1, float c0) {
     return s;
 }
 
-// Optimal sorting networks for 4 and 8 keys (5 and 19 compare-exchanges), bitonic beyond.
-__device__ __forceinline__ void cswap(float& a, float& b) {
-    float lo = fminf(a, b), hi = fmaxf(a, b);
-    a = lo; b = hi;
-}
-template <int M>
-__device__ __forceinline__ void wt_sort(float (&v)[M]) {
-    if constexpr (M == 4) {
-        cswap(v[0], v[1]); cswap(v[2], v[3]); cswap(v[0], v[2]); cswap(v[1], v[3]); cswap(v[1], v[2]);
-    } else if constexpr (M == 8) {
-        cswap(v[0], v[1]); cswap(v[2], v[3]); cswap(v[4], v[5]); cswap(v[6], v[7]);
-        cswap(v[0], v[2]); cswap(v[1], v[3]); cswap(v[4], v[6]); cswap(v[5], v[7]);
-        cswap(v[1], v[2]); cswap(v[5], v[6]); cswap(v[0], v[4]); cswap(v[3], v[7]);
-        cswap(v[1], v[5]); cswap(v[2], v[6]);
-        cswap(v[1], v[4]); cswap(v[3], v[6]);
-        cswap(v[2], v[4]); cswap(v[3], v[5]);
-        cswap(v[3], v[4]);
-    } else {
-        bitonic_sort<M>(v);
-    }
-}
-
 struct PairAcc {
     f2 n0, n1, n2, den;
-    uint32_t risky;  // bit 0: first entry of the pair, bit 1: second
+    f2 tau, nxt;     // kp-th and (kp+1)-th smallest score of each entry (meaningful where a tie bit is set)
+    uint32_t risky;  // bits 0, 1: near-tie at the k-boundary (first / second entry of the pair; wt_resolve_tie settles it);
+                     // bits 2, 3: the selection itself gave up (the entry needs the reference's arithmetic throughout)
 };
 
-// kp-th and (kp+1)-th smallest of the first mU of `sc` (component C of each pair).
-template <int M, int C>
-__device__ __forceinline__ void wt_threshold(const f2 (&sc)[M], int mU, int kp, float& tau, float& nxt) {
-    float s[M];
+// ---- choosing among the uncertain colours: kp of mU (0 < kp < mU) ------------------------------------
+// With a palette of a few dozen colours the choice is nearly always lopsided (measured on the headline CLUT:
+// one colour to take or to leave out in 61 % of the choosing tiles, two in 29 %, three in 8 %):
+//   from below : the c = kp smallest scores are the chosen ones; their weights are added afterwards
+//   from above : the c = mU - kp largest are the ones left out; the caller's direct loop has added every
+//                uncertain colour, theirs are subtracted afterwards (Gaussian and Shepard weights fall with the
+//                distance, so what is subtracted is the smallest part of the sum; Linear, whose weights grow,
+//                never comes here)
+// One rolled pass over the list keeps the c + 1 smallest scores (or negated scores) per entry -- an insertion
+// of 2c + 1 FMNMX -- each carrying its list position in four mantissa bits, and m[c] - m[c-1] is the gap the
+// near-tie test looks at. Three small loops where the sorting networks this replaces were 900 instructions:
+// warps run free of each other, so the kernel's working set of code has to fit the SM's 32 KB instruction
+// cache -- beyond it 'no instruction' was 47 % of the stall samples.
+constexpr int WT_TRACK = 6;   // c <= WT_TRACK - 1
+
+template <int D>
+__device__ __forceinline__ void wt_track(float (&m)[D], float v) {   // keep the D smallest, ascending
+    float t[D];
 #pragma unroll
-    for (int i = 0; i < M; ++i) s[i] = i < mU ? (C == 0 ? sc[i].x : sc[i].y) : INFINITY;
-    wt_sort<M>(s);
-    tau = s[0];
-    nxt = s[M - 1];
-    pick_threshold<M>(s, kp, tau, nxt);
+    for (int i = 0; i + 1 < D; ++i) t[i] = fmaxf(m[i], v);
+    m[0] = fminf(m[0], v);
+#pragma unroll
+    for (int i = 1; i < D; ++i) m[i] = fminf(m[i], t[i - 1]);
 }
 
-// Choose the kp nearest of mU (kp < mU <= M) uncertain colours for the two entries of a pair and
-// accumulate them.
-template <int M, int KIND>
-__device__ __forceinline__ PairAcc wt_select(const float4* __restrict__ unc, int mU, int kp, f2 L, f2 A, f2 B, f2 cc, float c1, float c0, float tol) {
-    f2 sc[M];
-#pragma unroll
-    for (int i = 0; i < M; ++i) sc[i] = i < mU ? wt_score2<KIND>(unc[i], L, A, B, cc) : splat(INFINITY);
-    float tau0, nxt0, tau1, nxt1;
-    wt_threshold<M, 0>(sc, mU, kp, tau0, nxt0);
-    wt_threshold<M, 1>(sc, mU, kp, tau1, nxt1);
+// Weight of the tagged score's colour into one entry's sums (sign = -1: taken out again). The weight is taken
+// from the tagged score itself: the tag is at most 16 ulp of the score.
+template <int KIND>
+__device__ __forceinline__ void wt_add_one(const float4* __restrict__ unc, float tagged, float sign, float c1, float c0, float& n0, float& n1,
+                                           float& n2, float& den) {
+    const float4 q = unc[__float_as_uint(tagged) & 15u];
+    const float w = sign * wt_weight2<KIND>(splat(sign * tagged), c1, c0).x;
+    n0 = fmaf(q.x, w, n0); n1 = fmaf(q.y, w, n1); n2 = fmaf(q.z, w, n2); den += w;
+}
+
+// mU <= 16, c = C <= WT_TRACK - 1; top: C counts the colours left out (see above).
+template <int KIND, int C>
+__device__ __forceinline__ PairAcc wt_select_c(const float4* __restrict__ unc, int mU, bool top, f2 L, f2 A, f2 B, float c1, float c0, float tol) {
     PairAcc r;
     r.n0 = r.n1 = r.n2 = r.den = splat(0.f);
+    float mx[C + 1], my[C + 1];
 #pragma unroll
-    for (int i = 0; i < M; ++i) {
-        if (i < mU) {
-            float4 q = unc[i];
-            f2 w = wt_weight2<KIND>(sc[i], c1, c0);
-            w.x = sc[i].x <= tau0 ? w.x : 0.0f;
-            w.y = sc[i].y <= tau1 ? w.y : 0.0f;
+    for (int t = 0; t <= C; ++t) mx[t] = my[t] = INFINITY;
+    const float sgn = top ? -1.0f : 1.0f;
+#pragma unroll 1
+    for (int i = 0; i < mU; ++i) {
+        const f2 sg = mul2(wt_score2<KIND>(unc[i], L, A, B), splat(sgn));
+        wt_track<C + 1>(mx, __uint_as_float((__float_as_uint(sg.x) & ~15u) | (uint32_t)i));
+        wt_track<C + 1>(my, __uint_as_float((__float_as_uint(sg.y) & ~15u) | (uint32_t)i));
+    }
+    // the boundary lies between the C-th and the (C+1)-th tracked score; the tags cost up to 16 ulp of each
+    r.risky = (((mx[C] - mx[C - 1] <= fmaf(fabsf(mx[C]), 4e-6f, tol)) && (mx[C] < INFINITY)) ? 1u : 0u) |
+              (((my[C] - my[C - 1] <= fmaf(fabsf(my[C]), 4e-6f, tol)) && (my[C] < INFINITY)) ? 2u : 0u);
+    r.tau = top ? make_float2(-mx[C], -my[C]) : make_float2(mx[C - 1], my[C - 1]);
+    r.nxt = top ? make_float2(-mx[C - 1], -my[C - 1]) : make_float2(mx[C], my[C]);
+    if constexpr (C <= 2) {
+#pragma unroll
+        for (int t = 0; t < C; ++t) {
+            wt_add_one<KIND>(unc, mx[t], sgn, c1, c0, r.n0.x, r.n1.x, r.n2.x, r.den.x);
+            wt_add_one<KIND>(unc, my[t], sgn, c1, c0, r.n0.y, r.n1.y, r.n2.y, r.den.y);
+        }
+    } else {
+        // three to five (11 % of the choosing tiles): a second rolled pass, every colour whose tagged score is at most the C-th
+#pragma unroll 1
+        for (int i = 0; i < mU; ++i) {
+            const float4 q = unc[i];
+            const f2 sc = wt_score2<KIND>(q, L, A, B);
+            const f2 sg = mul2(sc, splat(sgn));
+            f2 w = mul2(wt_weight2<KIND>(sc, c1, c0), splat(sgn));
+            w.x = __uint_as_float((__float_as_uint(sg.x) & ~15u) | (uint32_t)i) <= mx[C - 1] ? w.x : 0.f;
+            w.y = __uint_as_float((__float_as_uint(sg.y) & ~15u) | (uint32_t)i) <= my[C - 1] ? w.y : 0.f;
             r.n0 = fma2(splat(q.x), w, r.n0);
             r.n1 = fma2(splat(q.y), w, r.n1);
             r.n2 = fma2(splat(q.z), w, r.n2);
             r.den = add2(r.den, w);
         }
     }
-    r.risky = (((nxt0 - tau0 <= tol) && (nxt0 < INFINITY)) ? 1u : 0u) | (((nxt1 - tau1 <= tol) && (nxt1 < INFINITY)) ? 2u : 0u);
     return r;
 }
 
-// More than 16 uncertain colours (rare with warp tiles): per entry, one pass keeping the kp + 1
-// best scores sorted in a small local array.
 template <int KIND>
-__device__ __forceinline__ PairAcc wt_select_insert(const float4* __restrict__ unc, int mU, int kp, f2 L, f2 A, f2 B, f2 cc, float c1, float c0,
-                                                    float tol) {
+__device__ __forceinline__ PairAcc wt_select_small(const float4* __restrict__ unc, int mU, int c, bool top, f2 L, f2 A, f2 B, float c1, float c0,
+                                                   float tol) {
+    if (c == 1) return wt_select_c<KIND, 1>(unc, mU, top, L, A, B, c1, c0, tol);
+    if (c == 2) return wt_select_c<KIND, 2>(unc, mU, top, L, A, B, c1, c0, tol);
+    if (c == 3) return wt_select_c<KIND, 3>(unc, mU, top, L, A, B, c1, c0, tol);
+    if (c == 4) return wt_select_c<KIND, 4>(unc, mU, top, L, A, B, c1, c0, tol);
+    return wt_select_c<KIND, 5>(unc, mU, top, L, A, B, c1, c0, tol);
+}
+
+// Anything else (more than 16 uncertain colours, or neither side of the choice is small): per entry, one pass
+// keeping the kp + 1 best scores sorted in a small local array. Rare with warp tiles; out of line.
+template <int KIND>
+__device__ __noinline__ PairAcc wt_select_insert(const float4* __restrict__ unc, int mU, int kp, f2 L, f2 A, f2 B, float c1, float c0, float tol) {
     constexpr int CAP = 33;
     PairAcc r;
-    r.n0 = r.n1 = r.n2 = r.den = splat(0.f);
+    r.n0 = r.n1 = r.n2 = r.den = r.tau = r.nxt = splat(0.f);
     r.risky = 0;
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
@@ -196,7 +239,7 @@ __device__ __forceinline__ PairAcc wt_select_insert(const float4* __restrict__ u
         const int keep = kp + 1;
         int cnt = 0;
         for (int j = 0; j < mU; ++j) {
-            f2 s2 = wt_score2<KIND>(unc[j], L, A, B, cc);
+            f2 s2 = wt_score2<KIND>(unc[j], L, A, B);
             float d = half ? s2.y : s2.x;
             if (cnt < keep || d < td[cnt - 1]) {
                 int i = cnt < keep ? cnt : keep - 1;
@@ -210,7 +253,7 @@ __device__ __forceinline__ PairAcc wt_select_insert(const float4* __restrict__ u
                 if (cnt < keep) ++cnt;
             }
         }
-        if (cnt < keep) { r.risky |= 1u << half; continue; }
+        if (cnt < keep) { r.risky |= 4u << half; continue; }
         float n0 = 0.f, n1 = 0.f, n2 = 0.f, den = 0.f;
         for (int i = 0; i < kp; ++i) {
             float4 q = unc[tj[i]];
@@ -220,22 +263,127 @@ __device__ __forceinline__ PairAcc wt_select_insert(const float4* __restrict__ u
             n2 = fmaf(q.z, w2.x, n2);
             den += w2.x;
         }
-        if (td[kp] - td[kp - 1] <= tol) r.risky |= 1u << half;
+        if (td[kp] - td[kp - 1] <= tol) {
+            // a near-tie: wt_resolve_tie settles it when the list positions fit its band keys, else the whole entry is redone
+            if (mU <= 256) { r.risky |= 1u << half; if (half) { r.tau.y = td[kp - 1]; r.nxt.y = td[kp]; } else { r.tau.x = td[kp - 1]; r.nxt.x = td[kp]; } }
+            else r.risky |= 4u << half;
+        }
         if (half) { r.n0.y = n0; r.n1.y = n1; r.n2.y = n2; r.den.y = den; }
         else { r.n0.x = n0; r.n1.x = n1; r.n2.x = n2; r.den.x = den; }
     }
     return r;
 }
 
-// One call site per pair of entries; the bucket (4 / 8 / 16 / more) is chosen inside. Out of line:
-// a copy of every network per pair made the kernel 100 KB of SASS, and warps that run free of each
-// other then spend their time waiting for instruction fetch.
+// ---- near-ties at the k-boundary, settled by the lane that met them ---------------------------------
+// The f32 scores of two uncertain colours are closer than their error bound: which of them the reference
+// takes depends on its own arithmetic -- f32 Oklab with a correctly rounded cube root, widened, squared
+// distances in f64 in kiddo's fold order (rbf.rs:59-63, 85-97; nearest_neighbor.rs:47-48). Only the ORDER
+// is in doubt, so only the distances of the colours inside the doubtful band are recomputed that way; the
+// weights of whatever is chosen stay f32 like every other entry's. About 300 instructions for one lane,
+// where the f64 weights, sums and divisions of wt_exact_entry are 1600 for the whole warp -- executed for
+// 0.13 % of the entries, those evicted the hot loop from the instruction cache (0.30 -> 0.44 ms).
+//   certain : s_i <  tau - tol          (tau = kp-th smallest score, nxt = the next one)
+//   band    : tau - tol <= s_i <= nxt + tol   -> the kp - |certain| nearest by (f64 distance, palette index)
+// A score is within tol / 2 of its true value, so a colour below the band is nearer than at least
+// mU - kp others and one above it farther than at least kp + 1 -- whatever the order inside the band.
+// False: the band holds more than WT_BAND colours (the caller falls back to the full f64 evaluation).
+constexpr int WT_BAND = 4;
+
+// linear_to_oklab_exact with ONE out-of-line copy of the correctly rounded cube root (the resolvers run rarely, but often
+// enough that their code competes with the hot loop for the instruction cache: three inlined copies were 140 instructions).
+__device__ __noinline__ float wt_cbrt_cr(float x) { return cbrtf_cr(x); }
+__device__ __forceinline__ void wt_exact_colour(const float* __restrict__ decode, uint32_t rgb, double lum64, double (&e)[3]) {
+    const float r = decode[rgb & 255u], g = decode[(rgb >> 8) & 255u], b = decode[rgb >> 16];
+    const float l = __fadd_rn(__fadd_rn(__fmul_rn(0.4122214708f, r), __fmul_rn(0.5363325363f, g)), __fmul_rn(0.0514459929f, b));
+    const float m = __fadd_rn(__fadd_rn(__fmul_rn(0.2119034982f, r), __fmul_rn(0.6806995451f, g)), __fmul_rn(0.1073969566f, b));
+    const float s = __fadd_rn(__fadd_rn(__fmul_rn(0.0883024619f, r), __fmul_rn(0.2817188376f, g)), __fmul_rn(0.6299787005f, b));
+    const float l_ = wt_cbrt_cr(l), m_ = wt_cbrt_cr(m), s_ = wt_cbrt_cr(s);
+    const float ol = __fsub_rn(__fadd_rn(__fmul_rn(0.2104542553f, l_), __fmul_rn(0.7936177850f, m_)), __fmul_rn(0.0040720468f, s_));
+    const float oa = __fadd_rn(__fsub_rn(__fmul_rn(1.9779984951f, l_), __fmul_rn(2.4285922050f, m_)), __fmul_rn(0.4505937099f, s_));
+    const float ob = __fsub_rn(__fadd_rn(__fmul_rn(0.0259040371f, l_), __fmul_rn(0.7827717662f, m_)), __fmul_rn(0.8086757660f, s_));
+    e[0] = __dmul_rn((double)ol, lum64);
+    e[1] = (double)oa;
+    e[2] = (double)ob;
+}
+
+// out: the uncertain colours' part of the entry's sums in the convention of the selection that met the tie --
+// the chosen ones added (from below), or the ones not chosen subtracted (from above: the direct loop has added all).
 template <int KIND>
-__device__ __noinline__ PairAcc wt_select_any(const float4* __restrict__ unc, int mU, int kp, f2 L, f2 A, f2 B, f2 cc, float c1, float c0, float tol) {
-    if (mU <= 4) return wt_select<4, KIND>(unc, mU, kp, L, A, B, cc, c1, c0, tol);
-    if (mU <= 8) return wt_select<8, KIND>(unc, mU, kp, L, A, B, cc, c1, c0, tol);
-    if (mU <= 16) return wt_select<16, KIND>(unc, mU, kp, L, A, B, cc, c1, c0, tol);
-    return wt_select_insert<KIND>(unc, mU, kp, L, A, B, cc, c1, c0, tol);
+__device__ __noinline__ bool wt_resolve_tie(const double* __restrict__ pal64, double lum64, const float* __restrict__ decode,
+                                            const float4* __restrict__ unc, const uint32_t* __restrict__ uidx, int mU, int kp, bool top, uint32_t rgb,
+                                            float L, float A, float B, float c1, float c0, float tau, float nxt, float tol, float4& out) {
+    if (mU > 32) return false;
+    double e[3];
+    wt_exact_colour(decode, rgb, lum64, e);
+    const float lo = tau - tol, hi = nxt + tol;
+    // the band, ascending by (f64 distance, palette index), in registers: every index below is static
+    double bd[WT_BAND];
+    uint32_t bk[WT_BAND];   // palette index << 8 | list position
+#pragma unroll
+    for (int t = 0; t < WT_BAND; ++t) { bd[t] = INFINITY; bk[t] = 0xffffffffu; }
+    int nb = 0, certain = 0;
+#pragma unroll 1
+    for (int i = 0; i < mU; ++i) {
+        const float sc = wt_score2<KIND>(unc[i], splat(L), splat(A), splat(B)).x;
+        if (sc < lo) ++certain;
+        else if (sc <= hi) {
+            if (nb == WT_BAND) return false;
+            ++nb;
+            const uint32_t j = uidx[i];
+            double d = sq_dist_exact(e[0], e[1], e[2], pal64 + 3 * j);
+            uint32_t key = (j << 8) | (uint32_t)i;
+#pragma unroll
+            for (int t = 0; t < WT_BAND; ++t) {
+                const bool before = d < bd[t] || (d == bd[t] && key < bk[t]);
+                const double td = bd[t];
+                const uint32_t tk = bk[t];
+                bd[t] = before ? d : td;
+                bk[t] = before ? key : tk;
+                d = before ? td : d;
+                key = before ? tk : key;
+            }
+        }
+    }
+    const int need = kp - certain;
+    uint32_t chosen = 0;   // by list position
+#pragma unroll
+    for (int t = 0; t < WT_BAND; ++t)
+        if (t < need && t < nb) chosen |= 1u << (bk[t] & 255u);
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f, den = 0.f;
+#pragma unroll 1
+    for (int i = 0; i < mU; ++i) {
+        const float4 q = unc[i];
+        const float sc = wt_score2<KIND>(q, splat(L), splat(A), splat(B)).x;
+        const bool in_set = sc < lo || ((chosen >> i) & 1u);
+        if (in_set != top) {
+            float w = wt_weight2<KIND>(splat(sc), c1, c0).x;
+            w = top ? -w : w;
+            n0 = fmaf(q.x, w, n0); n1 = fmaf(q.y, w, n1); n2 = fmaf(q.z, w, n2); den += w;
+        }
+    }
+    out = make_float4(n0, n1, n2, den);
+    return true;
+}
+
+// NearestNeighbor: the colours whose score is within tol of the best one, by (f64 distance, palette index);
+// returns the list position of the winner (nearest_neighbor.rs:48: kiddo's nearest_one, first minimum).
+__device__ __noinline__ uint32_t wt_resolve_tie_nn(const double* __restrict__ pal64, double lum64, const float* __restrict__ decode,
+                                                   const float4* __restrict__ cand, const uint32_t* __restrict__ cidx, uint32_t ncand, uint32_t rgb,
+                                                   float L, float A, float B, float best, float tol) {
+    double e[3];
+    wt_exact_colour(decode, rgb, lum64, e);
+    double bd = INFINITY;
+    uint32_t bj = 0xffffffffu, bpos = 0;
+#pragma unroll 1
+    for (uint32_t i = 0; i < ncand; ++i) {
+        const float sc = wt_score2<KIND_NN>(cand[i], splat(L), splat(A), splat(B)).x;
+        if (sc <= best + tol) {
+            const uint32_t j = cidx[i];
+            const double d = sq_dist_exact(e[0], e[1], e[2], pal64 + 3 * j);
+            if (d < bd || (d == bd && j < bj)) { bd = d; bj = j; bpos = i; }
+        }
+    }
+    return bpos;
 }
 
 // Entries (bits of `mask`) this lane hands to the exact kernel. Out of line and rare.
@@ -247,6 +395,126 @@ __device__ __noinline__ void wt_flag_mask(uint32_t* flag_count, uint32_t* flag_l
         uint32_t pos = atomicAdd(flag_count, 1u);
         flag_list[pos] = slot0 + e * slot_step;
         if (stats) atomicAdd(&stats[127], 1u);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One colour in the reference's own arithmetic, by the whole warp (palettes of at most 32 colours:
+// lane j owns palette colour j). This is what k_rbf_exact / k_nn_exact do with one thread per colour
+// in a second launch over a work list; here the warp that met the undecidable entry resolves it on the
+// spot, so the result leaves with the rest of its tile (one kernel, no list, no second pass whose
+// few thousand serial threads were 6 % of the step). r, g, b are warp uniform.
+//   rbf.rs:57-111: f32 Oklab (no contraction, correctly rounded cube root), widened; palette.contains;
+//   squared distances in kiddo's fold order; the k nearest by (distance, index); weights and sums in
+//   f64, ascending distance; division, casts and the conversion back as the Rust does them.
+//   nearest_neighbor.rs:46-61: first minimum in palette order.
+// Returns r | g<<8 | b<<16; bit 31 set: the colour is a palette colour (rbf.rs:66: left as it is).
+// `scratch`: 32 x 4 doubles of this warp.
+struct WtExactArgs {   // by value: a reference to the kernel's parameter block would have it copied to the stack
+    const double* pal64;
+    const uint32_t* pal_rgb;
+    const float* pal_ab;
+    double lum64, param64;
+    uint32_t n, k;
+    int preserve;
+};
+__device__ __forceinline__ WtExactArgs wt_exact_args(const WarpArgs& a) {
+    WtExactArgs x;
+    x.pal64 = a.pal64; x.pal_rgb = a.pal_rgb; x.pal_ab = a.pal_ab; x.lum64 = a.lum64; x.param64 = a.param64;
+    x.n = a.n; x.k = a.k; x.preserve = a.preserve;
+    return x;
+}
+
+template <int KIND>
+__device__ __noinline__ uint32_t wt_exact_entry(const WtExactArgs a, const SmemTables& st, double* __restrict__ scratch, uint32_t r, uint32_t g,
+                                                uint32_t b) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u, n = a.n;
+    const Lab c = linear_to_oklab_exact(st.decode[r], st.decode[g], st.decode[b]);
+    const double c0 = __dmul_rn((double)c.l, a.lum64), c1 = (double)c.a, c2 = (double)c.b;
+    const bool act = lane < n;
+    double p[3] = {0.0, 0.0, 0.0}, d = INFINITY;
+    if (act) {
+        p[0] = a.pal64[3 * lane]; p[1] = a.pal64[3 * lane + 1]; p[2] = a.pal64[3 * lane + 2];
+        d = sq_dist_exact(c0, c1, c2, p);
+    }
+    Lab o;
+    if (KIND == KIND_NN) {
+        // distances are >= 0: their bit patterns order like the values
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+        const uint32_t hi = (uint32_t)(bits >> 32), lo = (uint32_t)bits;
+        const uint32_t hmin = __reduce_min_sync(FULL, act ? hi : 0xffffffffu);
+        const bool top = act && hi == hmin;
+        const uint32_t lmin = __reduce_min_sync(FULL, top ? lo : 0xffffffffu);
+        const uint32_t best = __ffs(__ballot_sync(FULL, top && lo == lmin)) - 1u;
+        if (!a.preserve) return a.pal_rgb[best] & 0xffffffu;
+        o.l = c.l; o.a = a.pal_ab[2 * best]; o.b = a.pal_ab[2 * best + 1];
+    } else {
+        if (__any_sync(FULL, act && p[0] == c0 && p[1] == c1 && p[2] == c2)) return r | (g << 8) | (b << 16) | 0x80000000u;
+        const uint32_t k = a.k, cnt = k ? k : n;
+        uint32_t rank = lane;
+        if (k != 0) {
+            __syncwarp();
+            scratch[lane] = d;
+            __syncwarp();
+            rank = 0;
+#pragma unroll 2
+            for (uint32_t q = 0; q < n; ++q) {
+                const double dq = scratch[q];
+                rank += (dq < d || (dq == d && q < lane)) ? 1u : 0u;
+            }
+        }
+        __syncwarp();
+        if (act && rank < cnt) {
+            const double w = radial_basis_exact<(KIND < 3 ? KIND : 0)>(d, a.param64);
+            scratch[4 * rank] = __dmul_rn(p[0], w);
+            scratch[4 * rank + 1] = __dmul_rn(p[1], w);
+            scratch[4 * rank + 2] = __dmul_rn(p[2], w);
+            scratch[4 * rank + 3] = w;
+        }
+        __syncwarp();
+        // lanes 0..3 sum one component each, ascending distance as the reference's loop does
+        double acc = 0.0;
+        if (lane < 4) {
+#pragma unroll 1
+            for (uint32_t i = 0; i < cnt; ++i) acc = __dadd_rn(acc, scratch[4 * i + lane]);
+        }
+        const double n0 = __shfl_sync(FULL, acc, 0), n1 = __shfl_sync(FULL, acc, 1), n2 = __shfl_sync(FULL, acc, 2), den = __shfl_sync(FULL, acc, 3);
+        o.l = a.preserve ? __double2float_rn(__ddiv_rn(c0, a.lum64)) : __double2float_rn(__ddiv_rn(__ddiv_rn(n0, den), a.lum64));
+        o.a = __double2float_rn(__ddiv_rn(n1, den));
+        o.b = __double2float_rn(__ddiv_rn(n2, den));
+    }
+    float fr, fg, fb;
+    oklab_to_linear_exact(o, fr, fg, fb);
+    return f32_to_srgb8(fr, st.encode2) | (f32_to_srgb8(fg, st.encode2) << 8) | (f32_to_srgb8(fb, st.encode2) << 16);
+}
+
+// The entries in `flag_mask` of every lane, one after the other through wt_exact_entry; the owning lane
+// takes the result into res / smask. Warp uniform.
+template <int KIND, int MODE, int EPT>
+__device__ __forceinline__ void wt_resolve_exact(const WarpArgs& a, const SmemTables& st, double* scratch, uint32_t R, uint32_t G,
+                                                 const uint32_t (&Bq)[EPT], uint32_t flag_mask, uint32_t (&res)[EPT], uint32_t& smask) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr bool BRICK = MODE != FRONT_IMAGE;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t pend = __ballot_sync(FULL, flag_mask != 0);
+    while (pend) {
+        const int src = __ffs(pend) - 1;
+        pend &= pend - 1;
+        const uint32_t m = __shfl_sync(FULL, flag_mask, src);
+        const uint32_t sr = __shfl_sync(FULL, R, src), sg = __shfl_sync(FULL, G, src);
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const uint32_t q = __shfl_sync(FULL, Bq[e], src);
+            if (!((m >> e) & 1u)) continue;  // uniform
+            const uint32_t cr = BRICK ? sr : (q & 255u), cg = BRICK ? sg : ((q >> 8) & 255u), cb = BRICK ? q : (q >> 16);
+            const uint32_t v = wt_exact_entry<KIND>(wt_exact_args(a), st, scratch, cr, cg, cb);
+            if (a.stats && lane == 0) atomicAdd(&a.stats[127], 1u);
+            if ((int)lane == src && !((v >> 31) && MODE == FRONT_IMAGE)) {   // images: a palette-coloured pixel stays as it is
+                res[e] = v & 0xffffffu;
+                smask |= 1u << e;
+            }
+        }
     }
 }
 
@@ -272,6 +540,7 @@ struct WtTile {
     uint32_t valid_mask;
     uint32_t blo[3], bhi[3];
     float lo[3], hi[3];
+    float mid[3];                // centre of the box; after wt_centre, Lp / Ap / Bp are offsets from it
 };
 
 struct WtShared {
@@ -291,9 +560,9 @@ __device__ __forceinline__ void wt_convert_brick(const WarpArgs& a, const WtShar
     const bool rg_in = r < cs && g < cs;
     T.R = sh.chv[rc]; T.G = sh.chv[gc];
     const float linr = sh.lin[rc], ling = sh.lin[gc];
-    const float pl = fmaf(0.5363325363f, ling, 0.4122214708f * linr);
-    const float pm = fmaf(0.6806995451f, ling, 0.2119034982f * linr);
-    const float ps = fmaf(0.2817188376f, ling, 0.0883024619f * linr);
+    const float pl = fmaf(0.5363325363f, ling, 0.4122214708f * linr) + LMS_FLOOR;
+    const float pm = fmaf(0.6806995451f, ling, 0.2119034982f * linr) + LMS_FLOOR;
+    const float ps = fmaf(0.2817188376f, ling, 0.0883024619f * linr) + LMS_FLOOR;
     T.slot0 = (b0 * cs + g) * cs + r;
     T.slot_step = cs * cs;
     T.valid_mask = 0;
@@ -305,10 +574,13 @@ __device__ __forceinline__ void wt_convert_brick(const WarpArgs& a, const WtShar
         T.Bq[2 * i + 1] = sh.chv[bcB];
         lms_to_lab2(fma2(splat(0.0514459929f), linb, splat(pl)), fma2(splat(0.1073969566f), linb, splat(pm)),
                     fma2(splat(0.6299787005f), linb, splat(ps)), a.lum, T.Lp[i], T.Ap[i], T.Bp[i]);
-        const uint32_t flatA = T.slot0 + (2 * i) * T.slot_step, flatB = flatA + T.slot_step;
-        if (rg_in && bA < cs && flatA >= begin && flatA < end) T.valid_mask |= 1u << (2 * i);
-        if (rg_in && bB < cs && flatB >= begin && flatB < end) T.valid_mask |= 2u << (2 * i);
+        if (!a.whole_tiles) {
+            const uint32_t flatA = T.slot0 + (2 * i) * T.slot_step, flatB = flatA + T.slot_step;
+            if (rg_in && bA < cs && flatA >= begin && flatA < end) T.valid_mask |= 1u << (2 * i);
+            if (rg_in && bB < cs && flatB >= begin && flatB < end) T.valid_mask |= 2u << (2 * i);
+        }
     }
+    if (a.whole_tiles) T.valid_mask = (1u << EPT) - 1u;   // every tile of the launch lies wholly inside its range (the usual case)
     T.blo[0] = sh.chv[min(r0, csm1)]; T.bhi[0] = sh.chv[min(r0 + 7u, csm1)];
     T.blo[1] = sh.chv[min(g0, csm1)]; T.bhi[1] = sh.chv[min(g0 + 3u, csm1)];
     T.blo[2] = sh.chv[min(b0, csm1)]; T.bhi[2] = sh.chv[min(b0 + EPT - 1, csm1)];
@@ -342,9 +614,9 @@ __device__ __forceinline__ void wt_convert_image(const WarpArgs& a, const WtShar
     }
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-        f2 l = fma2(splat(0.4122214708f), lin[0][i], fma2(splat(0.5363325363f), lin[1][i], mul2(splat(0.0514459929f), lin[2][i])));
-        f2 m = fma2(splat(0.2119034982f), lin[0][i], fma2(splat(0.6806995451f), lin[1][i], mul2(splat(0.1073969566f), lin[2][i])));
-        f2 s = fma2(splat(0.0883024619f), lin[0][i], fma2(splat(0.2817188376f), lin[1][i], mul2(splat(0.6299787005f), lin[2][i])));
+        f2 l = fma2(splat(0.4122214708f), lin[0][i], fma2(splat(0.5363325363f), lin[1][i], fma2(splat(0.0514459929f), lin[2][i], splat(LMS_FLOOR))));
+        f2 m = fma2(splat(0.2119034982f), lin[0][i], fma2(splat(0.6806995451f), lin[1][i], fma2(splat(0.1073969566f), lin[2][i], splat(LMS_FLOOR))));
+        f2 s = fma2(splat(0.0883024619f), lin[0][i], fma2(splat(0.2817188376f), lin[1][i], fma2(splat(0.6299787005f), lin[2][i], splat(LMS_FLOOR))));
         lms_to_lab2(l, m, s, a.lum, T.Lp[i], T.Ap[i], T.Bp[i]);
     }
 #pragma unroll
@@ -390,15 +662,30 @@ __device__ __forceinline__ void wt_box(WtTile<EPT>& T) {
     wt_box_reduce(mn, mx, T.lo, T.hi);
 }
 
-// What the list holds for palette colour p (header).
+// What the list holds for palette colour p, relative to the tile centre m (header).
 template <int KIND>
-__device__ __forceinline__ float4 wt_list_entry(float4 p, float psq, float c1, float lbmin) {
+__device__ __forceinline__ float4 wt_list_entry(float4 p, const float (&m)[3], float c1, float lbmin) {
+    const float x = p.x - m[0], y = p.y - m[1], z = p.z - m[2];
+    const float sq = fmaf(x, x, fmaf(y, y, z * z));
     if (KIND == 0) {
         const float C = -c1;
-        return make_float4(-2.f * C * p.x, -2.f * C * p.y, -2.f * C * p.z, C * (psq - lbmin));
+        return make_float4(-2.f * C * x, -2.f * C * y, -2.f * C * z, C * (sq - lbmin));
     }
-    if (KIND == KIND_NN) return make_float4(-2.f * p.x, -2.f * p.y, -2.f * p.z, psq);
-    return p;
+    if (KIND == KIND_NN) return make_float4(-2.f * x, -2.f * y, -2.f * z, sq);
+    return make_float4(x, y, z, 0.f);
+}
+
+// The tile's entries as offsets from the centre of its Oklab box (what the scores are written in).
+template <int EPT>
+__device__ __forceinline__ void wt_centre(WtTile<EPT>& T) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) T.mid[c] = 0.5f * (T.lo[c] + T.hi[c]);
+#pragma unroll
+    for (int i = 0; i < EPT / 2; ++i) {
+        T.Lp[i] = add2(T.Lp[i], splat(-T.mid[0]));
+        T.Ap[i] = add2(T.Ap[i], splat(-T.mid[1]));
+        T.Bp[i] = add2(T.Bp[i], splat(-T.mid[2]));
+    }
 }
 
 // Outcome of the classification of one tile (warp uniform).
@@ -424,10 +711,22 @@ struct WtStage {
     uint32_t staged;  // out: bit `slot` set when the tile was staged and its store deferred
 };
 
+// Stores to an NVSwitch multicast address (one store, replicated by the switch into every GPU's copy of the
+// buffer). PTX defines multicast addresses for multimem.* operations only: a plain st.global to one is
+// undefined behaviour, even though both become STG in SASS.
+__device__ __forceinline__ void multimem_st_u32(uint8_t* mc_addr, uint32_t v) {
+    asm volatile("multimem.st.relaxed.sys.global.b32 [%0], %1;" ::"l"(mc_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_st_v4(uint8_t* mc_addr, uint4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)),
+                 "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                 : "memory");
+}
+
 // One tile's rows (24 bytes each) from the staging image to the CLUT and every extra destination,
-// as aligned 32-bit words.
+// as aligned 32-bit words. mc: `out` is a multicast address (and there are no extras).
 template <int EPT>
-__device__ __noinline__ void wt_flush_tile(uint8_t* out, uint8_t* const* extras, int nextra, uint32_t cs, const uint32_t* stage, uint32_t pitch,
+__device__ __noinline__ void wt_flush_tile(uint8_t* out, bool mc, uint8_t* const* extras, int nextra, uint32_t cs, const uint32_t* stage, uint32_t pitch,
                                            uint32_t slot, uint32_t flat0, uint32_t slot_step) {
     const uint32_t lane = threadIdx.x & 31u;
 #pragma unroll
@@ -437,7 +736,8 @@ __device__ __noinline__ void wt_flush_tile(uint8_t* out, uint8_t* const* extras,
             const uint32_t row = (wi * 43u) >> 8, e = row >> 2, gi = row & 3u, q = wi - row * 6u;   // wi / 6 for wi < 256
             const size_t off = 3ull * (flat0 + e * slot_step + gi * cs) + 4u * q;
             const uint32_t v = stage[(row * pitch + slot * 24u) / 4u + q];
-            *reinterpret_cast<uint32_t*>(out + off) = v;
+            if (mc) multimem_st_u32(out + off, v);
+            else *reinterpret_cast<uint32_t*>(out + off) = v;
 #pragma unroll 1
             for (int x = 0; x < nextra; ++x) *reinterpret_cast<uint32_t*>(extras[x] + off) = v;
         }
@@ -447,7 +747,7 @@ __device__ __noinline__ void wt_flush_tile(uint8_t* out, uint8_t* const* extras,
 // A whole hand-out (WT_BATCH tiles consecutive in r, all staged): every (b, g) row is 96 contiguous
 // bytes = six 16-byte stores per destination -- the unit in which the rows travel to the peer GPUs.
 template <int EPT>
-__device__ __noinline__ void wt_flush_batch(uint8_t* out, uint8_t* const* extras, int nextra, uint32_t cs, const uint32_t* stage, uint32_t flat0,
+__device__ __noinline__ void wt_flush_batch(uint8_t* out, bool mc, uint8_t* const* extras, int nextra, uint32_t cs, const uint32_t* stage, uint32_t flat0,
                                             uint32_t slot_step) {
     const uint32_t lane = threadIdx.x & 31u;
     constexpr uint32_t ROW16 = 24u * WT_BATCH / 16u;   // 16-byte pieces per row
@@ -458,7 +758,8 @@ __device__ __noinline__ void wt_flush_batch(uint8_t* out, uint8_t* const* extras
             const uint32_t row = wi / ROW16, e = row >> 2, gi = row & 3u, q = wi - row * ROW16;
             const size_t off = 3ull * (flat0 + e * slot_step + gi * cs) + 16u * q;
             const uint4 v = reinterpret_cast<const uint4*>(stage)[wi];
-            *reinterpret_cast<uint4*>(out + off) = v;
+            if (mc) multimem_st_v4(out + off, v);
+            else *reinterpret_cast<uint4*>(out + off) = v;
 #pragma unroll 1
             for (int x = 0; x < nextra; ++x) *reinterpret_cast<uint4*>(extras[x] + off) = v;
         }
@@ -538,7 +839,7 @@ __device__ __forceinline__ void wt_store(const WarpArgs& a, const WtTile<EPT>& T
             }
             if (sg.defer) { sg.staged |= 1u << sg.slot; return; }
             __syncwarp();
-            wt_flush_tile<EPT>(a.f.mc ? a.f.mc : a.f.out, sg.extras, a.f.mc ? 0 : a.f.nextra, a.f.cs, sg.buf, sg.pitch, sg.slot,
+            wt_flush_tile<EPT>(a.f.mc ? a.f.mc : a.f.out, a.f.mc != nullptr, sg.extras, a.f.mc ? 0 : a.f.nextra, a.f.cs, sg.buf, sg.pitch, sg.slot,
                                __shfl_sync(FULL, T.slot0, 0), T.slot_step);
             return;
         }
@@ -549,17 +850,23 @@ __device__ __forceinline__ void wt_store(const WarpArgs& a, const WtTile<EPT>& T
 // Step 5: everything per entry, given the candidate list.
 //   cand  : per-warp list (wt_list_entry of every listed colour), cidx: palette index of each
 //   hits  : packed sRGB of the palette colours that may equal a colour of the tile exactly
-template <int KIND, int MODE, int EPT, bool MULTI>
+//   INLINE_EXACT : entries the f32 arithmetic cannot decide are resolved here by wt_exact_entry (`scratch`:
+//           32 x 4 doubles per warp) and stored with their tile; otherwise they go to the work list of the
+//           exact kernels' second pass
+template <int KIND, int MODE, int EPT, bool MULTI, bool INLINE_EXACT>
 __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& st, const WtTile<EPT>& T, const WtClass& cl,
                                            const float4* __restrict__ cand, const uint32_t* __restrict__ cidx,
-                                           const uint32_t* __restrict__ hits, WtStage& stage) {
+                                           const uint32_t* __restrict__ hits, WtStage& stage, double* __restrict__ scratch) {
     constexpr int NP = EPT / 2;
     constexpr bool BRICK = MODE != FRONT_IMAGE;
     const float c1 = a.c1;
     const uint32_t k = a.k, nin = cl.nin, nunc = cl.nunc;
     const int kp = (int)k - (int)cl.nin_all;
     const bool choose = !cl.take_all && kp > 0 && (int)cl.nunc_all > kp && (int)nunc > kp;
-    const uint32_t direct = (cl.take_all || kp <= 0 || choose) ? nin : nin + nunc;
+    // choosing from above (wt_select_c): every uncertain colour is added by the direct loop, the few left out are taken out again
+    const int left_out = (int)nunc - kp;
+    const bool top = choose && KIND != 2 && KIND != KIND_NN && left_out < kp && left_out < WT_TRACK && nunc <= 16u;
+    const uint32_t direct = (cl.take_all || kp <= 0 || (choose && !top)) ? nin : nin + nunc;
     // per-tile conditions that send every entry to the exact kernel: more exact-hit candidates than
     // the list holds; weights so far from 1 that the reference's f64 sums leave their range; more
     // neighbours to choose than the selection handles
@@ -576,7 +883,15 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
     if (KIND == 0) tol *= -c1;
 
     if (all_exact) {
-        if (T.valid_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, T.valid_mask, T.slot0, T.slot_step);
+        if (INLINE_EXACT) {
+            uint32_t res[EPT], smask = 0;
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) res[e] = 0;
+            wt_resolve_exact<KIND, MODE, EPT>(a, st, scratch, T.R, T.G, T.Bq, T.valid_mask, res, smask);
+            wt_store<MODE, EPT, MULTI>(a, T, res, smask, stage);
+        } else if (T.valid_mask) {
+            wt_flag_mask(a.flag_count, a.flag_list, a.stats, T.valid_mask, T.slot0, T.slot_step);
+        }
         return;
     }
     uint32_t flag_mask = 0;
@@ -594,7 +909,7 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
                 const float4 q = cand[j];
 #pragma unroll
                 for (int i = 0; i < NP; ++i) {
-                    f2 d2 = wt_score2<KIND_NN>(q, T.Lp[i], T.Ap[i], T.Bp[i], splat(0.f));
+                    f2 d2 = wt_score2<KIND_NN>(q, T.Lp[i], T.Ap[i], T.Bp[i]);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int e = 2 * i + h;
@@ -607,8 +922,14 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
                 }
             }
 #pragma unroll
-            for (int e = 0; e < EPT; ++e)
-                if ((second[e] - best[e] <= tol) && (second[e] < INFINITY)) risky_mask |= 1u << e;
+            for (int e = 0; e < EPT; ++e) {
+                if (!((second[e] - best[e] <= tol) && (second[e] < INFINITY)) || !((T.valid_mask >> e) & 1u)) continue;
+                // near-tie: the reference's own distances decide (this lane alone; rare)
+                const uint32_t rgb = BRICK ? (T.R | (T.G << 8) | (T.Bq[e] << 16)) : T.Bq[e];
+                best_j[e] = wt_resolve_tie_nn(a.pal64, a.lum64, st.decode, cand, cidx, nunc, rgb, (e & 1) ? T.Lp[e / 2].y : T.Lp[e / 2].x,
+                                              (e & 1) ? T.Ap[e / 2].y : T.Ap[e / 2].x, (e & 1) ? T.Bp[e / 2].y : T.Bp[e / 2].x, best[e], tol);
+                if (a.stats) atomicAdd(&a.stats[126], 1u);
+            }
         }
         flag_mask = risky_mask & T.valid_mask;
         uint32_t res[EPT];
@@ -625,78 +946,100 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
                 Lab o = {ex.l, a.pal_ab[2 * idx], a.pal_ab[2 * idx + 1]};
                 float r, g, b;
                 oklab_to_linear_exact(o, r, g, b);
-                res[e] = f32_to_srgb8(r, st.encode) | (f32_to_srgb8(g, st.encode) << 8) | (f32_to_srgb8(b, st.encode) << 16);
+                res[e] = f32_to_srgb8(r, st.encode2) | (f32_to_srgb8(g, st.encode2) << 8) | (f32_to_srgb8(b, st.encode2) << 16);
             }
         }
-        wt_store<MODE, EPT, MULTI>(a, T, res, T.valid_mask & ~risky_mask, stage);
-        if (flag_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, flag_mask, T.slot0, T.slot_step);
+        uint32_t smask = T.valid_mask & ~risky_mask;
+        if (INLINE_EXACT) wt_resolve_exact<KIND, MODE, EPT>(a, st, scratch, T.R, T.G, T.Bq, flag_mask, res, smask);
+        wt_store<MODE, EPT, MULTI>(a, T, res, smask, stage);
+        if (!INLINE_EXACT && flag_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, flag_mask, T.slot0, T.slot_step);
         return;
     } else {
-    f2 n0[NP], n1[NP], n2[NP], den[NP], cc[NP];
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        n0[i] = n1[i] = n2[i] = den[i] = splat(0.f);
-        cc[i] = KIND == 0 ? mul2(splat(-c1), fma2(T.Lp[i], T.Lp[i], fma2(T.Ap[i], T.Ap[i], mul2(T.Bp[i], T.Bp[i])))) : splat(0.f);
-    }
-#pragma unroll 2
-    for (uint32_t j = 0; j < direct; ++j) {
-        const float4 q = cand[j];
-#pragma unroll
-        for (int i = 0; i < NP; ++i) {
-            f2 w = wt_weight2<KIND>(wt_score2<KIND>(q, T.Lp[i], T.Ap[i], T.Bp[i], cc[i]), c1, c0);
-            n0[i] = fma2(splat(q.x), w, n0[i]);
-            n1[i] = fma2(splat(q.y), w, n1[i]);
-            n2[i] = fma2(splat(q.z), w, n2[i]);
-            den[i] = add2(den[i], w);
-        }
-    }
-    uint32_t risky_mask = 0;
-    if (choose) {
-        const float4* unc = cand + nin;
-#pragma unroll
-        for (int i = 0; i < NP; ++i) {
-            PairAcc pa = wt_select_any<KIND>(unc, (int)nunc, kp, T.Lp[i], T.Ap[i], T.Bp[i], cc[i], c1, c0, tol);
-            n0[i] = add2(n0[i], pa.n0); n1[i] = add2(n1[i], pa.n1); n2[i] = add2(n2[i], pa.n2); den[i] = add2(den[i], pa.den);
-            risky_mask |= pa.risky << (2 * i);
-        }
-    }
-    const float fs = KIND == 0 ? 0.5f / c1 : 1.0f;  // the Gaussian sums ran over -2C p = 2 c1 p
+    static_assert(NP == 2, "the loop below picks its pair with selects");
+    // One pair of entries at a time, rolled: ONE copy of the accumulate / select / convert-back code for both pairs
+    // (half the code -- what decides whether the SM's instruction cache holds the loop -- and half the accumulators
+    // live at a time), at the price of walking the candidate list twice.
+    const float fs = KIND == 0 ? 0.5f / c1 : 1.0f;  // the Gaussian sums run over -2C (p - m) = 2 c1 (p - m)
+    const float4* unc = cand + nin;
+    const int mU = (int)nunc;
+    const int csel = top ? left_out : kp;
+    const bool small = csel < WT_TRACK && mU <= 16;
     uint32_t res[EPT], smask = 0;
 #pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        const f2 d = den[i];
-        if (!(d.x > 1e-30f) || !(d.x < 1e30f)) risky_mask |= 1u << (2 * i);
-        if (!(d.y > 1e-30f) || !(d.y < 1e30f)) risky_mask |= 2u << (2 * i);
-        const f2 inv = mul2(make_float2(rcp_approx(d.x), rcp_approx(d.y)), splat(fs));
-        f2 oL = a.preserve ? T.Lp[i] : mul2(n0[i], inv);
-        oL = mul2(oL, splat(a.inv_lum));
-        f2 r2, g2, b2;
-        oklab_to_linear2(oL, mul2(n1[i], inv), mul2(n2[i], inv), r2, g2, b2);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int e = 2 * i + h;
-            res[e] = 0;
-            if (!((T.valid_mask >> e) & 1u)) continue;
-            const uint32_t pr = BRICK ? T.R : (T.Bq[e] & 255u), pg = BRICK ? T.G : ((T.Bq[e] >> 8) & 255u), pb = BRICK ? T.Bq[e] : (T.Bq[e] >> 16);
-            // rbf.rs:66-68 palette.contains(&color): identical sRGB <=> identical Oklab triple
-            if (nhit) {
-                const uint32_t packed = pr | (pg << 8) | (pb << 16);
-                bool hit = false;
+    for (int e = 0; e < EPT; ++e) res[e] = 0;
 #pragma unroll 1
-                for (uint32_t hh = 0; hh < nhit; ++hh) hit |= (hits[hh] == packed);
-                if (hit) {
-                    if (MODE != FRONT_IMAGE) { res[e] = packed; smask |= 1u << e; }  // images: the pixel stays as it is
-                    continue;
+    for (int pr = 0; pr < NP; ++pr) {
+        const f2 L = pr ? T.Lp[1] : T.Lp[0], A = pr ? T.Ap[1] : T.Ap[0], B = pr ? T.Bp[1] : T.Bp[0];
+        const uint32_t bq0 = pr ? T.Bq[2] : T.Bq[0], bq1 = pr ? T.Bq[3] : T.Bq[1];
+        const uint32_t vm = (T.valid_mask >> (2 * pr)) & 3u;
+        f2 n0 = splat(0.f), n1 = n0, n2 = n0, den = n0;
+#pragma unroll 4
+        for (uint32_t j = 0; j < direct; ++j) {
+            const float4 q = cand[j];
+            const f2 w = wt_weight2<KIND>(wt_score2<KIND>(q, L, A, B), c1, c0);
+            n0 = fma2(splat(q.x), w, n0);
+            n1 = fma2(splat(q.y), w, n1);
+            n2 = fma2(splat(q.z), w, n2);
+            den = add2(den, w);
+        }
+        uint32_t risky = 0;   // bit h: entry h of the pair needs the reference's arithmetic throughout
+        if (choose) {
+            PairAcc pa = small ? wt_select_small<KIND>(unc, mU, csel, top, L, A, B, c1, c0, tol) : wt_select_insert<KIND>(unc, mU, kp, L, A, B, c1, c0, tol);
+            if (pa.risky & 3u) {
+                // near-ties: the reference's own distances decide the order inside the doubtful band (this lane alone; rare)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (!((pa.risky >> h) & 1u)) continue;
+                    pa.risky &= ~(1u << h);
+                    if (!((vm >> h) & 1u)) continue;
+                    const uint32_t bq = h ? bq1 : bq0;
+                    const uint32_t rgb = BRICK ? (T.R | (T.G << 8) | (bq << 16)) : bq;
+                    const float nx = h ? pa.nxt.y : pa.nxt.x;
+                    float4 o;
+                    if (wt_resolve_tie<KIND>(a.pal64, a.lum64, st.decode, unc, cidx + nin, mU, kp, top, rgb, h ? L.y : L.x, h ? A.y : A.x, h ? B.y : B.x, c1, c0,
+                                             h ? pa.tau.y : pa.tau.x, nx, fmaf(fabsf(nx), 4e-6f, tol), o)) {
+                        if (h) { pa.n0.y = o.x; pa.n1.y = o.y; pa.n2.y = o.z; pa.den.y = o.w; }
+                        else { pa.n0.x = o.x; pa.n1.x = o.y; pa.n2.x = o.z; pa.den.x = o.w; }
+                        if (a.stats) atomicAdd(&a.stats[126], 1u);
+                    } else {
+                        pa.risky |= 4u << h;
+                    }
                 }
             }
-            if ((risky_mask >> e) & 1u) { flag_mask |= 1u << e; continue; }
-            res[e] = f32_to_srgb8(h ? r2.y : r2.x, st.encode) | (f32_to_srgb8(h ? g2.y : g2.x, st.encode) << 8) |
-                     (f32_to_srgb8(h ? b2.y : b2.x, st.encode) << 16);
-            smask |= 1u << e;
+            n0 = add2(n0, pa.n0); n1 = add2(n1, pa.n1); n2 = add2(n2, pa.n2); den = add2(den, pa.den);
+            risky = pa.risky >> 2;
         }
+        // num / den, the centre added back, to linear sRGB
+        if (!(den.x > 1e-30f) || !(den.x < 1e30f)) risky |= 1u;
+        if (!(den.y > 1e-30f) || !(den.y < 1e30f)) risky |= 2u;
+        const f2 inv = mul2(make_float2(rcp_approx(den.x), rcp_approx(den.y)), splat(fs));
+        f2 oL = a.preserve ? add2(L, splat(T.mid[0])) : fma2(n0, inv, splat(T.mid[0]));
+        oL = mul2(oL, splat(a.inv_lum));
+        f2 r2, g2, b2;
+        oklab_to_linear2(oL, fma2(n1, inv, splat(T.mid[1])), fma2(n2, inv, splat(T.mid[2])), r2, g2, b2);
+        uint32_t out0 = srgb8_pack3(f32_to_srgb8_wide(r2.x, st.encode2), f32_to_srgb8_wide(g2.x, st.encode2), f32_to_srgb8_wide(b2.x, st.encode2));
+        uint32_t out1 = srgb8_pack3(f32_to_srgb8_wide(r2.y, st.encode2), f32_to_srgb8_wide(g2.y, st.encode2), f32_to_srgb8_wide(b2.y, st.encode2));
+        uint32_t ok = vm & ~risky;   // entries with a result
+        if (nhit) {
+            // rbf.rs:66-68 palette.contains(&color): identical sRGB <=> identical Oklab triple; the colour is left as it is
+            const uint32_t p0 = BRICK ? (T.R | (T.G << 8) | (bq0 << 16)) : bq0, p1 = BRICK ? (T.R | (T.G << 8) | (bq1 << 16)) : bq1;
+            uint32_t hit = 0;
+#pragma unroll 1
+            for (uint32_t hh = 0; hh < nhit; ++hh) hit |= (hits[hh] == p0 ? 1u : 0u) | (hits[hh] == p1 ? 2u : 0u);
+            hit &= vm;
+            if (hit & 1u) out0 = p0;
+            if (hit & 2u) out1 = p1;
+            risky &= ~hit;
+            ok = MODE == FRONT_IMAGE ? (ok & ~hit) : (ok | hit);   // images: the pixel stays as it is
+        }
+        flag_mask |= (risky & vm) << (2 * pr);
+        smask |= ok << (2 * pr);
+        if (pr) { res[2] = out0; res[3] = out1; }
+        else { res[0] = out0; res[1] = out1; }
     }
+    if (INLINE_EXACT) wt_resolve_exact<KIND, MODE, EPT>(a, st, scratch, T.R, T.G, T.Bq, flag_mask, res, smask);
     wt_store<MODE, EPT, MULTI>(a, T, res, smask, stage);
-    if (flag_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, flag_mask, T.slot0, T.slot_step);
+    if (!INLINE_EXACT && flag_mask) wt_flag_mask(a.flag_count, a.flag_list, a.stats, flag_mask, T.slot0, T.slot_step);
     }  // RBF kinds
 }
 
@@ -716,12 +1059,13 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
     __shared__ float s_lin[BRICK ? WT_MAX_CS : 1];
     __shared__ uint8_t s_chv[BRICK ? WT_MAX_CS + 3 : 4];
     __shared__ __align__(16) float4 s_cand[WT_WARPS][WT_MAX_N];
-    __shared__ __align__(8) float2 s_bnd[WT_WARPS][WT_MAX_N];
+    __shared__ __align__(16) uint32_t s_rank[WT_WARPS][WT_MAX_N];   // (UB, LB) of the lane's colour as an fp16 pair
     __shared__ uint32_t s_cidx[WT_WARPS][WT_MAX_N];
     __shared__ uint32_t s_hit[WT_WARPS][FAST_MAX_HITS];
     __shared__ f2 s_stash[GROUPS == 2 ? WT_WARPS : 1][6][GROUPS == 2 ? 32 : 1];   // the second group's Lp, Ap, Bp pairs
     __shared__ __align__(16) uint32_t s_stage[MULTI ? WT_WARPS : 1][MULTI ? EPT * 24 * WT_BATCH : 1];
     __shared__ uint8_t* s_extra[LUTGEN_MAX_PEERS];
+    __shared__ __align__(16) double s_exact[WT_WARPS][128];   // wt_exact_entry's scratch
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n = a.n, k = a.k;
@@ -753,20 +1097,26 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
     const bool active = lane < n;
     const float4 p = active ? a.pal[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
     const uint32_t prgb = active ? (a.pal_rgb[lane] & 0xffffffu) : 0u;
-    const float psq = fmaf(p.x, p.x, fmaf(p.y, p.y, p.z * p.z));
+    const __half k16 = __ushort2half_rn((unsigned short)(k < 1024u ? k : 1024u));
     float4* cand = s_cand[warp];
-    float2* bnd = s_bnd[warp];
+    uint32_t* rnk = s_rank[warp];
     uint32_t* cidx = s_cidx[warp];
     uint32_t* hits = s_hit[warp];
 
     // the hand-out after the current one is requested before the current one is processed: the atomic's
     // round trip (1.6 % of the stall samples when taken at the point of use) hides behind a hand-out's work
+    // Tickets advance by a.batch. Up to a.tail_cut a ticket IS the first tile of a hand-out of a.batch tiles; beyond it
+    // every ticket stands for a single tile (tile tail_cut + (ticket - tail_cut) / batch): the last couple of tiles per warp
+    // are handed out one by one, so the warps finish within a tile of each other instead of within a hand-out (a warp
+    // has only ~9 hand-outs of a level-16 CLUT: the uneven end was 5 % of the kernel).
     uint32_t ticket = 0;
     if (lane == 0) ticket = atomicAdd(a.tile_counter, a.batch);
     for (;;) {
-        uint32_t t0 = __shfl_sync(FULL, ticket, 0);
-        if (t0 >= a.ntiles) break;
+        const uint32_t tk = __shfl_sync(FULL, ticket, 0);
+        if (tk >= a.ticket_end) break;
         if (lane == 0) ticket = atomicAdd(a.tile_counter, a.batch);
+        uint32_t t0 = tk, nb = a.batch;
+        if (tk >= a.tail_cut) { t0 = a.tail_cut + (tk - a.tail_cut) / a.batch; nb = 1u; }
         if (a.shard_count > 1) t0 = ((t0 / a.batch) * a.shard_count + a.shard_index) * a.batch;
         if (t0 >= a.ntiles_global) break;
         uint32_t ir = 0, ig = 0, ib = 0;
@@ -775,7 +1125,7 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
             wt_divmod(t0, a.tiles_r, a.inv_tiles_r, rest, ir);
             wt_divmod(rest, a.tiles_g, a.inv_tiles_g, ib, ig);
         }
-        const uint32_t t1 = min(t0 + a.batch, a.ntiles_global);
+        const uint32_t t1 = min(t0 + nb, a.ntiles_global);
         WtStage sg;
         sg.extras = s_extra;
         sg.buf = s_stage[MULTI ? warp : 0];
@@ -819,6 +1169,7 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
                 if (!__any_sync(FULL, T.valid_mask != 0)) continue;
                 wt_box<EPT>(T);
             }
+            wt_centre<EPT>(T);
 
             // ---- 2.-4. classification, one palette colour per lane --------------------------------
             WtClass cl;
@@ -829,7 +1180,7 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
             cl.lbmin = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(lbv)));
             cl.ubmin = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(ubv)));
             cl.nhit = 0;
-            __syncwarp();  // the previous tile's reads of hits / cand / cidx / bnd are over
+            __syncwarp();  // the previous tile's reads of hits / cand / cidx / rnk are over
             if (KIND != KIND_NN) {
                 const uint32_t qr = prgb & 255u, qg = (prgb >> 8) & 255u, qb = prgb >> 16;
                 const bool inside = active && qr >= T.blo[0] && qr <= T.bhi[0] && qg >= T.blo[1] && qg <= T.bhi[1] && qb >= T.blo[2] && qb <= T.bhi[2];
@@ -848,22 +1199,29 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
             }
             bool is_in = active, is_unc = false;
             if (!cl.take_all) {
-                // U_k = k-th smallest UB. Keys made unique by the lane number in the low mantissa bits
-                // (UB rounded UP to a multiple of 32 ulps first, so the bound stays conservative).
-                const uint32_t ukey = ((__float_as_uint(ubv) + 31u) & ~31u) | lane;
-                bnd[lane] = make_float2(lbv, __uint_as_float(ukey));
+                // U_k = the k-th smallest UB bounds every entry's k-th neighbour distance: a colour with LB > U_k is OUT;
+                // one with at most k colours (itself included) whose LB <= its UB is IN. Both counts come from ONE packed
+                // comparison per palette colour: the bounds as fp16 pairs (UB rounded up, LB rounded down -- conservative),
+                // (UB_q, LB_q) <= (UB_me, UB_me) as HSET2, summed with HADD2, four colours per 16-byte load. (The scalar
+                // loop this replaces -- LDS, two compares, two adds per colour -- was 9 % of the kernel's instructions.)
+                const __half ub16 = __float2half_ru(ubv * a.rank_scale), lb16 = __float2half_rd(lbv * a.rank_scale);
+                rnk[lane] = (uint32_t)__half_as_ushort(ub16) | ((uint32_t)__half_as_ushort(lb16) << 16);
                 __syncwarp();
-                uint32_t rank_u = 0, rivals = 0;
-#pragma unroll 4
-                for (uint32_t q = 0; q < n; ++q) {
-                    const float2 bq = bnd[q];
-                    rank_u += (__float_as_uint(bq.y) < ukey) ? 1u : 0u;
-                    rivals += (bq.x <= ubv) ? 1u : 0u;  // counts the lane itself once (LB <= UB)
+                const __half2 me = __half2half2(ub16);
+                __half2 acc0 = __float2half2_rn(0.f), acc1 = acc0;
+#pragma unroll
+                for (int q4 = 0; q4 < WT_MAX_N / 4; ++q4) {
+                    const uint4 v = reinterpret_cast<const uint4*>(rnk)[q4];   // inactive lanes hold (inf, inf): never <= a finite bound
+                    acc0 = __hadd2(acc0, __hle2(u32_as_half2(v.x), me));
+                    acc1 = __hadd2(acc1, __hle2(u32_as_half2(v.y), me));
+                    acc0 = __hadd2(acc0, __hle2(u32_as_half2(v.z), me));
+                    acc1 = __hadd2(acc1, __hle2(u32_as_half2(v.w), me));
                 }
-                const uint32_t bu = __ballot_sync(FULL, active && rank_u == k - 1);
-                const float uk = __uint_as_float(__shfl_sync(FULL, ukey, __ffs(bu) - 1) | 31u);
-                const bool near = active && lbv <= uk;
-                is_in = near && rivals <= k;  // rivals - 1 (others) <= k - 1
+                const __half2 cnt = __hadd2(acc0, acc1);   // low: #{UB_q <= UB_me}, high: #{LB_q <= UB_me} (counts up to 32 are exact)
+                const bool kth = active && __hge(__low2half(cnt), k16);
+                const uint32_t uk = __reduce_min_sync(FULL, kth ? (uint32_t)__half_as_ushort(ub16) : 0xffffu);   // bounds are >= 0: bit patterns order like values
+                const bool near = active && (uint32_t)__half_as_ushort(lb16) <= uk;
+                is_in = near && __hle(__high2half(cnt), k16);
                 is_unc = near && !is_in;
             }
             cl.nin_all = __popc(__ballot_sync(FULL, is_in));
@@ -875,9 +1233,9 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
             // largest distance an uncertain colour can have: scales the near-tie tolerance
             cl.ubmax_unc = __uint_as_float(__reduce_max_sync(FULL, list_unc ? __float_as_uint(ubv) : 0u));
             {
-                const float4 q = wt_list_entry<KIND>(p, psq, c1, cl.lbmin);
-                if (list_in) { const uint32_t pos = __popc(bin & lt); cand[pos] = q; if (KIND == KIND_NN) cidx[pos] = lane; }
-                if (list_unc) { const uint32_t pos = cl.nin + __popc(bun & lt); cand[pos] = q; if (KIND == KIND_NN) cidx[pos] = lane; }
+                const float4 q = wt_list_entry<KIND>(p, T.mid, c1, cl.lbmin);
+                if (list_in) { const uint32_t pos = __popc(bin & lt); cand[pos] = q; cidx[pos] = lane; }
+                if (list_unc) { const uint32_t pos = cl.nin + __popc(bun & lt); cand[pos] = q; cidx[pos] = lane; }
                 __syncwarp();
             }
             if (a.stats && lane == 0) {
@@ -892,20 +1250,22 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
                     // the second group: same classification, its own colours
 #pragma unroll
                     for (int i = 0; i < EPT / 2; ++i) {
-                        T.Lp[i] = s_stash[warp][i][lane]; T.Ap[i] = s_stash[warp][2 + i][lane]; T.Bp[i] = s_stash[warp][4 + i][lane];
+                        T.Lp[i] = add2(s_stash[warp][i][lane], splat(-T.mid[0]));
+                        T.Ap[i] = add2(s_stash[warp][2 + i][lane], splat(-T.mid[1]));
+                        T.Bp[i] = add2(s_stash[warp][4 + i][lane], splat(-T.mid[2]));
                     }
 #pragma unroll
                     for (int e = 0; e < EPT; ++e) T.Bq[e] = s_chv[min(tile_b0 + (uint32_t)EPT + e, csm1)];
                     T.slot0 += (uint32_t)EPT * T.slot_step;
                     T.valid_mask = valid1;
                 }
-                wt_entries<KIND, MODE, EPT, MULTI>(a, st, T, cl, cand, cidx, hits, sg);
+                wt_entries<KIND, MODE, EPT, MULTI, true>(a, st, T, cl, cand, cidx, hits, sg, s_exact[warp]);
             }
         }
         if (MULTI && sg.staged) {
             __syncwarp();
             if (sg.staged == (1u << WT_BATCH) - 1u) {
-                wt_flush_batch<EPT>(a.f.mc ? a.f.mc : a.f.out, sg.extras, a.f.mc ? 0 : a.f.nextra, cs, sg.buf, batch_flat0, batch_step);
+                wt_flush_batch<EPT>(a.f.mc ? a.f.mc : a.f.out, a.f.mc != nullptr, sg.extras, a.f.mc ? 0 : a.f.nextra, cs, sg.buf, batch_flat0, batch_step);
             } else {
                 // some tiles of the hand-out went out entry by entry (or were skipped): the staged ones go tile by tile.
                 // batch_flat0 is the first tile's origin only if that tile reached step 5; recompute from the tile number
@@ -916,7 +1276,41 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
 #pragma unroll 1
                 for (uint32_t sl = 0; sl < (uint32_t)WT_BATCH; ++sl)
                     if ((sg.staged >> sl) & 1u)
-                        wt_flush_tile<EPT>(a.f.mc ? a.f.mc : a.f.out, sg.extras, a.f.mc ? 0 : a.f.nextra, cs, sg.buf, sg.pitch, sl, flat_first + 8u * sl, cs * cs);
+                        wt_flush_tile<EPT>(a.f.mc ? a.f.mc : a.f.out, a.f.mc != nullptr, sg.extras, a.f.mc ? 0 : a.f.nextra, cs, sg.buf, sg.pitch, sl, flat_first + 8u * sl, cs * cs);
+            }
+        }
+    }
+    // The last WARP to finish leaves the two counters as every launch expects to find them (zero): no memset
+    // between launches, and a captured graph can be replayed as it is. (Warps, not CTAs: no CTA barrier at the end.)
+    //
+    // MULTI with a barrier: that warp is also the one that knows every store of this GPU to the peers' CLUTs has been
+    // issued. It publishes this rank's step number in every rank's flag array (release, system scope) and waits until
+    // all ranks have published theirs in its own array: when the kernel ends, the CLUT is complete on this GPU -- the
+    // exchange and its barrier cost no launch of their own.
+    __syncwarp();
+    if (lane == 0) {
+        if (MULTI && a.f.bar_nranks > 1) __threadfence_system();   // this warp's stores (ordered before by the barrier above) before its count
+        else __threadfence();
+        const uint32_t prev = atomicAdd(a.done_counter, 1u);
+        if (prev == gridDim.x * (uint32_t)WT_WARPS - 1u) {
+            __threadfence();
+            *a.tile_counter = 0u;
+            *a.done_counter = 0u;
+            if (MULTI && a.f.bar_nranks > 1) {
+                unsigned* mine = a.f.bar_flags[a.f.bar_rank];
+                const unsigned epoch = mine[LUTGEN_BAR_EPOCH] + 1u;
+                mine[LUTGEN_BAR_EPOCH] = epoch;
+                __threadfence_system();
+                for (int t = 0; t < a.f.bar_nranks; ++t) {
+                    unsigned* remote = a.f.bar_flags[t] + a.f.bar_rank;
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+                }
+                for (int t = 0; t < a.f.bar_nranks; ++t) {
+                    unsigned v;
+                    do {
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + t) : "memory");
+                    } while ((int)(v - epoch) < 0);
+                }
             }
         }
     }
@@ -1025,6 +1419,7 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp_big(const Wa
             if (ct * (256u * EPT) + warp * (32u * EPT) >= end) T.valid_mask = 0;
         }
         wt_box<EPT>(T);
+        wt_centre<EPT>(T);
         if (lane < 6) {
             s_wbox[warp][lane] = lane < 3 ? T.lo[lane] : T.hi[lane - 3];
             s_wsrgb[warp][lane] = lane < 3 ? T.blo[lane] : T.bhi[lane - 3];
@@ -1185,7 +1580,7 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp_big(const Wa
                 const bool list_in = is_in && !negl, list_unc = is_unc && !negl;
                 const uint32_t bin = __ballot_sync(FULL, list_in), bun = __ballot_sync(FULL, list_unc), lt = (1u << lane) - 1u;
                 // IN colours fill the list from the front, UNCERTAIN ones from the back (reversed below)
-                const float4 q = wt_list_entry<KIND>(pj, fmaf(pj.x, pj.x, fmaf(pj.y, pj.y, pj.z * pj.z)), c1, cl.lbmin);
+                const float4 q = wt_list_entry<KIND>(pj, T.mid, c1, cl.lbmin);
                 if (list_in) { const uint32_t pos = cl.nin + __popc(bin & lt); cand[pos] = q; cidx[pos] = s_sidx[j]; }
                 if (list_unc) { const uint32_t pos = WB_MAX_M - 1u - (cl.nunc + __popc(bun & lt)); cand[pos] = q; cidx[pos] = s_sidx[j]; }
                 if (list_unc) ubmax_bits = max(ubmax_bits, __float_as_uint(ubr));
@@ -1224,7 +1619,7 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp_big(const Wa
         sg.slot = 0;
         sg.defer = false;
         sg.staged = 0;
-        wt_entries<KIND, MODE, EPT, MULTI>(a, st, T, cl, cand, cidx, s_hit, sg);
+        wt_entries<KIND, MODE, EPT, MULTI, false>(a, st, T, cl, cand, cidx, s_hit, sg, nullptr);
     }
 }
 

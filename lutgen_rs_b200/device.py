@@ -120,7 +120,7 @@ class PeerLut:
     rank of `group` must construct it at the same time."""
 
     MAX_WORLD = 8  # 1 + LUTGEN_MAX_PEERS destinations per launch
-    FLAG_BYTES = 256
+    FLAG_BYTES = 256   # 16 u32 used: slots 0..7 written by the peers, word 8 the owner's step counter (lutgen_cuda.h)
 
     def __init__(self, nbytes, group=None):
         import ctypes as C
@@ -184,8 +184,10 @@ class PeerLut:
                 ptrs.append(q.value)
             self._ptrs.append(ptrs)
         self.tensors = [torch.as_tensor(_RawCuda(p, self.nbytes), device="cuda") for p in self._own]
-        # the barrier uses the flag arrays of copy 0 throughout: device table of their addresses, by rank
+        # flag arrays of copy 0 throughout, device tables of their addresses by rank: bytes 0..63 belong to the
+        # exchange kernel's own barrier (lutgen_cuda_generate_lut_exchange_dev), bytes 128.. to barrier() below
         self._flag_table = torch.tensor([q + self._lut_bytes for q in self._ptrs[0]], dtype=torch.int64, device="cuda")
+        self._flag_table_host = torch.tensor([q + self._lut_bytes + 128 for q in self._ptrs[0]], dtype=torch.int64, device="cuda")
         self._epoch = 0
         self._turn = 0
         torch.cuda.synchronize()
@@ -204,14 +206,14 @@ class PeerLut:
     def barrier(self, stream=None):
         """All ranks' earlier writes into the peer buffers are complete and visible after this."""
         self._epoch += 1
-        _native.check(_native.lib().lutgen_cuda_peer_barrier_dev(self._flag_table.data_ptr(), self.world, self.rank,
+        _native.check(_native.lib().lutgen_cuda_peer_barrier_dev(self._flag_table_host.data_ptr(), self.world, self.rank,
                                                                   self._epoch & 0xFFFFFFFF, _stream(stream)))
 
     def close(self):
         import ctypes as C
         L = _native.lib()
         self.tensors = []
-        self._flag_table = None
+        self._flag_table = self._flag_table_host = None
         for q in self._imported:
             L.lutgen_cuda_ipc_close(C.c_void_p(q))
         self._imported = []
@@ -247,9 +249,9 @@ def generate_lut_fused(remapper, level, group=None, stream=None):
     if peers is None:
         peers = _peer_luts[key] = PeerLut(3 * side * side, group)
     mine, ptrs, mc = peers.next()
-    _native.check(_native.lib().lutgen_cuda_generate_lut_shard_mc_dev(remapper._h, level, ptrs, len(ptrs), mc or None, peers.rank, world,
-                                                                     _stream(stream)))
-    peers.barrier(stream)
+    # one launch: the kernel's last thread block signals and waits for the peers (no barrier launch, no collective)
+    _native.check(_native.lib().lutgen_cuda_generate_lut_exchange_dev(remapper._h, level, ptrs, len(ptrs), mc or None, peers.rank, world,
+                                                                     peers._flag_table.data_ptr(), _stream(stream)))
     return mine.view(side, side, 3)
 
 

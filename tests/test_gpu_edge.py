@@ -163,3 +163,21 @@ def test_apply_wrong_clut_size_panics():
         identity.correct_image_with_level(img, np.zeros((27, 27, 3), np.uint8), 4)
     with pytest.raises(lg.LutgenPanic):
         identity.correct_image(img, np.zeros((10, 10, 3), np.uint8))
+
+
+def test_baseline_config4_at_its_stated_size_sampled_against_the_oracle():
+    """BASELINE.json config 4 as stated: GaussianSamplingRemapper, level 12, 512 iterations, 256 synthetic colours
+    (gaussian_sample.rs:49-76). The whole CLUT is generated on the GPU; every 64th entry is checked against the
+    oracle run with the SAME noise table (K is a power of two: bit exact)."""
+    pal = synthetic_palette(256, 1)
+    level, K = 12, 512
+    r = interpolation.GaussianSamplingRemapper(pal, 0.0, 20.0, K, 1.0, 42080085, False)
+    got = r.par_generate_lut(level).reshape(-1, 3)
+    ident = O.identity(level).reshape(-1, 3)
+    idx = np.arange(7, ident.shape[0], 64)
+    px = np.concatenate([ident[idx], np.full((idx.size, 1), 255, np.uint8)], axis=1)
+    o = O.Remapper(O.SAMPLING, pal, mean=0.0, std_dev=20.0, iterations=K, seed=42080085)
+    o.set_noise(r.noise())
+    want = o.remap_image(px)
+    assert (want[:, 3] == 255).all()
+    assert (got[idx] == want[:, :3]).all(), int((got[idx] != want[:, :3]).any(axis=1).sum())

@@ -70,8 +70,9 @@ def main():
         tiles = max(1, int(st[:64].sum()))
         print("tiles", tiles, "(all reps)")
         print("  |UNCERTAIN| histogram:", {i: int(v) for i, v in enumerate(st[:64]) if v})
-        print("  |IN| histogram:", {i: int(v) for i, v in enumerate(st[64:127]) if v})
-        print("  colours sent to the exact kernel:", int(st[127]))
+        print("  |IN| histogram:", {i: int(v) for i, v in enumerate(st[64:126]) if v})
+        print("  near-ties settled by the lane itself (f64 distances only):", int(st[126]))
+        print("  colours evaluated entirely in the reference's f64 arithmetic:", int(st[127]))
 
 
 if __name__ == "__main__":
