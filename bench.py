@@ -343,18 +343,36 @@ def run_b200(args):
     host_frames = [torch.randint(0, 256, (FRAME_H, FRAME_W, 4), dtype=torch.uint8).pin_memory() for _ in range(e2e_frames)]
     host_frames_np = [t.numpy() for t in host_frames]
 
+    # N > 1, CLUT wanted on the host: ONE page-locked image in POSIX shared memory, mapped by every rank; each rank
+    # generates its share of the row groups and copies it to its place over its own PCIe link (no GPU-to-GPU exchange)
+    shared_img = None
+    if world > 1:
+        shm_path = f"/dev/shm/lutgen_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
+        if rank == 0:
+            with open(shm_path, "wb") as f:
+                f.truncate(3 * entries)
+        barrier()
+        shared_img = np.memmap(shm_path, dtype=np.uint8, mode="r+", shape=(side, side, 3))
+        rc = torch.cuda.cudart().cudaHostRegister(shared_img.ctypes.data, 3 * entries, 0)
+        if int(rc) != 0:
+            print(f"rank {rank}: cudaHostRegister of the shared image failed ({rc}); copies will be pageable", file=sys.stderr)
+        barrier()
+        if rank == 0:
+            os.unlink(shm_path)
+
     def gen_e2e():
+        if world > 1:
+            rm = interpolation.GaussianRemapper(pal, GEN_PARAMS["shape"], GEN_PARAMS["nearest"], GEN_PARAMS["lum"], GEN_PARAMS["preserve"])
+            rm.generate_lut_part(LEVEL_GEN, shared_img, rank, world)
+            del rm
+            return
         if world == 1:
             # as `lutgen generate` does (crates/cli/src/main.rs:334-348): the remapper is built per invocation, so its
             # construction (palette upload + Oklab conversion on the device) is inside the timed region
             rm = interpolation.GaussianRemapper(pal, GEN_PARAMS["shape"], GEN_PARAMS["nearest"], GEN_PARAMS["lum"], GEN_PARAMS["preserve"])
             rm.generate_lut(LEVEL_GEN, out=lut16_host.numpy())
             del rm
-        else:
-            full = device.generate_lut_fused(remapper, LEVEL_GEN) if fused else device.generate_lut(remapper, LEVEL_GEN, out=lut16)
-            if rank == 0:
-                lut16_host.copy_(full, non_blocking=True)
-            torch.cuda.synchronize()
+
 
     def apply_e2e():
         identity.correct_images(host_frames_np, lut8_host, LEVEL_APPLY)
@@ -434,6 +452,10 @@ def run_b200(args):
         gen_e2e()
     barrier()
     gen_e2e_t = max_over_ranks((time.perf_counter() - t0) / steps)
+    if rank == 0:
+        host_img = shared_img if world > 1 else lut16_host.numpy()
+        checks["e2e_host_image_matches_device_clut"] = bool((np.asarray(host_img).reshape(-1) == ref16_host.reshape(-1)).all())
+        assert checks["e2e_host_image_matches_device_clut"], "the CLUT delivered to the host differs from the device-resident one"
     host_pristine = [t.clone() for t in host_frames]
     acc = 0.0
     for _ in range(steps):
@@ -465,8 +487,11 @@ def run_b200(args):
         "gpu_launches": int(gen_launches),
         "e2e": {"value": entries / gen_e2e_t, "unit": "entries/s", "h2d_bytes_per_step": 4 * len(pal), "d2h_bytes_per_step": 3 * entries,
                 "ms_per_step": gen_e2e_t * 1e3,
-                "what": "GaussianRemapper(palette, ...) constructed (palette upload: 4 bytes per colour), generate_lut(16) into a page-locked "
-                        "host buffer, remapper dropped -- every step"},
+                "what": ("GaussianRemapper(palette, ...) constructed (palette upload: 4 bytes per colour), generate_lut(16) into a page-locked "
+                         "host buffer, remapper dropped -- every step") if world == 1 else
+                        (f"every rank: GaussianRemapper constructed, lutgen_cuda_generate_lut_part -- its share of the row groups generated and copied "
+                         f"over its own PCIe link into ONE page-locked image in shared memory ({world} ranks, no GPU-to-GPU exchange), remapper dropped -- "
+                         "every step; h2d bytes are per rank")},
         "roofline": {"bound": "fp32", "achieved": gen_achieved, "peak": fp32.value, "unit": "TFLOP/s",
                      "frac": gen_achieved / fp32.value if fp32.value else None,
                      "traffic": profiled_traffic().get("k_remap_warp_level16_bytes_per_launch") if world == 1 else None,

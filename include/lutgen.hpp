@@ -104,6 +104,9 @@ inline void correct_image(RgbaImage& image, const RgbImage& hald_clut) {
 // identity::correct_pixel(&[u8;3], &RgbImage, level) -> [u8;3]   identity.rs:40-52
 inline void correct_pixel(const uint8_t input[3], const RgbImage& hald_clut, uint8_t level, uint8_t output[3]) {
     detail::ensure_init();
+    const uint32_t n = (uint32_t)level * level * level;
+    if (level >= 2 && level <= 33 && (hald_clut.width != n || hald_clut.height != n))   // the reference's get_pixel would panic
+        throw Panic("hald clut is smaller than the level asks for (identity.rs:48-51 indexes out of bounds)");
     detail::check(lutgen_cuda_correct_pixels(input, 1, hald_clut.data.data(), level, output));
 }
 

@@ -19,9 +19,14 @@
  *    seen set -- the reference returns `None`), or a negative LUTGEN_ERR_*. The
  *    library never aborts the process where the reference panics; the message
  *    is available from lutgen_cuda_last_error() (thread local).
- *  - One process drives one GPU (select it with lutgen_cuda_init). Multi-GPU
- *    jobs run one process per GPU and shard rows / frames through the `_dev`
- *    entry points; the collective (NCCL all-gather) lives in the host layer.
+ *  - Multi-GPU, two ways. (1) ONE process, several GPUs -- what a CLI or Studio process is
+ *    (crates/cli/src/main.rs:329-401): lutgen_cuda_init_devices, or LUTGEN_CUDA_DEVICES=0,1,..
+ *    in the environment of an unchanged caller; lutgen_cuda_generate_lut deals the CLUT's
+ *    row groups out to the GPUs, each copying its rows straight into the caller's image,
+ *    lutgen_cuda_apply_hald_batch deals out the frames. Everything else runs on the first
+ *    (primary) device. (2) One process per GPU (torch.distributed / MPI style): rows or
+ *    tiles are sharded through the `_dev` entry points and exchanged by the kernel itself
+ *    (lutgen_cuda_generate_lut_exchange_dev) or by the caller's collective.
  *  - There is no CPU fallback: without a usable sm_100 device every compute
  *    entry point returns LUTGEN_ERR_NO_DEVICE / LUTGEN_ERR_CUDA.
  *  - `stream` arguments are `cudaStream_t` passed as void*; 0 / NULL is CUDA's
@@ -90,6 +95,15 @@ typedef struct lutgen_remapper lutgen_remapper; /* opaque; owns device copies */
  * Idempotent for the same device. Fails with LUTGEN_ERR_NO_DEVICE when there is
  * no device of compute capability 10.x. */
 LUTGEN_API int lutgen_cuda_init(int device);
+/* The same for a list of distinct devices (at most 8; devices[0] is the primary one): one context, stream set and
+ * host worker thread per GPU. With more than one device lutgen_cuda_generate_lut and lutgen_cuda_apply_hald_batch
+ * shard their work over all of them (GenerateLut::par_generate_lut, crates/lib/src/lib.rs:143-147, and the frame loop
+ * of crates/cli/src/main.rs:878-888 are one call each in the reference: the sharding is invisible to the caller);
+ * every other entry point uses the primary device. lutgen_cuda_init(-1) calls this with the devices named in
+ * $LUTGEN_CUDA_DEVICES ("0,1,2,3") when that variable is set. */
+LUTGEN_API int lutgen_cuda_init_devices(const int* devices, int ndevices);
+/* Devices this process was initialised with (0 before lutgen_cuda_init*). */
+LUTGEN_API int lutgen_cuda_device_count_in_use(int* count);
 LUTGEN_API int lutgen_cuda_shutdown(void);
 LUTGEN_API int lutgen_cuda_device_count(int* count);
 LUTGEN_API const char* lutgen_cuda_last_error(void);
@@ -143,6 +157,15 @@ LUTGEN_API int lutgen_cuda_remapper_destroy(lutgen_remapper* r);
  * unspecified (the reference returns None, lib.rs:149-170). */
 LUTGEN_API int lutgen_cuda_generate_lut(const lutgen_remapper* r, uint8_t level, uint8_t* out_rgb,
                                         const volatile uint8_t* abort_flag);
+
+/* One process per GPU, CLUT wanted on the HOST: part `part_index` of `part_count` of the CLUT -- the row groups this
+ * rank is dealt, round robin -- generated on this process's GPU and copied to their places in out_rgb, the WHOLE
+ * image's base address (e.g. a buffer in shared memory that every rank has mapped, and page-locked with
+ * cudaHostRegister for full PCIe speed). Every rank uses its own PCIe link; no GPU-to-GPU exchange is needed. The
+ * image is complete when all ranks have returned. Same arithmetic as lutgen_cuda_generate_lut, so the bytes are those
+ * of one GPU. (crates/lib/src/lib.rs:143-147 par_generate_lut, sharded by rows.) */
+LUTGEN_API int lutgen_cuda_generate_lut_part(const lutgen_remapper* r, uint8_t level, uint8_t* out_rgb, uint32_t part_index, uint32_t part_count,
+                                             const volatile uint8_t* abort_flag);
 
 /* GenerateLut::generate_lut / generate_lut_with_interrupt, the SEQUENTIAL spellings (lib.rs:113-132). Identical to
  * lutgen_cuda_generate_lut for every remapper but GaussianBlurRemapper, whose sequential generate_lut_inner carries

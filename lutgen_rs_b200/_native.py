@@ -28,7 +28,8 @@ EXPORTS = [
     "lutgen_cuda_generate_lut_rows_multi_dev", "lutgen_cuda_device_alloc", "lutgen_cuda_device_free",
     "lutgen_cuda_ipc_export", "lutgen_cuda_ipc_import", "lutgen_cuda_ipc_close",
     "lutgen_cuda_generate_lut_shard_multi_dev", "lutgen_cuda_peer_barrier_dev", "lutgen_cuda_generate_lut_shard_mc_dev",
-    "lutgen_cuda_generate_lut_exchange_dev",
+    "lutgen_cuda_generate_lut_exchange_dev", "lutgen_cuda_init_devices", "lutgen_cuda_device_count_in_use",
+    "lutgen_cuda_generate_lut_part",
     "lutgen_cuda_generate_lut_sequential",
     "lutgen_cuda_png_bound", "lutgen_cuda_encode_png", "lutgen_cuda_encode_png_dev", "lutgen_cuda_generate_lut_png",
     "lutgen_cuda_apply_hald_png", "lutgen_cuda_extract_palette",
@@ -115,6 +116,9 @@ def load():
             "lutgen_cuda_generate_lut_shard_multi_dev": ([vp, u8, C.POINTER(vp), i32, u32, u32, vp], i32),
             "lutgen_cuda_generate_lut_shard_mc_dev": ([vp, u8, C.POINTER(vp), i32, vp, u32, u32, vp], i32),
             "lutgen_cuda_generate_lut_exchange_dev": ([vp, u8, C.POINTER(vp), i32, vp, u32, u32, vp, vp], i32),
+            "lutgen_cuda_init_devices": ([C.POINTER(i32), i32], i32),
+            "lutgen_cuda_generate_lut_part": ([vp, u8, vp, u32, u32, vp], i32),
+            "lutgen_cuda_device_count_in_use": ([C.POINTER(i32)], i32),
             "lutgen_cuda_peer_barrier_dev": ([vp, i32, i32, u32, vp], i32),
             "lutgen_cuda_device_alloc": ([sz, C.POINTER(vp)], i32),
             "lutgen_cuda_device_free": ([vp], i32),
@@ -160,6 +164,24 @@ def init(device=-1):
         check(L.lutgen_cuda_init(int(device)))
         _initialised = True
     return L
+
+
+def init_devices(devices):
+    """One process, several GPUs (lutgen_cuda_init_devices): generate_lut and correct_images shard their work over
+    them; devices[0] is the primary device every other entry point uses."""
+    global _initialised
+    L = load()
+    arr = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+    check(L.lutgen_cuda_init_devices(arr, len(devices)))
+    _initialised = True
+    return L
+
+
+def shutdown():
+    """Release every device (remappers must have been dropped first)."""
+    global _initialised
+    check(load().lutgen_cuda_shutdown())
+    _initialised = False
 
 
 def lib():

@@ -10,8 +10,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -124,6 +127,80 @@ struct UseCtx {
     }
 };
 
+// One host thread per additional GPU, bound to its context for life: the entry points that shard their work over
+// the process's GPUs hand every device its share as a job; the calling thread does device 0's share itself. (One
+// thread issuing for all devices would serialise on every copy to or from pageable host memory -- such copies block
+// their caller -- and a caller's RgbImage is pageable.)
+struct Worker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<int()> job;
+    bool has_job = false, done = false, quit = false;
+    int rc = 0;
+    std::string err;
+};
+Worker* g_workers[kMaxDevices] = {};
+
+void worker_main(int index) {
+    tl_ctx = &g_ctx[index];
+    cudaSetDevice(tl_ctx->device);
+    Worker& w = *g_workers[index];
+    std::unique_lock<std::mutex> lk(w.mu);
+    for (;;) {
+        w.cv.wait(lk, [&] { return w.has_job || w.quit; });
+        if (w.quit) return;
+        lk.unlock();
+        int rc = w.job();
+        lk.lock();
+        w.rc = rc;
+        w.err = rc ? g_err : std::string();
+        w.has_job = false;
+        w.done = true;
+        w.cv.notify_all();
+    }
+}
+
+void worker_submit(int index, std::function<int()> job) {
+    Worker& w = *g_workers[index];
+    std::lock_guard<std::mutex> lk(w.mu);
+    w.job = std::move(job);
+    w.has_job = true;
+    w.done = false;
+    w.cv.notify_all();
+}
+
+int worker_wait(int index) {
+    Worker& w = *g_workers[index];
+    std::unique_lock<std::mutex> lk(w.mu);
+    w.cv.wait(lk, [&] { return w.done; });
+    w.done = false;
+    if (w.rc) g_err = w.err;
+    return w.rc;
+}
+
+void workers_start(int ndev) {
+    for (int i = 1; i < ndev; ++i) {
+        g_workers[i] = new Worker();
+        g_workers[i]->th = std::thread(worker_main, i);
+    }
+}
+
+void workers_stop() {
+    for (int i = 1; i < kMaxDevices; ++i) {
+        Worker* w = g_workers[i];
+        if (!w) continue;
+        {
+            std::lock_guard<std::mutex> lk(w->mu);
+            w->quit = true;
+            w->cv.notify_all();
+        }
+        w->th.join();
+        delete w;
+        g_workers[i] = nullptr;
+    }
+}
+
 int ensure_ready() {
     if (!g.ready) return fail(LUTGEN_ERR_NO_DEVICE, "lutgen_cuda_init has not succeeded in this process (no CPU fallback exists)");
     cudaError_t e = cudaSetDevice(g.device);
@@ -148,6 +225,10 @@ struct lutgen_remapper {
     uint32_t n = 0;
     uint32_t k_eff = 0;              // 0: every colour
     std::vector<uint8_t> pal_host;   // n x 3
+    int ctx_index = 0;               // the context (GPU) this object's device state lives on
+    // the same remapper on the process's other GPUs, made on first use by the entry points that shard their work over
+    // all of them (generate_lut); replica[0] is unused
+    mutable lutgen_remapper* replica[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     void* arena = nullptr;           // one stream-ordered allocation holding every palette array below (and the upal_* ones)
     uint8_t* pal_rgb4 = nullptr;     // device n x 4
     double* pal_lab = nullptr;       // device n x 3
@@ -159,6 +240,7 @@ struct lutgen_remapper {
     mutable uint32_t* nn_table = nullptr;  // device 2^24 x u32, built lazily
     mutable bool nn_table_ready = false;
     mutable std::mutex mu;
+    mutable std::mutex table_mu;     // held for the whole of a table build (nn_table / full_table): concurrent callers build it once
     mutable cudaEvent_t nn_table_ev = nullptr;
     // whole-cube table of the remapper itself (r | g<<8 | b<<16 per sRGB colour): large images
     // are remapped as "build the level-16 CLUT once, then gather" (remap_pixel is a pure function
@@ -580,6 +662,7 @@ int launch_rbf(const Front& f, const lutgen_remapper* r, cudaStream_t s) {
 
 // NN over the whole sRGB cube, once per sampling remapper (see kernels_apply.cuh).
 int ensure_nn_table(const lutgen_remapper* r, cudaStream_t s) {
+    std::lock_guard<std::mutex> build(r->table_mu);
     std::unique_lock<std::mutex> lk(r->mu);
     if (!r->nn_table_ready) {
         if (!r->nn_table) CU_TRY(cudaMalloc((void**)&r->nn_table, sizeof(uint32_t) << 24));
@@ -770,6 +853,7 @@ int launch_remap(const Front& f, const lutgen_remapper* r, cudaStream_t s);
 
 // The remapper tabulated over all 2^24 colours (= its level-16 CLUT in packed form).
 int ensure_full_table(const lutgen_remapper* r, cudaStream_t s) {
+    std::lock_guard<std::mutex> build(r->table_mu);
     std::unique_lock<std::mutex> lk(r->mu);
     if (!r->full_table_ready) {
         if (!r->full_table) CU_TRY(cudaMalloc((void**)&r->full_table, sizeof(uint32_t) << 24));
@@ -833,6 +917,11 @@ int launch_apply(uint8_t* rgba_dev, size_t npix, const uint32_t* lut_rgbx, uint8
     // enough resident work to cover the gather latency, capped so the grid-stride loop amortises launch
     size_t cap = (size_t)g.sm_count * 64;
     unsigned grid = (unsigned)(want < cap ? want : cap);
+    static bool carve_done[kMaxDevices] = {};
+    if (!carve_done[g.index]) {   // no shared memory in this kernel: the whole unified array as L1 (see kernels_apply.cuh)
+        CU_TRY(cudaFuncSetAttribute(k_apply, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+        carve_done[g.index] = true;
+    }
     k_apply<<<grid, 256, 0, s>>>((uint32_t*)rgba_dev, npix, head, nvec, lut_rgbx, cs, cs - 1);
     LAUNCH_CHECK();
     return LUTGEN_OK;
@@ -969,6 +1058,7 @@ int lutgen_cuda_init_devices(const int* devices, int ndevices) {
     }
     g_ndev = ndevices;
     cudaSetDevice(g_ctx[0].device);
+    workers_start(ndevices);
     return LUTGEN_OK;
 }
 
@@ -1011,6 +1101,7 @@ int lutgen_cuda_init(int device) {
 int lutgen_cuda_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_init_mu);
     if (g_ndev == 0) return LUTGEN_OK;
+    workers_stop();
     {
         UseCtx u(0);
         png_release();
@@ -1115,18 +1206,16 @@ int lutgen_cuda_apply_hald(uint8_t* rgba, size_t npix, const uint8_t* lut_rgb, u
     return LUTGEN_OK;
 }
 
-int lutgen_cuda_apply_hald_batch(uint8_t* const* frames, const size_t* npix, size_t nframes, const uint8_t* lut_rgb, uint8_t level) {
+namespace {
+// Frames first, first + stride, ... on the current context: CLUT up once, then a three-stream pipeline (frame i's
+// upload overlaps frame i-1's kernel and frame i-2's download: separate copy engines per direction).
+int apply_batch_share(uint8_t* const* frames, const size_t* npix, size_t nframes, const uint8_t* lut_rgb, uint8_t level, size_t first, size_t stride) {
     int rc = ensure_ready();
     if (rc) return rc;
-    if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33", level);
-    if (!lut_rgb || (nframes && (!frames || !npix))) return fail(LUTGEN_ERR_INVALID, "NULL buffer");
-    if (nframes == 0) return LUTGEN_OK;
     std::lock_guard<std::mutex> lk(g.mu);
     size_t lut_bytes = 3 * lut_entries(level), max_px = 0;
-    for (size_t i = 0; i < nframes; ++i) {
-        if (npix[i] && !frames[i]) return fail(LUTGEN_ERR_INVALID, "frame %zu is NULL", i);
+    for (size_t i = first; i < nframes; i += stride)
         if (npix[i] > max_px) max_px = npix[i];
-    }
     if (max_px == 0) return LUTGEN_OK;
     CU_TRY(g.lut_rgb.reserve(lut_bytes));
     CU_TRY(cudaMemcpyAsync(g.lut_rgb.p, lut_rgb, lut_bytes, cudaMemcpyHostToDevice, g.stream));
@@ -1134,26 +1223,55 @@ int lutgen_cuda_apply_hald_batch(uint8_t* const* frames, const size_t* npix, siz
     if (rc) return rc;
     cudaEvent_t lut_ready;
     CU_TRY(cudaEventCreateWithFlags(&lut_ready, cudaEventDisableTiming));
-    CU_TRY(cudaEventRecord(lut_ready, g.stream));
-    for (int i = 0; i < kBatchStreams; ++i) {
-        CU_TRY(g.batch_frames[i].reserve(max_px * 4));
-        CU_TRY(cudaStreamWaitEvent(g.batch_streams[i], lut_ready, 0));
+    int result = LUTGEN_OK;
+    cudaError_t e = cudaEventRecord(lut_ready, g.stream);
+    for (int i = 0; i < kBatchStreams && e == cudaSuccess; ++i) {
+        e = g.batch_frames[i].reserve(max_px * 4);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(g.batch_streams[i], lut_ready, 0);
     }
-    // Frame i rides stream i % 3: its upload overlaps frame i-1's kernel and
-    // frame i-2's download (separate copy engines per direction).
-    for (size_t i = 0; i < nframes; ++i) {
+    size_t k = 0;
+    for (size_t i = first; i < nframes && e == cudaSuccess && result == LUTGEN_OK; i += stride) {
         if (!npix[i]) continue;
-        int b = (int)(i % kBatchStreams);
+        int b = (int)(k++ % kBatchStreams);
         cudaStream_t s = g.batch_streams[b];
         uint8_t* dev = (uint8_t*)g.batch_frames[b].p;
-        CU_TRY(cudaMemcpyAsync(dev, frames[i], npix[i] * 4, cudaMemcpyHostToDevice, s));
-        rc = launch_apply(dev, npix[i], (const uint32_t*)g.lut_rgbx.p, level, s);
-        if (rc) return rc;
-        CU_TRY(cudaMemcpyAsync(frames[i], dev, npix[i] * 4, cudaMemcpyDeviceToHost, s));
+        e = cudaMemcpyAsync(dev, frames[i], npix[i] * 4, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) break;
+        result = launch_apply(dev, npix[i], (const uint32_t*)g.lut_rgbx.p, level, s);
+        if (result != LUTGEN_OK) break;
+        e = cudaMemcpyAsync(frames[i], dev, npix[i] * 4, cudaMemcpyDeviceToHost, s);
     }
-    for (int i = 0; i < kBatchStreams; ++i) CU_TRY(cudaStreamSynchronize(g.batch_streams[i]));
+    // whatever happened, nothing may still be copying from or into the caller's frames when this returns
+    for (int i = 0; i < kBatchStreams; ++i) {
+        cudaError_t es = cudaStreamSynchronize(g.batch_streams[i]);
+        if (e == cudaSuccess) e = es;
+    }
     cudaEventDestroy(lut_ready);
+    if (result != LUTGEN_OK) return result;
+    if (e != cudaSuccess) return fail(LUTGEN_ERR_CUDA, "apply_hald_batch: %s", cudaGetErrorString(e));
     return LUTGEN_OK;
+}
+}  // namespace
+
+int lutgen_cuda_apply_hald_batch(uint8_t* const* frames, const size_t* npix, size_t nframes, const uint8_t* lut_rgb, uint8_t level) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33", level);
+    if (!lut_rgb || (nframes && (!frames || !npix))) return fail(LUTGEN_ERR_INVALID, "NULL buffer");
+    if (nframes == 0) return LUTGEN_OK;
+    for (size_t i = 0; i < nframes; ++i)
+        if (npix[i] && !frames[i]) return fail(LUTGEN_ERR_INVALID, "frame %zu is NULL", i);
+    // several GPUs in this process: frames are dealt out round robin, every GPU runs its own pipeline (no exchange)
+    const int ndev = tl_ctx == &g_ctx[0] ? (int)std::min<size_t>((size_t)g_ndev, nframes) : 1;
+    for (int i = 1; i < ndev; ++i) worker_submit(i, [=] { return apply_batch_share(frames, npix, nframes, lut_rgb, level, (size_t)i, (size_t)ndev); });
+    int result = apply_batch_share(frames, npix, nframes, lut_rgb, level, 0, (size_t)(ndev > 1 ? ndev : 1));
+    std::string first_err = result ? g_err : std::string();
+    for (int i = 1; i < ndev; ++i) {
+        int wrc = worker_wait(i);
+        if (wrc && result == LUTGEN_OK) { result = wrc; first_err = g_err; }
+    }
+    if (result) g_err = first_err;
+    return result;
 }
 
 int lutgen_cuda_correct_pixels(const uint8_t* in_rgb, size_t n, const uint8_t* lut_rgb, uint8_t level, uint8_t* out_rgb) {
@@ -1185,8 +1303,12 @@ int lutgen_cuda_correct_pixels(const uint8_t* in_rgb, size_t n, const uint8_t* l
 // ---------------------------------------------------------------------------
 int lutgen_cuda_remapper_destroy(lutgen_remapper* r) {
     if (!r) return LUTGEN_OK;
+    for (int i = 1; i < kMaxDevices; ++i) {
+        if (r->replica[i]) lutgen_cuda_remapper_destroy(r->replica[i]);
+        r->replica[i] = nullptr;
+    }
+    UseCtx use(r->ctx_index);
     if (g.ready) {
-        cudaSetDevice(g.device);
         cudaDeviceSynchronize();
         if (r->arena) cudaFreeAsync(r->arena, g.stream);   // back to the pool: creating the next remapper costs no cudaMalloc
         cudaFree(r->offsets);
@@ -1231,6 +1353,7 @@ int lutgen_cuda_remapper_create(const lutgen_remapper_desc* desc, lutgen_remappe
         return fail(LUTGEN_ERR_INVALID, "empty palette (kiddo nearest_one on an empty tree panics)");
     std::lock_guard<std::mutex> lk(g.mu);
     lutgen_remapper* r = new lutgen_remapper();
+    r->ctx_index = g.index;
     r->d = *desc;
     r->n = (uint32_t)desc->palette_len;
     r->pal_host.assign(desc->palette, desc->palette + 3 * (size_t)r->n);
@@ -1357,6 +1480,10 @@ int lutgen_cuda_sampling_set_noise(lutgen_remapper* r, const double* noise) {
     if (!r || !noise) return fail(LUTGEN_ERR_INVALID, "NULL argument");
     if (r->d.kind != LUTGEN_SAMPLING) return fail(LUTGEN_ERR_INVALID, "not a sampling remapper");
     std::lock_guard<std::mutex> lk(g.mu);
+    for (int i = 1; i < kMaxDevices; ++i) {   // the other GPUs' copies are rebuilt, with this table, on next use
+        if (r->replica[i]) lutgen_cuda_remapper_destroy(r->replica[i]);
+        r->replica[i] = nullptr;
+    }
     std::vector<double> old = r->noise;
     r->noise.assign(noise, noise + r->noise.size());
     {
@@ -1413,6 +1540,27 @@ int lutgen_cuda_generate_lut(const lutgen_remapper* r, uint8_t level, uint8_t* o
 
 int lutgen_cuda_generate_lut_sequential(const lutgen_remapper* r, uint8_t level, uint8_t* out_rgb, const volatile uint8_t* abort_flag) {
     return generate_lut_impl(r, level, out_rgb, abort_flag, 1);
+}
+
+namespace {
+int generate_lut_share(const lutgen_remapper* r, uint8_t level, uint8_t* out_rgb, const volatile uint8_t* abort_flag, int sequential, uint32_t chunks,
+                       uint32_t first, uint32_t stride);
+}
+
+int lutgen_cuda_generate_lut_part(const lutgen_remapper* r, uint8_t level, uint8_t* out_rgb, uint32_t part_index, uint32_t part_count,
+                                  const volatile uint8_t* abort_flag) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!r || !out_rgb) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33", level);
+    if (part_count == 0 || part_index >= part_count) return fail(LUTGEN_ERR_INVALID, "part %u of %u", part_index, part_count);
+    if (abort_flag && *abort_flag) return LUTGEN_ABORTED;
+    const uint32_t side = (uint32_t)level * level * level, ngroups = (side + 16u * level - 1) / (16u * level);
+    // the same dealing-out as lutgen_cuda_generate_lut does over the GPUs of one process
+    uint32_t chunks = std::min<uint32_t>(ngroups, part_count * (ngroups >= 2u * part_count ? 2u : 1u));
+    if (abort_flag) chunks = std::min<uint32_t>(ngroups, std::max<uint32_t>(chunks, 8u));
+    if (part_index >= chunks) return LUTGEN_OK;   // more parts than row groups: nothing for this one
+    return generate_lut_share(r, level, out_rgb, abort_flag, 0, chunks, part_index, part_count);
 }
 
 int lutgen_cuda_generate_lut_rows_multi_dev(const lutgen_remapper* r, uint8_t level, uint8_t* const* luts_rgb_dev, int nluts, uint32_t row_begin,
@@ -1564,12 +1712,12 @@ int lutgen_cuda_ipc_close(void* dev_ptr) {
 }
 
 namespace {
-int generate_lut_impl(const lutgen_remapper* r, uint8_t level, uint8_t* out_rgb, const volatile uint8_t* abort_flag, int sequential) {
+// The current context's share of a CLUT into the caller's host image: chunks `first`, first + `stride`, ... of `chunks`
+// equal runs of row groups (the whole CLUT for first = 0, stride = 1). `r` lives on the current context.
+int generate_lut_share(const lutgen_remapper* r, uint8_t level, uint8_t* out_rgb, const volatile uint8_t* abort_flag, int sequential, uint32_t chunks,
+                       uint32_t first, uint32_t stride) {
     int rc = ensure_ready();
     if (rc) return rc;
-    if (!r || !out_rgb) return fail(LUTGEN_ERR_INVALID, "NULL argument");
-    if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33", level);
-    if (abort_flag && *abort_flag) return LUTGEN_ABORTED;
     std::lock_guard<std::mutex> lk(g.mu);
     size_t bytes = 3 * lut_entries(level);
     uint32_t side = (uint32_t)level * level * level;
@@ -1580,14 +1728,12 @@ int generate_lut_impl(const lutgen_remapper* r, uint8_t level, uint8_t* out_rgb,
     // of 16 blue planes (16*level rows), the kernels' brick depth, so no brick is visited twice.
     const uint32_t group = 16u * level;
     uint32_t ngroups = (side + group - 1) / group;
-    uint32_t chunks = (bytes >= (8u << 20)) ? 4u : 1u;
-    if (abort_flag && chunks < 8u) chunks = 8u;
-    if (chunks > ngroups) chunks = ngroups;
     cudaStream_t copy_stream = g.batch_streams[0];
-    cudaEvent_t done[8];
+    cudaEvent_t done[64];
+    if (chunks > 64u) chunks = 64u;
     for (uint32_t c = 0; c < chunks; ++c) CU_TRY(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
     int result = LUTGEN_OK;
-    for (uint32_t c = 0; c < chunks && result == LUTGEN_OK; ++c) {
+    for (uint32_t c = first; c < chunks && result == LUTGEN_OK; c += stride) {
         uint32_t r0 = (uint32_t)((uint64_t)ngroups * c / chunks) * group, r1 = (uint32_t)((uint64_t)ngroups * (c + 1) / chunks) * group;
         if (r1 > side) r1 = side;
         rc = generate_lut_rows_impl(r, level, (uint8_t*)g.lut_rgb.p, r0, r1, g.stream, sequential);
@@ -1609,6 +1755,71 @@ int generate_lut_impl(const lutgen_remapper* r, uint8_t level, uint8_t* out_rgb,
         return fail(LUTGEN_ERR_CUDA, "generate_lut: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     if (abort_flag && *abort_flag) return LUTGEN_ABORTED;
     return LUTGEN_OK;
+}
+
+// The same remapper on context `index` (made on first use; r->mu held by the caller).
+int ensure_replica(const lutgen_remapper* r, int index) {
+    if (r->replica[index]) return LUTGEN_OK;
+    UseCtx use(index);
+    lutgen_remapper* rep = nullptr;
+    lutgen_remapper_desc d = r->d;
+    d.palette = r->pal_host.data();
+    int rc = lutgen_cuda_remapper_create(&d, &rep);
+    if (rc) return rc;
+    if (r->d.kind == LUTGEN_SAMPLING && !r->noise.empty()) {   // the same noise table, whatever the caller has set
+        rc = lutgen_cuda_sampling_set_noise(rep, r->noise.data());
+        if (rc) {
+            lutgen_cuda_remapper_destroy(rep);
+            return rc;
+        }
+    }
+    r->replica[index] = rep;
+    return LUTGEN_OK;
+}
+
+int generate_lut_impl(const lutgen_remapper* r, uint8_t level, uint8_t* out_rgb, const volatile uint8_t* abort_flag, int sequential) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!r || !out_rgb) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33", level);
+    if (abort_flag && *abort_flag) return LUTGEN_ABORTED;
+    const size_t bytes = 3 * lut_entries(level);
+    const uint32_t side = (uint32_t)level * level * level, ngroups = (side + 16u * level - 1) / (16u * level);
+    // Several GPUs in this process (lutgen_cuda_init_devices / LUTGEN_CUDA_DEVICES): the row groups are dealt out to
+    // them round robin (dark and light ends of the cube cost differently), every GPU computes its groups with its
+    // own copy of the remapper and copies them straight into the caller's image over its own PCIe link -- no exchange
+    // between the GPUs is needed for a CLUT that is wanted on the host. GaussianBlurRemapper stays on one GPU: its
+    // cost is the blurred volume, which every GPU would have to compute in full.
+    const int ndev = (tl_ctx == &g_ctx[0] && r->ctx_index == 0 && r->d.kind != LUTGEN_BLUR && bytes >= (4u << 20)) ? std::min<int>(g_ndev, (int)ngroups) : 1;
+    if (ndev > 1) {
+        {
+            std::lock_guard<std::mutex> lk(r->mu);
+            for (int i = 1; i < ndev; ++i) {
+                rc = ensure_replica(r, i);
+                if (rc) return rc;
+            }
+        }
+        // at least two chunks per GPU so that a chunk's download overlaps the next one's kernel
+        uint32_t chunks = std::min<uint32_t>(ngroups, (uint32_t)ndev * (ngroups >= 2u * ndev ? 2u : 1u));
+        if (abort_flag) chunks = std::min<uint32_t>(ngroups, std::max<uint32_t>(chunks, 8u));
+        for (int i = 1; i < ndev; ++i) {
+            const lutgen_remapper* rep = r->replica[i];
+            worker_submit(i, [=] { return generate_lut_share(rep, level, out_rgb, abort_flag, sequential, chunks, (uint32_t)i, (uint32_t)ndev); });
+        }
+        int result = generate_lut_share(r, level, out_rgb, abort_flag, sequential, chunks, 0u, (uint32_t)ndev);
+        std::string first_err = result ? g_err : std::string();
+        for (int i = 1; i < ndev; ++i) {
+            int wrc = worker_wait(i);
+            if (wrc && (result == LUTGEN_OK || result == LUTGEN_ABORTED) && wrc != LUTGEN_ABORTED) { result = wrc; first_err = g_err; }
+            else if (wrc == LUTGEN_ABORTED && result == LUTGEN_OK) result = wrc;
+        }
+        if (result && result != LUTGEN_ABORTED) g_err = first_err;
+        return result;
+    }
+    uint32_t chunks = (bytes >= (8u << 20)) ? 4u : 1u;
+    if (abort_flag && chunks < 8u) chunks = 8u;
+    if (chunks > ngroups) chunks = ngroups;
+    return generate_lut_share(r, level, out_rgb, abort_flag, sequential, chunks, 0u, 1u);
 }
 }  // namespace
 

@@ -40,8 +40,10 @@
 
 namespace lutgen {
 
+// Two CTAs of 256 threads per SM (128 registers per thread, no spills) measured 5 % faster than three (80 registers):
+// the kernel is bound by instruction delivery and issue, not by latency that more resident warps would hide.
 #ifndef WT_MINB
-#define WT_MINB 3
+#define WT_MINB 2
 #endif
 constexpr int WT_THREADS = 256;
 constexpr int WT_WARPS = WT_THREADS / 32;
@@ -189,27 +191,51 @@ __device__ __forceinline__ PairAcc wt_select_c(const float4* __restrict__ unc, i
               (((my[C] - my[C - 1] <= fmaf(fabsf(my[C]), 4e-6f, tol)) && (my[C] < INFINITY)) ? 2u : 0u);
     r.tau = top ? make_float2(-mx[C], -my[C]) : make_float2(mx[C - 1], my[C - 1]);
     r.nxt = top ? make_float2(-mx[C - 1], -my[C - 1]) : make_float2(mx[C], my[C]);
-    if constexpr (C <= 2) {
+    static_assert(C <= 2, "deeper choices: wt_select_deep");
 #pragma unroll
-        for (int t = 0; t < C; ++t) {
-            wt_add_one<KIND>(unc, mx[t], sgn, c1, c0, r.n0.x, r.n1.x, r.n2.x, r.den.x);
-            wt_add_one<KIND>(unc, my[t], sgn, c1, c0, r.n0.y, r.n1.y, r.n2.y, r.den.y);
-        }
-    } else {
-        // three to five (11 % of the choosing tiles): a second rolled pass, every colour whose tagged score is at most the C-th
+    for (int t = 0; t < C; ++t) {
+        wt_add_one<KIND>(unc, mx[t], sgn, c1, c0, r.n0.x, r.n1.x, r.n2.x, r.den.x);
+        wt_add_one<KIND>(unc, my[t], sgn, c1, c0, r.n0.y, r.n1.y, r.n2.y, r.den.y);
+    }
+    return r;
+}
+
+// c = 3 .. WT_TRACK - 1 (11 % of the choosing tiles), ONE copy of the code for all of them: the WT_TRACK smallest are
+// tracked whatever c is, the boundary pair is picked by uniform selects, and a second rolled pass adds (or takes out
+// again) every colour whose tagged score is at most the c-th.
+template <int KIND>
+__device__ __noinline__ PairAcc wt_select_deep(const float4* __restrict__ unc, int mU, int c, bool top, f2 L, f2 A, f2 B, float c1, float c0, float tol) {
+    PairAcc r;
+    r.n0 = r.n1 = r.n2 = r.den = splat(0.f);
+    float mx[WT_TRACK], my[WT_TRACK];
+#pragma unroll
+    for (int t = 0; t < WT_TRACK; ++t) mx[t] = my[t] = INFINITY;
+    const float sgn = top ? -1.0f : 1.0f;
 #pragma unroll 1
-        for (int i = 0; i < mU; ++i) {
-            const float4 q = unc[i];
-            const f2 sc = wt_score2<KIND>(q, L, A, B);
-            const f2 sg = mul2(sc, splat(sgn));
-            f2 w = mul2(wt_weight2<KIND>(sc, c1, c0), splat(sgn));
-            w.x = __uint_as_float((__float_as_uint(sg.x) & ~15u) | (uint32_t)i) <= mx[C - 1] ? w.x : 0.f;
-            w.y = __uint_as_float((__float_as_uint(sg.y) & ~15u) | (uint32_t)i) <= my[C - 1] ? w.y : 0.f;
-            r.n0 = fma2(splat(q.x), w, r.n0);
-            r.n1 = fma2(splat(q.y), w, r.n1);
-            r.n2 = fma2(splat(q.z), w, r.n2);
-            r.den = add2(r.den, w);
-        }
+    for (int i = 0; i < mU; ++i) {
+        const f2 sg = mul2(wt_score2<KIND>(unc[i], L, A, B), splat(sgn));
+        wt_track<WT_TRACK>(mx, __uint_as_float((__float_as_uint(sg.x) & ~15u) | (uint32_t)i));
+        wt_track<WT_TRACK>(my, __uint_as_float((__float_as_uint(sg.y) & ~15u) | (uint32_t)i));
+    }
+    static_assert(WT_TRACK == 6, "the selects below pick m[c-1], m[c] for c = 3, 4, 5");
+    const float lox = c == 3 ? mx[2] : (c == 4 ? mx[3] : mx[4]), hix = c == 3 ? mx[3] : (c == 4 ? mx[4] : mx[5]);
+    const float loy = c == 3 ? my[2] : (c == 4 ? my[3] : my[4]), hiy = c == 3 ? my[3] : (c == 4 ? my[4] : my[5]);
+    r.risky = (((hix - lox <= fmaf(fabsf(hix), 4e-6f, tol)) && (hix < INFINITY)) ? 1u : 0u) |
+              (((hiy - loy <= fmaf(fabsf(hiy), 4e-6f, tol)) && (hiy < INFINITY)) ? 2u : 0u);
+    r.tau = top ? make_float2(-hix, -hiy) : make_float2(lox, loy);
+    r.nxt = top ? make_float2(-lox, -loy) : make_float2(hix, hiy);
+#pragma unroll 1
+    for (int i = 0; i < mU; ++i) {
+        const float4 q = unc[i];
+        const f2 sc = wt_score2<KIND>(q, L, A, B);
+        const f2 sg = mul2(sc, splat(sgn));
+        f2 w = mul2(wt_weight2<KIND>(sc, c1, c0), splat(sgn));
+        w.x = __uint_as_float((__float_as_uint(sg.x) & ~15u) | (uint32_t)i) <= lox ? w.x : 0.f;
+        w.y = __uint_as_float((__float_as_uint(sg.y) & ~15u) | (uint32_t)i) <= loy ? w.y : 0.f;
+        r.n0 = fma2(splat(q.x), w, r.n0);
+        r.n1 = fma2(splat(q.y), w, r.n1);
+        r.n2 = fma2(splat(q.z), w, r.n2);
+        r.den = add2(r.den, w);
     }
     return r;
 }
@@ -219,9 +245,7 @@ __device__ __forceinline__ PairAcc wt_select_small(const float4* __restrict__ un
                                                    float tol) {
     if (c == 1) return wt_select_c<KIND, 1>(unc, mU, top, L, A, B, c1, c0, tol);
     if (c == 2) return wt_select_c<KIND, 2>(unc, mU, top, L, A, B, c1, c0, tol);
-    if (c == 3) return wt_select_c<KIND, 3>(unc, mU, top, L, A, B, c1, c0, tol);
-    if (c == 4) return wt_select_c<KIND, 4>(unc, mU, top, L, A, B, c1, c0, tol);
-    return wt_select_c<KIND, 5>(unc, mU, top, L, A, B, c1, c0, tol);
+    return wt_select_deep<KIND>(unc, mU, c, top, L, A, B, c1, c0, tol);
 }
 
 // Anything else (more than 16 uncertain colours, or neither side of the choice is small): per entry, one pass
@@ -566,14 +590,21 @@ __device__ __forceinline__ void wt_convert_brick(const WarpArgs& a, const WtShar
     T.slot0 = (b0 * cs + g) * cs + r;
     T.slot_step = cs * cs;
     T.valid_mask = 0;
-#pragma unroll
+    static_assert(NP == 2, "the rolled loop below stores its pair with a uniform branch");
+#ifdef WT_CONV_ROLLED
+#pragma unroll 1
+#else
+#pragma unroll   // both pairs inline: measured 3 % faster than one rolled copy (unlike the per-entry part below)
+#endif
     for (int i = 0; i < NP; ++i) {
         const uint32_t bA = b0 + 2 * i, bB = bA + 1, bcA = min(bA, csm1), bcB = min(bB, csm1);
         const f2 linb = make_float2(sh.lin[bcA], sh.lin[bcB]);
-        T.Bq[2 * i] = sh.chv[bcA];
-        T.Bq[2 * i + 1] = sh.chv[bcB];
+        const uint32_t qA = sh.chv[bcA], qB = sh.chv[bcB];
+        f2 L, A, B;
         lms_to_lab2(fma2(splat(0.0514459929f), linb, splat(pl)), fma2(splat(0.1073969566f), linb, splat(pm)),
-                    fma2(splat(0.6299787005f), linb, splat(ps)), a.lum, T.Lp[i], T.Ap[i], T.Bp[i]);
+                    fma2(splat(0.6299787005f), linb, splat(ps)), a.lum, L, A, B);
+        if (i) { T.Lp[1] = L; T.Ap[1] = A; T.Bp[1] = B; T.Bq[2] = qA; T.Bq[3] = qB; }
+        else { T.Lp[0] = L; T.Ap[0] = A; T.Bp[0] = B; T.Bq[0] = qA; T.Bq[1] = qB; }
         if (!a.whole_tiles) {
             const uint32_t flatA = T.slot0 + (2 * i) * T.slot_step, flatB = flatA + T.slot_step;
             if (rg_in && bA < cs && flatA >= begin && flatA < end) T.valid_mask |= 1u << (2 * i);
@@ -967,7 +998,11 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
     uint32_t res[EPT], smask = 0;
 #pragma unroll
     for (int e = 0; e < EPT; ++e) res[e] = 0;
+#ifdef WT_PAIR_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
     for (int pr = 0; pr < NP; ++pr) {
         const f2 L = pr ? T.Lp[1] : T.Lp[0], A = pr ? T.Ap[1] : T.Ap[0], B = pr ? T.Bp[1] : T.Bp[0];
         const uint32_t bq0 = pr ? T.Bq[2] : T.Bq[0], bq1 = pr ? T.Bq[3] : T.Bq[1];
@@ -1098,6 +1133,7 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
     const float4 p = active ? a.pal[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
     const uint32_t prgb = active ? (a.pal_rgb[lane] & 0xffffffu) : 0u;
     const __half k16 = __ushort2half_rn((unsigned short)(k < 1024u ? k : 1024u));
+    const uint32_t nq4 = (n + 3u) >> 2;
     float4* cand = s_cand[warp];
     uint32_t* rnk = s_rank[warp];
     uint32_t* cidx = s_cidx[warp];
@@ -1209,8 +1245,8 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
                 __syncwarp();
                 const __half2 me = __half2half2(ub16);
                 __half2 acc0 = __float2half2_rn(0.f), acc1 = acc0;
-#pragma unroll
-                for (int q4 = 0; q4 < WT_MAX_N / 4; ++q4) {
+#pragma unroll 1
+                for (uint32_t q4 = 0; q4 < nq4; ++q4) {   // rolled: code size (see wt_select_c); nq4 = ceil(n / 4)
                     const uint4 v = reinterpret_cast<const uint4*>(rnk)[q4];   // inactive lanes hold (inf, inf): never <= a finite bound
                     acc0 = __hadd2(acc0, __hle2(u32_as_half2(v.x), me));
                     acc1 = __hadd2(acc1, __hle2(u32_as_half2(v.y), me));

@@ -94,6 +94,9 @@ def generate_lut(remapper, level, group=None, stream=None, out=None):
 
     With a process group of G ranks each rank computes side/G rows and an in-place
     all-gather (NCCL, NVLink) leaves the complete CLUT on every rank.
+
+    Stream contract: the kernels AND the collective run on `stream` (torch's current stream when None); the returned
+    tensor is ordered with that stream like any torch result.
     """
     level = int(level)
     side = level ** 3
@@ -101,9 +104,12 @@ def generate_lut(remapper, level, group=None, stream=None, out=None):
         _check_u8(out, "out")
 
     def compute_rows(flat, r0, r1):
-        generate_lut_rows_(remapper, level, flat, r0, r1, stream)
+        generate_lut_rows_(remapper, level, flat, r0, r1, None)   # torch's current stream: the one the collective uses
 
-    return sharded_rows_all_gather(side, compute_rows, out=out, group=group, device="cuda")
+    if stream is None:
+        return sharded_rows_all_gather(side, compute_rows, out=out, group=group, device="cuda")
+    with torch.cuda.stream(stream):
+        return sharded_rows_all_gather(side, compute_rows, out=out, group=group, device="cuda")
 
 
 class _RawCuda:

@@ -23,6 +23,15 @@ def _as_lut(hald_clut):
     return np.ascontiguousarray(lut)
 
 
+def _check_lut_level(lut, level):
+    """The reference's `get_pixel` indexes out of bounds and panics when the CLUT is smaller than the level asks for
+    (identity.rs:48-51); the library would read past the host buffer instead. Shared by every entry that takes a level."""
+    level = int(level)
+    n = level ** 3
+    if 2 <= level <= 33 and lut.shape[:2] != (n, n):
+        raise _native.LutgenPanic(f"hald clut is {lut.shape[1]}x{lut.shape[0]}, level {level} needs {n}x{n}")
+
+
 def _check_rgba(image):
     if not isinstance(image, np.ndarray) or image.dtype != np.uint8 or image.shape[-1] != 4:
         raise TypeError("image must be a (..., 4) uint8 numpy array (RgbaImage)")
@@ -60,6 +69,7 @@ def correct_pixel(input, hald_clut, level):
 def correct_pixels(colors, hald_clut, level):
     """correct_pixel over an (n, 3) array of colours in one launch."""
     lut = _as_lut(hald_clut)
+    _check_lut_level(lut, level)
     cols = np.ascontiguousarray(colors, np.uint8).reshape(-1, 3)
     out = np.empty_like(cols)
     L = _native.lib()
@@ -71,10 +81,7 @@ def correct_image_with_level(image, hald_clut, level):
     """identity::correct_image_with_level(&mut RgbaImage, &RgbImage, level)   (identity.rs:71-78)"""
     _check_rgba(image)
     lut = _as_lut(hald_clut)
-    n = int(level) ** 3
-    if 2 <= int(level) <= 33 and lut.shape[:2] != (n, n):
-        # the reference's get_pixel would index out of bounds and panic
-        raise _native.LutgenPanic(f"hald clut is {lut.shape[1]}x{lut.shape[0]}, level {level} needs {n}x{n}")
+    _check_lut_level(lut, level)
     L = _native.lib()
     _native.check(L.lutgen_cuda_apply_hald(_ptr(image), image.size // 4, _ptr(lut), int(level)))
 
@@ -90,6 +97,7 @@ def correct_images(images, hald_clut, level=None):
     lut = _as_lut(hald_clut)
     if level is None:
         level = detect_level(lut)
+    _check_lut_level(lut, level)
     for im in images:
         _check_rgba(im)
     n = len(images)

@@ -106,6 +106,18 @@ class InterpolatedRemapper:
     def par_generate_lut_with_interrupt(self, level, abort, out=None):
         return self._generate(level, abort, out, sequential=False)
 
+    def generate_lut_part(self, level, out, part_index, part_count, abort=None):
+        """One process per GPU, CLUT wanted on the host (lutgen_cuda_generate_lut_part): this rank's share of the row
+        groups, generated on its GPU and copied to their places in `out`, the WHOLE (n, n, 3) image -- e.g. a shared-memory
+        buffer all ranks have mapped. Complete when every rank has returned."""
+        level = int(level)
+        n = level ** 3 if 2 <= level <= 33 else 1
+        if out.dtype != np.uint8 or out.size != 3 * n * n or not out.flags.c_contiguous:
+            raise TypeError("out must be a contiguous uint8 array of 3*level^6 bytes")
+        aborted = _native.check(_native.lib().lutgen_cuda_generate_lut_part(self._h, level, _ptr(out), int(part_index), int(part_count),
+                                                                           _abort_ptr(abort)))
+        return None if aborted else out
+
     def _generate(self, level, abort, out, sequential):
         """`out` (optional, not in the reference): a preallocated (n, n, 3) uint8 array to fill,
         e.g. page-locked memory so the device-to-host copy is a single DMA."""
