@@ -917,11 +917,6 @@ int launch_apply(uint8_t* rgba_dev, size_t npix, const uint32_t* lut_rgbx, uint8
     // enough resident work to cover the gather latency, capped so the grid-stride loop amortises launch
     size_t cap = (size_t)g.sm_count * 64;
     unsigned grid = (unsigned)(want < cap ? want : cap);
-    static bool carve_done[kMaxDevices] = {};
-    if (!carve_done[g.index]) {   // no shared memory in this kernel: the whole unified array as L1 (see kernels_apply.cuh)
-        CU_TRY(cudaFuncSetAttribute(k_apply, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
-        carve_done[g.index] = true;
-    }
     k_apply<<<grid, 256, 0, s>>>((uint32_t*)rgba_dev, npix, head, nvec, lut_rgbx, cs, cs - 1);
     LAUNCH_CHECK();
     return LUTGEN_OK;

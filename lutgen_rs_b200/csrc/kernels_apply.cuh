@@ -21,28 +21,16 @@ __global__ void k_expand_lut(const uint8_t* __restrict__ lut_rgb, size_t n, uint
 // What bounds the kernel on pixels that share no CLUT cells (uniform random input) is not HBM and not the L2
 // slices but the SM's request port into the crossbar: one 32-byte sector request per gather that misses L1, at most
 // one request per clock and SM (ncu: l1tex__m_l1tex2xbar_req_cycles_active 91 % of peak at 254 Gpix/s, lts__throughput
-// 68 %, DRAM 21 % -- profiles/r2_apply_k_apply_ncu.txt). The only lever left is the L1 hit rate of the gathers: the
-// CLUT is read through the L1 with evict-last priority, the frame's own loads and stores bypass L1 allocation so that
-// they do not push CLUT lines out, and the kernel asks for the largest L1 carve-out (it uses no shared memory).
-__device__ __forceinline__ uint32_t ld_clut(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
-    uint4 v;
-    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_stream(uint4* p, uint4 v) {
-    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
+// 68 %, DRAM 21 % -- profiles/r2_apply_k_apply_ncu.txt). The L1 cannot take the gathers off that port: it tags
+// 128-byte lines, a scattered 4-byte gather fills one 32-byte sector of a line, so its ~196 KB hold ~49 KB of distinct
+// CLUT sectors -- 5 % of a level-8 CLUT, which is the hit rate measured, with or without evict-last on the CLUT loads,
+// no-allocate on the frame's own loads and stores and the largest L1 carve-out (tried in round 2, no change: 254 vs
+// 250 Gpix/s). Pixels of real images share cells with their neighbours and run at 85-89 % of HBM bandwidth.
 __device__ __forceinline__ uint32_t apply_one(uint32_t p, const uint32_t* __restrict__ lut, uint32_t cs, uint32_t csm1) {
     uint32_t r = (p & 255u) * csm1 / 255u;
     uint32_t g = ((p >> 8) & 255u) * csm1 / 255u;
     uint32_t b = ((p >> 16) & 255u) * csm1 / 255u;
-    uint32_t v = ld_clut(lut + ((b * cs + g) * cs + r));
+    uint32_t v = __ldg(lut + ((b * cs + g) * cs + r));
     return (v & 0x00ffffffu) | (p & 0xff000000u);
 }
 
@@ -55,12 +43,12 @@ __global__ void __launch_bounds__(256) k_apply(uint32_t* __restrict__ px, size_t
     size_t stride = (size_t)gridDim.x * blockDim.x;
     uint4* v = reinterpret_cast<uint4*>(px + head);
     for (size_t i = tid; i < nvec; i += stride) {
-        uint4 p = ld_stream(v + i);
+        uint4 p = v[i];
         p.x = apply_one(p.x, lut, cs, csm1);
         p.y = apply_one(p.y, lut, cs, csm1);
         p.z = apply_one(p.z, lut, cs, csm1);
         p.w = apply_one(p.w, lut, cs, csm1);
-        st_stream(v + i, p);
+        v[i] = p;
     }
     // scalar head + tail
     size_t tail_begin = head + nvec * 4;
