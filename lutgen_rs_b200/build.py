@@ -6,8 +6,8 @@ The shared object lands next to this file so it travels to the GPU box with the
 repository snapshot. cudart is linked statically: the library needs nothing but
 the NVIDIA driver at run time (no torch, no toolkit).
 
-Three translation units: api.cu (the C ABI and most kernels), blur.cu (the GaussianBlurRemapper
-kernels, compiled with --fmad=false: see csrc/blur_launch.h) and png.cu (the PNG writer).
+Four translation units: api.cu (the C ABI and most kernels), blur.cu (the GaussianBlurRemapper
+kernels, compiled with --fmad=false: see csrc/blur_launch.h), png.cu (the PNG writer) and png_decode.cu (the PNG reader).
 """
 import os
 import shutil
@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "liblutgen_cuda.so")
 OBJ_DIR = os.path.join(HERE, "_obj")
 # (source, extra nvcc flags)
-UNITS = [("api.cu", []), ("blur.cu", ["--fmad=false"]), ("png.cu", [])]
+UNITS = [("api.cu", []), ("blur.cu", ["--fmad=false"]), ("png.cu", []), ("png_decode.cu", [])]
 SOURCES = [os.path.join(CSRC, u) for u, _ in UNITS]
 
 COMMON_FLAGS = [

@@ -149,7 +149,8 @@ struct PairAcc {
 // near-tie test looks at. Three small loops where the sorting networks this replaces were 900 instructions:
 // warps run free of each other, so the kernel's working set of code has to fit the SM's 32 KB instruction
 // cache -- beyond it 'no instruction' was 47 % of the stall samples.
-constexpr int WT_TRACK = 6;   // c <= WT_TRACK - 1
+constexpr int WT_TRACK = 6;        // c <= WT_TRACK - 1: the usual deep choice
+constexpr int WT_TRACK_WIDE = 9;   // c <= 8 = every choice among up to 16 colours (c = min(kp, mU - kp))
 
 template <int D>
 __device__ __forceinline__ void wt_track(float (&m)[D], float v) {   // keep the D smallest, ascending
@@ -200,26 +201,28 @@ __device__ __forceinline__ PairAcc wt_select_c(const float4* __restrict__ unc, i
     return r;
 }
 
-// c = 3 .. WT_TRACK - 1 (11 % of the choosing tiles), ONE copy of the code for all of them: the WT_TRACK smallest are
-// tracked whatever c is, the boundary pair is picked by uniform selects, and a second rolled pass adds (or takes out
-// again) every colour whose tagged score is at most the c-th.
-template <int KIND>
+// c = 3 .. D - 1, ONE copy of the code for all of them (11 % of the choosing tiles of a small palette; D = WT_TRACK
+// covers them; D = WT_TRACK_WIDE covers every choice among up to 16 colours, which the 33..256-colour kernel meets
+// daily): the D smallest are tracked whatever c is, the boundary pair is picked by uniform selects, and a second rolled
+// pass adds (or takes out again) every colour whose tagged score is at most the c-th.
+template <int KIND, int D>
 __device__ __noinline__ PairAcc wt_select_deep(const float4* __restrict__ unc, int mU, int c, bool top, f2 L, f2 A, f2 B, float c1, float c0, float tol) {
     PairAcc r;
     r.n0 = r.n1 = r.n2 = r.den = splat(0.f);
-    float mx[WT_TRACK], my[WT_TRACK];
+    float mx[D], my[D];
 #pragma unroll
-    for (int t = 0; t < WT_TRACK; ++t) mx[t] = my[t] = INFINITY;
+    for (int t = 0; t < D; ++t) mx[t] = my[t] = INFINITY;
     const float sgn = top ? -1.0f : 1.0f;
 #pragma unroll 1
     for (int i = 0; i < mU; ++i) {
         const f2 sg = mul2(wt_score2<KIND>(unc[i], L, A, B), splat(sgn));
-        wt_track<WT_TRACK>(mx, __uint_as_float((__float_as_uint(sg.x) & ~15u) | (uint32_t)i));
-        wt_track<WT_TRACK>(my, __uint_as_float((__float_as_uint(sg.y) & ~15u) | (uint32_t)i));
+        wt_track<D>(mx, __uint_as_float((__float_as_uint(sg.x) & ~15u) | (uint32_t)i));
+        wt_track<D>(my, __uint_as_float((__float_as_uint(sg.y) & ~15u) | (uint32_t)i));
     }
-    static_assert(WT_TRACK == 6, "the selects below pick m[c-1], m[c] for c = 3, 4, 5");
-    const float lox = c == 3 ? mx[2] : (c == 4 ? mx[3] : mx[4]), hix = c == 3 ? mx[3] : (c == 4 ? mx[4] : mx[5]);
-    const float loy = c == 3 ? my[2] : (c == 4 ? my[3] : my[4]), hiy = c == 3 ? my[3] : (c == 4 ? my[4] : my[5]);
+    float lox = mx[2], hix = mx[3], loy = my[2], hiy = my[3];   // c = 3
+#pragma unroll
+    for (int t = 4; t < D; ++t)
+        if (c >= t) { lox = mx[t - 1]; hix = mx[t]; loy = my[t - 1]; hiy = my[t]; }   // uniform
     r.risky = (((hix - lox <= fmaf(fabsf(hix), 4e-6f, tol)) && (hix < INFINITY)) ? 1u : 0u) |
               (((hiy - loy <= fmaf(fabsf(hiy), 4e-6f, tol)) && (hiy < INFINITY)) ? 2u : 0u);
     r.tau = top ? make_float2(-hix, -hiy) : make_float2(lox, loy);
@@ -245,7 +248,8 @@ __device__ __forceinline__ PairAcc wt_select_small(const float4* __restrict__ un
                                                    float tol) {
     if (c == 1) return wt_select_c<KIND, 1>(unc, mU, top, L, A, B, c1, c0, tol);
     if (c == 2) return wt_select_c<KIND, 2>(unc, mU, top, L, A, B, c1, c0, tol);
-    return wt_select_deep<KIND>(unc, mU, c, top, L, A, B, c1, c0, tol);
+    if (c < WT_TRACK) return wt_select_deep<KIND, WT_TRACK>(unc, mU, c, top, L, A, B, c1, c0, tol);
+    return wt_select_deep<KIND, WT_TRACK_WIDE>(unc, mU, c, top, L, A, B, c1, c0, tol);
 }
 
 // Anything else (more than 16 uncertain colours, or neither side of the choice is small): per entry, one pass
@@ -896,7 +900,7 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
     const bool choose = !cl.take_all && kp > 0 && (int)cl.nunc_all > kp && (int)nunc > kp;
     // choosing from above (wt_select_c): every uncertain colour is added by the direct loop, the few left out are taken out again
     const int left_out = (int)nunc - kp;
-    const bool top = choose && KIND != 2 && KIND != KIND_NN && left_out < kp && left_out < WT_TRACK && nunc <= 16u;
+    const bool top = choose && KIND != 2 && KIND != KIND_NN && left_out < kp && left_out < WT_TRACK_WIDE && nunc <= 16u;
     const uint32_t direct = (cl.take_all || kp <= 0 || (choose && !top)) ? nin : nin + nunc;
     // per-tile conditions that send every entry to the exact kernel: more exact-hit candidates than
     // the list holds; weights so far from 1 that the reference's f64 sums leave their range; more
@@ -994,7 +998,7 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
     const float4* unc = cand + nin;
     const int mU = (int)nunc;
     const int csel = top ? left_out : kp;
-    const bool small = csel < WT_TRACK && mU <= 16;
+    const bool small = csel < WT_TRACK_WIDE && mU <= 16;
     uint32_t res[EPT], smask = 0;
 #pragma unroll
     for (int e = 0; e < EPT; ++e) res[e] = 0;
@@ -1369,8 +1373,13 @@ constexpr int WB_MAX_N = 256;    // one palette colour per thread
 constexpr int WB_MAX_M = 128;    // survivors a warp can classify (4 per lane); beyond: exact kernel
 constexpr int WB_BISECT = 12;
 
+// Three CTAs per SM here: this kernel's CTAs meet at barriers (31 % of the stall samples with two), which more
+// resident warps do hide.
+#ifndef WB_MINB
+#define WB_MINB 3
+#endif
 template <int KIND, int MODE, int EPT, bool MULTI>
-__global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp_big(const WarpArgs a) {
+__global__ void __launch_bounds__(WT_THREADS, WB_MINB) k_remap_warp_big(const WarpArgs a) {
     static_assert(EPT % 2 == 0, "entries are processed in pairs");
     constexpr uint32_t FULL = 0xffffffffu;
     constexpr bool BRICK = MODE != FRONT_IMAGE;

@@ -1,0 +1,242 @@
+// png_decode.cu -- PNG decoder kernels (png_decode_core.h): inflate, Adler-32, scanline reconstruction, channel expansion.
+// Replaces the decode half of `load_image` (crates/cli/src/main.rs:602-613: image::open + to_rgba8 / to_rgb8) for the
+// files `lutgen apply` reads, so that a frame can go file -> pixels -> corrected pixels -> file without its pixels ever
+// crossing PCIe (only the compressed bytes do).
+//
+//   k_pngd_inflate_pieces  one thread per 16 KB piece of a file this library wrote (independent block sequences)
+//   k_pngd_inflate_serial  one thread: any other zlib stream (a deflate stream is one serial chain of bits)
+//   k_pngd_adler_parts / k_pngd_adler_check   Adler-32 of the inflated stream against the stream's trailer
+//   k_pngd_unfilter        Sub / Up / Average / Paeth as an anti-diagonal wavefront: a warp per band of 32 rows
+//   k_pngd_expand          to the channel count asked for (palette, grey -> RGB, alpha added or dropped)
+#include "png_decode_launch.h"
+
+#include "png_decode_core.h"
+
+namespace lutgen {
+namespace {
+
+constexpr int ADLER_SPAN = 4096;
+
+__global__ void k_pngd_inflate_pieces(const uint8_t* __restrict__ z, const unsigned long long* __restrict__ off, uint32_t npieces, uint8_t* __restrict__ dst,
+                                      unsigned long long total, int* __restrict__ status) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npieces) return;
+    lpngd::InflateScratch X;
+    const unsigned long long o0 = (unsigned long long)i * lpngd::PIECE;
+    const size_t expect = (size_t)(total - o0 < (unsigned long long)lpngd::PIECE ? total - o0 : (unsigned long long)lpngd::PIECE);
+    const int rc = lpngd::inflate_piece(z + off[i], (size_t)(off[i + 1] - off[i]), dst + o0, expect, X);
+    if (rc != lpngd::OK) atomicCAS(status, 0, rc);
+}
+
+__global__ void k_pngd_inflate_serial(const uint8_t* __restrict__ z, size_t n, uint8_t* __restrict__ dst, size_t cap, int* __restrict__ status) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    lpngd::InflateScratch X;
+    size_t produced = 0;
+    int rc = lpngd::inflate_zlib(z, n, dst, cap, &produced, X);
+    if (rc == lpngd::OK && produced != cap) rc = lpngd::ERR_LENGTH;
+    status[0] = rc;
+}
+
+// parts[i] = (a, b) of span i (ADLER_SPAN bytes each, the last one shorter)
+__global__ void k_pngd_adler_parts(const uint8_t* __restrict__ p, unsigned long long n, uint2* __restrict__ parts) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long o = i * ADLER_SPAN;
+    if (o >= n) return;
+    const size_t len = (size_t)(n - o < (unsigned long long)ADLER_SPAN ? n - o : (unsigned long long)ADLER_SPAN);
+    uint32_t a, b;
+    lpngd::adler_span(p + o, len, a, b);
+    parts[i] = make_uint2(a, b);
+}
+
+// One thread folds the parts and compares with the four bytes that follow the deflate data (big endian).
+__global__ void k_pngd_adler_check(const uint2* __restrict__ parts, unsigned long long n, const uint8_t* __restrict__ trailer, int* __restrict__ status) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    uint32_t A = 1, B = 0;
+    const unsigned long long nparts = (n + ADLER_SPAN - 1) / ADLER_SPAN;
+    for (unsigned long long i = 0; i < nparts; ++i) {
+        const size_t len = (size_t)(n - i * ADLER_SPAN < (unsigned long long)ADLER_SPAN ? n - i * ADLER_SPAN : (unsigned long long)ADLER_SPAN);
+        lpngd::adler_append(A, B, parts[i].x, parts[i].y, len);
+    }
+    const uint32_t want = ((uint32_t)trailer[0] << 24) | ((uint32_t)trailer[1] << 16) | ((uint32_t)trailer[2] << 8) | trailer[3];
+    status[1] = (((B << 16) | A) == want) ? 1 : 0;
+}
+
+__device__ __forceinline__ uint32_t load_pixel(const uint8_t* p, uint32_t bpp) {
+    uint32_t v = 0;
+    for (uint32_t k = 0; k < bpp; ++k) v |= (uint32_t)p[k] << (8u * k);
+    return v;
+}
+__device__ __forceinline__ uint32_t load_pixel_cg(const uint8_t* p, uint32_t bpp) {   // written by another warp: not through L1
+    uint32_t v = 0;
+    for (uint32_t k = 0; k < bpp; ++k) v |= (uint32_t)__ldcg(p + k) << (8u * k);
+    return v;
+}
+__device__ __forceinline__ void store_pixel(uint8_t* p, uint32_t v, uint32_t bpp) {
+    for (uint32_t k = 0; k < bpp; ++k) p[k] = (uint8_t)(v >> (8u * k));
+}
+
+// Reconstruction. Band = 32 consecutive rows = one warp, lane i = row band*32 + i, and at step s lane i does pixel
+// x = s - i: the pixel above it was done by lane i-1 one step earlier (it arrives by shuffle), the one above-left
+// the step before that. Lane 0's row above belongs to the previous band: that band publishes how many pixels of its
+// last row are done (progress[band], release) and this one reads them 32 at a time (one per lane, acquire), so the
+// round trip through L2 is paid once per 32 steps. Bands are numbered in launch order, so a band only ever waits for
+// CTAs that were scheduled before its own.
+__global__ void __launch_bounds__(256) k_pngd_unfilter(const uint8_t* __restrict__ stream, uint32_t w, uint32_t h, uint32_t bpp, uint8_t* __restrict__ out,
+                                                        int* progress, int* status) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u, band = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nbands = (h + 31u) / 32u;
+    if (band >= nbands) return;
+    const size_t rb = (size_t)w * bpp;
+    const uint32_t r = band * 32u + lane;
+    const bool valid = r < h;
+    const uint8_t* src = stream + (size_t)(valid ? r : 0) * (rb + 1);
+    const uint32_t ft = valid ? src[0] : 0u;
+    if (ft > 4u) atomicOr(status + 3, 1);   // not a filter type (PNG specification 9.2): the file is corrupt
+    ++src;
+    uint8_t* dstrow = out + (size_t)(valid ? r : 0) * rb;
+    const uint8_t* above_row = band > 0 ? out + (size_t)(band * 32u - 1u) * rb : nullptr;
+    const bool publish = band + 1 < nbands;   // full band with a follower: lane 31 is its last row
+    uint32_t a = 0, prev_b = 0, last_out = 0, above = 0;
+    const uint32_t steps = w + 31u;
+    for (uint32_t s = 0; s < steps; ++s) {
+        // the row above the band, 32 pixels at a time
+        if (above_row && s < w && (s & 31u) == 0) {
+            const uint32_t need = min(s + 32u, w);
+            if (lane == 0) {
+                int v;
+                do {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(progress + band - 1) : "memory");
+                } while ((uint32_t)v < need);
+            }
+            __syncwarp();
+            const uint32_t xa = s + lane;
+            above = xa < w ? load_pixel_cg(above_row + (size_t)xa * bpp, bpp) : 0u;
+        }
+        uint32_t b = __shfl_up_sync(FULL, last_out, 1);
+        const uint32_t from_above = __shfl_sync(FULL, above, s & 31u);
+        if (lane == 0) b = above_row ? from_above : 0u;
+        const int x = (int)s - (int)lane;
+        uint32_t cur = 0;
+        if (valid && x >= 0 && x < (int)w) {
+            const uint32_t xv = load_pixel(src + (size_t)x * bpp, bpp);
+            cur = lpngd::unfilter_pixel(ft, xv, a, b, prev_b, bpp);
+            store_pixel(dstrow + (size_t)x * bpp, cur, bpp);
+            a = cur;
+        }
+        prev_b = b;
+        last_out = cur;
+        if (publish && lane == 31u && x >= 0 && x < (int)w && (((uint32_t)x & 31u) == 31u || x == (int)w - 1)) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(progress + band), "r"(x + 1) : "memory");
+        }
+    }
+}
+
+__global__ void k_pngd_expand(const uint8_t* __restrict__ rows, unsigned long long npix, int color_type, int channels, int out_channels,
+                              const uint32_t* __restrict__ palette, uint8_t* __restrict__ out) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const uint8_t* p = rows + i * (unsigned long long)channels;
+    uint32_t r, g, b, al = 255u;
+    if (color_type == 3) {
+        const uint32_t e = palette[p[0]];
+        r = e & 255u; g = (e >> 8) & 255u; b = (e >> 16) & 255u; al = e >> 24;
+    } else if (color_type == 0) {
+        r = g = b = p[0];
+    } else if (color_type == 4) {
+        r = g = b = p[0]; al = p[1];
+    } else if (color_type == 2) {
+        r = p[0]; g = p[1]; b = p[2];
+    } else {
+        r = p[0]; g = p[1]; b = p[2]; al = p[3];
+    }
+    uint8_t* q = out + i * (unsigned long long)out_channels;
+    if (out_channels == 1) {
+        q[0] = (uint8_t)r;   // only asked for grey sources
+    } else if (out_channels == 2) {
+        q[0] = (uint8_t)r; q[1] = (uint8_t)al;
+    } else {
+        q[0] = (uint8_t)r; q[1] = (uint8_t)g; q[2] = (uint8_t)b;
+        if (out_channels == 4) q[3] = (uint8_t)al;
+    }
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct DecodeLayout {
+    size_t stream, rows, parts, progress, status, total;
+};
+DecodeLayout decode_layout(const PngDecodePlan& p) {
+    DecodeLayout L;
+    const size_t rowbytes = (size_t)p.height * p.width * (size_t)p.channels;
+    L.stream = 0;
+    L.rows = align_up(L.stream + p.stream_bytes, 256);
+    L.parts = align_up(L.rows + rowbytes, 256);
+    L.progress = align_up(L.parts + sizeof(uint2) * ((p.stream_bytes + ADLER_SPAN - 1) / ADLER_SPAN + 1), 256);
+    L.status = align_up(L.progress + sizeof(int) * ((p.height + 31) / 32 + 1), 256);
+    L.total = L.status + 256;
+    return L;
+}
+
+}  // namespace
+
+size_t png_decode_scratch_bytes(const PngDecodePlan& plan) { return decode_layout(plan).total; }
+
+cudaError_t png_decode_async(const PngDecodePlan& plan, const uint8_t* z_dev, const unsigned long long* piece_off_dev, const uint32_t* palette_dev,
+                             uint8_t* out_dev, void* scratch_dev, int* status_host, cudaStream_t s, unsigned* launches) {
+    const DecodeLayout L = decode_layout(plan);
+    uint8_t* base = static_cast<uint8_t*>(scratch_dev);
+    uint8_t* stream = base + L.stream;
+    uint8_t* rows = base + L.rows;
+    uint2* parts = reinterpret_cast<uint2*>(base + L.parts);
+    int* progress = reinterpret_cast<int*>(base + L.progress);
+    int* status = reinterpret_cast<int*>(base + L.status);
+    unsigned nl = 0;
+    cudaError_t e = cudaMemsetAsync(base + L.progress, 0, L.total - L.progress, s);   // progress + status
+    if (e != cudaSuccess) return e;
+    const unsigned long long total = plan.stream_bytes;
+    const unsigned nparts = (unsigned)((total + ADLER_SPAN - 1) / ADLER_SPAN);
+    const uint8_t* trailer = z_dev + plan.zbytes - 4;
+    bool done = false;
+    status_host[0] = status_host[1] = status_host[2] = status_host[3] = 0;
+    if (plan.npieces > 0 && piece_off_dev) {
+        k_pngd_inflate_pieces<<<(plan.npieces + 63) / 64, 64, 0, s>>>(z_dev, piece_off_dev, plan.npieces, stream, total, status);
+        k_pngd_adler_parts<<<(nparts + 127) / 128, 128, 0, s>>>(stream, total, parts);
+        k_pngd_adler_check<<<1, 32, 0, s>>>(parts, total, trailer, status);
+        nl += 3;
+        e = cudaMemcpyAsync(status_host, status, 2 * sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return e;
+        done = status_host[0] == 0 && status_host[1] == 1;
+        status_host[2] = 1;
+        if (!done) {
+            e = cudaMemsetAsync(status, 0, 2 * sizeof(int), s);
+            if (e != cudaSuccess) return e;
+        }
+    }
+    if (!done) {
+        k_pngd_inflate_serial<<<1, 32, 0, s>>>(z_dev, plan.zbytes, stream, (size_t)total, status);
+        k_pngd_adler_parts<<<(nparts + 127) / 128, 128, 0, s>>>(stream, total, parts);
+        k_pngd_adler_check<<<1, 32, 0, s>>>(parts, total, trailer, status);
+        nl += 3;
+        e = cudaMemcpyAsync(status_host, status, 2 * sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) return e;
+        status_host[2] = 2;
+    }
+    const bool direct = plan.out_channels == plan.channels && plan.color_type != 3;
+    const unsigned nbands = (plan.height + 31) / 32;
+    k_pngd_unfilter<<<(nbands + 7) / 8, 256, 0, s>>>(stream, plan.width, plan.height, (uint32_t)plan.channels, direct ? out_dev : rows, progress, status);
+    e = cudaMemcpyAsync(status_host + 3, status + 3, sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) return e;
+    ++nl;
+    if (!direct) {
+        const unsigned long long npix = (unsigned long long)plan.width * plan.height;
+        k_pngd_expand<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(rows, npix, plan.color_type, plan.channels, plan.out_channels, palette_dev, out_dev);
+        ++nl;
+    }
+    if (launches) *launches = nl;
+    return cudaGetLastError();
+}
+
+}  // namespace lutgen
