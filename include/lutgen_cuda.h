@@ -286,6 +286,36 @@ LUTGEN_API int lutgen_cuda_generate_lut_png(const lutgen_remapper* r, uint8_t le
 LUTGEN_API int lutgen_cuda_apply_hald_png(const uint8_t* rgba, uint32_t width, uint32_t height, const uint8_t* lut_rgb,
                                           uint8_t level, uint8_t* out, size_t capacity, size_t* out_len);
 
+/* ---- PNG reader around the path (the decode half) -------------
+ * `load_image` (crates/cli/src/main.rs:602-613: image::open(path), then to_rgba8() for the image and to_rgb8() for the
+ * --hald-clut) for PNG files. The container is parsed on the host; inflate, scanline reconstruction and the channel
+ * conversion run on the device. 8 bits per sample, colour types 0 / 2 / 3 / 4 / 6 (grey, RGB, palette with optional
+ * tRNS, grey + alpha, RGBA), non-interlaced. Other flavours (16-bit samples, interlace, tRNS colour keys) return
+ * LUTGEN_ERR_UNSUPPORTED -- keep the caller's decoder for those; a damaged file (signature, chunk CRC, deflate data,
+ * Adler-32, filter type) returns LUTGEN_ERR_INVALID where the `image` crate returns an Err. Files written by this
+ * library's own encoder (one IDAT chunk per 16 KB piece) are inflated in parallel, one thread per piece; a foreign
+ * file's single deflate stream is inflated by one thread (correct, but no faster than a CPU). */
+
+/* Geometry of a PNG file without decoding it: *channels as lutgen_cuda_decode_png(…, 0, …) would deliver them
+ * (1, 2, 3 or 4; a palette image counts as 3, or 4 with tRNS); *has_alpha: the file carries transparency. */
+LUTGEN_API int lutgen_cuda_png_info(const uint8_t* file, size_t len, uint32_t* width, uint32_t* height, int* channels, int* has_alpha);
+
+/* PNG file bytes (host) -> pixels (host), tightly packed height x width x out_channels. out_channels: 3 = to_rgb8
+ * (alpha dropped, grey replicated), 4 = to_rgba8 (alpha 255 where the file has none), 0 = as in the file, 1 / 2 only for
+ * grey sources. `capacity` must hold width * height * channels bytes. */
+LUTGEN_API int lutgen_cuda_decode_png(const uint8_t* file, size_t len, int out_channels, uint8_t* out, size_t capacity);
+/* The same with the pixels left in device memory (the file bytes are still read from the host): enqueues on `stream`
+ * and synchronises it (the inflate status has to be read back). */
+LUTGEN_API int lutgen_cuda_decode_png_dev(const uint8_t* file, size_t len, int out_channels, uint8_t* out_dev, size_t capacity, void* stream);
+
+/* `lutgen apply --hald-clut clut.png image.png` for PNG files, file to file (crates/cli/src/main.rs:832-871: load_image
+ * twice, correct_image, image.save): both files are decoded on the device, the image is corrected and encoded there, and
+ * only compressed bytes cross PCIe in either direction. The CLUT's level is detected from its size (identity.rs:85-99;
+ * not a Hald CLUT -> LUTGEN_ERR_INVALID). The result is an RGBA PNG; *out_len / `capacity` as in lutgen_cuda_encode_png
+ * (bound: lutgen_cuda_png_bound(width, height, 4) with the image's size from lutgen_cuda_png_info). */
+LUTGEN_API int lutgen_cuda_apply_hald_png_file(const uint8_t* image_png, size_t image_len, const uint8_t* hald_png, size_t hald_len,
+                                               uint8_t* out, size_t capacity, size_t* out_len);
+
 /* ---- palette extraction next to the path ------------------- */
 
 /* `lutgen extract` (crates/cli/src/main.rs:772-815): a palette of at most `color_count` (1..=256; the CLI's

@@ -33,6 +33,7 @@ EXPORTS = [
     "lutgen_cuda_generate_lut_sequential",
     "lutgen_cuda_png_bound", "lutgen_cuda_encode_png", "lutgen_cuda_encode_png_dev", "lutgen_cuda_generate_lut_png",
     "lutgen_cuda_apply_hald_png", "lutgen_cuda_extract_palette",
+    "lutgen_cuda_png_info", "lutgen_cuda_decode_png", "lutgen_cuda_decode_png_dev", "lutgen_cuda_apply_hald_png_file",
 ]
 
 
@@ -129,6 +130,10 @@ def load():
             "lutgen_cuda_encode_png": ([vp, u32, u32, i32, vp, sz, C.POINTER(sz)], i32),
             "lutgen_cuda_encode_png_dev": ([vp, u32, u32, i32, vp, sz, C.POINTER(sz), vp], i32),
             "lutgen_cuda_generate_lut_png": ([vp, u8, vp, sz, C.POINTER(sz), vp], i32),
+            "lutgen_cuda_png_info": ([vp, sz, C.POINTER(u32), C.POINTER(u32), C.POINTER(i32), C.POINTER(i32)], i32),
+            "lutgen_cuda_decode_png": ([vp, sz, i32, vp, sz], i32),
+            "lutgen_cuda_decode_png_dev": ([vp, sz, i32, vp, sz, vp], i32),
+            "lutgen_cuda_apply_hald_png_file": ([vp, sz, vp, sz, vp, sz, C.POINTER(sz)], i32),
             "lutgen_cuda_apply_hald_png": ([vp, u32, u32, vp, u8, vp, sz, C.POINTER(sz)], i32),
             "lutgen_cuda_extract_palette": ([vp, sz, u32, u32, vp, C.POINTER(u32)], i32),
         }

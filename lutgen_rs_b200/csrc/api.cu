@@ -23,6 +23,8 @@
 #include "kernels_apply.cuh"
 #include "blur_launch.h"
 #include "png_launch.h"
+#include "png_decode_launch.h"
+#include "png_decode_core.h"
 #include "kernels_exact.cuh"
 #include "kernels_fast.cuh"
 #include "kernels_warp.cuh"
@@ -96,6 +98,8 @@ struct Ctx {
     DevBuf batch_frames[kBatchStreams];
     DevBuf misc;
     DevBuf png_in, png_out, png_scratch;  // PNG writer: pixels (host API), file bytes, per-piece scratch
+    DevBuf pngd_z, pngd_scratch, pngd_out;  // PNG reader: the zlib stream (+ piece offsets, palette), scratch, pixels (host API)
+    int* pngd_status = nullptr;          // page-locked, 4 ints
     DevBuf extract;                       // palette extraction: histogram, point list, centroids
     uint32_t* stats = nullptr;      // device [128], only with LUTGEN_CUDA_STATS set
     // k_remap_warp's tile / finished-CTA counter pairs: zero between launches (the kernel's last CTA resets its
@@ -995,6 +999,11 @@ void release_current_ctx() {
     g.png_in.release();
     g.png_out.release();
     g.png_scratch.release();
+    g.pngd_z.release();
+    g.pngd_scratch.release();
+    g.pngd_out.release();
+    if (g.pngd_status) cudaFreeHost(g.pngd_status);
+    g.pngd_status = nullptr;
     g.extract.release();
     for (int i = 0; i < kBatchStreams; ++i) {
         g.batch_frames[i].release();
@@ -1933,6 +1942,184 @@ int lutgen_cuda_apply_hald_png(const uint8_t* rgba, uint32_t width, uint32_t hei
     if (rc) return rc;
     size_t total = 0;
     rc = png_encode_locked((const uint8_t*)g.frame.p, width, height, 4, (uint8_t*)g.png_out.p, &total, g.stream);
+    if (rc) return rc;
+    *out_len = total;
+    if (total > capacity) return fail(LUTGEN_ERR_INVALID, "the PNG is %zu bytes, the buffer holds %zu", total, capacity);
+    CU_TRY(cudaMemcpyAsync(out, g.png_out.p, total, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    return LUTGEN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// PNG reader (png_decode.cu over png_decode_core.h)
+// ---------------------------------------------------------------------------
+namespace {
+struct IdatSpan {
+    size_t off, len;
+};
+
+int png_parse_checked(const uint8_t* file, size_t len, lpngd::Info& info, std::vector<IdatSpan>& idat) {
+    if (!file) return fail(LUTGEN_ERR_INVALID, "file is NULL");
+    const int prc = lpngd::png_parse(file, len, info, idat);
+    if (prc == lpngd::P_NOT_PNG) return fail(LUTGEN_ERR_INVALID, "not a PNG file (signature)");
+    if (prc == lpngd::P_CORRUPT) return fail(LUTGEN_ERR_INVALID, "corrupt PNG (chunk structure or CRC)");
+    if (prc == lpngd::P_UNSUPPORTED)
+        return fail(LUTGEN_ERR_UNSUPPORTED, "PNG flavour not decoded here (16-bit samples, interlace, colour key or unknown critical chunk): keep the caller's decoder for it");
+    return LUTGEN_OK;
+}
+
+// g.mu held. File bytes on the host -> pixels in out_dev (height x width x out_channels), on stream s; synchronises s.
+int png_decode_locked(const uint8_t* file, const lpngd::Info& info, const std::vector<IdatSpan>& idat, int out_channels, uint8_t* out_dev, cudaStream_t s) {
+    PngDecodePlan plan{};
+    plan.width = info.width;
+    plan.height = info.height;
+    plan.color_type = info.color_type;
+    plan.channels = info.channels;
+    plan.out_channels = out_channels;
+    plan.stream_bytes = (size_t)info.height * ((size_t)info.width * info.channels + 1);
+    size_t zbytes = 0;
+    for (const IdatSpan& c : idat) zbytes += c.len;
+    if (zbytes < 6) return fail(LUTGEN_ERR_INVALID, "corrupt PNG (no image data)");
+    plan.zbytes = zbytes;
+    // the chunk pattern of this library's own writer: one IDAT per 16 KB piece of the scanline stream + a 4-byte one (Adler-32)
+    const size_t npieces = (plan.stream_bytes + lpngd::PIECE - 1) / lpngd::PIECE;
+    const bool own = idat.size() == npieces + 1 && idat.back().len == 4 && idat.front().len >= 2;
+    plan.npieces = own ? (uint32_t)npieces : 0u;
+    // device layout of pngd_z: [the file as it is][pad][the zlib stream, contiguous][pad][piece / chunk offsets][palette].
+    // ONE upload of the file (a copy per IDAT chunk costs 20 us each from pageable memory: 60 ms for a level-16 CLUT);
+    // the IDAT payloads are gathered into one stream on the device.
+    const size_t file_len = idat.back().off + idat.back().len;   // everything behind the last IDAT payload is not needed
+    const size_t off_z = (file_len + 255) & ~(size_t)255, off_tab = (off_z + zbytes + 255) & ~(size_t)255;
+    const size_t ntab = 2 * idat.size() + npieces + 4, off_pal = off_tab + sizeof(unsigned long long) * ntab;
+    CU_TRY(g.pngd_z.reserve(off_pal + 1024));
+    CU_TRY(g.pngd_scratch.reserve(png_decode_scratch_bytes(plan)));
+    if (!g.pngd_status) CU_TRY(cudaHostAlloc((void**)&g.pngd_status, 4 * sizeof(int), cudaHostAllocDefault));
+    uint8_t* fdev = (uint8_t*)g.pngd_z.p;
+    uint8_t* zdev = fdev + off_z;
+    CU_TRY(cudaMemcpyAsync(fdev, file, file_len, cudaMemcpyHostToDevice, s));
+    // table: [src offset in the file, dst offset in the stream] per chunk, then (own files) the pieces' offsets in the stream
+    std::vector<unsigned long long> tab;
+    size_t pos = 0;
+    for (size_t i = 0; i < idat.size(); ++i) {
+        tab.push_back(idat[i].off);
+        tab.push_back(pos);
+        pos += idat[i].len;
+    }
+    tab.push_back(0);
+    tab.push_back(pos);
+    const size_t piece_tab = tab.size();
+    if (own) {
+        size_t p2 = 0;
+        for (size_t i = 0; i < npieces; ++i) {
+            tab.push_back(p2 + (i == 0 ? 2 : 0));   // the zlib header rides in front of the first piece
+            p2 += idat[i].len;
+        }
+        tab.push_back(p2);
+    }
+    unsigned long long* tab_dev = (unsigned long long*)(fdev + off_tab);
+    CU_TRY(cudaMemcpyAsync(tab_dev, tab.data(), sizeof(unsigned long long) * tab.size(), cudaMemcpyHostToDevice, s));
+    if (info.color_type == 3) CU_TRY(cudaMemcpyAsync(fdev + off_pal, info.palette, sizeof(info.palette), cudaMemcpyHostToDevice, s));
+    png_decode_gather(fdev, tab_dev, (uint32_t)idat.size(), zdev, s);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    unsigned launches = 0;
+    cudaError_t e = png_decode_async(plan, zdev, own ? tab_dev + piece_tab : nullptr, (const uint32_t*)(fdev + off_pal), out_dev, g.pngd_scratch.p,
+                                     g.pngd_status, s, &launches);
+    g_launches.fetch_add(launches, std::memory_order_relaxed);
+    if (e != cudaSuccess) return fail(LUTGEN_ERR_CUDA, "PNG decoder launch failed: %s", cudaGetErrorString(e));
+    CU_TRY(cudaStreamSynchronize(s));
+    if (g.pngd_status[0] != 0) return fail(LUTGEN_ERR_INVALID, "corrupt PNG (inflate error %d)", g.pngd_status[0]);
+    if (g.pngd_status[1] != 1) return fail(LUTGEN_ERR_INVALID, "corrupt PNG (Adler-32 of the image data does not match)");
+    if (g.pngd_status[3] != 0) return fail(LUTGEN_ERR_INVALID, "corrupt PNG (scanline with an unknown filter type)");
+    return LUTGEN_OK;
+}
+
+int png_out_channels(const lpngd::Info& info, int asked) {
+    if (asked == 0) return info.color_type == 3 ? info.out_channels : info.channels;   // native (a palette image has no native pixel form)
+    return asked;
+}
+}  // namespace
+
+int lutgen_cuda_png_info(const uint8_t* file, size_t len, uint32_t* width, uint32_t* height, int* channels, int* has_alpha) {
+    lpngd::Info info;
+    std::vector<IdatSpan> idat;
+    int rc = png_parse_checked(file, len, info, idat);
+    if (rc) return rc;
+    if (width) *width = info.width;
+    if (height) *height = info.height;
+    if (channels) *channels = info.color_type == 3 ? info.out_channels : info.channels;
+    if (has_alpha) *has_alpha = (info.color_type == 4 || info.color_type == 6 || info.has_trns) ? 1 : 0;
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_decode_png_dev(const uint8_t* file, size_t len, int out_channels, uint8_t* out_dev, size_t capacity, void* stream) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!out_dev) return fail(LUTGEN_ERR_INVALID, "out_dev is NULL");
+    if (out_channels < 0 || out_channels > 4) return fail(LUTGEN_ERR_INVALID, "%d output channels (0 = as in the file, 1..4)", out_channels);
+    lpngd::Info info;
+    std::vector<IdatSpan> idat;
+    rc = png_parse_checked(file, len, info, idat);
+    if (rc) return rc;
+    const int oc = png_out_channels(info, out_channels);
+    if ((oc == 1 || oc == 2) && !(info.color_type == 0 || info.color_type == 4)) return fail(LUTGEN_ERR_INVALID, "grey output asked of a colour image");
+    const size_t need = (size_t)info.width * info.height * (size_t)oc;
+    if (need > capacity) return fail(LUTGEN_ERR_INVALID, "the image is %zu bytes, the buffer holds %zu", need, capacity);
+    std::lock_guard<std::mutex> lk(g.mu);
+    return png_decode_locked(file, info, idat, oc, out_dev, (cudaStream_t)stream);
+}
+
+int lutgen_cuda_decode_png(const uint8_t* file, size_t len, int out_channels, uint8_t* out, size_t capacity) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!out) return fail(LUTGEN_ERR_INVALID, "out is NULL");
+    if (out_channels < 0 || out_channels > 4) return fail(LUTGEN_ERR_INVALID, "%d output channels (0 = as in the file, 1..4)", out_channels);
+    lpngd::Info info;
+    std::vector<IdatSpan> idat;
+    rc = png_parse_checked(file, len, info, idat);
+    if (rc) return rc;
+    const int oc = png_out_channels(info, out_channels);
+    if ((oc == 1 || oc == 2) && !(info.color_type == 0 || info.color_type == 4)) return fail(LUTGEN_ERR_INVALID, "grey output asked of a colour image");
+    const size_t need = (size_t)info.width * info.height * (size_t)oc;
+    if (need > capacity) return fail(LUTGEN_ERR_INVALID, "the image is %zu bytes, the buffer holds %zu", need, capacity);
+    std::lock_guard<std::mutex> lk(g.mu);
+    CU_TRY(g.pngd_out.reserve(need));
+    rc = png_decode_locked(file, info, idat, oc, (uint8_t*)g.pngd_out.p, g.stream);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(out, g.pngd_out.p, need, cudaMemcpyDeviceToHost, g.stream));
+    CU_TRY(cudaStreamSynchronize(g.stream));
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_apply_hald_png_file(const uint8_t* image_png, size_t image_len, const uint8_t* hald_png, size_t hald_len, uint8_t* out, size_t capacity,
+                                    size_t* out_len) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!out || !out_len) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    lpngd::Info ii, hi;
+    std::vector<IdatSpan> iidat, hidat;
+    rc = png_parse_checked(image_png, image_len, ii, iidat);
+    if (rc) return rc;
+    rc = png_parse_checked(hald_png, hald_len, hi, hidat);
+    if (rc) return rc;
+    uint8_t level = 0;
+    rc = lutgen_cuda_detect_level(hi.width, hi.height, &level);
+    if (rc) return rc;
+    rc = png_args_ok(ii.width, ii.height, 4);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g.mu);
+    const size_t npix = (size_t)ii.width * ii.height;
+    CU_TRY(g.lut_rgb.reserve(3 * lut_entries(level)));
+    CU_TRY(g.frame.reserve(npix * 4));
+    CU_TRY(g.png_out.reserve((size_t)png_bound(ii.width, ii.height, 4)));
+    // both files are decoded on the device: the CLUT as RGB8, the image as RGBA8 (load_image's to_rgb8 / to_rgba8)
+    rc = png_decode_locked(hald_png, hi, hidat, 3, (uint8_t*)g.lut_rgb.p, g.stream);
+    if (rc) return rc;
+    rc = png_decode_locked(image_png, ii, iidat, 4, (uint8_t*)g.frame.p, g.stream);
+    if (rc) return rc;
+    rc = lutgen_cuda_apply_hald_dev((uint8_t*)g.frame.p, npix, (const uint8_t*)g.lut_rgb.p, level, g.stream);
+    if (rc) return rc;
+    size_t total = 0;
+    rc = png_encode_locked((const uint8_t*)g.frame.p, ii.width, ii.height, 4, (uint8_t*)g.png_out.p, &total, g.stream);
     if (rc) return rc;
     *out_len = total;
     if (total > capacity) return fail(LUTGEN_ERR_INVALID, "the PNG is %zu bytes, the buffer holds %zu", total, capacity);

@@ -17,22 +17,43 @@ namespace {
 
 constexpr int ADLER_SPAN = 4096;
 
-__global__ void k_pngd_inflate_pieces(const uint8_t* __restrict__ z, const unsigned long long* __restrict__ off, uint32_t npieces, uint8_t* __restrict__ dst,
-                                      unsigned long long total, int* __restrict__ status) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per piece. Lane 0 decodes into the warp's 16 KB of shared memory -- a match is a chain of byte copies each
+// reading what the copy before it wrote, 30 cycles apart in shared memory and an L2 round trip apart in global memory
+// (the first version, one thread per piece writing global memory, took 94 ms for a level-16 CLUT; this one ~1 ms) --
+// then the whole warp stores the piece, 16 bytes per lane.
+constexpr int PIECE_WARPS = 4;
+__global__ void __launch_bounds__(PIECE_WARPS * 32) k_pngd_inflate_pieces(const uint8_t* __restrict__ z, const unsigned long long* __restrict__ off,
+                                                                          uint32_t npieces, uint8_t* __restrict__ dst, unsigned long long total,
+                                                                          int* __restrict__ status) {
+    extern __shared__ __align__(16) uint8_t s_piece[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t i = blockIdx.x * PIECE_WARPS + warp;
     if (i >= npieces) return;
-    lpngd::InflateScratch X;
+    uint8_t* buf = s_piece + (size_t)warp * lpngd::PIECE;
     const unsigned long long o0 = (unsigned long long)i * lpngd::PIECE;
-    const size_t expect = (size_t)(total - o0 < (unsigned long long)lpngd::PIECE ? total - o0 : (unsigned long long)lpngd::PIECE);
-    const int rc = lpngd::inflate_piece(z + off[i], (size_t)(off[i + 1] - off[i]), dst + o0, expect, X);
-    if (rc != lpngd::OK) atomicCAS(status, 0, rc);
+    const uint32_t expect = (uint32_t)(total - o0 < (unsigned long long)lpngd::PIECE ? total - o0 : (unsigned long long)lpngd::PIECE);
+    if (lane == 0) {
+        lpngd::InflateScratch X;
+        const int rc = lpngd::inflate_piece(z + off[i], (size_t)(off[i + 1] - off[i]), buf, expect, X);
+        if (rc != lpngd::OK) atomicCAS(status, 0, rc);
+    }
+    __syncwarp();
+    // o0 is a multiple of 16 KB and the stream buffer is 256-byte aligned: 16-byte stores
+    uint4* g4 = reinterpret_cast<uint4*>(dst + o0);
+    const uint4* s4 = reinterpret_cast<const uint4*>(buf);
+    const uint32_t n16 = expect / 16u;
+    for (uint32_t k = lane; k < n16; k += 32u) g4[k] = s4[k];
+    for (uint32_t k = n16 * 16u + lane; k < expect; k += 32u) dst[o0 + k] = buf[k];
 }
 
+// Any other zlib stream: one thread (a deflate stream is one serial chain of bits), with the 32 KB match history in
+// shared memory.
 __global__ void k_pngd_inflate_serial(const uint8_t* __restrict__ z, size_t n, uint8_t* __restrict__ dst, size_t cap, int* __restrict__ status) {
+    __shared__ uint8_t window[32768];
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     lpngd::InflateScratch X;
     size_t produced = 0;
-    int rc = lpngd::inflate_zlib(z, n, dst, cap, &produced, X);
+    int rc = lpngd::inflate_zlib(z, n, dst, cap, &produced, X, window);
     if (rc == lpngd::OK && produced != cap) rc = lpngd::ERR_LENGTH;
     status[0] = rc;
 }
@@ -48,17 +69,32 @@ __global__ void k_pngd_adler_parts(const uint8_t* __restrict__ p, unsigned long 
     parts[i] = make_uint2(a, b);
 }
 
-// One thread folds the parts and compares with the four bytes that follow the deflate data (big endian).
+// One warp folds the parts (each lane a contiguous run of them, then the 32 runs in order) and compares with the four
+// bytes that follow the deflate data (big endian).
 __global__ void k_pngd_adler_check(const uint2* __restrict__ parts, unsigned long long n, const uint8_t* __restrict__ trailer, int* __restrict__ status) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    uint32_t A = 1, B = 0;
-    const unsigned long long nparts = (n + ADLER_SPAN - 1) / ADLER_SPAN;
-    for (unsigned long long i = 0; i < nparts; ++i) {
-        const size_t len = (size_t)(n - i * ADLER_SPAN < (unsigned long long)ADLER_SPAN ? n - i * ADLER_SPAN : (unsigned long long)ADLER_SPAN);
-        lpngd::adler_append(A, B, parts[i].x, parts[i].y, len);
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    const unsigned long long nparts = (n + ADLER_SPAN - 1) / ADLER_SPAN, per = (nparts + 31) / 32;
+    const unsigned long long p0 = threadIdx.x * per, p1 = p0 + per < nparts ? p0 + per : nparts;
+    // sums of this lane's run alone (A from 0), and its length in bytes
+    uint32_t a = 0, b = 0;
+    unsigned long long len = 0;
+    for (unsigned long long i = p0; i < p1; ++i) {
+        const size_t l = (size_t)(n - i * ADLER_SPAN < (unsigned long long)ADLER_SPAN ? n - i * ADLER_SPAN : (unsigned long long)ADLER_SPAN);
+        // appending a span to sums that started from zero: b += l * a + b_span, a += a_span
+        b = (uint32_t)((b + (unsigned long long)(l % lpngd::ADLER_MOD) * a + parts[i].y) % lpngd::ADLER_MOD);
+        a = (a + parts[i].x) % lpngd::ADLER_MOD;
+        len += l;
     }
-    const uint32_t want = ((uint32_t)trailer[0] << 24) | ((uint32_t)trailer[1] << 16) | ((uint32_t)trailer[2] << 8) | trailer[3];
-    status[1] = (((B << 16) | A) == want) ? 1 : 0;
+    uint32_t A = 1, B = 0;
+    for (int t = 0; t < 32; ++t) {
+        const uint32_t ta = __shfl_sync(0xffffffffu, a, t), tb = __shfl_sync(0xffffffffu, b, t);
+        const unsigned long long tl = __shfl_sync(0xffffffffu, len, t);
+        lpngd::adler_append(A, B, ta, tb, (size_t)tl);
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t want = ((uint32_t)trailer[0] << 24) | ((uint32_t)trailer[1] << 16) | ((uint32_t)trailer[2] << 8) | trailer[3];
+        status[1] = (((B << 16) | A) == want) ? 1 : 0;
+    }
 }
 
 __device__ __forceinline__ uint32_t load_pixel(const uint8_t* p, uint32_t bpp) {
@@ -79,8 +115,10 @@ __device__ __forceinline__ void store_pixel(uint8_t* p, uint32_t v, uint32_t bpp
 // x = s - i: the pixel above it was done by lane i-1 one step earlier (it arrives by shuffle), the one above-left
 // the step before that. Lane 0's row above belongs to the previous band: that band publishes how many pixels of its
 // last row are done (progress[band], release) and this one reads them 32 at a time (one per lane, acquire), so the
-// round trip through L2 is paid once per 32 steps. Bands are numbered in launch order, so a band only ever waits for
-// CTAs that were scheduled before its own.
+// round trip through L2 is paid once per 32 steps. The filtered bytes of the next eight steps are loaded while the
+// current eight are worked on (their latency was the whole step in the first version: 18.7 ms for a level-16 CLUT).
+// Bands are numbered in launch order, so a band only ever waits for CTAs that were scheduled before its own.
+constexpr int UNF_AHEAD = 8;
 __global__ void __launch_bounds__(256) k_pngd_unfilter(const uint8_t* __restrict__ stream, uint32_t w, uint32_t h, uint32_t bpp, uint8_t* __restrict__ out,
                                                         int* progress, int* status) {
     constexpr uint32_t FULL = 0xffffffffu;
@@ -99,37 +137,88 @@ __global__ void __launch_bounds__(256) k_pngd_unfilter(const uint8_t* __restrict
     const bool publish = band + 1 < nbands;   // full band with a follower: lane 31 is its last row
     uint32_t a = 0, prev_b = 0, last_out = 0, above = 0;
     const uint32_t steps = w + 31u;
-    for (uint32_t s = 0; s < steps; ++s) {
-        // the row above the band, 32 pixels at a time
-        if (above_row && s < w && (s & 31u) == 0) {
-            const uint32_t need = min(s + 32u, w);
-            if (lane == 0) {
-                int v;
-                do {
-                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(progress + band - 1) : "memory");
-                } while ((uint32_t)v < need);
+    const uint32_t mA = ft == 1u ? 255u : 0u, mB = ft == 2u ? 255u : 0u, mV = ft == 3u ? 255u : 0u, mP = ft == 4u ? 255u : 0u;
+    // Stores: a lane writes its own row, so a warp's store touches 32 rows -- 32 sectors per instruction, and as single
+    // bytes that was 50 M partial-sector writes for a level-16 CLUT (the whole 17 ms of the first version). Pixels leave as
+    // 32-bit words instead: one per RGBA pixel, three per four RGB pixels (when the rows are word aligned).
+    const bool words4 = bpp == 4u && (reinterpret_cast<uintptr_t>(out) & 3u) == 0;
+    const bool words3 = bpp == 3u && (reinterpret_cast<uintptr_t>(out) & 3u) == 0 && (rb & 3u) == 0;
+    uint32_t pk0 = 0, pk1 = 0, pk2 = 0;
+    uint32_t blk[UNF_AHEAD], nxt[UNF_AHEAD];
+#pragma unroll
+    for (int j = 0; j < UNF_AHEAD; ++j) {
+        const int x = j - (int)lane;
+        blk[j] = (valid && x >= 0 && x < (int)w) ? load_pixel(src + (size_t)x * bpp, bpp) : 0u;
+    }
+    for (uint32_t s0 = 0; s0 < steps; s0 += UNF_AHEAD) {
+#pragma unroll
+        for (int j = 0; j < UNF_AHEAD; ++j) {
+            const int x = (int)(s0 + UNF_AHEAD) + j - (int)lane;
+            nxt[j] = (valid && x >= 0 && x < (int)w) ? load_pixel(src + (size_t)x * bpp, bpp) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < UNF_AHEAD; ++j) {
+            const uint32_t s = s0 + j;
+            // the row above the band, 32 pixels at a time (s0 is a multiple of 8: the test is uniform)
+            if (above_row && s < w && (s & 31u) == 0) {
+                const uint32_t need = min(s + 32u, w);
+                if (lane == 0) {
+                    // relaxed polls with a pause, ONE fence once the count is there: an acquire load per poll compiles to an
+                    // L1 invalidation each (CCTL.IVALL), and a hundred waiting bands polling flushed the working bands' L1
+                    // sixteen million times (33 % of the stall samples, 15 ms for a level-16 CLUT)
+                    int v;
+                    for (;;) {
+                        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(progress + band - 1) : "memory");
+                        if ((uint32_t)v >= need) break;
+                        __nanosleep(200);
+                    }
+                    __threadfence();
+                }
+                __syncwarp();
+                const uint32_t xa = s + lane;
+                above = xa < w ? load_pixel_cg(above_row + (size_t)xa * bpp, bpp) : 0u;
             }
-            __syncwarp();
-            const uint32_t xa = s + lane;
-            above = xa < w ? load_pixel_cg(above_row + (size_t)xa * bpp, bpp) : 0u;
+            uint32_t b = __shfl_up_sync(FULL, last_out, 1);
+            const uint32_t from_above = __shfl_sync(FULL, above, s & 31u);
+            if (lane == 0) b = above_row ? from_above : 0u;
+            const int x = (int)s - (int)lane;
+            uint32_t cur = 0;
+            if (valid && x >= 0 && x < (int)w) {
+                cur = bpp == 3u ? lpngd::unfilter_pixel_masked<3>(blk[j], a, b, prev_b, mA, mB, mV, mP)
+                                : (bpp == 4u ? lpngd::unfilter_pixel_masked<4>(blk[j], a, b, prev_b, mA, mB, mV, mP)
+                                             : (bpp == 1u ? lpngd::unfilter_pixel_masked<1>(blk[j], a, b, prev_b, mA, mB, mV, mP)
+                                                          : lpngd::unfilter_pixel_masked<2>(blk[j], a, b, prev_b, mA, mB, mV, mP)));
+                if (words4) {
+                    reinterpret_cast<uint32_t*>(dstrow)[x] = cur;
+                } else if (words3) {
+                    const uint32_t q = (uint32_t)x & 3u;
+                    if (q == 0) pk0 = cur;
+                    else if (q == 1) { pk0 |= cur << 24; pk1 = cur >> 8; }
+                    else if (q == 2) { pk1 |= cur << 16; pk2 = cur >> 16; }
+                    else {
+                        pk2 |= cur << 8;
+                        uint32_t* q32 = reinterpret_cast<uint32_t*>(dstrow + (size_t)(x - 3) * 3u);
+                        q32[0] = pk0; q32[1] = pk1; q32[2] = pk2;
+                    }
+                    if (x == (int)w - 1 && q != 3u) {   // the row's last one to three pixels
+                        uint8_t* t = dstrow + (size_t)(x - (int)q) * 3u;
+                        const uint32_t nb = (q + 1u) * 3u;
+                        for (uint32_t k = 0; k < nb; ++k) t[k] = (uint8_t)((k < 4 ? pk0 >> (8u * k) : (k < 8 ? pk1 >> (8u * (k - 4)) : pk2 >> (8u * (k - 8)))));
+                    }
+                } else {
+                    store_pixel(dstrow + (size_t)x * bpp, cur, bpp);
+                }
+                a = cur;
+            }
+            prev_b = b;
+            last_out = cur;
+            if (publish && lane == 31u && x >= 0 && x < (int)w && (((uint32_t)x & 31u) == 31u || x == (int)w - 1)) {
+                __threadfence();
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(progress + band), "r"(x + 1) : "memory");
+            }
         }
-        uint32_t b = __shfl_up_sync(FULL, last_out, 1);
-        const uint32_t from_above = __shfl_sync(FULL, above, s & 31u);
-        if (lane == 0) b = above_row ? from_above : 0u;
-        const int x = (int)s - (int)lane;
-        uint32_t cur = 0;
-        if (valid && x >= 0 && x < (int)w) {
-            const uint32_t xv = load_pixel(src + (size_t)x * bpp, bpp);
-            cur = lpngd::unfilter_pixel(ft, xv, a, b, prev_b, bpp);
-            store_pixel(dstrow + (size_t)x * bpp, cur, bpp);
-            a = cur;
-        }
-        prev_b = b;
-        last_out = cur;
-        if (publish && lane == 31u && x >= 0 && x < (int)w && (((uint32_t)x & 31u) == 31u || x == (int)w - 1)) {
-            __threadfence();
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(progress + band), "r"(x + 1) : "memory");
-        }
+#pragma unroll
+        for (int j = 0; j < UNF_AHEAD; ++j) blk[j] = nxt[j];
     }
 }
 
@@ -162,6 +251,12 @@ __global__ void k_pngd_expand(const uint8_t* __restrict__ rows, unsigned long lo
     }
 }
 
+// One CTA per IDAT chunk: its payload to its place in the contiguous stream.
+__global__ void k_pngd_gather(const uint8_t* __restrict__ file, const unsigned long long* __restrict__ tab, uint8_t* __restrict__ z) {
+    const unsigned long long src = tab[2 * blockIdx.x], dst = tab[2 * blockIdx.x + 1], len = tab[2 * blockIdx.x + 3] - dst;
+    for (unsigned long long i = threadIdx.x; i < len; i += blockDim.x) z[dst + i] = file[src + i];
+}
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct DecodeLayout {
@@ -183,8 +278,23 @@ DecodeLayout decode_layout(const PngDecodePlan& p) {
 
 size_t png_decode_scratch_bytes(const PngDecodePlan& plan) { return decode_layout(plan).total; }
 
+void png_decode_gather(const uint8_t* file_dev, const unsigned long long* tab_dev, uint32_t nchunks, uint8_t* z_dev, cudaStream_t s) {
+    k_pngd_gather<<<nchunks, 256, 0, s>>>(file_dev, tab_dev, z_dev);
+}
+
 cudaError_t png_decode_async(const PngDecodePlan& plan, const uint8_t* z_dev, const unsigned long long* piece_off_dev, const uint32_t* palette_dev,
                              uint8_t* out_dev, void* scratch_dev, int* status_host, cudaStream_t s, unsigned* launches) {
+    {
+        // per device: more than 48 KB of dynamic shared memory has to be asked for
+        static bool attr_done[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+            cudaError_t ea = cudaFuncSetAttribute(k_pngd_inflate_pieces, cudaFuncAttributeMaxDynamicSharedMemorySize, PIECE_WARPS * lpngd::PIECE);
+            if (ea != cudaSuccess) return ea;
+            attr_done[dev] = true;
+        }
+    }
     const DecodeLayout L = decode_layout(plan);
     uint8_t* base = static_cast<uint8_t*>(scratch_dev);
     uint8_t* stream = base + L.stream;
@@ -201,7 +311,8 @@ cudaError_t png_decode_async(const PngDecodePlan& plan, const uint8_t* z_dev, co
     bool done = false;
     status_host[0] = status_host[1] = status_host[2] = status_host[3] = 0;
     if (plan.npieces > 0 && piece_off_dev) {
-        k_pngd_inflate_pieces<<<(plan.npieces + 63) / 64, 64, 0, s>>>(z_dev, piece_off_dev, plan.npieces, stream, total, status);
+        k_pngd_inflate_pieces<<<(plan.npieces + PIECE_WARPS - 1) / PIECE_WARPS, PIECE_WARPS * 32, PIECE_WARPS * lpngd::PIECE, s>>>(z_dev, piece_off_dev, plan.npieces, stream,
+                                                                                                                   total, status);
         k_pngd_adler_parts<<<(nparts + 127) / 128, 128, 0, s>>>(stream, total, parts);
         k_pngd_adler_check<<<1, 32, 0, s>>>(parts, total, trailer, status);
         nl += 3;

@@ -26,4 +26,8 @@ size_t png_decode_scratch_bytes(const PngDecodePlan& plan);
 cudaError_t png_decode_async(const PngDecodePlan& plan, const uint8_t* z_dev, const unsigned long long* piece_off_dev, const uint32_t* palette_dev,
                              uint8_t* out_dev, void* scratch_dev, int* status_host, cudaStream_t s, unsigned* launches);
 
+// The IDAT payloads of a file in device memory into one contiguous stream: tab = nchunks + 1 pairs (offset in the file,
+// offset in the stream), the last pair closing the stream.
+void png_decode_gather(const uint8_t* file_dev, const unsigned long long* tab_dev, uint32_t nchunks, uint8_t* z_dev, cudaStream_t s);
+
 }  // namespace lutgen

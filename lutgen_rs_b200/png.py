@@ -1,7 +1,8 @@
-"""PNG writer around the path: what `RgbImage::save(path)` / `RgbaImage::save(path)`
-do for the reference's callers (crates/cli/src/main.rs:767, 811, 839 `lut.save(&path)`; 862-871
-`image.save(&path)`), with the encoding done by the CUDA kernels of csrc/png.cu through the C ABI
-(lutgen_cuda_encode_png*). Lossless: any PNG reader returns the pixels that went in. No CPU route.
+"""PNG files around the path: what `RgbImage::save(path)` / `RgbaImage::save(path)` do for the
+reference's callers (crates/cli/src/main.rs:767, 811, 839 `lut.save(&path)`; 862-871 `image.save(&path)`) and what
+`load_image` (main.rs:602-613: image::open + to_rgba8 / to_rgb8) does for the PNG files they read, with encoding and
+decoding done by the CUDA kernels of csrc/png.cu and csrc/png_decode.cu through the C ABI (lutgen_cuda_encode_png*,
+lutgen_cuda_decode_png*). Lossless both ways. No CPU route.
 """
 import ctypes as C
 import threading
@@ -99,4 +100,44 @@ def correct_image_png(image, hald_clut, level=None):
     with _stage_lock:
         out = _staging(bound(w, h, 4))
         _native.check(_native.lib().lutgen_cuda_apply_hald_png(_ptr(a), w, h, _ptr(lut), int(level), _ptr(out), out.size, C.byref(n)))
+        return out[:n.value].tobytes()
+
+
+def info(data):
+    """(width, height, channels, has_alpha) of a PNG file's bytes without decoding it (lutgen_cuda_png_info)."""
+    buf = np.frombuffer(data, np.uint8)
+    w, h, c, a = C.c_uint32(0), C.c_uint32(0), C.c_int32(0), C.c_int32(0)
+    _native.check(_native.load().lutgen_cuda_png_info(_ptr(buf), buf.size, C.byref(w), C.byref(h), C.byref(c), C.byref(a)))
+    return w.value, h.value, c.value, bool(a.value)
+
+
+def decode(data, channels=0):
+    """PNG file bytes -> (h, w, c) uint8 array, decoded on the device (`image::open(path)` for a PNG followed by
+    to_rgb8() for channels=3, to_rgba8() for channels=4; channels=0 keeps the file's own layout). Raises
+    LutgenError for flavours the decoder leaves to the caller (16-bit, interlaced) and for damaged files."""
+    buf = np.frombuffer(data, np.uint8)
+    w, h, c, _ = info(data)
+    oc = int(channels) if channels else c
+    out = np.empty((h, w, oc), np.uint8)
+    _native.check(_native.lib().lutgen_cuda_decode_png(_ptr(buf), buf.size, int(channels), _ptr(out), out.size))
+    return out
+
+
+def load(path, channels=0):
+    """`image::open(path)` for a .png path."""
+    with open(path, "rb") as f:
+        return decode(f.read(), channels)
+
+
+def correct_png_file(image_png, hald_clut_png):
+    """`lutgen apply --hald-clut clut.png image.png`, file bytes to file bytes (crates/cli/src/main.rs:832-871): both PNGs
+    are decoded, the image corrected and re-encoded on the device; only compressed bytes cross PCIe. Returns the PNG
+    bytes of the corrected RGBA image."""
+    a = np.frombuffer(image_png, np.uint8)
+    b = np.frombuffer(hald_clut_png, np.uint8)
+    w, h, _, _ = info(image_png)
+    n = C.c_size_t(0)
+    with _stage_lock:
+        out = _staging(bound(w, h, 4))
+        _native.check(_native.lib().lutgen_cuda_apply_hald_png_file(_ptr(a), a.size, _ptr(b), b.size, _ptr(out), out.size, C.byref(n)))
         return out[:n.value].tobytes()

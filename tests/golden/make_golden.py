@@ -19,12 +19,17 @@ Outputs (all under tests/golden/):
                              nearest 16, lum 1.0, preserve false, level 10
   nord_hald10.npz            docs/assets/nord-hald-clut.png, same parameters
 
+  gruvbox-dark-hald-clut.png the same docs/assets file as it is (277 KB): a foreign, single-stream PNG for the
+                             PNG reader's tests (tests/test_gpu_png_decode.py), whose expected pixels are the
+                             .npz above (PIL's decode of it)
+
 These three images are the ONLY numeric pins the reference holds for the RBF
 path; everything else is pinned by the KAT in
 crates/cli/src/main.rs:1192-1226 (restated in tests/test_oracle.py).
 """
 import json
 import os
+import shutil
 import tomllib
 
 import numpy as np
@@ -60,5 +65,10 @@ def main():
         print(out, arr.shape, "written")
 
 
+def copy_png_fixture():
+    shutil.copyfile(os.path.join(REF, "docs/assets/gruvbox-dark-hald-clut.png"), os.path.join(HERE, "gruvbox-dark-hald-clut.png"))
+
+
 if __name__ == "__main__":
+    copy_png_fixture()
     main()
