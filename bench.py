@@ -67,6 +67,31 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def bind_near_gpu(torch, local_rank):
+    """One process per GPU: run this process on the cores of the memory node its GPU hangs off (sysfs), so that the
+    host pages it touches first are allocated there and its PCIe copies do not cross the socket link. Returns a short
+    description for the JSON line. Only used for N > 1 (at N = 1 the CPU baseline wants every core)."""
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        dev = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{dev}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "no memory-node information for the GPU"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"node {node} has none of this process's cores"
+        os.sched_setaffinity(0, cpus)
+        return f"node {node}, {len(cpus)} cores"
+    except (OSError, ValueError, AttributeError) as e:
+        return f"unavailable ({type(e).__name__})"
+
+
 def load_palette():
     with open(os.path.join(ROOT, "tests", "golden", "palettes.json")) as f:
         return np.array(json.load(f)["catppuccin_mocha"], np.uint8)
@@ -220,6 +245,7 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    binding = bind_near_gpu(torch, local_rank) if world > 1 else None
     device.init(local_rank)
     if world > 1:
         # NCCL prints its version banner on stdout when the communicator comes up; stdout must
@@ -353,6 +379,11 @@ def run_b200(args):
                 f.truncate(3 * entries)
         barrier()
         shared_img = np.memmap(shm_path, dtype=np.uint8, mode="r+", shape=(side, side, 3))
+        # every rank touches the rows it will write first (the process runs next to its GPU, bind_near_gpu): the pages
+        # are allocated on that memory node, and the rank's copies stay on its own socket
+        for r0_, r1_ in interpolation.InterpolatedRemapper.part_rows(LEVEL_GEN, rank, world):
+            shared_img[r0_:r1_] = 0
+        barrier()
         rc = torch.cuda.cudart().cudaHostRegister(shared_img.ctypes.data, 3 * entries, 0)
         if int(rc) != 0:
             print(f"rank {rank}: cudaHostRegister of the shared image failed ({rc}); copies will be pageable", file=sys.stderr)
@@ -491,7 +522,9 @@ def run_b200(args):
                          "host buffer, remapper dropped -- every step") if world == 1 else
                         (f"every rank: GaussianRemapper constructed, lutgen_cuda_generate_lut_part -- its share of the row groups generated and copied "
                          f"over its own PCIe link into ONE page-locked image in shared memory ({world} ranks, no GPU-to-GPU exchange), remapper dropped -- "
-                         "every step; h2d bytes are per rank")},
+                         "every step; h2d bytes are per rank"),
+                **({"host_binding": f"each rank runs on the cores of its GPU's memory node and touched its own rows of the image first (rank 0: {binding})"}
+                   if world > 1 else {})},
         "roofline": {"bound": "fp32", "achieved": gen_achieved, "peak": fp32.value, "unit": "TFLOP/s",
                      "frac": gen_achieved / fp32.value if fp32.value else None,
                      "traffic": profiled_traffic().get("k_remap_warp_level16_bytes_per_launch") if world == 1 else None,

@@ -351,6 +351,19 @@ LUTGEN_API int lutgen_cuda_srgb_to_oklab_fast(const uint8_t* rgb, size_t n, floa
  * kernel's classification, out128[0..64) = number of UNCERTAIN colours, [64..128) = IN colours. */
 LUTGEN_API int lutgen_cuda_debug_stats(uint32_t* out128, int reset);
 
+/* With LUTGEN_CUDA_STATS=1: the timeline of the small-palette kernel's launches since the last reset, from the GPU's
+ * nanosecond clock (low words): out4[0] = first thread block started, [1] = last warp out of tiles, [2] = last warp's
+ * stores (to the peers too) complete, [3] = exchange barrier passed. Reset between launches to time one. */
+LUTGEN_API int lutgen_cuda_debug_timeline(uint32_t* out4, int reset);
+
+/* Measurement aid (tools/time_exchange.py): the exchange of lutgen_cuda_generate_lut_exchange_dev without its
+ * arithmetic. The level's CLUT is taken as already present in luts_rgb_dev[0]; this GPU's share of it is sent to the
+ * other destinations (or to the multicast address) and the barrier follows. pattern 0: whole strips (12 * level^2
+ * contiguous bytes), 1: hand-outs of four tiles (96-byte rows). Needs level % 4 == 0 and 16-byte aligned buffers. */
+LUTGEN_API int lutgen_cuda_debug_exchange_probe_dev(uint8_t level, uint8_t* const* luts_rgb_dev, int nluts, uint8_t* multicast_lut,
+                                                    uint32_t shard_index, uint32_t shard_count, unsigned* const* barrier_flags_dev_table,
+                                                    int pattern, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

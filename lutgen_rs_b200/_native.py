@@ -24,7 +24,7 @@ EXPORTS = [
     "lutgen_cuda_generate_lut", "lutgen_cuda_generate_lut_rows_dev", "lutgen_cuda_remap_image",
     "lutgen_cuda_remap_image_dev", "lutgen_cuda_sampling_get_noise", "lutgen_cuda_sampling_set_noise",
     "lutgen_cuda_srgb_to_oklab", "lutgen_cuda_oklab_to_srgb", "lutgen_cuda_measure_peaks",
-    "lutgen_cuda_srgb_to_oklab_fast", "lutgen_cuda_debug_stats",
+    "lutgen_cuda_srgb_to_oklab_fast", "lutgen_cuda_debug_stats", "lutgen_cuda_debug_exchange_probe_dev", "lutgen_cuda_debug_timeline",
     "lutgen_cuda_generate_lut_rows_multi_dev", "lutgen_cuda_device_alloc", "lutgen_cuda_device_free",
     "lutgen_cuda_ipc_export", "lutgen_cuda_ipc_import", "lutgen_cuda_ipc_close",
     "lutgen_cuda_generate_lut_shard_multi_dev", "lutgen_cuda_peer_barrier_dev", "lutgen_cuda_generate_lut_shard_mc_dev",
@@ -112,6 +112,8 @@ def load():
             "lutgen_cuda_oklab_to_srgb": ([vp, sz, vp], i32),
             "lutgen_cuda_srgb_to_oklab_fast": ([vp, sz, vp], i32),
             "lutgen_cuda_debug_stats": ([vp, i32], i32),
+            "lutgen_cuda_debug_timeline": ([vp, i32], i32),
+            "lutgen_cuda_debug_exchange_probe_dev": ([u8, C.POINTER(vp), i32, vp, u32, u32, vp, i32, vp], i32),
             "lutgen_cuda_measure_peaks": ([C.POINTER(C.c_double), C.POINTER(C.c_double)], i32),
             "lutgen_cuda_generate_lut_rows_multi_dev": ([vp, u8, C.POINTER(vp), i32, u32, u32, vp], i32),
             "lutgen_cuda_generate_lut_shard_multi_dev": ([vp, u8, C.POINTER(vp), i32, u32, u32, vp], i32),

@@ -106,9 +106,12 @@ struct Ctx {
     // pair), handed out round robin so that launches in flight on different streams do not share one
     uint32_t* counters = nullptr;
     std::atomic<uint32_t> counter_next{0};
+    uint32_t* strip_counters = nullptr;   // kStripRings x kStripMax, zero between launches (k_remap_warp's strip exchange)
+    std::atomic<uint32_t> strip_next{0};
     int index = 0;                  // position in g_ctx
 };
 constexpr uint32_t kCounterPairs = 1024;
+constexpr uint32_t kStripMax = 65536, kStripRings = 4;   // strips of a level-32 CLUT; launches in flight per GPU
 
 // One context per GPU this process drives (ONE process, up to 8 devices). g_ctx[0] is the primary one:
 // every entry point runs on it unless it shards its work over the others itself (generate_lut, apply_hald_batch).
@@ -493,36 +496,67 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
     a.ntiles_global = a.ntiles;
     a.shard_index = 0;
     a.shard_count = 1;
+    a.deal = 1;
+    a.strip_counter = nullptr;
     // hand-outs of WT_BATCH warp tiles keep neighbouring tiles in one warp (and feed the 96-byte row stores of
     // the MULTI variant); small ranges take single tiles so that every SM gets work
+    const char* batch_str = getenv("LUTGEN_CUDA_BATCH");   // experiments (tools/time_shares.py, tools/time_exchange.py)
+    const int batch_env = batch_str ? atoi(batch_str) : 0;
+    // Several GPUs, whole CLUT, rows that are multiples of 16 bytes: the strip exchange (wt_push_strip) is possible --
+    // whole strips are dealt to the shards, so what a GPU sends is 12 cs contiguous bytes at a time however small its
+    // hand-outs are. Measured and NOT chosen by default (tools/time_exchange.py, level 16, 8 / 4 GPUs): sent alone, the
+    // CLUT takes 90 us to arrive as 3072-byte runs and 112-121 us as the staged form's 96-byte rows, but the fused step
+    // takes 127 / 148 us with strips and 127 / 134 us staged: a strip leaves only when its 32 tiles are done, its sender
+    // stalls on the saturated fabric like any other warp, and the count per tile (a release + an atomic, 0.7 us) makes
+    // the arithmetic slower (tools/time_multi_dest.py, half a CLUT: 174 us against 162 us). LUTGEN_CUDA_STRIPS=1 selects it.
+    const char* strips_env = getenv("LUTGEN_CUDA_STRIPS");   // 0 / 1: never / whenever possible
+    const bool strips = !BIG && multi && f.shard_count > 1 && a.whole_tiles && a.words_ok == 2 && (f.cs & 15u) == 0 && f.begin == 0 &&
+                        f.count == (unsigned long long)f.cs * f.cs * f.cs && a.ntiles / a.tiles_r <= kStripMax &&
+                        strips_env && atoi(strips_env) != 0;
     {
         const uint32_t share = a.ntiles / (MODE == FRONT_LUT && f.shard_count > 1 ? f.shard_count : 1u);
-        a.batch = share >= (uint32_t)g.sm_count * WT_WARPS * 3u * WT_BATCH ? (uint32_t)WT_BATCH : 1u;
+        // measured (tools/time_shares.py, level 16): hand-outs of 4 win 3 % on the whole CLUT (131072 tiles, 55 per resident
+        // warp) and lose 6 / 16 / 24 % on a half / quarter / eighth of it, where the last hand-out of a warp is a larger
+        // part of its work. The staged exchange keeps them while a warp has three: its rows on NVLink are 24 bytes per tile.
+        const uint32_t per_warp = (multi && !strips) ? 3u : 24u;
+        a.batch = share >= (uint32_t)g.sm_count * WT_WARPS * per_warp * WT_BATCH ? (uint32_t)WT_BATCH : 1u;
+        if (batch_env == 1 || batch_env == WT_BATCH) a.batch = (uint32_t)batch_env;
     }
-    if (MODE == FRONT_LUT && f.shard_count > 1) {
+    if (strips) {
+        const uint32_t nstrips = a.ntiles_global / a.tiles_r;
+        const uint32_t mine = nstrips > f.shard_index ? (nstrips - f.shard_index + f.shard_count - 1) / f.shard_count : 0;
+        a.shard_index = f.shard_index;
+        a.shard_count = f.shard_count;
+        a.deal = a.tiles_r;
+        a.ntiles = mine * a.tiles_r;
+        if (a.tiles_r % a.batch) a.batch = 1;   // a hand-out stays inside one strip
+        a.strip_counter = g.strip_counters + (size_t)(g.strip_next.fetch_add(1, std::memory_order_relaxed) % kStripRings) * kStripMax;
+    } else if (MODE == FRONT_LUT && f.shard_count > 1) {
         // hand-outs (a.batch warp tiles, or one CTA tile) index, index + count, ...
         const uint32_t per = BIG ? 1u : a.batch, handouts = (a.ntiles_global + per - 1) / per;
         a.shard_index = f.shard_index;
         a.shard_count = f.shard_count;
+        a.deal = per;
         a.ntiles = handouts > f.shard_index ? ((handouts - f.shard_index + f.shard_count - 1) / f.shard_count) * per : 0;
-        if (a.ntiles == 0 && !(f.bar_nranks > 1)) {   // with a barrier the (empty) kernel still has to take part in it
-            if (BIG) CU_TRY(cudaMemsetAsync(r->flag_count, 0, 2 * sizeof(uint32_t), s));
-            return LUTGEN_OK;
-        }
+    }
+    if (a.shard_count > 1 && a.ntiles == 0 && !(f.bar_nranks > 1)) {   // with a barrier the (empty) kernel still has to take part in it
+        if (BIG) CU_TRY(cudaMemsetAsync(r->flag_count, 0, 2 * sizeof(uint32_t), s));
+        return LUTGEN_OK;
     }
     // MULTI: the variant that stages tiles and writes them to several destinations (multi-GPU); a single
     // destination takes the leaner kernel (the extra code costs instruction-cache misses)
-    const int variant = multi ? 1 : (deep ? 2 : 0);
-    static int per_sm[3] = {0, 0, 0};  // per instantiation
+    const int variant = strips ? 3 : (multi ? 1 : (deep ? 2 : 0));
+    static int per_sm[4] = {0, 0, 0, 0};  // per instantiation
     if (per_sm[variant] == 0) {
         int v = 0;
         if (BIG) {
             if (multi) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp_big<KIND, MODE, EPT, MODE == FRONT_LUT>, WT_THREADS, 0));
             else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp_big<KIND, MODE, EPT, false>, WT_THREADS, 0));
         } else {
-            if (multi) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, MODE == FRONT_LUT, 1>, WT_THREADS, 0));
-            else if (deep) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, false, GROUPS_LEAN>, WT_THREADS, 0));
-            else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, false, 1>, WT_THREADS, 0));
+            if (strips) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, MODE == FRONT_LUT ? 2 : 0, 1>, WT_THREADS, 0));
+            else if (multi) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, MODE == FRONT_LUT ? 1 : 0, 1>, WT_THREADS, 0));
+            else if (deep) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, 0, GROUPS_LEAN>, WT_THREADS, 0));
+            else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, 0, 1>, WT_THREADS, 0));
         }
         per_sm[variant] = v < 1 ? 1 : v;
     }
@@ -531,7 +565,7 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     a.tail_cut = a.ticket_end = a.ntiles;
-    if (!BIG && a.batch > 1 && a.shard_count == 1) {
+    if (!BIG && a.batch > 1 && (a.shard_count == 1 || strips)) {
         // the last two tiles per resident warp go out one by one (k_remap_warp's ticket scheme)
         const uint32_t singles = std::min(a.ntiles, grid * (uint32_t)WT_WARPS * 2u);
         a.tail_cut = (a.ntiles - singles) / a.batch * a.batch;
@@ -542,9 +576,10 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
         if (multi) k_remap_warp_big<KIND, MODE, EPT, MODE == FRONT_LUT><<<grid, WT_THREADS, 0, s>>>(a);
         else k_remap_warp_big<KIND, MODE, EPT, false><<<grid, WT_THREADS, 0, s>>>(a);
     } else {
-        if (multi) k_remap_warp<KIND, MODE, EPT, MODE == FRONT_LUT, 1><<<grid, WT_THREADS, 0, s>>>(a);
-        else if (deep) k_remap_warp<KIND, MODE, EPT, false, GROUPS_LEAN><<<grid, WT_THREADS, 0, s>>>(a);
-        else k_remap_warp<KIND, MODE, EPT, false, 1><<<grid, WT_THREADS, 0, s>>>(a);
+        if (strips) k_remap_warp<KIND, MODE, EPT, MODE == FRONT_LUT ? 2 : 0, 1><<<grid, WT_THREADS, 0, s>>>(a);
+        else if (multi) k_remap_warp<KIND, MODE, EPT, MODE == FRONT_LUT ? 1 : 0, 1><<<grid, WT_THREADS, 0, s>>>(a);
+        else if (deep) k_remap_warp<KIND, MODE, EPT, 0, GROUPS_LEAN><<<grid, WT_THREADS, 0, s>>>(a);
+        else k_remap_warp<KIND, MODE, EPT, 0, 1><<<grid, WT_THREADS, 0, s>>>(a);
     }
     LAUNCH_CHECK();
     return LUTGEN_OK;
@@ -980,9 +1015,12 @@ int init_current_ctx(int device, int visible) {
     CU_TRY(cudaMemcpy(g.tables, &host, sizeof host, cudaMemcpyHostToDevice));
     CU_TRY(cudaMalloc((void**)&g.counters, 2 * kCounterPairs * sizeof(uint32_t)));
     CU_TRY(cudaMemset(g.counters, 0, 2 * kCounterPairs * sizeof(uint32_t)));
+    CU_TRY(cudaMalloc((void**)&g.strip_counters, kStripRings * kStripMax * sizeof(uint32_t)));
+    CU_TRY(cudaMemset(g.strip_counters, 0, kStripRings * kStripMax * sizeof(uint32_t)));
     if (getenv("LUTGEN_CUDA_STATS")) {
-        CU_TRY(cudaMalloc((void**)&g.stats, 128 * sizeof(uint32_t)));
-        CU_TRY(cudaMemset(g.stats, 0, 128 * sizeof(uint32_t)));
+        CU_TRY(cudaMalloc((void**)&g.stats, 136 * sizeof(uint32_t)));
+        CU_TRY(cudaMemset(g.stats, 0, 136 * sizeof(uint32_t)));
+        CU_TRY(cudaMemset(g.stats + 128, 0xff, sizeof(uint32_t)));
     }
     g.ready = true;
     return LUTGEN_OK;
@@ -1014,6 +1052,8 @@ void release_current_ctx() {
     g.tables = nullptr;
     if (g.counters) cudaFree(g.counters);
     g.counters = nullptr;
+    if (g.strip_counters) cudaFree(g.strip_counters);
+    g.strip_counters = nullptr;
     if (g.stats) cudaFree(g.stats);
     g.stats = nullptr;
     if (g.stream) cudaStreamDestroy(g.stream);
@@ -2312,6 +2352,50 @@ int lutgen_cuda_srgb_to_oklab(const uint8_t* rgb, size_t n, float* out_lab) {
     LAUNCH_CHECK();
     CU_TRY(cudaMemcpyAsync(out_lab, dout, 12 * n, cudaMemcpyDeviceToHost, g.stream));
     CU_TRY(cudaStreamSynchronize(g.stream));
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_debug_exchange_probe_dev(uint8_t level, uint8_t* const* luts_rgb_dev, int nluts, uint8_t* multicast_lut, uint32_t shard_index,
+                                         uint32_t shard_count, unsigned* const* barrier_flags_dev_table, int pattern, void* stream) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!luts_rgb_dev || nluts < 2 || nluts > 1 + LUTGEN_MAX_PEERS || !level_ok(level) || (level & 3) || shard_count == 0 || shard_index >= shard_count ||
+        pattern < 0 || pattern > 1)
+        return fail(LUTGEN_ERR_INVALID, "exchange probe: level %u, %d destinations, shard %u of %u, pattern %d", level, nluts, shard_index, shard_count, pattern);
+    uintptr_t bits = reinterpret_cast<uintptr_t>(multicast_lut);
+    for (int i = 0; i < nluts; ++i) bits |= reinterpret_cast<uintptr_t>(luts_rgb_dev[i]);
+    if (bits & 15u) return fail(LUTGEN_ERR_INVALID, "exchange probe: buffers must be 16-byte aligned");
+    Front f{};
+    f.out = luts_rgb_dev[0];
+    f.nextra = nluts - 1;
+    for (int i = 1; i < nluts; ++i) f.extra[i - 1] = luts_rgb_dev[i];
+    f.cs = (uint32_t)level * level;
+    f.csm1 = f.cs - 1;
+    f.shard_index = shard_index;
+    f.shard_count = shard_count;
+    f.mc = multicast_lut;
+    if (barrier_flags_dev_table) {
+        f.bar_flags = barrier_flags_dev_table;
+        f.bar_nranks = nluts;
+        f.bar_rank = (int)shard_index;
+    }
+    const uint32_t pair = g.counter_next.fetch_add(1, std::memory_order_relaxed) % kCounterPairs;
+    k_exchange_probe<<<2 * g.sm_count, WT_THREADS, 0, (cudaStream_t)stream>>>(f, f.cs / 8u, f.cs / 4u, pattern, g.counters + 2 * pair + 1);
+    LAUNCH_CHECK();
+    return LUTGEN_OK;
+}
+
+int lutgen_cuda_debug_timeline(uint32_t* out4, int reset) {
+    int rc = ensure_ready();
+    if (rc) return rc;
+    if (!out4) return fail(LUTGEN_ERR_INVALID, "NULL argument");
+    if (!g.stats) return fail(LUTGEN_ERR_UNSUPPORTED, "set LUTGEN_CUDA_STATS=1 before lutgen_cuda_init");
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(out4, g.stats + 128, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (reset) {
+        CU_TRY(cudaMemset(g.stats + 128, 0, 8 * sizeof(uint32_t)));
+        CU_TRY(cudaMemset(g.stats + 128, 0xff, sizeof(uint32_t)));
+    }
     return LUTGEN_OK;
 }
 

@@ -72,6 +72,8 @@ struct WarpArgs {
     uint32_t shard_index, shard_count;  // this launch takes hand-outs index, index + count, ... (1 hand-out = `batch` warp tiles / 1 CTA tile)
     uint32_t batch;           // warp tiles per hand-out: WT_BATCH, or 1 when the range has too few tiles to fill the GPU otherwise
     uint32_t tail_cut, ticket_end;   // k_remap_warp: single-tile hand-outs from ticket tail_cut on; tickets end at ticket_end
+    uint32_t deal;            // shards: runs of `deal` consecutive tiles go to the shards in turn (the hand-out, or a whole strip)
+    uint32_t* strip_counter;  // MULTI, strip exchange: tiles finished per local strip (zero at launch, left zero), else nullptr
     uint32_t* flag_list;
     uint32_t* flag_count;
     uint32_t* tile_counter;   // zero at launch; k_remap_warp's last CTA zeroes it (and done_counter) again
@@ -84,6 +86,13 @@ struct WarpArgs {
     int words_ok;             // FRONT_LUT, cs % 4 == 0: 1 = destinations 4-byte aligned (whole tiles leave as words),
                               // 2 = 16-byte aligned (whole hand-outs leave as 16-byte pieces), 0 = byte stores
 };
+
+// Nanosecond clock shared by all SMs (low word): k_remap_warp's timeline under LUTGEN_CUDA_STATS (stats[128..132)).
+__device__ __forceinline__ uint32_t wt_clock_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return (uint32_t)t;
+}
 
 __device__ __forceinline__ __half2 u32_as_half2(uint32_t v) {
     return *reinterpret_cast<const __half2*>(&v);
@@ -801,6 +810,94 @@ __device__ __noinline__ void wt_flush_batch(uint8_t* out, bool mc, uint8_t* cons
     }
 }
 
+// The barrier that ends an exchange, run by ONE thread once every store of this GPU to the peers has been issued and
+// fenced: it publishes this rank's step number in every rank's flag array (release, system scope) and waits until all
+// ranks have published theirs in its own array. The step number lives on the device (word LUTGEN_BAR_EPOCH of the
+// rank's own array), so the host passes nothing per launch.
+__device__ __forceinline__ void wt_peer_barrier(unsigned* const* flags, int nranks, int rank) {
+    unsigned* mine = flags[rank];
+    const unsigned epoch = mine[LUTGEN_BAR_EPOCH] + 1u;
+    mine[LUTGEN_BAR_EPOCH] = epoch;
+    // ONE system-scope fence, then plain flag stores: a st.release.sys per peer is a fence each, one after the other
+    // (8 ranks: 20 us between "stores landed" and "barrier passed" in tools/time_exchange_timeline.py, on every rank)
+    __threadfence_system();
+    for (int t = 0; t < nranks; ++t) {
+        unsigned* remote = flags[t] + rank;
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+    }
+    for (int t = 0; t < nranks; ++t) {
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + t) : "memory");
+        } while ((int)(v - epoch) < 0);
+    }
+}
+
+// Strip exchange. A strip is the tiles_r warp tiles that share (g, b): EPT planes x 4 rows of cs entries, and the 4 rows
+// of a plane are ONE run of 12 cs bytes in the CLUT. The strips are dealt to the GPUs in turn; a GPU's warps write their
+// tiles into the GPU's own CLUT exactly as the one-GPU kernel does, and the warp that completes a strip reads it back
+// (L2) and sends its EPT runs to the peers in 16-byte pieces, 512 contiguous bytes per warp instruction -- whole 128-byte
+// lines on the NVLink side whatever the hand-out size, where staged hand-outs travel as 96-byte rows.
+// Needs cs % 16 == 0 (16-byte aligned runs) and 16-byte aligned destinations.
+template <int EPT>
+__device__ __noinline__ void wt_push_strip(const uint8_t* own, uint8_t* dst, uint8_t* const* extras, int nextra, uint32_t cs, uint32_t b0, uint32_t g0) {
+    // (scalars, not the kernel's argument struct: a reference to it would make the caller copy it to local memory)
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t pieces = (cs * 3u) >> 2;   // 16-byte pieces in 4 rows
+#pragma unroll 1
+    for (uint32_t e = 0; e < (uint32_t)EPT; ++e) {
+        const size_t off = 3ull * (((size_t)(b0 + e) * cs + g0) * cs);
+        const uint4* src = reinterpret_cast<const uint4*>(own + off);
+#pragma unroll 1
+        for (uint32_t i0 = 0; i0 < pieces; i0 += 192u) {
+            uint4 v[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const uint32_t i = i0 + 32u * j + lane;
+                if (i < pieces) v[j] = __ldcg(src + i);
+            }
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const uint32_t i = i0 + 32u * j + lane;
+                if (i < pieces) {
+                    if (dst) multimem_st_v4(dst + off + 16ull * i, v[j]);
+#pragma unroll 1
+                    for (int x = 0; x < nextra; ++x) *reinterpret_cast<uint4*>(extras[x] + off + 16ull * i) = v[j];
+                }
+            }
+        }
+    }
+}
+
+// What wt_strip_done needs, in shared memory (one copy per CTA) so that the call passes a pointer, not a dozen values.
+struct WtStripCfg {
+    uint32_t* counter;
+    uint8_t* own;
+    uint8_t* mc;
+    int nextra;
+    uint32_t cs, b_lo, tiles_g, deal, shard_count, shard_index;
+};
+
+// `n` more tiles of local strip `strip` are in this GPU's CLUT. The warp whose count completes the strip sends it.
+template <int EPT>
+__device__ __noinline__ void wt_strip_done(const WtStripCfg* c, uint8_t* const* extras, uint32_t strip, uint32_t n) {
+    uint32_t full = 0;
+    __syncwarp();
+    if ((threadIdx.x & 31u) == 0) {
+        // this warp's stores before its count: a release on the atomic (MEMBAR.ALL.GPU), not __threadfence(), whose
+        // MEMBAR.SC.GPU + invalidation of the SM's L1 cost 1.4 us per tile when measured here
+        uint32_t prev;
+        asm volatile("atom.release.gpu.global.add.u32 %0, [%1], %2;" : "=r"(prev) : "l"(c->counter + strip), "r"(n) : "memory");
+        full = prev + n == c->deal;
+        if (full) c->counter[strip] = 0u;   // as the next launch expects to find it
+    }
+    if (__shfl_sync(0xffffffffu, full, 0)) {
+        __threadfence();   // the other warps' stores (counted before ours) before our loads (once per strip)
+        const uint32_t gs = strip * c->shard_count + c->shard_index, sb = gs / c->tiles_g;
+        wt_push_strip<EPT>(c->own, c->mc, extras, c->nextra, c->cs, c->b_lo + sb * (uint32_t)EPT, (gs - sb * c->tiles_g) * 4u);
+    }
+}
+
 // Entry-by-entry stores of one lane's four results (tiles cut by the launch's range or by the cube's
 // edge, images, the table front end). Out of line: with up to eight destinations the byte stores
 // are a few hundred instructions that whole tiles never execute.
@@ -842,7 +939,8 @@ __device__ __forceinline__ void wt_store(const WarpArgs& a, const WtTile<EPT>& T
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
     if (!MULTI) {
-        // one destination: plain stores, entry by entry (the CLUT stays in L2, which merges the bytes)
+        // one destination: plain stores, entry by entry (the CLUT stays in L2, which merges the bytes). Strip exchange:
+        // the same, into this GPU's own CLUT -- whole strips leave for the peers later (wt_push_strip)
 #pragma unroll
         for (int e = 0; e < EPT; ++e) {
             if (!((smask >> e) & 1u)) continue;
@@ -1087,8 +1185,13 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
 // GROUPS = 2 (brick front ends, single destination): the tile is 8 blue planes deep, two groups of four
 // entries per lane that share ONE classification -- the second group's Oklab values wait in shared memory
 // while the first is processed. Halves the classification's share of the work for a slightly larger box.
-template <int KIND, int MODE, int EPT, bool MULTI, int GROUPS>
+// XCH (several destinations, FRONT_LUT): 0 = one destination; 1 = tiles staged in shared memory and stored to every
+// destination by the warp that computed them; 2 = strip exchange (wt_push_strip): the one-destination stores, plus a
+// count per strip -- its hot loop is the one-destination kernel's (the staged variant's larger code misses the
+// instruction cache: 83-87 % hit rate against 99.5 %, measured).
+template <int KIND, int MODE, int EPT, int XCH, int GROUPS>
 __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpArgs a) {
+    constexpr bool MULTI = XCH == 1, STRIPS = XCH == 2;
     static_assert(EPT == 4, "entries are processed in two pairs (wt_store_entries takes four results)");
     static_assert(GROUPS == 1 || (GROUPS == 2 && MODE != FRONT_IMAGE && !MULTI), "two groups: brick tiles of the lean kernel only");
     constexpr uint32_t TD = (uint32_t)EPT * GROUPS;   // blue planes per tile
@@ -1104,6 +1207,7 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
     __shared__ f2 s_stash[GROUPS == 2 ? WT_WARPS : 1][6][GROUPS == 2 ? 32 : 1];   // the second group's Lp, Ap, Bp pairs
     __shared__ __align__(16) uint32_t s_stage[MULTI ? WT_WARPS : 1][MULTI ? EPT * 24 * WT_BATCH : 1];
     __shared__ uint8_t* s_extra[LUTGEN_MAX_PEERS];
+    __shared__ WtStripCfg s_strip[STRIPS ? 1 : 1];
     __shared__ __align__(16) double s_exact[WT_WARPS][128];   // wt_exact_entry's scratch
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1119,6 +1223,9 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
     if (tid == 0) {
 #pragma unroll
         for (int x = 0; x < LUTGEN_MAX_PEERS; ++x) s_extra[x] = a.f.extra[x];
+        if (STRIPS) {
+            s_strip[0] = {a.strip_counter, a.f.out, a.f.mc, a.f.mc ? 0 : a.f.nextra, a.f.cs, a.b_lo, a.tiles_g, a.deal, a.shard_count, a.shard_index};
+        }
     }
     stage_tables(st, a.tables);  // ends with __syncthreads()
     if (BRICK) {
@@ -1149,7 +1256,9 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
     // every ticket stands for a single tile (tile tail_cut + (ticket - tail_cut) / batch): the last couple of tiles per warp
     // are handed out one by one, so the warps finish within a tile of each other instead of within a hand-out (a warp
     // has only ~9 hand-outs of a level-16 CLUT: the uneven end was 5 % of the kernel).
+    if (a.stats && tid == 0) atomicMin(&a.stats[128], wt_clock_ns());
     uint32_t ticket = 0;
+    uint32_t pend_strip = 0, pend_n = 0;   // strip exchange: tiles whose stores are issued but not yet counted
     if (lane == 0) ticket = atomicAdd(a.tile_counter, a.batch);
     for (;;) {
         const uint32_t tk = __shfl_sync(FULL, ticket, 0);
@@ -1157,7 +1266,8 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
         if (lane == 0) ticket = atomicAdd(a.tile_counter, a.batch);
         uint32_t t0 = tk, nb = a.batch;
         if (tk >= a.tail_cut) { t0 = a.tail_cut + (tk - a.tail_cut) / a.batch; nb = 1u; }
-        if (a.shard_count > 1) t0 = ((t0 / a.batch) * a.shard_count + a.shard_index) * a.batch;
+        const uint32_t t_local = t0;
+        if (a.shard_count > 1) { const uint32_t u = t0 / a.deal; t0 = (u * a.shard_count + a.shard_index) * a.deal + (t0 - u * a.deal); }
         if (t0 >= a.ntiles_global) break;
         uint32_t ir = 0, ig = 0, ib = 0;
         if (BRICK) {
@@ -1283,6 +1393,12 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
                 atomicAdd(&a.stats[64 + min(cl.nin, 63u)], 1u);
             }
             // ---- 5. per entry ------------------------------------------------------------------
+            if (STRIPS && pend_n) {
+                // strip exchange: the previous hand-out's tiles are counted here, a classification after their stores were
+                // issued -- the fence the count needs finds nothing left to wait for
+                wt_strip_done<EPT>(s_strip, s_extra, pend_strip, pend_n);
+                pend_n = 0;
+            }
             if (MULTI && t == t0) { batch_flat0 = __shfl_sync(FULL, T.slot0, 0); batch_step = T.slot_step; }
 #pragma unroll 1
             for (int grp = 0; grp < GROUPS; ++grp) {
@@ -1302,7 +1418,11 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
                 wt_entries<KIND, MODE, EPT, MULTI, true>(a, st, T, cl, cand, cidx, hits, sg, s_exact[warp]);
             }
         }
-        if (MULTI && sg.staged) {
+        if (STRIPS) {
+            // strip exchange: these tiles are counted as finished later, when their stores have long landed (below)
+            pend_strip = t_local / a.deal;
+            pend_n = t1 - t0;
+        } else if (MULTI && sg.staged) {
             __syncwarp();
             if (sg.staged == (1u << WT_BATCH) - 1u) {
                 wt_flush_batch<EPT>(a.f.mc ? a.f.mc : a.f.out, a.f.mc != nullptr, sg.extras, a.f.mc ? 0 : a.f.nextra, cs, sg.buf, batch_flat0, batch_step);
@@ -1320,6 +1440,8 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
             }
         }
     }
+    if (STRIPS && pend_n) wt_strip_done<EPT>(s_strip, s_extra, pend_strip, pend_n);
+    if (a.stats && lane == 0) atomicMax(&a.stats[129], wt_clock_ns());   // out of tiles
     // The last WARP to finish leaves the two counters as every launch expects to find them (zero): no memset
     // between launches, and a captured graph can be replayed as it is. (Warps, not CTAs: no CTA barrier at the end.)
     //
@@ -1329,29 +1451,61 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
     // exchange and its barrier cost no launch of their own.
     __syncwarp();
     if (lane == 0) {
-        if (MULTI && a.f.bar_nranks > 1) __threadfence_system();   // this warp's stores (ordered before by the barrier above) before its count
+        if ((MULTI || STRIPS) && a.f.bar_nranks > 1) __threadfence_system();   // this warp's stores (ordered before by the barrier above) before its count
         else __threadfence();
+        if (a.stats) atomicMax(&a.stats[130], wt_clock_ns());   // this warp's stores have landed
         const uint32_t prev = atomicAdd(a.done_counter, 1u);
         if (prev == gridDim.x * (uint32_t)WT_WARPS - 1u) {
             __threadfence();
             *a.tile_counter = 0u;
             *a.done_counter = 0u;
-            if (MULTI && a.f.bar_nranks > 1) {
-                unsigned* mine = a.f.bar_flags[a.f.bar_rank];
-                const unsigned epoch = mine[LUTGEN_BAR_EPOCH] + 1u;
-                mine[LUTGEN_BAR_EPOCH] = epoch;
-                __threadfence_system();
-                for (int t = 0; t < a.f.bar_nranks; ++t) {
-                    unsigned* remote = a.f.bar_flags[t] + a.f.bar_rank;
-                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
-                }
-                for (int t = 0; t < a.f.bar_nranks; ++t) {
-                    unsigned v;
-                    do {
-                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + t) : "memory");
-                    } while ((int)(v - epoch) < 0);
-                }
+            if ((MULTI || STRIPS) && a.f.bar_nranks > 1) wt_peer_barrier(a.f.bar_flags, a.f.bar_nranks, a.f.bar_rank);
+            if (a.stats) a.stats[131] = wt_clock_ns();   // every rank's stores have landed
+        }
+    }
+}
+
+// The exchange without the arithmetic (tools/time_exchange.py): every warp sends strips (pattern 0) or hand-outs of
+// WT_BATCH tiles as 96-byte rows (pattern 1) of this GPU's share of a CLUT that is already in `own`, then the barrier.
+// What it takes is the floor of a fused step on N GPUs; the difference between the patterns is what the size of the
+// contiguous runs costs on the NVLink side.
+__global__ void __launch_bounds__(WT_THREADS) k_exchange_probe(Front f, uint32_t tiles_r, uint32_t tiles_g, int pattern, uint32_t* done_counter) {
+    __shared__ __align__(16) uint32_t s_stage[WT_WARPS][4 * 24 * WT_BATCH];
+    __shared__ uint8_t* s_extra[LUTGEN_MAX_PEERS];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, cs = f.cs;
+    if (threadIdx.x == 0)
+        for (int x = 0; x < LUTGEN_MAX_PEERS; ++x) s_extra[x] = f.extra[x];
+    __syncthreads();
+    const uint32_t gw = blockIdx.x * WT_WARPS + warp, nw = gridDim.x * WT_WARPS;
+    const uint32_t nstrips = tiles_g * (cs / 4u);
+    if (pattern == 0) {
+        for (uint32_t ls = gw; ls * f.shard_count + f.shard_index < nstrips; ls += nw) {
+            const uint32_t gs = ls * f.shard_count + f.shard_index, sb = gs / tiles_g;
+            wt_push_strip<4>(f.out, f.mc, s_extra, f.mc ? 0 : f.nextra, cs, sb * 4u, (gs - sb * tiles_g) * 4u);
+        }
+    } else {
+        const uint32_t per_row = tiles_r / WT_BATCH, nh = nstrips * per_row;
+        for (uint32_t lh = gw; lh * f.shard_count + f.shard_index < nh; lh += nw) {
+            const uint32_t gh = lh * f.shard_count + f.shard_index, gs = gh / per_row, ir = (gh - gs * per_row) * WT_BATCH, sb = gs / tiles_g;
+            const uint32_t flat0 = ((sb * 4u) * cs + (gs - sb * tiles_g) * 4u) * cs + ir * 8u;
+            __syncwarp();
+            // 16 rows of 96 bytes into the staging image (6 pieces per row)
+            for (uint32_t wi = lane; wi < 96u; wi += 32u) {
+                const uint32_t row = wi / 6u, q = wi - row * 6u;
+                reinterpret_cast<uint4*>(s_stage[warp])[wi] =
+                    __ldcg(reinterpret_cast<const uint4*>(f.out + 3ull * (flat0 + (row >> 2) * cs * cs + (row & 3u) * cs) + 16u * q));
             }
+            __syncwarp();
+            wt_flush_batch<4>(f.mc ? f.mc : f.out, f.mc != nullptr, s_extra, f.mc ? 0 : f.nextra, cs, s_stage[warp], flat0, cs * cs);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_system();
+        if (atomicAdd(done_counter, 1u) == nw - 1u) {
+            __threadfence();
+            *done_counter = 0u;
+            if (f.bar_nranks > 1) wt_peer_barrier(f.bar_flags, f.bar_nranks, f.bar_rank);
         }
     }
 }

@@ -118,6 +118,22 @@ class InterpolatedRemapper:
                                                                            _abort_ptr(abort)))
         return None if aborted else out
 
+    @staticmethod
+    def part_rows(level, part_index, part_count):
+        """The row ranges [(r0, r1), ...] of the (n, n, 3) image that generate_lut_part(level, out, part_index, part_count)
+        writes (without an abort flag): row groups of 16 * level rows dealt to the parts in turn. For callers that place
+        `out` themselves -- e.g. touch their own rows of a shared buffer first, so that those pages are allocated on
+        the memory node next to their GPU."""
+        level, part_index, part_count = int(level), int(part_index), int(part_count)
+        n = level ** 3
+        group = 16 * level
+        ngroups = (n + group - 1) // group
+        chunks = min(ngroups, part_count * (2 if ngroups >= 2 * part_count else 1))
+        rows = []
+        for c in range(part_index, chunks, part_count):
+            rows.append((min(n, ngroups * c // chunks * group), min(n, ngroups * (c + 1) // chunks * group)))
+        return rows
+
     def _generate(self, level, abort, out, sequential):
         """`out` (optional, not in the reference): a preallocated (n, n, 3) uint8 array to fill,
         e.g. page-locked memory so the device-to-host copy is a single DMA."""

@@ -74,3 +74,18 @@ def test_shard_helpers():
             assert all(r[1] - r[0] <= r[2] for r in rows)
     assert device.shard_frames(10, 4, 3) == (9, 10)
     assert device.shard_frames(2, 4, 3) == (2, 2)
+
+
+def test_part_rows_partition_the_image():
+    """InterpolatedRemapper.part_rows (what generate_lut_part writes per rank): disjoint, whole row groups of 16 * level
+    rows, covering every row once whatever the number of parts (more parts than row groups: the last ones get nothing)."""
+    from lutgen_rs_b200.interpolation import InterpolatedRemapper
+    for level in (2, 3, 8, 16, 33):
+        n, group = level ** 3, 16 * level
+        for parts in (1, 2, 3, 8, 64):
+            seen = np.zeros(n, int)
+            for p in range(parts):
+                for r0, r1 in InterpolatedRemapper.part_rows(level, p, parts):
+                    assert r0 % group == 0 and (r1 % group == 0 or r1 == n) and r0 < r1
+                    seen[r0:r1] += 1
+            assert (seen == 1).all(), (level, parts)

@@ -181,3 +181,27 @@ def test_baseline_config4_at_its_stated_size_sampled_against_the_oracle():
     want = o.remap_image(px)
     assert (want[:, 3] == 255).all()
     assert (got[idx] == want[:, :3]).all(), int((got[idx] != want[:, :3]).any(axis=1).sum())
+
+
+@pytest.mark.parametrize("level,parts", [(16, 8), (16, 3), (8, 2), (5, 4), (3, 8), (12, 1)])
+def test_parts_of_a_clut_tile_it_and_write_only_their_rows(palettes, level, parts):
+    """generate_lut_part (one process per GPU, CLUT wanted in one shared host image): every part writes exactly the
+    rows InterpolatedRemapper.part_rows names, nothing else, and all parts together give generate_lut's CLUT."""
+    pal = palettes["catppuccin_mocha"]
+    n = level ** 3
+    for r in (interpolation.GaussianRemapper(pal, 128.0, 16, 1.0, False), interpolation.GaussianBlurRemapper(pal, 4.0, 1.0, False)):
+        whole = r.generate_lut(level)
+        img = np.full((n, n, 3), 0xA5, np.uint8)
+        covered = np.zeros(n, bool)
+        for p in range(parts):
+            before = img.copy()
+            assert r.generate_lut_part(level, img, p, parts) is img
+            mine = np.zeros(n, bool)
+            for r0, r1 in interpolation.InterpolatedRemapper.part_rows(level, p, parts):
+                assert 0 <= r0 <= r1 <= n
+                assert not mine[r0:r1].any() and not covered[r0:r1].any()
+                mine[r0:r1] = True
+            covered |= mine
+            assert (img[mine] == whole[mine]).all()
+            assert (img[~mine] == before[~mine]).all()
+        assert covered.all() and (img == whole).all()

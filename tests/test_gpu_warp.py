@@ -178,3 +178,37 @@ def test_multi_destination_rows_write_every_copy(palettes):
             torch.cuda.synchronize()
             for c in copies:
                 assert torch.equal(c, ref)
+
+
+@pytest.mark.parametrize("form", [None, "1", "0"], ids=["library-choice", "strips", "staged"])
+def test_interleaved_shards_into_several_destinations(palettes, form, monkeypatch):
+    """The exchange kernel's two forms on ONE GPU (the peers' CLUTs are ordinary device pointers to it): shard i of c
+    into three destinations, strips sent whole by the warp that completes them (levels that are multiples of 4; from
+    four shards on when the library chooses) or tiles staged and stored by their own warp. The c launches together must
+    leave the one-GPU CLUT in every copy, and the per-strip counters must come back to zero (second round)."""
+    import ctypes as C
+
+    import torch
+    from lutgen_rs_b200 import _native, device
+    device.init(0)
+    if form is None:
+        monkeypatch.delenv("LUTGEN_CUDA_STRIPS", raising=False)
+    else:
+        monkeypatch.setenv("LUTGEN_CUDA_STRIPS", form)
+    pal = palettes["catppuccin_mocha"]
+    s = torch.cuda.current_stream().cuda_stream
+    for level in (16, 8, 4, 9):
+        side = level ** 3
+        for r in (interpolation.GaussianRemapper(pal, 128.0, 16, 1.0, False), interpolation.NearestNeighborRemapper(pal, 1.0, False)):
+            whole = torch.from_numpy(r.generate_lut(level)).cuda().reshape(-1)
+            for count in (2, 4, 7):
+                for _round in range(2):
+                    copies = [torch.full((3 * side * side,), 7, dtype=torch.uint8, device="cuda") for _ in range(3)]
+                    for idx in range(count):
+                        # each shard's own CLUT first, as a rank passes them: the copies take turns being "own"
+                        order = [copies[idx % 3]] + [c for j, c in enumerate(copies) if j != idx % 3]
+                        ptrs = (C.c_void_p * 3)(*[c.data_ptr() for c in order])
+                        _native.check(_native.lib().lutgen_cuda_generate_lut_shard_multi_dev(r._h, level, ptrs, 3, idx, count, s))
+                    torch.cuda.synchronize()
+                    for c in copies:
+                        assert torch.equal(c, whole), (level, count, int((c != whole).sum()))

@@ -41,13 +41,20 @@ def main():
             single = torch.empty(3 * side * side, dtype=torch.uint8, device="cuda")
             device.generate_lut_rows_(r, level, single, 0, side)
             ag = device.generate_lut(r, level).clone().reshape(-1)[: 3 * side * side]
-            for rep in range(3):   # both buffers of the pair, and the first again
-                fused = device.generate_lut_fused(r, level)
-                torch.cuda.synchronize()
-                nf, na = int((fused.reshape(-1) != single).sum()), int((ag != single).sum())
-                if nf or na:
-                    bad += 1
-                    print(f"rank {rank}: {name} level {level} rep {rep}: {nf} bytes differ (exchange kernel), {na} (all-gather)", flush=True)
+            # the exchange kernel's two forms (strips sent whole by the warp that completes them / tiles staged and sent
+            # by their own warp) and the library's own choice between them; LUTGEN_CUDA_STRIPS is read at every launch
+            for form in (None, "1", "0"):
+                os.environ.pop("LUTGEN_CUDA_STRIPS", None)
+                if form is not None:
+                    os.environ["LUTGEN_CUDA_STRIPS"] = form
+                for rep in range(3):   # both buffers of the pair, and the first again
+                    fused = device.generate_lut_fused(r, level)
+                    torch.cuda.synchronize()
+                    nf, na = int((fused.reshape(-1) != single).sum()), int((ag != single).sum())
+                    if nf or na:
+                        bad += 1
+                        print(f"rank {rank}: {name} level {level} strips={form} rep {rep}: {nf} bytes differ (exchange kernel), {na} (all-gather)", flush=True)
+            os.environ.pop("LUTGEN_CUDA_STRIPS", None)
     t = torch.tensor([bad], device="cuda")
     dist.all_reduce(t)
     if rank == 0 and int(t.item()) == 0:
