@@ -8,7 +8,8 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "liblutgen_cuda.so")
+# LUTGEN_CUDA_LIB: an experiment build to load instead (tools/build_variants.py); never set by the product or the tests
+SO_PATH = os.environ.get("LUTGEN_CUDA_LIB") or os.path.join(HERE, "liblutgen_cuda.so")
 
 OK, ABORTED = 0, 1
 ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED = -1, -2, -3, -4
@@ -74,7 +75,7 @@ def load():
             return _lib
         from . import build as _build
         try:
-            if _build.needs_build():
+            if not os.environ.get("LUTGEN_CUDA_LIB") and _build.needs_build():
                 _build.build()
         except Exception as e:  # no nvcc on this machine: use the prebuilt .so if any
             if not os.path.exists(SO_PATH):

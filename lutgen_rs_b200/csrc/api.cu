@@ -398,7 +398,9 @@ bool fast_path_supported(const lutgen_remapper* r) {
     if (getenv("LUTGEN_CUDA_EXACT_ONLY")) return false;
     double lum = r->d.lum_factor;
     // the f32 tile bounds assume Oklab-sized coordinates; anything exotic goes to the f64 kernel
-    if (!(lum >= 1e-3 && lum <= 1e3)) return false;
+    // and the error bounds of the fast conversion are absolute in (L * lum, a, b): the CTA-tile kernel's constants
+    // (FAST_TIE_TOL, its box padding) hold them up to lum = 16; the warp-tile kernels scale theirs with lum
+    if (!(lum >= 1e-3 && lum <= 16.0)) return false;
     bool nn = r->d.kind == LUTGEN_NEAREST || r->d.kind == LUTGEN_SAMPLING;
     uint32_t n = nn ? r->un : r->n;
     if (n == 0 || n > 2048) return false;
@@ -459,6 +461,10 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
     a.lum64 = r->d.lum_factor;
     a.param64 = r->d.param;
     a.rank_scale = (float)(32768.0 / (r->d.lum_factor * r->d.lum_factor + 1.0));   // squared Oklab distances stay below lum^2 + 1
+    {
+        const float es = (float)std::max(1.0, r->d.lum_factor);   // L, and the error of the fast conversion in it, are scaled by lum
+        a.tie_slope = WT_TIE_SLOPE * es; a.tie_const = WT_TIE_CONST * es; a.pad = WT_BOX_PAD * es;
+    }
     if (!BIG) {
         const uint32_t pair = g.counter_next.fetch_add(1, std::memory_order_relaxed) % kCounterPairs;
         a.tile_counter = g.counters + 2 * pair;
@@ -519,7 +525,7 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
         // warp) and lose 6 / 16 / 24 % on a half / quarter / eighth of it, where the last hand-out of a warp is a larger
         // part of its work. The staged exchange keeps them while a warp has three: its rows on NVLink are 24 bytes per tile.
         const uint32_t per_warp = (multi && !strips) ? 3u : 24u;
-        a.batch = share >= (uint32_t)g.sm_count * WT_WARPS * per_warp * WT_BATCH ? (uint32_t)WT_BATCH : 1u;
+        a.batch = share >= (uint32_t)g.sm_count * (BIG ? WT_WARPS : WL_WARPS) * per_warp * WT_BATCH ? (uint32_t)WT_BATCH : 1u;
         if (batch_env == 1 || batch_env == WT_BATCH) a.batch = (uint32_t)batch_env;
     }
     if (strips) {
@@ -553,21 +559,21 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
             if (multi) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp_big<KIND, MODE, EPT, MODE == FRONT_LUT>, WT_THREADS, 0));
             else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp_big<KIND, MODE, EPT, false>, WT_THREADS, 0));
         } else {
-            if (strips) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, MODE == FRONT_LUT ? 2 : 0, 1>, WT_THREADS, 0));
-            else if (multi) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, MODE == FRONT_LUT ? 1 : 0, 1>, WT_THREADS, 0));
-            else if (deep) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, 0, GROUPS_LEAN>, WT_THREADS, 0));
-            else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, 0, 1>, WT_THREADS, 0));
+            if (strips) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, MODE == FRONT_LUT ? 2 : 0, 1>, WL_THREADS, 0));
+            else if (multi) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, MODE == FRONT_LUT ? 1 : 0, 1>, WL_THREADS, 0));
+            else if (deep) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, 0, GROUPS_LEAN>, WL_THREADS, 0));
+            else CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_remap_warp<KIND, MODE, EPT, 0, 1>, WL_THREADS, 0));
         }
         per_sm[variant] = v < 1 ? 1 : v;
     }
     unsigned grid = (unsigned)per_sm[variant] * (unsigned)g.sm_count;
-    unsigned need = BIG ? a.ntiles : blocks_for(a.ntiles, WT_WARPS * a.batch);
+    unsigned need = BIG ? a.ntiles : blocks_for(a.ntiles, WL_WARPS * a.batch);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     a.tail_cut = a.ticket_end = a.ntiles;
     if (!BIG && a.batch > 1 && (a.shard_count == 1 || strips)) {
         // the last two tiles per resident warp go out one by one (k_remap_warp's ticket scheme)
-        const uint32_t singles = std::min(a.ntiles, grid * (uint32_t)WT_WARPS * 2u);
+        const uint32_t singles = std::min(a.ntiles, grid * (uint32_t)WL_WARPS * 2u);
         a.tail_cut = (a.ntiles - singles) / a.batch * a.batch;
         a.ticket_end = a.tail_cut + (a.ntiles - a.tail_cut) * a.batch;
     }
@@ -576,10 +582,10 @@ int launch_warp(const Front& f, const lutgen_remapper* r, cudaStream_t s, const 
         if (multi) k_remap_warp_big<KIND, MODE, EPT, MODE == FRONT_LUT><<<grid, WT_THREADS, 0, s>>>(a);
         else k_remap_warp_big<KIND, MODE, EPT, false><<<grid, WT_THREADS, 0, s>>>(a);
     } else {
-        if (strips) k_remap_warp<KIND, MODE, EPT, MODE == FRONT_LUT ? 2 : 0, 1><<<grid, WT_THREADS, 0, s>>>(a);
-        else if (multi) k_remap_warp<KIND, MODE, EPT, MODE == FRONT_LUT ? 1 : 0, 1><<<grid, WT_THREADS, 0, s>>>(a);
-        else if (deep) k_remap_warp<KIND, MODE, EPT, 0, GROUPS_LEAN><<<grid, WT_THREADS, 0, s>>>(a);
-        else k_remap_warp<KIND, MODE, EPT, 0, 1><<<grid, WT_THREADS, 0, s>>>(a);
+        if (strips) k_remap_warp<KIND, MODE, EPT, MODE == FRONT_LUT ? 2 : 0, 1><<<grid, WL_THREADS, 0, s>>>(a);
+        else if (multi) k_remap_warp<KIND, MODE, EPT, MODE == FRONT_LUT ? 1 : 0, 1><<<grid, WL_THREADS, 0, s>>>(a);
+        else if (deep) k_remap_warp<KIND, MODE, EPT, 0, GROUPS_LEAN><<<grid, WL_THREADS, 0, s>>>(a);
+        else k_remap_warp<KIND, MODE, EPT, 0, 1><<<grid, WL_THREADS, 0, s>>>(a);
     }
     LAUNCH_CHECK();
     return LUTGEN_OK;

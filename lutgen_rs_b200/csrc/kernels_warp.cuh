@@ -47,11 +47,36 @@ namespace lutgen {
 #endif
 constexpr int WT_THREADS = 256;
 constexpr int WT_WARPS = WT_THREADS / 32;
+// CTA size of k_remap_warp (warps run free of each other: any multiple of 32 works; k_remap_warp_big's CTA tile needs WT_THREADS)
+#ifndef WL_THREADS_N
+#define WL_THREADS_N 256
+#endif
+constexpr int WL_THREADS = WL_THREADS_N;
+constexpr int WL_WARPS = WL_THREADS / 32;
+#ifndef WT_DIRECT_UNROLL
+#define WT_DIRECT_UNROLL 4
+#endif
+constexpr int WT_DIRECT_UNROLL_N = WT_DIRECT_UNROLL;   // colours per trip of the accumulation loop
 constexpr int WT_BATCH = 4;          // warp tiles per hand-out
 constexpr int WT_MAX_N = 32;         // one palette colour per lane
 constexpr int WT_MAX_CS = 1089;      // level 33
-constexpr float WT_TIE_SLOPE = 2.24e-5f;   // sqrt(FAST_TIE_TOL): conversion error, scales with sqrt(d)
-constexpr float WT_TIE_CONST = 1.5e-6f;    // rounding of the expanded distance (|p|^2 - 2 p.c + |c|^2)
+// Near-tie tolerance of the warp-tile kernels (squared-distance units): gap <= WT_TIE_SLOPE sqrt(d) + WT_TIE_CONST sends the
+// decision to the reference's own arithmetic. Two scores are compared, and each is off by at most
+//   2 sqrt(d) E   conversion: E = |fast Oklab - the reference's f32 Oklab| as a vector. The domain is the 2^24 sRGB colours
+//                 and the kernels are deterministic, so E is MEASURED, not estimated: 5.87e-7 over the whole cube
+//                 (tools/measure_fast_oklab.py; tests/test_gpu_parity.py::test_fast_oklab_within_tile_padding holds it
+//                 below WT_OKLAB_ERR); the image front end sums the LMS terms in another order (+1 ulp of an LMS value,
+//                 <= 1e-7 after the cube root and the matrix), hence WT_OKLAB_ERR = 8e-7.
+//   2.5e-7 sqrt(d)  rounding of the list entry: p - m and |p - m|^2 are rounded once per component (2^-24 relative), and
+//                 |p - m| <= sqrt(d) + the tile's half diagonal
+// => 4 E + 5e-7 per sqrt(d), and 1e-7 for the fma chain of the score itself. (Round 1 assumed E = 3e-6 per component:
+// nine times the measured value, and seven times as many entries sent to wt_resolve_tie as necessary -- the resolver
+// was 6 % of the kernel's issue slots.) L is scaled by lum_factor before it enters a distance, and so is its error:
+// the host passes both constants multiplied by max(1, lum) (WarpArgs::tie_slope, tie_const, pad).
+constexpr float WT_OKLAB_ERR = 8e-7f;
+constexpr float WT_TIE_SLOPE = 4.0f * WT_OKLAB_ERR + 5e-7f;
+constexpr float WT_TIE_CONST = 1e-7f;
+constexpr float WT_BOX_PAD = 2e-5f;        // the tile's Oklab box is inflated by this much (times max(1, lum)): >> E and the rounding of the +2 trick
 
 struct WarpArgs {
     Front f;
@@ -63,6 +88,7 @@ struct WarpArgs {
     float lum, inv_lum;
     float c1;                 // weight slope (kernels_fast.cuh header)
     float rank_scale;         // squared distances times this fit fp16 with room to spare (k_remap_warp's rank counting)
+    float tie_slope, tie_const, pad;   // WT_TIE_SLOPE, WT_TIE_CONST, WT_BOX_PAD times max(1, lum)
     int whole_tiles;          // brick front ends: no tile of the launch is cut by the cube's edge or by the range
     uint32_t tiles_r, tiles_g;
     float inv_tiles_r, inv_tiles_g;
@@ -685,11 +711,10 @@ __device__ __forceinline__ void wt_minmax(const WtTile<EPT>& T, float (&mn)[3], 
     }
 }
 
-__device__ __forceinline__ void wt_box_reduce(const float (&mn)[3], const float (&mx)[3], float (&lo)[3], float (&hi)[3]) {
+__device__ __forceinline__ void wt_box_reduce(const float (&mn)[3], const float (&mx)[3], float (&lo)[3], float (&hi)[3], const float PAD) {
     constexpr uint32_t FULL = 0xffffffffu;
     // warp reduction on integer keys: a, b + 2 are positive floats (|a|, |b| < 0.5 inside the sRGB
     // gamut; the 1.2e-7 rounding disappears in PAD); L*lum can be large and goes through f2key
-    const float PAD = 2e-5f;
     lo[0] = key2f(__reduce_min_sync(FULL, f2key(mn[0]))) - PAD;
     hi[0] = key2f(__reduce_max_sync(FULL, f2key(mx[0]))) + PAD;
 #pragma unroll
@@ -700,10 +725,10 @@ __device__ __forceinline__ void wt_box_reduce(const float (&mn)[3], const float 
 }
 
 template <int EPT>
-__device__ __forceinline__ void wt_box(WtTile<EPT>& T) {
+__device__ __forceinline__ void wt_box(WtTile<EPT>& T, float pad) {
     float mn[3], mx[3];
     wt_minmax<EPT>(T, mn, mx, true);
-    wt_box_reduce(mn, mx, T.lo, T.hi);
+    wt_box_reduce(mn, mx, T.lo, T.hi, pad);
 }
 
 // What the list holds for palette colour p, relative to the tile centre m (header).
@@ -1011,8 +1036,7 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
         all_exact |= !(fabsf(c0) < 890.0f);
     }
     const uint32_t nhit = min(cl.nhit, (uint32_t)FAST_MAX_HITS);
-    float tol = WT_TIE_SLOPE * sqrt_approx(cl.ubmax_unc);
-    if (KIND == 0 || KIND == KIND_NN) tol += WT_TIE_CONST;
+    float tol = fmaf(a.tie_slope, sqrt_approx(cl.ubmax_unc), a.tie_const);
     if (KIND == 0) tol *= -c1;
 
     if (all_exact) {
@@ -1110,7 +1134,7 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
         const uint32_t bq0 = pr ? T.Bq[2] : T.Bq[0], bq1 = pr ? T.Bq[3] : T.Bq[1];
         const uint32_t vm = (T.valid_mask >> (2 * pr)) & 3u;
         f2 n0 = splat(0.f), n1 = n0, n2 = n0, den = n0;
-#pragma unroll 4
+#pragma unroll WT_DIRECT_UNROLL_N
         for (uint32_t j = 0; j < direct; ++j) {
             const float4 q = cand[j];
             const f2 w = wt_weight2<KIND>(wt_score2<KIND>(q, L, A, B), c1, c0);
@@ -1190,7 +1214,7 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
 // count per strip -- its hot loop is the one-destination kernel's (the staged variant's larger code misses the
 // instruction cache: 83-87 % hit rate against 99.5 %, measured).
 template <int KIND, int MODE, int EPT, int XCH, int GROUPS>
-__global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpArgs a) {
+__global__ void __launch_bounds__(WL_THREADS, WT_MINB) k_remap_warp(const WarpArgs a) {
     constexpr bool MULTI = XCH == 1, STRIPS = XCH == 2;
     static_assert(EPT == 4, "entries are processed in two pairs (wt_store_entries takes four results)");
     static_assert(GROUPS == 1 || (GROUPS == 2 && MODE != FRONT_IMAGE && !MULTI), "two groups: brick tiles of the lean kernel only");
@@ -1200,15 +1224,15 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
     __shared__ SmemTables st;
     __shared__ float s_lin[BRICK ? WT_MAX_CS : 1];
     __shared__ uint8_t s_chv[BRICK ? WT_MAX_CS + 3 : 4];
-    __shared__ __align__(16) float4 s_cand[WT_WARPS][WT_MAX_N];
-    __shared__ __align__(16) uint32_t s_rank[WT_WARPS][WT_MAX_N];   // (UB, LB) of the lane's colour as an fp16 pair
-    __shared__ uint32_t s_cidx[WT_WARPS][WT_MAX_N];
-    __shared__ uint32_t s_hit[WT_WARPS][FAST_MAX_HITS];
-    __shared__ f2 s_stash[GROUPS == 2 ? WT_WARPS : 1][6][GROUPS == 2 ? 32 : 1];   // the second group's Lp, Ap, Bp pairs
-    __shared__ __align__(16) uint32_t s_stage[MULTI ? WT_WARPS : 1][MULTI ? EPT * 24 * WT_BATCH : 1];
+    __shared__ __align__(16) float4 s_cand[WL_WARPS][WT_MAX_N];
+    __shared__ __align__(16) uint32_t s_rank[WL_WARPS][WT_MAX_N];   // (UB, LB) of the lane's colour as an fp16 pair
+    __shared__ uint32_t s_cidx[WL_WARPS][WT_MAX_N];
+    __shared__ uint32_t s_hit[WL_WARPS][FAST_MAX_HITS];
+    __shared__ f2 s_stash[GROUPS == 2 ? WL_WARPS : 1][6][GROUPS == 2 ? 32 : 1];   // the second group's Lp, Ap, Bp pairs
+    __shared__ __align__(16) uint32_t s_stage[MULTI ? WL_WARPS : 1][MULTI ? EPT * 24 * WT_BATCH : 1];
     __shared__ uint8_t* s_extra[LUTGEN_MAX_PEERS];
     __shared__ WtStripCfg s_strip[STRIPS ? 1 : 1];
-    __shared__ __align__(16) double s_exact[WT_WARPS][128];   // wt_exact_entry's scratch
+    __shared__ __align__(16) double s_exact[WL_WARPS][128];   // wt_exact_entry's scratch
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n = a.n, k = a.k;
@@ -1218,7 +1242,7 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
 
     if (BRICK) {
 #pragma unroll 1
-        for (uint32_t v = tid; v < cs; v += WT_THREADS) s_chv[v] = (uint8_t)(MODE == FRONT_TABLE ? v : hald_channel(v, csm1));
+        for (uint32_t v = tid; v < cs; v += WL_THREADS) s_chv[v] = (uint8_t)(MODE == FRONT_TABLE ? v : hald_channel(v, csm1));
     }
     if (tid == 0) {
 #pragma unroll
@@ -1230,7 +1254,7 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
     stage_tables(st, a.tables);  // ends with __syncthreads()
     if (BRICK) {
 #pragma unroll 1
-        for (uint32_t v = tid; v < cs; v += WT_THREADS) s_lin[v] = st.decode[s_chv[v]];
+        for (uint32_t v = tid; v < cs; v += WL_THREADS) s_lin[v] = st.decode[s_chv[v]];
         __syncthreads();
     }
     WtShared sh;
@@ -1313,11 +1337,11 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
                 wt_minmax<EPT>(T, mn, mx, GROUPS == 1);
                 if (GROUPS == 2) T.bhi[2] = s_chv[min(b0 + TD - 1, csm1)];
                 if (!__any_sync(FULL, (T.valid_mask | valid1) != 0)) continue;
-                wt_box_reduce(mn, mx, T.lo, T.hi);
+                wt_box_reduce(mn, mx, T.lo, T.hi, a.pad);
             } else {
                 wt_convert_image<EPT>(a, sh, lane, t * (32u * EPT), T);
                 if (!__any_sync(FULL, T.valid_mask != 0)) continue;
-                wt_box<EPT>(T);
+                wt_box<EPT>(T, a.pad);
             }
             wt_centre<EPT>(T);
 
@@ -1455,7 +1479,7 @@ __global__ void __launch_bounds__(WT_THREADS, WT_MINB) k_remap_warp(const WarpAr
         else __threadfence();
         if (a.stats) atomicMax(&a.stats[130], wt_clock_ns());   // this warp's stores have landed
         const uint32_t prev = atomicAdd(a.done_counter, 1u);
-        if (prev == gridDim.x * (uint32_t)WT_WARPS - 1u) {
+        if (prev == gridDim.x * (uint32_t)WL_WARPS - 1u) {
             __threadfence();
             *a.tile_counter = 0u;
             *a.done_counter = 0u;
@@ -1617,7 +1641,7 @@ __global__ void __launch_bounds__(WT_THREADS, WB_MINB) k_remap_warp_big(const Wa
             wt_convert_image<EPT>(a, sh, lane, base, T);
             if (ct * (256u * EPT) + warp * (32u * EPT) >= end) T.valid_mask = 0;
         }
-        wt_box<EPT>(T);
+        wt_box<EPT>(T, a.pad);
         wt_centre<EPT>(T);
         if (lane < 6) {
             s_wbox[warp][lane] = lane < 3 ? T.lo[lane] : T.hi[lane - 3];

@@ -318,7 +318,9 @@ def _exact_only(monkeypatch, on):
 
 
 def test_fast_oklab_within_tile_padding():
-    """The tile bounds are padded by 2e-5; the fast f32 conversion must stay well inside that."""
+    """The near-tie tolerance of the warp-tile kernels is built on a MEASURED bound: the fast f32 conversion stays within
+    WT_OKLAB_ERR = 8e-7 (as a vector) of the reference's f32 Oklab over all 2^24 colours -- the whole domain, so the
+    maximum is a bound (kernels_warp.cuh; measured 5.87e-7, tools/measure_fast_oklab.py). The tile boxes are padded by 2e-5."""
     import ctypes as C
     from lutgen_rs_b200 import _native
     L = _native.lib()
@@ -331,8 +333,9 @@ def test_fast_oklab_within_tile_padding():
         exact = np.empty((step, 3), np.float32)
         _native.check(L.lutgen_cuda_srgb_to_oklab_fast(C.c_void_p(rgb.ctypes.data), step, C.c_void_p(fast.ctypes.data)))
         _native.check(L.lutgen_cuda_srgb_to_oklab(C.c_void_p(rgb.ctypes.data), step, C.c_void_p(exact.ctypes.data)))
-        worst = max(worst, float(np.abs(fast.astype(np.float64) - exact.astype(np.float64)).max()))
-    assert worst < 3e-6, worst
+        d = fast.astype(np.float64) - exact.astype(np.float64)
+        worst = max(worst, float(np.sqrt((d * d).sum(1)).max()))
+    assert worst < 7e-7, worst   # WT_OKLAB_ERR less the 1e-7 allowed for the image front end's summation order
 
 
 @pytest.mark.parametrize("lum,preserve", [(1.0, False), (0.7, True)])
