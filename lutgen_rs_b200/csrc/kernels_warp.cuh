@@ -40,16 +40,18 @@
 
 namespace lutgen {
 
-// Two CTAs of 256 threads per SM (128 registers per thread, no spills) measured 5 % faster than three (80 registers):
-// the kernel is bound by instruction delivery and issue, not by latency that more resident warps would hide.
+// Resident warps. The lean kernel is bound by instruction delivery and issue, not by latency that more resident warps
+// would hide: 2 x 256 threads (128 registers), 2 x 320 (96), 3 x 192 (96) and 4 x 128 (128) per SM all land within 2 % of
+// each other on the headline CLUT (tools/time_variants.py, round 2); 2 x 384 (80 registers) is 7 % slower. Three CTAs of
+// 192 threads are the default: level with the best on the RBF kinds, 4 % ahead on NearestNeighbor.
 #ifndef WT_MINB
-#define WT_MINB 2
+#define WT_MINB 3
 #endif
 constexpr int WT_THREADS = 256;
 constexpr int WT_WARPS = WT_THREADS / 32;
 // CTA size of k_remap_warp (warps run free of each other: any multiple of 32 works; k_remap_warp_big's CTA tile needs WT_THREADS)
 #ifndef WL_THREADS_N
-#define WL_THREADS_N 256
+#define WL_THREADS_N 192
 #endif
 constexpr int WL_THREADS = WL_THREADS_N;
 constexpr int WL_WARPS = WL_THREADS / 32;

@@ -278,7 +278,6 @@ struct Shared {
         uint32_t hist[NSYM];     // symbol frequencies, until the code lengths are known
         uint32_t codelen[NSYM];  // then: canonical code, bit reversed (ready for the LSB-first stream) | length << 16 | header position << 20
     };
-    uint32_t next_code[MAX_BITS + 1];  // first canonical code of each length
     uint8_t len[NSYM];
     unsigned long long eq[THREADS];  // bit k: stream byte lo+k equals the byte bpp before it
     unsigned long long ev[THREADS];  // bit k: a token starts at stream byte lo+k
@@ -299,9 +298,11 @@ struct Scratch {
     uint16_t node_parent[2 * NSYM];
     uint16_t used[NSYM];            // used symbols, any order
     uint16_t order[NSYM];           // used symbols by ascending (frequency, symbol)
+    uint32_t next_code[MAX_BITS + 1];  // first canonical code of each length (read by assign_codes, before the buffer is cleared)
 };
 static_assert(sizeof(uint32_t) * HIST_REPLICAS * HIST_PITCH + sizeof(Scratch) <= OUT_BYTES, "histogram copies + scratch must fit in the output buffer");
-static_assert(sizeof(Shared) <= 45670, "keep the shared state near the five-CTAs-per-SM size");
+// five CTAs per SM: 5 x (round_up(sizeof(Shared), 128) + 1024 reserved per CTA) <= 228 KB  <=>  sizeof(Shared) <= 45568
+static_assert(sizeof(Shared) <= 45568, "keep the shared state at the five-CTAs-per-SM size");
 
 LPNG_HD Scratch& scratch(Shared& S) { return *reinterpret_cast<Scratch*>(S.out + HIST_REPLICAS * HIST_PITCH); }
 
@@ -594,10 +595,10 @@ LPNG_HDN void build_code(Shared& S) {
         for (uint32_t c = 0; c < cnt[l]; ++c) S.len[X.order[i--]] = (uint8_t)l;
     uint32_t code = 0;
     cnt[0] = 0;
-    S.next_code[0] = 0;
+    X.next_code[0] = 0;
     for (int l = 1; l <= MAX_BITS; ++l) {
         code = (code + cnt[l - 1]) << 1;
-        S.next_code[l] = code;
+        X.next_code[l] = code;
     }
 }
 
@@ -622,7 +623,7 @@ LPNG_HD void assign_codes(Shared& S, int t) {
         }
         // where the symbol's code length goes in the block header: one bit per unused symbol before it, five per used one
         const uint32_t hpos = HEADER_FIXED_BITS + (uint32_t)s + 4u * below;
-        S.codelen[s] = bit_reverse(S.next_code[l] + before, l) | ((uint32_t)l << 16) | (hpos << 20);
+        S.codelen[s] = bit_reverse(X.next_code[l] + before, l) | ((uint32_t)l << 16) | (hpos << 20);
     }
 }
 
