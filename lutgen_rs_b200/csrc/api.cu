@@ -824,7 +824,7 @@ int ensure_blur_volume(const lutgen_remapper* r, uint32_t level, int sequential,
             // side, each; zero-padded weights behind them
             const size_t tile = (size_t)((P.size + 3u) / 4u * 4u + 2u * (uint32_t)(klen / 2) + 3u) * P.pitch;
             size_t smem = (2 * tile + (size_t)((klen + 6) / 4 * 4 + 4)) * sizeof(float);
-            if (smem > 227 * 1024) return fail(LUTGEN_ERR_UNSUPPORTED, "blur: %zu bytes of shared memory per tile (level %u, radius %g)", smem, level, r->d.param);
+            if (smem > (size_t)BLUR_MAX_DYN_SMEM) return fail(LUTGEN_ERR_UNSUPPORTED, "blur: %zu bytes of shared memory per tile (level %u, radius %g)", smem, level, r->d.param);
             const uint32_t ntiles = P.groups * outers;
             unsigned per_sm = (unsigned)((227 * 1024) / (smem + 1024));
             if (per_sm > 8) per_sm = 8;

@@ -1,4 +1,6 @@
 // blur.cu -- GaussianBlurRemapper kernels, compiled with --fmad=false (see blur_launch.h).
+#include <cstdlib>
+
 #include "blur_launch.h"
 #include "kernels_blur.cuh"
 
@@ -7,7 +9,13 @@ namespace lutgen {
 cudaError_t blur_set_attributes() {
     cudaError_t e = cudaFuncSetAttribute(k_blur_nn_volume, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_blur_axis, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    e = cudaFuncSetAttribute(k_blur_axis<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLUR_MAX_DYN_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_blur_axis<BLUR_PITCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLUR_MAX_DYN_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_blur_axis<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLUR_MAX_DYN_SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_blur_axis<BLUR_PITCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLUR_MAX_DYN_SMEM);
 }
 
 void blur_launch_palette(unsigned grid, cudaStream_t s, const uint8_t* pal_rgb4, uint32_t n, float lum, const float* decode, float* pal3, float* out3) {
@@ -21,9 +29,20 @@ void blur_launch_nn_volume(unsigned grid, size_t smem, cudaStream_t s, float* co
                                                              end_prev, end_cur, changed);
 }
 
-void blur_launch_axis(unsigned grid, size_t smem, cudaStream_t s, const float* src, float* dst, const BlurAxis& P, uint32_t ntiles, const float* kernel,
+void blur_launch_axis(unsigned grid, size_t smem, cudaStream_t s, const float* src, float* dst, const BlurAxis& P_in, uint32_t ntiles, const float* kernel,
                       int klen) {
-    k_blur_axis<<<grid, 256, smem, s>>>(src, dst, P, ntiles, kernel, klen, 1.0f);
+    BlurAxis P = P_in;
+    // bulk staging: rows of contiguous columns, every row start and length a multiple of 16 bytes on both sides
+    // (the tile rows are: pitch * 4 and half * pitch * 4 are multiples of 16 when pitch is a multiple of 4)
+    P.bulk = P.cpl == 0 && (P.cols & 3u) == 0 && (P.total_cols & 3u) == 0 && (P.pstride & 3u) == 0 && (P.outer_stride & 3u) == 0 && (P.pitch & 3u) == 0 &&
+             (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && !getenv("LUTGEN_CUDA_BLUR_NO_BULK");
+    if (P.pitch == BLUR_PITCH) {
+        if (P.bulk) k_blur_axis<BLUR_PITCH, true><<<grid, 256, smem, s>>>(src, dst, P, ntiles, kernel, klen, 1.0f);
+        else k_blur_axis<BLUR_PITCH, false><<<grid, 256, smem, s>>>(src, dst, P, ntiles, kernel, klen, 1.0f);
+    } else {
+        if (P.bulk) k_blur_axis<0, true><<<grid, 256, smem, s>>>(src, dst, P, ntiles, kernel, klen, 1.0f);
+        else k_blur_axis<0, false><<<grid, 256, smem, s>>>(src, dst, P, ntiles, kernel, klen, 1.0f);
+    }
 }
 
 void blur_launch_to_lut(unsigned grid, cudaStream_t s, const float* colors, uint32_t size, uint32_t ch, const uint8_t* chan, uint8_t* out_rgb,

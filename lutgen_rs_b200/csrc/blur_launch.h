@@ -14,10 +14,12 @@ struct ColorTables;
 
 constexpr int BLUR_ROW_WARPS = 8;
 constexpr int BLUR_TR = 32, BLUR_TB = 8;
+constexpr int BLUR_MAX_DYN_SMEM = 226 * 1024;   // k_blur_axis: dynamic shared memory (the tiles) next to 16 bytes of static (the mbarriers)
 
 // One blur pass along one axis of the [r][g][b][ch] volume (see k_blur_axis).
 struct BlurAxis {
     uint32_t size, pstride, cols, pitch, cpl, run_stride, total_cols, groups, outer_stride;
+    uint32_t bulk;   // every tile row is a 16-byte aligned run of floats on both sides: staged by cp.async.bulk (blur_launch_axis decides)
 };
 
 cudaError_t blur_set_attributes();

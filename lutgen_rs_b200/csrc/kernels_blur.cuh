@@ -212,27 +212,43 @@ __global__ void __launch_bounds__(BLUR_ROW_WARPS * 32) k_blur_nn_volume(float* _
 // finite (a volume is either finite or NaN throughout: its cells are palette colours or blurs of
 // them), s never is -0.0 (it starts at +0.0), and a NaN sum stays NaN.
 constexpr int BLUR_R = 4;
+constexpr uint32_t BLUR_PITCH = 20;   // the usual tile pitch (16 or 18 columns): a compile-time constant for the tap loop's addresses
 
-__device__ __forceinline__ void blur_taps4x2(const float* __restrict__ row0, uint32_t pitch, const float* __restrict__ kwz, int steps, float one,
+// PITCH > 0: the tile pitch is known at compile time, so the four input rows of a trip are immediate offsets from ONE
+// running address (the IMADs that computed them from a run-time pitch shared the FMA pipe with the packed arithmetic,
+// where an IMAD between FFMA2s costs as much as an FFMA2: tools/microbench_fp32.cu). The weights arrive as one 16-byte
+// load per trip; with the trip unrolled twice their four live registers rotate by renaming instead of by moves.
+template <uint32_t PITCH>
+__device__ __forceinline__ void blur_taps4x2(const float* __restrict__ row0, uint32_t pitch_rt, const float* __restrict__ kwz, int steps, float one,
                                              float2 (&out)[BLUR_R]) {
     // row0: the input row of step 0 (position p0 - half); kwz[j] = kw[j] for 0 <= j < klen, else 0 (j < steps + 4)
     float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
     // weights live in four registers named by j mod 4 (ra = kw[j] for j = 0 mod 4, ...): no shifting
     float ra, rb = 0.0f, rc = 0.0f, rd = 0.0f;
-#define BLUR_ACC(S, W, V) S = blur_add2(S, __fmul2_rn(make_float2(W, W), V), one)
+    // One step = four rounded products, then four rounded adds: written products first so that an add does not wait on
+    // the multiply issued just before it (ptxas otherwise pairs them back to back through one temporary to save registers,
+    // and the dependent FFMA2 sits out the FMUL2's latency: 'wait' was 21 % of the stall samples).
+#define BLUR_STEP(V, W0, W1, W2, W3)                                                                            \
+    {                                                                                                           \
+        const float2 p0 = __fmul2_rn(make_float2(W0, W0), V), p1 = __fmul2_rn(make_float2(W1, W1), V);         \
+        const float2 p2 = __fmul2_rn(make_float2(W2, W2), V), p3 = __fmul2_rn(make_float2(W3, W3), V);         \
+        s0 = blur_add2(s0, p0, one); s1 = blur_add2(s1, p1, one); s2 = blur_add2(s2, p2, one); s3 = blur_add2(s3, p3, one); \
+    }
+    const uint32_t pitch = PITCH ? PITCH : pitch_rt;
     const float* q = row0;
-    const float* kq = kwz;
+    const float4* kq = reinterpret_cast<const float4*>(kwz);   // 16-byte aligned: the tiles in front of it are multiples of 16 bytes
     const uint32_t p4 = 4u * pitch;
-#pragma unroll 1
-    for (int j = 0; j < steps; j += 4, q += p4, kq += 4) {
+#pragma unroll 2
+    for (int j = 0; j < steps; j += 4, q += p4, ++kq) {
         const float2 v0 = *reinterpret_cast<const float2*>(q), v1 = *reinterpret_cast<const float2*>(q + pitch);
         const float2 v2 = *reinterpret_cast<const float2*>(q + 2u * pitch), v3 = *reinterpret_cast<const float2*>(q + 3u * pitch);
-        ra = kq[0]; BLUR_ACC(s0, ra, v0); BLUR_ACC(s1, rd, v0); BLUR_ACC(s2, rc, v0); BLUR_ACC(s3, rb, v0);
-        rb = kq[1]; BLUR_ACC(s0, rb, v1); BLUR_ACC(s1, ra, v1); BLUR_ACC(s2, rd, v1); BLUR_ACC(s3, rc, v1);
-        rc = kq[2]; BLUR_ACC(s0, rc, v2); BLUR_ACC(s1, rb, v2); BLUR_ACC(s2, ra, v2); BLUR_ACC(s3, rd, v2);
-        rd = kq[3]; BLUR_ACC(s0, rd, v3); BLUR_ACC(s1, rc, v3); BLUR_ACC(s2, rb, v3); BLUR_ACC(s3, ra, v3);
+        const float4 w = *kq;
+        ra = w.x; BLUR_STEP(v0, ra, rd, rc, rb);
+        rb = w.y; BLUR_STEP(v1, rb, ra, rd, rc);
+        rc = w.z; BLUR_STEP(v2, rc, rb, ra, rd);
+        rd = w.w; BLUR_STEP(v3, rd, rc, rb, ra);
     }
-#undef BLUR_ACC
+#undef BLUR_STEP
     out[0] = s0; out[1] = s1; out[2] = s2; out[3] = s3;
 }
 
@@ -252,12 +268,59 @@ __device__ __forceinline__ void blur_cp_async4(float* smem_dst, const float* gme
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 
-// Asynchronous staging of one tile's `size` positions (rows half .. half + size of `tile`).
-__device__ __forceinline__ void blur_stage_async(const float* __restrict__ src, float* __restrict__ s_body, const BlurAxis& P, uint32_t t) {
+// ---- bulk-copy staging (the R and G passes: every tile row is one run of `cols` contiguous floats) ------------------
+// One cp.async.bulk per tile row -- the copy engine moves the 64 bytes and signals an mbarrier -- instead of sixteen
+// 4-byte cp.async with their address arithmetic (12 instructions each: 9 % of the kernel's instructions, and IMADs the
+// tap loop's FMA pipe pays for). Needs 16-byte aligned rows on both sides: cols, total_cols, pstride, outer_stride
+// multiples of 4 floats and a 16-byte aligned volume (BlurAxis::bulk, decided on the host).
+__device__ __forceinline__ uint32_t blur_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void blur_mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(blur_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void blur_mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(blur_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void blur_mbar_wait(unsigned long long* bar, uint32_t parity) {
+    const uint32_t a = blur_smem_u32(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void blur_bulk_row(float* smem_dst, const float* gmem_src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(blur_smem_u32(smem_dst)), "l"(gmem_src),
+                 "r"(bytes), "r"(blur_smem_u32(bar)) : "memory");
+}
+
+// Where tile t starts in the volume, and how many of its columns exist.
+__device__ __forceinline__ size_t blur_tile_base(const BlurAxis& P, uint32_t t, uint32_t& ncols) {
     const uint32_t outer = t / P.groups, grp = t % P.groups;
-    const uint32_t col0 = grp * P.cols, ncols = min(P.cols, P.total_cols - col0);
+    const uint32_t col0 = grp * P.cols;
+    ncols = min(P.cols, P.total_cols - col0);
     const uint32_t cpl = P.cpl ? P.cpl : P.total_cols;
-    const size_t base = (size_t)outer * P.outer_stride + (size_t)(col0 / cpl) * P.run_stride + (col0 % cpl);
+    return (size_t)outer * P.outer_stride + (size_t)(col0 / cpl) * P.run_stride + (col0 % cpl);
+}
+
+// Asynchronous staging of one tile's `size` positions (rows half .. half + size of `tile`).
+template <bool BULK>
+__device__ __forceinline__ void blur_stage_async(const float* __restrict__ src, float* __restrict__ s_body, const BlurAxis& P, uint32_t t,
+                                                 unsigned long long* bar) {
+    uint32_t ncols;
+    const size_t base = blur_tile_base(P, t, ncols);
+    if (BULK) {
+        // the barrier's phase ends when its one arrival (below) has happened and every row's bytes have landed
+        if (threadIdx.x == 0) blur_mbar_expect_tx(bar, P.size * ncols * (uint32_t)sizeof(float));
+        // one row per thread and trip (the compiler serialises a warp's 32 copies through an elect loop: UBLKCP takes its
+        // addresses from uniform registers; issuing them from one lane per warp in a uniform loop was measured slower)
+        const float* q = src + base;
+        const uint32_t bytes = ncols * (uint32_t)sizeof(float);
+        for (uint32_t p = threadIdx.x; p < P.size; p += blockDim.x) blur_bulk_row(s_body + p * P.pitch, q + (size_t)p * P.pstride, bytes, bar);
+        return;
+    }
     if (P.cpl == 0) {
         // the columns are contiguous floats: thread = (row of the wave, column), waves of 256 / cols rows
         const uint32_t c = threadIdx.x % P.cols, prow = threadIdx.x / P.cols, pstep = blockDim.x / P.cols;
@@ -281,68 +344,104 @@ __device__ __forceinline__ void blur_stage_async(const float* __restrict__ src, 
 }
 
 // Persistent CTAs walk tiles blockIdx.x, blockIdx.x + gridDim.x, ...; two tile buffers: while one is
-// blurred the next tile's rows arrive through cp.async (the staging loads were 43 % of the stall
-// samples of the single-buffer version).
-__global__ void __launch_bounds__(256) k_blur_axis(const float* __restrict__ src, float* __restrict__ dst, const BlurAxis P, uint32_t ntiles,
+// blurred the next tile's rows arrive asynchronously (the staging loads were 43 % of the stall
+// samples of the single-buffer version) -- by cp.async.bulk rows signalling an mbarrier per buffer (BULK), or by
+// 4-byte cp.async groups where rows are not 16-byte aligned runs (the B pass, odd sizes).
+template <uint32_t PITCH, bool BULK>
+__global__ void __launch_bounds__(256, 4) k_blur_axis(const float* __restrict__ src, float* __restrict__ dst, const BlurAxis P, uint32_t ntiles,
                                                     const float* __restrict__ kernel, int klen, float one) {
     extern __shared__ __align__(16) float s_blur[];
+    __shared__ __align__(8) unsigned long long s_bar[2];
     const int half = klen / 2;
     const uint32_t trows = blur_tile_rows(P.size, klen);
     const size_t tile_floats = (size_t)trows * P.pitch;
     float* s_kwz = s_blur + 2 * tile_floats;                   // zero-padded weights behind the two tiles
     for (uint32_t i = threadIdx.x; i < blur_kwz_len(klen); i += blockDim.x) s_kwz[i] = (int)i < klen ? kernel[i] : 0.0f;
+    if (BULK) {
+        if (threadIdx.x == 0) {
+            blur_mbar_init(&s_bar[0], 1);
+            blur_mbar_init(&s_bar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
     const int steps = klen ? (klen + BLUR_R - 1 + 3) / 4 * 4 : 0;   // klen + 3 steps, in fours; no taps: the sums stay 0.0
-    uint32_t t = blockIdx.x, buf = 0;
-    if (t < ntiles) blur_stage_async(src, s_blur + (size_t)half * P.pitch, P, t);
-    for (; t < ntiles; t += gridDim.x, buf ^= 1u) {
+    // the thread's place in a full tile (all but a slab's last group): worked out once, not per tile
+    const uint32_t full_pairs = (P.cols + 1) / 2, full_pair = threadIdx.x % full_pairs, full_pb0 = threadIdx.x / full_pairs, full_pbstep = blockDim.x / full_pairs;
+    const uint32_t pad_w = (P.cols + 1u) & ~1u, pad_c = threadIdx.x % pad_w, pad_k = threadIdx.x / pad_w, pad_kstep = blockDim.x / pad_w;
+    uint32_t t = blockIdx.x, buf = 0, it = 0;
+    if (t < ntiles) blur_stage_async<BULK>(src, s_blur + (size_t)half * P.pitch, P, t, &s_bar[0]);
+    for (; t < ntiles; t += gridDim.x, buf ^= 1u, ++it) {
         float* s_tile = s_blur + buf * tile_floats;
         float* s_body = s_tile + (size_t)half * P.pitch;        // row of position 0
         const uint32_t tn = t + gridDim.x;
-        if (tn < ntiles) {
-            blur_stage_async(src, s_blur + (buf ^ 1u) * tile_floats + (size_t)half * P.pitch, P, tn);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        if (BULK) {
+            // the other buffer was last read before the barrier that ended the previous trip
+            if (tn < ntiles) blur_stage_async<BULK>(src, s_blur + (buf ^ 1u) * tile_floats + (size_t)half * P.pitch, P, tn, &s_bar[buf ^ 1u]);
+            blur_mbar_wait(&s_bar[buf], (it >> 1) & 1u);        // this buffer's (it / 2)-th use
         } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (tn < ntiles) {
+                blur_stage_async<BULK>(src, s_blur + (buf ^ 1u) * tile_floats + (size_t)half * P.pitch, P, tn, nullptr);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        const uint32_t outer = t / P.groups, grp = t % P.groups;
-        const uint32_t col0 = grp * P.cols, ncols = min(P.cols, P.total_cols - col0);
-        const uint32_t cpl = P.cpl ? P.cpl : P.total_cols;
-        const size_t base = (size_t)outer * P.outer_stride + (size_t)(col0 / cpl) * P.run_stride + (col0 % cpl);
+        uint32_t ncols;
+        const size_t base = blur_tile_base(P, t, ncols);
         {
             // the clamp of the reference, once: rows before position 0 repeat it, rows after size-1 repeat that
             const uint32_t npad = trows - P.size, wcols = (ncols + 1u) & ~1u;
-            for (uint32_t i = threadIdx.x; i < npad * wcols; i += blockDim.x) {
-                const uint32_t k = i / wcols, c = i - k * wcols;
-                const bool lo = k < (uint32_t)half;
-                const uint32_t row = lo ? k : P.size + k;                       // in tile rows: [0, half) and [half + size, trows)
-                s_tile[row * P.pitch + c] = lo ? s_body[c] : s_body[(P.size - 1) * P.pitch + c];
+            const uint32_t c = ncols == P.cols ? pad_c : threadIdx.x % wcols, k0 = ncols == P.cols ? pad_k : threadIdx.x / wcols;
+            const uint32_t kstep = ncols == P.cols ? pad_kstep : blockDim.x / wcols;
+            if (k0 < kstep) {
+                const float first = s_body[c], last = s_body[(P.size - 1) * P.pitch + c];
+                for (uint32_t k = k0; k < npad; k += kstep) {
+                    const bool lo = k < (uint32_t)half;
+                    s_tile[(lo ? k : P.size + k) * P.pitch + c] = lo ? first : last;   // tile rows [0, half) and [half + size, trows)
+                }
             }
         }
         __syncthreads();
-        const uint32_t pblocks = (P.size + BLUR_R - 1) / BLUR_R, npairs = (ncols + 1) / 2;
-        const uint32_t pair = threadIdx.x % npairs, pb0 = threadIdx.x / npairs, pbstep = blockDim.x / npairs;
+        const uint32_t pblocks = (P.size + BLUR_R - 1) / BLUR_R;
+        uint32_t pair = full_pair, pb0 = full_pb0, pbstep = full_pbstep;
+        if (ncols != P.cols) {   // the last group of a slab may be narrower
+            const uint32_t npairs = (ncols + 1) / 2;
+            pair = threadIdx.x % npairs; pb0 = threadIdx.x / npairs; pbstep = blockDim.x / npairs;
+        }
         if (pb0 < pbstep) {  // blockDim.x is not a multiple of npairs: the remainder threads idle
             const uint32_t c = 2 * pair;
-            const uint32_t rcols = P.cpl ? P.cpl : ncols;
-            const size_t offA = base + (size_t)(c / rcols) * P.run_stride + (c % rcols);
-            const size_t offB = base + (size_t)((c + 1) / rcols) * P.run_stride + ((c + 1) % rcols);
+            size_t offA, offB;
+            if (P.cpl == 0) {   // contiguous columns
+                offA = base + c; offB = offA + 1;
+            } else {
+                offA = base + (size_t)(c / P.cpl) * P.run_stride + (c % P.cpl);
+                offB = base + (size_t)((c + 1) / P.cpl) * P.run_stride + ((c + 1) % P.cpl);
+            }
             const bool hasB = c + 1 < ncols;
+            // the pair's two columns are neighbours in the volume and 8-byte aligned: one store per position
+            const bool pair_store = hasB && offB == offA + 1 && ((offA | P.pstride) & 1u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0;
             for (uint32_t pb = pb0; pb < pblocks; pb += pbstep) {
                 float2 o[BLUR_R];
                 // step 0 reads position pb*4 - half = tile row pb*4
-                blur_taps4x2(s_tile + (size_t)(pb * BLUR_R) * P.pitch + c, P.pitch, s_kwz, steps, one, o);
+                blur_taps4x2<PITCH>(s_tile + (size_t)(pb * BLUR_R) * P.pitch + c, P.pitch, s_kwz, steps, one, o);
+                float* d = dst + offA + (size_t)(pb * BLUR_R) * P.pstride;
 #pragma unroll
-                for (int q = 0; q < BLUR_R; ++q) {
+                for (int q = 0; q < BLUR_R; ++q, d += P.pstride) {
                     const uint32_t pq = pb * BLUR_R + q;
                     if (pq < P.size) {
-                        dst[offA + (size_t)pq * P.pstride] = o[q].x;
-                        if (hasB) dst[offB + (size_t)pq * P.pstride] = o[q].y;
+                        if (pair_store) {
+                            *reinterpret_cast<float2*>(d) = o[q];
+                        } else {
+                            *d = o[q].x;
+                            if (hasB) dst[offB + (size_t)pq * P.pstride] = o[q].y;
+                        }
                     }
                 }
             }
         }
-        __syncthreads();  // this buffer is refilled by the next iteration's cp.async
+        __syncthreads();  // this buffer is refilled by the next iteration's staging
     }
 }
 
