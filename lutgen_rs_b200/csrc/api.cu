@@ -82,7 +82,7 @@ struct DevBuf {
     }
 };
 
-constexpr int kBatchStreams = 3;
+constexpr int kBatchStreams = 4;
 
 struct Ctx {
     std::mutex mu;
@@ -90,7 +90,7 @@ struct Ctx {
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t batch_streams[kBatchStreams] = {nullptr, nullptr, nullptr};
+    cudaStream_t batch_streams[kBatchStreams] = {};
     ColorTables* tables = nullptr;  // device
     DevBuf lut_rgb;                 // RGB8 CLUT (host-API scratch)
     DevBuf lut_rgbx;                // expanded CLUT for apply
@@ -1237,28 +1237,24 @@ int lutgen_cuda_apply_hald_dev(uint8_t* rgba_dev, size_t npix, const uint8_t* lu
     return LUTGEN_OK;
 }
 
+namespace {
+int apply_batch_share(uint8_t* const* frames, const size_t* npix, size_t nframes, const uint8_t* lut_rgb, uint8_t level, size_t first, size_t stride);
+}
 int lutgen_cuda_apply_hald(uint8_t* rgba, size_t npix, const uint8_t* lut_rgb, uint8_t level) {
     int rc = ensure_ready();
     if (rc) return rc;
     if (!level_ok(level)) return fail(LUTGEN_ERR_INVALID, "level %u outside 2..=33", level);
     if (!lut_rgb || (!rgba && npix)) return fail(LUTGEN_ERR_INVALID, "NULL buffer");
     if (npix == 0) return LUTGEN_OK;
-    std::lock_guard<std::mutex> lk(g.mu);
-    size_t lut_bytes = 3 * lut_entries(level);
-    CU_TRY(g.lut_rgb.reserve(lut_bytes));
-    CU_TRY(g.frame.reserve(npix * 4));
-    CU_TRY(cudaMemcpyAsync(g.lut_rgb.p, lut_rgb, lut_bytes, cudaMemcpyHostToDevice, g.stream));
-    CU_TRY(cudaMemcpyAsync(g.frame.p, rgba, npix * 4, cudaMemcpyHostToDevice, g.stream));
-    rc = lutgen_cuda_apply_hald_dev((uint8_t*)g.frame.p, npix, (const uint8_t*)g.lut_rgb.p, level, g.stream);
-    if (rc) return rc;
-    CU_TRY(cudaMemcpyAsync(rgba, g.frame.p, npix * 4, cudaMemcpyDeviceToHost, g.stream));
-    CU_TRY(cudaStreamSynchronize(g.stream));
-    return LUTGEN_OK;
+    // one frame through the chunked upload / kernel / download pipeline of the batch entry point
+    return apply_batch_share(&rgba, &npix, 1, lut_rgb, level, 0, 1);
 }
 
 namespace {
-// Frames first, first + stride, ... on the current context: CLUT up once, then a three-stream pipeline (frame i's
-// upload overlaps frame i-1's kernel and frame i-2's download: separate copy engines per direction).
+// Frames first, first + stride, ... on the current context: CLUT up once, then a pipeline over kBatchStreams streams in
+// CHUNKS of 2 M or 4 M pixels, whatever the frame sizes: chunk i's upload overlaps chunk i-1's kernel and chunk i-2's
+// download (separate copy engines per direction). With whole frames as the unit (round 1) a single frame's upload and
+// download did not overlap at all. LUTGEN_CUDA_APPLY_CHUNK=<pixels> overrides the chunk size (0: whole frames).
 int apply_batch_share(uint8_t* const* frames, const size_t* npix, size_t nframes, const uint8_t* lut_rgb, uint8_t level, size_t first, size_t stride) {
     int rc = ensure_ready();
     if (rc) return rc;
@@ -1267,6 +1263,15 @@ int apply_batch_share(uint8_t* const* frames, const size_t* npix, size_t nframes
     for (size_t i = first; i < nframes; i += stride)
         if (npix[i] > max_px) max_px = npix[i];
     if (max_px == 0) return LUTGEN_OK;
+    size_t total_px = 0;
+    for (size_t i = first; i < nframes; i += stride) total_px += npix[i];
+    // measured (tools/time_apply_e2e.py, pinned 4K frames): one frame 1.53 ms whole, 1.12 ms in 2 M-pixel chunks; four
+    // frames 3.68 ms whole, 3.63 / 3.50 ms in chunks of 2 M / 4 M pixels, 4.35 / 5.40 ms in chunks of 1 M / 0.5 M (a copy
+    // costs ~10 us to set up, and the two directions share the link: 37 GB/s each way when both run)
+    size_t chunk = total_px >= ((size_t)1 << 24) ? (size_t)1 << 22 : (size_t)1 << 21;
+    if (const char* e = getenv("LUTGEN_CUDA_APPLY_CHUNK")) chunk = (size_t)strtoull(e, nullptr, 10);
+    if (chunk == 0 || chunk > max_px) chunk = max_px;
+    chunk = (chunk + 3) & ~(size_t)3;   // k_apply takes four pixels per thread: chunk starts stay 16-byte aligned in the frame
     CU_TRY(g.lut_rgb.reserve(lut_bytes));
     CU_TRY(cudaMemcpyAsync(g.lut_rgb.p, lut_rgb, lut_bytes, cudaMemcpyHostToDevice, g.stream));
     rc = expand_lut((const uint8_t*)g.lut_rgb.p, level, g.stream);
@@ -1276,20 +1281,23 @@ int apply_batch_share(uint8_t* const* frames, const size_t* npix, size_t nframes
     int result = LUTGEN_OK;
     cudaError_t e = cudaEventRecord(lut_ready, g.stream);
     for (int i = 0; i < kBatchStreams && e == cudaSuccess; ++i) {
-        e = g.batch_frames[i].reserve(max_px * 4);
+        e = g.batch_frames[i].reserve(chunk * 4);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(g.batch_streams[i], lut_ready, 0);
     }
     size_t k = 0;
     for (size_t i = first; i < nframes && e == cudaSuccess && result == LUTGEN_OK; i += stride) {
-        if (!npix[i]) continue;
-        int b = (int)(k++ % kBatchStreams);
-        cudaStream_t s = g.batch_streams[b];
-        uint8_t* dev = (uint8_t*)g.batch_frames[b].p;
-        e = cudaMemcpyAsync(dev, frames[i], npix[i] * 4, cudaMemcpyHostToDevice, s);
-        if (e != cudaSuccess) break;
-        result = launch_apply(dev, npix[i], (const uint32_t*)g.lut_rgbx.p, level, s);
-        if (result != LUTGEN_OK) break;
-        e = cudaMemcpyAsync(frames[i], dev, npix[i] * 4, cudaMemcpyDeviceToHost, s);
+        for (size_t p0 = 0; p0 < npix[i] && e == cudaSuccess && result == LUTGEN_OK; p0 += chunk) {
+            const size_t n = std::min(chunk, npix[i] - p0);
+            int b = (int)(k++ % kBatchStreams);
+            cudaStream_t s = g.batch_streams[b];
+            uint8_t* dev = (uint8_t*)g.batch_frames[b].p;
+            uint8_t* host = frames[i] + 4 * p0;
+            e = cudaMemcpyAsync(dev, host, n * 4, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) break;
+            result = launch_apply(dev, n, (const uint32_t*)g.lut_rgbx.p, level, s);
+            if (result != LUTGEN_OK) break;
+            e = cudaMemcpyAsync(host, dev, n * 4, cudaMemcpyDeviceToHost, s);
+        }
     }
     // whatever happened, nothing may still be copying from or into the caller's frames when this returns
     for (int i = 0; i < kBatchStreams; ++i) {
