@@ -99,7 +99,7 @@ def load_palette():
 
 def profiled_traffic():
     """DRAM bytes per launch of the two headline kernels from this round's ncu --set full captures."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f)
@@ -528,7 +528,7 @@ def run_b200(args):
         "roofline": {"bound": "fp32", "achieved": gen_achieved, "peak": fp32.value, "unit": "TFLOP/s",
                      "frac": gen_achieved / fp32.value if fp32.value else None,
                      "traffic": profiled_traffic().get("k_remap_warp_level16_bytes_per_launch") if world == 1 else None,
-                     "traffic_note": "DRAM bytes of one k_remap_warp launch (ncu --set full, profiles/r1_traffic.json): the CLUT it writes stays in L2",
+                     "traffic_note": "DRAM bytes of one k_remap_warp launch (ncu --set full, profiles/r2_traffic.json): the CLUT it writes stays in L2",
                      "peak_source": "on-box FFMA micro-benchmark (lutgen_cuda_measure_peaks), this run",
                      "mufu_peak_tops": mufu.value, "kernel_ms": gen_kernel_t * 1e3,
                      "algorithmic_flops_per_entry": GEN_FLOPS_PER_ENTRY,

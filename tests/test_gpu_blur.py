@@ -41,6 +41,21 @@ def test_blur_level16_bit_exact(palettes):
     assert (got == want).all(), int((got != want).sum())
 
 
+@pytest.mark.parametrize("level,radius,preserve", [(8, 8.0, False), (16, 3.0, True), (4, 2.0, False)])
+def test_blur_bulk_and_plain_staging_agree(palettes, monkeypatch, level, radius, preserve):
+    """The R and G passes stage their tiles with cp.async.bulk rows + an mbarrier per buffer where every row is a 16-byte
+    aligned run (kernels_blur.cuh), with 4-byte cp.async otherwise; LUTGEN_CUDA_BLUR_NO_BULK forces the latter."""
+    pal = palettes["catppuccin_mocha"]
+    monkeypatch.delenv("LUTGEN_CUDA_BLUR_NO_BULK", raising=False)
+    bulk = interpolation.GaussianBlurRemapper(pal, radius, 1.0, preserve).par_generate_lut(level)
+    monkeypatch.setenv("LUTGEN_CUDA_BLUR_NO_BULK", "1")
+    plain = interpolation.GaussianBlurRemapper(pal, radius, 1.0, preserve).par_generate_lut(level)
+    assert (bulk == plain).all()
+    if level <= 8:
+        want = O.Remapper(O.BLUR, pal, param=radius, preserve=preserve).generate_lut(level)
+        assert (bulk == want).all()
+
+
 def test_blur_256_colour_palette(palettes):
     got, want = _case(synthetic_palette(256, seed=1), 8, 4.0)
     assert (got == want).all()

@@ -89,6 +89,24 @@ def test_apply_level16_identity_is_noop():
     assert (got == img).all()
 
 
+def test_apply_chunked_pipeline(palettes, monkeypatch):
+    """Host frames travel in chunks through an upload / kernel / download pipeline (api.cu: apply_batch_share). Tiny
+    chunks force many of them, with ragged last chunks, across frame boundaries and over several streams."""
+    lut = O.Remapper(O.NEAREST, palettes["nord"], lum_factor=1.0).generate_lut(6)
+    sizes = (100003, 5, 4000, 999, 1000, 1001, 0, 12345)
+    for chunk in ("1000", "4096", "0"):
+        monkeypatch.setenv("LUTGEN_CUDA_APPLY_CHUNK", chunk)
+        frames = [random_rgba(n, seed=n + 1).reshape(1, n, 4) if n else np.zeros((1, 0, 4), np.uint8) for n in sizes]
+        want = [O.correct_image(f, lut, 6) if f.size else f.copy() for f in frames]
+        identity.correct_images(frames, lut)
+        for f, w in zip(frames, want):
+            assert (f == w).all()
+        one = random_rgba(77777, seed=3).reshape(1, -1, 4)
+        w1 = O.correct_image(one, lut, 6)
+        identity.correct_image(one, lut)
+        assert (one == w1).all()
+
+
 def test_apply_batch_matches_single(palettes):
     lut = O.Remapper(O.NEAREST, palettes["nord"], lum_factor=1.0).generate_lut(6)
     frames = [random_rgba(n, seed=n).reshape(1, n, 4) for n in (1000, 1, 77777, 4096, 31)]
