@@ -47,7 +47,8 @@ void blur_launch_axis(unsigned grid, size_t smem, cudaStream_t s, const float* s
 
 void blur_launch_to_lut(unsigned grid, cudaStream_t s, const float* colors, uint32_t size, uint32_t ch, const uint8_t* chan, uint8_t* out_rgb,
                         unsigned long long begin, unsigned long long count, uint32_t b_first, uint32_t tiles_r, uint32_t ntiles, const ColorTables* tables) {
-    k_blur_to_lut<<<grid, 256, 0, s>>>(colors, size, ch, chan, out_rgb, begin, count, b_first, tiles_r, ntiles, tables);
+    if (ch == 2) k_blur_to_lut<2><<<grid, 256, 0, s>>>(colors, size, chan, out_rgb, begin, count, b_first, tiles_r, ntiles, tables);
+    else k_blur_to_lut<3><<<grid, 256, 0, s>>>(colors, size, chan, out_rgb, begin, count, b_first, tiles_r, ntiles, tables);
 }
 
 }  // namespace lutgen

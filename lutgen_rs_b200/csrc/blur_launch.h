@@ -13,7 +13,7 @@ namespace lutgen {
 struct ColorTables;
 
 constexpr int BLUR_ROW_WARPS = 8;
-constexpr int BLUR_TR = 32, BLUR_TB = 8;
+constexpr int BLUR_TR = 32, BLUR_TB = 32;   // k_blur_to_lut's tile: r x b cells of one g
 constexpr int BLUR_MAX_DYN_SMEM = 226 * 1024;   // k_blur_axis: dynamic shared memory (the tiles) next to 16 bytes of static (the mbarriers)
 
 // One blur pass along one axis of the [r][g][b][ch] volume (see k_blur_axis).

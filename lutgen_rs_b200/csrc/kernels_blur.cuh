@@ -446,55 +446,125 @@ __global__ void __launch_bounds__(256, 4) k_blur_axis(const float* __restrict__ 
 }
 
 // colors_to_lut / cell_to_rgb, gaussian_blur.rs:433-500: the [r][g][b] volume to Hald order
-// (b outer, g, r inner), entries [begin, begin + count). A tile is 32 r x 8 b cells of one g,
-// transposed through shared memory (reads are runs of 8*ch floats, writes runs of 96 bytes); CTAs
-// are persistent and walk tiles blockIdx.x, blockIdx.x + gridDim.x, ...
-__global__ void __launch_bounds__(256) k_blur_to_lut(const float* __restrict__ colors, uint32_t size, uint32_t ch, const uint8_t* __restrict__ chan,
+// (b outer, g, r inner), entries [begin, begin + count). A tile is BLUR_TR r x BLUR_TB b cells of one g,
+// transposed through shared memory: a warp reads one r's run of BLUR_TB * ch contiguous floats (384 bytes), a
+// thread converts four cells, and a warp's stores are the 96 contiguous bytes of 32 r entries of one b -- as 24 words
+// through a per-warp staging row when they are aligned, else as bytes. CTAs are persistent and walk tiles blockIdx.x,
+// blockIdx.x + gridDim.x, ...; the NEXT tile's floats are loaded into registers before the current tile is converted
+// (twelve loads in flight per thread: the kernel is bound by how many bytes an SM keeps in flight, not by instructions --
+// quadrupling the tile and halving the instructions per cell left round 1's 125 us where they were).
+struct BlurTile { uint32_t g, r0, b0; };
+__device__ __forceinline__ BlurTile blur_lut_tile(uint32_t t, uint32_t tiles_r, float inv_tr, uint32_t size, float inv_size, uint32_t b_first) {
+    // t = (tb * size + g) * tiles_r + tr   (float estimate + correction: t < 2^24)
+    uint32_t q1 = (uint32_t)(__uint2float_rz(t) * inv_tr);
+    int rem = (int)(t - q1 * tiles_r);
+    if (rem < 0) { --q1; rem += (int)tiles_r; }
+    if (rem >= (int)tiles_r) { ++q1; rem -= (int)tiles_r; }
+    uint32_t tb = (uint32_t)(__uint2float_rz(q1) * inv_size);
+    int g_ = (int)(q1 - tb * size);
+    if (g_ < 0) { --tb; g_ += (int)size; }
+    if (g_ >= (int)size) { ++tb; g_ -= (int)size; }
+    BlurTile T;
+    T.g = (uint32_t)g_; T.r0 = (uint32_t)rem * BLUR_TR; T.b0 = b_first + tb * BLUR_TB;
+    return T;
+}
+constexpr int BLUR_LUT_ROWS = BLUR_TR / 8, BLUR_LUT_X = (BLUR_TB * 3 + 31) / 32;   // per thread: rows (one per trip of its warp) x floats per row
+
+__device__ __forceinline__ void blur_lut_fetch(const float* __restrict__ colors, uint32_t size, uint32_t ch, const BlurTile& T, uint32_t warp, uint32_t lane,
+                                               float (&v)[BLUR_LUT_ROWS][BLUR_LUT_X]) {
+    const uint32_t run = T.b0 < size ? min((uint32_t)BLUR_TB, size - T.b0) * ch : 0u;   // floats of one r's cells in this tile
+#pragma unroll
+    for (int i = 0; i < BLUR_LUT_ROWS; ++i) {
+        const uint32_t lr = warp + 8u * i;
+        const bool row = T.r0 + lr < size;
+        const float* q = colors + (((size_t)(row ? T.r0 + lr : 0u) * size + T.g) * size + (run ? T.b0 : 0u)) * ch;
+#pragma unroll
+        for (int j = 0; j < BLUR_LUT_X; ++j) {
+            const uint32_t x = lane + 32u * j;
+            v[i][j] = (row && x < run) ? __ldcs(q + x) : 0.f;   // read once
+        }
+    }
+}
+
+// One cell: the blurred Oklab value (preserve: the cell's own L) back to packed sRGB.
+template <int CH>
+__device__ __forceinline__ uint32_t blur_cell_rgb(const SmemTables& st, const float* __restrict__ cell, float own_r, float own_g, float own_b) {
+    Lab o;
+    if (CH == 2) {
+        const Lab own = linear_to_oklab_exact(own_r, own_g, own_b);
+        o.l = own.l; o.a = cell[0]; o.b = cell[1];
+    } else {
+        o.l = cell[0]; o.a = cell[1]; o.b = cell[2];
+    }
+    float r, g, b;
+    oklab_to_linear_exact(o, r, g, b);
+    return srgb8_pack3(f32_to_srgb8_wide(r, st.encode2), f32_to_srgb8_wide(g, st.encode2), f32_to_srgb8_wide(b, st.encode2));
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256) k_blur_to_lut(const float* __restrict__ colors, uint32_t size, const uint8_t* __restrict__ chan,
                                                       uint8_t* __restrict__ out_rgb, unsigned long long begin, unsigned long long count,
                                                       uint32_t b_first, uint32_t tiles_r, uint32_t ntiles, const ColorTables* __restrict__ tables) {
     __shared__ SmemTables st;
     __shared__ float s_c[BLUR_TR][BLUR_TB * 3 + 1];
+    __shared__ __align__(16) uint8_t s_out[8][96];
+    static_assert(BLUR_TR == 32 && BLUR_TB % 8 == 0, "a warp stores the 32 r entries of one b; eight warps share the b cells");
     stage_tables(st, tables);
-    const uint32_t lr = threadIdx.x >> 3, lb = threadIdx.x & 7u;      // loading: 8 b cells of one r are contiguous
-    const uint32_t rr = threadIdx.x & 31u, bb = threadIdx.x >> 5;      // storing: 32 r entries of one b are contiguous
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const float inv_tr = 1.0f / (float)tiles_r, inv_size = 1.0f / (float)size;
-    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        // t = (tb * size + g) * tiles_r + tr   (float estimate + correction: t < 2^24)
-        uint32_t q1 = (uint32_t)(__uint2float_rz(t) * inv_tr);
-        int rem = (int)(t - q1 * tiles_r);
-        if (rem < 0) { --q1; rem += (int)tiles_r; }
-        if (rem >= (int)tiles_r) { ++q1; rem -= (int)tiles_r; }
-        const uint32_t tr = (uint32_t)rem;
-        uint32_t tb = (uint32_t)(__uint2float_rz(q1) * inv_size);
-        int g_ = (int)(q1 - tb * size);
-        if (g_ < 0) { --tb; g_ += (int)size; }
-        if (g_ >= (int)size) { ++tb; g_ -= (int)size; }
-        const uint32_t g = (uint32_t)g_, r0 = tr * BLUR_TR, b0 = b_first + tb * BLUR_TB;
+    const bool out_aligned = (reinterpret_cast<uintptr_t>(out_rgb) & 3u) == 0 && (size & 3u) == 0;
+    const unsigned long long plane = (unsigned long long)size * size, end = begin + count;
+    float v[BLUR_LUT_ROWS][BLUR_LUT_X];
+    uint32_t t = blockIdx.x;
+    BlurTile T = blur_lut_tile(t < ntiles ? t : 0u, tiles_r, inv_tr, size, inv_size, b_first);
+    if (t < ntiles) blur_lut_fetch(colors, size, (uint32_t)CH, T, warp, lane, v);
+    for (; t < ntiles; t += gridDim.x) {
         __syncthreads();  // the previous tile's s_c is no longer read
-        if (r0 + lr < size && b0 + lb < size) {
-            const float* q = colors + (((size_t)(r0 + lr) * size + g) * size + b0 + lb) * ch;
-            s_c[lr][lb * ch] = q[0];
-            s_c[lr][lb * ch + 1] = q[1];
-            if (ch == 3) s_c[lr][lb * ch + 2] = q[2];
-        }
+#pragma unroll
+        for (int i = 0; i < BLUR_LUT_ROWS; ++i)
+#pragma unroll
+            for (int j = 0; j < BLUR_LUT_X; ++j) s_c[warp + 8u * i][lane + 32u * j] = v[i][j];
         __syncthreads();
-        const uint32_t ri = r0 + rr, bi = b0 + bb;
-        if (ri >= size || bi >= size) continue;
-        const unsigned long long px = ((unsigned long long)bi * size + g) * size + ri;
-        if (px < begin || px >= begin + count) continue;
-        Lab o;
-        if (ch == 2) {
-            Lab own = linear_to_oklab_exact(st.decode[chan[ri]], st.decode[chan[g]], st.decode[chan[bi]]);
-            o.l = own.l; o.a = s_c[rr][bb * 2]; o.b = s_c[rr][bb * 2 + 1];
-        } else {
-            o.l = s_c[rr][bb * 3]; o.a = s_c[rr][bb * 3 + 1]; o.b = s_c[rr][bb * 3 + 2];
+        const BlurTile C = T;
+        const uint32_t tn = t + gridDim.x;
+        if (tn < ntiles) {
+            T = blur_lut_tile(tn, tiles_r, inv_tr, size, inv_size, b_first);
+            blur_lut_fetch(colors, size, (uint32_t)CH, T, warp, lane, v);   // in flight while this tile is converted
         }
-        float r, gg, b;
-        oklab_to_linear_exact(o, r, gg, b);
-        uint8_t* q = out_rgb + 3ull * px;
-        q[0] = (uint8_t)f32_to_srgb8(r, st.encode2);
-        q[1] = (uint8_t)f32_to_srgb8(gg, st.encode2);
-        q[2] = (uint8_t)f32_to_srgb8(b, st.encode2);
+        const uint32_t g = C.g, ri = C.r0 + lane;
+        if (C.b0 >= size) continue;
+        const bool r_ok = ri < size;
+        const float own_r = (CH == 2 && r_ok) ? st.decode[chan[ri]] : 0.f, own_g = CH == 2 ? st.decode[chan[g]] : 0.f;
+        const uint32_t nb = min((uint32_t)BLUR_TB, size - C.b0);
+        // entry of (b0 + warp, g, r0): the warp's first row of this tile; its next one is 8 planes on
+        unsigned long long px0 = ((unsigned long long)(C.b0 + warp) * size + g) * size + C.r0;
+        const unsigned long long tile_first = ((unsigned long long)C.b0 * size + g) * size + C.r0;
+        const unsigned long long tile_last = ((unsigned long long)(C.b0 + nb - 1u) * size + g) * size + min(C.r0 + 31u, size - 1u);
+        // the usual tile: whole rows of 32 entries, all inside the launch's range, word-aligned in the CLUT -- no test per cell
+        if (out_aligned && C.r0 + 31u < size && tile_first >= begin && tile_last < end) {
+            uint8_t* sb = s_out[warp];
+            uint8_t* dst = out_rgb + 3ull * px0;
+            const size_t step = (size_t)(24ull * plane);   // 8 planes of 3-byte entries
+#pragma unroll 1
+            for (uint32_t bb = warp; bb < nb; bb += 8u, dst += step) {
+                const float own_b = CH == 2 ? st.decode[chan[C.b0 + bb]] : 0.f;
+                const uint32_t packed = blur_cell_rgb<CH>(st, &s_c[lane][bb * CH], own_r, own_g, own_b);
+                __syncwarp();   // the previous row's words have been read
+                sb[3u * lane] = (uint8_t)packed; sb[3u * lane + 1] = (uint8_t)(packed >> 8); sb[3u * lane + 2] = (uint8_t)(packed >> 16);
+                __syncwarp();
+                if (lane < 24u) reinterpret_cast<uint32_t*>(dst)[lane] = reinterpret_cast<const uint32_t*>(sb)[lane];
+            }
+            continue;
+        }
+#pragma unroll 1
+        for (uint32_t bb = warp; bb < nb; bb += 8u, px0 += 8ull * plane) {
+            const unsigned long long px = px0 + lane;
+            if (!(r_ok && px >= begin && px < end)) continue;
+            const float own_b = CH == 2 ? st.decode[chan[C.b0 + bb]] : 0.f;
+            const uint32_t packed = blur_cell_rgb<CH>(st, &s_c[lane][bb * CH], own_r, own_g, own_b);
+            uint8_t* q = out_rgb + 3ull * px;
+            q[0] = (uint8_t)packed; q[1] = (uint8_t)(packed >> 8); q[2] = (uint8_t)(packed >> 16);
+        }
     }
 }
 

@@ -8,6 +8,7 @@
 //   k_pngd_adler_parts / k_pngd_adler_check   Adler-32 of the inflated stream against the stream's trailer
 //   k_pngd_unfilter        Sub / Up / Average / Paeth as an anti-diagonal wavefront: a warp per band of 32 rows
 //   k_pngd_expand          to the channel count asked for (palette, grey -> RGB, alpha added or dropped)
+#include <cstdlib>
 #include "png_decode_launch.h"
 
 #include "png_decode_core.h"
@@ -222,6 +223,118 @@ __global__ void __launch_bounds__(256) k_pngd_unfilter(const uint8_t* __restrict
     }
 }
 
+// The same wavefront with the pixel size known at compile time and no branch that depends on the lane's position in its
+// row: the generic kernel above picks its pixel routine and its store form at run time inside every step, and its packing
+// of RGB pixels into words branches on x mod 4 -- which differs from lane to lane, so a warp walked all four arms at
+// every step (277 instructions per step, 15 ms for a level-16 CLUT). WORDS: rows start on word boundaries (RGBA always
+// when `out` is aligned; RGB when the row length is a multiple of 4 bytes too): pixels leave as 32-bit words.
+template <int BPP>
+__device__ __forceinline__ uint32_t load_pixel_t(const uint8_t* p) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < BPP; ++k) v |= (uint32_t)p[k] << (8 * k);
+    return v;
+}
+template <int BPP>
+__device__ __forceinline__ uint32_t load_pixel_cg_t(const uint8_t* p) {   // written by another warp: not through L1
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < BPP; ++k) v |= (uint32_t)__ldcg(p + k) << (8 * k);
+    return v;
+}
+template <int BPP, bool WORDS>
+__global__ void __launch_bounds__(256) k_pngd_unfilter_t(const uint8_t* __restrict__ stream, uint32_t w, uint32_t h, uint8_t* __restrict__ out, int* progress,
+                                                          int* status) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u, band = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nbands = (h + 31u) / 32u;
+    if (band >= nbands) return;
+    const size_t rb = (size_t)w * BPP;
+    const uint32_t r = band * 32u + lane;
+    const bool valid = r < h;
+    const uint8_t* src = stream + (size_t)(valid ? r : 0) * (rb + 1);
+    const uint32_t ft = valid ? src[0] : 0u;
+    if (ft > 4u) atomicOr(status + 3, 1);   // not a filter type (PNG specification 9.2): the file is corrupt
+    ++src;
+    uint8_t* dstrow = out + (size_t)(valid ? r : 0) * rb;
+    const uint8_t* above_row = band > 0 ? out + (size_t)(band * 32u - 1u) * rb : nullptr;
+    const bool publish = band + 1 < nbands;   // full band with a follower: lane 31 is its last row
+    uint32_t a = 0, prev_b = 0, last_out = 0, above = 0;
+    const uint32_t steps = w + 31u;
+    const uint32_t mA = ft == 1u ? 255u : 0u, mB = ft == 2u ? 255u : 0u, mV = ft == 3u ? 255u : 0u, mP = ft == 4u ? 255u : 0u;
+    uint32_t pk0 = 0, pk1 = 0, pk2 = 0;
+    uint32_t blk[UNF_AHEAD], nxt[UNF_AHEAD];
+#pragma unroll
+    for (int j = 0; j < UNF_AHEAD; ++j) {
+        const int x = j - (int)lane;
+        blk[j] = (valid && x >= 0 && x < (int)w) ? load_pixel_t<BPP>(src + (size_t)x * BPP) : 0u;
+    }
+    for (uint32_t s0 = 0; s0 < steps; s0 += UNF_AHEAD) {
+#pragma unroll
+        for (int j = 0; j < UNF_AHEAD; ++j) {
+            const int x = (int)(s0 + UNF_AHEAD) + j - (int)lane;
+            nxt[j] = (valid && x >= 0 && x < (int)w) ? load_pixel_t<BPP>(src + (size_t)x * BPP) : 0u;
+        }
+        // the row above the band, 32 pixels at a time: once per four trips (s0 advances by 8), outside the unrolled steps
+        if (above_row && s0 < w && (s0 & 31u) == 0) {
+            const uint32_t need = min(s0 + 32u, w);
+            if (lane == 0) {
+                int v;
+                for (;;) {   // relaxed polls with a pause, ONE fence once the count is there (see the generic kernel)
+                    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(progress + band - 1) : "memory");
+                    if ((uint32_t)v >= need) break;
+                    __nanosleep(100);
+                }
+                __threadfence();
+            }
+            __syncwarp();
+            const uint32_t xa = s0 + lane;
+            above = xa < w ? load_pixel_cg_t<BPP>(above_row + (size_t)xa * BPP) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < UNF_AHEAD; ++j) {
+            const uint32_t s = s0 + j;
+            uint32_t b = __shfl_up_sync(FULL, last_out, 1);
+            const uint32_t from_above = __shfl_sync(FULL, above, s & 31u);
+            if (lane == 0) b = above_row ? from_above : 0u;
+            const int x = (int)s - (int)lane;
+            const bool in_row = valid && x >= 0 && x < (int)w;
+            uint32_t cur = lpngd::unfilter_pixel_masked<BPP>(blk[j], a, b, prev_b, mA, mB, mV, mP);
+            cur = in_row ? cur : 0u;
+            if (WORDS && BPP == 4) {
+                if (in_row) reinterpret_cast<uint32_t*>(dstrow)[x] = cur;
+            } else if (WORDS && BPP == 3) {
+                // four pixels = three words, assembled without a branch on x mod 4: pixel q lands at bit 24 q
+                const uint32_t q = (uint32_t)x & 3u, sh = (q * 24u) & 31u;
+                const uint32_t lo = cur << sh, hi = sh ? cur >> (32u - sh) : 0u;   // cur < 2^24: hi is empty for q = 0 and q = 3
+                pk0 = q == 0u ? lo : (q == 1u ? (pk0 | lo) : pk0);
+                pk1 = q == 1u ? hi : (q == 2u ? (pk1 | lo) : pk1);
+                pk2 = q == 2u ? hi : (q == 3u ? (pk2 | lo) : pk2);
+                if (in_row && q == 3u) {
+                    uint32_t* q32 = reinterpret_cast<uint32_t*>(dstrow + (size_t)(x - 3) * 3u);
+                    q32[0] = pk0; q32[1] = pk1; q32[2] = pk2;
+                } else if (in_row && x == (int)w - 1) {   // the row's last one to three pixels (once per row)
+                    uint8_t* t = dstrow + (size_t)(x - (int)q) * 3u;
+                    const uint32_t nb = (q + 1u) * 3u;
+                    for (uint32_t k = 0; k < nb; ++k) t[k] = (uint8_t)((k < 4 ? pk0 >> (8u * k) : (k < 8 ? pk1 >> (8u * (k - 4)) : pk2 >> (8u * (k - 8)))));
+                }
+            } else if (in_row) {
+#pragma unroll
+                for (int k = 0; k < BPP; ++k) dstrow[(size_t)x * BPP + k] = (uint8_t)(cur >> (8 * k));
+            }
+            a = in_row ? cur : a;
+            prev_b = b;
+            last_out = cur;
+            if (publish && lane == 31u && x >= 0 && x < (int)w && (((uint32_t)x & 31u) == 31u || x == (int)w - 1)) {
+                __threadfence();
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(progress + band), "r"(x + 1) : "memory");
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < UNF_AHEAD; ++j) blk[j] = nxt[j];
+    }
+}
+
 __global__ void k_pngd_expand(const uint8_t* __restrict__ rows, unsigned long long npix, int color_type, int channels, int out_channels,
                               const uint32_t* __restrict__ palette, uint8_t* __restrict__ out) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -337,7 +450,19 @@ cudaError_t png_decode_async(const PngDecodePlan& plan, const uint8_t* z_dev, co
     }
     const bool direct = plan.out_channels == plan.channels && plan.color_type != 3;
     const unsigned nbands = (plan.height + 31) / 32;
-    k_pngd_unfilter<<<(nbands + 7) / 8, 256, 0, s>>>(stream, plan.width, plan.height, (uint32_t)plan.channels, direct ? out_dev : rows, progress, status);
+    {
+        uint8_t* dst = direct ? out_dev : rows;
+        const size_t rowb = (size_t)plan.width * (size_t)plan.channels;
+        const bool aligned = (reinterpret_cast<uintptr_t>(dst) & 3u) == 0;
+        const unsigned grid = (nbands + 7) / 8;
+        if (getenv("LUTGEN_CUDA_PNG_GENERIC_UNFILTER")) k_pngd_unfilter<<<grid, 256, 0, s>>>(stream, plan.width, plan.height, (uint32_t)plan.channels, dst, progress, status);
+        else if (plan.channels == 4 && aligned) k_pngd_unfilter_t<4, true><<<grid, 256, 0, s>>>(stream, plan.width, plan.height, dst, progress, status);
+        else if (plan.channels == 4) k_pngd_unfilter_t<4, false><<<grid, 256, 0, s>>>(stream, plan.width, plan.height, dst, progress, status);
+        else if (plan.channels == 3 && aligned && (rowb & 3u) == 0) k_pngd_unfilter_t<3, true><<<grid, 256, 0, s>>>(stream, plan.width, plan.height, dst, progress, status);
+        else if (plan.channels == 3) k_pngd_unfilter_t<3, false><<<grid, 256, 0, s>>>(stream, plan.width, plan.height, dst, progress, status);
+        else if (plan.channels == 2) k_pngd_unfilter_t<2, false><<<grid, 256, 0, s>>>(stream, plan.width, plan.height, dst, progress, status);
+        else k_pngd_unfilter_t<1, false><<<grid, 256, 0, s>>>(stream, plan.width, plan.height, dst, progress, status);
+    }
     e = cudaMemcpyAsync(status_host + 3, status + 3, sizeof(int), cudaMemcpyDeviceToHost, s);
     if (e != cudaSuccess) return e;
     ++nl;
