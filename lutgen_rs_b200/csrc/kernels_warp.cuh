@@ -352,7 +352,13 @@ __device__ __noinline__ PairAcc wt_select_insert(const float4* __restrict__ unc,
 // A score is within tol / 2 of its true value, so a colour below the band is nearer than at least
 // mU - kp others and one above it farther than at least kp + 1 -- whatever the order inside the band.
 // False: the band holds more than WT_BAND colours (the caller falls back to the full f64 evaluation).
-constexpr int WT_BAND = 4;
+// (A band of 8 was measured: the larger resolver makes both warp-tile kernels 2.5 % slower and settles nothing more. What
+// did reach the f64 list pass with 256 colours -- six entries of a level-16 CLUT, 70 us of ONE thread's latency for them --
+// were uncertain sets of more than 32 colours: the chosen set is a 64-bit mask now.)
+#ifndef WT_BAND_N
+#define WT_BAND_N 4
+#endif
+constexpr int WT_BAND = WT_BAND_N;   // (4 until round 2's end: with 256 colours a handful of entries per CLUT overflowed it, and each of them costs the f64 list pass 70 us of one thread's latency)
 
 // linear_to_oklab_exact with ONE out-of-line copy of the correctly rounded cube root (the resolvers run rarely, but often
 // enough that their code competes with the hot loop for the instruction cache: three inlined copies were 140 instructions).
@@ -377,7 +383,7 @@ template <int KIND>
 __device__ __noinline__ bool wt_resolve_tie(const double* __restrict__ pal64, double lum64, const float* __restrict__ decode,
                                             const float4* __restrict__ unc, const uint32_t* __restrict__ uidx, int mU, int kp, bool top, uint32_t rgb,
                                             float L, float A, float B, float c1, float c0, float tau, float nxt, float tol, float4& out) {
-    if (mU > 32) return false;
+    if (mU > 64) return false;
     double e[3];
     wt_exact_colour(decode, rgb, lum64, e);
     const float lo = tau - tol, hi = nxt + tol;
@@ -410,16 +416,16 @@ __device__ __noinline__ bool wt_resolve_tie(const double* __restrict__ pal64, do
         }
     }
     const int need = kp - certain;
-    uint32_t chosen = 0;   // by list position
+    unsigned long long chosen = 0;   // by list position (mU <= 64)
 #pragma unroll
     for (int t = 0; t < WT_BAND; ++t)
-        if (t < need && t < nb) chosen |= 1u << (bk[t] & 255u);
+        if (t < need && t < nb) chosen |= 1ull << (bk[t] & 255u);
     float n0 = 0.f, n1 = 0.f, n2 = 0.f, den = 0.f;
 #pragma unroll 1
     for (int i = 0; i < mU; ++i) {
         const float4 q = unc[i];
         const float sc = wt_score2<KIND>(q, splat(L), splat(A), splat(B)).x;
-        const bool in_set = sc < lo || ((chosen >> i) & 1u);
+        const bool in_set = sc < lo || ((chosen >> i) & 1ull);
         if (in_set != top) {
             float w = wt_weight2<KIND>(splat(sc), c1, c0).x;
             w = top ? -w : w;

@@ -15,6 +15,12 @@ import zlib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _synthetic_palette(n, seed):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import synthetic_palette
+    return synthetic_palette(n, seed)
+
+
 def child(reps):
     sys.path.insert(0, ROOT)
     import numpy as np
@@ -28,7 +34,8 @@ def child(reps):
     cases = {"gauss16": (interpolation.GaussianRemapper(pal, 128.0, 16, 1.0, False), 16),
              "nn16": (interpolation.NearestNeighborRemapper(pal, 1.0, False), 16),
              "shep16": (interpolation.ShepardRemapper(pal, 4.0, 16, 1.0, False), 16),
-             "gauss12": (interpolation.GaussianRemapper(pal, 128.0, 16, 1.0, False), 12)}
+             "gauss12": (interpolation.GaussianRemapper(pal, 128.0, 16, 1.0, False), 12),
+             "shep256": (interpolation.ShepardRemapper(_synthetic_palette(256, 1), 4.0, 16, 1.0, False), 16)}
     for name, (r, level) in cases.items():
         side = level ** 3
         lut = torch.empty(3 * side * side, dtype=torch.uint8, device="cuda")
