@@ -13,6 +13,17 @@
 
 namespace lutgen {
 
+// Margin of k_blur_nn_volume's fast decision (squared-distance units, per unit of max(1, lum)): 4 x 8e-7 per sqrt(d) for the
+// conversion (see the kernel), 5e-7 per sqrt(d) + 1.5e-6 for the rounding of the expanded distance.
+constexpr float BLUR_TIE_SLOPE = 3.7e-6f, BLUR_TIE_CONST = 1.5e-6f;
+
+// Order-preserving integer keys of floats (warp min / max by REDUX).
+__device__ __forceinline__ uint32_t blur_f2key(float x) {
+    const uint32_t b = __float_as_uint(x);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float blur_key2f(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+
 // sq_dist, gaussian_blur.rs:504-510 (f32, left to right).
 __device__ __forceinline__ float blur_sq_dist(float c0, float c1, float c2, const float* __restrict__ p) {
     float dl = __fsub_rn(c0, p[0]), da = __fsub_rn(c1, p[1]), db = __fsub_rn(c2, p[2]);
@@ -103,6 +114,7 @@ __global__ void __launch_bounds__(BLUR_ROW_WARPS * 32) k_blur_nn_volume(float* _
     const uint32_t FULL = 0xffffffffu;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rows = size * size;
+    const float es = fmaxf(1.0f, lum);   // L, and the error of the fast conversion in it, are scaled by lum
     (void)one;
     for (uint32_t row = blockIdx.x * BLUR_ROW_WARPS + warp; row < rows; row += gridDim.x * BLUR_ROW_WARPS) {
         const uint32_t r = row / size, g = row % size;
@@ -123,23 +135,83 @@ __global__ void __launch_bounds__(BLUR_ROW_WARPS * 32) k_blur_nn_volume(float* _
                 f2 L, A, B;
                 lms_to_lab2(fma2(splat(0.0514459929f), linb, splat(pl)), fma2(splat(0.1073969566f), linb, splat(pm)),
                             fma2(splat(0.6299787005f), linb, splat(ps)), lum, L, A, B);
-#pragma unroll 2
-                for (uint32_t t = 0; t < n; ++t) {
-                    const float4 q = s_q[t];
-                    const f2 d = fma2(splat(q.x), L, fma2(splat(q.y), A, fma2(splat(q.z), B, splat(q.w))));   // d - |c|^2
-                    const bool bx_ = d.x < best.x, by_ = d.y < best.y;
-                    second.x = bx_ ? best.x : fminf(second.x, d.x);
-                    second.y = by_ ? best.y : fminf(second.y, d.y);
-                    best.x = bx_ ? d.x : best.x;
-                    best.y = by_ ? d.y : best.y;
-                    ix = bx_ ? t : ix;
-                    iy = by_ ? t : iy;
+                // Palettes of at most 32 colours: only the colours that can be the nearest, or within the doubtful margin of
+                // it, of ANY of the warp's 64 cells are scanned (ascending palette index, as the full scan goes). One colour
+                // per lane is bounded against the cells' Oklab box: U = the smallest of the largest distances bounds every
+                // cell's nearest distance, and a colour whose smallest distance exceeds U + slack is farther than
+                // best + slack from every cell -- it is neither the nearest nor a second that could make a cell doubtful
+                // (slack = the early-exit threshold plus the largest margin the tests below use). Doubtful cells are
+                // rescanned over the whole palette as before. Typically 2-5 of 26 colours survive: the scan was half of the
+                // kernel's instructions (profiles/r2_blur_k_blur_nn_volume_ncu.txt).
+                uint32_t todo = 0xffffffffu;
+                if (n <= 32u) {
+                    float lo[3], hi[3];
+                    {
+                        const float v[3][2] = {{L.x, L.y}, {A.x, A.y}, {B.x, B.y}};
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            lo[c] = blur_key2f(__reduce_min_sync(FULL, blur_f2key(fminf(v[c][0], v[c][1])))) - 1e-5f;
+                            hi[c] = blur_key2f(__reduce_max_sync(FULL, blur_f2key(fmaxf(v[c][0], v[c][1])))) + 1e-5f;
+                        }
+                    }
+                    float lbv = INFINITY, ubv = INFINITY;
+                    if (lane < n) {
+                        const float pv[3] = {s_pal[3 * lane], s_pal[3 * lane + 1], s_pal[3 * lane + 2]};
+                        lbv = 0.f; ubv = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float ex = fmaxf(0.f, fmaxf(lo[c] - pv[c], pv[c] - hi[c]));
+                            const float fx = fmaxf(fabsf(pv[c] - lo[c]), fabsf(pv[c] - hi[c]));
+                            lbv = fmaf(ex, ex, lbv);
+                            ubv = fmaf(fx, fx, ubv);
+                        }
+                        lbv *= (1.0f - 4e-6f);
+                        ubv *= (1.0f + 4e-6f);
+                    }
+                    const float U = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(ubv)));                      // >= 0: bits order like values
+                    const float Umax = __uint_as_float(__reduce_max_sync(FULL, lane < n ? __float_as_uint(ubv) : 0u));
+                    const float slack = threshold_sq + 2.0f * es * (BLUR_TIE_SLOPE * sqrtf(Umax) + BLUR_TIE_CONST);
+                    todo = __ballot_sync(FULL, lane < n && lbv <= U + slack);
+                } else {
+                    todo = 0u;
                 }
-                // |c|^2 back in; what the fast arithmetic can be off by: the conversion (3e-6 per coordinate,
-                // 2 sqrt(d) of it in a distance) and the rounding of the expansion
+                if (n <= 32u) {
+#pragma unroll 1
+                    while (todo) {
+                        const uint32_t t = __ffs(todo) - 1u;
+                        todo &= todo - 1u;
+                        const float4 q = s_q[t];
+                        const f2 d = fma2(splat(q.x), L, fma2(splat(q.y), A, fma2(splat(q.z), B, splat(q.w))));   // d - |c|^2
+                        const bool bx_ = d.x < best.x, by_ = d.y < best.y;
+                        second.x = bx_ ? best.x : fminf(second.x, d.x);
+                        second.y = by_ ? best.y : fminf(second.y, d.y);
+                        best.x = bx_ ? d.x : best.x;
+                        best.y = by_ ? d.y : best.y;
+                        ix = bx_ ? t : ix;
+                        iy = by_ ? t : iy;
+                    }
+                } else {
+#pragma unroll 2
+                    for (uint32_t t = 0; t < n; ++t) {
+                        const float4 q = s_q[t];
+                        const f2 d = fma2(splat(q.x), L, fma2(splat(q.y), A, fma2(splat(q.z), B, splat(q.w))));   // d - |c|^2
+                        const bool bx_ = d.x < best.x, by_ = d.y < best.y;
+                        second.x = bx_ ? best.x : fminf(second.x, d.x);
+                        second.y = by_ ? best.y : fminf(second.y, d.y);
+                        best.x = bx_ ? d.x : best.x;
+                        best.y = by_ ? d.y : best.y;
+                        ix = bx_ ? t : ix;
+                        iy = by_ ? t : iy;
+                    }
+                }
+                // |c|^2 back in; what the fast arithmetic can be off by: the conversion -- MEASURED over all 2^24 colours,
+                // 5.87e-7 as a vector (tools/measure_fast_oklab.py; bound 8e-7, scaled with lum like L itself), 2 sqrt(d)
+                // of it in each of the two distances compared -- and the rounding of the expansion |p|^2 - 2 p.c
+                // (three roundings of terms up to ~2 per distance). Round 1 assumed 3e-6 per coordinate: seven times the
+                // margin, and every doubtful cell costs its warp a serial scan of the whole palette by one lane.
                 const f2 cc = fma2(L, L, fma2(A, A, mul2(B, B)));
                 const f2 d2 = add2(second, cc), gap = make_float2(second.x - best.x, second.y - best.y);
-                const float mx = 2.24e-5f * sqrtf(fmaxf(d2.x, 0.f)) + 3e-6f, my = 2.24e-5f * sqrtf(fmaxf(d2.y, 0.f)) + 3e-6f;
+                const float mx = es * (BLUR_TIE_SLOPE * sqrtf(fmaxf(d2.x, 0.f)) + BLUR_TIE_CONST), my = es * (BLUR_TIE_SLOPE * sqrtf(fmaxf(d2.y, 0.f)) + BLUR_TIE_CONST);
                 riskx = !(gap.x > mx) || !(d2.x > threshold_sq + mx);
                 risky = !(gap.y > my) || !(d2.y > threshold_sq + my);
             }
