@@ -202,16 +202,17 @@ __device__ __forceinline__ void wt_track(float (&m)[D], float v) {   // keep the
 // Weight of the tagged score's colour into one entry's sums (sign = -1: taken out again). The weight is taken
 // from the tagged score itself: the tag is at most 16 ulp of the score.
 template <int KIND>
-__device__ __forceinline__ void wt_add_one(const float4* __restrict__ unc, float tagged, float sign, float c1, float c0, float& n0, float& n1,
+__device__ __forceinline__ void wt_add_one(const float4* __restrict__ unc, float tagged, float sign, float c1, float c0, uint32_t tm, float& n0, float& n1,
                                            float& n2, float& den) {
-    const float4 q = unc[__float_as_uint(tagged) & 15u];
+    const float4 q = unc[__float_as_uint(tagged) & tm];
     const float w = sign * wt_weight2<KIND>(splat(sign * tagged), c1, c0).x;
     n0 = fmaf(q.x, w, n0); n1 = fmaf(q.y, w, n1); n2 = fmaf(q.z, w, n2); den += w;
 }
 
 // mU <= 16, c = C <= WT_TRACK - 1; top: C counts the colours left out (see above).
 template <int KIND, int C>
-__device__ __forceinline__ PairAcc wt_select_c(const float4* __restrict__ unc, int mU, bool top, f2 L, f2 A, f2 B, float c1, float c0, float tol) {
+__device__ __forceinline__ PairAcc wt_select_c(const float4* __restrict__ unc, int mU, bool top, f2 L, f2 A, f2 B, float c1, float c0, float tol, uint32_t tm,
+                                               float tagtol) {
     PairAcc r;
     r.n0 = r.n1 = r.n2 = r.den = splat(0.f);
     float mx[C + 1], my[C + 1];
@@ -221,19 +222,19 @@ __device__ __forceinline__ PairAcc wt_select_c(const float4* __restrict__ unc, i
 #pragma unroll 1
     for (int i = 0; i < mU; ++i) {
         const f2 sg = mul2(wt_score2<KIND>(unc[i], L, A, B), splat(sgn));
-        wt_track<C + 1>(mx, __uint_as_float((__float_as_uint(sg.x) & ~15u) | (uint32_t)i));
-        wt_track<C + 1>(my, __uint_as_float((__float_as_uint(sg.y) & ~15u) | (uint32_t)i));
+        wt_track<C + 1>(mx, __uint_as_float((__float_as_uint(sg.x) & ~tm) | (uint32_t)i));
+        wt_track<C + 1>(my, __uint_as_float((__float_as_uint(sg.y) & ~tm) | (uint32_t)i));
     }
     // the boundary lies between the C-th and the (C+1)-th tracked score; the tags cost up to 16 ulp of each
-    r.risky = (((mx[C] - mx[C - 1] <= fmaf(fabsf(mx[C]), 4e-6f, tol)) && (mx[C] < INFINITY)) ? 1u : 0u) |
-              (((my[C] - my[C - 1] <= fmaf(fabsf(my[C]), 4e-6f, tol)) && (my[C] < INFINITY)) ? 2u : 0u);
+    r.risky = (((mx[C] - mx[C - 1] <= fmaf(fabsf(mx[C]), tagtol, tol)) && (mx[C] < INFINITY)) ? 1u : 0u) |
+              (((my[C] - my[C - 1] <= fmaf(fabsf(my[C]), tagtol, tol)) && (my[C] < INFINITY)) ? 2u : 0u);
     r.tau = top ? make_float2(-mx[C], -my[C]) : make_float2(mx[C - 1], my[C - 1]);
     r.nxt = top ? make_float2(-mx[C - 1], -my[C - 1]) : make_float2(mx[C], my[C]);
     static_assert(C <= 2, "deeper choices: wt_select_deep");
 #pragma unroll
     for (int t = 0; t < C; ++t) {
-        wt_add_one<KIND>(unc, mx[t], sgn, c1, c0, r.n0.x, r.n1.x, r.n2.x, r.den.x);
-        wt_add_one<KIND>(unc, my[t], sgn, c1, c0, r.n0.y, r.n1.y, r.n2.y, r.den.y);
+        wt_add_one<KIND>(unc, mx[t], sgn, c1, c0, tm, r.n0.x, r.n1.x, r.n2.x, r.den.x);
+        wt_add_one<KIND>(unc, my[t], sgn, c1, c0, tm, r.n0.y, r.n1.y, r.n2.y, r.den.y);
     }
     return r;
 }
@@ -243,7 +244,8 @@ __device__ __forceinline__ PairAcc wt_select_c(const float4* __restrict__ unc, i
 // daily): the D smallest are tracked whatever c is, the boundary pair is picked by uniform selects, and a second rolled
 // pass adds (or takes out again) every colour whose tagged score is at most the c-th.
 template <int KIND, int D>
-__device__ __noinline__ PairAcc wt_select_deep(const float4* __restrict__ unc, int mU, int c, bool top, f2 L, f2 A, f2 B, float c1, float c0, float tol) {
+__device__ __noinline__ PairAcc wt_select_deep(const float4* __restrict__ unc, int mU, int c, bool top, f2 L, f2 A, f2 B, float c1, float c0, float tol,
+                                               uint32_t tm, float tagtol) {
     PairAcc r;
     r.n0 = r.n1 = r.n2 = r.den = splat(0.f);
     float mx[D], my[D];
@@ -253,15 +255,15 @@ __device__ __noinline__ PairAcc wt_select_deep(const float4* __restrict__ unc, i
 #pragma unroll 1
     for (int i = 0; i < mU; ++i) {
         const f2 sg = mul2(wt_score2<KIND>(unc[i], L, A, B), splat(sgn));
-        wt_track<D>(mx, __uint_as_float((__float_as_uint(sg.x) & ~15u) | (uint32_t)i));
-        wt_track<D>(my, __uint_as_float((__float_as_uint(sg.y) & ~15u) | (uint32_t)i));
+        wt_track<D>(mx, __uint_as_float((__float_as_uint(sg.x) & ~tm) | (uint32_t)i));
+        wt_track<D>(my, __uint_as_float((__float_as_uint(sg.y) & ~tm) | (uint32_t)i));
     }
     float lox = mx[2], hix = mx[3], loy = my[2], hiy = my[3];   // c = 3
 #pragma unroll
     for (int t = 4; t < D; ++t)
         if (c >= t) { lox = mx[t - 1]; hix = mx[t]; loy = my[t - 1]; hiy = my[t]; }   // uniform
-    r.risky = (((hix - lox <= fmaf(fabsf(hix), 4e-6f, tol)) && (hix < INFINITY)) ? 1u : 0u) |
-              (((hiy - loy <= fmaf(fabsf(hiy), 4e-6f, tol)) && (hiy < INFINITY)) ? 2u : 0u);
+    r.risky = (((hix - lox <= fmaf(fabsf(hix), tagtol, tol)) && (hix < INFINITY)) ? 1u : 0u) |
+              (((hiy - loy <= fmaf(fabsf(hiy), tagtol, tol)) && (hiy < INFINITY)) ? 2u : 0u);
     r.tau = top ? make_float2(-hix, -hiy) : make_float2(lox, loy);
     r.nxt = top ? make_float2(-lox, -loy) : make_float2(hix, hiy);
 #pragma unroll 1
@@ -270,8 +272,8 @@ __device__ __noinline__ PairAcc wt_select_deep(const float4* __restrict__ unc, i
         const f2 sc = wt_score2<KIND>(q, L, A, B);
         const f2 sg = mul2(sc, splat(sgn));
         f2 w = mul2(wt_weight2<KIND>(sc, c1, c0), splat(sgn));
-        w.x = __uint_as_float((__float_as_uint(sg.x) & ~15u) | (uint32_t)i) <= lox ? w.x : 0.f;
-        w.y = __uint_as_float((__float_as_uint(sg.y) & ~15u) | (uint32_t)i) <= loy ? w.y : 0.f;
+        w.x = __uint_as_float((__float_as_uint(sg.x) & ~tm) | (uint32_t)i) <= lox ? w.x : 0.f;
+        w.y = __uint_as_float((__float_as_uint(sg.y) & ~tm) | (uint32_t)i) <= loy ? w.y : 0.f;
         r.n0 = fma2(splat(q.x), w, r.n0);
         r.n1 = fma2(splat(q.y), w, r.n1);
         r.n2 = fma2(splat(q.z), w, r.n2);
@@ -282,11 +284,11 @@ __device__ __noinline__ PairAcc wt_select_deep(const float4* __restrict__ unc, i
 
 template <int KIND>
 __device__ __forceinline__ PairAcc wt_select_small(const float4* __restrict__ unc, int mU, int c, bool top, f2 L, f2 A, f2 B, float c1, float c0,
-                                                   float tol) {
-    if (c == 1) return wt_select_c<KIND, 1>(unc, mU, top, L, A, B, c1, c0, tol);
-    if (c == 2) return wt_select_c<KIND, 2>(unc, mU, top, L, A, B, c1, c0, tol);
-    if (c < WT_TRACK) return wt_select_deep<KIND, WT_TRACK>(unc, mU, c, top, L, A, B, c1, c0, tol);
-    return wt_select_deep<KIND, WT_TRACK_WIDE>(unc, mU, c, top, L, A, B, c1, c0, tol);
+                                                   float tol, uint32_t tm, float tagtol) {
+    if (c == 1) return wt_select_c<KIND, 1>(unc, mU, top, L, A, B, c1, c0, tol, tm, tagtol);
+    if (c == 2) return wt_select_c<KIND, 2>(unc, mU, top, L, A, B, c1, c0, tol, tm, tagtol);
+    if (c < WT_TRACK) return wt_select_deep<KIND, WT_TRACK>(unc, mU, c, top, L, A, B, c1, c0, tol, tm, tagtol);
+    return wt_select_deep<KIND, WT_TRACK_WIDE>(unc, mU, c, top, L, A, B, c1, c0, tol, tm, tagtol);
 }
 
 // Anything else (more than 16 uncertain colours, or neither side of the choice is small): per entry, one pass
@@ -1031,7 +1033,7 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
     const bool choose = !cl.take_all && kp > 0 && (int)cl.nunc_all > kp && (int)nunc > kp;
     // choosing from above (wt_select_c): every uncertain colour is added by the direct loop, the few left out are taken out again
     const int left_out = (int)nunc - kp;
-    const bool top = choose && KIND != 2 && KIND != KIND_NN && left_out < kp && left_out < WT_TRACK_WIDE && nunc <= 16u;
+    const bool top = choose && KIND != 2 && KIND != KIND_NN && left_out < kp && left_out < WT_TRACK_WIDE && nunc <= 32u;
     const uint32_t direct = (cl.take_all || kp <= 0 || (choose && !top)) ? nin : nin + nunc;
     // per-tile conditions that send every entry to the exact kernel: more exact-hit candidates than
     // the list holds; weights so far from 1 that the reference's f64 sums leave their range; more
@@ -1128,7 +1130,12 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
     const float4* unc = cand + nin;
     const int mU = (int)nunc;
     const int csel = top ? left_out : kp;
-    const bool small = csel < WT_TRACK_WIDE && mU <= 16;
+    // the tracked scores carry their list position in the low mantissa bits: four bits (16 ulp of the score) up to 16 uncertain
+    // colours, five (32 ulp) up to 32 -- the 33..256-colour kernel meets 17..32 in a sixth of its tiles, and the insertion path
+    // they used to take was 9 % of its instructions (profiles/r2_shepard256_k_remap_warp_big_ncu.txt)
+    const bool small = csel < WT_TRACK_WIDE && mU <= 32;
+    const uint32_t tm = mU > 16 ? 31u : 15u;
+    const float tagtol = mU > 16 ? 8e-6f : 4e-6f;
     uint32_t res[EPT], smask = 0;
 #pragma unroll
     for (int e = 0; e < EPT; ++e) res[e] = 0;
@@ -1153,7 +1160,7 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
         }
         uint32_t risky = 0;   // bit h: entry h of the pair needs the reference's arithmetic throughout
         if (choose) {
-            PairAcc pa = small ? wt_select_small<KIND>(unc, mU, csel, top, L, A, B, c1, c0, tol) : wt_select_insert<KIND>(unc, mU, kp, L, A, B, c1, c0, tol);
+            PairAcc pa = small ? wt_select_small<KIND>(unc, mU, csel, top, L, A, B, c1, c0, tol, tm, tagtol) : wt_select_insert<KIND>(unc, mU, kp, L, A, B, c1, c0, tol);
             if (pa.risky & 3u) {
                 // near-ties: the reference's own distances decide the order inside the doubtful band (this lane alone; rare)
 #pragma unroll
@@ -1166,7 +1173,7 @@ __device__ __forceinline__ void wt_entries(const WarpArgs& a, const SmemTables& 
                     const float nx = h ? pa.nxt.y : pa.nxt.x;
                     float4 o;
                     if (wt_resolve_tie<KIND>(a.pal64, a.lum64, st.decode, unc, cidx + nin, mU, kp, top, rgb, h ? L.y : L.x, h ? A.y : A.x, h ? B.y : B.x, c1, c0,
-                                             h ? pa.tau.y : pa.tau.x, nx, fmaf(fabsf(nx), 4e-6f, tol), o)) {
+                                             h ? pa.tau.y : pa.tau.x, nx, fmaf(fabsf(nx), tagtol, tol), o)) {
                         if (h) { pa.n0.y = o.x; pa.n1.y = o.y; pa.n2.y = o.z; pa.den.y = o.w; }
                         else { pa.n0.x = o.x; pa.n1.x = o.y; pa.n2.x = o.z; pa.den.x = o.w; }
                         if (a.stats) atomicAdd(&a.stats[126], 1u);
