@@ -53,3 +53,21 @@ def test_no_cpu_fallback_without_gpu():
     with pytest.raises(_native.LutgenError):
         from lutgen_rs_b200 import identity
         identity.generate(2)
+
+
+def test_documented_environment_switches_exist_in_the_sources():
+    """DESIGN.md's appendix lists the environment switches; each must be read somewhere in the sources it names
+    (a guard against the table drifting from the code)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "DESIGN.md")).read()
+    appendix = text[text.index("## Appendix: environment switches"):]
+    names = set(re.findall(r"`(LUTGEN_[A-Z_]+)", appendix))
+    assert len(names) >= 15
+    blob = ""
+    for d in ("lutgen_rs_b200", os.path.join("lutgen_rs_b200", "csrc")):
+        for f in os.listdir(os.path.join(root, d)):
+            if f.endswith((".cu", ".cuh", ".h", ".py")):
+                blob += open(os.path.join(root, d, f), errors="ignore").read()
+    missing = [n for n in names if f'"{n}"' not in blob]
+    assert not missing, missing
